@@ -1,0 +1,101 @@
+/* sidekit_b200 -- C ABI of the B200-native speaker-verification inference hot path.
+ *
+ * The reference (deep-privacy/sidekit) is pure Python over PyTorch/numpy and has no FFI: its
+ * boundary for this path is the Python API.  Each entry point below names the
+ * reference interface it replaces; sidekit_b200/*.py binds them with ctypes and re-creates the
+ * reference's Python signatures on top (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions: plain pointers and sizes only; `*_dev` pointers are CUDA device pointers on the
+ * current device, everything else is host memory; `stream` is a cudaStream_t passed as void*
+ * (NULL = default stream); every function returns SKB_OK (0) or a negative error code and
+ * skb_last_error() then describes the failure.  Calls on one handle must not overlap.
+ */
+#ifndef SIDEKIT_B200_H
+#define SIDEKIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKB_OK 0
+#define SKB_ERR_ARG (-1)
+#define SKB_ERR_CUDA (-2)
+#define SKB_ERR_WEIGHTS (-3)
+#define SKB_ERR_STATE (-4)
+
+#define SKB_ARCHI_HALFRESNET34 0 /* Xtractor(model_archi="halfresnet34"), sidekit/nnet/xvector.py:569-599 */
+#define SKB_ARCHI_XVECTOR 1      /* Xtractor(model_archi="xvector") TDNN,  sidekit/nnet/xvector.py:453-498 */
+
+typedef struct skb_xtractor skb_xtractor_t;
+
+int skb_version(void);
+const char* skb_last_error(void);
+/* Number of CUDA kernels launched by this library since process start (bench.py reports deltas). */
+int64_t skb_kernel_launches(void);
+
+/* ---- extraction: replaces sidekit.nnet.xvector.Xtractor.__init__ / load_state_dict / forward -----------
+ * Weights are handed over as named fp32 host tensors using the reference's state_dict keys
+ * (SURVEY.md Appendix A.6), e.g. "sequence_network.layer1.0.conv1.weight"; BatchNorm folding,
+ * 16-bit conversion and UMMA packing happen inside.  compute_dtype: 0 = fp16 operands (default,
+ * meets 1e-3 relative L2), 1 = bf16 operands; accumulation is always fp32. */
+int skb_xtractor_create(int archi, int n_tensors, const char* const* names, const float* const* data,
+                        const int64_t* const* shapes, const int* ndims, int compute_dtype, float margin_s,
+                        skb_xtractor_t** out);
+void skb_xtractor_destroy(skb_xtractor_t* h);
+int skb_xtractor_embedding_size(const skb_xtractor_t* h);
+int skb_xtractor_speaker_number(const skb_xtractor_t* h);
+
+/* Xtractor.forward(x, is_eval=True) (sidekit/nnet/xvector.py:876-907) on a packed batch:
+ * wave_dev = the n_utt utterances back to back (fp32, 16 kHz), lengths[i] samples each (host array).
+ * emb_dev (n_utt, E) receives F.normalize(x); logits_dev (n_utt, n_spk) the margin-head output
+ * s*cos(x, W) (may be NULL).  Utterances of different lengths are handled exactly (no padding
+ * artefacts): every reduction is per utterance. */
+int skb_xtractor_forward(skb_xtractor_t* h, const float* wave_dev, const int64_t* lengths, int n_utt,
+                         int norm_embedding, float* emb_dev, float* logits_dev, void* stream);
+/* The embedding BEFORE the final F.normalize of the most recent forward call (what the reference
+ * returns for loss='cce' with is_eval=True, xvector.py:896-898): out_dev (n_utt, E). */
+int skb_xtractor_pre_embedding(skb_xtractor_t* h, int n_utt, float* out_dev, void* stream);
+/* Same call with HOST buffers: H2D of the waveforms, forward, D2H of the results, synchronous. */
+int skb_xtractor_forward_host(skb_xtractor_t* h, const float* wave_host, const int64_t* lengths, int n_utt,
+                              int norm_embedding, float* emb_host, float* logits_host, void* stream);
+
+/* MelSpecFrontEnd.forward / MfccFrontEnd.forward (sidekit/nnet/preprocessor.py:267-285, :113-124):
+ * feats_dev is (n_utt, n_coef, t_max) fp32, zero beyond each utterance's frame count. */
+int skb_xtractor_frontend(skb_xtractor_t* h, const float* wave_dev, const int64_t* lengths, int n_utt, int t_max,
+                          float* feats_dev, void* stream);
+int skb_xtractor_num_frames(const skb_xtractor_t* h, int64_t n_samples);
+
+/* Test hook: run the forward pass up to `stage` ("stem", "layer1.0" ... "layer4.2", "pooled") and
+ * write that activation as dense fp32: trunk stages (n_utt, C, h_max, W) zero padded along h;
+ * "pooled" (n_utt, 2*C*W).  Returns the number of floats written per utterance in *per_utt. */
+int skb_xtractor_debug_stage(skb_xtractor_t* h, const float* wave_dev, const int64_t* lengths, int n_utt,
+                             const char* stage, int h_max, float* out_dev, int64_t* per_utt, void* stream);
+
+/* ---- pooling ops: replace MeanStdPooling.forward (sidekit/nnet/pooling.py:55-70) ---------------------- */
+/* x_dev (n_utt, D, T) fp32 contiguous -> out_dev (n_utt, 2*D) = [mean ; unbiased std]. */
+int skb_meanstd_pool(const float* x_dev, int n_utt, int D, int T, float* out_dev, void* stream);
+
+/* ---- scoring: replaces the dense algebra of sidekit/iv_scoring.py:108-109, :451-462, :192-205 ---------
+ * S[i][j] = alpha * (rowterm[i] + colterm[j] + cst) + alpha * sum_k E[i][k] * T[j][k]
+ * E_dev (Ne, D), T_dev (Nt, D) fp32 row-major; rowterm/colterm may be NULL (treated as 0).
+ * passes: 1 = single 16-bit pass, 3 = split (hi*hi + hi*lo + lo*hi) for fp32-class accuracy,
+ * 0 = choose from the operand magnitudes so that the absolute error stays below 2.5e-4.
+ * out_dtype: 0 = float32, 1 = float64.  out_dev is (Ne, Nt) row-major with leading dimension ld_out. */
+int skb_score_gemm(const float* E_dev, const float* T_dev, int Ne, int Nt, int D, const float* rowterm_dev,
+                   const float* colterm_dev, double cst, double alpha, int passes, int out_dtype, void* out_dev,
+                   int64_t ld_out, void* stream);
+
+/* as-norm statistics (sidekit/score_normalization.py:127-133): per row of X_dev (N, D), mean and
+ * unbiased std of the top_k largest scores against the (already normalised) cohort_dev (C, D). */
+int skb_asnorm_stats(const float* X_dev, const float* cohort_dev, int N, int C, int D, int top_k, float* mean_dev,
+                     float* std_dev, void* stream);
+/* out[i][j] = 0.5*(S[i][j]-mean[i])/std[i] + 0.5*(S[i][j]-mean[j])/std[j], S = X X^T  (:135-138). */
+int skb_asnorm_apply(const float* X_dev, int N, int D, const float* mean_dev, const float* std_dev, float* out_dev,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIDEKIT_B200_H */

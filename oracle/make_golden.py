@@ -1,0 +1,154 @@
+"""Regenerate tests/golden/*.npz from the REAL reference (build container only).
+
+    python -m oracle.make_golden
+
+TEST INFRASTRUCTURE ONLY.  The reference is imported by oracle/ref_import.py
+(stub modules + patches P1/P2); weights come from
+``sidekit_b200.synth.fill_state_dict`` (key-hash seeded, so they can be rebuilt
+on the GPU box without a checkpoint).  Only inputs that cannot be regenerated
+(the real-audio snippet) and the reference's OUTPUTS are stored.
+"""
+import copy
+import os
+import sys
+import wave as wavmod
+
+import numpy
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_import                      # noqa: E402
+from sidekit_b200 import synth                     # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _ref_model(archi, emb, n_spk=32, seed=0):
+    m = ref_import.build_xtractor(n_spk, archi, emb)
+    sd = m.state_dict()
+    synth.fill_state_dict(sd, seed)
+    m.load_state_dict(sd)
+    return m
+
+
+def golden_extraction():
+    torch.set_num_threads(8)
+    out = {}
+    # HalfResNet34: two equal-length utterances (batched) + two of other lengths (run one by one, like
+    # the reference's extractors do) -> exercises every T parity through the three stride-2 stages.
+    m = _ref_model("halfresnet34", 256)
+    lengths = [16000, 16000, 24160, 11111]
+    waves = [synth.synth_wave(1, L, seed=100 + i)[0] for i, L in enumerate(lengths)]
+    with torch.no_grad():
+        lo01, em01 = m(torch.stack(waves[:2]), is_eval=True)
+        res = [m(w, is_eval=True) for w in waves[2:]]
+        feats0 = m.preprocessor(waves[0], True)
+    out["hr_lengths"] = numpy.array(lengths)
+    out["hr_seeds"] = numpy.array([100, 101, 102, 103])
+    out["hr_emb"] = torch.cat([em01] + [r[1] for r in res]).numpy()
+    out["hr_logits"] = torch.cat([lo01] + [r[0] for r in res]).numpy()
+    out["hr_feats0"] = feats0[0].numpy()
+    # TDNN
+    m = _ref_model("xvector", 512)
+    lengths = [32000, 32000, 51234]
+    waves = [synth.synth_wave(1, L, seed=200 + i)[0] for i, L in enumerate(lengths)]
+    with torch.no_grad():
+        lo01, em01 = m(torch.stack(waves[:2]), is_eval=True)
+        lo2, em2 = m(waves[2].unsqueeze(0), is_eval=True)
+        feats0 = m.preprocessor(waves[0].unsqueeze(0), True)
+    out["td_lengths"] = numpy.array(lengths)
+    out["td_seeds"] = numpy.array([200, 201, 202])
+    out["td_emb"] = torch.cat([em01, em2]).numpy()
+    out["td_logits"] = torch.cat([lo01, lo2]).numpy()
+    out["td_feats0"] = feats0[0].numpy()
+    # real audio: first 1.5 s of one of the reference's example wavs through the log-Mel front-end
+    wdir = os.path.join(ref_import.REFERENCE_ROOT, "egs", "examples_decode")
+    wavs = sorted(f for f in os.listdir(wdir) if f.endswith(".wav"))
+    with wavmod.open(os.path.join(wdir, wavs[0]), "rb") as f:
+        assert f.getframerate() == 16000 and f.getnchannels() == 1 and f.getsampwidth() == 2
+        pcm = numpy.frombuffer(f.readframes(24000), dtype=numpy.int16).copy()
+    x = torch.from_numpy(pcm.astype(numpy.float32) / 32768.0)
+    m = _ref_model("halfresnet34", 256)
+    with torch.no_grad():
+        feats = m.preprocessor(x, True)
+        lo, em = m(x, is_eval=True)
+    out["real_pcm16"] = pcm
+    out["real_feats"] = feats[0].numpy()
+    out["real_emb"] = em.numpy()
+    numpy.savez_compressed(os.path.join(GOLD, "extraction.npz"), **out)
+    print("extraction.npz", {k: v.shape for k, v in out.items()})
+
+
+def _statserver(sidekit, ids, X):
+    s = sidekit.StatServer()
+    s.modelset = numpy.array(ids)
+    s.segset = numpy.array(ids)
+    s.start = numpy.empty(len(ids), dtype="|O")
+    s.stop = numpy.empty(len(ids), dtype="|O")
+    s.stat0 = numpy.ones((len(ids), 1))
+    s.stat1 = numpy.array(X, dtype=numpy.float64)
+    return s
+
+
+def golden_scoring():
+    sidekit = ref_import.import_reference()
+    from sidekit.iv_scoring import cosine_scoring, PLDA_scoring, fast_PLDA_scoring, two_covariance_scoring
+    from sidekit.score_normalization import asnorm
+    rng = numpy.random.default_rng(4321)
+    D, R = 16, 10
+    Ne, Nt = 37, 29
+    en_ids = ["m%02d" % i for i in range(Ne)]
+    te_ids = ["s%02d" % i for i in range(Nt)]
+    te_ids[7] = te_ids[3]                                   # duplicate test id -> first match wins
+    E = rng.standard_normal((Ne, D))
+    T = rng.standard_normal((Nt, D))
+    mu = 0.1 * rng.standard_normal(D)
+    F = 0.5 * rng.standard_normal((D, R))
+    A = 0.3 * rng.standard_normal((D, D))
+    Sigma = A @ A.T + numpy.eye(D)
+    B = F @ F.T + 0.1 * numpy.eye(D)
+    ndx = sidekit.Ndx()
+    perm_m = rng.permutation(Ne)[:30]
+    perm_s = rng.permutation(Nt)[:25]
+    ndx.modelset = numpy.array([en_ids[i] for i in perm_m] + ["missing_model", en_ids[perm_m[0]]])
+    ndx.segset = numpy.array([te_ids[i] for i in perm_s] + ["missing_seg"])
+    ndx.trialmask = rng.random((ndx.modelset.shape[0], ndx.segset.shape[0])) < 0.6
+    out = dict(en_ids=numpy.array(en_ids), te_ids=numpy.array(te_ids), E=E, T=T, mu=mu, F=F, Sigma=Sigma, B=B,
+               ndx_models=ndx.modelset, ndx_segs=ndx.segset, trialmask=ndx.trialmask)
+
+    def pack(name, sc):
+        out[name + "_modelset"] = numpy.array(sc.modelset)
+        out[name + "_segset"] = numpy.array(sc.segset)
+        out[name + "_mask"] = numpy.array(sc.scoremask)
+        out[name + "_mat"] = numpy.array(sc.scoremat)
+
+    mk = lambda: (_statserver(sidekit, en_ids, E), _statserver(sidekit, te_ids, T), copy.deepcopy(ndx))
+    pack("cosine", cosine_scoring(*mk(), device=torch.device("cpu")))
+    pack("plda", PLDA_scoring(*mk(), mu, F, numpy.zeros((D, 0)), Sigma))
+    pack("plda_sf", PLDA_scoring(*mk(), mu, F, numpy.zeros((D, 0)), Sigma, scaling_factor=0.7))
+    pack("plda_open", fast_PLDA_scoring(*mk(), mu, F, Sigma, p_known=0.3))
+    pack("twocov", two_covariance_scoring(*mk(), Sigma, B))
+    # duplicate enrol models -> averaged per sorted-unique model (fast-PLDA path)
+    en_dup = list(en_ids)
+    en_dup[5] = en_dup[2]
+    en_dup[11] = en_dup[2]
+    out["en_ids_dup"] = numpy.array(en_dup)
+    pack("plda_dup", fast_PLDA_scoring(_statserver(sidekit, en_dup, E), _statserver(sidekit, te_ids, T),
+                                       copy.deepcopy(ndx), mu, F, Sigma))
+    # as-norm
+    N, C, Dx = 40, 260, 32
+    X = rng.standard_normal((N, Dx)).astype(numpy.float32)
+    X /= numpy.linalg.norm(X, axis=1, keepdims=True)
+    coh = rng.standard_normal((C, Dx)).astype(numpy.float32)
+    out["asnorm_X"] = X
+    out["asnorm_cohort"] = coh
+    out["asnorm_out"] = asnorm(torch.from_numpy(X), torch.from_numpy(coh), None)
+    numpy.savez_compressed(os.path.join(GOLD, "scoring.npz"), **out)
+    print("scoring.npz", sorted(out.keys()))
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    golden_scoring()
+    golden_extraction()

@@ -1,0 +1,12 @@
+"""sidekit_b200 -- B200-native drop-in for SIDEKIT's speaker-verification inference hot path.
+
+Public surface mirrors the reference package for that path only:
+``Xtractor``, the front-end / pooling modules, ``StatServer`` / ``Ndx`` / ``Scores`` containers and
+``cosine_scoring`` / ``PLDA_scoring`` / ``fast_PLDA_scoring`` / ``two_covariance_scoring`` / ``asnorm``.
+All arithmetic runs in hand-written CUDA kernels for sm_100a behind ``libsidekit_b200.so``
+(include/sidekit_b200.h); there is no CPU fallback.
+"""
+from . import _lib
+from .nnet import Xtractor, MeanStdPooling, AttentivePooling, PreHalfResNet34, MfccFrontEnd, MelSpecFrontEnd
+
+__version__ = "0.1.0"

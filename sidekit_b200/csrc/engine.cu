@@ -1,0 +1,909 @@
+// Extraction engine: owns the packed weights, the per-batch geometry plan and the activation
+// workspace, and sequences the kernels of one Xtractor.forward(x, is_eval=True) call
+// (sidekit/nnet/xvector.py:876-907) for the "halfresnet34" and "xvector" (TDNN) architectures.
+#include "sidekit_b200.h"
+#include "conv_umma.cuh"
+#include "layers.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace skb {
+
+// ----------------------------------------------------------------------------- errors / counters
+static thread_local char g_err[512] = "";
+void set_last_error(const char* file, int line, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s:%d: %s", file, line, msg);
+}
+std::atomic<long long> g_launches{0};
+
+
+// ----------------------------------------------------------------------------- small host utilities
+struct HostTensor {
+    const float* p = nullptr;
+    std::vector<int64_t> shape;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto d : shape) n *= d;
+        return n;
+    }
+};
+typedef std::map<std::string, HostTensor> WeightMap;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes, bool* grew = nullptr) {
+        if (bytes <= cap) return SKB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            set_last_error(__FILE__, __LINE__, cudaGetErrorString(e));
+            return SKB_ERR_CUDA;
+        }
+        cap = want;
+        if (grew) *grew = true;
+        return SKB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <typename T>
+static int dev_upload(const std::vector<T>& v, T** out) {
+    *out = nullptr;
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    SKB_CUDA_CHECK(cudaMalloc(out, bytes));
+    if (!v.empty()) SKB_CUDA_CHECK(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SKB_OK;
+}
+
+static uint16_t to16(float v, bool bf16) {
+    if (bf16) {
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        uint16_t u;
+        memcpy(&u, &h, 2);
+        return u;
+    }
+    __half h = __float2half_rn(v);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+}
+
+static const HostTensor* find(const WeightMap& w, const std::string& k) {
+    auto it = w.find(k);
+    if (it == w.end()) {
+        set_last_error(__FILE__, __LINE__, ("missing weight tensor: " + k).c_str());
+        return nullptr;
+    }
+    return &it->second;
+}
+
+// BatchNorm (eval) as y = s*x + t  (eps 1e-5, torch default)
+static int bn_affine(const WeightMap& w, const std::string& prefix, std::vector<double>* s, std::vector<double>* t) {
+    const HostTensor *g = find(w, prefix + ".weight"), *b = find(w, prefix + ".bias"),
+                     *m = find(w, prefix + ".running_mean"), *v = find(w, prefix + ".running_var");
+    if (!g || !b || !m || !v) return SKB_ERR_WEIGHTS;
+    const int64_t n = g->numel();
+    s->resize(n);
+    t->resize(n);
+    for (int64_t i = 0; i < n; ++i) {
+        const double sc = (double)g->p[i] / std::sqrt((double)v->p[i] + 1e-5);
+        (*s)[i] = sc;
+        (*t)[i] = (double)b->p[i] - (double)m->p[i] * sc;
+    }
+    return SKB_OK;
+}
+
+// ----------------------------------------------------------------------------- packed conv weights
+struct ConvW {
+    uint16_t* w = nullptr;   // device, UMMA images
+    float* bias = nullptr;   // device [cout]
+    int cin = 0, cout = 0, taps = 0, ncta = 0;
+};
+
+// wf: folded weights [cout][cin_src][taps] (double), channels >= cin_src zero padded up to cin_pad.
+static int pack_conv(const std::vector<double>& wf, const std::vector<double>& bias, int cout, int cin_src, int cin_pad,
+                     int taps, bool bf16, ConvW* out) {
+    const int ncta = conv_pick_ncta(cout);
+    const int n_split = cout / ncta, n_kc = cin_pad / kConvKC;
+    std::vector<uint16_t> img((size_t)n_split * n_kc * taps * 4 * ncta * 8);
+    size_t o = 0;
+    for (int ns = 0; ns < n_split; ++ns)
+        for (int kc = 0; kc < n_kc; ++kc)
+            for (int tap = 0; tap < taps; ++tap)
+                for (int j = 0; j < 4; ++j)
+                    for (int n = 0; n < ncta; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            const int co = ns * ncta + n, ci = kc * kConvKC + j * 8 + e;
+                            const double v = ci < cin_src ? wf[((size_t)co * cin_src + ci) * taps + tap] : 0.0;
+                            img[o++] = to16((float)v, bf16);
+                        }
+    std::vector<float> bf(bias.begin(), bias.end());
+    out->cin = cin_pad; out->cout = cout; out->taps = taps; out->ncta = ncta;
+    int rc = dev_upload(img, &out->w);
+    if (rc) return rc;
+    return dev_upload(bf, &out->bias);
+}
+
+// Conv2d (no bias) followed by BatchNorm2d: w' = w*s[co], b' = t[co]
+static int pack_conv_bn(const WeightMap& w, const std::string& conv_key, const std::string& bn_prefix, bool bf16, ConvW* out) {
+    const HostTensor* cw = find(w, conv_key);
+    if (!cw || cw->shape.size() != 4) return SKB_ERR_WEIGHTS;
+    const int cout = (int)cw->shape[0], cin = (int)cw->shape[1], taps = (int)(cw->shape[2] * cw->shape[3]);
+    std::vector<double> s, t;
+    int rc = bn_affine(w, bn_prefix, &s, &t);
+    if (rc) return rc;
+    std::vector<double> wf((size_t)cout * cin * taps);
+    for (int co = 0; co < cout; ++co)
+        for (size_t i = 0; i < (size_t)cin * taps; ++i) wf[(size_t)co * cin * taps + i] = (double)cw->p[(size_t)co * cin * taps + i] * s[co];
+    return pack_conv(wf, t, cout, cin, cin, taps, bf16, out);
+}
+
+static void free_conv(ConvW* c) {
+    cudaFree(c->w);
+    cudaFree(c->bias);
+    *c = ConvW();
+}
+
+// ----------------------------------------------------------------------------- models
+struct BlockW {
+    ConvW conv1, conv2, sc;
+    bool has_sc = false;
+    int stride = 1, C = 0;
+    float *se_w1 = nullptr, *se_w2 = nullptr;
+};
+
+struct Model {
+    int archi = 0;
+    bool bf16 = false;
+    int emb = 0, n_spk = 0;
+    float margin_s = 30.f;
+    FrontendConsts fe;
+    // halfresnet34
+    float *stem_w = nullptr, *stem_b = nullptr;
+    std::vector<BlockW> blocks;
+    float *att_w1x = nullptr, *att_w1g = nullptr, *att_b1 = nullptr, *att_bn_s = nullptr, *att_bn_t = nullptr;
+    float *att_w2 = nullptr, *att_b2 = nullptr;
+    int att_A = 0, pool_D = 0;
+    // head
+    float *lin_w = nullptr, *lin_b = nullptr, *be_s = nullptr, *be_t = nullptr, *spk_wn = nullptr;
+    // tdnn
+    std::vector<ConvW> tdnn;
+    std::vector<int> tdnn_k, tdnn_d;
+    float *pool_s = nullptr, *pool_t = nullptr;
+};
+
+static int upload_f(const std::vector<double>& v, float** out) {
+    std::vector<float> f(v.begin(), v.end());
+    return dev_upload(f, out);
+}
+static int upload_raw(const HostTensor* t, float** out) {
+    std::vector<float> f(t->p, t->p + t->numel());
+    return dev_upload(f, out);
+}
+
+static int build_frontend(const WeightMap& w, Model* m) {
+    if (m->archi == SKB_ARCHI_HALFRESNET34) {
+        const HostTensor *win = find(w, "preprocessor.MelSpec.spectrogram.window"), *fb = find(w, "preprocessor.MelSpec.mel_scale.fb");
+        if (!win || !fb) return SKB_ERR_WEIGHTS;
+        if (win->numel() != 400 || fb->shape.size() != 2 || fb->shape[0] != 513) {
+            set_last_error(__FILE__, __LINE__, "unexpected log-Mel front-end buffers (want window 400, fb 513 x n_mels)");
+            return SKB_ERR_WEIGHTS;
+        }
+        return frontend_consts_create(&m->fe, 1024, 400, 160, (int)fb->shape[1], (int)fb->shape[1], win->p, fb->p, nullptr);
+    }
+    const HostTensor *win = find(w, "preprocessor.MFCC.MelSpectrogram.spectrogram.window"),
+                     *fb = find(w, "preprocessor.MFCC.MelSpectrogram.mel_scale.fb"), *dct = find(w, "preprocessor.MFCC.dct_mat");
+    if (!win || !fb || !dct) return SKB_ERR_WEIGHTS;
+    if (win->numel() != 1024 || fb->shape.size() != 2 || fb->shape[0] != 1025 || dct->shape.size() != 2 || dct->shape[0] != fb->shape[1]) {
+        set_last_error(__FILE__, __LINE__, "unexpected MFCC front-end buffers");
+        return SKB_ERR_WEIGHTS;
+    }
+    return frontend_consts_create(&m->fe, 2048, 1024, 512, (int)fb->shape[1], (int)dct->shape[1], win->p, fb->p, dct->p);
+}
+
+static int build_margin_head(const WeightMap& w, Model* m) {
+    if (!w.count("after_speaker_embedding.weight")) {   // loss='cce': no margin head at inference time
+        m->n_spk = 0;
+        return SKB_OK;
+    }
+    const HostTensor* sw = find(w, "after_speaker_embedding.weight");
+    if (!sw || sw->shape.size() != 2 || sw->shape[1] != m->emb) return SKB_ERR_WEIGHTS;
+    m->n_spk = (int)sw->shape[0];
+    std::vector<float> wn((size_t)m->n_spk * m->emb);
+    for (int i = 0; i < m->n_spk; ++i) {   // F.normalize(weight): row / max(norm, 1e-12), loss.py:307
+        double ss = 0;
+        for (int k = 0; k < m->emb; ++k) ss += (double)sw->p[(size_t)i * m->emb + k] * sw->p[(size_t)i * m->emb + k];
+        const double inv = 1.0 / std::max(std::sqrt(ss), 1e-12);
+        for (int k = 0; k < m->emb; ++k) wn[(size_t)i * m->emb + k] = (float)(sw->p[(size_t)i * m->emb + k] * inv);
+    }
+    return dev_upload(wn, &m->spk_wn);
+}
+
+static int build_hr34(const WeightMap& w, Model* m) {
+    int rc;
+    const std::string sn = "sequence_network";
+    {   // stem: conv1 (32,1,3,3) + bn1 -> fp32 folded
+        const HostTensor* cw = find(w, sn + ".conv1.weight");
+        if (!cw || cw->numel() != 32 * 9) return SKB_ERR_WEIGHTS;
+        std::vector<double> s, t;
+        if ((rc = bn_affine(w, sn + ".bn1", &s, &t))) return rc;
+        std::vector<double> wf(288);
+        for (int c = 0; c < 32; ++c)
+            for (int k = 0; k < 9; ++k) wf[c * 9 + k] = (double)cw->p[c * 9 + k] * s[c];
+        if ((rc = upload_f(wf, &m->stem_w))) return rc;
+        if ((rc = upload_f(t, &m->stem_b))) return rc;
+    }
+    const int nblocks[4] = {3, 4, 6, 3}, planes[4] = {32, 64, 128, 256};
+    for (int li = 0; li < 4; ++li)
+        for (int bi = 0; bi < nblocks[li]; ++bi) {
+            const std::string p = sn + ".layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+            BlockW b;
+            b.C = planes[li];
+            b.stride = (bi == 0 && li > 0) ? 2 : 1;
+            if ((rc = pack_conv_bn(w, p + ".conv1.weight", p + ".bn1", m->bf16, &b.conv1))) return rc;
+            if ((rc = pack_conv_bn(w, p + ".conv2.weight", p + ".bn2", m->bf16, &b.conv2))) return rc;
+            b.has_sc = w.count(p + ".shortcut.0.weight") > 0;
+            if (b.has_sc && (rc = pack_conv_bn(w, p + ".shortcut.0.weight", p + ".shortcut.1", m->bf16, &b.sc))) return rc;
+            const HostTensor *f0 = find(w, p + ".se.fc.0.weight"), *f2 = find(w, p + ".se.fc.2.weight");
+            if (!f0 || !f2) return SKB_ERR_WEIGHTS;
+            if ((rc = upload_raw(f0, &b.se_w1))) return rc;
+            if ((rc = upload_raw(f2, &b.se_w2))) return rc;
+            m->blocks.push_back(b);
+        }
+    // attentive pooling (num_channels*num_freqs = 2560, attention 128, global context)
+    const HostTensor *a0w = find(w, "stat_pooling.attention.0.weight"), *a0b = find(w, "stat_pooling.attention.0.bias"),
+                     *a4w = find(w, "stat_pooling.attention.4.weight"), *a4b = find(w, "stat_pooling.attention.4.bias");
+    if (!a0w || !a0b || !a4w || !a4b) return SKB_ERR_WEIGHTS;
+    const int A = (int)a0w->shape[0], D = (int)a4w->shape[0];
+    if (a0w->shape[1] != 3 * D || D != 2560) {
+        set_last_error(__FILE__, __LINE__, "stat_pooling.attention must be AttentivePooling(256, 10, global_context=True) (7680 -> 128 -> 2560)");
+        return SKB_ERR_WEIGHTS;
+    }
+    m->att_A = A;
+    m->pool_D = D;
+    std::vector<float> w1x((size_t)A * D), w1g((size_t)A * 2 * D);
+    for (int a = 0; a < A; ++a) {
+        memcpy(&w1x[(size_t)a * D], a0w->p + (size_t)a * 3 * D, D * sizeof(float));
+        memcpy(&w1g[(size_t)a * 2 * D], a0w->p + (size_t)a * 3 * D + D, 2 * D * sizeof(float));
+    }
+    if ((rc = dev_upload(w1x, &m->att_w1x))) return rc;
+    if ((rc = dev_upload(w1g, &m->att_w1g))) return rc;
+    if ((rc = upload_raw(a0b, &m->att_b1))) return rc;
+    std::vector<double> s, t;
+    if ((rc = bn_affine(w, "stat_pooling.attention.2", &s, &t))) return rc;
+    if ((rc = upload_f(s, &m->att_bn_s))) return rc;
+    if ((rc = upload_f(t, &m->att_bn_t))) return rc;
+    if ((rc = upload_raw(a4w, &m->att_w2))) return rc;
+    if ((rc = upload_raw(a4b, &m->att_b2))) return rc;
+    // embedding head: Linear(5120 -> E, no bias) + BatchNorm1d(E)
+    const HostTensor* lw = find(w, "before_speaker_embedding.lin_be.weight");
+    if (!lw || lw->shape.size() != 2 || lw->shape[1] != 2 * D) return SKB_ERR_WEIGHTS;
+    m->emb = (int)lw->shape[0];
+    if ((rc = upload_raw(lw, &m->lin_w))) return rc;
+    if ((rc = bn_affine(w, "before_speaker_embedding.bn_be", &s, &t))) return rc;
+    if ((rc = upload_f(s, &m->be_s))) return rc;
+    if ((rc = upload_f(t, &m->be_t))) return rc;
+    return build_margin_head(w, m);
+}
+
+static int build_tdnn(const WeightMap& w, Model* m) {
+    // conv -> LeakyReLU(0.2) -> BatchNorm, x5 (xvector.py:467-483): BN_k folds FORWARD into conv_{k+1}
+    // (exact: no padding), BN_5 folds into the statistics pooling.
+    const int ks[5] = {5, 3, 3, 1, 1}, ds[5] = {1, 2, 3, 1, 1};
+    std::vector<double> ps, pt;   // previous layer's BN affine
+    int rc;
+    for (int i = 0; i < 5; ++i) {
+        const std::string c = "sequence_network.conv" + std::to_string(i + 1);
+        const HostTensor *cw = find(w, c + ".weight"), *cb = find(w, c + ".bias");
+        if (!cw || !cb || cw->shape.size() != 3 || cw->shape[2] != ks[i]) return SKB_ERR_WEIGHTS;
+        const int cout = (int)cw->shape[0], cin = (int)cw->shape[1], K = ks[i];
+        std::vector<double> wf((size_t)cout * cin * K), bf(cout);
+        for (int co = 0; co < cout; ++co) {
+            double b = cb->p[co];
+            for (int ci = 0; ci < cin; ++ci)
+                for (int k = 0; k < K; ++k) {
+                    const double v = cw->p[((size_t)co * cin + ci) * K + k];
+                    wf[((size_t)co * cin + ci) * K + k] = ps.empty() ? v : v * ps[ci];
+                    if (!ps.empty()) b += v * pt[ci];
+                }
+            bf[co] = b;
+        }
+        const int cin_pad = (cin + kConvKC - 1) / kConvKC * kConvKC;
+        ConvW cv;
+        if ((rc = pack_conv(wf, bf, cout, cin, cin_pad, K, m->bf16, &cv))) return rc;
+        m->tdnn.push_back(cv);
+        m->tdnn_k.push_back(K);
+        m->tdnn_d.push_back(ds[i]);
+        if ((rc = bn_affine(w, "sequence_network.batch_norm" + std::to_string(i + 1), &ps, &pt))) return rc;
+    }
+    if ((rc = upload_f(ps, &m->pool_s))) return rc;
+    if ((rc = upload_f(pt, &m->pool_t))) return rc;
+    m->pool_D = (int)ps.size();
+    const HostTensor *lw = find(w, "before_speaker_embedding.linear6.weight"), *lb = find(w, "before_speaker_embedding.linear6.bias");
+    if (!lw || !lb || lw->shape[1] != 2 * m->pool_D) return SKB_ERR_WEIGHTS;
+    m->emb = (int)lw->shape[0];
+    if ((rc = upload_raw(lw, &m->lin_w))) return rc;
+    if ((rc = upload_raw(lb, &m->lin_b))) return rc;
+    return build_margin_head(w, m);
+}
+
+static void free_model(Model* m) {
+    frontend_consts_destroy(&m->fe);
+    cudaFree(m->stem_w); cudaFree(m->stem_b);
+    for (auto& b : m->blocks) {
+        free_conv(&b.conv1); free_conv(&b.conv2);
+        if (b.has_sc) free_conv(&b.sc);
+        cudaFree(b.se_w1); cudaFree(b.se_w2);
+    }
+    for (auto& c : m->tdnn) free_conv(&c);
+    cudaFree(m->att_w1x); cudaFree(m->att_w1g); cudaFree(m->att_b1); cudaFree(m->att_bn_s); cudaFree(m->att_bn_t);
+    cudaFree(m->att_w2); cudaFree(m->att_b2); cudaFree(m->lin_w); cudaFree(m->lin_b); cudaFree(m->be_s); cudaFree(m->be_t);
+    cudaFree(m->spk_wn); cudaFree(m->pool_s); cudaFree(m->pool_t);
+}
+
+// ----------------------------------------------------------------------------- per-batch plan
+struct Level {
+    int W = 0, Wp = 0, C = 0;
+    int n_rows = 0, G = 0, p_end = 0;
+    long long plane = 0;           // pixels per chunk plane (incl. guards)
+    std::vector<int> H;            // lines per utterance
+    // offsets (in ints) into the device table buffer
+    size_t o_row_b = 0, o_row_h = 0, o_utt_row0 = 0, o_utt_count = 0;
+};
+
+struct Plan {
+    int B = 0;
+    std::vector<int64_t> lengths;
+    std::vector<int> T;            // feature frames per utterance
+    int t_max = 0;
+    long long total_frames = 0, total_samples = 0;
+    std::vector<Level> lv;         // 4 levels (halfresnet34) / 6 row-table variants (tdnn: input + 5 layers)
+    int pool_frames = 0;           // frames entering the pooling
+    size_t o_wave_len = 0, o_nframes = 0, o_frame_row = 0, o_frame_utt = 0, o_pool_nfr = 0, o_row_src = 0;
+    size_t o_wave_off = 0, o_feat_off = 0, o_pool_off = 0;   // offsets (in long long) into the 64-bit table
+    std::vector<int> tab32;
+    std::vector<long long> tab64;
+};
+
+constexpr int kTailGuard = 640;    // >= largest CTA tile (512 pixels) + slack, so the last slab stays in bounds
+
+static void plan_level(Plan* pl, Level* L, int W, int C, const std::vector<int>& H, bool pad_lines, int halo) {
+    L->W = W; L->Wp = pad_lines ? W + 1 : W; L->C = C; L->H = H;
+    const int B = (int)H.size();
+    std::vector<int> row_b, row_h, utt_row0(B), utt_count(B);
+    if (pad_lines) { row_b.push_back(-1); row_h.push_back(-1); }
+    for (int b = 0; b < B; ++b) {
+        utt_row0[b] = (int)row_b.size();
+        utt_count[b] = H[b] * W;
+        for (int h = 0; h < H[b]; ++h) { row_b.push_back(b); row_h.push_back(h); }
+        if (pad_lines) { row_b.push_back(-1); row_h.push_back(-1); }
+    }
+    L->n_rows = (int)row_b.size();
+    L->G = (halo + 7) / 8 * 8;
+    if (L->G < 8) L->G = 8;
+    L->p_end = L->G + L->n_rows * L->Wp;
+    L->plane = (long long)L->p_end + kTailGuard + halo + 8;
+    L->o_row_b = pl->tab32.size(); pl->tab32.insert(pl->tab32.end(), row_b.begin(), row_b.end());
+    L->o_row_h = pl->tab32.size(); pl->tab32.insert(pl->tab32.end(), row_h.begin(), row_h.end());
+    L->o_utt_row0 = pl->tab32.size(); pl->tab32.insert(pl->tab32.end(), utt_row0.begin(), utt_row0.end());
+    L->o_utt_count = pl->tab32.size(); pl->tab32.insert(pl->tab32.end(), utt_count.begin(), utt_count.end());
+}
+
+}  // namespace skb
+
+using namespace skb;
+
+// ----------------------------------------------------------------------------- the handle
+struct skb_xtractor {
+    Model m;
+    Plan plan;
+    bool plan_valid = false;
+    DevBuf tab32, tab64, feats, sums, scale, poolX, poolH, poolL, gc, hb, pooled, lin, emb_pre, emb, logits, wave, dbg;
+    std::vector<DevBuf> act;      // activation buffers
+    std::vector<size_t> act_bytes;
+    const int* d32 = nullptr;
+    const long long* d64 = nullptr;
+};
+
+namespace skb {
+
+static int num_frames(const Model& m, int64_t n) { return 1 + (int)(n / m.fe.hop); }
+
+static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream_t st) {
+    Plan& pl = h->plan;
+    if (h->plan_valid && pl.B == B && std::equal(lengths, lengths + B, pl.lengths.begin())) return SKB_OK;
+    h->plan_valid = false;
+    pl = Plan();
+    pl.B = B;
+    pl.lengths.assign(lengths, lengths + B);
+    const Model& m = h->m;
+    std::vector<long long> wave_off(B), feat_off(B);
+    std::vector<int> wave_len(B);
+    for (int b = 0; b < B; ++b) {
+        if (lengths[b] <= m.fe.n_fft / 2 || lengths[b] > 0x7fffffff) {
+            set_last_error(__FILE__, __LINE__, "utterance too short for the reflect-padded STFT (needs > n_fft/2 samples) or too long");
+            return SKB_ERR_ARG;
+        }
+        wave_off[b] = pl.total_samples;
+        wave_len[b] = (int)lengths[b];
+        pl.total_samples += lengths[b];
+        const int T = num_frames(m, lengths[b]);
+        pl.T.push_back(T);
+        feat_off[b] = pl.total_frames;
+        pl.total_frames += T;
+        pl.t_max = std::max(pl.t_max, T);
+    }
+    pl.o_wave_len = pl.tab32.size(); pl.tab32.insert(pl.tab32.end(), wave_len.begin(), wave_len.end());
+    pl.o_nframes = pl.tab32.size(); pl.tab32.insert(pl.tab32.end(), pl.T.begin(), pl.T.end());
+    pl.o_wave_off = pl.tab64.size(); pl.tab64.insert(pl.tab64.end(), wave_off.begin(), wave_off.end());
+    pl.o_feat_off = pl.tab64.size(); pl.tab64.insert(pl.tab64.end(), feat_off.begin(), feat_off.end());
+
+    std::vector<int> pool_nfr(B);
+    std::vector<long long> pool_off(B);
+    std::vector<int> frame_row, frame_utt;
+    if (m.archi == SKB_ARCHI_HALFRESNET34) {
+        pl.lv.resize(4);
+        std::vector<int> H = pl.T;
+        const int Ws[4] = {80, 40, 20, 10}, Cs[4] = {32, 64, 128, 256};
+        for (int l = 0; l < 4; ++l) {
+            if (l > 0) for (auto& x : H) x = (x - 1) / 2 + 1;
+            plan_level(&pl, &pl.lv[l], Ws[l], Cs[l], H, true, Ws[l] + 2);
+        }
+        const Level& L4 = pl.lv[3];
+        long long off = 0;
+        for (int b = 0; b < B; ++b) {
+            pool_nfr[b] = L4.H[b];
+            pool_off[b] = off;
+            off += L4.H[b];
+            const int r0 = pl.tab32[L4.o_utt_row0 + b];
+            for (int t = 0; t < L4.H[b]; ++t) { frame_row.push_back(r0 + t); frame_utt.push_back(b); }
+        }
+        pl.pool_frames = (int)off;
+    } else {
+        // TDNN: one "line" per frame (W = 1, no pad lines); a row table per layer output marks the
+        // frames that still exist after the unpadded dilated convolutions (T -> T-4 -> T-8 -> T-14).
+        const int shrink[6] = {0, 4, 8, 14, 14, 14};
+        const int Cs[6] = {96, 512, 512, 512, 512, 1536};
+        pl.lv.resize(6);
+        for (int l = 0; l < 6; ++l) {
+            plan_level(&pl, &pl.lv[l], 1, Cs[l], pl.T, false, 8);
+            // overwrite row_h with the validity of this layer's output
+            size_t r = pl.lv[l].o_row_h;
+            for (int b = 0; b < B; ++b)
+                for (int t = 0; t < pl.T[b]; ++t, ++r) pl.tab32[r] = (t < pl.T[b] - shrink[l]) ? t : -1;
+        }
+        long long off = 0;
+        for (int b = 0; b < B; ++b) {
+            const int To = pl.T[b] - 14;
+            if (To < 1) {
+                set_last_error(__FILE__, __LINE__, "utterance shorter than the TDNN context (15 frames)");
+                return SKB_ERR_ARG;
+            }
+            pool_nfr[b] = To;
+            pool_off[b] = off;
+            off += To;
+            const int r0 = pl.tab32[pl.lv[5].o_utt_row0 + b];
+            for (int t = 0; t < To; ++t) { frame_row.push_back(r0 + t); frame_utt.push_back(b); }
+        }
+        pl.pool_frames = (int)off;
+        // source frame of every input row (identity here; kept explicit for the pack kernel)
+        pl.o_row_src = pl.tab32.size();
+        for (long long i = 0; i < pl.total_frames; ++i) pl.tab32.push_back((int)i);
+    }
+    pl.o_frame_row = pl.tab32.size(); pl.tab32.insert(pl.tab32.end(), frame_row.begin(), frame_row.end());
+    pl.o_frame_utt = pl.tab32.size(); pl.tab32.insert(pl.tab32.end(), frame_utt.begin(), frame_utt.end());
+    pl.o_pool_nfr = pl.tab32.size(); pl.tab32.insert(pl.tab32.end(), pool_nfr.begin(), pool_nfr.end());
+    pl.o_pool_off = pl.tab64.size(); pl.tab64.insert(pl.tab64.end(), pool_off.begin(), pool_off.end());
+
+    int rc;
+    if ((rc = h->tab32.ensure(pl.tab32.size() * sizeof(int)))) return rc;
+    if ((rc = h->tab64.ensure(pl.tab64.size() * sizeof(long long)))) return rc;
+    // (synchronous copies: the host vectors are pageable and the plan is cached across calls)
+    SKB_CUDA_CHECK(cudaStreamSynchronize(st));
+    SKB_CUDA_CHECK(cudaMemcpy(h->tab32.p, pl.tab32.data(), pl.tab32.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SKB_CUDA_CHECK(cudaMemcpy(h->tab64.p, pl.tab64.data(), pl.tab64.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    h->d32 = (const int*)h->tab32.p;
+    h->d64 = (const long long*)h->tab64.p;
+
+    // activation buffers: zero them so pad pixels / guards are zero for this geometry
+    std::vector<size_t> need;
+    if (m.archi == SKB_ARCHI_HALFRESNET34) {
+        for (int l = 0; l < 4; ++l) {
+            const size_t bytes = (size_t)(pl.lv[l].C / 8) * pl.lv[l].plane * 16;
+            for (int k = 0; k < 5; ++k) need.push_back(bytes);   // A, B, Y1, Y2, SC
+        }
+    } else {
+        for (int l = 0; l < 6; ++l) need.push_back((size_t)(pl.lv[l].C / 8) * pl.lv[l].plane * 16);
+    }
+    h->act.resize(need.size());
+    h->act_bytes = need;
+    for (size_t i = 0; i < need.size(); ++i) {
+        if ((rc = h->act[i].ensure(need[i]))) return rc;
+        SKB_CUDA_CHECK(cudaMemsetAsync(h->act[i].p, 0, need[i], st));
+    }
+    const int Cmax = m.archi == SKB_ARCHI_HALFRESNET34 ? 256 : 0;
+    if (Cmax) {
+        if ((rc = h->sums.ensure((size_t)B * Cmax * sizeof(float)))) return rc;
+        if ((rc = h->scale.ensure((size_t)B * Cmax * sizeof(float)))) return rc;
+        SKB_CUDA_CHECK(cudaMemsetAsync(h->sums.p, 0, (size_t)B * Cmax * sizeof(float), st));
+    }
+    if ((rc = h->feats.ensure((size_t)pl.total_frames * m.fe.n_out * sizeof(float)))) return rc;
+    const int D = m.pool_D;
+    if ((rc = h->poolX.ensure((size_t)pl.pool_frames * D * sizeof(float)))) return rc;
+    if (m.archi == SKB_ARCHI_HALFRESNET34) {
+        if ((rc = h->poolH.ensure((size_t)pl.pool_frames * m.att_A * sizeof(float)))) return rc;
+        if ((rc = h->poolL.ensure((size_t)pl.pool_frames * D * sizeof(float)))) return rc;
+        if ((rc = h->gc.ensure((size_t)B * 2 * D * sizeof(float)))) return rc;
+        if ((rc = h->hb.ensure((size_t)B * m.att_A * sizeof(float)))) return rc;
+    }
+    if ((rc = h->pooled.ensure((size_t)B * 2 * D * sizeof(float)))) return rc;
+    if ((rc = h->lin.ensure((size_t)B * m.emb * sizeof(float)))) return rc;
+    if ((rc = h->emb_pre.ensure((size_t)B * m.emb * sizeof(float)))) return rc;
+    h->plan_valid = true;
+    return SKB_OK;
+}
+
+// ----------------------------------------------------------------------------- conv launch helper
+static int run_conv(skb_xtractor* h, const ConvW& cw, const Level& Lin, const uint16_t* in, uint16_t* out, const Level& Lout,
+                    bool subsample, int act, bool conv3x3, const int* tdnn_shifts, float* se_sums, size_t row_h_override,
+                    cudaStream_t st) {
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = in; p.in_plane = Lin.plane; p.w = cw.w; p.bias = cw.bias; p.out = out; p.out_plane = Lout.plane;
+    p.cin = cw.cin; p.cout = cw.cout; p.taps = cw.taps;
+    p.Wp = Lin.Wp; p.W = Lin.W; p.G = Lin.G; p.p_end = Lin.p_end;
+    int max_shift = 0;
+    if (conv3x3) {
+        p.halo = Lin.Wp + 1;
+        for (int t = 0; t < 9; ++t) p.tap_shift[t] = (t / 3 - 1) * Lin.Wp + (t % 3 - 1);
+        max_shift = Lin.Wp + 1;
+    } else if (tdnn_shifts) {
+        p.halo = 0;
+        for (int t = 0; t < cw.taps; ++t) { p.tap_shift[t] = tdnn_shifts[t]; max_shift = std::max(max_shift, tdnn_shifts[t]); }
+    } else {
+        p.halo = 0;
+        p.tap_shift[0] = 0;
+    }
+    const int tile_m = conv_tile_m(cw.ncta);
+    p.rows_pad = (tile_m + p.halo + max_shift + 7) / 8 * 8;
+    p.act = act;
+    p.row_b = h->d32 + Lin.o_row_b;
+    p.row_h = h->d32 + (row_h_override ? row_h_override : Lin.o_row_h);
+    p.subsample = subsample ? 1 : 0;
+    p.out_G = Lout.G; p.out_Wp = Lout.Wp;
+    p.out_utt_row0 = h->d32 + Lout.o_utt_row0;
+    p.se_sums = se_sums;
+    g_launches++;
+    return launch_conv_umma(p, cw.ncta, h->m.bf16, st);
+}
+
+#define SKB_TRY(x)            \
+    do {                      \
+        int _rc = (x);        \
+        if (_rc) return _rc;  \
+    } while (0)
+
+// planes -> dense (B, C, h_max, W) fp32 (test hook)
+template <bool BF16>
+__global__ void unpack_planes_kernel(const uint16_t* __restrict__ act, long long plane, int C, int W, int Wp, int G,
+                                     const int* __restrict__ utt_row0, const int* __restrict__ utt_count, int h_max,
+                                     float* __restrict__ out, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int w = (int)(idx % W);
+    const int hh = (int)((idx / W) % h_max);
+    const int c = (int)((idx / ((long long)W * h_max)) % C);
+    const int b = (int)(idx / ((long long)W * h_max * C));
+    const int H = utt_count[b] / W;
+    float v = 0.f;
+    if (hh < H) {
+        const long long pix = (long long)G + (long long)(utt_row0[b] + hh) * Wp + w;
+        const uint16_t u = act[((size_t)(c >> 3) * plane + pix) * 8 + (c & 7)];
+        if (BF16) {
+            __nv_bfloat16 t;
+            memcpy(&t, &u, 2);
+            v = __bfloat162float(t);
+        } else {
+            __half t;
+            memcpy(&t, &u, 2);
+            v = __half2float(t);
+        }
+    }
+    out[idx] = v;
+}
+
+static int export_stage(skb_xtractor* h, const uint16_t* act, const Level& L, int h_max, float* out, int64_t* per_utt,
+                        cudaStream_t st) {
+    const long long total = (long long)h->plan.B * L.C * h_max * L.W;
+    *per_utt = (int64_t)L.C * h_max * L.W;
+    const int blocks = (int)((total + 255) / 256);
+    if (h->m.bf16)
+        unpack_planes_kernel<true><<<blocks, 256, 0, st>>>(act, L.plane, L.C, L.W, L.Wp, L.G, h->d32 + L.o_utt_row0, h->d32 + L.o_utt_count, h_max, out, total);
+    else
+        unpack_planes_kernel<false><<<blocks, 256, 0, st>>>(act, L.plane, L.C, L.W, L.Wp, L.G, h->d32 + L.o_utt_row0, h->d32 + L.o_utt_count, h_max, out, total);
+    SKB_CUDA_CHECK(cudaGetLastError());
+    return SKB_OK;
+}
+
+// ----------------------------------------------------------------------------- forward passes
+static int head_and_logits(skb_xtractor* h, int norm_embedding, float* emb_out, float* logits_out, cudaStream_t st) {
+    const Model& m = h->m;
+    const int B = h->plan.B, D = m.pool_D;
+    // before_speaker_embedding: Linear (+ folded BatchNorm1d) (xvector.py:578-581 / :489-491)
+    SKB_TRY(launch_sgemm_nt((const float*)h->pooled.p, m.lin_w, (float*)h->lin.p, m.lin_b, B, m.emb, 2 * D, 2 * D, 2 * D, m.emb, 1.f, st));
+    SKB_TRY(launch_head_norm((const float*)h->lin.p, m.be_s, m.be_t, B, m.emb, norm_embedding, (float*)h->emb_pre.p, emb_out, st));
+    g_launches += 2;
+    if (logits_out && m.n_spk > 0) {   // ArcMarginProduct(target=None): s * cos (loss.py:299-310)
+        SKB_TRY(launch_sgemm_nt(emb_out, m.spk_wn, logits_out, nullptr, B, m.n_spk, m.emb, m.emb, m.emb, m.n_spk, m.margin_s, st));
+        g_launches++;
+    }
+    return SKB_OK;
+}
+
+static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, float* emb_out, float* logits_out,
+                        const char* stop, int h_max, float* dbg_out, int64_t* per_utt, cudaStream_t st) {
+    const Model& m = h->m;
+    Plan& pl = h->plan;
+    const int B = pl.B;
+    const int* d32 = h->d32;
+    const long long* d64 = h->d64;
+    float* feats = (float*)h->feats.p;
+    SKB_TRY(frontend_launch(m.fe, wave, d64 + pl.o_wave_off, d32 + pl.o_wave_len, d64 + pl.o_feat_off, d32 + pl.o_nframes, B,
+                            pl.t_max, feats, nullptr, st));
+    g_launches += 2;
+    auto buf = [&](int level, int k) { return (uint16_t*)h->act[level * 5 + k].p; };
+    const Level& L1 = pl.lv[0];
+    SKB_TRY(launch_stem(m.bf16, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, m.stem_w, m.stem_b, buf(0, 0), L1.plane, L1.G,
+                        L1.p_end, L1.Wp, L1.W, d32 + L1.o_row_b, d32 + L1.o_row_h, st));
+    g_launches++;
+    int level = 0, cur = 0;   // current activation = buf(level, cur), cur in {0, 1}
+    if (stop && !strcmp(stop, "stem")) return export_stage(h, buf(0, 0), L1, h_max, dbg_out, per_utt, st);
+    int bi_in_layer = 0, layer = 1;
+    for (size_t i = 0; i < m.blocks.size(); ++i) {
+        const BlockW& bw = m.blocks[i];
+        const int in_level = level;
+        const uint16_t* x = buf(level, cur);
+        if (bw.stride == 2) { level++; layer++; bi_in_layer = 0; cur = 1; }   // output goes to buf(level, 0)
+        const Level& Lin = pl.lv[in_level];
+        const Level& L = pl.lv[level];
+        uint16_t *y1 = buf(level, 2), *y2 = buf(level, 3), *scb = buf(level, 4), *nxt = buf(level, cur ^ 1);
+        SKB_TRY(run_conv(h, bw.conv1, Lin, x, y1, L, bw.stride == 2, 1, true, nullptr, nullptr, 0, st));
+        SKB_TRY(run_conv(h, bw.conv2, L, y1, y2, L, false, 0, true, nullptr, (float*)h->sums.p, 0, st));
+        const uint16_t* res = x;
+        if (bw.has_sc) {
+            SKB_TRY(run_conv(h, bw.sc, Lin, x, scb, L, bw.stride == 2, 0, false, nullptr, nullptr, 0, st));
+            res = scb;
+        }
+        SKB_TRY(launch_se_fc((float*)h->sums.p, d32 + L.o_utt_count, bw.se_w1, bw.se_w2, (float*)h->scale.p, B, bw.C, st));
+        SKB_TRY(launch_se_apply(m.bf16, y2, res, nxt, L.plane, (const float*)h->scale.p, bw.C, L.G, L.p_end, L.Wp, d32 + L.o_row_b, st));
+        g_launches += 2;
+        cur ^= 1;
+        if (stop) {
+            char name[32];
+            snprintf(name, sizeof(name), "layer%d.%d", layer, bi_in_layer);
+            if (!strcmp(stop, name)) return export_stage(h, buf(level, cur), L, h_max, dbg_out, per_utt, st);
+        }
+        bi_in_layer++;
+    }
+    // attentive statistics pooling with global context (pooling.py:151-171)
+    const Level& L4 = pl.lv[3];
+    const int D = m.pool_D, A = m.att_A, F = pl.pool_frames;
+    float *X = (float*)h->poolX.p, *Hh = (float*)h->poolH.p, *Lg = (float*)h->poolL.p;
+    SKB_TRY(launch_gather_frames(m.bf16, buf(level, cur), L4.plane, L4.C, L4.W, L4.Wp, L4.G, d32 + pl.o_frame_row, F, X, st));
+    SKB_TRY(launch_meanstd(X, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, nullptr, nullptr, (float*)h->gc.p, st));
+    SKB_TRY(launch_sgemm_nt((const float*)h->gc.p, m.att_w1g, (float*)h->hb.p, m.att_b1, B, A, 2 * D, 2 * D, 2 * D, A, 1.f, st));
+    SKB_TRY(launch_sgemm_nt(X, m.att_w1x, Hh, nullptr, F, A, D, D, D, A, 1.f, st));
+    SKB_TRY(launch_att_act(Hh, (const float*)h->hb.p, d32 + pl.o_frame_utt, m.att_bn_s, m.att_bn_t, F, A, st));
+    SKB_TRY(launch_sgemm_nt(Hh, m.att_w2, Lg, m.att_b2, F, D, A, A, A, D, 1.f, st));
+    SKB_TRY(launch_softmax_pool(X, Lg, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, (float*)h->pooled.p, st));
+    g_launches += 7;
+    if (stop && !strcmp(stop, "pooled")) {
+        *per_utt = 2 * D;
+        SKB_CUDA_CHECK(cudaMemcpyAsync(dbg_out, h->pooled.p, (size_t)B * 2 * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return SKB_OK;
+    }
+    if (stop) {
+        set_last_error(__FILE__, __LINE__, "unknown debug stage");
+        return SKB_ERR_ARG;
+    }
+    return head_and_logits(h, norm_embedding, emb_out, logits_out, st);
+}
+
+static int forward_tdnn(skb_xtractor* h, const float* wave, int norm_embedding, float* emb_out, float* logits_out,
+                        const char* stop, int h_max, float* dbg_out, int64_t* per_utt, cudaStream_t st) {
+    const Model& m = h->m;
+    Plan& pl = h->plan;
+    const int B = pl.B;
+    const int* d32 = h->d32;
+    const long long* d64 = h->d64;
+    float* feats = (float*)h->feats.p;
+    SKB_TRY(frontend_launch(m.fe, wave, d64 + pl.o_wave_off, d32 + pl.o_wave_len, d64 + pl.o_feat_off, d32 + pl.o_nframes, B,
+                            pl.t_max, feats, nullptr, st));
+    const Level& L0 = pl.lv[0];
+    SKB_TRY(launch_pack_frames(m.bf16, feats, m.fe.n_out, L0.C, (int)pl.total_frames, d32 + pl.o_row_src, (uint16_t*)h->act[0].p,
+                               L0.plane, L0.G, st));
+    g_launches += 3;
+    for (int i = 0; i < 5; ++i) {
+        int shifts[10];
+        for (int k = 0; k < m.tdnn_k[i]; ++k) shifts[k] = k * m.tdnn_d[i];
+        const Level& Lin = pl.lv[i];
+        const Level& Lout = pl.lv[i + 1];
+        // validity (row_h) of the OUTPUT rows decides what gets stored as non-zero
+        SKB_TRY(run_conv(h, m.tdnn[i], Lin, (const uint16_t*)h->act[i].p, (uint16_t*)h->act[i + 1].p, Lout, false, 2, false,
+                         shifts, nullptr, Lout.o_row_h, st));
+        if (stop) {
+            char name[32];
+            snprintf(name, sizeof(name), "tdnn%d", i + 1);
+            if (!strcmp(stop, name)) return export_stage(h, (const uint16_t*)h->act[i + 1].p, Lout, h_max, dbg_out, per_utt, st);
+        }
+    }
+    const Level& L5 = pl.lv[5];
+    const int D = m.pool_D, F = pl.pool_frames;
+    float* X = (float*)h->poolX.p;
+    SKB_TRY(launch_gather_frames(m.bf16, (const uint16_t*)h->act[5].p, L5.plane, L5.C, 1, 1, L5.G, d32 + pl.o_frame_row, F, X, st));
+    SKB_TRY(launch_meanstd(X, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, m.pool_s, m.pool_t, (float*)h->pooled.p, st));
+    g_launches += 2;
+    if (stop && !strcmp(stop, "pooled")) {
+        *per_utt = 2 * D;
+        SKB_CUDA_CHECK(cudaMemcpyAsync(dbg_out, h->pooled.p, (size_t)B * 2 * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return SKB_OK;
+    }
+    if (stop) {
+        set_last_error(__FILE__, __LINE__, "unknown debug stage");
+        return SKB_ERR_ARG;
+    }
+    return head_and_logits(h, norm_embedding, emb_out, logits_out, st);
+}
+
+static int forward_any(skb_xtractor* h, const float* wave, const int64_t* lengths, int B, int norm_embedding, float* emb,
+                       float* logits, const char* stop, int h_max, float* dbg, int64_t* per_utt, cudaStream_t st) {
+    if (!h || !wave || !lengths || B <= 0) {
+        set_last_error(__FILE__, __LINE__, "bad arguments");
+        return SKB_ERR_ARG;
+    }
+    SKB_TRY(build_plan(h, lengths, B, st));
+    if (h->m.archi == SKB_ARCHI_HALFRESNET34) return forward_hr34(h, wave, norm_embedding, emb, logits, stop, h_max, dbg, per_utt, st);
+    return forward_tdnn(h, wave, norm_embedding, emb, logits, stop, h_max, dbg, per_utt, st);
+}
+
+}  // namespace skb
+
+// ----------------------------------------------------------------------------- C ABI
+extern "C" {
+
+int skb_version(void) { return 100; }
+const char* skb_last_error(void) { return g_err; }
+int64_t skb_kernel_launches(void) { return (int64_t)g_launches.load(); }
+
+int skb_xtractor_create(int archi, int n_tensors, const char* const* names, const float* const* data,
+                        const int64_t* const* shapes, const int* ndims, int compute_dtype, float margin_s,
+                        skb_xtractor_t** out) {
+    if (!out || !names || !data || !shapes || !ndims || (archi != SKB_ARCHI_HALFRESNET34 && archi != SKB_ARCHI_XVECTOR)) {
+        set_last_error(__FILE__, __LINE__, "bad arguments");
+        return SKB_ERR_ARG;
+    }
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+        set_last_error(__FILE__, __LINE__, "no CUDA device: sidekit_b200 has no CPU fallback");
+        return SKB_ERR_CUDA;
+    }
+    WeightMap w;
+    for (int i = 0; i < n_tensors; ++i) {
+        HostTensor t;
+        t.p = data[i];
+        t.shape.assign(shapes[i], shapes[i] + ndims[i]);
+        w[names[i]] = t;
+    }
+    skb_xtractor* h = new skb_xtractor();
+    h->m.archi = archi;
+    h->m.bf16 = compute_dtype == 1;
+    h->m.margin_s = margin_s;
+    int rc = build_frontend(w, &h->m);
+    if (!rc) rc = archi == SKB_ARCHI_HALFRESNET34 ? build_hr34(w, &h->m) : build_tdnn(w, &h->m);
+    if (rc) {
+        skb_xtractor_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return SKB_OK;
+}
+
+void skb_xtractor_destroy(skb_xtractor_t* h) {
+    if (!h) return;
+    free_model(&h->m);
+    DevBuf* bufs[] = {&h->tab32, &h->tab64, &h->feats, &h->sums, &h->scale, &h->poolX, &h->poolH, &h->poolL, &h->gc, &h->hb,
+                      &h->pooled, &h->lin, &h->emb_pre, &h->emb, &h->logits, &h->wave, &h->dbg};
+    for (auto* b : bufs) b->release();
+    for (auto& b : h->act) b.release();
+    delete h;
+}
+
+int skb_xtractor_embedding_size(const skb_xtractor_t* h) { return h ? h->m.emb : 0; }
+int skb_xtractor_speaker_number(const skb_xtractor_t* h) { return h ? h->m.n_spk : 0; }
+int skb_xtractor_num_frames(const skb_xtractor_t* h, int64_t n_samples) { return h ? num_frames(h->m, n_samples) : 0; }
+
+int skb_xtractor_forward(skb_xtractor_t* h, const float* wave_dev, const int64_t* lengths, int n_utt, int norm_embedding,
+                         float* emb_dev, float* logits_dev, void* stream) {
+    if (!emb_dev) {
+        set_last_error(__FILE__, __LINE__, "emb_dev is NULL");
+        return SKB_ERR_ARG;
+    }
+    return forward_any(h, wave_dev, lengths, n_utt, norm_embedding, emb_dev, logits_dev, nullptr, 0, nullptr, nullptr,
+                       (cudaStream_t)stream);
+}
+
+int skb_xtractor_forward_host(skb_xtractor_t* h, const float* wave_host, const int64_t* lengths, int n_utt, int norm_embedding,
+                              float* emb_host, float* logits_host, void* stream) {
+    if (!h || !wave_host || !lengths || !emb_host || n_utt <= 0) {
+        set_last_error(__FILE__, __LINE__, "bad arguments");
+        return SKB_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t total = 0;
+    for (int i = 0; i < n_utt; ++i) total += lengths[i];
+    SKB_TRY(h->wave.ensure((size_t)total * sizeof(float)));
+    SKB_TRY(h->emb.ensure((size_t)n_utt * h->m.emb * sizeof(float)));
+    if (logits_host) SKB_TRY(h->logits.ensure((size_t)n_utt * h->m.n_spk * sizeof(float)));
+    SKB_CUDA_CHECK(cudaMemcpyAsync(h->wave.p, wave_host, (size_t)total * sizeof(float), cudaMemcpyHostToDevice, st));
+    SKB_TRY(forward_any(h, (const float*)h->wave.p, lengths, n_utt, norm_embedding, (float*)h->emb.p,
+                        logits_host ? (float*)h->logits.p : nullptr, nullptr, 0, nullptr, nullptr, st));
+    SKB_CUDA_CHECK(cudaMemcpyAsync(emb_host, h->emb.p, (size_t)n_utt * h->m.emb * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (logits_host)
+        SKB_CUDA_CHECK(cudaMemcpyAsync(logits_host, h->logits.p, (size_t)n_utt * h->m.n_spk * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SKB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SKB_OK;
+}
+
+int skb_xtractor_pre_embedding(skb_xtractor_t* h, int n_utt, float* out_dev, void* stream) {
+    if (!h || !out_dev || !h->plan_valid || n_utt != h->plan.B) {
+        set_last_error(__FILE__, __LINE__, "pre_embedding: no matching forward call");
+        return SKB_ERR_STATE;
+    }
+    SKB_CUDA_CHECK(cudaMemcpyAsync(out_dev, h->emb_pre.p, (size_t)n_utt * h->m.emb * sizeof(float), cudaMemcpyDeviceToDevice,
+                                   (cudaStream_t)stream));
+    return SKB_OK;
+}
+
+int skb_xtractor_frontend(skb_xtractor_t* h, const float* wave_dev, const int64_t* lengths, int n_utt, int t_max,
+                          float* feats_dev, void* stream) {
+    if (!h || !wave_dev || !lengths || !feats_dev || n_utt <= 0) {
+        set_last_error(__FILE__, __LINE__, "bad arguments");
+        return SKB_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SKB_TRY(build_plan(h, lengths, n_utt, st));
+    Plan& pl = h->plan;
+    if (t_max < pl.t_max) {
+        set_last_error(__FILE__, __LINE__, "t_max smaller than the longest utterance's frame count");
+        return SKB_ERR_ARG;
+    }
+    SKB_CUDA_CHECK(cudaMemsetAsync(feats_dev, 0, (size_t)n_utt * h->m.fe.n_out * t_max * sizeof(float), st));
+    g_launches += 2;
+    return frontend_launch(h->m.fe, wave_dev, h->d64 + pl.o_wave_off, h->d32 + pl.o_wave_len, h->d64 + pl.o_feat_off,
+                           h->d32 + pl.o_nframes, n_utt, t_max, (float*)h->feats.p, feats_dev, st);
+}
+
+int skb_xtractor_debug_stage(skb_xtractor_t* h, const float* wave_dev, const int64_t* lengths, int n_utt, const char* stage,
+                             int h_max, float* out_dev, int64_t* per_utt, void* stream) {
+    if (!stage || !out_dev || !per_utt) {
+        set_last_error(__FILE__, __LINE__, "bad arguments");
+        return SKB_ERR_ARG;
+    }
+    return forward_any(h, wave_dev, lengths, n_utt, 1, nullptr, nullptr, stage, h_max, out_dev, per_utt, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,347 @@
+// Fused front-end: pre-emphasis -> framing (reflect pad, periodic Hann) -> real FFT in shared
+// memory -> power -> sparse triangular Mel filterbank -> log(. + 1e-6) [-> DCT for MFCC], then a
+// per-(utterance, coefficient) CMVN pass.  One kernel replaces PreEmphasis conv1d + torch.stft (cuFFT)
+// + |.|^2 + mel matmul + log of sidekit/nnet/preprocessor.py:267-285 (log-Mel) and :113-124 (MFCC);
+// the 513 x T spectrogram never touches HBM.
+//
+// FFT: a real frame of n_fft samples is packed as n_fft/2 complex points z[n] = f[2n] + i f[2n+1],
+// transformed by a radix-8 decimation-in-frequency FFT (digit-reversed output), and unpacked with
+//   X[k] = (Z[k] + conj Z[N/2-k])/2 - (i/2) e^{-2 pi i k/n_fft} (Z[k] - conj Z[N/2-k]).
+// The window sits at the start of the frame instead of the centre: a circular shift only changes
+// the phase, and only |X|^2 is used.
+#include "sidekit_b200.h"
+#include "common.cuh"
+#include "layers.cuh"
+
+namespace skb {
+
+struct FrontendParams {
+    const float* wave;        // concatenated utterances
+    const long long* wave_off;// [B] start of each utterance in `wave`
+    const int* wave_len;      // [B] samples
+    const long long* feat_off;// [B] start (in frames) of each utterance in the frame-major output
+    const int* n_frames;      // [B]
+    float* out;               // [sum T][n_out] frame-major
+    const float* window;      // [win]
+    const float2* tw_half;    // [NC] e^{-2 pi i m / NC}, NC = n_fft/2
+    const float2* tw_full;    // [NC+1] e^{-2 pi i k / n_fft}
+    const int* mel_lo;        // [n_mels] first FFT bin of each filter
+    const int* mel_cnt;       // [n_mels] number of bins
+    const int* mel_ofs;       // [n_mels] offset into mel_w
+    const float* mel_w;       // filter weights, concatenated
+    const float* dct;         // [n_mels][n_out] or nullptr (log-Mel)
+    int n_mels, n_out;
+    int hop, win;
+    float preemph;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// 8-point DFT (forward, e^{-2 pi i qr/8}), natural order in and out.
+__device__ __forceinline__ void dft8(float2 (&a)[8]) {
+    const float r = 0.70710678118654752440f;
+    float2 e0 = cadd(a[0], a[4]), e1 = csub(a[0], a[4]);
+    float2 e2 = cadd(a[2], a[6]), e3 = cmul_mi(csub(a[2], a[6]));
+    float2 o0 = cadd(a[1], a[5]), o1 = csub(a[1], a[5]);
+    float2 o2 = cadd(a[3], a[7]), o3 = cmul_mi(csub(a[3], a[7]));
+    float2 E0 = cadd(e0, e2), E2 = csub(e0, e2), E1 = cadd(e1, e3), E3 = csub(e1, e3);
+    float2 O0 = cadd(o0, o2), O2 = csub(o0, o2), O1 = cadd(o1, o3), O3 = csub(o1, o3);
+    // twiddles w8^k: k=1: (1-i)/sqrt2, k=2: -i, k=3: (-1-i)/sqrt2
+    float2 t1 = make_float2((O1.x + O1.y) * r, (O1.y - O1.x) * r);
+    float2 t2 = cmul_mi(O2);
+    float2 t3 = make_float2((-O3.x + O3.y) * r, (-O3.y - O3.x) * r);
+    a[0] = cadd(E0, O0); a[4] = csub(E0, O0);
+    a[1] = cadd(E1, t1); a[5] = csub(E1, t1);
+    a[2] = cadd(E2, t2); a[6] = csub(E2, t2);
+    a[3] = cadd(E3, t3); a[7] = csub(E3, t3);
+}
+
+// One radix-8 DIF stage over sub-transforms of length `len` (len = 8 * sub): thread handles index j of block blk.
+template <int NC>
+__device__ __forceinline__ void stage8(float2* z, const float2* tw, int len, int t) {
+    const int sub = len >> 3;
+    const int blk = t / sub, j = t - blk * sub;
+    float2* base = z + blk * len + j;
+    float2 a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = base[q * sub];
+    dft8(a);
+    const int tstep = (NC / len) * j;       // w_len^{j r} = w_NC^{(NC/len) j r}
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        float2 v = a[r];
+        if (sub > 1 && r > 0) v = cmul(v, tw[(tstep * r) & (NC - 1)]);
+        base[r * sub] = v;
+    }
+}
+
+// position of natural-order output k in the digit-reversed result of the DIF stages
+template <int NC>
+__device__ __forceinline__ int rev_index(int k);
+template <>
+__device__ __forceinline__ int rev_index<512>(int k) {     // 8 x 8 x 8
+    return ((k & 7) << 6) | (((k >> 3) & 7) << 3) | (k >> 6);
+}
+template <>
+__device__ __forceinline__ int rev_index<1024>(int k) {    // 8 x 8 x 8 x 2: k = r1 + 8 r2 + 64 r3 + 512 r4
+    return ((k & 7) << 7) | (((k >> 3) & 7) << 4) | (((k >> 6) & 7) << 1) | (k >> 9);
+}
+
+// NC complex points per frame, NC/8 threads per frame, FR frames per CTA iteration.
+template <int NC, int FR>
+__global__ void __launch_bounds__(NC / 8 * FR) frontend_kernel(const FrontendParams p, int frames_per_cta) {
+    constexpr int TPF = NC / 8;                 // threads per frame
+    extern __shared__ __align__(16) uint8_t fsm[];
+    float2* tw = reinterpret_cast<float2*>(fsm);                 // [NC]
+    float2* zall = tw + NC;                                      // [FR][NC + 1]
+    float* melall = reinterpret_cast<float*>(zall + FR * (NC + 1));   // [FR][n_mels]
+    const int b = blockIdx.y;
+    const int T = p.n_frames[b];
+    const int t_begin = blockIdx.x * frames_per_cta;
+    if (t_begin >= T) return;
+    const int t_end = min(T, t_begin + frames_per_cta);
+    const int fr = threadIdx.x / TPF;
+    const int t = threadIdx.x - fr * TPF;
+    for (int i = threadIdx.x; i < NC; i += blockDim.x) tw[i] = p.tw_half[i];
+    const float* x = p.wave + p.wave_off[b];
+    const int L = p.wave_len[b];
+    float2* z = zall + fr * (NC + 1);
+    float* mel = melall + fr * p.n_mels;
+    const int half_win = p.win >> 1;
+
+    for (int tb = t_begin; tb < t_end; tb += FR) {
+        const int frame = tb + fr;
+        const bool active = frame < t_end;
+        __syncthreads();
+        if (active) {
+            // windowed, pre-emphasised frame: sample n <-> y[hop*frame - win/2 + n] with reflect padding of y
+            for (int n2 = t; n2 < NC; n2 += TPF) {
+                float v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = 2 * n2 + e;
+                    float val = 0.f;
+                    if (n < p.win) {
+                        int i = p.hop * frame - half_win + n;
+                        if (i < 0) i = -i;
+                        if (i >= L) i = 2 * (L - 1) - i;
+                        const float cur = __ldg(x + i);
+                        const float prev = __ldg(x + (i == 0 ? 1 : i - 1));
+                        val = (cur - p.preemph * prev) * __ldg(p.window + n);
+                    }
+                    v[e] = val;
+                }
+                z[n2] = make_float2(v[0], v[1]);
+            }
+        }
+        __syncthreads();
+        if (active) stage8<NC>(z, tw, NC, t);
+        __syncthreads();
+        if (active) stage8<NC>(z, tw, NC / 8, t);
+        __syncthreads();
+        if (active) stage8<NC>(z, tw, NC / 64, t);
+        __syncthreads();
+        if (NC == 1024) {
+            if (active) {   // final radix-2 stage on pairs
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = (t * 4 + u) * 2;
+                    const float2 a0 = z[i], a1 = z[i + 1];
+                    z[i] = cadd(a0, a1);
+                    z[i + 1] = csub(a0, a1);
+                }
+            }
+            __syncthreads();
+        }
+        if (active) {
+            // unpack the real spectrum, take |X|^2 for k = 0..NC and store it in natural order into a
+            // power buffer that aliases z (all reads first).
+            constexpr int kPer = (NC + TPF) / TPF;      // ceil((NC + 1) / TPF)
+            float pw[kPer];
+#pragma unroll
+            for (int c = 0; c < kPer; ++c) {
+                const int k = t + c * TPF;
+                pw[c] = 0.f;
+                if (k <= NC) {
+                    const float2 zk = z[rev_index<NC>(k & (NC - 1))];
+                    const float2 zr = z[rev_index<NC>((NC - k) & (NC - 1))];
+                    const float2 zc = make_float2(zr.x, -zr.y);
+                    const float2 s = cadd(zk, zc), d = csub(zk, zc);
+                    const float2 wd = cmul(__ldg(p.tw_full + k), d);      // e^{-2 pi i k / n_fft} (Z[k] - conj Z[N-k])
+                    const float re = 0.5f * (s.x + wd.y);                   // (-i/2) wd = (wd.y - i wd.x) / 2
+                    const float im = 0.5f * (s.y - wd.x);
+                    pw[c] = re * re + im * im;
+                }
+            }
+            // every read of z by this frame's threads completes before the power spectrum overwrites it
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + fr), "r"(TPF) : "memory");
+            float* pwr = reinterpret_cast<float*>(z);
+#pragma unroll
+            for (int c = 0; c < kPer; ++c) {
+                const int k = t + c * TPF;
+                if (k <= NC) pwr[k] = pw[c];
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + fr), "r"(TPF) : "memory");
+            for (int m = t; m < p.n_mels; m += TPF) {
+                const int lo = p.mel_lo[m], c = p.mel_cnt[m];
+                const float* w = p.mel_w + p.mel_ofs[m];
+                float acc = 0.f;
+                for (int i = 0; i < c; ++i) acc = fmaf(pwr[lo + i], __ldg(w + i), acc);
+                mel[m] = logf(acc + 1e-6f);
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + fr), "r"(TPF) : "memory");
+            float* dst = p.out + (size_t)(p.feat_off[b] + frame) * p.n_out;
+            if (p.dct == nullptr) {
+                for (int m = t; m < p.n_out; m += TPF) dst[m] = mel[m];
+            } else {
+                for (int c = t; c < p.n_out; c += TPF) {
+                    float acc = 0.f;
+                    for (int m = 0; m < p.n_mels; ++m) acc = fmaf(mel[m], __ldg(p.dct + m * p.n_out + c), acc);
+                    dst[c] = acc;
+                }
+            }
+        }
+    }
+}
+
+// CMVN (torch.nn.InstanceNorm1d, biased variance, eps 1e-5): exact two-pass statistics per
+// (utterance, coefficient) over time on the frame-major buffer; optionally also writes the
+// (B, n_out, T_max)-shaped tensor the reference's front-end returns.
+__global__ void cmvn_kernel(float* feats, const long long* feat_off, const int* n_frames, int n_out,
+                            float* api_out, int t_max) {
+    const int b = blockIdx.x;
+    const int T = n_frames[b];
+    float* f = feats + (size_t)feat_off[b] * n_out;
+    __shared__ float s_mean[128], s_rstd[128];
+    __shared__ float part[8][128];
+    const int c = threadIdx.x % n_out, g = threadIdx.x / n_out;
+    const int ng = blockDim.x / n_out;
+    float acc = 0.f;
+    if (g < ng) for (int t = g; t < T; t += ng) acc += f[(size_t)t * n_out + c];
+    if (g < ng) part[g][c] = acc;
+    __syncthreads();
+    if (threadIdx.x < n_out) {
+        float s = 0.f;
+        for (int i = 0; i < ng; ++i) s += part[i][threadIdx.x];
+        s_mean[threadIdx.x] = s / (float)T;
+    }
+    __syncthreads();
+    acc = 0.f;
+    if (g < ng) {
+        const float mu = s_mean[c];
+        for (int t = g; t < T; t += ng) {
+            const float d = f[(size_t)t * n_out + c] - mu;
+            acc = fmaf(d, d, acc);
+        }
+        part[g][c] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_out) {
+        float s = 0.f;
+        for (int i = 0; i < ng; ++i) s += part[i][threadIdx.x];
+        s_rstd[threadIdx.x] = rsqrtf(s / (float)T + 1e-5f);
+    }
+    __syncthreads();
+    if (g < ng) {
+        const float mu = s_mean[c], rs = s_rstd[c];
+        for (int t = g; t < T; t += ng) {
+            const float v = (f[(size_t)t * n_out + c] - mu) * rs;
+            f[(size_t)t * n_out + c] = v;
+            if (api_out) api_out[((size_t)b * n_out + c) * t_max + t] = v;
+        }
+    }
+}
+
+}  // namespace skb
+
+#include <cmath>
+#include <vector>
+
+namespace skb {
+
+int frontend_consts_create(FrontendConsts* fc, int n_fft, int win, int hop, int n_mels, int n_out, const float* window,
+                           const float* fb /* [n_fft/2+1][n_mels] */, const float* dct /* [n_mels][n_out] or null */) {
+    fc->n_fft = n_fft; fc->win = win; fc->hop = hop; fc->n_mels = n_mels; fc->n_out = n_out;
+    const int NC = n_fft / 2, NB = NC + 1;
+    std::vector<float2> th(NC), tf(NB);
+    for (int i = 0; i < NC; ++i) {
+        const double a = -2.0 * M_PI * i / NC;
+        th[i] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (int k = 0; k < NB; ++k) {
+        const double a = -2.0 * M_PI * k / n_fft;
+        tf[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    std::vector<int> lo(n_mels), cnt(n_mels), ofs(n_mels);
+    std::vector<float> w;
+    for (int m = 0; m < n_mels; ++m) {
+        int first = -1, last = -1;
+        for (int k = 0; k < NB; ++k)
+            if (fb[(size_t)k * n_mels + m] != 0.f) { if (first < 0) first = k; last = k; }
+        lo[m] = first < 0 ? 0 : first;
+        cnt[m] = first < 0 ? 0 : last - first + 1;
+        ofs[m] = (int)w.size();
+        for (int k = 0; k < cnt[m]; ++k) w.push_back(fb[(size_t)(lo[m] + k) * n_mels + m]);
+    }
+    if (w.empty()) w.push_back(0.f);
+    SKB_CUDA_CHECK(cudaMalloc(&fc->window, win * sizeof(float)));
+    SKB_CUDA_CHECK(cudaMemcpy(fc->window, window, win * sizeof(float), cudaMemcpyHostToDevice));
+    SKB_CUDA_CHECK(cudaMalloc(&fc->tw_half, NC * sizeof(float2)));
+    SKB_CUDA_CHECK(cudaMemcpy(fc->tw_half, th.data(), NC * sizeof(float2), cudaMemcpyHostToDevice));
+    SKB_CUDA_CHECK(cudaMalloc(&fc->tw_full, NB * sizeof(float2)));
+    SKB_CUDA_CHECK(cudaMemcpy(fc->tw_full, tf.data(), NB * sizeof(float2), cudaMemcpyHostToDevice));
+    SKB_CUDA_CHECK(cudaMalloc(&fc->mel_lo, n_mels * sizeof(int)));
+    SKB_CUDA_CHECK(cudaMemcpy(fc->mel_lo, lo.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    SKB_CUDA_CHECK(cudaMalloc(&fc->mel_cnt, n_mels * sizeof(int)));
+    SKB_CUDA_CHECK(cudaMemcpy(fc->mel_cnt, cnt.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    SKB_CUDA_CHECK(cudaMalloc(&fc->mel_ofs, n_mels * sizeof(int)));
+    SKB_CUDA_CHECK(cudaMemcpy(fc->mel_ofs, ofs.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    SKB_CUDA_CHECK(cudaMalloc(&fc->mel_w, w.size() * sizeof(float)));
+    SKB_CUDA_CHECK(cudaMemcpy(fc->mel_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (dct) {
+        SKB_CUDA_CHECK(cudaMalloc(&fc->dct, (size_t)n_mels * n_out * sizeof(float)));
+        SKB_CUDA_CHECK(cudaMemcpy(fc->dct, dct, (size_t)n_mels * n_out * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return SKB_OK;
+}
+
+void frontend_consts_destroy(FrontendConsts* fc) {
+    cudaFree(fc->window); cudaFree(fc->tw_half); cudaFree(fc->tw_full); cudaFree(fc->mel_lo);
+    cudaFree(fc->mel_cnt); cudaFree(fc->mel_ofs); cudaFree(fc->mel_w); cudaFree(fc->dct);
+    *fc = FrontendConsts();
+}
+
+// feats: frame-major [sum T][n_out]; api_out optional (B, n_out, t_max).
+int frontend_launch(const FrontendConsts& fc, const float* wave, const long long* wave_off, const int* wave_len,
+                    const long long* feat_off, const int* n_frames, int B, int t_max, float* feats, float* api_out,
+                    cudaStream_t stream) {
+    FrontendParams p;
+    p.wave = wave; p.wave_off = wave_off; p.wave_len = wave_len; p.feat_off = feat_off; p.n_frames = n_frames;
+    p.out = feats; p.window = fc.window; p.tw_half = fc.tw_half; p.tw_full = fc.tw_full;
+    p.mel_lo = fc.mel_lo; p.mel_cnt = fc.mel_cnt; p.mel_ofs = fc.mel_ofs; p.mel_w = fc.mel_w; p.dct = fc.dct;
+    p.n_mels = fc.n_mels; p.n_out = fc.n_out; p.hop = fc.hop; p.win = fc.win; p.preemph = 0.97f;
+    const int frames_per_cta = 16;
+    dim3 grid((t_max + frames_per_cta - 1) / frames_per_cta, B);
+    if (fc.n_fft == 1024) {
+        constexpr int NC = 512, FR = 4;
+        const size_t smem = NC * sizeof(float2) + FR * (NC + 1) * sizeof(float2) + FR * fc.n_mels * sizeof(float);
+        frontend_kernel<NC, FR><<<grid, NC / 8 * FR, smem, stream>>>(p, frames_per_cta);
+    } else if (fc.n_fft == 2048) {
+        constexpr int NC = 1024, FR = 2;
+        const size_t smem = NC * sizeof(float2) + FR * (NC + 1) * sizeof(float2) + FR * fc.n_mels * sizeof(float);
+        frontend_kernel<NC, FR><<<grid, NC / 8 * FR, smem, stream>>>(p, frames_per_cta);
+    } else {
+        set_last_error(__FILE__, __LINE__, "unsupported n_fft (1024 or 2048)");
+        return SKB_ERR_ARG;
+    }
+    SKB_CUDA_CHECK(cudaGetLastError());
+    const int ng = 512 / fc.n_out;
+    cmvn_kernel<<<B, ng * fc.n_out, 0, stream>>>(feats, feat_off, n_frames, fc.n_out, api_out, t_max);
+    SKB_CUDA_CHECK(cudaGetLastError());
+    return SKB_OK;
+}
+
+}  // namespace skb

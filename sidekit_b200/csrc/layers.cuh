@@ -1,0 +1,55 @@
+// Host-side launch wrappers for the kernels in layers.cu / frontend.cu / conv_umma.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace skb {
+
+struct ConvParams;
+
+struct FrontendConsts {
+    int n_fft = 0, win = 0, hop = 0, n_mels = 0, n_out = 0;
+    float* window = nullptr;
+    float2* tw_half = nullptr;
+    float2* tw_full = nullptr;
+    int *mel_lo = nullptr, *mel_cnt = nullptr, *mel_ofs = nullptr;
+    float* mel_w = nullptr;
+    float* dct = nullptr;
+};
+
+int launch_stem(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float* w,
+                const float* bias, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
+                const int* row_b, const int* row_h, cudaStream_t st);
+int launch_se_fc(float* sums, const int* utt_count, const float* w1, const float* w2, float* scale, int B, int C,
+                 cudaStream_t st);
+int launch_se_apply(bool bf16, const uint16_t* y, const uint16_t* sc, uint16_t* out, long long plane, const float* scale,
+                    int C, int G, int p_end, int Wp, const int* row_b, cudaStream_t st);
+int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C, int W, int Wp, int G,
+                         const int* frame_row, int n_frames, float* X, cudaStream_t st);
+int launch_meanstd(const float* X, const long long* frame_off, const int* n_fr, int B, int D, const float* aff_s,
+                   const float* aff_t, float* out, cudaStream_t st);
+int launch_att_act(float* h, const float* hb, const int* frame_utt, const float* bn_s, const float* bn_t, int n_frames,
+                   int A, cudaStream_t st);
+int launch_softmax_pool(const float* X, const float* logit, const long long* frame_off, const int* n_fr, int B, int D,
+                        float* out, cudaStream_t st);
+int launch_head_norm(const float* x, const float* aff_s, const float* aff_t, int B, int E, int norm_embedding,
+                     float* emb_pre, float* emb, cudaStream_t st);
+int launch_sgemm_nt(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
+                    int ldc, float alpha, cudaStream_t st);
+int launch_pack_frames(bool bf16, const float* X, int C_src, int C_dst, int n_rows, const int* row_src, uint16_t* out,
+                       long long plane, int G, cudaStream_t st);
+
+// conv_umma.cu
+int launch_conv_umma(const ConvParams& p, int n_cta, bool bf16, cudaStream_t st);
+int conv_tile_m(int n_cta);          // output pixels per CTA for a given N_CTA configuration
+int conv_pick_ncta(int cout);        // 32 / 64 / 128
+
+// frontend.cu
+int frontend_consts_create(FrontendConsts* fc, int n_fft, int win, int hop, int n_mels, int n_out, const float* window,
+                           const float* fb, const float* dct);
+void frontend_consts_destroy(FrontendConsts* fc);
+int frontend_launch(const FrontendConsts& fc, const float* wave, const long long* wave_off, const int* wave_len,
+                    const long long* feat_off, const int* n_frames, int B, int t_max, float* feats, float* api_out,
+                    cudaStream_t stream);
+
+}  // namespace skb

@@ -1,0 +1,28 @@
+"""Margin head and normalisation helpers (sidekit/nnet/loss.py:91-100, :256-326); inference branch only."""
+import math
+
+import torch
+
+
+def l2_norm(input, axis=1):
+    norm = torch.norm(input, 2, axis, True)
+    return torch.div(input, norm)
+
+
+class ArcMarginProduct(torch.nn.Module):
+    """Parameter container; ``forward(target=None)`` = s * cos(x, W) is computed by the engine's head GEMM."""
+
+    def __init__(self, in_features, out_features, s=30.0, m=0.50, easy_margin=False):
+        super().__init__()
+        self.in_features, self.out_features, self.s, self.m = in_features, out_features, s, m
+        self.weight = torch.nn.Parameter(torch.FloatTensor(out_features, in_features))
+        torch.nn.init.xavier_uniform_(self.weight)
+        self.easy_margin = easy_margin
+        self.cos_m, self.sin_m = math.cos(self.m), math.sin(self.m)
+        self.th = math.cos(math.pi - self.m)
+        self.mm = math.sin(math.pi - self.m) * self.m
+
+    def forward(self, input, target=None):
+        if target is not None:
+            raise NotImplementedError("training-time margin is out of scope (inference hot path only)")
+        raise RuntimeError("the margin head runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True)")

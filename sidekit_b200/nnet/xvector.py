@@ -1,0 +1,261 @@
+"""``Xtractor`` -- drop-in for ``sidekit.nnet.xvector.Xtractor`` on the inference path
+(sidekit/nnet/xvector.py:419-686 constructor, :876-907 forward, :909-924 context_size).
+
+Same constructor signature, same module tree and ``state_dict`` keys, same
+return convention: ``(logits, embedding)`` for the margin losses, the bare embedding for
+``loss='cce'`` with ``is_eval=True``.  The torch modules are parameter containers; ``forward`` hands
+the whole pass to the native engine (csrc/engine.cu) through the C ABI.  Two deliberate deviations
+from the reference as shipped, both required for its ``forward`` to run at all (SURVEY.md finding 4):
+``halfresnet34`` pools with ``AttentivePooling(256, 10, global_context=True)`` (the shipped
+``(256, 80)`` cannot consume the trunk output) and ``MfccFrontEnd.forward`` accepts ``is_eval``.
+"""
+import ctypes
+import weakref
+from collections import OrderedDict
+
+import torch
+
+from .. import _lib
+from .loss import ArcMarginProduct
+from .pooling import AttentivePooling, MeanStdPooling
+from .preprocessor import MelSpecFrontEnd, MfccFrontEnd
+from .res_net import PreHalfResNet34
+
+_ARCHI_ID = {"halfresnet34": 0, "xvector": 1}
+
+
+class _NativeHandle:
+    """Owns one ``skb_xtractor_t``; destroyed with the Python object."""
+
+    def __init__(self, archi, state_dict, compute_dtype, margin_s):
+        names, tensors = [], []
+        for k, v in state_dict.items():
+            if not v.is_floating_point():
+                continue
+            names.append(k.encode())
+            tensors.append(v.detach().to("cpu", torch.float32).contiguous())
+        n = len(names)
+        c_names = (ctypes.c_char_p * n)(*names)
+        c_data = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        shape_arrays = [_lib.i64_array(list(t.shape) or [1]) for t in tensors]
+        c_shapes = (_lib.c_i64_p * n)(*[ctypes.cast(a, _lib.c_i64_p) for a in shape_arrays])
+        c_ndims = (ctypes.c_int * n)(*[max(t.dim(), 1) for t in tensors])
+        out = ctypes.c_void_p()
+        _lib.check(_lib.lib().skb_xtractor_create(_ARCHI_ID[archi], n, c_names, c_data, c_shapes, c_ndims,
+                                                  compute_dtype, float(margin_s), ctypes.byref(out)))
+        self.ptr = out
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().skb_xtractor_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class Xtractor(torch.nn.Module):
+    """x-vector extractor; see the module docstring.  ``compute_dtype``: 'fp16' (default) or 'bf16'
+    tensor-core operands, fp32 accumulation -- an extension, not a reference argument."""
+
+    def __init__(self, speaker_number, model_archi="xvector", loss=None, norm_embedding=False, aam_margin=0.2,
+                 aam_s=30, embedding_size=256, compute_dtype="fp16"):
+        super().__init__()
+        self.speaker_number = speaker_number
+        self.feature_size = None
+        self.norm_embedding = norm_embedding
+        self.model_archi = model_archi
+        self.compute_dtype = compute_dtype
+        self._native = None
+        self._native_device = None
+
+        if model_archi == "xvector":
+            self.input_nbdim = 2
+            if loss not in ["cce", "aam"]:
+                raise NotImplementedError("The valid loss are for now cce and aam ")
+            self.loss = loss
+            self.activation = torch.nn.LeakyReLU(0.2)
+            self.preprocessor = MfccFrontEnd()
+            self.feature_size = self.preprocessor.n_mfcc
+            self.sequence_network = torch.nn.Sequential(OrderedDict([
+                ("conv1", torch.nn.Conv1d(self.feature_size, 512, 5, dilation=1)),
+                ("activation1", torch.nn.LeakyReLU(0.2)),
+                ("batch_norm1", torch.nn.BatchNorm1d(512)),
+                ("conv2", torch.nn.Conv1d(512, 512, 3, dilation=2)),
+                ("activation2", torch.nn.LeakyReLU(0.2)),
+                ("batch_norm2", torch.nn.BatchNorm1d(512)),
+                ("conv3", torch.nn.Conv1d(512, 512, 3, dilation=3)),
+                ("activation3", torch.nn.LeakyReLU(0.2)),
+                ("batch_norm3", torch.nn.BatchNorm1d(512)),
+                ("conv4", torch.nn.Conv1d(512, 512, 1)),
+                ("activation4", torch.nn.LeakyReLU(0.2)),
+                ("batch_norm4", torch.nn.BatchNorm1d(512)),
+                ("conv5", torch.nn.Conv1d(512, 1536, 1)),
+                ("activation5", torch.nn.LeakyReLU(0.2)),
+                ("batch_norm5", torch.nn.BatchNorm1d(1536)),
+            ]))
+            self.embedding_size = embedding_size
+            self.stat_pooling = MeanStdPooling()
+            self.before_speaker_embedding = torch.nn.Sequential(OrderedDict([
+                ("linear6", torch.nn.Linear(3072, self.embedding_size))]))
+            if self.loss == "aam":
+                self.after_speaker_embedding = ArcMarginProduct(self.embedding_size, int(self.speaker_number),
+                                                                s=64, m=0.2, easy_margin=False)
+                self._margin_s = 64.0
+            else:   # 'cce': the classifier stack only matters in training; forward(is_eval=True) returns x
+                self.after_speaker_embedding = torch.nn.Sequential(OrderedDict([
+                    ("activation6", torch.nn.LeakyReLU(0.2)),
+                    ("batch_norm6", torch.nn.BatchNorm1d(512)),
+                    ("dropout6", torch.nn.Dropout(p=0.05)),
+                    ("linear7", torch.nn.Linear(512, 512)),
+                    ("activation7", torch.nn.LeakyReLU(0.2)),
+                    ("batch_norm7", torch.nn.BatchNorm1d(512)),
+                    ("linear8", torch.nn.Linear(512, int(self.speaker_number)))]))
+                self._margin_s = 0.0
+        elif model_archi == "halfresnet34":
+            self.preprocessor = MelSpecFrontEnd(n_fft=1024, win_length=400, hop_length=160, n_mels=80)
+            self.sequence_network = PreHalfResNet34()
+            self.embedding_size = embedding_size
+            self.before_speaker_embedding = torch.nn.Sequential(OrderedDict([
+                ("lin_be", torch.nn.Linear(in_features=5120, out_features=self.embedding_size, bias=False)),
+                ("bn_be", torch.nn.BatchNorm1d(self.embedding_size))]))
+            self.stat_pooling = AttentivePooling(256, 10, global_context=True)
+            self.loss = loss
+            if self.loss == "aam":
+                self.after_speaker_embedding = ArcMarginProduct(self.embedding_size, int(self.speaker_number),
+                                                                s=30, m=0.2, easy_margin=False)
+                self._margin_s = 30.0
+            else:
+                raise NotImplementedError("only loss='aam' is implemented for halfresnet34 (inference hot path)")
+        else:
+            raise NotImplementedError("model_archi %r: the B200 engine implements 'halfresnet34' and 'xvector'"
+                                      % (model_archi,))
+        self.preprocessor.__dict__["_owner"] = weakref.ref(self)
+
+    # ------------------------------------------------------------------ native engine management
+    def _apply(self, fn, *a, **k):
+        self._native = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._native = None
+        return super().load_state_dict(*a, **k)
+
+    def refresh(self):
+        """Re-pack the weights after an in-place parameter edit."""
+        self._native = None
+
+    def _handle(self, device):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sidekit_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if self._native is None or self._native_device != device:
+            with torch.cuda.device(device):
+                dt = {"fp16": 0, "bf16": 1}[self.compute_dtype]
+                self._native = _NativeHandle(self.model_archi, self.state_dict(), dt, self._margin_s)
+            self._native_device = device
+        return self._native.ptr
+
+    # ------------------------------------------------------------------ forward
+    def _pack(self, waves):
+        lengths = [int(w.shape[-1]) for w in waves]
+        flat = torch.cat([w.reshape(-1) for w in waves]) if len(waves) > 1 else waves[0].reshape(-1)
+        return flat.contiguous().float(), lengths
+
+    def _run(self, flat, lengths, norm_embedding, want_logits=True):
+        B = len(lengths)
+        if self.loss == "cce":
+            want_logits = False
+        on_cpu = not flat.is_cuda
+        device = torch.device("cuda", torch.cuda.current_device()) if on_cpu else flat.device
+        h = self._handle(device)
+        lens = _lib.i64_array(lengths)
+        E, S = self.embedding_size, int(self.speaker_number)
+        with torch.cuda.device(device):
+            if on_cpu:
+                emb = torch.empty((B, E), dtype=torch.float32)
+                logits = torch.empty((B, S), dtype=torch.float32) if want_logits else None
+                _lib.check(_lib.lib().skb_xtractor_forward_host(h, flat.data_ptr(), lens, B, int(norm_embedding),
+                                                               emb.data_ptr(), logits.data_ptr() if want_logits else None,
+                                                               _lib.stream_ptr()))
+            else:
+                emb = torch.empty((B, E), dtype=torch.float32, device=device)
+                logits = torch.empty((B, S), dtype=torch.float32, device=device) if want_logits else None
+                _lib.check(_lib.lib().skb_xtractor_forward(h, flat.data_ptr(), lens, B, int(norm_embedding),
+                                                          emb.data_ptr(), logits.data_ptr() if want_logits else None,
+                                                          _lib.stream_ptr()))
+        return logits, emb
+
+    def forward(self, x, is_eval=False, target=None, norm_embedding=True):
+        """Same contract as the reference's ``forward`` for ``is_eval=True, target=None``:
+        ``x`` is a (L,) or (B, L) float waveform at 16 kHz; returns ``(s*cos logits, F.normalize(embedding))``."""
+        if not is_eval or target is not None:
+            raise NotImplementedError("sidekit_b200 implements the inference path: call forward(x, is_eval=True)")
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        assert x.dim() == 2, "expected a (B, L) or (L,) waveform tensor"
+        B, L = x.shape
+        flat = x.contiguous().float().reshape(-1)
+        logits, emb = self._run(flat, [L] * B, norm_embedding)
+        if self.loss == "cce":            # xvector.py:896-898: the bare (l2-normalised or raw) embedding
+            return self._pre_embedding(B, flat)
+        return logits, emb
+
+    def _pre_embedding(self, B, like):
+        """x before the final F.normalize (what loss='cce' returns at eval time)."""
+        on_cpu = not like.is_cuda
+        device = self._native_device
+        out = torch.empty((B, self.embedding_size), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().skb_xtractor_pre_embedding(self._native.ptr, B, out.data_ptr(), _lib.stream_ptr()))
+        return out.cpu() if on_cpu else out
+
+    def extract_varlen(self, waves, norm_embedding=True, want_logits=False):
+        """Extension: one call for a list of utterances of DIFFERENT lengths, packed without padding
+        (every reduction in the engine is per utterance, so results equal one-by-one extraction)."""
+        flat, lengths = self._pack(list(waves))
+        logits, emb = self._run(flat, lengths, norm_embedding, want_logits)
+        return (logits, emb) if want_logits else emb
+
+    def _frontend(self, x):
+        B, L = x.shape
+        if not x.is_cuda:
+            raise RuntimeError("sidekit_b200 has no CPU path: move the waveform to a CUDA device")
+        h = self._handle(x.device)
+        T = _lib.lib().skb_xtractor_num_frames(h, L)
+        out = torch.empty((B, self.preprocessor.n_mfcc if self.model_archi == "xvector" else self.preprocessor.n_mels, T),
+                          dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().skb_xtractor_frontend(h, x.contiguous().float().data_ptr(), _lib.i64_array([L] * B), B, T,
+                                                        out.data_ptr(), _lib.stream_ptr()))
+        return out
+
+    def debug_stage(self, waves, stage):
+        """Test hook: activation after ``stage`` ('stem', 'layer1.0' ... 'layer4.2', 'tdnn1'..'tdnn5', 'pooled')."""
+        flat, lengths = self._pack(list(waves))
+        h = self._handle(flat.device)
+        B = len(lengths)
+        T = [_lib.lib().skb_xtractor_num_frames(h, L) for L in lengths]
+        if stage == "pooled":
+            numel, shape = None, None
+        per = ctypes.c_int64(0)
+        if self.model_archi == "halfresnet34":
+            li = 0 if stage == "stem" else int(stage[5]) - 1 if stage.startswith("layer") else 3
+            C, W = (32, 64, 128, 256)[li], (80, 40, 20, 10)[li]
+            Hm = max(T)
+            for _ in range(li):
+                Hm = (Hm - 1) // 2 + 1
+        else:
+            C, W, Hm = (1536 if stage in ("tdnn5",) else 512), 1, max(T)
+        size = B * (2 * 2560 if self.model_archi == "halfresnet34" else 3072) if stage == "pooled" else B * C * Hm * W
+        out = torch.zeros(size, dtype=torch.float32, device=flat.device)
+        with torch.cuda.device(flat.device):
+            _lib.check(_lib.lib().skb_xtractor_debug_stage(h, flat.data_ptr(), _lib.i64_array(lengths), B, stage.encode(), Hm,
+                                                           out.data_ptr(), ctypes.byref(per), _lib.stream_ptr()))
+        return out.view(B, -1) if stage == "pooled" else out.view(B, C, Hm, W)
+
+    def context_size(self):
+        context = 1
+        for name, module in self.sequence_network.named_modules():
+            if name.startswith("conv"):
+                context += module.dilation[0] * (module.kernel_size[0] - 1)
+        return context

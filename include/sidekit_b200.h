@@ -87,6 +87,13 @@ int skb_score_gemm(const float* E_dev, const float* T_dev, int Ne, int Nt, int D
                    const float* colterm_dev, double cst, double alpha, int passes, int out_dtype, void* out_dev,
                    int64_t ld_out, void* stream);
 
+/* Operand preparation for the quadratic scorers (center_stat1 statserver.py:810-817, then the
+ * model_part / seg_part / Psi fold of iv_scoring.py:451-462): xc = X - mu (mu may be NULL);
+ * rowterm[i] = 0.5 * xc_i^T Phi xc_i (Phi symmetric, (D, D)); Xout = xc . Psi when PsiT_dev (= Psi
+ * transposed, row-major) is given, else Xout = xc.  All device fp32; split-precision GEMMs inside. */
+int skb_quadratic_prepare(const float* X_dev, const float* mu_dev, const float* PsiT_dev, const float* Phi_dev, int N, int D,
+                          float* Xout_dev, float* rowterm_dev, void* stream);
+
 /* as-norm statistics (sidekit/score_normalization.py:127-133): per row of X_dev (N, D), mean and
  * unbiased std of the top_k largest scores against the (already normalised) cohort_dev (C, D). */
 int skb_asnorm_stats(const float* X_dev, const float* cohort_dev, int N, int C, int D, int top_k, float* mean_dev,

@@ -9,4 +9,9 @@ All arithmetic runs in hand-written CUDA kernels for sm_100a behind ``libsidekit
 from . import _lib
 from .nnet import Xtractor, MeanStdPooling, AttentivePooling, PreHalfResNet34, MfccFrontEnd, MelSpecFrontEnd
 
+from .bosaris import Ndx, Scores
+from .statserver import StatServer
+from .iv_scoring import cosine_scoring, PLDA_scoring, fast_PLDA_scoring, two_covariance_scoring, score_matrix
+from .score_normalization import asnorm
+
 __version__ = "0.1.0"

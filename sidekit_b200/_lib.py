@@ -47,6 +47,7 @@ def _declare(lib):
         "skb_xtractor_pre_embedding": (i32, [vp, i32, vp, vp]),
         "skb_meanstd_pool": (i32, [vp, i32, i32, i32, vp, vp]),
         "skb_score_gemm": (i32, [vp, vp, i32, i32, i32, vp, vp, f64, f64, i32, i32, vp, i64, vp]),
+        "skb_quadratic_prepare": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp]),
         "skb_asnorm_stats": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
         "skb_asnorm_apply": (i32, [vp, i32, i32, vp, vp, vp, vp]),
     }

@@ -43,7 +43,7 @@ struct ConvParams {
     int subsample;          // 1: keep even (h, w) only and write into the next level's geometry
     int out_G, out_Wp;
     const int* out_utt_row0;  // [B] first line of each utterance at the output level
-    float* se_sums;         // [B][cout] or nullptr
+    unsigned long long* se_sums;   // [B][cout] fixed-point (2^24) channel sums, or nullptr
 };
 
 constexpr int kConvKC = 32;            // input channels per A/B stage (two K=16 MMAs)
@@ -214,29 +214,31 @@ __global__ void __launch_bounds__(kConvThreads) conv_umma_kernel(const ConvParam
                     }
                 }
                 if (p.se_sums != nullptr) {
-                    // per-(utterance, channel) sums of the fp32 values for the SE squeeze; a warp's 32
-                    // pixels almost always belong to one utterance, the loop covers the boundaries.
+                    // per-(utterance, channel) sums of the fp32 values for the SE squeeze, accumulated in
+                    // 2^-24 fixed point: integer addition is associative, so the result is bit-identical
+                    // whatever the tile / warp / atomic order (and however the batch is packed).  A warp's
+                    // 32 pixels almost always belong to one utterance; the loop covers the boundaries.
                     unsigned vmask = __ballot_sync(0xffffffffu, valid);
                     while (vmask) {
                         const int leader = __ffs(vmask) - 1;
                         const int b0 = __shfl_sync(0xffffffffu, b, leader);
                         const bool mine = valid && (b == b0);
                         const unsigned mm = __ballot_sync(0xffffffffu, mine);
-                        float t[32];
+                        long long t[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) t[i] = mine ? v[i] : 0.f;
-                        // transposing butterfly: 31 shuffles, lane l ends with the sum of channel c0 + l
+                        for (int i = 0; i < 32; ++i) t[i] = mine ? __float2ll_rn(v[i] * 16777216.f) : 0ll;
+                        // transposing butterfly: 31 exchanges, lane l ends with the sum of channel c0 + l
 #pragma unroll
                         for (int s = 16; s >= 1; s >>= 1) {
                             const bool upper = (lane & s) != 0;
 #pragma unroll
                             for (int i = 0; i < s; ++i) {
-                                const float send = upper ? t[i] : t[i + s];
-                                const float keep = upper ? t[i + s] : t[i];
+                                const long long send = upper ? t[i] : t[i + s];
+                                const long long keep = upper ? t[i + s] : t[i];
                                 t[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
                             }
                         }
-                        atomicAdd(p.se_sums + (size_t)b0 * p.cout + n_base + c0 + lane, t[0]);
+                        atomicAdd(p.se_sums + (size_t)b0 * p.cout + n_base + c0 + lane, (unsigned long long)t[0]);
                         vmask &= ~mm;
                     }
                 }

@@ -537,9 +537,9 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     }
     const int Cmax = m.archi == SKB_ARCHI_HALFRESNET34 ? 256 : 0;
     if (Cmax) {
-        if ((rc = h->sums.ensure((size_t)B * Cmax * sizeof(float)))) return rc;
+        if ((rc = h->sums.ensure((size_t)B * Cmax * sizeof(unsigned long long)))) return rc;
         if ((rc = h->scale.ensure((size_t)B * Cmax * sizeof(float)))) return rc;
-        SKB_CUDA_CHECK(cudaMemsetAsync(h->sums.p, 0, (size_t)B * Cmax * sizeof(float), st));
+        SKB_CUDA_CHECK(cudaMemsetAsync(h->sums.p, 0, (size_t)B * Cmax * sizeof(unsigned long long), st));
     }
     if ((rc = h->feats.ensure((size_t)pl.total_frames * m.fe.n_out * sizeof(float)))) return rc;
     const int D = m.pool_D;
@@ -559,7 +559,7 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
 
 // ----------------------------------------------------------------------------- conv launch helper
 static int run_conv(skb_xtractor* h, const ConvW& cw, const Level& Lin, const uint16_t* in, uint16_t* out, const Level& Lout,
-                    bool subsample, int act, bool conv3x3, const int* tdnn_shifts, float* se_sums, size_t row_h_override,
+                    bool subsample, int act, bool conv3x3, const int* tdnn_shifts, unsigned long long* se_sums, size_t row_h_override,
                     cudaStream_t st) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
@@ -682,13 +682,13 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
         const Level& L = pl.lv[level];
         uint16_t *y1 = buf(level, 2), *y2 = buf(level, 3), *scb = buf(level, 4), *nxt = buf(level, cur ^ 1);
         SKB_TRY(run_conv(h, bw.conv1, Lin, x, y1, L, bw.stride == 2, 1, true, nullptr, nullptr, 0, st));
-        SKB_TRY(run_conv(h, bw.conv2, L, y1, y2, L, false, 0, true, nullptr, (float*)h->sums.p, 0, st));
+        SKB_TRY(run_conv(h, bw.conv2, L, y1, y2, L, false, 0, true, nullptr, (unsigned long long*)h->sums.p, 0, st));
         const uint16_t* res = x;
         if (bw.has_sc) {
             SKB_TRY(run_conv(h, bw.sc, Lin, x, scb, L, bw.stride == 2, 0, false, nullptr, nullptr, 0, st));
             res = scb;
         }
-        SKB_TRY(launch_se_fc((float*)h->sums.p, d32 + L.o_utt_count, bw.se_w1, bw.se_w2, (float*)h->scale.p, B, bw.C, st));
+        SKB_TRY(launch_se_fc((unsigned long long*)h->sums.p, d32 + L.o_utt_count, bw.se_w1, bw.se_w2, (float*)h->scale.p, B, bw.C, st));
         SKB_TRY(launch_se_apply(m.bf16, y2, res, nxt, L.plane, (const float*)h->scale.p, bw.C, L.G, L.p_end, L.Wp, d32 + L.o_row_b, st));
         g_launches += 2;
         cur ^= 1;

@@ -76,16 +76,16 @@ int launch_stem(bool bf16, const float* feats, const long long* feat_off, const 
 // ----------------------------------------------------------------------------- SE: squeeze FCs
 // sidekit/nnet/res_net.py:272-281: scale = sigmoid(W2 relu(W1 mean)).  One CTA per utterance; consumes
 // (and re-zeroes) the per-(utterance, channel) sums produced by the conv2 epilogue.
-__global__ void se_fc_kernel(float* __restrict__ sums, const int* __restrict__ utt_count, const float* __restrict__ w1 /*[C/16][C]*/,
+__global__ void se_fc_kernel(unsigned long long* __restrict__ sums, const int* __restrict__ utt_count, const float* __restrict__ w1 /*[C/16][C]*/,
                              const float* __restrict__ w2 /*[C][C/16]*/, float* __restrict__ scale, int C) {
     __shared__ float mean[256];
     __shared__ float hid[16];
     const int b = blockIdx.x;
     const int R = C / 16;
-    const float inv = 1.f / (float)utt_count[b];
+    const double inv = 1.0 / (16777216.0 * (double)utt_count[b]);      // sums are 2^-24 fixed point
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        mean[c] = sums[(size_t)b * C + c] * inv;
-        sums[(size_t)b * C + c] = 0.f;
+        mean[c] = (float)((double)(long long)sums[(size_t)b * C + c] * inv);
+        sums[(size_t)b * C + c] = 0ull;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,7 +103,7 @@ __global__ void se_fc_kernel(float* __restrict__ sums, const int* __restrict__ u
     }
 }
 
-int launch_se_fc(float* sums, const int* utt_count, const float* w1, const float* w2, float* scale, int B, int C,
+int launch_se_fc(unsigned long long* sums, const int* utt_count, const float* w1, const float* w2, float* scale, int B, int C,
                  cudaStream_t st) {
     se_fc_kernel<<<B, 256, 0, st>>>(sums, utt_count, w1, w2, scale, C);
     SKB_CUDA_CHECK(cudaGetLastError());

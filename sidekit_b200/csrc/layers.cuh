@@ -20,7 +20,7 @@ struct FrontendConsts {
 int launch_stem(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float* w,
                 const float* bias, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
                 const int* row_b, const int* row_h, cudaStream_t st);
-int launch_se_fc(float* sums, const int* utt_count, const float* w1, const float* w2, float* scale, int B, int C,
+int launch_se_fc(unsigned long long* sums, const int* utt_count, const float* w1, const float* w2, float* scale, int B, int C,
                  cudaStream_t st);
 int launch_se_apply(bool bf16, const uint16_t* y, const uint16_t* sc, uint16_t* out, long long plane, const float* scale,
                     int C, int G, int p_end, int Wp, const int* row_b, cudaStream_t st);

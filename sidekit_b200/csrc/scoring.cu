@@ -1,0 +1,578 @@
+// Trial scoring on tcgen05: S = acc * (ra_i + ca_j + a0) + (r_i + q_j + c0),  acc = E . T^T.
+//
+// Covers cosine scoring (sidekit/iv_scoring.py:108-109), simplified PLDA (:451-462: model_part +
+// seg_part + cst + E Psi T^T, Psi folded into E on the host side), two-covariance scoring
+// (:192-205, expanded to the same form) and as-norm (sidekit/score_normalization.py:127-138).
+//
+// Operands are converted once to fp16 "chunk planes" [D/8][rows][8] (the no-swizzle K-major UMMA
+// layout, see conv_umma.cuh) after scaling each matrix by a power of two so its largest entry sits
+// near 2^9.  Single-pass mode multiplies the fp16 values; split mode also keeps lo = x - hi and
+// issues hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator, which restores fp32-class
+// accuracy (error ~ 2^-22 relative per product) at 3x the tensor work.  The mode is chosen ON THE
+// DEVICE from the operands' row norms (no host sync).
+//
+// Kernel: persistent CTAs, each owning a contiguous run of (row panel, column tile) pairs in
+// panel-major order.  The 128-row E panel stays resident in shared memory; 128-column T tiles stream
+// through a ring of 64-deep K chunks (1-D bulk copies); accumulators are double-buffered in TMEM so
+// the epilogue of tile i overlaps the MMAs of tile i+1.  The score matrix is HBM-write-bound
+// (128 FLOP per output byte at D = 256), so the epilogue stages each 32x32 block in a warp-private
+// shared buffer and writes full 128-byte row segments with bulk shared->global copies.
+#include "sidekit_b200.h"
+#include "common.cuh"
+#include "layers.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <vector>
+
+namespace skb {
+extern std::atomic<long long> g_launches;
+
+// ----------------------------------------------------------------------------- operand preparation
+// stats[0] = max |x| (as float bits), stats[1] = max row sum of squares (float bits)
+__global__ void absmax_kernel(const float* __restrict__ X, int rows, int D, unsigned* __restrict__ stats) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float mx = 0.f, ss = 0.f;
+    for (int k = lane; k < D; k += 32) {
+        const float v = X[(size_t)row * D + k];
+        mx = fmaxf(mx, fabsf(v));
+        ss = fmaf(v, v, ss);
+    }
+    mx = warp_max(mx);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+        atomicMax(stats, __float_as_uint(mx));          // non-negative floats order like their bit patterns
+        atomicMax(stats + 1, __float_as_uint(ss));
+    }
+}
+
+// ctrl[0] = scale exponent of E, ctrl[1] = of T, ctrl[2] = number of passes (1 or 3)
+__global__ void decide_kernel(const unsigned* statsE, const unsigned* statsT, int D, float abs_alpha, int passes_req, int* ctrl) {
+    const float mE = __uint_as_float(statsE[0]), mT = __uint_as_float(statsT[0]);
+    int eE = 0, eT = 0;
+    if (mE > 0.f) { int e; frexpf(mE, &e); eE = 10 - e; }      // mE * 2^eE in [2^9, 2^10)
+    if (mT > 0.f) { int e; frexpf(mT, &e); eT = 10 - e; }
+    ctrl[0] = eE;
+    ctrl[1] = eT;
+    int passes = passes_req;
+    if (passes == 0) {
+        // single-pass error estimate: fp16 rounding 2^-11 per operand, random-sign accumulation over D terms
+        const float nE = sqrtf(__uint_as_float(statsE[1])), nT = sqrtf(__uint_as_float(statsT[1]));
+        const float est = abs_alpha * 4.8828125e-4f * nE * nT * 4.f * rsqrtf((float)D);
+        passes = est < 2.5e-4f ? 1 : 3;
+    }
+    ctrl[2] = passes;
+}
+
+// X (rows, D) fp32 -> hi / lo fp16 planes [Dp/8][rows_pad][8]; rows >= `rows` and columns >= D are zero.
+__global__ void pack_split_kernel(const float* __restrict__ X, int rows, int rows_pad, int D, int Dp,
+                                  const int* __restrict__ ctrl, int which, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunks = Dp >> 3;
+    if (idx >= (long long)rows_pad * chunks) return;
+    const int row = (int)(idx % rows_pad), j = (int)(idx / rows_pad);
+    const float sc = ldexpf(1.f, ctrl[which]);
+    float h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = j * 8 + e;
+        const float v = (row < rows && k < D) ? X[(size_t)row * D + k] * sc : 0.f;
+        const float hv = __half2float(__float2half_rn(v));
+        h[e] = hv;
+        l[e] = v - hv;
+    }
+    uint4 oh, ol;
+    oh.x = pack2<false>(h[0], h[1]); oh.y = pack2<false>(h[2], h[3]); oh.z = pack2<false>(h[4], h[5]); oh.w = pack2<false>(h[6], h[7]);
+    ol.x = pack2<false>(l[0], l[1]); ol.y = pack2<false>(l[2], l[3]); ol.z = pack2<false>(l[4], l[5]); ol.w = pack2<false>(l[6], l[7]);
+    const size_t o = ((size_t)j * rows_pad + row) * 8;
+    *reinterpret_cast<uint4*>(hi + o) = oh;
+    *reinterpret_cast<uint4*>(lo + o) = ol;
+}
+
+// ----------------------------------------------------------------------------- the GEMM
+struct ScoreParams {
+    const uint16_t *Ehi, *Elo, *Thi, *Tlo;   // planes [Dp/8][rows_pad][8]
+    int Ne, Nt, Ne_pad, Nt_pad, Dp;
+    const int* ctrl;                          // scale exponents + passes (device)
+    const float *ra, *ca;                     // multiplicative row / column terms (may be null)
+    const float *r, *q;                       // additive row / column terms (may be null)
+    float a0, c0, rq_scale;                   // acc * (ra_i + ca_j + a0) * 2^-(eE+eT) + rq_scale * (r_i + q_j) + c0
+    int mul_scaled;                           // 1: ra / ca are also divided by the operand scales
+    void* out;
+    long long ld_out;
+    int out_f64;
+    int tiles_total, n_ntiles;
+};
+
+constexpr int kScThreads = 6 * 32;       // warps: 0 producer, 1 MMA, 2..5 epilogue
+constexpr int kScKChunk = 64;
+constexpr int kScBStageBytes = 128 * kScKChunk * 2;      // hi part of one stage (16 KB)
+
+// smem: [ctrl 256 B][A hi (+lo)][B ring][staging 4 warps x 32 x (32 x 8 + 16) B]
+template <int PASSES>
+struct ScoreSmem {
+    static constexpr int kBStages = PASSES == 1 ? 4 : 2;
+    static constexpr int kParts = PASSES == 1 ? 1 : 2;
+    static constexpr int kStageRowBytes = 32 * 8 + 16;   // fp64 worst case + 16 B pad (bank spread)
+    static size_t a_bytes(int Dp) { return (size_t)kParts * 128 * Dp * 2; }
+    static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kParts * kScBStageBytes + 4 * 32 * kStageRowBytes; }
+};
+
+template <int PASSES>
+__global__ void __launch_bounds__(kScThreads) score_gemm_kernel(const ScoreParams p) {
+    using SM = ScoreSmem<PASSES>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* a_empty = a_full + 1;
+    uint64_t* b_full = a_empty + 1;                 // [kBStages]
+    uint64_t* b_empty = b_full + SM::kBStages;      // [kBStages]
+    uint64_t* acc_full = b_empty + SM::kBStages;    // [2]
+    uint64_t* acc_empty = acc_full + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint8_t* a_smem = smem + 256;
+    const uint32_t a_part = 128 * p.Dp * 2;
+    uint8_t* b_smem = a_smem + SM::kParts * a_part;
+    uint8_t* stage_smem = b_smem + SM::kBStages * SM::kParts * kScBStageBytes;
+
+    if (p.ctrl[2] != PASSES) return;   // the other instantiation handles this launch (uniform across the grid)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // contiguous run of tiles for this CTA
+    const long long t_begin = (long long)p.tiles_total * blockIdx.x / gridDim.x;
+    const long long t_end = (long long)p.tiles_total * (blockIdx.x + 1) / gridDim.x;
+    const int n_kc = p.Dp / kScKChunk;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int i = 0; i < SM::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int cur_panel = -1, n_panels = 0;
+            long long it = 0;
+            for (long long t = t_begin; t < t_end; ++t) {
+                const int panel = (int)(t / p.n_ntiles), nt = (int)(t % p.n_ntiles);
+                if (panel != cur_panel) {
+                    mbar_wait(a_empty, (n_panels & 1) ^ 1);
+                    mbar_arrive_expect_tx(a_full, SM::kParts * a_part);
+                    for (int part = 0; part < SM::kParts; ++part) {
+                        const uint16_t* src = part == 0 ? p.Ehi : p.Elo;
+                        for (int j = 0; j < p.Dp / 8; ++j)
+                            bulk_g2s(a_smem + part * a_part + j * 2048, src + ((size_t)j * p.Ne_pad + (size_t)panel * 128) * 8, 2048, a_full);
+                    }
+                    cur_panel = panel;
+                    n_panels++;
+                }
+                for (int kc = 0; kc < n_kc; ++kc, ++it) {
+                    const int s = (int)(it % SM::kBStages);
+                    mbar_wait(&b_empty[s], (uint32_t)((it / SM::kBStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&b_full[s], SM::kParts * kScBStageBytes);
+                    for (int part = 0; part < SM::kParts; ++part) {
+                        const uint16_t* src = part == 0 ? p.Thi : p.Tlo;
+                        uint8_t* dst = b_smem + (s * SM::kParts + part) * kScBStageBytes;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            bulk_g2s(dst + j * 2048, src + ((size_t)(kc * 8 + j) * p.Nt_pad + (size_t)nt * 128) * 8, 2048, &b_full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, 128, false);
+            int cur_panel = -1, n_panels = 0;
+            long long it = 0, nt_done = 0;
+            for (long long t = t_begin; t < t_end; ++t, ++nt_done) {
+                const int panel = (int)(t / p.n_ntiles);
+                if (panel != cur_panel) {
+                    mbar_wait(a_full, n_panels & 1);
+                    cur_panel = panel;
+                    n_panels++;
+                }
+                const int buf = (int)(nt_done & 1);
+                mbar_wait(&acc_empty[buf], (uint32_t)((nt_done >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 128;
+                for (int kc = 0; kc < n_kc; ++kc, ++it) {
+                    const int s = (int)(it % SM::kBStages);
+                    mbar_wait(&b_full[s], (uint32_t)((it / SM::kBStages) & 1));
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_u32(b_smem + (s * SM::kParts) * kScBStageBytes);
+                    const uint32_t a_hi = smem_u32(a_smem) + kc * 8 * 2048;
+#pragma unroll
+                    for (int combo = 0; combo < (PASSES == 1 ? 1 : 3); ++combo) {
+                        // combo 0: hi*hi, 1: hi*lo, 2: lo*hi
+                        const uint32_t a_b = a_hi + (combo == 2 ? a_part : 0);
+                        const uint32_t b_b = b_hi + (combo == 1 ? kScBStageBytes : 0);
+#pragma unroll
+                        for (int ks = 0; ks < kScKChunk / 16; ++ks) {
+                            const uint64_t ad = umma_desc_kmajor_noswz(a_b + ks * 2 * 2048, 2048, 128);
+                            const uint64_t bd = umma_desc_kmajor_noswz(b_b + ks * 2 * 2048, 2048, 128);
+                            umma_f16(d_tmem, ad, bd, idesc, (kc > 0 || combo > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&b_empty[s]);
+                }
+                umma_commit(&acc_full[buf]);
+                const bool last_of_panel = (t + 1 == t_end) || ((int)((t + 1) / p.n_ntiles) != panel);
+                if (last_of_panel) umma_commit(a_empty);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        uint8_t* stg = stage_smem + q * 32 * SM::kStageRowBytes;
+        const float inv_scale = ldexpf(1.f, -(p.ctrl[0] + p.ctrl[1]));
+        const float a0 = p.a0 * inv_scale;
+        const float mscale = p.mul_scaled ? inv_scale : 1.f;
+        const int esize = p.out_f64 ? 8 : 4;
+        const bool bulk_ok = ((p.ld_out * esize) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+        long long nt_done = 0;
+        for (long long t = t_begin; t < t_end; ++t, ++nt_done) {
+            const int panel = (int)(t / p.n_ntiles), nt = (int)(t % p.n_ntiles);
+            const int buf = (int)(nt_done & 1);
+            mbar_wait(&acc_full[buf], (uint32_t)((nt_done >> 1) & 1));
+            tc_fence_after();
+            const int row = panel * 128 + q * 32 + lane;
+            const bool row_ok = row < p.Ne;
+            const float ra = (p.ra && row_ok) ? p.ra[row] * mscale : 0.f;
+            const float rr = (p.r && row_ok) ? p.r[row] : 0.f;
+#pragma unroll 1
+            for (int cb = 0; cb < 4; ++cb) {
+                const int col0 = nt * 128 + cb * 32;
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + cb * 32, v);
+                if (cb == 3) {   // accumulator fully read: hand the TMEM buffer back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                if (col0 >= p.Nt) continue;
+                // previous bulk stores of this warp must have finished READING the staging buffer
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                uint8_t* myrow = stg + lane * SM::kStageRowBytes;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int col = col0 + i;
+                    const float ca = (p.ca && col < p.Nt) ? __ldg(p.ca + col) * mscale : 0.f;
+                    const float qq = (p.q && col < p.Nt) ? __ldg(p.q + col) : 0.f;
+                    const float s = fmaf(v[i], ra + ca + a0, fmaf(rr + qq, p.rq_scale, p.c0));
+                    if (p.out_f64) reinterpret_cast<double*>(myrow)[i] = (double)s;
+                    else reinterpret_cast<float*>(myrow)[i] = s;
+                }
+                const int ncols = min(32, p.Nt - col0);
+                if (row_ok) {
+                    uint8_t* gdst = reinterpret_cast<uint8_t*>(p.out) + ((size_t)row * p.ld_out + col0) * esize;
+                    if (bulk_ok && ncols == 32) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(myrow)),
+                                     "r"(32 * esize)
+                                     : "memory");
+                    } else {
+                        for (int i = 0; i < ncols; ++i) {
+                            if (p.out_f64) reinterpret_cast<double*>(gdst)[i] = reinterpret_cast<double*>(myrow)[i];
+                            else reinterpret_cast<float*>(gdst)[i] = reinterpret_cast<float*>(myrow)[i];
+                        }
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// ----------------------------------------------------------------------------- workspace + launch
+struct ScoreWorkspace {
+    uint16_t* planes = nullptr;
+    size_t planes_cap = 0;
+    unsigned* stats = nullptr;   // [4]
+    int* ctrl = nullptr;         // [4]
+    float* tmp = nullptr;        // scratch score matrix (as-norm cohort scores)
+    size_t tmp_cap = 0;
+};
+static thread_local ScoreWorkspace g_ws;
+
+static int ws_ensure(size_t plane_bytes, size_t tmp_bytes) {
+    if (!g_ws.stats) {
+        SKB_CUDA_CHECK(cudaMalloc(&g_ws.stats, 4 * sizeof(unsigned)));
+        SKB_CUDA_CHECK(cudaMalloc(&g_ws.ctrl, 4 * sizeof(int)));
+    }
+    if (plane_bytes > g_ws.planes_cap) {
+        if (g_ws.planes) cudaFree(g_ws.planes);
+        g_ws.planes = nullptr; g_ws.planes_cap = 0;
+        SKB_CUDA_CHECK(cudaMalloc(&g_ws.planes, plane_bytes));
+        g_ws.planes_cap = plane_bytes;
+    }
+    if (tmp_bytes > g_ws.tmp_cap) {
+        if (g_ws.tmp) cudaFree(g_ws.tmp);
+        g_ws.tmp = nullptr; g_ws.tmp_cap = 0;
+        SKB_CUDA_CHECK(cudaMalloc(&g_ws.tmp, tmp_bytes));
+        g_ws.tmp_cap = tmp_bytes;
+    }
+    return SKB_OK;
+}
+
+// out = acc * (ra_i + ca_j + a0) + (r_i + q_j + c0)
+static int score_gemm_general(const float* E, const float* T, int Ne, int Nt, int D, const float* ra, const float* ca, float a0,
+                              const float* r, const float* q, float c0, float rq_scale, float abs_alpha_for_auto, int passes, int out_f64,
+                              void* out, long long ld_out, size_t tmp_bytes, cudaStream_t st) {
+    if (!E || !T || !out || Ne <= 0 || Nt <= 0 || D <= 0 || ld_out < Nt || (passes != 0 && passes != 1 && passes != 3)) {
+        set_last_error(__FILE__, __LINE__, "score_gemm: bad arguments");
+        return SKB_ERR_ARG;
+    }
+    const int Dp = (D + kScKChunk - 1) / kScKChunk * kScKChunk;
+    if (Dp > 384) {
+        set_last_error(__FILE__, __LINE__, "score_gemm: embedding dimension > 384 not supported by the resident-panel kernel");
+        return SKB_ERR_ARG;
+    }
+    const int Ne_pad = (Ne + 127) / 128 * 128, Nt_pad = (Nt + 127) / 128 * 128;
+    const size_t eb = (size_t)Dp * Ne_pad * 2, tb = (size_t)Dp * Nt_pad * 2;
+    int rc = ws_ensure(2 * (eb + tb), tmp_bytes);
+    if (rc) return rc;
+    uint16_t* Ehi = g_ws.planes;
+    uint16_t* Elo = Ehi + eb / 2;
+    uint16_t* Thi = Elo + eb / 2;
+    uint16_t* Tlo = Thi + tb / 2;
+    SKB_CUDA_CHECK(cudaMemsetAsync(g_ws.stats, 0, 4 * sizeof(unsigned), st));
+    absmax_kernel<<<(Ne + 7) / 8, 256, 0, st>>>(E, Ne, D, g_ws.stats);
+    absmax_kernel<<<(Nt + 7) / 8, 256, 0, st>>>(T, Nt, D, g_ws.stats + 2);
+    decide_kernel<<<1, 1, 0, st>>>(g_ws.stats, g_ws.stats + 2, D, abs_alpha_for_auto, passes, g_ws.ctrl);
+    {
+        const long long n = (long long)Ne_pad * (Dp / 8);
+        pack_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, Ne, Ne_pad, D, Dp, g_ws.ctrl, 0, Ehi, Elo);
+    }
+    {
+        const long long n = (long long)Nt_pad * (Dp / 8);
+        pack_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T, Nt, Nt_pad, D, Dp, g_ws.ctrl, 1, Thi, Tlo);
+    }
+    SKB_CUDA_CHECK(cudaGetLastError());
+    ScoreParams p;
+    p.Ehi = Ehi; p.Elo = Elo; p.Thi = Thi; p.Tlo = Tlo;
+    p.Ne = Ne; p.Nt = Nt; p.Ne_pad = Ne_pad; p.Nt_pad = Nt_pad; p.Dp = Dp;
+    p.ctrl = g_ws.ctrl; p.ra = ra; p.ca = ca; p.r = r; p.q = q; p.a0 = a0; p.c0 = c0; p.rq_scale = rq_scale;
+    p.mul_scaled = 1;
+    p.out = out; p.ld_out = ld_out; p.out_f64 = out_f64;
+    p.n_ntiles = Nt_pad / 128;
+    p.tiles_total = (Ne_pad / 128) * p.n_ntiles;
+    const int grid = std::min(p.tiles_total, kNumSMs);
+    static bool configured = false;
+    if (!configured) {
+        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    // both variants are launched; exactly one does the work (decided on the device, no host sync)
+    if (passes != 3) score_gemm_kernel<1><<<grid, kScThreads, ScoreSmem<1>::total(Dp), st>>>(p);
+    if (passes != 1) {
+        if (ScoreSmem<3>::total(Dp) > 227 * 1024) {
+            set_last_error(__FILE__, __LINE__, "score_gemm: split mode needs D <= 256");
+            return SKB_ERR_ARG;
+        }
+        score_gemm_kernel<3><<<grid, kScThreads, ScoreSmem<3>::total(Dp), st>>>(p);
+    }
+    SKB_CUDA_CHECK(cudaGetLastError());
+    g_launches += 6 + (passes == 0 ? 1 : 0);
+    return SKB_OK;
+}
+
+// ----------------------------------------------------------------------------- as-norm: top-k statistics per row
+__device__ __forceinline__ unsigned f2key(float f) {   // order-preserving float -> uint
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+    const unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+// One CTA per row: radix-select the k-th largest score, then mean and unbiased std of the top k
+// (torch.topk + mean + std, sidekit/score_normalization.py:131-133).  Ties at the threshold are
+// counted exactly k - (#greater) times, like a sort would.
+__global__ void __launch_bounds__(256) topk_stats_kernel(const float* __restrict__ S, int C, long long ld, int k,
+                                                         float* __restrict__ mean_out, float* __restrict__ std_out) {
+    extern __shared__ unsigned keys[];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned sel_prefix, sel_remaining;
+    __shared__ double red[2][8];
+    const float* row = S + (size_t)blockIdx.x * ld;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) keys[i] = f2key(row[i]);
+    if (threadIdx.x == 0) { sel_prefix = 0; sel_remaining = k; }
+    __syncthreads();
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned prefix = sel_prefix;
+        const unsigned mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            const unsigned key = keys[i];
+            if ((key & mask) == (prefix & mask)) atomicAdd(&hist[(key >> shift) & 255], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned rem = sel_remaining;
+            int b = 255;
+            for (; b > 0; --b) {
+                if (hist[b] >= rem) break;
+                rem -= hist[b];
+            }
+            sel_prefix = prefix | ((unsigned)b << shift);
+            sel_remaining = rem;          // how many of the keys equal to the final threshold are taken
+        }
+        __syncthreads();
+    }
+    const unsigned thr = sel_prefix;
+    const unsigned n_thr = sel_remaining;
+    const float thr_f = key2f(thr);
+    // pass 1: mean
+    double s = 0.0;
+    for (int i = threadIdx.x; i < C; i += blockDim.x)
+        if (keys[i] > thr) s += (double)key2f(keys[i]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s;
+    __syncthreads();
+    double tot = 0.0;
+    for (int i = 0; i < 8; ++i) tot += red[0][i];
+    const double mean = (tot + (double)n_thr * thr_f) / k;
+    double v = 0.0;
+    for (int i = threadIdx.x; i < C; i += blockDim.x)
+        if (keys[i] > thr) {
+            const double d = (double)key2f(keys[i]) - mean;
+            v += d * d;
+        }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[1][threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double vt = 0.0;
+        for (int i = 0; i < 8; ++i) vt += red[1][i];
+        const double d = (double)thr_f - mean;
+        vt += (double)n_thr * d * d;
+        mean_out[blockIdx.x] = (float)mean;
+        std_out[blockIdx.x] = (float)sqrt(vt / (k - 1));
+    }
+}
+
+// ra_i = 0.5 / std_i,  r_i = -0.5 * mean_i / std_i   (the symmetric as-norm as acc*(ra_i+ra_j) + (r_i+r_j))
+__global__ void asnorm_terms_kernel(const float* mean, const float* sd, int N, float* ra, float* r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    ra[i] = 0.5f / sd[i];
+    r[i] = -0.5f * mean[i] / sd[i];
+}
+
+// x - mu (row-wise); rowterm_i = 0.5 * sum_j tmp[i][j] * xc[i][j]
+__global__ void center_kernel(const float* __restrict__ X, const float* __restrict__ mu, int N, int D, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * D) return;
+    out[i] = X[i] - (mu ? mu[i % D] : 0.f);
+}
+__global__ void half_rowdot_kernel(const float* __restrict__ A, const float* __restrict__ B, int N, int D, float* __restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int k = lane; k < D; k += 32) s = fmaf(A[(size_t)row * D + k], B[(size_t)row * D + k], s);
+    s = warp_sum(s);
+    if (lane == 0) out[row] = 0.5f * s;
+}
+
+}  // namespace skb
+
+using namespace skb;
+
+extern "C" {
+
+int skb_quadratic_prepare(const float* X_dev, const float* mu_dev, const float* PsiT_dev, const float* Phi_dev, int N, int D,
+                          float* Xout_dev, float* rowterm_dev, void* stream) {
+    if (!X_dev || !Phi_dev || !Xout_dev || !rowterm_dev || N <= 0 || D <= 0) {
+        set_last_error(__FILE__, __LINE__, "quadratic_prepare: bad arguments");
+        return SKB_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nd = (size_t)N * D;
+    int rc = ws_ensure(0, 2 * nd * sizeof(float));
+    if (rc) return rc;
+    float* xc = g_ws.tmp;
+    float* tmp = g_ws.tmp + nd;
+    center_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, st>>>(X_dev, mu_dev, N, D, xc);
+    // tmp = xc . Phi  (Phi symmetric, so rows of Phi serve as the K-major "T" operand)
+    rc = score_gemm_general(xc, Phi_dev, N, D, D, nullptr, nullptr, 1.f, nullptr, nullptr, 0.f, 1.f, 1.f, 3, 0, tmp, D,
+                            2 * nd * sizeof(float), st);
+    if (rc) return rc;
+    half_rowdot_kernel<<<(N + 7) / 8, 256, 0, st>>>(tmp, xc, N, D, rowterm_dev);
+    if (PsiT_dev) {
+        rc = score_gemm_general(xc, PsiT_dev, N, D, D, nullptr, nullptr, 1.f, nullptr, nullptr, 0.f, 1.f, 1.f, 3, 0, Xout_dev, D,
+                                2 * nd * sizeof(float), st);
+        if (rc) return rc;
+    } else {
+        SKB_CUDA_CHECK(cudaMemcpyAsync(Xout_dev, xc, nd * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    g_launches += 2;
+    SKB_CUDA_CHECK(cudaGetLastError());
+    return SKB_OK;
+}
+
+int skb_score_gemm(const float* E_dev, const float* T_dev, int Ne, int Nt, int D, const float* rowterm_dev,
+                   const float* colterm_dev, double cst, double alpha, int passes, int out_dtype, void* out_dev,
+                   int64_t ld_out, void* stream) {
+    return score_gemm_general(E_dev, T_dev, Ne, Nt, D, nullptr, nullptr, (float)alpha, rowterm_dev, colterm_dev,
+                              (float)(alpha * cst), (float)alpha, (float)fabs(alpha), passes, out_dtype, out_dev, ld_out, 0,
+                              (cudaStream_t)stream);
+}
+
+int skb_asnorm_stats(const float* X_dev, const float* cohort_dev, int N, int C, int D, int top_k, float* mean_dev,
+                     float* std_dev, void* stream) {
+    if (top_k < 2 || C < top_k || C * sizeof(unsigned) > 200 * 1024) {
+        set_last_error(__FILE__, __LINE__, "asnorm_stats: need 2 <= top_k <= C <= 51200");
+        return SKB_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ld = (C + 3) / 4 * 4;
+    const size_t tmp_bytes = (size_t)N * ld * sizeof(float);
+    int rc = ws_ensure(0, tmp_bytes);
+    if (rc) return rc;
+    rc = score_gemm_general(X_dev, cohort_dev, N, C, D, nullptr, nullptr, 1.f, nullptr, nullptr, 0.f, 1.f, 1.f, 3, 0, g_ws.tmp, ld,
+                            tmp_bytes, st);
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+        SKB_CUDA_CHECK(cudaFuncSetAttribute(topk_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    topk_stats_kernel<<<N, 256, C * sizeof(unsigned), st>>>(g_ws.tmp, C, ld, top_k, mean_dev, std_dev);
+    g_launches++;
+    SKB_CUDA_CHECK(cudaGetLastError());
+    return SKB_OK;
+}
+
+int skb_asnorm_apply(const float* X_dev, int N, int D, const float* mean_dev, const float* std_dev, float* out_dev,
+                     void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t tmp_bytes = (size_t)2 * N * sizeof(float);
+    int rc = ws_ensure(0, tmp_bytes);
+    if (rc) return rc;
+    float* ra = g_ws.tmp;
+    float* r = ra + N;
+    asnorm_terms_kernel<<<(N + 255) / 256, 256, 0, st>>>(mean_dev, std_dev, N, ra, r);
+    g_launches++;
+    return score_gemm_general(X_dev, X_dev, N, N, D, ra, ra, 0.f, r, r, 0.f, 1.f, 30.f, 3, 0, out_dev, N, tmp_bytes, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+"""Trial scoring with the reference's signatures and return objects (sidekit/iv_scoring.py:52-113 cosine,
+:159-212 two-covariance, :215-269 PLDA dispatcher, :370-477 fast PLDA).
+
+Host side (numpy, like the reference): id matching -- an O(N) hash join instead of the reference's O(N^2)
+``item in ndarray`` scans, with identical ordering semantics (rows follow ``ndx.modelset`` restricted to the
+enrolled ids, first occurrence wins, every occurrence in the ndx kept) -- and the D x D PLDA algebra.  Device
+side (CUDA, csrc/scoring.cu): centring, the Psi / Phi folds, the quadratic row / column terms and the
+Ne x Nt score matrix.  The result stays on the device until ``Scores.scoremat`` is read.
+"""
+import copy
+import logging
+
+import numpy
+import scipy.linalg
+import torch
+
+from . import _lib
+from .bosaris import Ndx, Scores
+from .statserver import StatServer
+
+
+def _check_missing_model(enroll, test, ndx):
+    """iv_scoring.py:52-60."""
+    clean_ndx = ndx.filter(enroll.modelset, test.segset, True)
+    enroll.align_models(clean_ndx.modelset)
+    test.align_segments(clean_ndx.segset)
+    return clean_ndx
+
+
+def _device(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("sidekit_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _dev32(a, device):
+    return torch.as_tensor(numpy.ascontiguousarray(a, dtype=numpy.float32)).to(device, non_blocking=True)
+
+
+def score_matrix(E, T, rowterm=None, colterm=None, cst=0.0, alpha=1.0, passes=0, out_dtype=torch.float32, out=None):
+    """S = alpha*(rowterm_i + colterm_j + cst) + alpha * E T^T on the device (all arguments torch CUDA fp32)."""
+    Ne, D = E.shape
+    Nt = T.shape[0]
+    if out is None:
+        out = torch.empty((Ne, Nt), dtype=out_dtype, device=E.device)
+    with torch.cuda.device(E.device):
+        _lib.check(_lib.lib().skb_score_gemm(
+            E.data_ptr(), T.data_ptr(), Ne, Nt, D, None if rowterm is None else rowterm.data_ptr(),
+            None if colterm is None else colterm.data_ptr(), float(cst), float(alpha), int(passes),
+            1 if out.dtype == torch.float64 else 0, out.data_ptr(), out.stride(0), _lib.stream_ptr()))
+    return out
+
+
+def _quadratic_prepare(X, mu, Psi, Phi):
+    """xc = X - mu; returns (xc . Psi, 0.5 * diag(xc Phi xc^T)) on the device."""
+    N, D = X.shape
+    Xout = torch.empty_like(X)
+    rowterm = torch.empty((N,), dtype=torch.float32, device=X.device)
+    psi_t = None if Psi is None else _dev32(numpy.asarray(Psi).T, X.device)
+    phi = _dev32(Phi, X.device)
+    mu_d = None if mu is None else _dev32(mu, X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.lib().skb_quadratic_prepare(X.data_ptr(), None if mu_d is None else mu_d.data_ptr(),
+                                                    None if psi_t is None else psi_t.data_ptr(), phi.data_ptr(), N, D,
+                                                    Xout.data_ptr(), rowterm.data_ptr(), _lib.stream_ptr()))
+    return Xout, rowterm
+
+
+def _finish(clean_ndx, mat_dev):
+    score = Scores()
+    score.modelset = clean_ndx.modelset
+    score.segset = clean_ndx.segset
+    score.scoremask = clean_ndx.trialmask
+    score.scoremat_device = mat_dev
+    score.scoremat = None           # materialised lazily from the device tensor
+    return score
+
+
+def cosine_scoring(enroll, test, ndx, wccn=None, check_missing=True, device=None):
+    """Cosine similarities for the trials of ``ndx`` (iv_scoring.py:63-113); ``scoremat`` is float32."""
+    assert isinstance(enroll, StatServer), 'First parameter should be a StatServer'
+    assert isinstance(test, StatServer), 'Second parameter should be a StatServer'
+    assert isinstance(ndx, Ndx), 'Third parameter should be an Ndx'
+    enroll_copy = copy.deepcopy(enroll)
+    test_copy = copy.deepcopy(test)
+    clean_ndx = _check_missing_model(enroll_copy, test_copy, ndx) if check_missing else ndx
+    if wccn is not None:
+        enroll_copy.rotate_stat1(wccn)
+        test_copy.rotate_stat1(wccn)
+    enroll_copy.norm_stat1()
+    test_copy.norm_stat1()
+    dev = _device(device)
+    E, T = _dev32(enroll_copy.stat1, dev), _dev32(test_copy.stat1, dev)
+    # the reference multiplies fp32 operands (torch.einsum on FloatTensors): split mode keeps fp32-class accuracy
+    return _finish(clean_ndx, score_matrix(E, T, passes=3))
+
+
+def fast_PLDA_scoring(enroll, test, ndx, mu, F, Sigma, test_uncertainty=None, Vtrans=None, p_known=0.0,
+                      scaling_factor=1., check_missing=True):
+    """Simplified PLDA log-likelihood ratios (iv_scoring.py:370-477); ``scoremat`` is float64 like the reference."""
+    enroll_ctr = copy.deepcopy(enroll)
+    test_ctr = copy.deepcopy(test)
+    if not numpy.unique(enroll_ctr.modelset).shape == enroll_ctr.modelset.shape:
+        logging.warning("Enrollment models are not unique, average i-vectors")
+        enroll_ctr = enroll_ctr.mean_stat_per_model()
+    clean_ndx = _check_missing_model(enroll_ctr, test_ctr, ndx) if check_missing else ndx
+    if not numpy.unique(enroll_ctr.modelset).shape == enroll_ctr.modelset.shape:
+        # the reference averages a second time after alignment (:422-425); see oracle/scoring_ref.py
+        logging.warning("Enrollment models are not unique, average i-vectors")
+        enroll_ctr = enroll_ctr.mean_stat_per_model()
+
+    # D x D algebra on the host in float64, exactly as the reference (:429-448)
+    invSigma = scipy.linalg.inv(Sigma)
+    I_spk = numpy.eye(F.shape[1], dtype='float')
+    K = F.T.dot(invSigma * scaling_factor).dot(F)
+    K1 = scipy.linalg.inv(K + I_spk)
+    K2 = scipy.linalg.inv(2 * K + I_spk)
+    alpha1 = numpy.linalg.slogdet(K1)[1]
+    alpha2 = numpy.linalg.slogdet(K2)[1]
+    plda_cst = alpha2 / 2.0 - alpha1
+    Sigma_ac = numpy.dot(F, F.T)
+    Sigma_tot = Sigma_ac + Sigma
+    Sigma_tot_inv = scipy.linalg.inv(Sigma_tot)
+    Tmp = numpy.linalg.inv(Sigma_tot - Sigma_ac.dot(Sigma_tot_inv).dot(Sigma_ac))
+    Phi = Sigma_tot_inv - Tmp
+    Psi = Sigma_tot_inv.dot(Sigma_ac).dot(Tmp)
+
+    dev = _device()
+    E, T = _dev32(enroll_ctr.stat1, dev), _dev32(test_ctr.stat1, dev)
+    Ep, model_part = _quadratic_prepare(E, mu, Psi, Phi)           # (E - mu) Psi ; 0.5 diag((E-mu) Phi (E-mu)^T)
+    Tc, seg_part = _quadratic_prepare(T, mu, None, Phi)
+    S = score_matrix(Ep, Tc, model_part, seg_part, cst=plda_cst, alpha=scaling_factor, passes=0, out_dtype=torch.float64)
+    if p_known != 0:
+        # open-set correction (:467-475), vectorised: sum_{k != i} exp(S_kj) = colsum_j - exp(S_ij)
+        N = S.shape[0]
+        tmp = torch.exp(S)
+        S = S - torch.log(p_known * (tmp.sum(dim=0, keepdim=True) - tmp) / (N - 1) + (1 - p_known))
+    return _finish(clean_ndx, S)
+
+
+def PLDA_scoring(enroll, test, ndx, mu, F, G, Sigma, test_uncertainty=None, Vtrans=None, p_known=0.0,
+                 scaling_factor=1., full_model=False):
+    """PLDA dispatcher (iv_scoring.py:215-269)."""
+    assert isinstance(enroll, StatServer), 'First parameter should be a StatServer'
+    assert isinstance(test, StatServer), 'Second parameter should be a StatServer'
+    assert isinstance(ndx, Ndx), 'Third parameter should be an Ndx'
+    assert enroll.stat1.shape[1] == test.stat1.shape[1], 'I-vectors dimension mismatch'
+    assert enroll.stat1.shape[1] == F.shape[0], 'I-vectors and co-variance matrix dimension mismatch'
+    assert enroll.stat1.shape[1] == G.shape[0], 'I-vectors and co-variance matrix dimension mismatch'
+    if not full_model:
+        return fast_PLDA_scoring(enroll, test, ndx, mu, F, Sigma, test_uncertainty, Vtrans, p_known=p_known,
+                                 scaling_factor=scaling_factor, check_missing=True)
+    raise NotImplementedError("full_PLDA_scoring (G != 0) is outside the hot path (SURVEY.md 8f rank 4)")
+
+
+def two_covariance_scoring(enroll, test, ndx, W, B, check_missing=True):
+    """Two-covariance scores (iv_scoring.py:159-212).  Like the reference it works on the caller's objects:
+    ``enroll`` / ``test`` are aligned (reordered / shrunk) in place."""
+    assert isinstance(enroll, StatServer), 'First parameter should be a directory'
+    assert isinstance(test, StatServer), 'Second parameter should be a StatServer'
+    assert isinstance(ndx, Ndx), 'Third parameter should be an Ndx'
+    assert enroll.stat1.shape[1] == test.stat1.shape[1], 'I-vectors dimension mismatch'
+    assert enroll.stat1.shape[1] == W.shape[0], 'I-vectors and co-variance matrix dimension mismatch'
+    assert enroll.stat1.shape[1] == B.shape[0], 'I-vectors and co-variance matrix dimension mismatch'
+    if not numpy.unique(enroll.modelset).shape == enroll.modelset.shape:
+        logging.warning("Enrollment models are not unique, average i-vectors")
+        enroll = enroll.mean_stat_per_model()
+    clean_ndx = _check_missing_model(enroll, test, ndx) if check_missing else ndx
+    iW = scipy.linalg.inv(W)
+    iB = scipy.linalg.inv(B)
+    G = iW @ scipy.linalg.inv(iB + 2 * iW) @ iW
+    H = iW @ scipy.linalg.inv(iB + iW) @ iW
+    # (e+t)' G (e+t) - t' H t - e' H e  =  e'(G-H)e + t'(G-H)t + 2 e' G t
+    dev = _device()
+    E, T = _dev32(enroll.stat1, dev), _dev32(test.stat1, dev)
+    Ep, model_part = _quadratic_prepare(E, None, 2.0 * G, 2.0 * (G - H))
+    Tc, seg_part = _quadratic_prepare(T, None, None, 2.0 * (G - H))
+    S = score_matrix(Ep, Tc, model_part, seg_part, passes=0, out_dtype=torch.float64)
+    return _finish(clean_ndx, S)

@@ -166,6 +166,8 @@ class Xtractor(torch.nn.Module):
         if self.loss == "cce":
             want_logits = False
         on_cpu = not flat.is_cuda
+        if not torch.cuda.is_available():
+            raise RuntimeError("sidekit_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         device = torch.device("cuda", torch.cuda.current_device()) if on_cpu else flat.device
         h = self._handle(device)
         lens = _lib.i64_array(lengths)

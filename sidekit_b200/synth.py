@@ -22,11 +22,15 @@ def _gen(key, seed):
     return g
 
 
-def fill_state_dict(state_dict, seed=0):
+def fill_state_dict(state_dict, seed=0, init="default"):
     """Overwrite every learnable tensor / BN statistic of ``state_dict`` in place.
 
     Front-end buffers (window, mel filterbank, DCT, pre-emphasis filter) are
-    left untouched: they are constants of the architecture.
+    left untouched: they are constants of the architecture.  ``init='default'``
+    draws conv / linear weights from torch's default-initialisation distribution
+    (what a freshly constructed reference model has); ``init='he'`` is a stress
+    variant (He-normal, 6x the variance) whose residual branches dominate, so a
+    wrong convolution or a precision loss shows up much more strongly.
     """
     for key in sorted(state_dict.keys()):
         t = state_dict[key]
@@ -42,11 +46,17 @@ def fill_state_dict(state_dict, seed=0):
             v = torch.rand(shape, generator=g) * 0.4 + 0.8
         elif t.dim() == 1:                       # biases (conv / linear / BN)
             v = torch.randn(shape, generator=g) * 0.1
-        else:                                    # conv / linear weights: He-style fan-in scaling
+        else:
+            # conv / linear weights: U(-1/sqrt(fan_in), 1/sqrt(fan_in)), the distribution torch's default
+            # reset_parameters() (kaiming_uniform_, a=sqrt(5)) gives the reference's freshly built modules
             fan_in = 1
             for d in shape[1:]:
                 fan_in *= d
-            v = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+            if init == "he":
+                v = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+            else:
+                bound = 1.0 / math.sqrt(fan_in)
+                v = (torch.rand(shape, generator=g) * 2.0 - 1.0) * bound
         t.copy_(v.to(t.dtype))
     return state_dict
 

@@ -1,0 +1,133 @@
+"""GPU parity of the scoring path (through the C ABI) against the oracle, the KAT and the golden fixtures.
+Scores within 1e-3 absolute; modelset / segset / scoremask bit-exact (BASELINE.json north_star)."""
+import copy
+
+import numpy
+import pytest
+import torch
+
+import sidekit_b200 as sk
+from oracle import scoring_ref as S
+from sidekit_b200 import synth
+from tests import kat
+from tests.helpers import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _ss(ids, X):
+    return sk.StatServer.from_embeddings(numpy.asarray(ids), X)
+
+
+def _ndx(models, segs, mask):
+    n = sk.Ndx()
+    n.modelset, n.segset, n.trialmask = numpy.asarray(models), numpy.asarray(segs), numpy.asarray(mask)
+    return n
+
+
+def _check(score, ref, tol, dtype):
+    assert numpy.array_equal(score.modelset, ref[0]) and numpy.array_equal(score.segset, ref[1])
+    assert numpy.array_equal(score.scoremask, ref[2])
+    assert score.scoremat.dtype == dtype
+    assert score.scoremat.shape == ref[3].shape
+    assert numpy.abs(score.scoremat - ref[3]).max() < tol
+
+
+def test_kat_vectors():
+    k = kat.kat_inputs()
+    mk = lambda: (_ss(k["en_ids"], k["en"]), _ss(k["te_ids"], k["te"]), _ndx(k["ndx_models"], k["ndx_segs"], k["trialmask"]))
+    B = k["F"] @ k["F"].T + 0.1 * numpy.eye(8)
+    res = {
+        "plda": sk.PLDA_scoring(*mk(), k["mu"], k["F"], numpy.zeros((8, 0)), k["Sigma"]),
+        "plda_sf05": sk.PLDA_scoring(*mk(), k["mu"], k["F"], numpy.zeros((8, 0)), k["Sigma"], scaling_factor=0.5),
+        "twocov": sk.two_covariance_scoring(*mk(), k["Sigma"], B),
+        "cosine": sk.cosine_scoring(*mk()),
+    }
+    for name, sc in res.items():
+        exp = kat.KAT[name]
+        assert sc.modelset.tolist() == kat.KAT_MODELSET and sc.segset.tolist() == kat.KAT_SEGSET
+        assert sc.scoremask.sum() == kat.KAT_MASK_SUM and sc.scoremask[0].tolist() == kat.KAT_MASK_ROW0
+        assert str(sc.scoremat.dtype) == exp["dtype"] and sc.validate()
+        assert numpy.abs(sc.scoremat[0] - numpy.array(exp["row0"])).max() < 1e-4, name
+        assert abs(float(sc.scoremat.sum()) - exp["total"]) < 1e-3, name
+
+
+def test_two_covariance_mutates_callers_objects_like_the_reference():
+    k = kat.kat_inputs()
+    en, te = _ss(k["en_ids"], k["en"]), _ss(k["te_ids"], k["te"])
+    sk.two_covariance_scoring(en, te, _ndx(k["ndx_models"], k["ndx_segs"], k["trialmask"]), k["Sigma"],
+                              k["F"] @ k["F"].T + 0.1 * numpy.eye(8))
+    assert en.modelset.tolist() == kat.KAT_MODELSET
+    en2 = _ss(k["en_ids"], k["en"])
+    sk.cosine_scoring(en2, te, _ndx(k["ndx_models"], k["ndx_segs"], k["trialmask"]))
+    assert en2.modelset.tolist() == k["en_ids"].tolist()          # cosine / PLDA deep-copy
+
+
+@pytest.mark.parametrize("name", ["cosine", "plda", "plda_sf", "plda_open", "twocov", "plda_dup"])
+def test_golden_scoring(name):
+    g = golden("scoring.npz")
+    en = _ss(g["en_ids_dup"] if name == "plda_dup" else g["en_ids"], g["E"])
+    te = _ss(g["te_ids"], g["T"])
+    ndx = _ndx(g["ndx_models"], g["ndx_segs"], g["trialmask"])
+    D = g["E"].shape[1]
+    if name == "cosine":
+        sc = sk.cosine_scoring(en, te, ndx)
+    elif name in ("plda", "plda_dup"):
+        sc = sk.PLDA_scoring(en, te, ndx, g["mu"], g["F"], numpy.zeros((D, 0)), g["Sigma"])
+    elif name == "plda_sf":
+        sc = sk.PLDA_scoring(en, te, ndx, g["mu"], g["F"], numpy.zeros((D, 0)), g["Sigma"], scaling_factor=0.7)
+    elif name == "plda_open":
+        sc = sk.fast_PLDA_scoring(en, te, ndx, g["mu"], g["F"], g["Sigma"], p_known=0.3)
+    else:
+        sc = sk.two_covariance_scoring(en, te, ndx, g["Sigma"], g["B"])
+    ref = (g[name + "_modelset"], g[name + "_segset"], g[name + "_mask"], g[name + "_mat"])
+    _check(sc, ref, 1e-3, ref[3].dtype)
+
+
+@pytest.mark.parametrize("unit_norm", [True, False])
+@pytest.mark.parametrize("Ne,Nt,D", [(1000, 777, 256), (130, 3000, 256), (257, 129, 200)])
+def test_plda_and_cosine_random(Ne, Nt, D, unit_norm):
+    """Ragged sizes (tile edges), permuted / missing ids, unit-norm and N(0,1)-scale embeddings (split-precision path)."""
+    rng = numpy.random.default_rng(Ne + Nt)
+    E = synth.synth_embeddings(Ne, D, seed=1, unit_norm=unit_norm)
+    T = synth.synth_embeddings(Nt, D, seed=2, unit_norm=unit_norm)
+    mu, F, Sigma = synth.synth_plda(D, D, seed=3)
+    en_ids = numpy.array(["m%05d" % i for i in range(Ne)])
+    te_ids = numpy.array(["s%05d" % i for i in range(Nt)])
+    nm = numpy.concatenate([en_ids[rng.permutation(Ne)[: Ne - 3]], ["nope"]])
+    ns = numpy.concatenate([["nope2"], te_ids[rng.permutation(Nt)[: Nt - 5]]])
+    mask = rng.random((nm.shape[0], ns.shape[0])) < 0.5
+    a = (en_ids, E, te_ids, T, nm, ns, mask)
+    sc = sk.PLDA_scoring(_ss(en_ids, E), _ss(te_ids, T), _ndx(nm, ns, mask), mu, F, numpy.zeros((D, 0)), Sigma)
+    _check(sc, S.fast_plda_scoring(*a, mu, F, Sigma), 1e-3, numpy.float64)
+    sc = sk.cosine_scoring(_ss(en_ids, E), _ss(te_ids, T), _ndx(nm, ns, mask))
+    _check(sc, S.cosine_scoring(*a), 2e-5, numpy.float32)
+    sc = sk.two_covariance_scoring(_ss(en_ids, E), _ss(te_ids, T), _ndx(nm, ns, mask), Sigma, F @ F.T + 0.1 * numpy.eye(D))
+    _check(sc, S.two_covariance_scoring(*a, Sigma, F @ F.T + 0.1 * numpy.eye(D)), 1e-3, numpy.float64)
+
+
+def test_score_matrix_linearity_and_symmetry_at_scale():
+    """Size-independent properties at a size the numpy oracle would take long on: S(E,T) = S(T,E)^T bit-exactly
+    is not required (different tilings), but cosine self-scores have a unit diagonal and S is linear in alpha."""
+    X = torch.from_numpy(synth.synth_embeddings(6000, 256, seed=9)).float().cuda()
+    S1 = sk.score_matrix(X, X, passes=3)
+    assert (torch.diagonal(S1) - 1).abs().max().item() < 1e-5
+    assert (S1 - S1.t()).abs().max().item() < 1e-5
+    S2 = sk.score_matrix(X, X, alpha=2.0, cst=0.25, passes=3)
+    assert (S2 - (2 * S1 + 0.5)).abs().max().item() < 1e-5
+    S3 = sk.score_matrix(X, X, passes=1)
+    assert (S3 - S1).abs().max().item() < 2.5e-4                  # single-pass fp16 on unit-norm rows
+    ref = (X[:512].double() @ X[:700].double().t()).float()
+    assert (S1[:512, :700] - ref).abs().max().item() < 1e-5
+
+
+def test_asnorm_golden_and_oracle():
+    g = golden("scoring.npz")
+    out = sk.asnorm(torch.from_numpy(g["asnorm_X"]), torch.from_numpy(g["asnorm_cohort"]), None)
+    assert out.dtype == numpy.float32 and out.shape == g["asnorm_out"].shape
+    assert numpy.abs(out - g["asnorm_out"]).max() < 1e-3
+    rng = numpy.random.default_rng(5)
+    X = synth.synth_embeddings(700, 256, seed=21).astype(numpy.float32)
+    coh = rng.standard_normal((1500, 256)).astype(numpy.float32)
+    out = sk.asnorm(torch.from_numpy(X), torch.from_numpy(coh), None)
+    assert numpy.abs(out - S.asnorm(X, coh)).max() < 1e-3

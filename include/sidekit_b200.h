@@ -35,6 +35,13 @@ const char* skb_last_error(void);
 /* Number of CUDA kernels launched by this library since process start (bench.py reports deltas). */
 int64_t skb_kernel_launches(void);
 
+/* Device-time attribution for bench.py's roofline: while enabled, the extractor brackets each kernel group
+ * with CUDA events on the launching stream.  skb_profile_read synchronises, sums the elapsed milliseconds per
+ * category into ms_by_category[0..7] = {front-end, stem, tcgen05 convolutions, SE, pooling+head, -, -, -}
+ * and clears the record. */
+void skb_profile_enable(int on);
+int skb_profile_read(float* ms_by_category, int n_categories);
+
 /* ---- extraction: replaces sidekit.nnet.xvector.Xtractor.__init__ / load_state_dict / forward -----------
  * Weights are handed over as named fp32 host tensors using the reference's state_dict keys
  * (SURVEY.md Appendix A.6), e.g. "sequence_network.layer1.0.conv1.weight"; BatchNorm folding,

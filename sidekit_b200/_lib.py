@@ -34,6 +34,8 @@ def _declare(lib):
         "skb_version": (i32, []),
         "skb_last_error": (ctypes.c_char_p, []),
         "skb_kernel_launches": (i64, []),
+        "skb_profile_enable": (None, [i32]),
+        "skb_profile_read": (i32, [ctypes.POINTER(ctypes.c_float), i32]),
         "skb_xtractor_create": (i32, [i32, i32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(vp),
                                       ctypes.POINTER(c_i64_p), ctypes.POINTER(i32), i32, f32, ctypes.POINTER(vp)]),
         "skb_xtractor_destroy": (None, [vp]),

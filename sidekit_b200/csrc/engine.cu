@@ -22,6 +22,24 @@ void set_last_error(const char* file, int line, const char* msg) {
 }
 std::atomic<long long> g_launches{0};
 
+// Optional per-category device timing (CUDA events on the launching stream) used by bench.py for the
+// roofline of the dominant kernel.  Off by default: events between launches cost a little.
+enum { PROF_FRONTEND = 0, PROF_STEM = 1, PROF_CONV = 2, PROF_SE = 3, PROF_POOL = 4, PROF_HEAD = 5, PROF_NCAT = 8 };
+struct ProfEv { int cat; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfEv> g_prof;
+struct ProfScope {
+    cudaStream_t st; int idx = -1;
+    ProfScope(int cat, cudaStream_t s) : st(s) {
+        if (!g_prof_on) return;
+        ProfEv e; e.cat = cat;
+        cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, st);
+        g_prof.push_back(e); idx = (int)g_prof.size() - 1;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].b, st); }
+};
+
 
 // ----------------------------------------------------------------------------- small host utilities
 struct HostTensor {
@@ -662,13 +680,19 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     const int* d32 = h->d32;
     const long long* d64 = h->d64;
     float* feats = (float*)h->feats.p;
-    SKB_TRY(frontend_launch(m.fe, wave, d64 + pl.o_wave_off, d32 + pl.o_wave_len, d64 + pl.o_feat_off, d32 + pl.o_nframes, B,
-                            pl.t_max, feats, nullptr, st));
+    {
+        ProfScope ps(PROF_FRONTEND, st);
+        SKB_TRY(frontend_launch(m.fe, wave, d64 + pl.o_wave_off, d32 + pl.o_wave_len, d64 + pl.o_feat_off, d32 + pl.o_nframes, B,
+                                pl.t_max, feats, nullptr, st));
+    }
     g_launches += 2;
     auto buf = [&](int level, int k) { return (uint16_t*)h->act[level * 5 + k].p; };
     const Level& L1 = pl.lv[0];
-    SKB_TRY(launch_stem(m.bf16, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, m.stem_w, m.stem_b, buf(0, 0), L1.plane, L1.G,
-                        L1.p_end, L1.Wp, L1.W, d32 + L1.o_row_b, d32 + L1.o_row_h, st));
+    {
+        ProfScope ps(PROF_STEM, st);
+        SKB_TRY(launch_stem(m.bf16, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, m.stem_w, m.stem_b, buf(0, 0), L1.plane, L1.G,
+                            L1.p_end, L1.Wp, L1.W, d32 + L1.o_row_b, d32 + L1.o_row_h, st));
+    }
     g_launches++;
     int level = 0, cur = 0;   // current activation = buf(level, cur), cur in {0, 1}
     if (stop && !strcmp(stop, "stem")) return export_stage(h, buf(0, 0), L1, h_max, dbg_out, per_utt, st);
@@ -681,15 +705,21 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
         const Level& Lin = pl.lv[in_level];
         const Level& L = pl.lv[level];
         uint16_t *y1 = buf(level, 2), *y2 = buf(level, 3), *scb = buf(level, 4), *nxt = buf(level, cur ^ 1);
-        SKB_TRY(run_conv(h, bw.conv1, Lin, x, y1, L, bw.stride == 2, 1, true, nullptr, nullptr, 0, st));
-        SKB_TRY(run_conv(h, bw.conv2, L, y1, y2, L, false, 0, true, nullptr, (unsigned long long*)h->sums.p, 0, st));
         const uint16_t* res = x;
-        if (bw.has_sc) {
-            SKB_TRY(run_conv(h, bw.sc, Lin, x, scb, L, bw.stride == 2, 0, false, nullptr, nullptr, 0, st));
-            res = scb;
+        {
+            ProfScope ps(PROF_CONV, st);
+            SKB_TRY(run_conv(h, bw.conv1, Lin, x, y1, L, bw.stride == 2, 1, true, nullptr, nullptr, 0, st));
+            SKB_TRY(run_conv(h, bw.conv2, L, y1, y2, L, false, 0, true, nullptr, (unsigned long long*)h->sums.p, 0, st));
+            if (bw.has_sc) {
+                SKB_TRY(run_conv(h, bw.sc, Lin, x, scb, L, bw.stride == 2, 0, false, nullptr, nullptr, 0, st));
+                res = scb;
+            }
         }
-        SKB_TRY(launch_se_fc((unsigned long long*)h->sums.p, d32 + L.o_utt_count, bw.se_w1, bw.se_w2, (float*)h->scale.p, B, bw.C, st));
-        SKB_TRY(launch_se_apply(m.bf16, y2, res, nxt, L.plane, (const float*)h->scale.p, bw.C, L.G, L.p_end, L.Wp, d32 + L.o_row_b, st));
+        {
+            ProfScope ps(PROF_SE, st);
+            SKB_TRY(launch_se_fc((unsigned long long*)h->sums.p, d32 + L.o_utt_count, bw.se_w1, bw.se_w2, (float*)h->scale.p, B, bw.C, st));
+            SKB_TRY(launch_se_apply(m.bf16, y2, res, nxt, L.plane, (const float*)h->scale.p, bw.C, L.G, L.p_end, L.Wp, d32 + L.o_row_b, st));
+        }
         g_launches += 2;
         cur ^= 1;
         if (stop) {
@@ -703,6 +733,7 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     const Level& L4 = pl.lv[3];
     const int D = m.pool_D, A = m.att_A, F = pl.pool_frames;
     float *X = (float*)h->poolX.p, *Hh = (float*)h->poolH.p, *Lg = (float*)h->poolL.p;
+    ProfScope pool_scope(PROF_POOL, st);
     SKB_TRY(launch_gather_frames(m.bf16, buf(level, cur), L4.plane, L4.C, L4.W, L4.Wp, L4.G, d32 + pl.o_frame_row, F, X, st));
     SKB_TRY(launch_meanstd(X, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, nullptr, nullptr, (float*)h->gc.p, st));
     SKB_TRY(launch_sgemm_nt((const float*)h->gc.p, m.att_w1g, (float*)h->hb.p, m.att_b1, B, A, 2 * D, 2 * D, 2 * D, A, 1.f, st));
@@ -731,8 +762,11 @@ static int forward_tdnn(skb_xtractor* h, const float* wave, int norm_embedding, 
     const int* d32 = h->d32;
     const long long* d64 = h->d64;
     float* feats = (float*)h->feats.p;
-    SKB_TRY(frontend_launch(m.fe, wave, d64 + pl.o_wave_off, d32 + pl.o_wave_len, d64 + pl.o_feat_off, d32 + pl.o_nframes, B,
-                            pl.t_max, feats, nullptr, st));
+    {
+        ProfScope ps(PROF_FRONTEND, st);
+        SKB_TRY(frontend_launch(m.fe, wave, d64 + pl.o_wave_off, d32 + pl.o_wave_len, d64 + pl.o_feat_off, d32 + pl.o_nframes, B,
+                                pl.t_max, feats, nullptr, st));
+    }
     const Level& L0 = pl.lv[0];
     SKB_TRY(launch_pack_frames(m.bf16, feats, m.fe.n_out, L0.C, (int)pl.total_frames, d32 + pl.o_row_src, (uint16_t*)h->act[0].p,
                                L0.plane, L0.G, st));
@@ -743,6 +777,7 @@ static int forward_tdnn(skb_xtractor* h, const float* wave, int norm_embedding, 
         const Level& Lin = pl.lv[i];
         const Level& Lout = pl.lv[i + 1];
         // validity (row_h) of the OUTPUT rows decides what gets stored as non-zero
+        ProfScope ps(PROF_CONV, st);
         SKB_TRY(run_conv(h, m.tdnn[i], Lin, (const uint16_t*)h->act[i].p, (uint16_t*)h->act[i + 1].p, Lout, false, 2, false,
                          shifts, nullptr, Lout.o_row_h, st));
         if (stop) {
@@ -754,6 +789,7 @@ static int forward_tdnn(skb_xtractor* h, const float* wave, int norm_embedding, 
     const Level& L5 = pl.lv[5];
     const int D = m.pool_D, F = pl.pool_frames;
     float* X = (float*)h->poolX.p;
+    ProfScope pool_scope(PROF_POOL, st);
     SKB_TRY(launch_gather_frames(m.bf16, (const uint16_t*)h->act[5].p, L5.plane, L5.C, 1, 1, L5.G, d32 + pl.o_frame_row, F, X, st));
     SKB_TRY(launch_meanstd(X, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, m.pool_s, m.pool_t, (float*)h->pooled.p, st));
     g_launches += 2;
@@ -788,6 +824,26 @@ extern "C" {
 int skb_version(void) { return 100; }
 const char* skb_last_error(void) { return g_err; }
 int64_t skb_kernel_launches(void) { return (int64_t)g_launches.load(); }
+
+void skb_profile_enable(int on) {
+    g_prof_on = on != 0;
+}
+int skb_profile_read(float* ms_by_category, int n_categories) {
+    if (!ms_by_category || n_categories < PROF_NCAT) {
+        set_last_error(__FILE__, __LINE__, "profile_read: need room for 8 categories");
+        return SKB_ERR_ARG;
+    }
+    for (int i = 0; i < n_categories; ++i) ms_by_category[i] = 0.f;
+    SKB_CUDA_CHECK(cudaDeviceSynchronize());
+    for (auto& e : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) ms_by_category[e.cat] += ms;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_prof.clear();
+    return SKB_OK;
+}
 
 int skb_xtractor_create(int archi, int n_tensors, const char* const* names, const float* const* data,
                         const int64_t* const* shapes, const int* ndims, int compute_dtype, float margin_s,

@@ -218,6 +218,13 @@ class Xtractor(torch.nn.Module):
         logits, emb = self._run(flat, lengths, norm_embedding, want_logits)
         return (logits, emb) if want_logits else emb
 
+    def extract_packed(self, flat, lengths, norm_embedding=True, want_logits=False):
+        """Extension for bulk extraction: ``flat`` already holds the utterances back to back (1-D fp32, CUDA or
+        -- ideally pinned -- host memory), ``lengths`` their sample counts.  Host input goes through
+        ``skb_xtractor_forward_host`` (H2D, forward, D2H inside one native call)."""
+        logits, emb = self._run(flat, [int(v) for v in lengths], norm_embedding, want_logits)
+        return (logits, emb) if want_logits else emb
+
     def _frontend(self, x):
         B, L = x.shape
         if not x.is_cuda:

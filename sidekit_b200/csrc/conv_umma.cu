@@ -9,21 +9,41 @@ int conv_pick_ncta(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
 int conv_tile_m(int n_cta) { return n_cta == 32 ? 512 : 256; }
 
 template <int N_CTA, int MT, bool BF16>
-static int launch_one(const ConvParams& p, cudaStream_t st) {
+static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     using Cfg = ConvCfg<N_CTA, MT>;
     static bool configured = false;
-    const size_t smem = Cfg::smem_bytes(p.rows_pad);
-    if (smem > 227 * 1024) {
+    ConvParams p = p_in;
+    const size_t a_stage = (size_t)p.rows_pad * (kConvKC / 8) * 16;
+    // weight ring: fetch several taps per stage when the per-tap image is small (fewer barrier round trips
+    // on the MMA issue path); always >= 2 stages so the next stage streams in behind the current one
+    int tps = 1;
+    for (int cand : {9, 5, 3}) {
+        if (p.taps % cand == 0 && (size_t)cand * Cfg::kBStageBytes <= 36 * 1024) { tps = cand; break; }
+    }
+    p.tps = tps;
+    const size_t b_stage = (size_t)tps * Cfg::kBStageBytes;
+    int bst = (int)((64 * 1024) / b_stage);
+    if (bst > kConvBStages) bst = kConvBStages;
+    if (bst < 2) bst = 2;
+    p.b_stages = bst;
+    const size_t fixed = Cfg::fixed_bytes(p.cout, bst, tps);
+    int stages = (int)((kConvSmemBudget - fixed) / a_stage);
+    if (stages > kConvMaxAStages) stages = kConvMaxAStages;
+    if (stages < 2) {
         set_last_error(__FILE__, __LINE__, "conv slab does not fit in shared memory");
         return SKB_ERR_ARG;
     }
+    p.a_stages = stages;
+    const size_t smem = fixed + (size_t)stages * a_stage;
     if (!configured) {
         SKB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<N_CTA, MT, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             227 * 1024));
         configured = true;
     }
     const int n_pix = p.p_end - p.G;
-    dim3 grid((n_pix + Cfg::kTileM - 1) / Cfg::kTileM, p.cout / N_CTA);
+    p.n_tiles = (n_pix + Cfg::kTileM - 1) / Cfg::kTileM;
+    const int n_items = p.n_tiles * (p.cout / N_CTA);
+    const int grid = n_items < kNumSMs ? n_items : kNumSMs;      // persistent: one CTA per SM
     conv_umma_kernel<N_CTA, MT, BF16><<<grid, kConvThreads, smem, st>>>(p);
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;

@@ -1,4 +1,4 @@
-// Shift-GEMM convolution on tcgen05 (sm_100a).
+// Shift-GEMM convolution on tcgen05 (sm_100a), persistent and fully pipelined.
 //
 // Activations live in HBM in a "chunk-plane, padded-linear" layout:
 //     act[chunk j = c/8][pixel p][8 channels]   (16 bytes per (j, p), 16-bit elements)
@@ -6,16 +6,20 @@
 // line (w == W) and ONE zero pad line between utterances:  p = G + row * Wp + w,  Wp = W + 1.
 // In that layout a 3x3 / stride-1 / pad-1 convolution is nine GEMMs whose A operands are the SAME
 // pixel slab shifted by (r-1)*Wp + (s-1) rows, and a contiguous run of pixels of one chunk plane is
-// exactly one column of 8x16-byte UMMA core matrices (K-major, no swizzle).  So a CTA
-//   * pulls its slab (128*MT output pixels + halo) with one 1-D bulk copy per chunk plane
-//     (cp.async.bulk, no tensor map, every input byte read ~once),
+// exactly one column of 8x16-byte UMMA core matrices (K-major, no swizzle).  So the kernel
+//   * pulls each slab (128*MT output pixels + halo, 32 input channels) with one 1-D bulk copy per
+//     chunk plane (cp.async.bulk, no tensor map, every input byte read ~once),
 //   * streams the folded-BN weights, pre-packed on the host into per-(tap, k-chunk) UMMA images,
 //   * issues tcgen05.mma M=128 x N x K=16 from one thread, descriptors differing per tap only in
 //     their start address, accumulating MT tiles in TMEM,
-//   * and four epilogue warps read TMEM with tcgen05.ld, add the bias, apply ReLU / the pad mask,
-//     optionally subsample (stride-2 convs are computed at stride 1 and every other pixel kept),
-//     optionally reduce per-(utterance, channel) sums for the squeeze-excitation layer, and store
-//     16-byte channel groups, fully coalesced across the warp.
+//   * and eight epilogue warps read TMEM with tcgen05.ld, add the bias, apply the activation / pad
+//     mask, optionally subsample (stride-2 convs are computed at stride 1 and every other pixel
+//     kept), optionally reduce per-(utterance, channel) sums for the squeeze-excitation layer, and
+//     store 16-byte channel groups, fully coalesced across the warp.
+// One CTA per SM walks the (pixel tile, N split) work items round-robin.  Three mbarrier pipelines
+// keep the roles decoupled across item boundaries: an A-slab ring and a weight ring (producers run
+// ahead into the next items) and a double-buffered TMEM accumulator (the epilogue of item i overlaps
+// the MMAs of item i+1).
 // Replaces cuDNN conv + BN + ReLU kernels behind sidekit/nnet/res_net.py:309-320 and the Conv1d
 // GEMMs of sidekit/nnet/xvector.py:467-483.
 #pragma once
@@ -36,6 +40,10 @@ struct ConvParams {
     int p_end;              // one past the last computed pixel
     int halo;               // slab rows before the tile's first pixel (Wp + 1 for 3x3, 0 for 1x1 / causal taps)
     int rows_pad;           // slab rows per chunk plane (multiple of 8)
+    int a_stages;           // slabs in the A ring (2..8)
+    int b_stages;           // stages in the weight ring (2..8)
+    int tps;                // taps per weight stage (divides taps): small layers fetch all taps of a k-chunk at once
+    int n_tiles;            // pixel tiles
     int tap_shift[10];      // pixel shift of each tap: (r-1)*Wp + (s-1) for 3x3; k*dilation for the TDNN
     int act;                // 0 none, 1 ReLU, 2 LeakyReLU(0.2)
     const int* row_b;       // [n_rows] utterance of each line, -1 for pad lines
@@ -47,55 +55,82 @@ struct ConvParams {
 };
 
 constexpr int kConvKC = 32;            // input channels per A/B stage (two K=16 MMAs)
-constexpr int kConvAStages = 2;
-constexpr int kConvThreads = 7 * 32;   // warps: 0 A-producer, 1 B-producer, 2 MMA, 3..6 epilogue
+constexpr int kConvMaxAStages = 8;
+constexpr int kConvBStages = 8;
+constexpr int kConvThreads = 12 * 32;  // warps: 0 A-producer, 1 B-producer, 2 MMA, 3 idle, 4..11 epilogue (2 per TMEM quadrant)
+constexpr int kConvCtrlBytes = 1024;
+constexpr int kConvSmemBudget = 225 * 1024;
 
 template <int N_CTA, int MT>
 struct ConvCfg {
-    static constexpr int kTmemCols = N_CTA * MT;   // 128 or 256 (power of two)
+    static constexpr int kAccCols = N_CTA * MT;        // one accumulator set
+    static constexpr int kTmemCols = 2 * kAccCols;     // double-buffered: 256 or 512 columns
     static constexpr int kBStageBytes = N_CTA * kConvKC * 2;
-    static constexpr int kBStages = (N_CTA <= 32) ? 8 : ((N_CTA <= 64) ? 6 : 4);
     static constexpr int kTileM = 128 * MT;
-    static size_t smem_bytes(int rows_pad) {
-        return 1024 + (size_t)kConvAStages * rows_pad * (kConvKC / 8) * 16 + (size_t)kBStages * kBStageBytes;
+    static size_t fixed_bytes(int cout, int b_stages, int tps) {
+        return kConvCtrlBytes + (size_t)cout * 4 + (size_t)b_stages * tps * kBStageBytes;
     }
 };
 
+// Fixed-point (2^-24) reduction of 16 per-lane partial channel sums into sums[b][ch0 .. ch0+15].  Lanes that
+// never accumulated (b_lane < 0) hold zeros.  Common case: every contributing lane belongs to one utterance ->
+// transposing butterfly (lane l ends with channel ch0 + (l & 15)) and one coalesced atomic per lane 0..15.
+// Utterance boundary inside the warp (rare): each lane adds its own 16 partial sums.
+__device__ __forceinline__ void se_flush(long long (&t)[16], int lane, int b_lane, unsigned long long* sums, int cout, int ch0) {
+    const unsigned has = __ballot_sync(0xffffffffu, b_lane >= 0);
+    if (has == 0u) return;
+    const int b0 = __shfl_sync(0xffffffffu, b_lane, __ffs(has) - 1);
+    if (__all_sync(0xffffffffu, b_lane < 0 || b_lane == b0)) {
+#pragma unroll
+        for (int s = 8; s >= 1; s >>= 1) {
+            const bool upper = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+                const long long send = upper ? t[i] : t[i + s];
+                const long long keep = upper ? t[i + s] : t[i];
+                t[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            }
+        }
+        t[0] += __shfl_xor_sync(0xffffffffu, t[0], 16);
+        if (lane < 16) atomicAdd(sums + (size_t)b0 * cout + ch0 + lane, (unsigned long long)t[0]);
+    } else if (b_lane >= 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(sums + (size_t)b_lane * cout + ch0 + i, (unsigned long long)t[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = 0ll;
+}
+
 template <int N_CTA, int MT, bool BF16>
-__global__ void __launch_bounds__(kConvThreads) conv_umma_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvParams p) {
     using Cfg = ConvCfg<N_CTA, MT>;
     extern __shared__ __align__(128) uint8_t smem[];
-    // control block (first 1024 bytes)
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);           // [2]
-    uint64_t* a_empty = a_full + kConvAStages;                      // [2]
-    uint64_t* b_full = a_empty + kConvAStages;                      // [kBStages]
-    uint64_t* b_empty = b_full + Cfg::kBStages;                     // [kBStages]
-    uint64_t* acc_full = b_empty + Cfg::kBStages;                   // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-    uint8_t* a_smem = smem + 1024;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);           // [kConvMaxAStages]
+    uint64_t* a_empty = a_full + kConvMaxAStages;
+    uint64_t* b_full = a_empty + kConvMaxAStages;                   // [kConvBStages]
+    uint64_t* b_empty = b_full + kConvBStages;
+    uint64_t* acc_full = b_empty + kConvBStages;                    // [2]
+    uint64_t* acc_empty = acc_full + 2;                             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* bias_s = reinterpret_cast<float*>(smem + kConvCtrlBytes);
+    uint8_t* b_smem = smem + kConvCtrlBytes + (size_t)p.cout * 4;
+    const uint32_t b_stage_bytes = (uint32_t)p.tps * Cfg::kBStageBytes;
+    uint8_t* a_smem = b_smem + (size_t)p.b_stages * b_stage_bytes;
     const uint32_t a_stage_bytes = (uint32_t)p.rows_pad * (kConvKC / 8) * 16;
-    uint8_t* b_smem = a_smem + kConvAStages * a_stage_bytes;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int nsplit = blockIdx.y;
-    const int p0 = p.G + tile * Cfg::kTileM;
+    const int n_split = p.cout / N_CTA;
+    const int n_items = p.n_tiles * n_split;
     const int n_kc = p.cin / kConvKC;
-    const int n_it = n_kc * p.taps;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kConvAStages; ++i) {
-            mbar_init(&a_full[i], 1);
-            mbar_init(&a_empty[i], 1);
-        }
-        for (int i = 0; i < Cfg::kBStages; ++i) {
-            mbar_init(&b_full[i], 1);
-            mbar_init(&b_empty[i], 1);
-        }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < kConvMaxAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kConvBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }   // first b_stages used
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         fence_barrier_init();
     }
+    for (int i = threadIdx.x; i < p.cout; i += blockDim.x) bias_s[i] = p.bias[i];
     if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -105,143 +140,186 @@ __global__ void __launch_bounds__(kConvThreads) conv_umma_kernel(const ConvParam
     if (warp == 0) {
         // ---------------------------------------------------------------- A producer: activation slabs
         if (lane == 0) {
-            const long long q0 = (long long)p0 - p.halo;    // first slab pixel (>= 0 thanks to the guard G)
-            for (int kc = 0; kc < n_kc; ++kc) {
-                const int s = kc % kConvAStages;
-                const int u = kc / kConvAStages;
-                mbar_wait(&a_empty[s], (u & 1) ^ 1);
-                mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
-                const uint32_t plane_bytes = (uint32_t)p.rows_pad * 16;
+            const uint32_t plane_bytes = (uint32_t)p.rows_pad * 16;
+            long long cnt = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int tile = item / n_split;
+                const long long q0 = (long long)p.G + (long long)tile * Cfg::kTileM - p.halo;   // >= 0 thanks to the guard G
+                for (int kc = 0; kc < n_kc; ++kc, ++cnt) {
+                    const int s = (int)(cnt % p.a_stages);
+                    mbar_wait(&a_empty[s], (uint32_t)((cnt / p.a_stages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
 #pragma unroll
-                for (int j = 0; j < kConvKC / 8; ++j) {
-                    const uint16_t* src = p.in + ((size_t)(kc * (kConvKC / 8) + j) * p.in_plane + q0) * 8;
-                    bulk_g2s(a_smem + s * a_stage_bytes + j * plane_bytes, src, plane_bytes, &a_full[s]);
+                    for (int j = 0; j < kConvKC / 8; ++j) {
+                        const uint16_t* src = p.in + ((size_t)(kc * (kConvKC / 8) + j) * p.in_plane + q0) * 8;
+                        bulk_g2s(a_smem + (size_t)s * a_stage_bytes + j * plane_bytes, src, plane_bytes, &a_full[s]);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- B producer: packed weights
         if (lane == 0) {
-            const uint16_t* wbase = p.w + (size_t)nsplit * n_it * (Cfg::kBStageBytes / 2);
-            for (int it = 0; it < n_it; ++it) {
-                const int s = it % Cfg::kBStages;
-                const int u = it / Cfg::kBStages;
-                mbar_wait(&b_empty[s], (u & 1) ^ 1);
-                mbar_arrive_expect_tx(&b_full[s], Cfg::kBStageBytes);
-                bulk_g2s(b_smem + s * Cfg::kBStageBytes, wbase + (size_t)it * (Cfg::kBStageBytes / 2),
-                         Cfg::kBStageBytes, &b_full[s]);
+            const int n_it = n_kc * p.taps;            // per-tap images per item
+            const int n_st = n_it / p.tps;             // weight stages per item
+            long long cnt = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int ns = item % n_split;
+                const uint16_t* wbase = p.w + (size_t)ns * n_it * (Cfg::kBStageBytes / 2);
+                for (int it = 0; it < n_st; ++it, ++cnt) {
+                    const int s = (int)(cnt % p.b_stages);
+                    mbar_wait(&b_empty[s], (uint32_t)((cnt / p.b_stages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
+                    bulk_g2s(b_smem + (size_t)s * b_stage_bytes, wbase + (size_t)it * (b_stage_bytes / 2), b_stage_bytes, &b_full[s]);
+                }
             }
         }
     } else if (warp == 2) {
-        // ---------------------------------------------------------------- MMA issuer (single thread)
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(128, N_CTA, BF16);
-            const uint32_t a_lbo = (uint32_t)p.rows_pad * 16;   // next 8-channel plane of the slab
-            const uint32_t b_lbo = N_CTA * 16;
-            int it = 0;
-            for (int kc = 0; kc < n_kc; ++kc) {
-                const int as = kc % kConvAStages;
-                mbar_wait(&a_full[as], (kc / kConvAStages) & 1);
-                const uint32_t a_base = smem_u32(a_smem + as * a_stage_bytes);
-                for (int tap = 0; tap < p.taps; ++tap, ++it) {
-                    const int bs = it % Cfg::kBStages;
-                    mbar_wait(&b_full[bs], (it / Cfg::kBStages) & 1);
+        // ---------------------------------------------------------------- MMA issuer
+        // The whole warp walks the loops (so addresses / descriptors stay warp-uniform); one elected lane issues.
+        const uint32_t idesc = umma_idesc_f16(128, N_CTA, BF16);
+        const uint32_t a_lbo = (uint32_t)p.rows_pad * 16;   // next 8-channel plane of the slab
+        const uint32_t b_lbo = N_CTA * 16;
+        const uint64_t desc_hi_a = (static_cast<uint64_t>((a_lbo >> 4) & 0x3FFF) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
+                                   (static_cast<uint64_t>(1) << 46);
+        const uint64_t desc_hi_b = (static_cast<uint64_t>((b_lbo >> 4) & 0x3FFF) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
+                                   (static_cast<uint64_t>(1) << 46);
+        long long a_cnt = 0, b_cnt = 0, n_done = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+            const int buf = (int)(n_done & 1);
+            mbar_wait(&acc_empty[buf], (uint32_t)((n_done >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * Cfg::kAccCols;
+            for (int kc = 0; kc < n_kc; ++kc, ++a_cnt) {
+                const int as = (int)(a_cnt % p.a_stages);
+                mbar_wait(&a_full[as], (uint32_t)((a_cnt / p.a_stages) & 1));
+                const uint32_t a_base = smem_u32(a_smem + (size_t)as * a_stage_bytes) + (uint32_t)p.halo * 16;
+                for (int tap0 = 0; tap0 < p.taps; tap0 += p.tps, ++b_cnt) {
+                    const int bs = (int)(b_cnt % p.b_stages);
+                    mbar_wait(&b_full[bs], (uint32_t)((b_cnt / p.b_stages) & 1));
                     tc_fence_after();
-                    const int shift = p.tap_shift[tap];
-                    const uint32_t b_base = smem_u32(b_smem + bs * Cfg::kBStageBytes);
+                    const uint32_t b_stage = smem_u32(b_smem + (size_t)bs * b_stage_bytes);
+                    if (elect_one()) {
+                        for (int tt = 0; tt < p.tps; ++tt) {
+                            const int tap = tap0 + tt;
+                            const uint32_t a_tap = a_base + (uint32_t)(p.tap_shift[tap] * 16);
+                            const uint32_t b_tap = b_stage + tt * Cfg::kBStageBytes;
 #pragma unroll
-                    for (int ks = 0; ks < kConvKC / 16; ++ks) {
-                        const uint64_t bdesc = umma_desc_kmajor_noswz(b_base + ks * 2 * b_lbo, b_lbo, 128);
+                            for (int ks = 0; ks < kConvKC / 16; ++ks) {
+                                const uint64_t bdesc = desc_hi_b | (((b_tap + ks * 2 * b_lbo) >> 4) & 0x3FFF);
 #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) {
-                            const uint32_t a_addr = a_base + ks * 2 * a_lbo + (uint32_t)(p.halo + shift + mt * 128) * 16;
-                            const uint64_t adesc = umma_desc_kmajor_noswz(a_addr, a_lbo, 128);
-                            umma_f16(tmem_base + mt * N_CTA, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-                        }
-                    }
-                    umma_commit(&b_empty[bs]);
-                }
-                umma_commit(&a_empty[as]);
-            }
-            umma_commit(acc_full);
-        }
-    } else {
-        // ---------------------------------------------------------------- epilogue warps (3..6)
-        const int q = warp & 3;   // TMEM lane quadrant this warp may read
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int n_base = nsplit * N_CTA;
-#pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt) {
-            const int pix = p0 + mt * 128 + q * 32 + lane;
-            const bool in_range = pix < p.p_end;
-            const int rel = pix - p.G;
-            const int row = rel / p.Wp;
-            const int w = rel - row * p.Wp;
-            int b = -1, h = -1;
-            if (in_range) {
-                b = __ldg(p.row_b + row);
-                h = __ldg(p.row_h + row);
-            }
-            const bool valid = in_range && (w < p.W) && (h >= 0);
-            bool do_store = in_range;
-            long long opix = pix;
-            if (p.subsample) {
-                do_store = valid && !(h & 1) && !(w & 1);
-                if (do_store) opix = (long long)p.out_G + (long long)(__ldg(p.out_utt_row0 + b) + (h >> 1)) * p.out_Wp + (w >> 1);
-            }
-#pragma unroll 1
-            for (int c0 = 0; c0 < N_CTA; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mt * N_CTA + c0, v);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float t = v[i] + __ldg(p.bias + n_base + c0 + i);
-                    if (p.act == 1) t = fmaxf(t, 0.f);
-                    else if (p.act == 2) t = t > 0.f ? t : 0.2f * t;
-                    v[i] = valid ? t : 0.f;
-                }
-                if (do_store) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 o;
-                        o.x = pack2<BF16>(v[j * 8 + 0], v[j * 8 + 1]);
-                        o.y = pack2<BF16>(v[j * 8 + 2], v[j * 8 + 3]);
-                        o.z = pack2<BF16>(v[j * 8 + 4], v[j * 8 + 5]);
-                        o.w = pack2<BF16>(v[j * 8 + 6], v[j * 8 + 7]);
-                        uint16_t* dst = p.out + ((size_t)((n_base + c0) / 8 + j) * p.out_plane + opix) * 8;
-                        *reinterpret_cast<uint4*>(dst) = o;
-                    }
-                }
-                if (p.se_sums != nullptr) {
-                    // per-(utterance, channel) sums of the fp32 values for the SE squeeze, accumulated in
-                    // 2^-24 fixed point: integer addition is associative, so the result is bit-identical
-                    // whatever the tile / warp / atomic order (and however the batch is packed).  A warp's
-                    // 32 pixels almost always belong to one utterance; the loop covers the boundaries.
-                    unsigned vmask = __ballot_sync(0xffffffffu, valid);
-                    while (vmask) {
-                        const int leader = __ffs(vmask) - 1;
-                        const int b0 = __shfl_sync(0xffffffffu, b, leader);
-                        const bool mine = valid && (b == b0);
-                        const unsigned mm = __ballot_sync(0xffffffffu, mine);
-                        long long t[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) t[i] = mine ? __float2ll_rn(v[i] * 16777216.f) : 0ll;
-                        // transposing butterfly: 31 exchanges, lane l ends with the sum of channel c0 + l
-#pragma unroll
-                        for (int s = 16; s >= 1; s >>= 1) {
-                            const bool upper = (lane & s) != 0;
-#pragma unroll
-                            for (int i = 0; i < s; ++i) {
-                                const long long send = upper ? t[i] : t[i + s];
-                                const long long keep = upper ? t[i + s] : t[i];
-                                t[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                                for (int mt = 0; mt < MT; ++mt) {
+                                    const uint64_t adesc = desc_hi_a | (((a_tap + ks * 2 * a_lbo + mt * 2048) >> 4) & 0x3FFF);
+                                    umma_f16(d_tmem + mt * N_CTA, adesc, bdesc, idesc, (kc > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+                                }
                             }
                         }
-                        atomicAdd(p.se_sums + (size_t)b0 * p.cout + n_base + c0 + lane, (unsigned long long)t[0]);
-                        vmask &= ~mm;
+                        umma_commit(&b_empty[bs]);
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) umma_commit(&a_empty[as]);
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(&acc_full[buf]);
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- epilogue warps (4..11)
+        // two warps per TMEM lane quadrant; each takes half of the item's MT accumulator tiles
+        constexpr int MTH = MT / 2;
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int mt0 = ((warp - 4) >> 2) * MTH;
+        long long n_done = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+            const int tile = item / n_split, ns = item % n_split;
+            const int buf = (int)(n_done & 1);
+            const int p0 = p.G + tile * Cfg::kTileM;
+            const int n_base = ns * N_CTA;
+            mbar_wait(&acc_full[buf], (uint32_t)((n_done >> 1) & 1));
+            tc_fence_after();
+            // per-pixel bookkeeping for the MT pixels this thread owns
+            bool valid[MTH], do_store[MTH];
+            int bidx[MTH];
+            long long opix[MTH];
+#pragma unroll
+            for (int mt = 0; mt < MTH; ++mt) {
+                const int pix = p0 + (mt0 + mt) * 128 + q * 32 + lane;
+                const bool in_range = pix < p.p_end;
+                const int rel = pix - p.G;
+                const int row = rel / p.Wp;
+                const int w = rel - row * p.Wp;
+                int b = -1, h = -1;
+                if (in_range) {
+                    b = __ldg(p.row_b + row);
+                    h = __ldg(p.row_h + row);
+                }
+                valid[mt] = in_range && (w < p.W) && (h >= 0);
+                bidx[mt] = valid[mt] ? b : -1;
+                do_store[mt] = in_range;
+                opix[mt] = pix;
+                if (p.subsample) {
+                    do_store[mt] = valid[mt] && !(h & 1) && !(w & 1);
+                    if (do_store[mt])
+                        opix[mt] = (long long)p.out_G + (long long)(__ldg(p.out_utt_row0 + b) + (h >> 1)) * p.out_Wp + (w >> 1);
+                }
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < N_CTA; c0 += 16) {
+                long long t[16];
+                int b_acc = -1;
+                if (p.se_sums != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) t[i] = 0ll;
+                }
+#pragma unroll
+                for (int mt = 0; mt < MTH; ++mt) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + (mt0 + mt) * N_CTA + c0, v);
+                    if (c0 + 16 >= N_CTA && mt == MTH - 1) {
+                        // accumulator completely read: hand this TMEM buffer back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float x = v[i] + bias_s[n_base + c0 + i];
+                        if (p.act == 1) x = fmaxf(x, 0.f);
+                        else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
+                        v[i] = valid[mt] ? x : 0.f;
+                    }
+                    if (do_store[mt]) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint4 o;
+                            o.x = pack2<BF16>(v[j * 8 + 0], v[j * 8 + 1]);
+                            o.y = pack2<BF16>(v[j * 8 + 2], v[j * 8 + 3]);
+                            o.z = pack2<BF16>(v[j * 8 + 4], v[j * 8 + 5]);
+                            o.w = pack2<BF16>(v[j * 8 + 6], v[j * 8 + 7]);
+                            uint16_t* dst = p.out + ((size_t)((n_base + c0) / 8 + j) * p.out_plane + opix[mt]) * 8;
+                            *reinterpret_cast<uint4*>(dst) = o;
+                        }
+                    }
+                    if (p.se_sums != nullptr) {
+                        // per-(utterance, channel) sums of the fp32 values for the SE squeeze, accumulated in
+                        // 2^-24 fixed point: integer addition is associative, so the result is bit-identical
+                        // whatever the tile / warp / atomic order (and however the batch is packed).  Each lane
+                        // first adds up its own pixels; one transposing butterfly per 16-channel block then
+                        // reduces across the warp (the rare utterance boundary flushes early).
+                        const bool clash = valid[mt] && b_acc >= 0 && bidx[mt] != b_acc;
+                        if (__any_sync(0xffffffffu, clash)) {
+                            se_flush(t, lane, b_acc, p.se_sums, p.cout, n_base + c0);
+                            b_acc = -1;
+                        }
+                        if (valid[mt]) {
+                            b_acc = bidx[mt];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) t[i] += __float2ll_rn(v[i] * 16777216.f);
+                        }
                     }
                 }
+                if (p.se_sums != nullptr) se_flush(t, lane, b_acc, p.se_sums, p.cout, n_base + c0);
             }
         }
         tc_fence_before();

@@ -15,8 +15,8 @@
 // panel-major order.  The 128-row E panel stays resident in shared memory; 128-column T tiles stream
 // through a ring of 64-deep K chunks (1-D bulk copies); accumulators are double-buffered in TMEM so
 // the epilogue of tile i overlaps the MMAs of tile i+1.  The score matrix is HBM-write-bound
-// (128 FLOP per output byte at D = 256), so the epilogue stages each 32x32 block in a warp-private
-// shared buffer and writes full 128-byte row segments with bulk shared->global copies.
+// (128 FLOP per output byte at D = 256), so the epilogue transposes each 32x32 block through a
+// warp-private shared buffer and every store instruction writes one full 128-byte row segment.
 #include "sidekit_b200.h"
 #include "common.cuh"
 #include "layers.cuh"
@@ -110,12 +110,12 @@ constexpr int kScThreads = 6 * 32;       // warps: 0 producer, 1 MMA, 2..5 epilo
 constexpr int kScKChunk = 64;
 constexpr int kScBStageBytes = 128 * kScKChunk * 2;      // hi part of one stage (16 KB)
 
-// smem: [ctrl 256 B][A hi (+lo)][B ring][staging 4 warps x 32 x (32 x 8 + 16) B]
+// smem: [ctrl 256 B][A hi (+lo)][B ring][4 warps x [32][33] fp32 transpose buffers]
 template <int PASSES>
 struct ScoreSmem {
     static constexpr int kBStages = PASSES == 1 ? 4 : 2;
     static constexpr int kParts = PASSES == 1 ? 1 : 2;
-    static constexpr int kStageRowBytes = 32 * 8 + 16;   // fp64 worst case + 16 B pad (bank spread)
+    static constexpr int kStageRowBytes = 33 * 4;        // [32][33] fp32 transpose buffer per epilogue warp
     static size_t a_bytes(int Dp) { return (size_t)kParts * 128 * Dp * 2; }
     static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kParts * kScBStageBytes + 4 * 32 * kStageRowBytes; }
 };
@@ -231,22 +231,21 @@ __global__ void __launch_bounds__(kScThreads) score_gemm_kernel(const ScoreParam
         }
     } else {
         const int q = warp & 3;
-        uint8_t* stg = stage_smem + q * 32 * SM::kStageRowBytes;
+        float* stg = reinterpret_cast<float*>(stage_smem) + q * 32 * 33;     // warp-private [32][33] transpose buffer
         const float inv_scale = ldexpf(1.f, -(p.ctrl[0] + p.ctrl[1]));
         const float a0 = p.a0 * inv_scale;
         const float mscale = p.mul_scaled ? inv_scale : 1.f;
-        const int esize = p.out_f64 ? 8 : 4;
-        const bool bulk_ok = ((p.ld_out * esize) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
         long long nt_done = 0;
         for (long long t = t_begin; t < t_end; ++t, ++nt_done) {
             const int panel = (int)(t / p.n_ntiles), nt = (int)(t % p.n_ntiles);
             const int buf = (int)(nt_done & 1);
             mbar_wait(&acc_full[buf], (uint32_t)((nt_done >> 1) & 1));
             tc_fence_after();
-            const int row = panel * 128 + q * 32 + lane;
-            const bool row_ok = row < p.Ne;
-            const float ra = (p.ra && row_ok) ? p.ra[row] * mscale : 0.f;
-            const float rr = (p.r && row_ok) ? p.r[row] : 0.f;
+            const int row0 = panel * 128 + q * 32;
+            const int my_row = row0 + lane;
+            const float ra = (p.ra && my_row < p.Ne) ? p.ra[my_row] * mscale : 0.f;
+            const float rr = (p.r && my_row < p.Ne) ? p.r[my_row] : 0.f;
+            const int n_rows = min(32, p.Ne - row0);
 #pragma unroll 1
             for (int cb = 0; cb < 4; ++cb) {
                 const int col0 = nt * 128 + cb * 32;
@@ -257,39 +256,36 @@ __global__ void __launch_bounds__(kScThreads) score_gemm_kernel(const ScoreParam
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
-                if (col0 >= p.Nt) continue;
-                // previous bulk stores of this warp must have finished READING the staging buffer
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (col0 >= p.Nt || n_rows <= 0) continue;
+                // transpose through shared memory so that each store instruction writes one 128-byte
+                // (256-byte for fp64) row segment: lane l owns column col0 + l in the write phase
                 __syncwarp();
-                uint8_t* myrow = stg + lane * SM::kStageRowBytes;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int col = col0 + i;
-                    const float ca = (p.ca && col < p.Nt) ? __ldg(p.ca + col) * mscale : 0.f;
-                    const float qq = (p.q && col < p.Nt) ? __ldg(p.q + col) : 0.f;
-                    const float s = fmaf(v[i], ra + ca + a0, fmaf(rr + qq, p.rq_scale, p.c0));
-                    if (p.out_f64) reinterpret_cast<double*>(myrow)[i] = (double)s;
-                    else reinterpret_cast<float*>(myrow)[i] = s;
-                }
-                const int ncols = min(32, p.Nt - col0);
-                if (row_ok) {
-                    uint8_t* gdst = reinterpret_cast<uint8_t*>(p.out) + ((size_t)row * p.ld_out + col0) * esize;
-                    if (bulk_ok && ncols == 32) {
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(myrow)),
-                                     "r"(32 * esize)
-                                     : "memory");
-                    } else {
-                        for (int i = 0; i < ncols; ++i) {
-                            if (p.out_f64) reinterpret_cast<double*>(gdst)[i] = reinterpret_cast<double*>(myrow)[i];
-                            else reinterpret_cast<float*>(gdst)[i] = reinterpret_cast<float*>(myrow)[i];
-                        }
+                for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = v[i];
+                __syncwarp();
+                const int col = col0 + lane;
+                const bool col_ok = col < p.Nt;
+                const float ca = (p.ca && col_ok) ? __ldg(p.ca + col) * mscale : 0.f;
+                const float qq = (p.q && col_ok) ? __ldg(p.q + col) : 0.f;
+                if (p.out_f64) {
+                    double* o = reinterpret_cast<double*>(p.out) + (size_t)row0 * p.ld_out + col;
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) {
+                        const float ra_r = __shfl_sync(0xffffffffu, ra, r), rr_r = __shfl_sync(0xffffffffu, rr, r);
+                        const float sv = fmaf(stg[r * 33 + lane], ra_r + ca + a0, fmaf(rr_r + qq, p.rq_scale, p.c0));
+                        if (r < n_rows && col_ok) o[(size_t)r * p.ld_out] = (double)sv;
+                    }
+                } else {
+                    float* o = reinterpret_cast<float*>(p.out) + (size_t)row0 * p.ld_out + col;
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) {
+                        const float ra_r = __shfl_sync(0xffffffffu, ra, r), rr_r = __shfl_sync(0xffffffffu, rr, r);
+                        const float sv = fmaf(stg[r * 33 + lane], ra_r + ca + a0, fmaf(rr_r + qq, p.rq_scale, p.c0));
+                        if (r < n_rows && col_ok) o[(size_t)r * p.ld_out] = sv;
                     }
                 }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     if (warp == 1) {

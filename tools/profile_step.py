@@ -34,8 +34,14 @@ def main():
             T = torch.from_numpy(synth.synth_embeddings(20000, 256, seed=7)).float().to(dev)
             r, q = torch.randn(20000, device=dev), torch.randn(20000, device=dev)
             out = torch.empty((20000, 20000), dtype=torch.float32, device=dev)
+            passes = int(os.environ.get("SKB_PASSES", "0"))
             for _ in range(n):
-                sk.score_matrix(E, T, r, q, cst=0.5, passes=0, out=out)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                sk.score_matrix(E, T, r, q, cst=0.5, passes=passes, out=out)
+                e1.record()
+                torch.cuda.synchronize()
+                print("score_matrix 20k x 20k passes=%d: %.3f ms" % (passes, e0.elapsed_time(e1)))
     torch.cuda.synchronize()
     print("ok")
 

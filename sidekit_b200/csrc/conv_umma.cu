@@ -14,19 +14,30 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     static bool configured = false;
     ConvParams p = p_in;
     const size_t a_stage = (size_t)p.rows_pad * (kConvKC / 8) * 16;
-    // weight ring: fetch several taps per stage when the per-tap image is small (fewer barrier round trips
-    // on the MMA issue path); always >= 2 stages so the next stage streams in behind the current one
-    int tps = 1;
-    for (int cand : {9, 5, 3}) {
-        if (p.taps % cand == 0 && (size_t)cand * Cfg::kBStageBytes <= 36 * 1024) { tps = cand; break; }
+    // Weights: resident for the life of the CTA when one N split's images fit in <= 96 KB (no per-item weight
+    // traffic, no barrier round trips on the MMA issue path); otherwise streamed through a ring deep enough to
+    // cover the L2 latency at the rate the MMAs consume them (the ring gets what the 3-slab A ring leaves).
+    p.bias_mma = p.cout <= 256 ? 1 : 0;     // wide layers (TDNN) keep the epilogue bias add: their bias images would not fit
+    const int n_it = (p.cin / kConvKC) * p.taps;
+    const int n_split = p.cout / N_CTA;
+    int tps = 1, bst = 1;
+    p.b_resident = (n_split == 1 && (size_t)n_it * Cfg::kBStageBytes <= 96 * 1024) ? 1 : 0;
+    size_t b_stage = Cfg::kBStageBytes;
+    if (p.b_resident) {
+        bst = n_it;
+    } else {
+        for (int cand : {3, 5}) {
+            if (p.taps % cand == 0 && (size_t)cand * Cfg::kBStageBytes <= 24 * 1024) { tps = cand; break; }
+        }
+        b_stage = (size_t)tps * Cfg::kBStageBytes;
+        const size_t left = kConvSmemBudget - Cfg::fixed_bytes(p.cout, p.bias_mma, 0, 0) - 3 * a_stage;
+        bst = (int)(left / b_stage);
+        if (bst > kConvBStages) bst = kConvBStages;
+        if (bst < 2) bst = 2;
     }
     p.tps = tps;
-    const size_t b_stage = (size_t)tps * Cfg::kBStageBytes;
-    int bst = (int)((64 * 1024) / b_stage);
-    if (bst > kConvBStages) bst = kConvBStages;
-    if (bst < 2) bst = 2;
     p.b_stages = bst;
-    const size_t fixed = Cfg::fixed_bytes(p.cout, bst, tps);
+    const size_t fixed = Cfg::fixed_bytes(p.cout, p.bias_mma, bst, tps);
     int stages = (int)((kConvSmemBudget - fixed) / a_stage);
     if (stages > kConvMaxAStages) stages = kConvMaxAStages;
     if (stages < 2) {

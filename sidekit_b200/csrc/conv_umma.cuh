@@ -35,7 +35,6 @@ struct ConvParams {
     uint16_t* out;          // output planes
     long long out_plane;
     int cin, cout, taps;
-    int Wp, W;              // input/level geometry
     int G;                  // first computed pixel
     int p_end;              // one past the last computed pixel
     int halo;               // slab rows before the tile's first pixel (Wp + 1 for 3x3, 0 for 1x1 / causal taps)
@@ -43,14 +42,14 @@ struct ConvParams {
     int a_stages;           // slabs in the A ring (2..8)
     int b_stages;           // stages in the weight ring (2..8)
     int tps;                // taps per weight stage (divides taps): small layers fetch all taps of a k-chunk at once
+    int b_resident;         // 1: all weight images of one N split fit in shared memory and are loaded once per CTA
     int n_tiles;            // pixel tiles
     int tap_shift[10];      // pixel shift of each tap: (r-1)*Wp + (s-1) for 3x3; k*dilation for the TDNN
-    int act;                // 0 none, 1 ReLU, 2 LeakyReLU(0.2)
-    const int* row_b;       // [n_rows] utterance of each line, -1 for pad lines
-    const int* row_h;       // [n_rows] line index inside its utterance, -1 for pad lines
-    int subsample;          // 1: keep even (h, w) only and write into the next level's geometry
-    int out_G, out_Wp;
-    const int* out_utt_row0;  // [B] first line of each utterance at the output level
+    float act_slope;        // activation as max(x, slope * x): 1 = identity, 0 = ReLU, 0.2 = LeakyReLU(0.2)
+    const int* pix_b;       // [p_end - G] utterance of each computed pixel, -1 for pad / invalid pixels
+    const int* pix_sub;     // stride-2 convs: [p_end - G] destination pixel at the next level (even h, even w) or -1;
+                            // nullptr for stride 1 (output pixel == input pixel)
+    int bias_mma;           // 1: the bias is added by one extra MMA (ones x [bias_hi, bias_lo]) instead of the epilogue
     unsigned long long* se_sums;   // [B][cout] fixed-point (2^24) channel sums, or nullptr
 };
 
@@ -67,8 +66,11 @@ struct ConvCfg {
     static constexpr int kTmemCols = 2 * kAccCols;     // double-buffered: 256 or 512 columns
     static constexpr int kBStageBytes = N_CTA * kConvKC * 2;
     static constexpr int kTileM = 128 * MT;
-    static size_t fixed_bytes(int cout, int b_stages, int tps) {
-        return kConvCtrlBytes + (size_t)cout * 4 + (size_t)b_stages * tps * kBStageBytes;
+    // ctrl | bias fp32 [cout] | ones operand (2 planes x 128 rows x 16 B) | bias images (2 planes x cout rows x 16 B) | B | A
+    static constexpr int kOnesBytes = 2 * 128 * 16;
+    static size_t fixed_bytes(int cout, int bias_mma, int b_stages, int tps) {
+        return kConvCtrlBytes + (size_t)cout * 4 + kOnesBytes + (bias_mma ? (size_t)cout * 32 : 0) +
+               (size_t)b_stages * tps * kBStageBytes;
     }
 };
 
@@ -113,7 +115,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     uint64_t* acc_empty = acc_full + 2;                             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* bias_s = reinterpret_cast<float*>(smem + kConvCtrlBytes);
-    uint8_t* b_smem = smem + kConvCtrlBytes + (size_t)p.cout * 4;
+    uint8_t* ones_smem = smem + kConvCtrlBytes + (size_t)p.cout * 4;
+    uint8_t* biasimg_smem = ones_smem + Cfg::kOnesBytes;          // per N split: [2 planes][N_CTA rows][8 halves]
+    uint8_t* b_smem = biasimg_smem + (p.bias_mma ? (size_t)p.cout * 32 : 0);
     const uint32_t b_stage_bytes = (uint32_t)p.tps * Cfg::kBStageBytes;
     uint8_t* a_smem = b_smem + (size_t)p.b_stages * b_stage_bytes;
     const uint32_t a_stage_bytes = (uint32_t)p.rows_pad * (kConvKC / 8) * 16;
@@ -131,6 +135,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < p.cout; i += blockDim.x) bias_s[i] = p.bias[i];
+    if (p.bias_mma) {
+        // "ones" A operand: every row = (1, 1, 0, ..., 0) over K = 16; bias B operand: row n = (hi_n, lo_n, 0, ..., 0) with
+        // hi + lo = bias to ~2^-22: one extra K=16 MMA per accumulator tile initialises it with the bias.
+        const uint32_t one2 = pack2<BF16>(1.f, 1.f);
+        for (int i = threadIdx.x; i < 2 * 128; i += blockDim.x)
+            reinterpret_cast<uint4*>(ones_smem)[i] = make_uint4(i < 128 ? one2 : 0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < 2 * p.cout; i += blockDim.x) {
+            const int ns = (i % p.cout) / N_CTA, n = (i % p.cout) % N_CTA, plane = i / p.cout;
+            uint32_t w0 = 0u;
+            if (plane == 0) {
+                const float b = p.bias[ns * N_CTA + n];
+                const float2 hi2 = unpack2<BF16>(pack2<BF16>(b, 0.f));
+                w0 = pack2<BF16>(b, b - hi2.x);
+            }
+            reinterpret_cast<uint4*>(biasimg_smem)[(size_t)ns * 2 * N_CTA + plane * N_CTA + n] = make_uint4(w0, 0u, 0u, 0u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -161,16 +183,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         // ---------------------------------------------------------------- B producer: packed weights
         if (lane == 0) {
             const int n_it = n_kc * p.taps;            // per-tap images per item
-            const int n_st = n_it / p.tps;             // weight stages per item
-            long long cnt = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int ns = item % n_split;
-                const uint16_t* wbase = p.w + (size_t)ns * n_it * (Cfg::kBStageBytes / 2);
-                for (int it = 0; it < n_st; ++it, ++cnt) {
-                    const int s = (int)(cnt % p.b_stages);
-                    mbar_wait(&b_empty[s], (uint32_t)((cnt / p.b_stages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
-                    bulk_g2s(b_smem + (size_t)s * b_stage_bytes, wbase + (size_t)it * (b_stage_bytes / 2), b_stage_bytes, &b_full[s]);
+            if (p.b_resident) {
+                // small layers: the whole weight tensor stays in shared memory for the life of the CTA
+                mbar_arrive_expect_tx(&b_full[0], (uint32_t)n_it * Cfg::kBStageBytes);
+                for (int it = 0; it < n_it; ++it)
+                    bulk_g2s(b_smem + (size_t)it * Cfg::kBStageBytes, p.w + (size_t)it * (Cfg::kBStageBytes / 2), Cfg::kBStageBytes,
+                             &b_full[0]);
+            } else {
+                const int n_st = n_it / p.tps;             // weight stages per item
+                long long cnt = 0;
+                for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                    const int ns = item % n_split;
+                    const uint16_t* wbase = p.w + (size_t)ns * n_it * (Cfg::kBStageBytes / 2);
+                    for (int it = 0; it < n_st; ++it, ++cnt) {
+                        const int s = (int)(cnt % p.b_stages);
+                        mbar_wait(&b_empty[s], (uint32_t)((cnt / p.b_stages) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
+                        bulk_g2s(b_smem + (size_t)s * b_stage_bytes, wbase + (size_t)it * (b_stage_bytes / 2), b_stage_bytes,
+                                 &b_full[s]);
+                    }
                 }
             }
         }
@@ -185,22 +216,45 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         const uint64_t desc_hi_b = (static_cast<uint64_t>((b_lbo >> 4) & 0x3FFF) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
                                    (static_cast<uint64_t>(1) << 46);
         long long a_cnt = 0, b_cnt = 0, n_done = 0;
+        if (p.b_resident) {
+            mbar_wait(&b_full[0], 0);
+            tc_fence_after();
+        }
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
             const int buf = (int)(n_done & 1);
             mbar_wait(&acc_empty[buf], (uint32_t)((n_done >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * Cfg::kAccCols;
+            if (p.bias_mma && elect_one()) {
+                const uint64_t ones_desc = (static_cast<uint64_t>(2048 >> 4) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
+                                           (static_cast<uint64_t>(1) << 46) | ((smem_u32(ones_smem) >> 4) & 0x3FFF);
+                const uint32_t img = smem_u32(biasimg_smem) + (uint32_t)(item % n_split) * 2 * N_CTA * 16;
+                const uint64_t bias_desc = desc_hi_b | ((img >> 4) & 0x3FFF);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) umma_f16(d_tmem + mt * N_CTA, ones_desc, bias_desc, idesc, 0u);
+            }
+            __syncwarp();
+            const uint32_t acc0 = p.bias_mma ? 1u : 0u;
             for (int kc = 0; kc < n_kc; ++kc, ++a_cnt) {
                 const int as = (int)(a_cnt % p.a_stages);
                 mbar_wait(&a_full[as], (uint32_t)((a_cnt / p.a_stages) & 1));
+                tc_fence_after();
                 const uint32_t a_base = smem_u32(a_smem + (size_t)as * a_stage_bytes) + (uint32_t)p.halo * 16;
-                for (int tap0 = 0; tap0 < p.taps; tap0 += p.tps, ++b_cnt) {
-                    const int bs = (int)(b_cnt % p.b_stages);
-                    mbar_wait(&b_full[bs], (uint32_t)((b_cnt / p.b_stages) & 1));
-                    tc_fence_after();
-                    const uint32_t b_stage = smem_u32(b_smem + (size_t)bs * b_stage_bytes);
+                const int tstep = p.b_resident ? p.taps : p.tps;
+                for (int tap0 = 0; tap0 < p.taps; tap0 += tstep) {
+                    uint32_t b_stage;
+                    int bs = 0;
+                    if (p.b_resident) {
+                        b_stage = smem_u32(b_smem) + (uint32_t)(kc * p.taps) * Cfg::kBStageBytes;
+                    } else {
+                        bs = (int)(b_cnt % p.b_stages);
+                        mbar_wait(&b_full[bs], (uint32_t)((b_cnt / p.b_stages) & 1));
+                        tc_fence_after();
+                        b_stage = smem_u32(b_smem + (size_t)bs * b_stage_bytes);
+                        ++b_cnt;
+                    }
                     if (elect_one()) {
-                        for (int tt = 0; tt < p.tps; ++tt) {
+                        for (int tt = 0; tt < tstep; ++tt) {
                             const int tap = tap0 + tt;
                             const uint32_t a_tap = a_base + (uint32_t)(p.tap_shift[tap] * 16);
                             const uint32_t b_tap = b_stage + tt * Cfg::kBStageBytes;
@@ -210,11 +264,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
 #pragma unroll
                                 for (int mt = 0; mt < MT; ++mt) {
                                     const uint64_t adesc = desc_hi_a | (((a_tap + ks * 2 * a_lbo + mt * 2048) >> 4) & 0x3FFF);
-                                    umma_f16(d_tmem + mt * N_CTA, adesc, bdesc, idesc, (kc > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+                                    umma_f16(d_tmem + mt * N_CTA, adesc, bdesc, idesc, (kc > 0 || tap > 0 || ks > 0) ? 1u : acc0);
                                 }
                             }
                         }
-                        umma_commit(&b_empty[bs]);
+                        if (!p.b_resident) umma_commit(&b_empty[bs]);
                     }
                     __syncwarp();
                 }
@@ -238,32 +292,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             const int n_base = ns * N_CTA;
             mbar_wait(&acc_full[buf], (uint32_t)((n_done >> 1) & 1));
             tc_fence_after();
-            // per-pixel bookkeeping for the MT pixels this thread owns
-            bool valid[MTH], do_store[MTH];
+            // per-pixel bookkeeping for the pixels this thread owns: one coalesced table read each
             int bidx[MTH];
-            long long opix[MTH];
+            uint16_t* optr[MTH];
 #pragma unroll
             for (int mt = 0; mt < MTH; ++mt) {
                 const int pix = p0 + (mt0 + mt) * 128 + q * 32 + lane;
                 const bool in_range = pix < p.p_end;
-                const int rel = pix - p.G;
-                const int row = rel / p.Wp;
-                const int w = rel - row * p.Wp;
-                int b = -1, h = -1;
-                if (in_range) {
-                    b = __ldg(p.row_b + row);
-                    h = __ldg(p.row_h + row);
-                }
-                valid[mt] = in_range && (w < p.W) && (h >= 0);
-                bidx[mt] = valid[mt] ? b : -1;
-                do_store[mt] = in_range;
-                opix[mt] = pix;
-                if (p.subsample) {
-                    do_store[mt] = valid[mt] && !(h & 1) && !(w & 1);
-                    if (do_store[mt])
-                        opix[mt] = (long long)p.out_G + (long long)(__ldg(p.out_utt_row0 + b) + (h >> 1)) * p.out_Wp + (w >> 1);
-                }
+                bidx[mt] = in_range ? __ldg(p.pix_b + (pix - p.G)) : -1;
+                long long opix = in_range ? (long long)pix : -1;
+                if (p.pix_sub != nullptr) opix = in_range ? (long long)__ldg(p.pix_sub + (pix - p.G)) : -1;
+                optr[mt] = opix >= 0 ? p.out + (size_t)opix * 8 : nullptr;
             }
+            const size_t plane8 = (size_t)p.out_plane * 8;
+            const float slope = p.act_slope;
 #pragma unroll 1
             for (int c0 = 0; c0 < N_CTA; c0 += 16) {
                 long long t[16];
@@ -282,23 +324,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);
                     }
+                    if (!p.bias_mma) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float x = v[i] + bias_s[n_base + c0 + i];
-                        if (p.act == 1) x = fmaxf(x, 0.f);
-                        else if (p.act == 2) x = x > 0.f ? x : 0.2f * x;
-                        v[i] = valid[mt] ? x : 0.f;
+                        for (int i = 0; i < 16; ++i) v[i] += bias_s[n_base + c0 + i];
                     }
-                    if (do_store[mt]) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * slope);
+                    const bool valid = bidx[mt] >= 0;
+                    if (optr[mt] != nullptr) {
+                        uint16_t* dst = optr[mt] + (size_t)((n_base + c0) >> 3) * plane8;
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             uint4 o;
-                            o.x = pack2<BF16>(v[j * 8 + 0], v[j * 8 + 1]);
-                            o.y = pack2<BF16>(v[j * 8 + 2], v[j * 8 + 3]);
-                            o.z = pack2<BF16>(v[j * 8 + 4], v[j * 8 + 5]);
-                            o.w = pack2<BF16>(v[j * 8 + 6], v[j * 8 + 7]);
-                            uint16_t* dst = p.out + ((size_t)((n_base + c0) / 8 + j) * p.out_plane + opix[mt]) * 8;
-                            *reinterpret_cast<uint4*>(dst) = o;
+                            o.x = valid ? pack2<BF16>(v[j * 8 + 0], v[j * 8 + 1]) : 0u;
+                            o.y = valid ? pack2<BF16>(v[j * 8 + 2], v[j * 8 + 3]) : 0u;
+                            o.z = valid ? pack2<BF16>(v[j * 8 + 4], v[j * 8 + 5]) : 0u;
+                            o.w = valid ? pack2<BF16>(v[j * 8 + 6], v[j * 8 + 7]) : 0u;
+                            *reinterpret_cast<uint4*>(dst + j * plane8) = o;
                         }
                     }
                     if (p.se_sums != nullptr) {
@@ -307,12 +349,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                         // whatever the tile / warp / atomic order (and however the batch is packed).  Each lane
                         // first adds up its own pixels; one transposing butterfly per 16-channel block then
                         // reduces across the warp (the rare utterance boundary flushes early).
-                        const bool clash = valid[mt] && b_acc >= 0 && bidx[mt] != b_acc;
+                        const bool clash = valid && b_acc >= 0 && bidx[mt] != b_acc;
                         if (__any_sync(0xffffffffu, clash)) {
                             se_flush(t, lane, b_acc, p.se_sums, p.cout, n_base + c0);
                             b_acc = -1;
                         }
-                        if (valid[mt]) {
+                        if (valid) {
                             b_acc = bidx[mt];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) t[i] += __float2ll_rn(v[i] * 16777216.f);

@@ -381,6 +381,8 @@ struct Level {
     std::vector<int> H;            // lines per utterance
     // offsets (in ints) into the device table buffer
     size_t o_row_b = 0, o_row_h = 0, o_utt_row0 = 0, o_utt_count = 0;
+    size_t o_pix_b = 0, o_pix_sub = 0;   // offsets (ints) into the device pixel-meta buffer; o_pix_sub valid when has_sub
+    bool has_sub = false;
 };
 
 struct Plan {
@@ -430,6 +432,7 @@ struct skb_xtractor {
     Model m;
     Plan plan;
     bool plan_valid = false;
+    DevBuf pixmeta;
     DevBuf tab32, tab64, feats, sums, scale, poolX, poolH, poolL, gc, hb, pooled, lin, emb_pre, emb, logits, wave, dbg;
     std::vector<DevBuf> act;      // activation buffers
     std::vector<size_t> act_bytes;
@@ -439,6 +442,7 @@ struct skb_xtractor {
 
 namespace skb {
 
+static int build_pixmeta(skb_xtractor* h, cudaStream_t st);
 static int num_frames(const Model& m, int64_t n) { return 1 + (int)(n / m.fe.hop); }
 
 static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream_t st) {
@@ -571,19 +575,61 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     if ((rc = h->pooled.ensure((size_t)B * 2 * D * sizeof(float)))) return rc;
     if ((rc = h->lin.ensure((size_t)B * m.emb * sizeof(float)))) return rc;
     if ((rc = h->emb_pre.ensure((size_t)B * m.emb * sizeof(float)))) return rc;
+    if ((rc = build_pixmeta(h, st))) return rc;
     h->plan_valid = true;
+    return SKB_OK;
+}
+
+// Per-pixel tables for the conv epilogue (one coalesced read instead of a division and two dependent gathers):
+// pix_b[rel] = utterance of pixel G + rel or -1 for pad / invalid; pix_sub[rel] = destination pixel at the next
+// level for the pixels a stride-2 convolution keeps (even h, even w), else -1.
+__global__ void pixmeta_kernel(int n, int Wp, int W, const int* __restrict__ row_b, const int* __restrict__ row_h,
+                               int* __restrict__ pix_b, int* __restrict__ pix_sub, int out_G, int out_Wp,
+                               const int* __restrict__ out_utt_row0) {
+    const int rel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rel >= n) return;
+    const int row = rel / Wp, w = rel - row * Wp;
+    const int b = row_b[row], hh = row_h[row];
+    const bool valid = b >= 0 && hh >= 0 && w < W;
+    pix_b[rel] = valid ? b : -1;
+    if (pix_sub) pix_sub[rel] = (valid && !(hh & 1) && !(w & 1)) ? out_G + (out_utt_row0[b] + (hh >> 1)) * out_Wp + (w >> 1) : -1;
+}
+
+static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
+    Plan& pl = h->plan;
+    size_t total = 0;
+    const bool hr = h->m.archi == SKB_ARCHI_HALFRESNET34;
+    for (size_t l = 0; l < pl.lv.size(); ++l) {
+        Level& L = pl.lv[l];
+        const size_t n = (size_t)(L.p_end - L.G);
+        L.o_pix_b = total; total += n;
+        L.has_sub = hr && l + 1 < pl.lv.size();
+        if (L.has_sub) { L.o_pix_sub = total; total += n; }
+    }
+    int rc = h->pixmeta.ensure(total * sizeof(int));
+    if (rc) return rc;
+    int* base = (int*)h->pixmeta.p;
+    for (size_t l = 0; l < pl.lv.size(); ++l) {
+        const Level& L = pl.lv[l];
+        const int n = L.p_end - L.G;
+        const Level* Lo = L.has_sub ? &pl.lv[l + 1] : nullptr;
+        pixmeta_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, L.Wp, L.W, h->d32 + L.o_row_b, h->d32 + L.o_row_h, base + L.o_pix_b,
+                                                        Lo ? base + L.o_pix_sub : nullptr, Lo ? Lo->G : 0, Lo ? Lo->Wp : 0,
+                                                        Lo ? h->d32 + Lo->o_utt_row0 : nullptr);
+    }
+    SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
 }
 
 // ----------------------------------------------------------------------------- conv launch helper
 static int run_conv(skb_xtractor* h, const ConvW& cw, const Level& Lin, const uint16_t* in, uint16_t* out, const Level& Lout,
-                    bool subsample, int act, bool conv3x3, const int* tdnn_shifts, unsigned long long* se_sums, size_t row_h_override,
+                    bool subsample, int act, bool conv3x3, const int* tdnn_shifts, unsigned long long* se_sums, bool pix_from_out,
                     cudaStream_t st) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
     p.in = in; p.in_plane = Lin.plane; p.w = cw.w; p.bias = cw.bias; p.out = out; p.out_plane = Lout.plane;
     p.cin = cw.cin; p.cout = cw.cout; p.taps = cw.taps;
-    p.Wp = Lin.Wp; p.W = Lin.W; p.G = Lin.G; p.p_end = Lin.p_end;
+    p.G = Lin.G; p.p_end = Lin.p_end;
     int max_shift = 0;
     if (conv3x3) {
         p.halo = Lin.Wp + 1;
@@ -598,12 +644,11 @@ static int run_conv(skb_xtractor* h, const ConvW& cw, const Level& Lin, const ui
     }
     const int tile_m = conv_tile_m(cw.ncta);
     p.rows_pad = (tile_m + p.halo + max_shift + 7) / 8 * 8;
-    p.act = act;
-    p.row_b = h->d32 + Lin.o_row_b;
-    p.row_h = h->d32 + (row_h_override ? row_h_override : Lin.o_row_h);
-    p.subsample = subsample ? 1 : 0;
-    p.out_G = Lout.G; p.out_Wp = Lout.Wp;
-    p.out_utt_row0 = h->d32 + Lout.o_utt_row0;
+    p.act_slope = act == 1 ? 0.f : (act == 2 ? 0.2f : 1.f);
+    const int* pm = (const int*)h->pixmeta.p;
+    // the validity table of the OUTPUT level decides what is stored as non-zero (TDNN: same geometry, fewer frames)
+    p.pix_b = pm + (pix_from_out ? Lout.o_pix_b : Lin.o_pix_b);
+    p.pix_sub = subsample ? pm + Lin.o_pix_sub : nullptr;
     p.se_sums = se_sums;
     g_launches++;
     return launch_conv_umma(p, cw.ncta, h->m.bf16, st);
@@ -708,10 +753,10 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
         const uint16_t* res = x;
         {
             ProfScope ps(PROF_CONV, st);
-            SKB_TRY(run_conv(h, bw.conv1, Lin, x, y1, L, bw.stride == 2, 1, true, nullptr, nullptr, 0, st));
-            SKB_TRY(run_conv(h, bw.conv2, L, y1, y2, L, false, 0, true, nullptr, (unsigned long long*)h->sums.p, 0, st));
+            SKB_TRY(run_conv(h, bw.conv1, Lin, x, y1, L, bw.stride == 2, 1, true, nullptr, nullptr, false, st));
+            SKB_TRY(run_conv(h, bw.conv2, L, y1, y2, L, false, 0, true, nullptr, (unsigned long long*)h->sums.p, false, st));
             if (bw.has_sc) {
-                SKB_TRY(run_conv(h, bw.sc, Lin, x, scb, L, bw.stride == 2, 0, false, nullptr, nullptr, 0, st));
+                SKB_TRY(run_conv(h, bw.sc, Lin, x, scb, L, bw.stride == 2, 0, false, nullptr, nullptr, false, st));
                 res = scb;
             }
         }
@@ -779,7 +824,7 @@ static int forward_tdnn(skb_xtractor* h, const float* wave, int norm_embedding, 
         // validity (row_h) of the OUTPUT rows decides what gets stored as non-zero
         ProfScope ps(PROF_CONV, st);
         SKB_TRY(run_conv(h, m.tdnn[i], Lin, (const uint16_t*)h->act[i].p, (uint16_t*)h->act[i + 1].p, Lout, false, 2, false,
-                         shifts, nullptr, Lout.o_row_h, st));
+                         shifts, nullptr, true, st));
         if (stop) {
             char name[32];
             snprintf(name, sizeof(name), "tdnn%d", i + 1);

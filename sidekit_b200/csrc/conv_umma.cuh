@@ -56,7 +56,7 @@ struct ConvParams {
 constexpr int kConvKC = 32;            // input channels per A/B stage (two K=16 MMAs)
 constexpr int kConvMaxAStages = 8;
 constexpr int kConvBStages = 8;
-constexpr int kConvThreads = 12 * 32;  // warps: 0 A-producer, 1 B-producer, 2 MMA, 3 idle, 4..11 epilogue (2 per TMEM quadrant)
+constexpr int kConvThreads = 12 * 32;  // warps: 0 A-producer, 1 B-producer, 2-3 MMA issuers, 4..11 epilogue (2 per TMEM quadrant)
 constexpr int kConvCtrlBytes = 1024;
 constexpr int kConvSmemBudget = 225 * 1024;
 
@@ -76,25 +76,25 @@ struct ConvCfg {
 
 // Fixed-point (2^-24) reduction of 16 per-lane partial channel sums into sums[b][ch0 .. ch0+15].  Lanes that
 // never accumulated (b_lane < 0) hold zeros.  Common case: every contributing lane belongs to one utterance ->
-// transposing butterfly (lane l ends with channel ch0 + (l & 15)) and one coalesced atomic per lane 0..15.
+// two-limb REDUX warp sums (lane i keeps channel ch0 + i) and one coalesced 64-bit atomic per lane 0..15.
 // Utterance boundary inside the warp (rare): each lane adds its own 16 partial sums.
 __device__ __forceinline__ void se_flush(long long (&t)[16], int lane, int b_lane, unsigned long long* sums, int cout, int ch0) {
     const unsigned has = __ballot_sync(0xffffffffu, b_lane >= 0);
     if (has == 0u) return;
     const int b0 = __shfl_sync(0xffffffffu, b_lane, __ffs(has) - 1);
     if (__all_sync(0xffffffffu, b_lane < 0 || b_lane == b0)) {
+        // exact warp sum of 64-bit values with the 32-bit hardware reduction (REDUX): split into a 20-bit low limb and a
+        // signed high limb (|x| < 2^42 => |hi| < 2^22, so 32 lanes cannot overflow either limb), reduce, recombine
+        long long mine = 0ll;
 #pragma unroll
-        for (int s = 8; s >= 1; s >>= 1) {
-            const bool upper = (lane & s) != 0;
-#pragma unroll
-            for (int i = 0; i < s; ++i) {
-                const long long send = upper ? t[i] : t[i + s];
-                const long long keep = upper ? t[i + s] : t[i];
-                t[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-            }
+        for (int i = 0; i < 16; ++i) {
+            const int lo = (int)(t[i] & 0xFFFFFll);
+            const int hi = (int)(t[i] >> 20);
+            const int slo = __reduce_add_sync(0xffffffffu, lo);
+            const int shi = __reduce_add_sync(0xffffffffu, hi);
+            if (lane == i) mine = ((long long)shi << 20) + (long long)slo;
         }
-        t[0] += __shfl_xor_sync(0xffffffffu, t[0], 16);
-        if (lane < 16) atomicAdd(sums + (size_t)b0 * cout + ch0 + lane, (unsigned long long)t[0]);
+        if (lane < 16) atomicAdd(sums + (size_t)b0 * cout + ch0 + lane, (unsigned long long)mine);
     } else if (b_lane >= 0) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) atomicAdd(sums + (size_t)b_lane * cout + ch0 + i, (unsigned long long)t[i]);
@@ -129,9 +129,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     const int n_kc = p.cin / kConvKC;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kConvMaxAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < kConvBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }   // first b_stages used
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        // two MMA-issuing warps (one half of the accumulator tiles each) arrive on the "consumed" barriers
+        for (int i = 0; i < kConvMaxAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
+        for (int i = 0; i < kConvBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }   // first b_stages used
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], 8); }
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < p.cout; i += blockDim.x) bias_s[i] = p.bias[i];
@@ -163,19 +164,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         // ---------------------------------------------------------------- A producer: activation slabs
         if (lane == 0) {
             const uint32_t plane_bytes = (uint32_t)p.rows_pad * 16;
-            long long cnt = 0;
+            int s = 0;
+            uint32_t ph = 1;     // ring position / parity kept incrementally (no divisions on the critical paths)
+            int tile = blockIdx.x / n_split, ns_ctr = blockIdx.x % n_split;
+            const int tile_step = gridDim.x / n_split, ns_step = gridDim.x % n_split;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int tile = item / n_split;
                 const long long q0 = (long long)p.G + (long long)tile * Cfg::kTileM - p.halo;   // >= 0 thanks to the guard G
-                for (int kc = 0; kc < n_kc; ++kc, ++cnt) {
-                    const int s = (int)(cnt % p.a_stages);
-                    mbar_wait(&a_empty[s], (uint32_t)((cnt / p.a_stages) & 1) ^ 1);
+                tile += tile_step; ns_ctr += ns_step;
+                if (ns_ctr >= n_split) { ns_ctr -= n_split; ++tile; }
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(&a_empty[s], ph);
                     mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
 #pragma unroll
                     for (int j = 0; j < kConvKC / 8; ++j) {
                         const uint16_t* src = p.in + ((size_t)(kc * (kConvKC / 8) + j) * p.in_plane + q0) * 8;
                         bulk_g2s(a_smem + (size_t)s * a_stage_bytes + j * plane_bytes, src, plane_bytes, &a_full[s]);
                     }
+                    if (++s == p.a_stages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -191,23 +196,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                              &b_full[0]);
             } else {
                 const int n_st = n_it / p.tps;             // weight stages per item
-                long long cnt = 0;
+                int s = 0;
+                uint32_t ph = 1;
+                int ns = blockIdx.x % n_split;
+                const int ns_step = gridDim.x % n_split;
                 for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                    const int ns = item % n_split;
                     const uint16_t* wbase = p.w + (size_t)ns * n_it * (Cfg::kBStageBytes / 2);
-                    for (int it = 0; it < n_st; ++it, ++cnt) {
-                        const int s = (int)(cnt % p.b_stages);
-                        mbar_wait(&b_empty[s], (uint32_t)((cnt / p.b_stages) & 1) ^ 1);
+                    ns += ns_step;
+                    if (ns >= n_split) ns -= n_split;
+                    for (int it = 0; it < n_st; ++it) {
+                        mbar_wait(&b_empty[s], ph);
                         mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
                         bulk_g2s(b_smem + (size_t)s * b_stage_bytes, wbase + (size_t)it * (b_stage_bytes / 2), b_stage_bytes,
                                  &b_full[s]);
+                        if (++s == p.b_stages) { s = 0; ph ^= 1; }
                     }
                 }
             }
         }
-    } else if (warp == 2) {
-        // ---------------------------------------------------------------- MMA issuer
-        // The whole warp walks the loops (so addresses / descriptors stay warp-uniform); one elected lane issues.
+    } else if (warp == 2 || warp == 3) {
+        // ---------------------------------------------------------------- MMA issuers
+        // Two warps, each owning half of the item's MT accumulator tiles (fixed per-accumulator MMA order, so the
+        // result does not depend on their relative timing): issue bandwidth, not the tensor pipe, limits small-N MMAs.
+        // The whole warp walks the loops (addresses / descriptors stay warp-uniform); one elected lane issues.
+        constexpr int MTW = MT / 2;
+        const int mtw0 = (warp - 2) * MTW;
         const uint32_t idesc = umma_idesc_f16(128, N_CTA, BF16);
         const uint32_t a_lbo = (uint32_t)p.rows_pad * 16;   // next 8-channel plane of the slab
         const uint32_t b_lbo = N_CTA * 16;
@@ -215,43 +228,44 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                                    (static_cast<uint64_t>(1) << 46);
         const uint64_t desc_hi_b = (static_cast<uint64_t>((b_lbo >> 4) & 0x3FFF) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
                                    (static_cast<uint64_t>(1) << 46);
-        long long a_cnt = 0, b_cnt = 0, n_done = 0;
+        int as = 0, bs = 0, ns = blockIdx.x % n_split;
+        const int ns_step = gridDim.x % n_split;
+        uint32_t a_ph = 0, b_ph = 0, n_done = 0;
         if (p.b_resident) {
             mbar_wait(&b_full[0], 0);
             tc_fence_after();
         }
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
             const int buf = (int)(n_done & 1);
-            mbar_wait(&acc_empty[buf], (uint32_t)((n_done >> 1) & 1) ^ 1);
+            mbar_wait(&acc_empty[buf], ((n_done >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * Cfg::kAccCols;
+            const int ns_item = ns;
+            ns += ns_step;
+            if (ns >= n_split) ns -= n_split;
             if (p.bias_mma && elect_one()) {
                 const uint64_t ones_desc = (static_cast<uint64_t>(2048 >> 4) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
                                            (static_cast<uint64_t>(1) << 46) | ((smem_u32(ones_smem) >> 4) & 0x3FFF);
-                const uint32_t img = smem_u32(biasimg_smem) + (uint32_t)(item % n_split) * 2 * N_CTA * 16;
+                const uint32_t img = smem_u32(biasimg_smem) + (uint32_t)ns_item * 2 * N_CTA * 16;
                 const uint64_t bias_desc = desc_hi_b | ((img >> 4) & 0x3FFF);
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) umma_f16(d_tmem + mt * N_CTA, ones_desc, bias_desc, idesc, 0u);
+                for (int mt = mtw0; mt < mtw0 + MTW; ++mt) umma_f16(d_tmem + mt * N_CTA, ones_desc, bias_desc, idesc, 0u);
             }
             __syncwarp();
             const uint32_t acc0 = p.bias_mma ? 1u : 0u;
-            for (int kc = 0; kc < n_kc; ++kc, ++a_cnt) {
-                const int as = (int)(a_cnt % p.a_stages);
-                mbar_wait(&a_full[as], (uint32_t)((a_cnt / p.a_stages) & 1));
+            for (int kc = 0; kc < n_kc; ++kc) {
+                mbar_wait(&a_full[as], a_ph);
                 tc_fence_after();
                 const uint32_t a_base = smem_u32(a_smem + (size_t)as * a_stage_bytes) + (uint32_t)p.halo * 16;
                 const int tstep = p.b_resident ? p.taps : p.tps;
                 for (int tap0 = 0; tap0 < p.taps; tap0 += tstep) {
                     uint32_t b_stage;
-                    int bs = 0;
                     if (p.b_resident) {
                         b_stage = smem_u32(b_smem) + (uint32_t)(kc * p.taps) * Cfg::kBStageBytes;
                     } else {
-                        bs = (int)(b_cnt % p.b_stages);
-                        mbar_wait(&b_full[bs], (uint32_t)((b_cnt / p.b_stages) & 1));
+                        mbar_wait(&b_full[bs], b_ph);
                         tc_fence_after();
                         b_stage = smem_u32(b_smem + (size_t)bs * b_stage_bytes);
-                        ++b_cnt;
                     }
                     if (elect_one()) {
                         for (int tt = 0; tt < tstep; ++tt) {
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                             for (int ks = 0; ks < kConvKC / 16; ++ks) {
                                 const uint64_t bdesc = desc_hi_b | (((b_tap + ks * 2 * b_lbo) >> 4) & 0x3FFF);
 #pragma unroll
-                                for (int mt = 0; mt < MT; ++mt) {
+                                for (int mt = mtw0; mt < mtw0 + MTW; ++mt) {
                                     const uint64_t adesc = desc_hi_a | (((a_tap + ks * 2 * a_lbo + mt * 2048) >> 4) & 0x3FFF);
                                     umma_f16(d_tmem + mt * N_CTA, adesc, bdesc, idesc, (kc > 0 || tap > 0 || ks > 0) ? 1u : acc0);
                                 }
@@ -271,9 +285,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                         if (!p.b_resident) umma_commit(&b_empty[bs]);
                     }
                     __syncwarp();
+                    if (!p.b_resident && ++bs == p.b_stages) { bs = 0; b_ph ^= 1; }
                 }
                 if (elect_one()) umma_commit(&a_empty[as]);
                 __syncwarp();
+                if (++as == p.a_stages) { as = 0; a_ph ^= 1; }
             }
             if (elect_one()) umma_commit(&acc_full[buf]);
             __syncwarp();
@@ -284,13 +300,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         constexpr int MTH = MT / 2;
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
         const int mt0 = ((warp - 4) >> 2) * MTH;
-        long long n_done = 0;
+        uint32_t n_done = 0;
+        int tile_next = blockIdx.x / n_split, ns_next = blockIdx.x % n_split;
+        const int tile_step = gridDim.x / n_split, ns_step = gridDim.x % n_split;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
-            const int tile = item / n_split, ns = item % n_split;
+            const int tile = tile_next, ns = ns_next;
+            tile_next += tile_step; ns_next += ns_step;
+            if (ns_next >= n_split) { ns_next -= n_split; ++tile_next; }
             const int buf = (int)(n_done & 1);
             const int p0 = p.G + tile * Cfg::kTileM;
             const int n_base = ns * N_CTA;
-            mbar_wait(&acc_full[buf], (uint32_t)((n_done >> 1) & 1));
+            mbar_wait(&acc_full[buf], (n_done >> 1) & 1);
             tc_fence_after();
             // per-pixel bookkeeping for the pixels this thread owns: one coalesced table read each
             int bidx[MTH];

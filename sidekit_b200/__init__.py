@@ -13,5 +13,7 @@ from .bosaris import Ndx, Scores
 from .statserver import StatServer
 from .iv_scoring import cosine_scoring, PLDA_scoring, fast_PLDA_scoring, two_covariance_scoring, score_matrix
 from .score_normalization import asnorm
+from . import bulk
+from .bulk import extract_embeddings
 
 __version__ = "0.1.0"

@@ -1,0 +1,107 @@
+"""Bulk extraction / scoring across GPUs: one process per GPU, utterances sharded by length
+bucket with greedy FLOP balancing, embeddings all-gathered with NCCL (the path's only collective); score
+matrices are sharded by row panel with no collective at all.  Host logic only -- the per-rank work goes through
+``Xtractor.extract_packed`` / ``score_matrix`` (CUDA).  Mirrors what the reference does one utterance at a time in
+``extract_embeddings`` (sidekit/nnet/xvector.py:1796-1916) and returns the same ``StatServer`` layout.
+"""
+import numpy
+import torch
+
+from .statserver import StatServer
+
+
+def halfresnet34_macs(n_samples):
+    """Algorithmic MACs of one HalfResNet34 embedding (SURVEY.md 8d closed form); used as the balancing weight."""
+    t1 = 1 + n_samples // 160
+    t2 = (t1 - 1) // 2 + 1
+    t3 = (t2 - 1) // 2 + 1
+    t4 = (t3 - 1) // 2 + 1
+    return 80 * t1 * 56608 + 40 * t2 * 278528 + 20 * t3 * 1703936 + 10 * t4 * 3276800 + 1310720 * t4 + 1350016
+
+
+def plan_shards(lengths, world_size, cost=halfresnet34_macs):
+    """Deterministic assignment of utterances to ranks: longest-first greedy on the MAC count.
+    Returns ``world_size`` index arrays, each sorted by length (so consecutive batches are length buckets)."""
+    lengths = numpy.asarray(lengths, dtype=numpy.int64)
+    order = numpy.argsort(-lengths, kind="stable")
+    load = numpy.zeros(world_size, dtype=numpy.float64)
+    shards = [[] for _ in range(world_size)]
+    for i in order:
+        r = int(numpy.argmin(load))            # ties -> lowest rank: deterministic
+        shards[r].append(int(i))
+        load[r] += float(cost(int(lengths[i])))
+    return [numpy.array(sorted(s, key=lambda i: (int(lengths[i]), i)), dtype=numpy.int64) for s in shards]
+
+
+def make_batches(indices, lengths, max_audio_seconds=1200.0, max_utts=256, sample_rate=16000):
+    """Split a length-sorted index list into packed batches bounded by total audio (activation memory) and count."""
+    batches, cur, cur_s = [], [], 0.0
+    for i in indices:
+        s = float(lengths[i]) / sample_rate
+        if cur and (cur_s + s > max_audio_seconds or len(cur) >= max_utts):
+            batches.append(cur)
+            cur, cur_s = [], 0.0
+        cur.append(int(i))
+        cur_s += s
+    if cur:
+        batches.append(cur)
+    return batches
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def extract_embeddings_sharded(extract_fn, waves, embedding_size, max_audio_seconds=1200.0, device=None):
+    """Embeddings of ``waves`` (list of 1-D tensors) on every rank, in input order.
+
+    ``extract_fn(list_of_waves) -> (n, E) tensor`` is ``model.extract_varlen`` in production.  Each rank extracts
+    its shard in length-bucketed packed batches; one ``all_gather`` of the padded (n_max, E) blocks plus the index
+    vectors restores the global order.  With a single process this is just the batched local extraction.
+    """
+    dist, rank, world = _dist()
+    lengths = numpy.array([int(w.shape[-1]) for w in waves], dtype=numpy.int64)
+    shards = plan_shards(lengths, world)
+    mine = shards[rank]
+    out_dev = device
+    parts = []
+    for batch in make_batches(mine, lengths, max_audio_seconds):
+        e = extract_fn([waves[i] for i in batch])
+        out_dev = e.device if out_dev is None else out_dev
+        parts.append(e.to(torch.float32))
+    if out_dev is None:
+        out_dev = torch.device("cpu")
+    local = torch.cat(parts) if parts else torch.zeros((0, embedding_size), dtype=torch.float32, device=out_dev)
+    n = len(waves)
+    result = torch.empty((n, embedding_size), dtype=torch.float32, device=out_dev)
+    if world == 1:
+        result[torch.as_tensor(mine, device=out_dev)] = local
+        return result
+    n_max = max(len(s) for s in shards)
+    block = torch.zeros((n_max, embedding_size), dtype=torch.float32, device=out_dev)
+    block[: local.shape[0]] = local
+    gathered = torch.empty((world * n_max, embedding_size), dtype=torch.float32, device=out_dev)
+    dist.all_gather_into_tensor(gathered, block)
+    for r, s in enumerate(shards):             # shards are a pure function of (lengths, world): no index exchange needed
+        result[torch.as_tensor(s, device=out_dev)] = gathered[r * n_max: r * n_max + len(s)]
+    return result
+
+
+def extract_embeddings(ids, waves, model, max_audio_seconds=1200.0):
+    """In-memory counterpart of the reference's ``extract_embeddings``: returns a ``StatServer`` whose ``stat1`` holds
+    the embeddings and ``stat0`` ones (xvector.py:1905-1914)."""
+    emb = extract_embeddings_sharded(lambda ws: model.extract_varlen([w.to(next(model.parameters()).device) for w in ws]),
+                                     waves, model.embedding_size, max_audio_seconds)
+    return StatServer.from_embeddings(numpy.asarray(ids), emb.cpu().numpy())
+
+
+def row_panel(n_rows, rank=None, world=None):
+    """Contiguous block of enrol rows scored by this rank (score-matrix sharding; no collective)."""
+    dist, r, w = _dist()
+    rank = r if rank is None else rank
+    world = w if world is None else world
+    per = (n_rows + world - 1) // world
+    return min(rank * per, n_rows), min((rank + 1) * per, n_rows)

@@ -31,20 +31,26 @@ extern std::atomic<long long> g_launches;
 // ----------------------------------------------------------------------------- operand preparation
 // stats[0] = max |x| (as float bits), stats[1] = max row sum of squares (float bits)
 __global__ void absmax_kernel(const float* __restrict__ X, int rows, int D, unsigned* __restrict__ stats) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const int lane = threadIdx.x & 31;
-    float mx = 0.f, ss = 0.f;
-    for (int k = lane; k < D; k += 32) {
-        const float v = X[(size_t)row * D + k];
-        mx = fmaxf(mx, fabsf(v));
-        ss = fmaf(v, v, ss);
+    // one warp per row, block-level max, a single pair of atomics per CTA
+    __shared__ float smx[8], sss[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float mx = 0.f, ssm = 0.f;
+    for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+        float ss = 0.f;
+        for (int k = lane; k < D; k += 32) {
+            const float v = X[(size_t)row * D + k];
+            mx = fmaxf(mx, fabsf(v));
+            ss = fmaf(v, v, ss);
+        }
+        ssm = fmaxf(ssm, warp_sum(ss));
     }
     mx = warp_max(mx);
-    ss = warp_sum(ss);
-    if (lane == 0) {
+    if (lane == 0) { smx[warp] = mx; sss[warp] = ssm; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) { mx = fmaxf(mx, smx[i]); ssm = fmaxf(ssm, sss[i]); }
         atomicMax(stats, __float_as_uint(mx));          // non-negative floats order like their bit patterns
-        atomicMax(stats + 1, __float_as_uint(ss));
+        atomicMax(stats + 1, __float_as_uint(ssm));
     }
 }
 
@@ -66,7 +72,8 @@ __global__ void decide_kernel(const unsigned* statsE, const unsigned* statsT, in
     ctrl[2] = passes;
 }
 
-// X (rows, D) fp32 -> hi / lo fp16 planes [Dp/8][rows_pad][8]; rows >= `rows` and columns >= D are zero.
+// X (rows, D) fp32 -> hi / lo fp16 in 128-row tiles of chunk planes: [rows_pad/128][Dp/8][128][8], so that a whole
+// (tile, K range) operand image is one contiguous block = one bulk copy; rows >= `rows` and columns >= D are zero.
 __global__ void pack_split_kernel(const float* __restrict__ X, int rows, int rows_pad, int D, int Dp,
                                   const int* __restrict__ ctrl, int which, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,14 +93,14 @@ __global__ void pack_split_kernel(const float* __restrict__ X, int rows, int row
     uint4 oh, ol;
     oh.x = pack2<false>(h[0], h[1]); oh.y = pack2<false>(h[2], h[3]); oh.z = pack2<false>(h[4], h[5]); oh.w = pack2<false>(h[6], h[7]);
     ol.x = pack2<false>(l[0], l[1]); ol.y = pack2<false>(l[2], l[3]); ol.z = pack2<false>(l[4], l[5]); ol.w = pack2<false>(l[6], l[7]);
-    const size_t o = ((size_t)j * rows_pad + row) * 8;
+    const size_t o = (((size_t)(row >> 7) * chunks + j) * 128 + (row & 127)) * 8;
     *reinterpret_cast<uint4*>(hi + o) = oh;
     *reinterpret_cast<uint4*>(lo + o) = ol;
 }
 
 // ----------------------------------------------------------------------------- the GEMM
 struct ScoreParams {
-    const uint16_t *Ehi, *Elo, *Thi, *Tlo;   // planes [Dp/8][rows_pad][8]
+    const uint16_t *Ehi, *Elo, *Thi, *Tlo;   // [rows_pad/128][Dp/8][128][8]
     int Ne, Nt, Ne_pad, Nt_pad, Dp;
     const int* ctrl;                          // scale exponents + passes (device)
     const float *ra, *ca;                     // multiplicative row / column terms (may be null)
@@ -106,22 +113,24 @@ struct ScoreParams {
     int tiles_total, n_ntiles;
 };
 
-constexpr int kScThreads = 6 * 32;       // warps: 0 producer, 1 MMA, 2..5 epilogue
+constexpr int kScEpiWarps = 8;
+constexpr int kScThreads = (2 + kScEpiWarps) * 32;   // warps: 0 producer, 1 MMA, 2..9 epilogue (2 per TMEM quadrant)
 constexpr int kScKChunk = 64;
-constexpr int kScBStageBytes = 128 * kScKChunk * 2;      // hi part of one stage (16 KB)
 
-// smem: [ctrl 256 B][A hi (+lo)][B ring][4 warps x [32][33] fp32 transpose buffers]
+// smem: [ctrl 256 B][A hi (+lo)][B ring][8 warps x [32][36] fp32 transpose buffers]
 template <int PASSES>
 struct ScoreSmem {
-    static constexpr int kBStages = PASSES == 1 ? 4 : 2;
+    static constexpr int kBStages = PASSES == 1 ? 7 : 3;
     static constexpr int kParts = PASSES == 1 ? 1 : 2;
-    static constexpr int kStageRowBytes = 33 * 4;        // [32][33] fp32 transpose buffer per epilogue warp
+    static constexpr int kChunk = PASSES == 1 ? 64 : 32;              // K elements per T stage
+    static constexpr int kStageBytes = 128 * kChunk * 2;              // one part (hi or lo) of one stage
+    static constexpr int kStageRowBytes = 36 * 4;        // [32][36] fp32 transpose buffer per epilogue warp (16-byte rows)
     static size_t a_bytes(int Dp) { return (size_t)kParts * 128 * Dp * 2; }
-    static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kParts * kScBStageBytes + 4 * 32 * kStageRowBytes; }
+    static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kParts * kStageBytes + kScEpiWarps * 32 * kStageRowBytes; }
 };
 
 template <int PASSES>
-__global__ void __launch_bounds__(kScThreads) score_gemm_kernel(const ScoreParams p) {
+__global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScoreParams p) {
     using SM = ScoreSmem<PASSES>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
@@ -134,21 +143,22 @@ __global__ void __launch_bounds__(kScThreads) score_gemm_kernel(const ScoreParam
     uint8_t* a_smem = smem + 256;
     const uint32_t a_part = 128 * p.Dp * 2;
     uint8_t* b_smem = a_smem + SM::kParts * a_part;
-    uint8_t* stage_smem = b_smem + SM::kBStages * SM::kParts * kScBStageBytes;
+    uint8_t* stage_smem = b_smem + SM::kBStages * SM::kParts * SM::kStageBytes;
 
     if (p.ctrl[2] != PASSES) return;   // the other instantiation handles this launch (uniform across the grid)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // contiguous run of tiles for this CTA
-    const long long t_begin = (long long)p.tiles_total * blockIdx.x / gridDim.x;
-    const long long t_end = (long long)p.tiles_total * (blockIdx.x + 1) / gridDim.x;
-    const int n_kc = p.Dp / kScKChunk;
+    // contiguous run of tiles for this CTA (panel-major), walked with incremental (panel, nt) counters
+    const int t_begin = (int)((long long)p.tiles_total * blockIdx.x / gridDim.x);
+    const int t_end = (int)((long long)p.tiles_total * (blockIdx.x + 1) / gridDim.x);
+    const int panel0 = t_begin / p.n_ntiles, nt0 = t_begin % p.n_ntiles;
+    const int n_kc = p.Dp / SM::kChunk;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int i = 0; i < SM::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kScEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -158,133 +168,186 @@ __global__ void __launch_bounds__(kScThreads) score_gemm_kernel(const ScoreParam
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        // ---------------------------------------------------------------- producer: E panel (on change) + T chunks
         if (lane == 0) {
-            int cur_panel = -1, n_panels = 0;
-            long long it = 0;
-            for (long long t = t_begin; t < t_end; ++t) {
-                const int panel = (int)(t / p.n_ntiles), nt = (int)(t % p.n_ntiles);
-                if (panel != cur_panel) {
-                    mbar_wait(a_empty, (n_panels & 1) ^ 1);
+            int panel = panel0, nt = nt0, s = 0;
+            uint32_t b_ph = 1, a_ph = 1;
+            bool new_panel = true;
+            for (int t = t_begin; t < t_end; ++t) {
+                if (new_panel) {
+                    mbar_wait(a_empty, a_ph);
+                    a_ph ^= 1;
                     mbar_arrive_expect_tx(a_full, SM::kParts * a_part);
                     for (int part = 0; part < SM::kParts; ++part) {
-                        const uint16_t* src = part == 0 ? p.Ehi : p.Elo;
-                        for (int j = 0; j < p.Dp / 8; ++j)
-                            bulk_g2s(a_smem + part * a_part + j * 2048, src + ((size_t)j * p.Ne_pad + (size_t)panel * 128) * 8, 2048, a_full);
+                        const uint16_t* src = (part == 0 ? p.Ehi : p.Elo) + (size_t)panel * p.Dp * 128;
+                        for (uint32_t off = 0; off < a_part; off += 32768)      // whole panel image is contiguous
+                            bulk_g2s(a_smem + part * a_part + off, src + off / 2, min(32768u, a_part - off), a_full);
                     }
-                    cur_panel = panel;
-                    n_panels++;
                 }
-                for (int kc = 0; kc < n_kc; ++kc, ++it) {
-                    const int s = (int)(it % SM::kBStages);
-                    mbar_wait(&b_empty[s], (uint32_t)((it / SM::kBStages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&b_full[s], SM::kParts * kScBStageBytes);
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(&b_empty[s], b_ph);
+                    mbar_arrive_expect_tx(&b_full[s], SM::kParts * SM::kStageBytes);
                     for (int part = 0; part < SM::kParts; ++part) {
-                        const uint16_t* src = part == 0 ? p.Thi : p.Tlo;
-                        uint8_t* dst = b_smem + (s * SM::kParts + part) * kScBStageBytes;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            bulk_g2s(dst + j * 2048, src + ((size_t)(kc * 8 + j) * p.Nt_pad + (size_t)nt * 128) * 8, 2048, &b_full[s]);
+                        const uint16_t* src = (part == 0 ? p.Thi : p.Tlo) + ((size_t)nt * p.Dp + (size_t)kc * SM::kChunk) * 128;
+                        bulk_g2s(b_smem + (s * SM::kParts + part) * SM::kStageBytes, src, SM::kStageBytes, &b_full[s]);   // contiguous planes
                     }
+                    if (++s == SM::kBStages) { s = 0; b_ph ^= 1; }
                 }
+                new_panel = false;
+                if (++nt == p.n_ntiles) { nt = 0; ++panel; new_panel = true; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(128, 128, false);
-            int cur_panel = -1, n_panels = 0;
-            long long it = 0, nt_done = 0;
-            for (long long t = t_begin; t < t_end; ++t, ++nt_done) {
-                const int panel = (int)(t / p.n_ntiles);
-                if (panel != cur_panel) {
-                    mbar_wait(a_full, n_panels & 1);
-                    cur_panel = panel;
-                    n_panels++;
-                }
-                const int buf = (int)(nt_done & 1);
-                mbar_wait(&acc_empty[buf], (uint32_t)((nt_done >> 1) & 1) ^ 1);
+        // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one elected lane)
+        const uint32_t idesc = umma_idesc_f16(128, 128, false);
+        const uint64_t desc_hi = (static_cast<uint64_t>(2048 >> 4) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
+                                 (static_cast<uint64_t>(1) << 46);
+        int nt = nt0, s = 0;
+        uint32_t b_ph = 0, a_ph = 0, nt_done = 0;
+        bool new_panel = true;
+        for (int t = t_begin; t < t_end; ++t, ++nt_done) {
+            if (new_panel) {
+                mbar_wait(a_full, a_ph);
+                a_ph ^= 1;
+            }
+            const int buf = (int)(nt_done & 1);
+            mbar_wait(&acc_empty[buf], ((nt_done >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * 128;
+            for (int kc = 0; kc < n_kc; ++kc) {
+                mbar_wait(&b_full[s], b_ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * 128;
-                for (int kc = 0; kc < n_kc; ++kc, ++it) {
-                    const int s = (int)(it % SM::kBStages);
-                    mbar_wait(&b_full[s], (uint32_t)((it / SM::kBStages) & 1));
-                    tc_fence_after();
-                    const uint32_t b_hi = smem_u32(b_smem + (s * SM::kParts) * kScBStageBytes);
-                    const uint32_t a_hi = smem_u32(a_smem) + kc * 8 * 2048;
+                const uint32_t b_hi = smem_u32(b_smem + (s * SM::kParts) * SM::kStageBytes);
+                const uint32_t a_hi = smem_u32(a_smem) + kc * (SM::kChunk / 8) * 2048;
+                if (elect_one()) {
 #pragma unroll
                     for (int combo = 0; combo < (PASSES == 1 ? 1 : 3); ++combo) {
                         // combo 0: hi*hi, 1: hi*lo, 2: lo*hi
                         const uint32_t a_b = a_hi + (combo == 2 ? a_part : 0);
-                        const uint32_t b_b = b_hi + (combo == 1 ? kScBStageBytes : 0);
+                        const uint32_t b_b = b_hi + (combo == 1 ? SM::kStageBytes : 0);
 #pragma unroll
-                        for (int ks = 0; ks < kScKChunk / 16; ++ks) {
-                            const uint64_t ad = umma_desc_kmajor_noswz(a_b + ks * 2 * 2048, 2048, 128);
-                            const uint64_t bd = umma_desc_kmajor_noswz(b_b + ks * 2 * 2048, 2048, 128);
+                        for (int ks = 0; ks < SM::kChunk / 16; ++ks) {
+                            const uint64_t ad = desc_hi | (((a_b + ks * 2 * 2048) >> 4) & 0x3FFF);
+                            const uint64_t bd = desc_hi | (((b_b + ks * 2 * 2048) >> 4) & 0x3FFF);
                             umma_f16(d_tmem, ad, bd, idesc, (kc > 0 || combo > 0 || ks > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(&b_empty[s]);
                 }
+                __syncwarp();
+                if (++s == SM::kBStages) { s = 0; b_ph ^= 1; }
+            }
+            new_panel = false;
+            if (++nt == p.n_ntiles) { nt = 0; new_panel = true; }
+            const bool last_of_panel = new_panel || (t + 1 == t_end);
+            if (elect_one()) {
                 umma_commit(&acc_full[buf]);
-                const bool last_of_panel = (t + 1 == t_end) || ((int)((t + 1) / p.n_ntiles) != panel);
                 if (last_of_panel) umma_commit(a_empty);
             }
+            __syncwarp();
         }
-    } else {
+    } else if (warp >= 2) {
+        // ---------------------------------------------------------------- epilogue: 8 warps, 2 per TMEM lane quadrant
         const int q = warp & 3;
-        float* stg = reinterpret_cast<float*>(stage_smem) + q * 32 * 33;     // warp-private [32][33] transpose buffer
+        const int half = (warp - 2) >> 2;                  // which two of the four 32-column blocks
+        float* stg = reinterpret_cast<float*>(stage_smem) + (warp - 2) * 32 * 36;   // warp-private [32][36] transpose buffer
+        const int esz = p.out_f64 ? 8 : 4;
+        const bool vec_ok = ((p.ld_out * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                            (p.q == nullptr || (reinterpret_cast<uintptr_t>(p.q) & 15) == 0);
         const float inv_scale = ldexpf(1.f, -(p.ctrl[0] + p.ctrl[1]));
         const float a0 = p.a0 * inv_scale;
         const float mscale = p.mul_scaled ? inv_scale : 1.f;
-        long long nt_done = 0;
-        for (long long t = t_begin; t < t_end; ++t, ++nt_done) {
-            const int panel = (int)(t / p.n_ntiles), nt = (int)(t % p.n_ntiles);
+        int panel = panel0, nt = nt0;
+        uint32_t nt_done = 0;
+        for (int t = t_begin; t < t_end; ++t, ++nt_done) {
             const int buf = (int)(nt_done & 1);
-            mbar_wait(&acc_full[buf], (uint32_t)((nt_done >> 1) & 1));
-            tc_fence_after();
             const int row0 = panel * 128 + q * 32;
             const int my_row = row0 + lane;
             const float ra = (p.ra && my_row < p.Ne) ? p.ra[my_row] * mscale : 0.f;
-            const float rr = (p.r && my_row < p.Ne) ? p.r[my_row] : 0.f;
+            const float rr = fmaf((p.r && my_row < p.Ne) ? p.r[my_row] : 0.f, p.rq_scale, p.c0);
             const int n_rows = min(32, p.Ne - row0);
+            mbar_wait(&acc_full[buf], (nt_done >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-            for (int cb = 0; cb < 4; ++cb) {
+            for (int cbi = 0; cbi < 2; ++cbi) {
+                const int cb = half * 2 + cbi;
                 const int col0 = nt * 128 + cb * 32;
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + cb * 32, v);
-                if (cb == 3) {   // accumulator fully read: hand the TMEM buffer back to the MMA warp
+                if (cbi == 1) {   // this warp's share of the accumulator is read: release the TMEM buffer
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
                 if (col0 >= p.Nt || n_rows <= 0) continue;
-                // transpose through shared memory so that each store instruction writes one 128-byte
-                // (256-byte for fp64) row segment: lane l owns column col0 + l in the write phase
+                // Transpose through shared memory: lane = row before the transpose (row terms applied there),
+                // lane = 4 columns x 1 of 4 rows after it, so every store instruction writes four 128-byte row segments.
                 __syncwarp();
+                const bool fast = (p.ca == nullptr) && n_rows == 32 && col0 + 32 <= p.Nt && vec_ok;
+                if (fast) {
+                    const float mul = ra + a0;
+                    float4* srow = reinterpret_cast<float4*>(stg + lane * 36);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = v[i];
+                    for (int k = 0; k < 8; ++k)
+                        srow[k] = make_float4(fmaf(v[4 * k], mul, rr), fmaf(v[4 * k + 1], mul, rr), fmaf(v[4 * k + 2], mul, rr),
+                                              fmaf(v[4 * k + 3], mul, rr));
+                    __syncwarp();
+                    const int rs = lane >> 3, c4 = (lane & 7) * 4;
+                    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.q) qv = __ldg(reinterpret_cast<const float4*>(p.q + col0 + c4));
+                    qv.x *= p.rq_scale; qv.y *= p.rq_scale; qv.z *= p.rq_scale; qv.w *= p.rq_scale;
+                    if (p.out_f64) {
+                        double* o = reinterpret_cast<double*>(p.out) + (size_t)(row0 + rs) * p.ld_out + col0 + c4;
+                        const size_t step = (size_t)4 * p.ld_out;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it, o += step) {
+                            const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
+                            reinterpret_cast<double2*>(o)[0] = make_double2((double)(x.x + qv.x), (double)(x.y + qv.y));
+                            reinterpret_cast<double2*>(o)[1] = make_double2((double)(x.z + qv.z), (double)(x.w + qv.w));
+                        }
+                    } else {
+                        float* o = reinterpret_cast<float*>(p.out) + (size_t)(row0 + rs) * p.ld_out + col0 + c4;
+                        const size_t step = (size_t)4 * p.ld_out;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it, o += step) {
+                            const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
+                            *reinterpret_cast<float4*>(o) = make_float4(x.x + qv.x, x.y + qv.y, x.z + qv.z, x.w + qv.w);
+                        }
+                    }
+                    continue;
+                }
+                // generic path: ragged tile edges, unaligned outputs, or the as-norm form whose column term also
+                // multiplies the accumulator
+                if (p.ca == nullptr) {
+                    const float mul = ra + a0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) stg[lane * 36 + i] = fmaf(v[i], mul, rr);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) stg[lane * 36 + i] = v[i];
+                }
                 __syncwarp();
                 const int col = col0 + lane;
                 const bool col_ok = col < p.Nt;
+                const float qq = ((p.q && col_ok) ? __ldg(p.q + col) : 0.f) * p.rq_scale;
                 const float ca = (p.ca && col_ok) ? __ldg(p.ca + col) * mscale : 0.f;
-                const float qq = (p.q && col_ok) ? __ldg(p.q + col) : 0.f;
-                if (p.out_f64) {
-                    double* o = reinterpret_cast<double*>(p.out) + (size_t)row0 * p.ld_out + col;
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) {
+                float* o = reinterpret_cast<float*>(p.out) + (size_t)row0 * p.ld_out + col;
+                double* od = reinterpret_cast<double*>(p.out) + (size_t)row0 * p.ld_out + col;
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                    float sv = stg[r * 36 + lane];
+                    if (p.ca != nullptr) {
                         const float ra_r = __shfl_sync(0xffffffffu, ra, r), rr_r = __shfl_sync(0xffffffffu, rr, r);
-                        const float sv = fmaf(stg[r * 33 + lane], ra_r + ca + a0, fmaf(rr_r + qq, p.rq_scale, p.c0));
-                        if (r < n_rows && col_ok) o[(size_t)r * p.ld_out] = (double)sv;
+                        sv = fmaf(sv, ra_r + ca + a0, rr_r);
                     }
-                } else {
-                    float* o = reinterpret_cast<float*>(p.out) + (size_t)row0 * p.ld_out + col;
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) {
-                        const float ra_r = __shfl_sync(0xffffffffu, ra, r), rr_r = __shfl_sync(0xffffffffu, rr, r);
-                        const float sv = fmaf(stg[r * 33 + lane], ra_r + ca + a0, fmaf(rr_r + qq, p.rq_scale, p.c0));
-                        if (r < n_rows && col_ok) o[(size_t)r * p.ld_out] = sv;
+                    sv += qq;
+                    if (r < n_rows && col_ok) {
+                        if (p.out_f64) od[(size_t)r * p.ld_out] = (double)sv;
+                        else o[(size_t)r * p.ld_out] = sv;
                     }
                 }
             }
+            if (++nt == p.n_ntiles) { nt = 0; ++panel; }
         }
     }
     __syncthreads();
@@ -347,8 +410,8 @@ static int score_gemm_general(const float* E, const float* T, int Ne, int Nt, in
     uint16_t* Thi = Elo + eb / 2;
     uint16_t* Tlo = Thi + tb / 2;
     SKB_CUDA_CHECK(cudaMemsetAsync(g_ws.stats, 0, 4 * sizeof(unsigned), st));
-    absmax_kernel<<<(Ne + 7) / 8, 256, 0, st>>>(E, Ne, D, g_ws.stats);
-    absmax_kernel<<<(Nt + 7) / 8, 256, 0, st>>>(T, Nt, D, g_ws.stats + 2);
+    absmax_kernel<<<std::min((Ne + 7) / 8, 4 * kNumSMs), 256, 0, st>>>(E, Ne, D, g_ws.stats);
+    absmax_kernel<<<std::min((Nt + 7) / 8, 4 * kNumSMs), 256, 0, st>>>(T, Nt, D, g_ws.stats + 2);
     decide_kernel<<<1, 1, 0, st>>>(g_ws.stats, g_ws.stats + 2, D, abs_alpha_for_auto, passes, g_ws.ctrl);
     {
         const long long n = (long long)Ne_pad * (Dp / 8);

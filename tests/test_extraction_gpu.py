@@ -144,6 +144,20 @@ def test_tdnn_embeddings_match_oracle_and_golden(tdnn):
     assert torch.equal(emb, solo)
 
 
+def test_bulk_extract_embeddings_statserver(hr34):
+    """bulk.extract_embeddings (length-bucketed batches) == one packed call, bit for bit; StatServer layout as the reference's."""
+    from sidekit_b200 import bulk
+    m, _ = hr34
+    lengths = (16000, 9000, 20321, 16000, 12345, 8000, 30000)
+    waves = [synth.synth_wave(1, L, seed=400 + i)[0] for i, L in enumerate(lengths)]
+    ids = numpy.array(["utt%d" % i for i in range(len(waves))])
+    ss = bulk.extract_embeddings(ids, waves, m, max_audio_seconds=2.5)           # forces several batches
+    ref = m.extract_varlen([w.cuda() for w in waves]).cpu().numpy()
+    assert ss.validate() and ss.stat1.shape == (7, 256) and ss.stat0.shape == (7, 1)
+    assert numpy.array_equal(ss.modelset, ids) and numpy.array_equal(ss.segset, ids)
+    assert numpy.array_equal(ss.stat1.astype(numpy.float32), ref)
+
+
 def test_meanstd_pooling_op():
     from sidekit_b200.nnet import MeanStdPooling
     x = torch.randn(3, 40, 77, generator=torch.Generator().manual_seed(0))

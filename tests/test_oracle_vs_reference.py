@@ -1,0 +1,69 @@
+"""The oracle restatement against the REAL reference, imported from /root/reference (build container only;
+skipped on the GPU box where the reference does not exist)."""
+import copy
+
+import numpy
+import pytest
+import torch
+
+from oracle import extract_ref as R, scoring_ref as S
+from sidekit_b200 import synth
+from tests import kat
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.mark.parametrize("archi,emb,L", [("halfresnet34", 256, 20000), ("xvector", 512, 40000)])
+def test_extraction_restatement_matches_reference(archi, emb, L):
+    from oracle import ref_import
+    m = ref_import.build_xtractor(32, archi, emb)
+    sd = m.state_dict()
+    synth.fill_state_dict(sd, 0)
+    m.load_state_dict(sd)
+    x = synth.synth_wave(2, L, seed=9)
+    with torch.no_grad():
+        lo, em = m(x, is_eval=True)
+    lo2, em2 = R.forward(sd, x, archi)
+    assert (em - em2).abs().max().item() < 2e-6 and (lo - lo2).abs().max().item() < 5e-5
+    fb = R.mel_filterbank(513, 90.0, 7600.0, 80, 16000) if archi == "halfresnet34" else R.mel_filterbank(1025, 133.333, 6855.4976, 100, 16000)
+    key = "preprocessor.MelSpec.mel_scale.fb" if archi == "halfresnet34" else "preprocessor.MFCC.MelSpectrogram.mel_scale.fb"
+    assert torch.equal(fb, sd[key])
+
+
+def test_scoring_kat_recorded_from_reference():
+    """Re-derive SURVEY.md Appendix B from the unmodified reference and compare with tests/kat.py and the oracle."""
+    from oracle import ref_import
+    sidekit = ref_import.import_reference()
+    from sidekit.iv_scoring import cosine_scoring, PLDA_scoring, two_covariance_scoring
+    k = kat.kat_inputs()
+
+    def ss(ids, X):
+        s = sidekit.StatServer()
+        s.modelset = numpy.array(ids); s.segset = numpy.array(ids)
+        s.start = numpy.empty(len(ids), dtype="|O"); s.stop = numpy.empty(len(ids), dtype="|O")
+        s.stat0 = numpy.ones((len(ids), 1)); s.stat1 = numpy.array(X, dtype=numpy.float64)
+        return s
+
+    def ndx():
+        n = sidekit.Ndx()
+        n.modelset, n.segset, n.trialmask = k["ndx_models"].copy(), k["ndx_segs"].copy(), k["trialmask"].copy()
+        return n
+
+    a = (k["en_ids"], k["en"], k["te_ids"], k["te"], k["ndx_models"], k["ndx_segs"], k["trialmask"])
+    B = k["F"] @ k["F"].T + 0.1 * numpy.eye(8)
+    cases = {
+        "plda": (PLDA_scoring(ss(k["en_ids"], k["en"]), ss(k["te_ids"], k["te"]), ndx(), k["mu"], k["F"], numpy.zeros((8, 0)), k["Sigma"]),
+                 S.fast_plda_scoring(*a, k["mu"], k["F"], k["Sigma"])),
+        "twocov": (two_covariance_scoring(ss(k["en_ids"], k["en"]), ss(k["te_ids"], k["te"]), ndx(), k["Sigma"], B),
+                   S.two_covariance_scoring(*a, k["Sigma"], B)),
+        "cosine": (cosine_scoring(ss(k["en_ids"], k["en"]), ss(k["te_ids"], k["te"]), ndx(), device=torch.device("cpu")),
+                   S.cosine_scoring(*a)),
+    }
+    for name, (ref, mine) in cases.items():
+        assert ref.modelset.tolist() == mine[0].tolist() == kat.KAT_MODELSET
+        assert ref.segset.tolist() == mine[1].tolist() == kat.KAT_SEGSET
+        assert numpy.array_equal(ref.scoremask, mine[2])
+        assert ref.scoremat.dtype == mine[3].dtype
+        tol = 1e-9 if ref.scoremat.dtype == numpy.float64 else 1e-6
+        assert numpy.abs(ref.scoremat - mine[3]).max() < tol
+        assert numpy.abs(ref.scoremat[0] - numpy.array(kat.KAT[name]["row0"])).max() < max(tol, 1e-9) * 10

@@ -198,6 +198,7 @@ struct Model {
     int att_A = 0, pool_D = 0;
     // head
     float *lin_w = nullptr, *lin_b = nullptr, *be_s = nullptr, *be_t = nullptr, *spk_wn = nullptr;
+    PackedOp p_w1x, p_w1g, p_w2, p_lin, p_spk;   // dense-layer weights packed for the split-precision tcgen05 GEMM
     // tdnn
     std::vector<ConvW> tdnn;
     std::vector<int> tdnn_k, tdnn_d;
@@ -248,7 +249,9 @@ static int build_margin_head(const WeightMap& w, Model* m) {
         const double inv = 1.0 / std::max(std::sqrt(ss), 1e-12);
         for (int k = 0; k < m->emb; ++k) wn[(size_t)i * m->emb + k] = (float)(sw->p[(size_t)i * m->emb + k] * inv);
     }
-    return dev_upload(wn, &m->spk_wn);
+    int rc = dev_upload(wn, &m->spk_wn);
+    if (rc) return rc;
+    return packed_create(m->spk_wn, m->n_spk, m->emb, &m->p_spk, 0);
 }
 
 static int build_hr34(const WeightMap& w, Model* m) {
@@ -315,6 +318,10 @@ static int build_hr34(const WeightMap& w, Model* m) {
     if ((rc = bn_affine(w, "before_speaker_embedding.bn_be", &s, &t))) return rc;
     if ((rc = upload_f(s, &m->be_s))) return rc;
     if ((rc = upload_f(t, &m->be_t))) return rc;
+    if ((rc = packed_create(m->att_w1x, A, D, &m->p_w1x, 0))) return rc;
+    if ((rc = packed_create(m->att_w1g, A, 2 * D, &m->p_w1g, 0))) return rc;
+    if ((rc = packed_create(m->att_w2, D, A, &m->p_w2, 0))) return rc;
+    if ((rc = packed_create(m->lin_w, m->emb, 2 * D, &m->p_lin, 0))) return rc;
     return build_margin_head(w, m);
 }
 
@@ -356,6 +363,7 @@ static int build_tdnn(const WeightMap& w, Model* m) {
     m->emb = (int)lw->shape[0];
     if ((rc = upload_raw(lw, &m->lin_w))) return rc;
     if ((rc = upload_raw(lb, &m->lin_b))) return rc;
+    if ((rc = packed_create(m->lin_w, m->emb, 2 * m->pool_D, &m->p_lin, 0))) return rc;
     return build_margin_head(w, m);
 }
 
@@ -371,6 +379,7 @@ static void free_model(Model* m) {
     cudaFree(m->att_w1x); cudaFree(m->att_w1g); cudaFree(m->att_b1); cudaFree(m->att_bn_s); cudaFree(m->att_bn_t);
     cudaFree(m->att_w2); cudaFree(m->att_b2); cudaFree(m->lin_w); cudaFree(m->lin_b); cudaFree(m->be_s); cudaFree(m->be_t);
     cudaFree(m->spk_wn); cudaFree(m->pool_s); cudaFree(m->pool_t);
+    packed_free(&m->p_w1x); packed_free(&m->p_w1g); packed_free(&m->p_w2); packed_free(&m->p_lin); packed_free(&m->p_spk);
 }
 
 // ----------------------------------------------------------------------------- per-batch plan
@@ -707,11 +716,11 @@ static int head_and_logits(skb_xtractor* h, int norm_embedding, float* emb_out, 
     const Model& m = h->m;
     const int B = h->plan.B, D = m.pool_D;
     // before_speaker_embedding: Linear (+ folded BatchNorm1d) (xvector.py:578-581 / :489-491)
-    SKB_TRY(launch_sgemm_nt((const float*)h->pooled.p, m.lin_w, (float*)h->lin.p, m.lin_b, B, m.emb, 2 * D, 2 * D, 2 * D, m.emb, 1.f, st));
+    SKB_TRY(gemm_nt_split((const float*)h->pooled.p, B, 2 * D, m.p_lin, m.lin_b, 1.f, (float*)h->lin.p, m.emb, st));
     SKB_TRY(launch_head_norm((const float*)h->lin.p, m.be_s, m.be_t, B, m.emb, norm_embedding, (float*)h->emb_pre.p, emb_out, st));
     g_launches += 2;
     if (logits_out && m.n_spk > 0) {   // ArcMarginProduct(target=None): s * cos (loss.py:299-310)
-        SKB_TRY(launch_sgemm_nt(emb_out, m.spk_wn, logits_out, nullptr, B, m.n_spk, m.emb, m.emb, m.emb, m.n_spk, m.margin_s, st));
+        SKB_TRY(gemm_nt_split(emb_out, B, m.emb, m.p_spk, nullptr, m.margin_s, logits_out, m.n_spk, st));
         g_launches++;
     }
     return SKB_OK;
@@ -781,10 +790,10 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     ProfScope pool_scope(PROF_POOL, st);
     SKB_TRY(launch_gather_frames(m.bf16, buf(level, cur), L4.plane, L4.C, L4.W, L4.Wp, L4.G, d32 + pl.o_frame_row, F, X, st));
     SKB_TRY(launch_meanstd(X, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, nullptr, nullptr, (float*)h->gc.p, st));
-    SKB_TRY(launch_sgemm_nt((const float*)h->gc.p, m.att_w1g, (float*)h->hb.p, m.att_b1, B, A, 2 * D, 2 * D, 2 * D, A, 1.f, st));
-    SKB_TRY(launch_sgemm_nt(X, m.att_w1x, Hh, nullptr, F, A, D, D, D, A, 1.f, st));
+    SKB_TRY(gemm_nt_split((const float*)h->gc.p, B, 2 * D, m.p_w1g, m.att_b1, 1.f, (float*)h->hb.p, A, st));
+    SKB_TRY(gemm_nt_split(X, F, D, m.p_w1x, nullptr, 1.f, Hh, A, st));
     SKB_TRY(launch_att_act(Hh, (const float*)h->hb.p, d32 + pl.o_frame_utt, m.att_bn_s, m.att_bn_t, F, A, st));
-    SKB_TRY(launch_sgemm_nt(Hh, m.att_w2, Lg, m.att_b2, F, D, A, A, A, D, 1.f, st));
+    SKB_TRY(gemm_nt_split(Hh, F, A, m.p_w2, m.att_b2, 1.f, Lg, D, st));
     SKB_TRY(launch_softmax_pool(X, Lg, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, (float*)h->pooled.p, st));
     g_launches += 7;
     if (stop && !strcmp(stop, "pooled")) {

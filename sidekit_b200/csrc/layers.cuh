@@ -39,6 +39,19 @@ int launch_sgemm_nt(const float* A, const float* B, float* C, const float* bias,
 int launch_pack_frames(bool bf16, const float* X, int C_src, int C_dst, int n_rows, const int* row_src, uint16_t* out,
                        long long plane, int G, cudaStream_t st);
 
+// scoring.cu: split-precision tcgen05 GEMM on packed fp16 operands (also used for the dense layers of the extractor)
+struct PackedOp {
+    uint16_t* hi = nullptr;      // [rows_pad/128][Dp/8][128][8] fp16 high parts (lo follows in the same allocation)
+    uint16_t* lo = nullptr;
+    unsigned* stats = nullptr;   // device: max |x| bits, max row sum of squares bits, then the int scale exponent
+    int* exp = nullptr;
+    int rows = 0, rows_pad = 0, D = 0, Dp = 0;
+};
+int packed_create(const float* X_dev, int rows, int D, PackedOp* op, cudaStream_t st);
+void packed_free(PackedOp* op);
+int gemm_nt_split(const float* A_dev, int M, int K, const PackedOp& W, const float* bias, float alpha, float* C, int ldc,
+                  cudaStream_t st);
+
 // conv_umma.cu
 int launch_conv_umma(const ConvParams& p, int n_cta, bool bf16, cudaStream_t st);
 int conv_tile_m(int n_cta);          // output pixels per CTA for a given N_CTA configuration

@@ -54,33 +54,34 @@ __global__ void absmax_kernel(const float* __restrict__ X, int rows, int D, unsi
     }
 }
 
-// ctrl[0] = scale exponent of E, ctrl[1] = of T, ctrl[2] = number of passes (1 or 3)
-__global__ void decide_kernel(const unsigned* statsE, const unsigned* statsT, int D, float abs_alpha, int passes_req, int* ctrl) {
-    const float mE = __uint_as_float(statsE[0]), mT = __uint_as_float(statsT[0]);
-    int eE = 0, eT = 0;
-    if (mE > 0.f) { int e; frexpf(mE, &e); eE = 10 - e; }      // mE * 2^eE in [2^9, 2^10)
-    if (mT > 0.f) { int e; frexpf(mT, &e); eT = 10 - e; }
-    ctrl[0] = eE;
-    ctrl[1] = eT;
+// exp[0] = e such that max|x| * 2^e lies in [2^9, 2^10) (0 for an all-zero operand)
+__global__ void exponent_kernel(const unsigned* stats, int* exp_out) {
+    const float m = __uint_as_float(stats[0]);
+    int e = 0;
+    if (m > 0.f) { int fe; frexpf(m, &fe); e = 10 - fe; }
+    exp_out[0] = e;
+}
+
+// passes_out[0] = 1 or 3.  Single-pass error estimate: fp16 rounding 2^-11 per operand, random-sign accumulation over D terms.
+__global__ void decide_kernel(const unsigned* statsE, const unsigned* statsT, int D, float abs_alpha, int passes_req, int* passes_out) {
     int passes = passes_req;
     if (passes == 0) {
-        // single-pass error estimate: fp16 rounding 2^-11 per operand, random-sign accumulation over D terms
         const float nE = sqrtf(__uint_as_float(statsE[1])), nT = sqrtf(__uint_as_float(statsT[1]));
         const float est = abs_alpha * 4.8828125e-4f * nE * nT * 4.f * rsqrtf((float)D);
         passes = est < 2.5e-4f ? 1 : 3;
     }
-    ctrl[2] = passes;
+    passes_out[0] = passes;
 }
 
 // X (rows, D) fp32 -> hi / lo fp16 in 128-row tiles of chunk planes: [rows_pad/128][Dp/8][128][8], so that a whole
 // (tile, K range) operand image is one contiguous block = one bulk copy; rows >= `rows` and columns >= D are zero.
 __global__ void pack_split_kernel(const float* __restrict__ X, int rows, int rows_pad, int D, int Dp,
-                                  const int* __restrict__ ctrl, int which, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+                                  const int* __restrict__ exp_dev, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int chunks = Dp >> 3;
     if (idx >= (long long)rows_pad * chunks) return;
     const int row = (int)(idx % rows_pad), j = (int)(idx / rows_pad);
-    const float sc = ldexpf(1.f, ctrl[which]);
+    const float sc = ldexpf(1.f, exp_dev[0]);
     float h[8], l[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -102,7 +103,7 @@ __global__ void pack_split_kernel(const float* __restrict__ X, int rows, int row
 struct ScoreParams {
     const uint16_t *Ehi, *Elo, *Thi, *Tlo;   // [rows_pad/128][Dp/8][128][8]
     int Ne, Nt, Ne_pad, Nt_pad, Dp;
-    const int* ctrl;                          // scale exponents + passes (device)
+    const int *expE, *expT, *passes;          // per-operand scale exponents and the pass count (all on the device)
     const float *ra, *ca;                     // multiplicative row / column terms (may be null)
     const float *r, *q;                       // additive row / column terms (may be null)
     float a0, c0, rq_scale;                   // acc * (ra_i + ca_j + a0) * 2^-(eE+eT) + rq_scale * (r_i + q_j) + c0
@@ -118,20 +119,22 @@ constexpr int kScThreads = (2 + kScEpiWarps) * 32;   // warps: 0 producer, 1 MMA
 constexpr int kScKChunk = 64;
 
 // smem: [ctrl 256 B][A hi (+lo)][B ring][8 warps x [32][36] fp32 transpose buffers]
-template <int PASSES>
+template <int PASSES, bool STREAM_A>
 struct ScoreSmem {
-    static constexpr int kBStages = PASSES == 1 ? 7 : 3;
     static constexpr int kParts = PASSES == 1 ? 1 : 2;
-    static constexpr int kChunk = PASSES == 1 ? 64 : 32;              // K elements per T stage
-    static constexpr int kStageBytes = 128 * kChunk * 2;              // one part (hi or lo) of one stage
+    static constexpr int kChunk = PASSES == 1 ? 64 : 32;              // K elements per stage
+    static constexpr int kStageBytes = 128 * kChunk * 2;              // one part (hi or lo) of one operand of one stage
+    // resident-panel mode: a stage holds a T chunk; streaming mode (large K): an E chunk and a T chunk
+    static constexpr int kRingStageBytes = (STREAM_A ? 2 : 1) * kParts * kStageBytes;
+    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? 7 : 3);
     static constexpr int kStageRowBytes = 36 * 4;        // [32][36] fp32 transpose buffer per epilogue warp (16-byte rows)
-    static size_t a_bytes(int Dp) { return (size_t)kParts * 128 * Dp * 2; }
-    static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kParts * kStageBytes + kScEpiWarps * 32 * kStageRowBytes; }
+    __host__ __device__ static size_t a_bytes(int Dp) { return STREAM_A ? 0 : (size_t)kParts * 128 * Dp * 2; }
+    static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kRingStageBytes + kScEpiWarps * 32 * kStageRowBytes; }
 };
 
-template <int PASSES>
+template <int PASSES, bool STREAM_A>
 __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScoreParams p) {
-    using SM = ScoreSmem<PASSES>;
+    using SM = ScoreSmem<PASSES, STREAM_A>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* a_empty = a_full + 1;
@@ -142,10 +145,10 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     uint8_t* a_smem = smem + 256;
     const uint32_t a_part = 128 * p.Dp * 2;
-    uint8_t* b_smem = a_smem + SM::kParts * a_part;
-    uint8_t* stage_smem = b_smem + SM::kBStages * SM::kParts * SM::kStageBytes;
+    uint8_t* b_smem = a_smem + SM::a_bytes(p.Dp);
+    uint8_t* stage_smem = b_smem + SM::kBStages * SM::kRingStageBytes;
 
-    if (p.ctrl[2] != PASSES) return;   // the other instantiation handles this launch (uniform across the grid)
+    if (p.passes[0] != PASSES) return;   // the other instantiation handles this launch (uniform across the grid)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // contiguous run of tiles for this CTA (panel-major), walked with incremental (panel, nt) counters
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
             uint32_t b_ph = 1, a_ph = 1;
             bool new_panel = true;
             for (int t = t_begin; t < t_end; ++t) {
-                if (new_panel) {
+                if (!STREAM_A && new_panel) {
                     mbar_wait(a_empty, a_ph);
                     a_ph ^= 1;
                     mbar_arrive_expect_tx(a_full, SM::kParts * a_part);
@@ -186,10 +189,17 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                 }
                 for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(&b_empty[s], b_ph);
-                    mbar_arrive_expect_tx(&b_full[s], SM::kParts * SM::kStageBytes);
-                    for (int part = 0; part < SM::kParts; ++part) {
+                    mbar_arrive_expect_tx(&b_full[s], SM::kRingStageBytes);
+                    uint8_t* dst = b_smem + (size_t)s * SM::kRingStageBytes;
+                    if (STREAM_A) {
+                        for (int part = 0; part < SM::kParts; ++part, dst += SM::kStageBytes) {
+                            const uint16_t* src = (part == 0 ? p.Ehi : p.Elo) + ((size_t)panel * p.Dp + (size_t)kc * SM::kChunk) * 128;
+                            bulk_g2s(dst, src, SM::kStageBytes, &b_full[s]);
+                        }
+                    }
+                    for (int part = 0; part < SM::kParts; ++part, dst += SM::kStageBytes) {
                         const uint16_t* src = (part == 0 ? p.Thi : p.Tlo) + ((size_t)nt * p.Dp + (size_t)kc * SM::kChunk) * 128;
-                        bulk_g2s(b_smem + (s * SM::kParts + part) * SM::kStageBytes, src, SM::kStageBytes, &b_full[s]);   // contiguous planes
+                        bulk_g2s(dst, src, SM::kStageBytes, &b_full[s]);   // contiguous planes
                     }
                     if (++s == SM::kBStages) { s = 0; b_ph ^= 1; }
                 }
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
         uint32_t b_ph = 0, a_ph = 0, nt_done = 0;
         bool new_panel = true;
         for (int t = t_begin; t < t_end; ++t, ++nt_done) {
-            if (new_panel) {
+            if (!STREAM_A && new_panel) {
                 mbar_wait(a_full, a_ph);
                 a_ph ^= 1;
             }
@@ -217,13 +227,15 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
             for (int kc = 0; kc < n_kc; ++kc) {
                 mbar_wait(&b_full[s], b_ph);
                 tc_fence_after();
-                const uint32_t b_hi = smem_u32(b_smem + (s * SM::kParts) * SM::kStageBytes);
-                const uint32_t a_hi = smem_u32(a_smem) + kc * (SM::kChunk / 8) * 2048;
+                const uint32_t st_base = smem_u32(b_smem + (size_t)s * SM::kRingStageBytes);
+                const uint32_t b_hi = st_base + (STREAM_A ? SM::kParts * SM::kStageBytes : 0);
+                const uint32_t a_hi = STREAM_A ? st_base : smem_u32(a_smem) + kc * (SM::kChunk / 8) * 2048;
+                const uint32_t a_lo_off = STREAM_A ? SM::kStageBytes : a_part;
                 if (elect_one()) {
 #pragma unroll
                     for (int combo = 0; combo < (PASSES == 1 ? 1 : 3); ++combo) {
                         // combo 0: hi*hi, 1: hi*lo, 2: lo*hi
-                        const uint32_t a_b = a_hi + (combo == 2 ? a_part : 0);
+                        const uint32_t a_b = a_hi + (combo == 2 ? a_lo_off : 0);
                         const uint32_t b_b = b_hi + (combo == 1 ? SM::kStageBytes : 0);
 #pragma unroll
                         for (int ks = 0; ks < SM::kChunk / 16; ++ks) {
@@ -242,7 +254,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
             const bool last_of_panel = new_panel || (t + 1 == t_end);
             if (elect_one()) {
                 umma_commit(&acc_full[buf]);
-                if (last_of_panel) umma_commit(a_empty);
+                if (!STREAM_A && last_of_panel) umma_commit(a_empty);
             }
             __syncwarp();
         }
@@ -254,7 +266,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
         const int esz = p.out_f64 ? 8 : 4;
         const bool vec_ok = ((p.ld_out * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
                             (p.q == nullptr || (reinterpret_cast<uintptr_t>(p.q) & 15) == 0);
-        const float inv_scale = ldexpf(1.f, -(p.ctrl[0] + p.ctrl[1]));
+        const float inv_scale = ldexpf(1.f, -(p.expE[0] + p.expT[0]));
         const float a0 = p.a0 * inv_scale;
         const float mscale = p.mul_scaled ? inv_scale : 1.f;
         int panel = panel0, nt = nt0;
@@ -357,22 +369,54 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
     }
 }
 
-// ----------------------------------------------------------------------------- workspace + launch
+// ----------------------------------------------------------------------------- packed operands, workspace, launch
+static int packed_alloc(PackedOp* op, int rows, int D) {
+    op->rows = rows; op->D = D;
+    op->Dp = (D + kScKChunk - 1) / kScKChunk * kScKChunk;
+    op->rows_pad = (rows + 127) / 128 * 128;
+    const size_t halves = (size_t)op->Dp * op->rows_pad;
+    SKB_CUDA_CHECK(cudaMalloc(&op->hi, 2 * halves * sizeof(uint16_t)));
+    op->lo = op->hi + halves;
+    SKB_CUDA_CHECK(cudaMalloc(&op->stats, 2 * sizeof(unsigned) + sizeof(int)));
+    op->exp = reinterpret_cast<int*>(op->stats + 2);
+    return SKB_OK;
+}
+
+void packed_free(PackedOp* op) {
+    cudaFree(op->hi);
+    cudaFree(op->stats);
+    *op = PackedOp();
+}
+
+// scale, split into fp16 hi / lo and lay out as 128-row tiles of chunk planes (buffers of `op` already sized)
+static int packed_fill(const float* X, PackedOp* op, cudaStream_t st) {
+    SKB_CUDA_CHECK(cudaMemsetAsync(op->stats, 0, 2 * sizeof(unsigned), st));
+    absmax_kernel<<<std::min((op->rows + 7) / 8, 4 * kNumSMs), 256, 0, st>>>(X, op->rows, op->D, op->stats);
+    exponent_kernel<<<1, 1, 0, st>>>(op->stats, op->exp);
+    const long long n = (long long)op->rows_pad * (op->Dp / 8);
+    pack_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X, op->rows, op->rows_pad, op->D, op->Dp, op->exp, op->hi, op->lo);
+    g_launches += 3;
+    SKB_CUDA_CHECK(cudaGetLastError());
+    return SKB_OK;
+}
+
+int packed_create(const float* X_dev, int rows, int D, PackedOp* op, cudaStream_t st) {
+    int rc = packed_alloc(op, rows, D);
+    if (rc) return rc;
+    return packed_fill(X_dev, op, st);
+}
+
 struct ScoreWorkspace {
     uint16_t* planes = nullptr;
     size_t planes_cap = 0;
-    unsigned* stats = nullptr;   // [4]
-    int* ctrl = nullptr;         // [4]
+    unsigned* stats = nullptr;   // 2 x (2 stats + 1 exponent) + passes
     float* tmp = nullptr;        // scratch score matrix (as-norm cohort scores)
     size_t tmp_cap = 0;
 };
 static thread_local ScoreWorkspace g_ws;
 
 static int ws_ensure(size_t plane_bytes, size_t tmp_bytes) {
-    if (!g_ws.stats) {
-        SKB_CUDA_CHECK(cudaMalloc(&g_ws.stats, 4 * sizeof(unsigned)));
-        SKB_CUDA_CHECK(cudaMalloc(&g_ws.ctrl, 4 * sizeof(int)));
-    }
+    if (!g_ws.stats) SKB_CUDA_CHECK(cudaMalloc(&g_ws.stats, 8 * sizeof(unsigned)));
     if (plane_bytes > g_ws.planes_cap) {
         if (g_ws.planes) cudaFree(g_ws.planes);
         g_ws.planes = nullptr; g_ws.planes_cap = 0;
@@ -388,67 +432,102 @@ static int ws_ensure(size_t plane_bytes, size_t tmp_bytes) {
     return SKB_OK;
 }
 
-// out = acc * (ra_i + ca_j + a0) + (r_i + q_j + c0)
+// workspace-backed operand view (slot 0 / 1 of the plane buffer, stats slots in g_ws.stats)
+static void ws_operand(PackedOp* op, int rows, int D, int slot, size_t offset_halves) {
+    op->rows = rows; op->D = D;
+    op->Dp = (D + kScKChunk - 1) / kScKChunk * kScKChunk;
+    op->rows_pad = (rows + 127) / 128 * 128;
+    op->hi = g_ws.planes + offset_halves;
+    op->lo = op->hi + (size_t)op->Dp * op->rows_pad;
+    op->stats = g_ws.stats + 3 * slot;
+    op->exp = reinterpret_cast<int*>(op->stats + 2);
+}
+
+template <int PASSES, bool STREAM_A>
+static int launch_score(const ScoreParams& p, int grid, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = ScoreSmem<PASSES, STREAM_A>::total(p.Dp);
+    if (smem > 227 * 1024) {
+        set_last_error(__FILE__, __LINE__, "score_gemm: operand panel does not fit in shared memory");
+        return SKB_ERR_ARG;
+    }
+    if (!configured) {
+        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<PASSES, STREAM_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    score_gemm_kernel<PASSES, STREAM_A><<<grid, kScThreads, smem, st>>>(p);
+    g_launches++;
+    SKB_CUDA_CHECK(cudaGetLastError());
+    return SKB_OK;
+}
+
+// out = acc * (ra_i + ca_j + a0) + rq_scale * (r_i + q_j) + c0 on two packed operands
+int gemm_packed(const PackedOp& E, const PackedOp& T, const float* ra, const float* ca, float a0, const float* r, const float* q,
+                float c0, float rq_scale, float abs_alpha_for_auto, int passes, int out_f64, void* out, long long ld_out,
+                cudaStream_t st) {
+    if (E.Dp != T.Dp || !out || ld_out < T.rows || (passes != 0 && passes != 1 && passes != 3)) {
+        set_last_error(__FILE__, __LINE__, "gemm_packed: bad arguments");
+        return SKB_ERR_ARG;
+    }
+    int rc = ws_ensure(0, 0);
+    if (rc) return rc;
+    int* passes_dev = reinterpret_cast<int*>(g_ws.stats + 6);
+    decide_kernel<<<1, 1, 0, st>>>(E.stats, T.stats, E.D, abs_alpha_for_auto, passes, passes_dev);
+    g_launches++;
+    ScoreParams p;
+    p.Ehi = E.hi; p.Elo = E.lo; p.Thi = T.hi; p.Tlo = T.lo;
+    p.Ne = E.rows; p.Nt = T.rows; p.Ne_pad = E.rows_pad; p.Nt_pad = T.rows_pad; p.Dp = E.Dp;
+    p.expE = E.exp; p.expT = T.exp; p.passes = passes_dev;
+    p.ra = ra; p.ca = ca; p.r = r; p.q = q; p.a0 = a0; p.c0 = c0; p.rq_scale = rq_scale;
+    p.mul_scaled = 1;
+    p.out = out; p.ld_out = ld_out; p.out_f64 = out_f64;
+    p.n_ntiles = T.rows_pad / 128;
+    p.tiles_total = (E.rows_pad / 128) * p.n_ntiles;
+    const int grid = std::min(p.tiles_total, kNumSMs);
+    // Large K (dense layers of the pooling / head) streams both operands; K <= 256 keeps the E panel resident.
+    // Both pass variants are launched when the count is decided on the device; exactly one does the work.
+    const bool stream_a = E.Dp > 256;
+    if (passes != 3) rc = stream_a ? launch_score<1, true>(p, grid, st) : launch_score<1, false>(p, grid, st);
+    if (rc) return rc;
+    if (passes != 1) rc = stream_a ? launch_score<3, true>(p, grid, st) : launch_score<3, false>(p, grid, st);
+    return rc;
+}
+
+// C[m][n] = sum_k A[m][k] * W[n][k] + bias[n] with fp32-class accuracy (split fp16 passes): the dense layers of the
+// attentive pooling and the embedding / margin heads.  W is packed once at model-build time.
+int gemm_nt_split(const float* A_dev, int M, int K, const PackedOp& W, const float* bias, float alpha, float* C, int ldc,
+                  cudaStream_t st) {
+    if (K != W.D) {
+        set_last_error(__FILE__, __LINE__, "gemm_nt_split: K mismatch");
+        return SKB_ERR_ARG;
+    }
+    const int Dp = W.Dp, Mp = (M + 127) / 128 * 128;
+    int rc = ws_ensure(2 * (size_t)Dp * Mp * sizeof(uint16_t), 0);
+    if (rc) return rc;
+    PackedOp a;
+    ws_operand(&a, M, K, 0, 0);
+    if ((rc = packed_fill(A_dev, &a, st))) return rc;
+    return gemm_packed(a, W, nullptr, nullptr, alpha, nullptr, bias, 0.f, 1.f, 1.f, 3, 0, C, ldc, st);
+}
+
+// out = acc * (ra_i + ca_j + a0) + rq_scale * (r_i + q_j) + c0 from fp32 row-major operands
 static int score_gemm_general(const float* E, const float* T, int Ne, int Nt, int D, const float* ra, const float* ca, float a0,
                               const float* r, const float* q, float c0, float rq_scale, float abs_alpha_for_auto, int passes, int out_f64,
                               void* out, long long ld_out, size_t tmp_bytes, cudaStream_t st) {
-    if (!E || !T || !out || Ne <= 0 || Nt <= 0 || D <= 0 || ld_out < Nt || (passes != 0 && passes != 1 && passes != 3)) {
+    if (!E || !T || !out || Ne <= 0 || Nt <= 0 || D <= 0 || ld_out < Nt) {
         set_last_error(__FILE__, __LINE__, "score_gemm: bad arguments");
         return SKB_ERR_ARG;
     }
     const int Dp = (D + kScKChunk - 1) / kScKChunk * kScKChunk;
-    if (Dp > 384) {
-        set_last_error(__FILE__, __LINE__, "score_gemm: embedding dimension > 384 not supported by the resident-panel kernel");
-        return SKB_ERR_ARG;
-    }
-    const int Ne_pad = (Ne + 127) / 128 * 128, Nt_pad = (Nt + 127) / 128 * 128;
-    const size_t eb = (size_t)Dp * Ne_pad * 2, tb = (size_t)Dp * Nt_pad * 2;
-    int rc = ws_ensure(2 * (eb + tb), tmp_bytes);
+    const size_t eh = (size_t)Dp * ((Ne + 127) / 128 * 128), th = (size_t)Dp * ((Nt + 127) / 128 * 128);
+    int rc = ws_ensure(2 * (eh + th) * sizeof(uint16_t), tmp_bytes);
     if (rc) return rc;
-    uint16_t* Ehi = g_ws.planes;
-    uint16_t* Elo = Ehi + eb / 2;
-    uint16_t* Thi = Elo + eb / 2;
-    uint16_t* Tlo = Thi + tb / 2;
-    SKB_CUDA_CHECK(cudaMemsetAsync(g_ws.stats, 0, 4 * sizeof(unsigned), st));
-    absmax_kernel<<<std::min((Ne + 7) / 8, 4 * kNumSMs), 256, 0, st>>>(E, Ne, D, g_ws.stats);
-    absmax_kernel<<<std::min((Nt + 7) / 8, 4 * kNumSMs), 256, 0, st>>>(T, Nt, D, g_ws.stats + 2);
-    decide_kernel<<<1, 1, 0, st>>>(g_ws.stats, g_ws.stats + 2, D, abs_alpha_for_auto, passes, g_ws.ctrl);
-    {
-        const long long n = (long long)Ne_pad * (Dp / 8);
-        pack_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, Ne, Ne_pad, D, Dp, g_ws.ctrl, 0, Ehi, Elo);
-    }
-    {
-        const long long n = (long long)Nt_pad * (Dp / 8);
-        pack_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T, Nt, Nt_pad, D, Dp, g_ws.ctrl, 1, Thi, Tlo);
-    }
-    SKB_CUDA_CHECK(cudaGetLastError());
-    ScoreParams p;
-    p.Ehi = Ehi; p.Elo = Elo; p.Thi = Thi; p.Tlo = Tlo;
-    p.Ne = Ne; p.Nt = Nt; p.Ne_pad = Ne_pad; p.Nt_pad = Nt_pad; p.Dp = Dp;
-    p.ctrl = g_ws.ctrl; p.ra = ra; p.ca = ca; p.r = r; p.q = q; p.a0 = a0; p.c0 = c0; p.rq_scale = rq_scale;
-    p.mul_scaled = 1;
-    p.out = out; p.ld_out = ld_out; p.out_f64 = out_f64;
-    p.n_ntiles = Nt_pad / 128;
-    p.tiles_total = (Ne_pad / 128) * p.n_ntiles;
-    const int grid = std::min(p.tiles_total, kNumSMs);
-    static bool configured = false;
-    if (!configured) {
-        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
-    // both variants are launched; exactly one does the work (decided on the device, no host sync)
-    if (passes != 3) score_gemm_kernel<1><<<grid, kScThreads, ScoreSmem<1>::total(Dp), st>>>(p);
-    if (passes != 1) {
-        if (ScoreSmem<3>::total(Dp) > 227 * 1024) {
-            set_last_error(__FILE__, __LINE__, "score_gemm: split mode needs D <= 256");
-            return SKB_ERR_ARG;
-        }
-        score_gemm_kernel<3><<<grid, kScThreads, ScoreSmem<3>::total(Dp), st>>>(p);
-    }
-    SKB_CUDA_CHECK(cudaGetLastError());
-    g_launches += 6 + (passes == 0 ? 1 : 0);
-    return SKB_OK;
+    PackedOp e, t;
+    ws_operand(&e, Ne, D, 0, 0);
+    ws_operand(&t, Nt, D, 1, 2 * eh);
+    if ((rc = packed_fill(E, &e, st))) return rc;
+    if ((rc = packed_fill(T, &t, st))) return rc;
+    return gemm_packed(e, t, ra, ca, a0, r, q, c0, rq_scale, abs_alpha_for_auto, passes, out_f64, out, ld_out, st);
 }
 
 // ----------------------------------------------------------------------------- as-norm: top-k statistics per row

@@ -14,8 +14,9 @@
 //     their start address, accumulating MT tiles in TMEM,
 //   * and eight epilogue warps read TMEM with tcgen05.ld, add the bias, apply the activation / pad
 //     mask, optionally subsample (stride-2 convs are computed at stride 1 and every other pixel
-//     kept), optionally reduce per-(utterance, channel) sums for the squeeze-excitation layer, and
-//     store 16-byte channel groups, fully coalesced across the warp.
+//     kept), optionally apply the squeeze-excitation tail of a BasicBlock (acc * scale[utt][c] + residual,
+//     ReLU -- the scales are known BEFORE this conv runs, see se_scale_kernel), and store 16-byte
+//     channel groups, fully coalesced across the warp.
 // One CTA per SM walks the (pixel tile, N split) work items round-robin.  Three mbarrier pipelines
 // keep the roles decoupled across item boundaries: an A-slab ring and a weight ring (producers run
 // ahead into the next items) and a double-buffered TMEM accumulator (the epilogue of item i overlaps
@@ -50,7 +51,10 @@ struct ConvParams {
     const int* pix_sub;     // stride-2 convs: [p_end - G] destination pixel at the next level (even h, even w) or -1;
                             // nullptr for stride 1 (output pixel == input pixel)
     int bias_mma;           // 1: the bias is added by one extra MMA (ones x [bias_hi, bias_lo]) instead of the epilogue
-    unsigned long long* se_sums;   // [B][cout] fixed-point (2^24) channel sums, or nullptr
+    // fused squeeze-excitation tail (conv2 of a BasicBlock): out = act(acc * se_scale[b][n] + res[p][n])
+    const float* se_scale;         // [B][cout] or nullptr
+    const uint16_t* res;           // residual planes in the OUTPUT geometry (block input or shortcut conv), or nullptr
+    long long res_plane;
 };
 
 constexpr int kConvKC = 32;            // input channels per A/B stage (two K=16 MMAs)
@@ -73,35 +77,6 @@ struct ConvCfg {
                (size_t)b_stages * tps * kBStageBytes;
     }
 };
-
-// Fixed-point (2^-24) reduction of 16 per-lane partial channel sums into sums[b][ch0 .. ch0+15].  Lanes that
-// never accumulated (b_lane < 0) hold zeros.  Common case: every contributing lane belongs to one utterance ->
-// two-limb REDUX warp sums (lane i keeps channel ch0 + i) and one coalesced 64-bit atomic per lane 0..15.
-// Utterance boundary inside the warp (rare): each lane adds its own 16 partial sums.
-__device__ __forceinline__ void se_flush(long long (&t)[16], int lane, int b_lane, unsigned long long* sums, int cout, int ch0) {
-    const unsigned has = __ballot_sync(0xffffffffu, b_lane >= 0);
-    if (has == 0u) return;
-    const int b0 = __shfl_sync(0xffffffffu, b_lane, __ffs(has) - 1);
-    if (__all_sync(0xffffffffu, b_lane < 0 || b_lane == b0)) {
-        // exact warp sum of 64-bit values with the 32-bit hardware reduction (REDUX): split into a 20-bit low limb and a
-        // signed high limb (|x| < 2^42 => |hi| < 2^22, so 32 lanes cannot overflow either limb), reduce, recombine
-        long long mine = 0ll;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int lo = (int)(t[i] & 0xFFFFFll);
-            const int hi = (int)(t[i] >> 20);
-            const int slo = __reduce_add_sync(0xffffffffu, lo);
-            const int shi = __reduce_add_sync(0xffffffffu, hi);
-            if (lane == i) mine = ((long long)shi << 20) + (long long)slo;
-        }
-        if (lane < 16) atomicAdd(sums + (size_t)b0 * cout + ch0 + lane, (unsigned long long)mine);
-    } else if (b_lane >= 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(sums + (size_t)b_lane * cout + ch0 + i, (unsigned long long)t[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) t[i] = 0ll;
-}
 
 template <int N_CTA, int MT, bool BF16>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvParams p) {
@@ -328,14 +303,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             const float slope = p.act_slope;
 #pragma unroll 1
             for (int c0 = 0; c0 < N_CTA; c0 += 16) {
-                long long t[16];
-                int b_acc = -1;
-                if (p.se_sums != nullptr) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) t[i] = 0ll;
-                }
 #pragma unroll
                 for (int mt = 0; mt < MTH; ++mt) {
+                    const bool valid = bidx[mt] >= 0;
+                    // fused SE tail: fetch the residual (two 16-byte chunks) and the per-(utterance, channel) scales
+                    // before waiting on TMEM so the loads overlap the tcgen05.ld
+                    uint4 rv[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+                    float4 sc4[4];
+                    if (p.se_scale != nullptr && valid) {
+                        const uint16_t* rsrc = p.res + (size_t)(optr[mt] - p.out) + (size_t)((n_base + c0) >> 3) * ((size_t)p.res_plane * 8);
+                        rv[0] = *reinterpret_cast<const uint4*>(rsrc);
+                        rv[1] = *reinterpret_cast<const uint4*>(rsrc + (size_t)p.res_plane * 8);
+                        const float4* sp = reinterpret_cast<const float4*>(p.se_scale + (size_t)bidx[mt] * p.cout + n_base + c0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) sc4[k] = __ldg(sp + k);
+                    }
                     float v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + (mt0 + mt) * N_CTA + c0, v);
                     if (c0 + 16 >= N_CTA && mt == MTH - 1) {
@@ -348,9 +330,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] += bias_s[n_base + c0 + i];
                     }
+                    if (p.se_scale != nullptr && valid) {
+                        const uint32_t rw[8] = {rv[0].x, rv[0].y, rv[0].z, rv[0].w, rv[1].x, rv[1].y, rv[1].z, rv[1].w};
+                        const float scv[16] = {sc4[0].x, sc4[0].y, sc4[0].z, sc4[0].w, sc4[1].x, sc4[1].y, sc4[1].z, sc4[1].w,
+                                               sc4[2].x, sc4[2].y, sc4[2].z, sc4[2].w, sc4[3].x, sc4[3].y, sc4[3].z, sc4[3].w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float2 r2 = unpack2<BF16>(rw[i]);
+                            v[2 * i] = fmaf(v[2 * i], scv[2 * i], r2.x);
+                            v[2 * i + 1] = fmaf(v[2 * i + 1], scv[2 * i + 1], r2.y);
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * slope);
-                    const bool valid = bidx[mt] >= 0;
                     if (optr[mt] != nullptr) {
                         uint16_t* dst = optr[mt] + (size_t)((n_base + c0) >> 3) * plane8;
 #pragma unroll
@@ -363,25 +355,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                             *reinterpret_cast<uint4*>(dst + j * plane8) = o;
                         }
                     }
-                    if (p.se_sums != nullptr) {
-                        // per-(utterance, channel) sums of the fp32 values for the SE squeeze, accumulated in
-                        // 2^-24 fixed point: integer addition is associative, so the result is bit-identical
-                        // whatever the tile / warp / atomic order (and however the batch is packed).  Each lane
-                        // first adds up its own pixels; one transposing butterfly per 16-channel block then
-                        // reduces across the warp (the rare utterance boundary flushes early).
-                        const bool clash = valid && b_acc >= 0 && bidx[mt] != b_acc;
-                        if (__any_sync(0xffffffffu, clash)) {
-                            se_flush(t, lane, b_acc, p.se_sums, p.cout, n_base + c0);
-                            b_acc = -1;
-                        }
-                        if (valid) {
-                            b_acc = bidx[mt];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) t[i] += __float2ll_rn(v[i] * 16777216.f);
-                        }
-                    }
                 }
-                if (p.se_sums != nullptr) se_flush(t, lane, b_acc, p.se_sums, p.cout, n_base + c0);
             }
         }
         tc_fence_before();

@@ -100,6 +100,17 @@ static uint16_t to16(float v, bool bf16) {
     return u;
 }
 
+static float from16(uint16_t u, bool bf16) {
+    if (bf16) {
+        __nv_bfloat16 h;
+        memcpy(&h, &u, 2);
+        return __bfloat162float(h);
+    }
+    __half h;
+    memcpy(&h, &u, 2);
+    return __half2float(h);
+}
+
 static const HostTensor* find(const WeightMap& w, const std::string& k) {
     auto it = w.find(k);
     if (it == w.end()) {
@@ -157,7 +168,8 @@ static int pack_conv(const std::vector<double>& wf, const std::vector<double>& b
 }
 
 // Conv2d (no bias) followed by BatchNorm2d: w' = w*s[co], b' = t[co]
-static int pack_conv_bn(const WeightMap& w, const std::string& conv_key, const std::string& bn_prefix, bool bf16, ConvW* out) {
+static int pack_conv_bn(const WeightMap& w, const std::string& conv_key, const std::string& bn_prefix, bool bf16, ConvW* out,
+                        float** w_rounded_t = nullptr) {
     const HostTensor* cw = find(w, conv_key);
     if (!cw || cw->shape.size() != 4) return SKB_ERR_WEIGHTS;
     const int cout = (int)cw->shape[0], cin = (int)cw->shape[1], taps = (int)(cw->shape[2] * cw->shape[3]);
@@ -167,6 +179,14 @@ static int pack_conv_bn(const WeightMap& w, const std::string& conv_key, const s
     std::vector<double> wf((size_t)cout * cin * taps);
     for (int co = 0; co < cout; ++co)
         for (size_t i = 0; i < (size_t)cin * taps; ++i) wf[(size_t)co * cin * taps + i] = (double)cw->p[(size_t)co * cin * taps + i] * s[co];
+    if (w_rounded_t) {
+        std::vector<float> wt((size_t)cin * taps * cout);
+        for (int co = 0; co < cout; ++co)
+            for (size_t i = 0; i < (size_t)cin * taps; ++i)
+                wt[i * cout + co] = from16(to16((float)wf[(size_t)co * cin * taps + i], bf16), bf16);
+        rc = dev_upload(wt, w_rounded_t);
+        if (rc) return rc;
+    }
     return pack_conv(wf, t, cout, cin, cin, taps, bf16, out);
 }
 
@@ -182,6 +202,7 @@ struct BlockW {
     bool has_sc = false;
     int stride = 1, C = 0;
     float *se_w1 = nullptr, *se_w2 = nullptr;
+    float* w2t = nullptr;      // conv2's folded weights as the tensor cores see them (16-bit rounded), fp32 [9*Cin][Cout]
 };
 
 struct Model {
@@ -276,7 +297,7 @@ static int build_hr34(const WeightMap& w, Model* m) {
             b.C = planes[li];
             b.stride = (bi == 0 && li > 0) ? 2 : 1;
             if ((rc = pack_conv_bn(w, p + ".conv1.weight", p + ".bn1", m->bf16, &b.conv1))) return rc;
-            if ((rc = pack_conv_bn(w, p + ".conv2.weight", p + ".bn2", m->bf16, &b.conv2))) return rc;
+            if ((rc = pack_conv_bn(w, p + ".conv2.weight", p + ".bn2", m->bf16, &b.conv2, &b.w2t))) return rc;
             b.has_sc = w.count(p + ".shortcut.0.weight") > 0;
             if (b.has_sc && (rc = pack_conv_bn(w, p + ".shortcut.0.weight", p + ".shortcut.1", m->bf16, &b.sc))) return rc;
             const HostTensor *f0 = find(w, p + ".se.fc.0.weight"), *f2 = find(w, p + ".se.fc.2.weight");
@@ -373,7 +394,7 @@ static void free_model(Model* m) {
     for (auto& b : m->blocks) {
         free_conv(&b.conv1); free_conv(&b.conv2);
         if (b.has_sc) free_conv(&b.sc);
-        cudaFree(b.se_w1); cudaFree(b.se_w2);
+        cudaFree(b.se_w1); cudaFree(b.se_w2); cudaFree(b.w2t);
     }
     for (auto& c : m->tdnn) free_conv(&c);
     cudaFree(m->att_w1x); cudaFree(m->att_w1g); cudaFree(m->att_b1); cudaFree(m->att_bn_s); cudaFree(m->att_bn_t);
@@ -441,7 +462,7 @@ struct skb_xtractor {
     Model m;
     Plan plan;
     bool plan_valid = false;
-    DevBuf pixmeta;
+    DevBuf pixmeta, brd;
     DevBuf tab32, tab64, feats, sums, scale, poolX, poolH, poolL, gc, hb, pooled, lin, emb_pre, emb, logits, wave, dbg;
     std::vector<DevBuf> act;      // activation buffers
     std::vector<size_t> act_bytes;
@@ -570,6 +591,7 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     if (Cmax) {
         if ((rc = h->sums.ensure((size_t)B * Cmax * sizeof(unsigned long long)))) return rc;
         if ((rc = h->scale.ensure((size_t)B * Cmax * sizeof(float)))) return rc;
+        if ((rc = h->brd.ensure((size_t)B * (8 + 36) * Cmax * sizeof(float)))) return rc;   // border sums + K-slice partial means
         SKB_CUDA_CHECK(cudaMemsetAsync(h->sums.p, 0, (size_t)B * Cmax * sizeof(unsigned long long), st));
     }
     if ((rc = h->feats.ensure((size_t)pl.total_frames * m.fe.n_out * sizeof(float)))) return rc;
@@ -632,8 +654,8 @@ static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
 
 // ----------------------------------------------------------------------------- conv launch helper
 static int run_conv(skb_xtractor* h, const ConvW& cw, const Level& Lin, const uint16_t* in, uint16_t* out, const Level& Lout,
-                    bool subsample, int act, bool conv3x3, const int* tdnn_shifts, unsigned long long* se_sums, bool pix_from_out,
-                    cudaStream_t st) {
+                    bool subsample, int act, bool conv3x3, const int* tdnn_shifts, const float* se_scale, const uint16_t* res,
+                    bool pix_from_out, cudaStream_t st) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
     p.in = in; p.in_plane = Lin.plane; p.w = cw.w; p.bias = cw.bias; p.out = out; p.out_plane = Lout.plane;
@@ -658,7 +680,9 @@ static int run_conv(skb_xtractor* h, const ConvW& cw, const Level& Lin, const ui
     // the validity table of the OUTPUT level decides what is stored as non-zero (TDNN: same geometry, fewer frames)
     p.pix_b = pm + (pix_from_out ? Lout.o_pix_b : Lin.o_pix_b);
     p.pix_sub = subsample ? pm + Lin.o_pix_sub : nullptr;
-    p.se_sums = se_sums;
+    p.se_scale = se_scale;
+    p.res = res;
+    p.res_plane = Lout.plane;
     g_launches++;
     return launch_conv_umma(p, cw.ncta, h->m.bf16, st);
 }
@@ -762,19 +786,27 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
         const uint16_t* res = x;
         {
             ProfScope ps(PROF_CONV, st);
-            SKB_TRY(run_conv(h, bw.conv1, Lin, x, y1, L, bw.stride == 2, 1, true, nullptr, nullptr, false, st));
-            SKB_TRY(run_conv(h, bw.conv2, L, y1, y2, L, false, 0, true, nullptr, (unsigned long long*)h->sums.p, false, st));
+            SKB_TRY(run_conv(h, bw.conv1, Lin, x, y1, L, bw.stride == 2, 1, true, nullptr, nullptr, nullptr, false, st));
             if (bw.has_sc) {
-                SKB_TRY(run_conv(h, bw.sc, Lin, x, scb, L, bw.stride == 2, 0, false, nullptr, nullptr, false, st));
+                SKB_TRY(run_conv(h, bw.sc, Lin, x, scb, L, bw.stride == 2, 0, false, nullptr, nullptr, nullptr, false, st));
                 res = scb;
             }
         }
         {
+            // SE scales from conv2's INPUT (linearity of the convolution): one bandwidth-bound pass over y1 + a tiny kernel
             ProfScope ps(PROF_SE, st);
-            SKB_TRY(launch_se_fc((unsigned long long*)h->sums.p, d32 + L.o_utt_count, bw.se_w1, bw.se_w2, (float*)h->scale.p, B, bw.C, st));
-            SKB_TRY(launch_se_apply(m.bf16, y2, res, nxt, L.plane, (const float*)h->scale.p, bw.C, L.G, L.p_end, L.Wp, d32 + L.o_row_b, st));
+            const int* pm = (const int*)h->pixmeta.p;
+            SKB_TRY(launch_plane_sum(m.bf16, y1, L.plane, L.G, L.p_end, pm + L.o_pix_b, bw.C, (unsigned long long*)h->sums.p, st));
+            SKB_TRY(launch_se_scale(m.bf16, (unsigned long long*)h->sums.p, y1, L.plane, L.G, L.Wp, L.W, d32 + L.o_utt_row0,
+                                    d32 + L.o_utt_count, B, bw.C, bw.C, bw.w2t, bw.conv2.bias, bw.se_w1, bw.se_w2,
+                                    (float*)h->brd.p, (float*)h->scale.p, st));
         }
-        g_launches += 2;
+        {
+            // conv2 with the fused SE tail: nxt = relu(bn2(conv2(y1)) * scale + residual)
+            ProfScope ps(PROF_CONV, st);
+            SKB_TRY(run_conv(h, bw.conv2, L, y1, nxt, L, false, 1, true, nullptr, (const float*)h->scale.p, res, false, st));
+        }
+        g_launches += 4;
         cur ^= 1;
         if (stop) {
             char name[32];
@@ -833,7 +865,7 @@ static int forward_tdnn(skb_xtractor* h, const float* wave, int norm_embedding, 
         // validity (row_h) of the OUTPUT rows decides what gets stored as non-zero
         ProfScope ps(PROF_CONV, st);
         SKB_TRY(run_conv(h, m.tdnn[i], Lin, (const uint16_t*)h->act[i].p, (uint16_t*)h->act[i + 1].p, Lout, false, 2, false,
-                         shifts, nullptr, true, st));
+                         shifts, nullptr, nullptr, true, st));
         if (stop) {
             char name[32];
             snprintf(name, sizeof(name), "tdnn%d", i + 1);
@@ -936,7 +968,7 @@ void skb_xtractor_destroy(skb_xtractor_t* h) {
     if (!h) return;
     free_model(&h->m);
     DevBuf* bufs[] = {&h->tab32, &h->tab64, &h->feats, &h->sums, &h->scale, &h->poolX, &h->poolH, &h->poolL, &h->gc, &h->hb,
-                      &h->pooled, &h->lin, &h->emb_pre, &h->emb, &h->logits, &h->wave, &h->dbg};
+                      &h->pooled, &h->lin, &h->emb_pre, &h->emb, &h->logits, &h->wave, &h->dbg, &h->pixmeta, &h->brd};
     for (auto* b : bufs) b->release();
     for (auto& b : h->act) b.release();
     delete h;

@@ -73,89 +73,228 @@ int launch_stem(bool bf16, const float* feats, const long long* feat_off, const 
     return SKB_OK;
 }
 
-// ----------------------------------------------------------------------------- SE: squeeze FCs
-// sidekit/nnet/res_net.py:272-281: scale = sigmoid(W2 relu(W1 mean)).  One CTA per utterance; consumes
-// (and re-zeroes) the per-(utterance, channel) sums produced by the conv2 epilogue.
-__global__ void se_fc_kernel(unsigned long long* __restrict__ sums, const int* __restrict__ utt_count, const float* __restrict__ w1 /*[C/16][C]*/,
-                             const float* __restrict__ w2 /*[C][C/16]*/, float* __restrict__ scale, int C) {
-    __shared__ float mean[256];
-    __shared__ float hid[16];
-    const int b = blockIdx.x;
-    const int R = C / 16;
-    const double inv = 1.0 / (16777216.0 * (double)utt_count[b]);      // sums are 2^-24 fixed point
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        mean[c] = (float)((double)(long long)sums[(size_t)b * C + c] * inv);
-        sums[(size_t)b * C + c] = 0ull;
+// ----------------------------------------------------------------------------- SE squeeze, computed BEFORE conv2 runs
+// The SE layer needs mean_{h,w}(bn2(conv2(y1))) per (utterance, channel) (sidekit/nnet/res_net.py:272-281, :316-317).
+// conv2 is linear, so that mean follows from sums of its INPUT y1:
+//     sum_{h,w} y2[c] = N*b2[c] + sum_{tap,ci} W2[c][ci][tap] * S_tap[ci],
+//     S_(dr,ds)[ci] = Total[ci] - (excluded border row) - (excluded border column) + (their corner)
+// (a tap shifted by (dr, ds) sees every pixel except one border row / column; the zero padding contributes nothing).
+// Knowing the scales up front lets conv2's epilogue apply scale + residual + ReLU directly: y2 is never stored and
+// the separate "scale, add, ReLU" pass disappears.
+//
+// plane_sum_kernel: Total[b][ci] over the valid pixels, in 2^-24 fixed point.  16-bit activations times 2^24 are
+// exact integers and integer addition is associative, so the sums -- and through them every embedding -- are
+// bit-identical whatever the packing, grid shape or atomic order.
+template <bool BF16>
+__global__ void __launch_bounds__(256) plane_sum_kernel(const uint16_t* __restrict__ act, long long plane, int G, int p_end,
+                                                        const int* __restrict__ pix_b, int C, unsigned long long* __restrict__ sums) {
+    constexpr int PX = 8;                                   // pixels per lane
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.y;
+    const int base = G + (blockIdx.x * 8 + warp) * 32 * PX;
+    long long t[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t[e] = 0ll;
+    int b_acc = -1;
+    bool mixed = false;
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+        const int pix = base + k * 32 + lane;
+        int b = -1;
+        if (pix < p_end) b = __ldg(pix_b + (pix - G));
+        if (b >= 0) {
+            if (b_acc >= 0 && b != b_acc) {               // utterance boundary inside this lane's pixels (rare): flush
+                for (int e = 0; e < 8; ++e) {
+                    atomicAdd(sums + (size_t)b_acc * C + j * 8 + e, (unsigned long long)t[e]);
+                    t[e] = 0ll;
+                }
+                mixed = true;
+            }
+            b_acc = b;
+            const uint4 a = *reinterpret_cast<const uint4*>(act + ((size_t)j * plane + pix) * 8);
+            const uint32_t u[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 v = unpack2<BF16>(u[e]);
+                t[2 * e] += __float2ll_rn(v.x * 16777216.f);
+                t[2 * e + 1] += __float2ll_rn(v.y * 16777216.f);
+            }
+        }
     }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = warp; j < R; j += blockDim.x >> 5) {
-        float a = 0.f;
-        for (int c = lane; c < C; c += 32) a = fmaf(w1[j * C + c], mean[c], a);
-        a = warp_sum(a);
-        if (lane == 0) hid[j] = fmaxf(a, 0.f);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a = 0.f;
-        for (int j = 0; j < R; ++j) a = fmaf(w2[c * R + j], hid[j], a);
-        scale[(size_t)b * C + c] = 1.f / (1.f + __expf(-a));
+    const unsigned has = __ballot_sync(0xffffffffu, b_acc >= 0);
+    if (has == 0u) return;
+    const int b0 = __shfl_sync(0xffffffffu, b_acc, __ffs(has) - 1);
+    if (__all_sync(0xffffffffu, (b_acc < 0 || b_acc == b0) && !mixed)) {
+        // exact warp sum of 64-bit values with the 32-bit hardware reduction: 20-bit low limb + signed high limb
+        long long mine = 0ll;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int slo = __reduce_add_sync(0xffffffffu, (int)(t[e] & 0xFFFFFll));
+            const int shi = __reduce_add_sync(0xffffffffu, (int)(t[e] >> 20));
+            if (lane == e) mine = ((long long)shi << 20) + (long long)slo;
+        }
+        if (lane < 8) atomicAdd(sums + (size_t)b0 * C + j * 8 + lane, (unsigned long long)mine);
+    } else if (b_acc >= 0) {
+        for (int e = 0; e < 8; ++e) atomicAdd(sums + (size_t)b_acc * C + j * 8 + e, (unsigned long long)t[e]);
     }
 }
 
-int launch_se_fc(unsigned long long* sums, const int* utt_count, const float* w1, const float* w2, float* scale, int B, int C,
-                 cudaStream_t st) {
-    se_fc_kernel<<<B, 256, 0, st>>>(sums, utt_count, w1, w2, scale, C);
+int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, int C,
+                     unsigned long long* sums, cudaStream_t st) {
+    const int n = p_end - G;
+    dim3 grid((n + 2047) / 2048, C / 8);
+    if (bf16)
+        plane_sum_kernel<true><<<grid, 256, 0, st>>>(act, plane, G, p_end, pix_b, C, sums);
+    else
+        plane_sum_kernel<false><<<grid, 256, 0, st>>>(act, plane, G, p_end, pix_b, C, sums);
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
 }
 
-// ----------------------------------------------------------------------------- SE scale + residual + ReLU
-// out = relu(y * scale[b][c] + shortcut)   (sidekit/nnet/res_net.py:317-319).  Pad pixels hold zeros in
-// both inputs and stay zero.  One thread per pixel walks the chunk planes (16-byte loads/stores,
-// coalesced across the warp).
+// se_border_kernel: sums of the first / last row and column of y1 and its four corner pixels, per (utterance, channel).
+// One CTA per (utterance, 8-channel chunk); threads stride over the border pixels with 16-byte loads; the block
+// reduction runs in a fixed order, so the result is deterministic.  brd layout: [B][8 kinds][C].
 template <bool BF16>
-__global__ void se_apply_kernel(const uint16_t* __restrict__ y, const uint16_t* __restrict__ sc, uint16_t* __restrict__ out,
-                                long long plane, const float* __restrict__ scale, int C, int G, int p_end, int Wp,
-                                const int* __restrict__ row_b) {
-    const int pix = G + blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= p_end) return;
-    const int row = (pix - G) / Wp;
-    const int b = row_b[row];
-    const int chunks = C >> 3;
-    if (b < 0) {
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        for (int j = 0; j < chunks; ++j) *reinterpret_cast<uint4*>(out + ((size_t)j * plane + pix) * 8) = z;
-        return;
+__global__ void __launch_bounds__(128) se_border_kernel(const uint16_t* __restrict__ y1, long long plane, int G, int Wp, int W,
+                                                        const int* __restrict__ utt_row0, const int* __restrict__ utt_count, int C,
+                                                        float* __restrict__ brd) {
+    __shared__ float part[128][33];
+    const int b = blockIdx.x, j = blockIdx.y;
+    const int H = utt_count[b] / W;
+    const uint16_t* base = y1 + ((size_t)j * plane + G + (size_t)utt_row0[b] * Wp) * 8;     // pixel (0, 0) of chunk j
+    float acc[32];                                  // [row0 | rowL | col0 | colL][8 channels]
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    auto add8 = [&](const uint16_t* p, int o) {
+        const uint4 a = *reinterpret_cast<const uint4*>(p);
+        const uint32_t u[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 v = unpack2<BF16>(u[e]);
+            acc[o + 2 * e] += v.x;
+            acc[o + 2 * e + 1] += v.y;
+        }
+    };
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        add8(base + (size_t)w * 8, 0);
+        add8(base + ((size_t)(H - 1) * Wp + w) * 8, 8);
     }
-    const float* s = scale + (size_t)b * C;
-#pragma unroll 4
-    for (int j = 0; j < chunks; ++j) {
-        const size_t off = ((size_t)j * plane + pix) * 8;
-        const uint4 a = *reinterpret_cast<const uint4*>(y + off);
-        const uint4 r = *reinterpret_cast<const uint4*>(sc + off);
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + j * 8));
-        const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + j * 8 + 4));
-        float2 a0 = unpack2<BF16>(a.x), a1 = unpack2<BF16>(a.y), a2 = unpack2<BF16>(a.z), a3 = unpack2<BF16>(a.w);
-        float2 r0 = unpack2<BF16>(r.x), r1 = unpack2<BF16>(r.y), r2 = unpack2<BF16>(r.z), r3 = unpack2<BF16>(r.w);
-        uint4 o;
-        o.x = pack2<BF16>(fmaxf(fmaf(a0.x, s0.x, r0.x), 0.f), fmaxf(fmaf(a0.y, s0.y, r0.y), 0.f));
-        o.y = pack2<BF16>(fmaxf(fmaf(a1.x, s0.z, r1.x), 0.f), fmaxf(fmaf(a1.y, s0.w, r1.y), 0.f));
-        o.z = pack2<BF16>(fmaxf(fmaf(a2.x, s1.x, r2.x), 0.f), fmaxf(fmaf(a2.y, s1.y, r2.y), 0.f));
-        o.w = pack2<BF16>(fmaxf(fmaf(a3.x, s1.z, r3.x), 0.f), fmaxf(fmaf(a3.y, s1.w, r3.y), 0.f));
-        *reinterpret_cast<uint4*>(out + off) = o;
+    for (int hh = threadIdx.x; hh < H; hh += blockDim.x) {
+        add8(base + (size_t)hh * Wp * 8, 16);
+        add8(base + ((size_t)hh * Wp + W - 1) * 8, 24);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) part[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < 32) {                         // thread i sums quantity i over the 128 partials, in order
+        double a = 0.0;
+        for (int t = 0; t < 128; ++t) a += (double)part[t][threadIdx.x];
+        const int kind = threadIdx.x >> 3, e = threadIdx.x & 7;
+        brd[((size_t)b * 8 + kind) * C + j * 8 + e] = (float)a;
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 64) {    // corners: (0,0) (0,W-1) (H-1,0) (H-1,W-1)
+        const int k = (threadIdx.x - 32) >> 3, e = threadIdx.x & 7;
+        const int hh = (k >> 1) ? H - 1 : 0, ww = (k & 1) ? W - 1 : 0;
+        const uint16_t u = base[((size_t)hh * Wp + ww) * 8 + e];
+        brd[((size_t)b * 8 + 4 + k) * C + j * 8 + e] = unpack2<BF16>((uint32_t)u).x;
     }
 }
 
-int launch_se_apply(bool bf16, const uint16_t* y, const uint16_t* sc, uint16_t* out, long long plane, const float* scale,
-                    int C, int G, int p_end, int Wp, const int* row_b, cudaStream_t st) {
-    const int n = p_end - G;
-    const int threads = 256;
-    const int blocks = (n + threads - 1) / threads;
+// se_mean_partial_kernel: the mean of conv2's output through the (16-bit-rounded, BN-folded) conv2 weights, as a small
+// GEMM  partial[ks][b][co] = sum_{i in K-slice ks} W2t[i][co] * S[b][i],  i = ci * 9 + tap,  S = the nine shifted sums.
+// Grid = (K / 64 slices, utterance groups of 16): enough CTAs to cover the L2 latency of the weight stream; every
+// weight row is read once per utterance group.  Fixed summation order everywhere -> deterministic.
+constexpr int kSeRows = 64, kSeUtt = 16;
+__global__ void __launch_bounds__(256) se_mean_partial_kernel(const unsigned long long* __restrict__ sums, const float* __restrict__ brd,
+                                                              int B, int Cin, int Cout, const float* __restrict__ w2t,
+                                                              float* __restrict__ partial) {
+    __shared__ float sS[kSeUtt][kSeRows];
+    const int K = 9 * Cin;
+    const int k0 = blockIdx.x * kSeRows, b0 = blockIdx.y * kSeUtt;
+    const int nr = min(kSeRows, K - k0), nu = min(kSeUtt, B - b0);
+    for (int idx = threadIdx.x; idx < kSeUtt * kSeRows; idx += blockDim.x) {
+        const int u = idx / kSeRows, r = idx - u * kSeRows;
+        float v = 0.f;
+        if (u < nu && r < nr) {
+            const int i = k0 + r, c = i / 9, tap = i - c * 9;
+            const int dr = tap / 3 - 1, ds = tap % 3 - 1;
+            const int b = b0 + u;
+            const float* bb = brd + (size_t)b * 8 * Cin + c;
+            v = (float)((double)(long long)sums[(size_t)b * Cin + c] * (1.0 / 16777216.0));
+            if (dr < 0) v -= bb[Cin];                 // shifted up: the last row is never read
+            if (dr > 0) v -= bb[0];
+            if (ds < 0) v -= bb[3 * Cin];
+            if (ds > 0) v -= bb[2 * Cin];
+            if (dr < 0 && ds < 0) v += bb[7 * Cin];
+            if (dr < 0 && ds > 0) v += bb[6 * Cin];
+            if (dr > 0 && ds < 0) v += bb[5 * Cin];
+            if (dr > 0 && ds > 0) v += bb[4 * Cin];
+        }
+        sS[u][r] = v;
+    }
+    __syncthreads();
+    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+        float acc[kSeUtt];
+#pragma unroll
+        for (int u = 0; u < kSeUtt; ++u) acc[u] = 0.f;
+        const float* wp = w2t + (size_t)k0 * Cout + co;
+#pragma unroll 8
+        for (int r = 0; r < nr; ++r) {
+            const float w = __ldg(wp + (size_t)r * Cout);
+#pragma unroll
+            for (int u = 0; u < kSeUtt; ++u) acc[u] = fmaf(w, sS[u][r], acc[u]);
+        }
+        for (int u = 0; u < nu; ++u) partial[((size_t)blockIdx.x * B + b0 + u) * Cout + co] = acc[u];
+    }
+}
+
+// se_fc_kernel: mean = b2 + (1/N) * sum of the K-slice partials (in slice order); scale = sigmoid(W2 relu(W1 mean))
+// (sidekit/nnet/res_net.py:272-281).  One CTA per utterance; re-zeroes the fixed-point channel sums for the next block.
+__global__ void __launch_bounds__(256) se_fc_kernel(unsigned long long* __restrict__ sums, const float* __restrict__ partial, int n_slices,
+                                                    const int* __restrict__ utt_count, int B, int Cin, int Cout,
+                                                    const float* __restrict__ b2, const float* __restrict__ fc1 /*[Cout/16][Cout]*/,
+                                                    const float* __restrict__ fc2 /*[Cout][Cout/16]*/, float* __restrict__ scale) {
+    __shared__ float mean[256];
+    __shared__ float hid[16];
+    const int b = blockIdx.x;
+    const float inv_n = 1.f / (float)utt_count[b];
+    for (int c = threadIdx.x; c < Cin; c += blockDim.x) sums[(size_t)b * Cin + c] = 0ull;
+    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+        float a = 0.f;
+        for (int k = 0; k < n_slices; ++k) a += partial[((size_t)k * B + b) * Cout + co];
+        mean[co] = fmaf(a, inv_n, b2[co]);
+    }
+    __syncthreads();
+    const int R = Cout / 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int jj = warp; jj < R; jj += blockDim.x >> 5) {
+        float a = 0.f;
+        for (int c = lane; c < Cout; c += 32) a = fmaf(fc1[jj * Cout + c], mean[c], a);
+        a = warp_sum(a);
+        if (lane == 0) hid[jj] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
+        float a = 0.f;
+        for (int jj = 0; jj < R; ++jj) a = fmaf(fc2[c * R + jj], hid[jj], a);
+        scale[(size_t)b * Cout + c] = 1.f / (1.f + __expf(-a));
+    }
+}
+
+int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, long long plane, int G, int Wp, int W,
+                    const int* utt_row0, const int* utt_count, int B, int Cin, int Cout, const float* w2t, const float* b2,
+                    const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st) {
+    // brd_ws: [B][8][Cin] border sums, followed by [n_slices][B][Cout] partial means
+    dim3 grid(B, Cin / 8);
     if (bf16)
-        se_apply_kernel<true><<<blocks, threads, 0, st>>>(y, sc, out, plane, scale, C, G, p_end, Wp, row_b);
+        se_border_kernel<true><<<grid, 128, 0, st>>>(y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws);
     else
-        se_apply_kernel<false><<<blocks, threads, 0, st>>>(y, sc, out, plane, scale, C, G, p_end, Wp, row_b);
+        se_border_kernel<false><<<grid, 128, 0, st>>>(y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws);
+    const int n_slices = (9 * Cin + kSeRows - 1) / kSeRows;
+    float* partial = brd_ws + (size_t)B * 8 * Cin;
+    dim3 g2(n_slices, (B + kSeUtt - 1) / kSeUtt);
+    se_mean_partial_kernel<<<g2, Cout < 256 ? (Cout < 32 ? 32 : Cout) : 256, 0, st>>>(sums, brd_ws, B, Cin, Cout, w2t, partial);
+    se_fc_kernel<<<B, 256, 0, st>>>(sums, partial, n_slices, utt_count, B, Cin, Cout, b2, fc1, fc2, scale);
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
 }

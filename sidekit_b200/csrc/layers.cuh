@@ -20,10 +20,11 @@ struct FrontendConsts {
 int launch_stem(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float* w,
                 const float* bias, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
                 const int* row_b, const int* row_h, cudaStream_t st);
-int launch_se_fc(unsigned long long* sums, const int* utt_count, const float* w1, const float* w2, float* scale, int B, int C,
-                 cudaStream_t st);
-int launch_se_apply(bool bf16, const uint16_t* y, const uint16_t* sc, uint16_t* out, long long plane, const float* scale,
-                    int C, int G, int p_end, int Wp, const int* row_b, cudaStream_t st);
+int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, int C,
+                     unsigned long long* sums, cudaStream_t st);
+int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, long long plane, int G, int Wp, int W,
+                    const int* utt_row0, const int* utt_count, int B, int Cin, int Cout, const float* w2t, const float* b2,
+                    const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st);
 int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C, int W, int Wp, int G,
                          const int* frame_row, int n_frames, float* X, cudaStream_t st);
 int launch_meanstd(const float* X, const long long* frame_off, const int* n_fr, int B, int D, const float* aff_s,

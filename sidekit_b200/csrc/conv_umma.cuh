@@ -285,8 +285,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             const int buf = (int)(n_done & 1);
             const int p0 = p.G + tile * Cfg::kTileM;
             const int n_base = ns * N_CTA;
-            mbar_wait(&acc_full[buf], (n_done >> 1) & 1);
-            tc_fence_after();
             // per-pixel bookkeeping for the pixels this thread owns: one coalesced table read each
             int bidx[MTH];
             uint16_t* optr[MTH];
@@ -300,59 +298,80 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                 optr[mt] = opix >= 0 ? p.out + (size_t)opix * 8 : nullptr;
             }
             const size_t plane8 = (size_t)p.out_plane * 8;
+            const size_t rplane8 = (size_t)p.res_plane * 8;
             const float slope = p.act_slope;
+            const bool fused = p.se_scale != nullptr;
+            // Fused SE tail: the residual comes from HBM/L2 (~1 us away).  Fetch it in groups of up to 8 channel chunks per
+            // pixel, the first group BEFORE waiting for the accumulator so its latency hides behind the MMAs.
+            constexpr int NCH = N_CTA / 8;                 // 8-channel chunks per pixel in this N slice
+            constexpr int RCH = NCH > 8 ? 8 : NCH;         // chunks per prefetch group
+            uint4 rv[MTH][RCH];
+            auto fetch_res = [&](int g) {
+#pragma unroll
+                for (int mt = 0; mt < MTH; ++mt)
+#pragma unroll
+                    for (int k = 0; k < RCH; ++k) {
+                        rv[mt][k] = make_uint4(0u, 0u, 0u, 0u);
+                        if (fused && bidx[mt] >= 0)
+                            rv[mt][k] = *reinterpret_cast<const uint4*>(p.res + (size_t)(optr[mt] - p.out) +
+                                                                        (size_t)((n_base >> 3) + g * RCH + k) * rplane8);
+                    }
+            };
+            fetch_res(0);
+            mbar_wait(&acc_full[buf], (n_done >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < N_CTA; c0 += 16) {
+            for (int g = 0; g < NCH / RCH; ++g) {
+                if (g > 0) fetch_res(g);
 #pragma unroll
-                for (int mt = 0; mt < MTH; ++mt) {
-                    const bool valid = bidx[mt] >= 0;
-                    // fused SE tail: fetch the residual (two 16-byte chunks) and the per-(utterance, channel) scales
-                    // before waiting on TMEM so the loads overlap the tcgen05.ld
-                    uint4 rv[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
-                    float4 sc4[4];
-                    if (p.se_scale != nullptr && valid) {
-                        const uint16_t* rsrc = p.res + (size_t)(optr[mt] - p.out) + (size_t)((n_base + c0) >> 3) * ((size_t)p.res_plane * 8);
-                        rv[0] = *reinterpret_cast<const uint4*>(rsrc);
-                        rv[1] = *reinterpret_cast<const uint4*>(rsrc + (size_t)p.res_plane * 8);
-                        const float4* sp = reinterpret_cast<const float4*>(p.se_scale + (size_t)bidx[mt] * p.cout + n_base + c0);
+                for (int cc = 0; cc < RCH; cc += 2) {
+                    const int c0 = (g * RCH + cc) * 8;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) sc4[k] = __ldg(sp + k);
-                    }
-                    float v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + (mt0 + mt) * N_CTA + c0, v);
-                    if (c0 + 16 >= N_CTA && mt == MTH - 1) {
-                        // accumulator completely read: hand this TMEM buffer back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
-                    }
-                    if (!p.bias_mma) {
+                    for (int mt = 0; mt < MTH; ++mt) {
+                        const bool valid = bidx[mt] >= 0;
+                        float4 sc4[4];
+                        if (fused && valid) {
+                            const float4* sp = reinterpret_cast<const float4*>(p.se_scale + (size_t)bidx[mt] * p.cout + n_base + c0);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += bias_s[n_base + c0 + i];
-                    }
-                    if (p.se_scale != nullptr && valid) {
-                        const uint32_t rw[8] = {rv[0].x, rv[0].y, rv[0].z, rv[0].w, rv[1].x, rv[1].y, rv[1].z, rv[1].w};
-                        const float scv[16] = {sc4[0].x, sc4[0].y, sc4[0].z, sc4[0].w, sc4[1].x, sc4[1].y, sc4[1].z, sc4[1].w,
-                                               sc4[2].x, sc4[2].y, sc4[2].z, sc4[2].w, sc4[3].x, sc4[3].y, sc4[3].z, sc4[3].w};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float2 r2 = unpack2<BF16>(rw[i]);
-                            v[2 * i] = fmaf(v[2 * i], scv[2 * i], r2.x);
-                            v[2 * i + 1] = fmaf(v[2 * i + 1], scv[2 * i + 1], r2.y);
+                            for (int k = 0; k < 4; ++k) sc4[k] = __ldg(sp + k);
                         }
-                    }
+                        float v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + (mt0 + mt) * N_CTA + c0, v);
+                        if (c0 + 16 >= N_CTA && mt == MTH - 1) {
+                            // accumulator completely read: hand this TMEM buffer back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                        }
+                        if (!p.bias_mma) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * slope);
-                    if (optr[mt] != nullptr) {
-                        uint16_t* dst = optr[mt] + (size_t)((n_base + c0) >> 3) * plane8;
+                            for (int i = 0; i < 16; ++i) v[i] += bias_s[n_base + c0 + i];
+                        }
+                        if (fused && valid) {
+                            const uint32_t rw[8] = {rv[mt][cc].x, rv[mt][cc].y, rv[mt][cc].z, rv[mt][cc].w,
+                                                    rv[mt][cc + 1].x, rv[mt][cc + 1].y, rv[mt][cc + 1].z, rv[mt][cc + 1].w};
+                            const float scv[16] = {sc4[0].x, sc4[0].y, sc4[0].z, sc4[0].w, sc4[1].x, sc4[1].y, sc4[1].z, sc4[1].w,
+                                                   sc4[2].x, sc4[2].y, sc4[2].z, sc4[2].w, sc4[3].x, sc4[3].y, sc4[3].z, sc4[3].w};
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            uint4 o;
-                            o.x = valid ? pack2<BF16>(v[j * 8 + 0], v[j * 8 + 1]) : 0u;
-                            o.y = valid ? pack2<BF16>(v[j * 8 + 2], v[j * 8 + 3]) : 0u;
-                            o.z = valid ? pack2<BF16>(v[j * 8 + 4], v[j * 8 + 5]) : 0u;
-                            o.w = valid ? pack2<BF16>(v[j * 8 + 6], v[j * 8 + 7]) : 0u;
-                            *reinterpret_cast<uint4*>(dst + j * plane8) = o;
+                            for (int i = 0; i < 8; ++i) {
+                                const float2 r2 = unpack2<BF16>(rw[i]);
+                                v[2 * i] = fmaf(v[2 * i], scv[2 * i], r2.x);
+                                v[2 * i + 1] = fmaf(v[2 * i + 1], scv[2 * i + 1], r2.y);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * slope);
+                        if (optr[mt] != nullptr) {
+                            uint16_t* dst = optr[mt] + (size_t)((n_base + c0) >> 3) * plane8;
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                uint4 o;
+                                o.x = valid ? pack2<BF16>(v[j * 8 + 0], v[j * 8 + 1]) : 0u;
+                                o.y = valid ? pack2<BF16>(v[j * 8 + 2], v[j * 8 + 3]) : 0u;
+                                o.z = valid ? pack2<BF16>(v[j * 8 + 4], v[j * 8 + 5]) : 0u;
+                                o.w = valid ? pack2<BF16>(v[j * 8 + 6], v[j * 8 + 7]) : 0u;
+                                *reinterpret_cast<uint4*>(dst + j * plane8) = o;
+                            }
                         }
                     }
                 }

@@ -18,7 +18,7 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     // traffic, no barrier round trips on the MMA issue path); otherwise streamed through a ring deep enough to
     // cover the L2 latency at the rate the MMAs consume them (the ring gets what the 3-slab A ring leaves).
     p.bias_mma = p.cout <= 256 ? 1 : 0;     // wide layers (TDNN) keep the epilogue bias add: their bias images would not fit
-    const int n_it = (p.cin / kConvKC) * p.taps;
+    const int n_it = p.n_pairs;
     const int n_split = p.cout / N_CTA;
     int tps = 1, bst = 1;
     p.b_resident = (n_split == 1 && (size_t)n_it * Cfg::kBStageBytes <= 96 * 1024) ? 1 : 0;
@@ -26,8 +26,10 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     if (p.b_resident) {
         bst = n_it;
     } else {
-        for (int cand : {3, 5}) {
-            if (p.taps % cand == 0 && (size_t)cand * Cfg::kBStageBytes <= 24 * 1024) { tps = cand; break; }
+        if (p.kc_per_grp == p.cin / kConvKC) {      // single tap group: several taps per weight stage
+            for (int cand : {3, 5}) {
+                if (p.taps % cand == 0 && (size_t)cand * Cfg::kBStageBytes <= 24 * 1024) { tps = cand; break; }
+            }
         }
         b_stage = (size_t)tps * Cfg::kBStageBytes;
         const size_t left = kConvSmemBudget - Cfg::fixed_bytes(p.cout, p.bias_mma, 0, 0) - 3 * a_stage;
@@ -61,7 +63,7 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
 }
 
 int launch_conv_umma(const ConvParams& p, int n_cta, bool bf16, cudaStream_t st) {
-    if (p.cin % kConvKC != 0 || p.cout % n_cta != 0 || p.taps < 1 || p.taps > 10 || p.rows_pad % 8 != 0) {
+    if (p.cin % kConvKC != 0 || p.cout % n_cta != 0 || p.taps < 1 || p.taps > 10 || p.rows_pad % 8 != 0 || p.kc_per_grp < 1 || p.n_pairs < 1) {
         set_last_error(__FILE__, __LINE__, "conv_umma: unsupported shape");
         return SKB_ERR_ARG;
     }

@@ -35,7 +35,13 @@ struct ConvParams {
     const float* bias;      // [cout] folded BN bias (fp32)
     uint16_t* out;          // output planes
     long long out_plane;
-    int cin, cout, taps;
+    int cin, cout, taps;    // taps = length of tap_shift[]
+    // Tap groups: k-chunk kc belongs to group kc / kc_per_grp and uses taps [grp_tap[g], grp_tap[g+1]).  Ordinary convs have
+    // one group with every tap.  A stride-2 conv reads a phase-split (space-to-depth) input: four phase images stacked as
+    // channel chunks, each seen by its own subset of the nine taps (1 + 2 + 2 + 4).
+    int kc_per_grp;
+    int grp_tap[5];
+    int n_pairs;            // (k-chunk, tap) pairs per work item = number of weight images per N split
     int G;                  // first computed pixel
     int p_end;              // one past the last computed pixel
     int halo;               // slab rows before the tile's first pixel (Wp + 1 for 3x3, 0 for 1x1 / causal taps)
@@ -53,7 +59,7 @@ struct ConvParams {
     int bias_mma;           // 1: the bias is added by one extra MMA (ones x [bias_hi, bias_lo]) instead of the epilogue
     // fused squeeze-excitation tail (conv2 of a BasicBlock): out = act(acc * se_scale[b][n] + res[p][n])
     const float* se_scale;         // [B][cout] or nullptr
-    const uint16_t* res;           // residual planes in the OUTPUT geometry (block input or shortcut conv), or nullptr
+    const uint16_t* res;           // residual planes in the INPUT pixel geometry (block input or shortcut conv), or nullptr
     long long res_plane;
 };
 
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     } else if (warp == 1) {
         // ---------------------------------------------------------------- B producer: packed weights
         if (lane == 0) {
-            const int n_it = n_kc * p.taps;            // per-tap images per item
+            const int n_it = p.n_pairs;                // weight images per item
             if (p.b_resident) {
                 // small layers: the whole weight tensor stays in shared memory for the life of the CTA
                 mbar_arrive_expect_tx(&b_full[0], (uint32_t)n_it * Cfg::kBStageBytes);
@@ -228,15 +234,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             }
             __syncwarp();
             const uint32_t acc0 = p.bias_mma ? 1u : 0u;
+            int grp = 0, in_grp = 0, flat = 0;
+            bool first = true;                       // first MMA of the item overwrites (or follows the bias MMA)
             for (int kc = 0; kc < n_kc; ++kc) {
                 mbar_wait(&a_full[as], a_ph);
                 tc_fence_after();
                 const uint32_t a_base = smem_u32(a_smem + (size_t)as * a_stage_bytes) + (uint32_t)p.halo * 16;
-                const int tstep = p.b_resident ? p.taps : p.tps;
-                for (int tap0 = 0; tap0 < p.taps; tap0 += tstep) {
+                const int tb = p.grp_tap[grp], te = p.grp_tap[grp + 1];
+                const int tstep = p.b_resident ? (te - tb) : p.tps;
+                for (int tap0 = tb; tap0 < te; tap0 += tstep) {
                     uint32_t b_stage;
                     if (p.b_resident) {
-                        b_stage = smem_u32(b_smem) + (uint32_t)(kc * p.taps) * Cfg::kBStageBytes;
+                        b_stage = smem_u32(b_smem) + (uint32_t)flat * Cfg::kBStageBytes;
                     } else {
                         mbar_wait(&b_full[bs], b_ph);
                         tc_fence_after();
@@ -253,18 +262,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
 #pragma unroll
                                 for (int mt = mtw0; mt < mtw0 + MTW; ++mt) {
                                     const uint64_t adesc = desc_hi_a | (((a_tap + ks * 2 * a_lbo + mt * 2048) >> 4) & 0x3FFF);
-                                    umma_f16(d_tmem + mt * N_CTA, adesc, bdesc, idesc, (kc > 0 || tap > 0 || ks > 0) ? 1u : acc0);
+                                    umma_f16(d_tmem + mt * N_CTA, adesc, bdesc, idesc, (!first || tt > 0 || ks > 0) ? 1u : acc0);
                                 }
                             }
                         }
                         if (!p.b_resident) umma_commit(&b_empty[bs]);
                     }
                     __syncwarp();
+                    first = false;
+                    flat += tstep;
                     if (!p.b_resident && ++bs == p.b_stages) { bs = 0; b_ph ^= 1; }
                 }
                 if (elect_one()) umma_commit(&a_empty[as]);
                 __syncwarp();
                 if (++as == p.a_stages) { as = 0; a_ph ^= 1; }
+                if (++in_grp == p.kc_per_grp) { in_grp = 0; ++grp; }
             }
             if (elect_one()) umma_commit(&acc_full[buf]);
             __syncwarp();
@@ -288,6 +300,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             // per-pixel bookkeeping for the pixels this thread owns: one coalesced table read each
             int bidx[MTH];
             uint16_t* optr[MTH];
+            size_t roff[MTH];                       // residual offset: same pixel as the conv input
 #pragma unroll
             for (int mt = 0; mt < MTH; ++mt) {
                 const int pix = p0 + (mt0 + mt) * 128 + q * 32 + lane;
@@ -296,6 +309,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                 long long opix = in_range ? (long long)pix : -1;
                 if (p.pix_sub != nullptr) opix = in_range ? (long long)__ldg(p.pix_sub + (pix - p.G)) : -1;
                 optr[mt] = opix >= 0 ? p.out + (size_t)opix * 8 : nullptr;
+                roff[mt] = (size_t)pix * 8;
             }
             const size_t plane8 = (size_t)p.out_plane * 8;
             const size_t rplane8 = (size_t)p.res_plane * 8;
@@ -313,7 +327,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                     for (int k = 0; k < RCH; ++k) {
                         rv[mt][k] = make_uint4(0u, 0u, 0u, 0u);
                         if (fused && bidx[mt] >= 0)
-                            rv[mt][k] = *reinterpret_cast<const uint4*>(p.res + (size_t)(optr[mt] - p.out) +
+                            rv[mt][k] = *reinterpret_cast<const uint4*>(p.res + roff[mt] +
                                                                         (size_t)((n_base >> 3) + g * RCH + k) * rplane8);
                     }
             };

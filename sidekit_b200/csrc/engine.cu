@@ -141,6 +141,7 @@ struct ConvW {
     uint16_t* w = nullptr;   // device, UMMA images
     float* bias = nullptr;   // device [cout]
     int cin = 0, cout = 0, taps = 0, ncta = 0;
+    bool phase_split = false;   // stride-2 3x3 conv packed for a phase-split input (cin = 4 * original channels)
 };
 
 // wf: folded weights [cout][cin_src][taps] (double), channels >= cin_src zero padded up to cin_pad.
@@ -188,6 +189,45 @@ static int pack_conv_bn(const WeightMap& w, const std::string& conv_key, const s
         if (rc) return rc;
     }
     return pack_conv(wf, t, cout, cin, cin, taps, bf16, out);
+}
+
+// Stride-2 3x3 conv + BN packed for a phase-split (space-to-depth) input: k-chunks run phase-major, phase (a, b) =
+// (h & 1, w & 1); each phase is read by its own taps: (0,0): (1,1) | (0,1): (1,0) (1,2) | (1,0): (0,1) (2,1) |
+// (1,1): (0,0) (0,2) (2,0) (2,2)   [(r, s) of the original kernel].
+static const int kPhaseTaps[9][2] = {{1, 1}, {1, 0}, {1, 2}, {0, 1}, {2, 1}, {0, 0}, {0, 2}, {2, 0}, {2, 2}};
+static const int kPhaseTapBegin[5] = {0, 1, 3, 5, 9};
+
+static int pack_conv_bn_phase_split(const WeightMap& w, const std::string& conv_key, const std::string& bn_prefix, bool bf16,
+                                    ConvW* out) {
+    const HostTensor* cw = find(w, conv_key);
+    if (!cw || cw->shape.size() != 4 || cw->shape[2] != 3 || cw->shape[3] != 3) return SKB_ERR_WEIGHTS;
+    const int cout = (int)cw->shape[0], cin = (int)cw->shape[1];
+    if (cin % kConvKC != 0) {
+        set_last_error(__FILE__, __LINE__, "phase-split conv needs input channels in multiples of 32");
+        return SKB_ERR_WEIGHTS;
+    }
+    std::vector<double> s, t;
+    int rc = bn_affine(w, bn_prefix, &s, &t);
+    if (rc) return rc;
+    const int ncta = conv_pick_ncta(cout), n_split = cout / ncta, cpp = cin / kConvKC;   // chunks per phase
+    std::vector<uint16_t> img((size_t)n_split * cpp * 9 * 4 * ncta * 8);
+    size_t o = 0;
+    for (int ns = 0; ns < n_split; ++ns)
+        for (int ph = 0; ph < 4; ++ph)
+            for (int ch = 0; ch < cpp; ++ch)
+                for (int tp = kPhaseTapBegin[ph]; tp < kPhaseTapBegin[ph + 1]; ++tp) {
+                    const int tap = kPhaseTaps[tp][0] * 3 + kPhaseTaps[tp][1];
+                    for (int j = 0; j < 4; ++j)
+                        for (int n = 0; n < ncta; ++n)
+                            for (int e = 0; e < 8; ++e) {
+                                const int co = ns * ncta + n, ci = ch * kConvKC + j * 8 + e;
+                                img[o++] = to16((float)((double)cw->p[((size_t)co * cin + ci) * 9 + tap] * s[co]), bf16);
+                            }
+                }
+    std::vector<float> bf(t.begin(), t.end());
+    out->cin = 4 * cin; out->cout = cout; out->taps = 9; out->ncta = ncta; out->phase_split = true;
+    if ((rc = dev_upload(img, &out->w))) return rc;
+    return dev_upload(bf, &out->bias);
 }
 
 static void free_conv(ConvW* c) {
@@ -296,7 +336,9 @@ static int build_hr34(const WeightMap& w, Model* m) {
             BlockW b;
             b.C = planes[li];
             b.stride = (bi == 0 && li > 0) ? 2 : 1;
-            if ((rc = pack_conv_bn(w, p + ".conv1.weight", p + ".bn1", m->bf16, &b.conv1))) return rc;
+            if (b.stride == 2) {
+                if ((rc = pack_conv_bn_phase_split(w, p + ".conv1.weight", p + ".bn1", m->bf16, &b.conv1))) return rc;
+            } else if ((rc = pack_conv_bn(w, p + ".conv1.weight", p + ".bn1", m->bf16, &b.conv1))) return rc;
             if ((rc = pack_conv_bn(w, p + ".conv2.weight", p + ".bn2", m->bf16, &b.conv2, &b.w2t))) return rc;
             b.has_sc = w.count(p + ".shortcut.0.weight") > 0;
             if (b.has_sc && (rc = pack_conv_bn(w, p + ".shortcut.0.weight", p + ".shortcut.1", m->bf16, &b.sc))) return rc;
@@ -411,7 +453,7 @@ struct Level {
     std::vector<int> H;            // lines per utterance
     // offsets (in ints) into the device table buffer
     size_t o_row_b = 0, o_row_h = 0, o_utt_row0 = 0, o_utt_count = 0;
-    size_t o_pix_b = 0, o_pix_sub = 0;   // offsets (ints) into the device pixel-meta buffer; o_pix_sub valid when has_sub
+    size_t o_pix_b = 0, o_pix_sub = 0;   // o_pix_sub: phase-split destination table (see pixmeta_kernel)   // offsets (ints) into the device pixel-meta buffer; o_pix_sub valid when has_sub
     bool has_sub = false;
 };
 
@@ -576,7 +618,9 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     if (m.archi == SKB_ARCHI_HALFRESNET34) {
         for (int l = 0; l < 4; ++l) {
             const size_t bytes = (size_t)(pl.lv[l].C / 8) * pl.lv[l].plane * 16;
-            for (int k = 0; k < 5; ++k) need.push_back(bytes);   // A, B, Y1, Y2, SC
+            // A, B (block in/out ping-pong), Y1, PS (phase-split copy of the previous level's output: 4 * C_prev/8 planes
+            // = twice this level's plane count), SC (shortcut conv output)
+            for (int k = 0; k < 5; ++k) need.push_back(k == 3 ? (l == 0 ? 256 : 2 * bytes) : bytes);
         }
     } else {
         for (int l = 0; l < 6; ++l) need.push_back((size_t)(pl.lv[l].C / 8) * pl.lv[l].plane * 16);
@@ -612,18 +656,21 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
 }
 
 // Per-pixel tables for the conv epilogue (one coalesced read instead of a division and two dependent gathers):
-// pix_b[rel] = utterance of pixel G + rel or -1 for pad / invalid; pix_sub[rel] = destination pixel at the next
-// level for the pixels a stride-2 convolution keeps (even h, even w), else -1.
+// pix_b[rel] = utterance of pixel G + rel or -1 for pad / invalid; pix_ps[rel] = destination of the pixel in the
+// PHASE-SPLIT copy that feeds the next level's stride-2 block: four phase images (h & 1, w & 1) in the next level's
+// geometry, stacked as groups of C/8 chunk planes:  dest = phase * (C/8) * plane' + G' + (row0'[b] + h/2) * Wp' + w/2.
 __global__ void pixmeta_kernel(int n, int Wp, int W, const int* __restrict__ row_b, const int* __restrict__ row_h,
-                               int* __restrict__ pix_b, int* __restrict__ pix_sub, int out_G, int out_Wp,
-                               const int* __restrict__ out_utt_row0) {
+                               int* __restrict__ pix_b, int* __restrict__ pix_ps, int out_G, int out_Wp,
+                               const int* __restrict__ out_utt_row0, long long phase_stride) {
     const int rel = blockIdx.x * blockDim.x + threadIdx.x;
     if (rel >= n) return;
     const int row = rel / Wp, w = rel - row * Wp;
     const int b = row_b[row], hh = row_h[row];
     const bool valid = b >= 0 && hh >= 0 && w < W;
     pix_b[rel] = valid ? b : -1;
-    if (pix_sub) pix_sub[rel] = (valid && !(hh & 1) && !(w & 1)) ? out_G + (out_utt_row0[b] + (hh >> 1)) * out_Wp + (w >> 1) : -1;
+    if (pix_ps)
+        pix_ps[rel] = valid ? (int)(((hh & 1) * 2 + (w & 1)) * phase_stride + out_G + (long long)(out_utt_row0[b] + (hh >> 1)) * out_Wp + (w >> 1))
+                            : -1;
 }
 
 static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
@@ -646,29 +693,48 @@ static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
         const Level* Lo = L.has_sub ? &pl.lv[l + 1] : nullptr;
         pixmeta_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, L.Wp, L.W, h->d32 + L.o_row_b, h->d32 + L.o_row_h, base + L.o_pix_b,
                                                         Lo ? base + L.o_pix_sub : nullptr, Lo ? Lo->G : 0, Lo ? Lo->Wp : 0,
-                                                        Lo ? h->d32 + Lo->o_utt_row0 : nullptr);
+                                                        Lo ? h->d32 + Lo->o_utt_row0 : nullptr, Lo ? (long long)(L.C / 8) * Lo->plane : 0);
     }
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
 }
 
 // ----------------------------------------------------------------------------- conv launch helper
-static int run_conv(skb_xtractor* h, const ConvW& cw, const Level& Lin, const uint16_t* in, uint16_t* out, const Level& Lout,
-                    bool subsample, int act, bool conv3x3, const int* tdnn_shifts, const float* se_scale, const uint16_t* res,
-                    bool pix_from_out, cudaStream_t st) {
+// kind: 0 = 1x1 / single tap, 1 = 3x3 pad 1, 2 = TDNN taps (tdnn_shifts), 3 = 3x3 stride 2 on a phase-split input.
+// `Lg` is the geometry the kernel walks (= the input's pixel layout); `to_phase_split` redirects the stores into the
+// phase-split buffer of the next level (`Lnext`).
+static int run_conv(skb_xtractor* h, const ConvW& cw, int kind, const Level& Lg, const uint16_t* in, uint16_t* out, int act,
+                    const int* tdnn_shifts, const float* se_scale, const uint16_t* res, const Level* pix_level,
+                    const Level* Lnext, cudaStream_t st) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
-    p.in = in; p.in_plane = Lin.plane; p.w = cw.w; p.bias = cw.bias; p.out = out; p.out_plane = Lout.plane;
+    p.in = in; p.in_plane = Lg.plane; p.w = cw.w; p.bias = cw.bias; p.out = out;
+    p.out_plane = Lnext ? Lnext->plane : Lg.plane;
     p.cin = cw.cin; p.cout = cw.cout; p.taps = cw.taps;
-    p.G = Lin.G; p.p_end = Lin.p_end;
+    p.G = Lg.G; p.p_end = Lg.p_end;
+    const int n_kc = cw.cin / kConvKC;
+    p.kc_per_grp = n_kc;
+    p.grp_tap[0] = 0;
+    for (int g = 1; g < 5; ++g) p.grp_tap[g] = cw.taps;
+    p.n_pairs = n_kc * cw.taps;
     int max_shift = 0;
-    if (conv3x3) {
-        p.halo = Lin.Wp + 1;
-        for (int t = 0; t < 9; ++t) p.tap_shift[t] = (t / 3 - 1) * Lin.Wp + (t % 3 - 1);
-        max_shift = Lin.Wp + 1;
-    } else if (tdnn_shifts) {
+    if (kind == 1) {
+        p.halo = Lg.Wp + 1;
+        for (int t = 0; t < 9; ++t) p.tap_shift[t] = (t / 3 - 1) * Lg.Wp + (t % 3 - 1);
+        max_shift = Lg.Wp + 1;
+    } else if (kind == 2) {
         p.halo = 0;
         for (int t = 0; t < cw.taps; ++t) { p.tap_shift[t] = tdnn_shifts[t]; max_shift = std::max(max_shift, tdnn_shifts[t]); }
+    } else if (kind == 3) {
+        // tap (r, s) of a stride-2 conv reads phase ((r-1) & 1, (s-1) & 1) at (h' + dh, w' + dw), dh/dw = -1 for r/s = 0 else 0
+        p.halo = Lg.Wp + 1;
+        for (int t = 0; t < 9; ++t) {
+            const int dh = kPhaseTaps[t][0] == 0 ? -1 : 0, dw = kPhaseTaps[t][1] == 0 ? -1 : 0;
+            p.tap_shift[t] = dh * Lg.Wp + dw;
+        }
+        p.kc_per_grp = n_kc / 4;
+        for (int g = 0; g < 5; ++g) p.grp_tap[g] = kPhaseTapBegin[g];
+        p.n_pairs = p.kc_per_grp * 9;
     } else {
         p.halo = 0;
         p.tap_shift[0] = 0;
@@ -677,12 +743,12 @@ static int run_conv(skb_xtractor* h, const ConvW& cw, const Level& Lin, const ui
     p.rows_pad = (tile_m + p.halo + max_shift + 7) / 8 * 8;
     p.act_slope = act == 1 ? 0.f : (act == 2 ? 0.2f : 1.f);
     const int* pm = (const int*)h->pixmeta.p;
-    // the validity table of the OUTPUT level decides what is stored as non-zero (TDNN: same geometry, fewer frames)
-    p.pix_b = pm + (pix_from_out ? Lout.o_pix_b : Lin.o_pix_b);
-    p.pix_sub = subsample ? pm + Lin.o_pix_sub : nullptr;
+    // the validity table of `pix_level` decides what is stored as non-zero (TDNN: same geometry, fewer frames per layer)
+    p.pix_b = pm + (pix_level ? pix_level->o_pix_b : Lg.o_pix_b);
+    p.pix_sub = Lnext ? pm + Lg.o_pix_sub : nullptr;
     p.se_scale = se_scale;
     p.res = res;
-    p.res_plane = Lout.plane;
+    p.res_plane = Lg.plane;
     g_launches++;
     return launch_conv_umma(p, cw.ncta, h->m.bf16, st);
 }
@@ -775,25 +841,33 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     int level = 0, cur = 0;   // current activation = buf(level, cur), cur in {0, 1}
     if (stop && !strcmp(stop, "stem")) return export_stage(h, buf(0, 0), L1, h_max, dbg_out, per_utt, st);
     int bi_in_layer = 0, layer = 1;
+    bool x_is_ps = false;     // the current activation lives phase-split in buf(level + 1, 3) instead of buf(level, cur)
     for (size_t i = 0; i < m.blocks.size(); ++i) {
         const BlockW& bw = m.blocks[i];
-        const int in_level = level;
-        const uint16_t* x = buf(level, cur);
-        if (bw.stride == 2) { level++; layer++; bi_in_layer = 0; cur = 1; }   // output goes to buf(level, 0)
-        const Level& Lin = pl.lv[in_level];
+        char name[32];
+        if (bw.stride == 2) { level++; layer++; bi_in_layer = 0; cur = 1; }   // this block's output goes to buf(level, 0)
+        snprintf(name, sizeof(name), "layer%d.%d", layer, bi_in_layer);
         const Level& L = pl.lv[level];
-        uint16_t *y1 = buf(level, 2), *y2 = buf(level, 3), *scb = buf(level, 4), *nxt = buf(level, cur ^ 1);
+        // the block after this one strides: write this block's output phase-split in the next level's geometry
+        const bool next_strides = i + 1 < m.blocks.size() && m.blocks[i + 1].stride == 2 && !(stop && !strcmp(stop, name));
+        const uint16_t* x = bw.stride == 2 ? buf(level, 3) : buf(level, cur);
+        if (bw.stride == 2 && !x_is_ps) {
+            set_last_error(__FILE__, __LINE__, "internal: stride-2 block without a phase-split input");
+            return SKB_ERR_STATE;
+        }
+        uint16_t *y1 = buf(level, 2), *scb = buf(level, 4), *nxt = buf(level, cur ^ 1);
         const uint16_t* res = x;
         {
             ProfScope ps(PROF_CONV, st);
-            SKB_TRY(run_conv(h, bw.conv1, Lin, x, y1, L, bw.stride == 2, 1, true, nullptr, nullptr, nullptr, false, st));
+            SKB_TRY(run_conv(h, bw.conv1, bw.stride == 2 ? 3 : 1, L, x, y1, 1, nullptr, nullptr, nullptr, nullptr, nullptr, st));
             if (bw.has_sc) {
-                SKB_TRY(run_conv(h, bw.sc, Lin, x, scb, L, bw.stride == 2, 0, false, nullptr, nullptr, nullptr, false, st));
+                // 1x1 shortcut; with stride 2 it reads phase (0, 0) = the first C_prev/8 planes of the phase-split input
+                SKB_TRY(run_conv(h, bw.sc, 0, L, x, scb, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st));
                 res = scb;
             }
         }
         {
-            // SE scales from conv2's INPUT (linearity of the convolution): one bandwidth-bound pass over y1 + a tiny kernel
+            // SE scales from conv2's INPUT (linearity of the convolution): one bandwidth-bound pass over y1 + small kernels
             ProfScope ps(PROF_SE, st);
             const int* pm = (const int*)h->pixmeta.p;
             SKB_TRY(launch_plane_sum(m.bf16, y1, L.plane, L.G, L.p_end, pm + L.o_pix_b, bw.C, (unsigned long long*)h->sums.p, st));
@@ -802,17 +876,16 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
                                     (float*)h->brd.p, (float*)h->scale.p, st));
         }
         {
-            // conv2 with the fused SE tail: nxt = relu(bn2(conv2(y1)) * scale + residual)
+            // conv2 with the fused SE tail: out = relu(bn2(conv2(y1)) * scale + residual)
             ProfScope ps(PROF_CONV, st);
-            SKB_TRY(run_conv(h, bw.conv2, L, y1, nxt, L, false, 1, true, nullptr, (const float*)h->scale.p, res, false, st));
+            uint16_t* dst = next_strides ? buf(level + 1, 3) : nxt;
+            SKB_TRY(run_conv(h, bw.conv2, 1, L, y1, dst, 1, nullptr, (const float*)h->scale.p, res, nullptr,
+                             next_strides ? &pl.lv[level + 1] : nullptr, st));
         }
+        x_is_ps = next_strides;
         g_launches += 4;
         cur ^= 1;
-        if (stop) {
-            char name[32];
-            snprintf(name, sizeof(name), "layer%d.%d", layer, bi_in_layer);
-            if (!strcmp(stop, name)) return export_stage(h, buf(level, cur), L, h_max, dbg_out, per_utt, st);
-        }
+        if (stop && !strcmp(stop, name)) return export_stage(h, buf(level, cur), L, h_max, dbg_out, per_utt, st);
         bi_in_layer++;
     }
     // attentive statistics pooling with global context (pooling.py:151-171)
@@ -864,8 +937,8 @@ static int forward_tdnn(skb_xtractor* h, const float* wave, int norm_embedding, 
         const Level& Lout = pl.lv[i + 1];
         // validity (row_h) of the OUTPUT rows decides what gets stored as non-zero
         ProfScope ps(PROF_CONV, st);
-        SKB_TRY(run_conv(h, m.tdnn[i], Lin, (const uint16_t*)h->act[i].p, (uint16_t*)h->act[i + 1].p, Lout, false, 2, false,
-                         shifts, nullptr, nullptr, true, st));
+        SKB_TRY(run_conv(h, m.tdnn[i], 2, Lin, (const uint16_t*)h->act[i].p, (uint16_t*)h->act[i + 1].p, 2, shifts, nullptr, nullptr,
+                         &Lout, nullptr, st));
         if (stop) {
             char name[32];
             snprintf(name, sizeof(name), "tdnn%d", i + 1);

@@ -74,7 +74,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -160,7 +160,7 @@ def cpu_reference_extraction(budget_s, n_threads):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     cores = os.cpu_count() or 1
     vals, sample = [], ""
     for i in range(args.warmup + args.steps):
@@ -174,7 +174,7 @@ def run_reference(args):
             "config": {"workload": "HalfResNet34 x-vector extraction, utterances 2-20 s (BASELINE config 4 shard shape)"},
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    return line
 
 
 def run_ours(args):
@@ -275,10 +275,12 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "extra": extra}
-        print(json.dumps(line))
+    else:
+        line = None
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 def run_extras(args, device, peaks, dist_on, rank, world):
@@ -343,19 +345,34 @@ def run_extras(args, device, peaks, dist_on, rank, world):
     return out
 
 
+class StdoutToStderr:
+    """Everything but the final JSON line goes to stderr (NCCL and friends print banners on stdout)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts", type=int, default=96, help="utterances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with StdoutToStderr():
+        line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -157,6 +157,34 @@ def cpu_reference_extraction(budget_s, n_threads):
     return done_s / dt, "%d utterances (%.0f audio-s) of the 2-20 s workload, batch-1 loop, %.1f s of CPU" % (n, done_s, dt)
 
 
+def gpu_eager_reference_extraction(budget_s):
+    """SURVEY.md 8d "reference GPU path": the reference's algorithm as stock PyTorch eager ops on this B200 (cuDNN /
+    cuBLAS / cuFFT), batch-1 loop like the reference's extractors, fp32 and fp16 autocast.  Reported next to the CPU
+    number in the `--impl reference` line; none of this repo's kernels run here."""
+    from oracle import extract_ref as R
+    from sidekit_b200 import synth
+    from tests.models import synthetic_state_dict
+    dev = torch.device("cuda", 0)
+    sd = {k: v.to(dev) for k, v in synthetic_state_dict("halfresnet34", N_SPK, 256).items()}
+    lengths = synth.synth_lengths(256, 2.0, 20.0, seed=4)
+    waves = [synth.synth_wave(1, int(L), seed=10 + i).to(dev) for i, L in enumerate(lengths[:64])]
+    out = {}
+    for name, amp in (("fp32", False), ("fp16_autocast", True)):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+            for w in waves[:3]:
+                R.forward(sd, w, "halfresnet34")
+            torch.cuda.synchronize()
+            t0, done, n = time.perf_counter(), 0.0, 0
+            while time.perf_counter() - t0 < budget_s:
+                w = waves[n % len(waves)]
+                R.forward(sd, w, "halfresnet34")[1].cpu()          # per-utterance D2H like extract_xvectors.py
+                done += w.shape[1] / 16000.0
+                n += 1
+            dt = time.perf_counter() - t0
+        out[name] = {"value": done / dt, "unit": "audio-s/s", "sample": "%d utterances, batch-1 loop, %.1f s" % (n, dt)}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -174,6 +202,11 @@ def run_reference(args):
             "config": {"workload": "HalfResNet34 x-vector extraction, utterances 2-20 s (BASELINE config 4 shard shape)"},
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if torch.cuda.is_available():
+        try:
+            line["extra"] = {"torch_eager_on_this_gpu": gpu_eager_reference_extraction(4.0)}
+        except Exception as e:                                        # informational only
+            line["extra"] = {"torch_eager_on_this_gpu": {"unavailable": repr(e)[:200]}}
     return line
 
 

@@ -72,9 +72,9 @@ def power_spectrogram(y, n_fft, win_length, hop, window=None):
     T = 1 + L // hop
     if window is None:
         window = hann_periodic(win_length, y.dtype)
-    w = torch.zeros(n_fft, dtype=y.dtype)
+    w = torch.zeros(n_fft, dtype=y.dtype, device=y.device)
     left = (n_fft - win_length) // 2
-    w[left:left + win_length] = window.to(y.dtype)
+    w[left:left + win_length] = window.to(device=y.device, dtype=y.dtype)
     frames = yp.unfold(1, n_fft, hop)[:, :T, :]              # (B, T, n_fft)
     spec = torch.fft.rfft(frames * w, dim=2)                 # (B, T, n_fft/2+1)
     return (spec.real ** 2 + spec.imag ** 2).transpose(1, 2)

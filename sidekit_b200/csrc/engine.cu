@@ -252,7 +252,7 @@ struct Model {
     float margin_s = 30.f;
     FrontendConsts fe;
     // halfresnet34
-    float *stem_w = nullptr, *stem_b = nullptr;
+    StemConsts stem;            // folded stem conv + BN (host copy: passed to the kernel by value)
     std::vector<BlockW> blocks;
     float *att_w1x = nullptr, *att_w1g = nullptr, *att_b1 = nullptr, *att_bn_s = nullptr, *att_bn_t = nullptr;
     float *att_w2 = nullptr, *att_b2 = nullptr;
@@ -323,11 +323,10 @@ static int build_hr34(const WeightMap& w, Model* m) {
         if (!cw || cw->numel() != 32 * 9) return SKB_ERR_WEIGHTS;
         std::vector<double> s, t;
         if ((rc = bn_affine(w, sn + ".bn1", &s, &t))) return rc;
-        std::vector<double> wf(288);
-        for (int c = 0; c < 32; ++c)
-            for (int k = 0; k < 9; ++k) wf[c * 9 + k] = (double)cw->p[c * 9 + k] * s[c];
-        if ((rc = upload_f(wf, &m->stem_w))) return rc;
-        if ((rc = upload_f(t, &m->stem_b))) return rc;
+        for (int c = 0; c < 32; ++c) {
+            for (int k = 0; k < 9; ++k) m->stem.w[c * 9 + k] = (float)((double)cw->p[c * 9 + k] * s[c]);
+            m->stem.b[c] = (float)t[c];
+        }
     }
     const int nblocks[4] = {3, 4, 6, 3}, planes[4] = {32, 64, 128, 256};
     for (int li = 0; li < 4; ++li)
@@ -432,7 +431,6 @@ static int build_tdnn(const WeightMap& w, Model* m) {
 
 static void free_model(Model* m) {
     frontend_consts_destroy(&m->fe);
-    cudaFree(m->stem_w); cudaFree(m->stem_b);
     for (auto& b : m->blocks) {
         free_conv(&b.conv1); free_conv(&b.conv2);
         if (b.has_sc) free_conv(&b.sc);
@@ -453,6 +451,7 @@ struct Level {
     std::vector<int> H;            // lines per utterance
     // offsets (in ints) into the device table buffer
     size_t o_row_b = 0, o_row_h = 0, o_utt_row0 = 0, o_utt_count = 0;
+    size_t o_span = 0;             // per-256-pixel utterance table for plane_sum_kernel (halfresnet34 only)
     size_t o_pix_b = 0, o_pix_sub = 0;   // o_pix_sub: phase-split destination table (see pixmeta_kernel)   // offsets (ints) into the device pixel-meta buffer; o_pix_sub valid when has_sub
     bool has_sub = false;
 };
@@ -504,7 +503,7 @@ struct skb_xtractor {
     Model m;
     Plan plan;
     bool plan_valid = false;
-    DevBuf pixmeta, brd;
+    DevBuf pixmeta, brd, cmvn, cmvn_part;
     DevBuf tab32, tab64, feats, sums, scale, poolX, poolH, poolL, gc, hb, pooled, lin, emb_pre, emb, logits, wave, dbg;
     std::vector<DevBuf> act;      // activation buffers
     std::vector<size_t> act_bytes;
@@ -639,6 +638,8 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
         SKB_CUDA_CHECK(cudaMemsetAsync(h->sums.p, 0, (size_t)B * Cmax * sizeof(unsigned long long), st));
     }
     if ((rc = h->feats.ensure((size_t)pl.total_frames * m.fe.n_out * sizeof(float)))) return rc;
+    if ((rc = h->cmvn.ensure((size_t)B * m.fe.n_out * sizeof(float2)))) return rc;
+    if ((rc = h->cmvn_part.ensure(frontend_cmvn_scratch_bytes(m.fe, B, pl.t_max)))) return rc;
     const int D = m.pool_D;
     if ((rc = h->poolX.ensure((size_t)pl.pool_frames * D * sizeof(float)))) return rc;
     if (m.archi == SKB_ARCHI_HALFRESNET34) {
@@ -683,6 +684,7 @@ static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
         L.o_pix_b = total; total += n;
         L.has_sub = hr && l + 1 < pl.lv.size();
         if (L.has_sub) { L.o_pix_sub = total; total += n; }
+        if (hr) { L.o_span = total; total += (size_t)span_table_size((int)n); }
     }
     int rc = h->pixmeta.ensure(total * sizeof(int));
     if (rc) return rc;
@@ -694,6 +696,10 @@ static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
         pixmeta_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, L.Wp, L.W, h->d32 + L.o_row_b, h->d32 + L.o_row_h, base + L.o_pix_b,
                                                         Lo ? base + L.o_pix_sub : nullptr, Lo ? Lo->G : 0, Lo ? Lo->Wp : 0,
                                                         Lo ? h->d32 + Lo->o_utt_row0 : nullptr, Lo ? (long long)(L.C / 8) * Lo->plane : 0);
+        if (hr) {
+            int rc2 = launch_span_table(base + L.o_pix_b, n, base + L.o_span, st);
+            if (rc2) return rc2;
+        }
     }
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
@@ -826,16 +832,17 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     float* feats = (float*)h->feats.p;
     {
         ProfScope ps(PROF_FRONTEND, st);
+        // raw log-Mel + CMVN statistics; the stem kernel normalises on the fly
         SKB_TRY(frontend_launch(m.fe, wave, d64 + pl.o_wave_off, d32 + pl.o_wave_len, d64 + pl.o_feat_off, d32 + pl.o_nframes, B,
-                                pl.t_max, feats, nullptr, st));
+                                pl.t_max, feats, (float2*)h->cmvn.p, h->cmvn_part.p, false, nullptr, st));
     }
-    g_launches += 2;
+    g_launches += 3;
     auto buf = [&](int level, int k) { return (uint16_t*)h->act[level * 5 + k].p; };
     const Level& L1 = pl.lv[0];
     {
         ProfScope ps(PROF_STEM, st);
-        SKB_TRY(launch_stem(m.bf16, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, m.stem_w, m.stem_b, buf(0, 0), L1.plane, L1.G,
-                            L1.p_end, L1.Wp, L1.W, d32 + L1.o_row_b, d32 + L1.o_row_h, st));
+        SKB_TRY(launch_stem(m.bf16, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, (const float2*)h->cmvn.p, m.stem, buf(0, 0),
+                            L1.plane, L1.G, L1.p_end, L1.Wp, L1.W, d32 + L1.o_row_b, d32 + L1.o_row_h, st));
     }
     g_launches++;
     int level = 0, cur = 0;   // current activation = buf(level, cur), cur in {0, 1}
@@ -870,7 +877,8 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
             // SE scales from conv2's INPUT (linearity of the convolution): one bandwidth-bound pass over y1 + small kernels
             ProfScope ps(PROF_SE, st);
             const int* pm = (const int*)h->pixmeta.p;
-            SKB_TRY(launch_plane_sum(m.bf16, y1, L.plane, L.G, L.p_end, pm + L.o_pix_b, bw.C, (unsigned long long*)h->sums.p, st));
+            SKB_TRY(launch_plane_sum(m.bf16, y1, L.plane, L.G, L.p_end, pm + L.o_pix_b, pm + L.o_span, bw.C,
+                                     (unsigned long long*)h->sums.p, st));
             SKB_TRY(launch_se_scale(m.bf16, (unsigned long long*)h->sums.p, y1, L.plane, L.G, L.Wp, L.W, d32 + L.o_utt_row0,
                                     d32 + L.o_utt_count, B, bw.C, bw.C, bw.w2t, bw.conv2.bias, bw.se_w1, bw.se_w2,
                                     (float*)h->brd.p, (float*)h->scale.p, st));
@@ -924,12 +932,12 @@ static int forward_tdnn(skb_xtractor* h, const float* wave, int norm_embedding, 
     {
         ProfScope ps(PROF_FRONTEND, st);
         SKB_TRY(frontend_launch(m.fe, wave, d64 + pl.o_wave_off, d32 + pl.o_wave_len, d64 + pl.o_feat_off, d32 + pl.o_nframes, B,
-                                pl.t_max, feats, nullptr, st));
+                                pl.t_max, feats, (float2*)h->cmvn.p, h->cmvn_part.p, true, nullptr, st));
     }
     const Level& L0 = pl.lv[0];
     SKB_TRY(launch_pack_frames(m.bf16, feats, m.fe.n_out, L0.C, (int)pl.total_frames, d32 + pl.o_row_src, (uint16_t*)h->act[0].p,
                                L0.plane, L0.G, st));
-    g_launches += 3;
+    g_launches += 5;
     for (int i = 0; i < 5; ++i) {
         int shifts[10];
         for (int k = 0; k < m.tdnn_k[i]; ++k) shifts[k] = k * m.tdnn_d[i];
@@ -1041,7 +1049,8 @@ void skb_xtractor_destroy(skb_xtractor_t* h) {
     if (!h) return;
     free_model(&h->m);
     DevBuf* bufs[] = {&h->tab32, &h->tab64, &h->feats, &h->sums, &h->scale, &h->poolX, &h->poolH, &h->poolL, &h->gc, &h->hb,
-                      &h->pooled, &h->lin, &h->emb_pre, &h->emb, &h->logits, &h->wave, &h->dbg, &h->pixmeta, &h->brd};
+                      &h->pooled, &h->lin, &h->emb_pre, &h->emb, &h->logits, &h->wave, &h->dbg, &h->pixmeta, &h->brd, &h->cmvn,
+                      &h->cmvn_part};
     for (auto* b : bufs) b->release();
     for (auto& b : h->act) b.release();
     delete h;
@@ -1107,9 +1116,10 @@ int skb_xtractor_frontend(skb_xtractor_t* h, const float* wave_dev, const int64_
         return SKB_ERR_ARG;
     }
     SKB_CUDA_CHECK(cudaMemsetAsync(feats_dev, 0, (size_t)n_utt * h->m.fe.n_out * t_max * sizeof(float), st));
-    g_launches += 2;
+    g_launches += 4;
     return frontend_launch(h->m.fe, wave_dev, h->d64 + pl.o_wave_off, h->d32 + pl.o_wave_len, h->d64 + pl.o_feat_off,
-                           h->d32 + pl.o_nframes, n_utt, t_max, (float*)h->feats.p, feats_dev, st);
+                           h->d32 + pl.o_nframes, n_utt, t_max, (float*)h->feats.p, (float2*)h->cmvn.p, h->cmvn_part.p, true,
+                           feats_dev, st);
 }
 
 int skb_xtractor_debug_stage(skb_xtractor_t* h, const float* wave_dev, const int64_t* lengths, int n_utt, const char* stage,

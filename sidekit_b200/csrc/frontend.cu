@@ -59,22 +59,26 @@ __device__ __forceinline__ void dft8(float2 (&a)[8]) {
     a[3] = cadd(E3, t3); a[7] = csub(E3, t3);
 }
 
-// One radix-8 DIF stage over sub-transforms of length `len` (len = 8 * sub): thread handles index j of block blk.
-template <int NC>
-__device__ __forceinline__ void stage8(float2* z, const float2* tw, int len, int t) {
-    const int sub = len >> 3;
+// Shared-memory index of complex point i: one pad slot every 8 points, so that the stride-8 (second stage), stride-64
+// (first stage) and contiguous-group (last stage) access patterns of the radix-8 passes all spread over the banks.
+__device__ __forceinline__ int zp(int i) { return i + (i >> 3); }
+
+// One radix-8 DIF butterfly of the stage whose sub-transforms have length LEN (LEN = 8 * sub); t = butterfly index.
+template <int NC, int LEN>
+__device__ __forceinline__ void stage8(float2* z, const float2* tw, int t) {
+    constexpr int sub = LEN >> 3;
     const int blk = t / sub, j = t - blk * sub;
-    float2* base = z + blk * len + j;
+    const int e0 = blk * LEN + j;
     float2 a[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] = base[q * sub];
+    for (int q = 0; q < 8; ++q) a[q] = z[zp(e0 + q * sub)];
     dft8(a);
-    const int tstep = (NC / len) * j;       // w_len^{j r} = w_NC^{(NC/len) j r}
+    const int tstep = (NC / LEN) * j;       // w_len^{j r} = w_NC^{(NC/len) j r}
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         float2 v = a[r];
         if (sub > 1 && r > 0) v = cmul(v, tw[(tstep * r) & (NC - 1)]);
-        base[r * sub] = v;
+        z[zp(e0 + r * sub)] = v;
     }
 }
 
@@ -90,169 +94,171 @@ __device__ __forceinline__ int rev_index<1024>(int k) {    // 8 x 8 x 8 x 2: k =
     return ((k & 7) << 7) | (((k >> 3) & 7) << 4) | (((k >> 6) & 7) << 1) | (k >> 9);
 }
 
-// NC complex points per frame, NC/8 threads per frame, FR frames per CTA iteration.
-template <int NC, int FR>
-__global__ void __launch_bounds__(NC / 8 * FR) frontend_kernel(const FrontendParams p, int frames_per_cta) {
-    constexpr int TPF = NC / 8;                 // threads per frame
+// NC complex points per frame.  One WARP per frame: the whole transform of a frame lives in a warp-private slice of
+// shared memory and the passes are separated by __syncwarp only, so the WPC warps of a CTA never wait for each other
+// (the first version used 64 threads per frame and 8 CTA-wide barriers per frame, and was barrier-stall-bound).
+template <int NC, int WPC>
+__global__ void __launch_bounds__(WPC * 32, 1024 / (WPC * 32)) frontend_kernel(const FrontendParams p, int frames_per_cta) {
+    constexpr int ZS = NC + NC / 8 + 8;         // padded complex points per frame buffer
+    constexpr int NB = NC / 8;                  // butterflies per radix-8 stage
     extern __shared__ __align__(16) uint8_t fsm[];
     float2* tw = reinterpret_cast<float2*>(fsm);                 // [NC]
-    float2* zall = tw + NC;                                      // [FR][NC + 1]
-    float* melall = reinterpret_cast<float*>(zall + FR * (NC + 1));   // [FR][n_mels]
+    float2* zall = tw + NC;                                      // [WPC][ZS]
+    float* melall = reinterpret_cast<float*>(zall + WPC * ZS);   // [WPC][n_mels]
     const int b = blockIdx.y;
     const int T = p.n_frames[b];
     const int t_begin = blockIdx.x * frames_per_cta;
     if (t_begin >= T) return;
     const int t_end = min(T, t_begin + frames_per_cta);
-    const int fr = threadIdx.x / TPF;
-    const int t = threadIdx.x - fr * TPF;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < NC; i += blockDim.x) tw[i] = p.tw_half[i];
+    __syncthreads();
     const float* x = p.wave + p.wave_off[b];
     const int L = p.wave_len[b];
-    float2* z = zall + fr * (NC + 1);
-    float* mel = melall + fr * p.n_mels;
+    float2* z = zall + warp * ZS;
+    float* mel = melall + warp * p.n_mels;
     const int half_win = p.win >> 1;
 
-    for (int tb = t_begin; tb < t_end; tb += FR) {
-        const int frame = tb + fr;
-        const bool active = frame < t_end;
-        __syncthreads();
-        if (active) {
-            // windowed, pre-emphasised frame: sample n <-> y[hop*frame - win/2 + n] with reflect padding of y
-            for (int n2 = t; n2 < NC; n2 += TPF) {
-                float v[2];
+    for (int frame = t_begin + warp; frame < t_end; frame += WPC) {
+        // windowed, pre-emphasised frame: sample n <-> y[hop*frame - win/2 + n] with reflect padding of y
+        for (int n2 = lane; n2 < NC; n2 += 32) {
+            float v[2];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int n = 2 * n2 + e;
-                    float val = 0.f;
-                    if (n < p.win) {
-                        int i = p.hop * frame - half_win + n;
-                        if (i < 0) i = -i;
-                        if (i >= L) i = 2 * (L - 1) - i;
-                        const float cur = __ldg(x + i);
-                        const float prev = __ldg(x + (i == 0 ? 1 : i - 1));
-                        val = (cur - p.preemph * prev) * __ldg(p.window + n);
-                    }
-                    v[e] = val;
+            for (int e = 0; e < 2; ++e) {
+                const int n = 2 * n2 + e;
+                float val = 0.f;
+                if (n < p.win) {
+                    int i = p.hop * frame - half_win + n;
+                    if (i < 0) i = -i;
+                    if (i >= L) i = 2 * (L - 1) - i;
+                    const float cur = __ldg(x + i);
+                    const float prev = __ldg(x + (i == 0 ? 1 : i - 1));
+                    val = (cur - p.preemph * prev) * __ldg(p.window + n);
                 }
-                z[n2] = make_float2(v[0], v[1]);
+                v[e] = val;
+            }
+            z[zp(n2)] = make_float2(v[0], v[1]);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int tt = 0; tt < NB / 32; ++tt) stage8<NC, NC>(z, tw, lane + 32 * tt);
+        __syncwarp();
+#pragma unroll 1
+        for (int tt = 0; tt < NB / 32; ++tt) stage8<NC, NC / 8>(z, tw, lane + 32 * tt);
+        __syncwarp();
+#pragma unroll 1
+        for (int tt = 0; tt < NB / 32; ++tt) stage8<NC, NC / 64>(z, tw, lane + 32 * tt);
+        __syncwarp();
+        if (NC == 1024) {   // final radix-2 stage on pairs
+#pragma unroll
+            for (int u = 0; u < NC / 64; ++u) {
+                const int i = (lane + 32 * u) * 2;
+                const float2 a0 = z[zp(i)], a1 = z[zp(i + 1)];
+                z[zp(i)] = cadd(a0, a1);
+                z[zp(i + 1)] = csub(a0, a1);
+            }
+            __syncwarp();
+        }
+        // unpack the real spectrum, take |X|^2 for k = 0..NC and store it in natural order into a power buffer
+        // that aliases z (all reads first).
+        constexpr int kPer = NC / 32 + 1;           // ceil((NC + 1) / 32)
+        float pw[kPer];
+#pragma unroll
+        for (int c = 0; c < kPer; ++c) {
+            const int k = lane + c * 32;
+            pw[c] = 0.f;
+            if (k <= NC) {
+                const float2 zk = z[zp(rev_index<NC>(k & (NC - 1)))];
+                const float2 zr = z[zp(rev_index<NC>((NC - k) & (NC - 1)))];
+                const float2 zc = make_float2(zr.x, -zr.y);
+                const float2 s = cadd(zk, zc), d = csub(zk, zc);
+                const float2 wd = cmul(__ldg(p.tw_full + k), d);      // e^{-2 pi i k / n_fft} (Z[k] - conj Z[N-k])
+                const float re = 0.5f * (s.x + wd.y);                   // (-i/2) wd = (wd.y - i wd.x) / 2
+                const float im = 0.5f * (s.y - wd.x);
+                pw[c] = re * re + im * im;
             }
         }
-        __syncthreads();
-        if (active) stage8<NC>(z, tw, NC, t);
-        __syncthreads();
-        if (active) stage8<NC>(z, tw, NC / 8, t);
-        __syncthreads();
-        if (active) stage8<NC>(z, tw, NC / 64, t);
-        __syncthreads();
-        if (NC == 1024) {
-            if (active) {   // final radix-2 stage on pairs
+        __syncwarp();
+        float* pwr = reinterpret_cast<float*>(z);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = (t * 4 + u) * 2;
-                    const float2 a0 = z[i], a1 = z[i + 1];
-                    z[i] = cadd(a0, a1);
-                    z[i + 1] = csub(a0, a1);
-                }
-            }
-            __syncthreads();
+        for (int c = 0; c < kPer; ++c) {
+            const int k = lane + c * 32;
+            if (k <= NC) pwr[k] = pw[c];
         }
-        if (active) {
-            // unpack the real spectrum, take |X|^2 for k = 0..NC and store it in natural order into a
-            // power buffer that aliases z (all reads first).
-            constexpr int kPer = (NC + TPF) / TPF;      // ceil((NC + 1) / TPF)
-            float pw[kPer];
-#pragma unroll
-            for (int c = 0; c < kPer; ++c) {
-                const int k = t + c * TPF;
-                pw[c] = 0.f;
-                if (k <= NC) {
-                    const float2 zk = z[rev_index<NC>(k & (NC - 1))];
-                    const float2 zr = z[rev_index<NC>((NC - k) & (NC - 1))];
-                    const float2 zc = make_float2(zr.x, -zr.y);
-                    const float2 s = cadd(zk, zc), d = csub(zk, zc);
-                    const float2 wd = cmul(__ldg(p.tw_full + k), d);      // e^{-2 pi i k / n_fft} (Z[k] - conj Z[N-k])
-                    const float re = 0.5f * (s.x + wd.y);                   // (-i/2) wd = (wd.y - i wd.x) / 2
-                    const float im = 0.5f * (s.y - wd.x);
-                    pw[c] = re * re + im * im;
-                }
-            }
-            // every read of z by this frame's threads completes before the power spectrum overwrites it
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + fr), "r"(TPF) : "memory");
-            float* pwr = reinterpret_cast<float*>(z);
-#pragma unroll
-            for (int c = 0; c < kPer; ++c) {
-                const int k = t + c * TPF;
-                if (k <= NC) pwr[k] = pw[c];
-            }
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + fr), "r"(TPF) : "memory");
-            for (int m = t; m < p.n_mels; m += TPF) {
-                const int lo = p.mel_lo[m], c = p.mel_cnt[m];
-                const float* w = p.mel_w + p.mel_ofs[m];
+        __syncwarp();
+        float* dst = p.out + (size_t)(p.feat_off[b] + frame) * p.n_out;
+        for (int m = lane; m < p.n_mels; m += 32) {
+            const int lo = p.mel_lo[m], c = p.mel_cnt[m];
+            const float* w = p.mel_w + p.mel_ofs[m];
+            float acc = 0.f;
+            for (int i = 0; i < c; ++i) acc = fmaf(pwr[lo + i], __ldg(w + i), acc);
+            const float lm = logf(acc + 1e-6f);
+            if (p.dct == nullptr) dst[m] = lm;
+            else mel[m] = lm;
+        }
+        if (p.dct != nullptr) {
+            __syncwarp();
+            for (int c = lane; c < p.n_out; c += 32) {
                 float acc = 0.f;
-                for (int i = 0; i < c; ++i) acc = fmaf(pwr[lo + i], __ldg(w + i), acc);
-                mel[m] = logf(acc + 1e-6f);
-            }
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + fr), "r"(TPF) : "memory");
-            float* dst = p.out + (size_t)(p.feat_off[b] + frame) * p.n_out;
-            if (p.dct == nullptr) {
-                for (int m = t; m < p.n_out; m += TPF) dst[m] = mel[m];
-            } else {
-                for (int c = t; c < p.n_out; c += TPF) {
-                    float acc = 0.f;
-                    for (int m = 0; m < p.n_mels; ++m) acc = fmaf(mel[m], __ldg(p.dct + m * p.n_out + c), acc);
-                    dst[c] = acc;
-                }
+                for (int m = 0; m < p.n_mels; ++m) acc = fmaf(mel[m], __ldg(p.dct + m * p.n_out + c), acc);
+                dst[c] = acc;
             }
         }
+        __syncwarp();     // the next frame's fill overwrites z / pwr / mel
     }
 }
 
-// CMVN (torch.nn.InstanceNorm1d, biased variance, eps 1e-5): exact two-pass statistics per
-// (utterance, coefficient) over time on the frame-major buffer; optionally also writes the
-// (B, n_out, T_max)-shaped tensor the reference's front-end returns.
-__global__ void cmvn_kernel(float* feats, const long long* feat_off, const int* n_frames, int n_out,
-                            float* api_out, int t_max) {
-    const int b = blockIdx.x;
+// CMVN (torch.nn.InstanceNorm1d, biased variance, eps 1e-5) statistics per (utterance, coefficient) over time on the
+// frame-major buffer: fixed 64-frame chunks summed in double (sum, sum of squares), then combined in chunk order --
+// deterministic and, in double, as exact as the two-pass formula.  The normalisation itself is applied by the consumer
+// (stem kernel) or by cmvn_apply_kernel.
+constexpr int kCmvnChunk = 64;
+__global__ void __launch_bounds__(128) cmvn_partial_kernel(const float* __restrict__ feats, const long long* __restrict__ feat_off,
+                                                           const int* __restrict__ n_frames, int n_out, int max_chunks,
+                                                           double2* __restrict__ part) {
+    const int b = blockIdx.y, ch = blockIdx.x, c = threadIdx.x;
+    const int T = n_frames[b], t0 = ch * kCmvnChunk;
+    if (t0 >= T || c >= n_out) return;
+    const int t1 = min(T, t0 + kCmvnChunk);
+    const float* f = feats + (size_t)feat_off[b] * n_out + c;
+    double s = 0.0, ss = 0.0;
+    for (int t = t0; t < t1; ++t) {
+        const double v = (double)f[(size_t)t * n_out];
+        s += v;
+        ss = fma(v, v, ss);
+    }
+    part[((size_t)b * max_chunks + ch) * n_out + c] = make_double2(s, ss);
+}
+
+__global__ void __launch_bounds__(128) cmvn_final_kernel(const double2* __restrict__ part, const int* __restrict__ n_frames, int n_out,
+                                                         int max_chunks, float2* __restrict__ cmvn) {
+    const int b = blockIdx.x, c = threadIdx.x;
+    if (c >= n_out) return;
+    const int T = n_frames[b], nch = (T + kCmvnChunk - 1) / kCmvnChunk;
+    double s = 0.0, ss = 0.0;
+    for (int ch = 0; ch < nch; ++ch) {
+        const double2 v = part[((size_t)b * max_chunks + ch) * n_out + c];
+        s += v.x;
+        ss += v.y;
+    }
+    const double mean = s / T;
+    const double var = fmax(ss / T - mean * mean, 0.0);
+    cmvn[(size_t)b * n_out + c] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+}
+
+// in-place normalisation (+ optionally the (B, n_out, t_max) tensor the reference's front-end returns)
+__global__ void cmvn_apply_kernel(float* __restrict__ feats, const long long* __restrict__ feat_off, const int* __restrict__ n_frames,
+                                  int n_out, const float2* __restrict__ cmvn, float* __restrict__ api_out, int t_max) {
+    const int b = blockIdx.y;
     const int T = n_frames[b];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)T * n_out) return;
+    const int t = (int)(idx / n_out), c = (int)(idx - (long long)t * n_out);
+    const float2 ms = cmvn[(size_t)b * n_out + c];
     float* f = feats + (size_t)feat_off[b] * n_out;
-    __shared__ float s_mean[128], s_rstd[128];
-    __shared__ float part[8][128];
-    const int c = threadIdx.x % n_out, g = threadIdx.x / n_out;
-    const int ng = blockDim.x / n_out;
-    float acc = 0.f;
-    if (g < ng) for (int t = g; t < T; t += ng) acc += f[(size_t)t * n_out + c];
-    if (g < ng) part[g][c] = acc;
-    __syncthreads();
-    if (threadIdx.x < n_out) {
-        float s = 0.f;
-        for (int i = 0; i < ng; ++i) s += part[i][threadIdx.x];
-        s_mean[threadIdx.x] = s / (float)T;
-    }
-    __syncthreads();
-    acc = 0.f;
-    if (g < ng) {
-        const float mu = s_mean[c];
-        for (int t = g; t < T; t += ng) {
-            const float d = f[(size_t)t * n_out + c] - mu;
-            acc = fmaf(d, d, acc);
-        }
-        part[g][c] = acc;
-    }
-    __syncthreads();
-    if (threadIdx.x < n_out) {
-        float s = 0.f;
-        for (int i = 0; i < ng; ++i) s += part[i][threadIdx.x];
-        s_rstd[threadIdx.x] = rsqrtf(s / (float)T + 1e-5f);
-    }
-    __syncthreads();
-    if (g < ng) {
-        const float mu = s_mean[c], rs = s_rstd[c];
-        for (int t = g; t < T; t += ng) {
-            const float v = (f[(size_t)t * n_out + c] - mu) * rs;
-            f[(size_t)t * n_out + c] = v;
-            if (api_out) api_out[((size_t)b * n_out + c) * t_max + t] = v;
-        }
-    }
+    const float v = (f[idx] - ms.x) * ms.y;
+    f[idx] = v;
+    if (api_out) api_out[((size_t)b * n_out + c) * t_max + t] = v;
 }
 
 }  // namespace skb
@@ -314,32 +320,49 @@ void frontend_consts_destroy(FrontendConsts* fc) {
     *fc = FrontendConsts();
 }
 
+size_t frontend_cmvn_scratch_bytes(const FrontendConsts& fc, int B, int t_max) {
+    const int max_chunks = (t_max + kCmvnChunk - 1) / kCmvnChunk;
+    return (size_t)B * max_chunks * fc.n_out * sizeof(double2);
+}
+
 // feats: frame-major [sum T][n_out]; api_out optional (B, n_out, t_max).
 int frontend_launch(const FrontendConsts& fc, const float* wave, const long long* wave_off, const int* wave_len,
-                    const long long* feat_off, const int* n_frames, int B, int t_max, float* feats, float* api_out,
-                    cudaStream_t stream) {
+                    const long long* feat_off, const int* n_frames, int B, int t_max, float* feats, float2* cmvn,
+                    void* cmvn_part, bool normalise, float* api_out, cudaStream_t stream) {
     FrontendParams p;
     p.wave = wave; p.wave_off = wave_off; p.wave_len = wave_len; p.feat_off = feat_off; p.n_frames = n_frames;
     p.out = feats; p.window = fc.window; p.tw_half = fc.tw_half; p.tw_full = fc.tw_full;
     p.mel_lo = fc.mel_lo; p.mel_cnt = fc.mel_cnt; p.mel_ofs = fc.mel_ofs; p.mel_w = fc.mel_w; p.dct = fc.dct;
     p.n_mels = fc.n_mels; p.n_out = fc.n_out; p.hop = fc.hop; p.win = fc.win; p.preemph = 0.97f;
-    const int frames_per_cta = 16;
-    dim3 grid((t_max + frames_per_cta - 1) / frames_per_cta, B);
+    if (fc.n_out > 128) {
+        set_last_error(__FILE__, __LINE__, "front-end: more than 128 output coefficients");
+        return SKB_ERR_ARG;
+    }
     if (fc.n_fft == 1024) {
-        constexpr int NC = 512, FR = 4;
-        const size_t smem = NC * sizeof(float2) + FR * (NC + 1) * sizeof(float2) + FR * fc.n_mels * sizeof(float);
-        frontend_kernel<NC, FR><<<grid, NC / 8 * FR, smem, stream>>>(p, frames_per_cta);
+        constexpr int NC = 512, WPC = 8;
+        const int frames_per_cta = 4 * WPC;
+        dim3 grid((t_max + frames_per_cta - 1) / frames_per_cta, B);
+        const size_t smem = NC * sizeof(float2) + WPC * (NC + NC / 8 + 8) * sizeof(float2) + WPC * fc.n_mels * sizeof(float);
+        frontend_kernel<NC, WPC><<<grid, WPC * 32, smem, stream>>>(p, frames_per_cta);
     } else if (fc.n_fft == 2048) {
-        constexpr int NC = 1024, FR = 2;
-        const size_t smem = NC * sizeof(float2) + FR * (NC + 1) * sizeof(float2) + FR * fc.n_mels * sizeof(float);
-        frontend_kernel<NC, FR><<<grid, NC / 8 * FR, smem, stream>>>(p, frames_per_cta);
+        constexpr int NC = 1024, WPC = 4;
+        const int frames_per_cta = 4 * WPC;
+        dim3 grid((t_max + frames_per_cta - 1) / frames_per_cta, B);
+        const size_t smem = NC * sizeof(float2) + WPC * (NC + NC / 8 + 8) * sizeof(float2) + WPC * fc.n_mels * sizeof(float);
+        frontend_kernel<NC, WPC><<<grid, WPC * 32, smem, stream>>>(p, frames_per_cta);
     } else {
         set_last_error(__FILE__, __LINE__, "unsupported n_fft (1024 or 2048)");
         return SKB_ERR_ARG;
     }
     SKB_CUDA_CHECK(cudaGetLastError());
-    const int ng = 512 / fc.n_out;
-    cmvn_kernel<<<B, ng * fc.n_out, 0, stream>>>(feats, feat_off, n_frames, fc.n_out, api_out, t_max);
+    const int max_chunks = (t_max + kCmvnChunk - 1) / kCmvnChunk;
+    cmvn_partial_kernel<<<dim3(max_chunks, B), 128, 0, stream>>>(feats, feat_off, n_frames, fc.n_out, max_chunks, (double2*)cmvn_part);
+    cmvn_final_kernel<<<B, 128, 0, stream>>>((const double2*)cmvn_part, n_frames, fc.n_out, max_chunks, cmvn);
+    if (normalise) {
+        const long long per_utt = (long long)t_max * fc.n_out;
+        cmvn_apply_kernel<<<dim3((unsigned)((per_utt + 255) / 256), B), 256, 0, stream>>>(feats, feat_off, n_frames, fc.n_out, cmvn,
+                                                                                        api_out, t_max);
+    }
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
 }

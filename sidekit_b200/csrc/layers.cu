@@ -12,14 +12,13 @@ namespace skb {
 // One thread per level-1 pixel; the normalised features are frame-major so a warp reads contiguous
 // mel bins.  fp32 math on CUDA cores (0.1 % of the trunk's FLOPs), 16-bit chunk-plane output.
 template <bool BF16>
-__global__ void stem_kernel(const float* __restrict__ feats, const long long* __restrict__ feat_off,
-                            const int* __restrict__ n_frames, const float* __restrict__ w /*[32][9]*/,
-                            const float* __restrict__ bias /*[32]*/, uint16_t* __restrict__ out, long long out_plane,
-                            int G, int p_end, int Wp, int W, const int* __restrict__ row_b,
-                            const int* __restrict__ row_h) {
-    __shared__ float sw[32 * 9 + 32];
-    for (int i = threadIdx.x; i < 32 * 9 + 32; i += blockDim.x) sw[i] = i < 288 ? w[i] : bias[i - 288];
-    __syncthreads();
+__global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemConsts sc, const float* __restrict__ feats,
+                                                   const long long* __restrict__ feat_off, const int* __restrict__ n_frames,
+                                                   const float2* __restrict__ cmvn /*[B][W] (mean, rstd)*/,
+                                                   uint16_t* __restrict__ out, long long out_plane, int G, int p_end, int Wp,
+                                                   int W, const int* __restrict__ row_b, const int* __restrict__ row_h) {
+    // The folded weights arrive as a kernel parameter: every FFMA takes its weight straight from the constant bank
+    // (a shared-memory copy costs one LDS per FMA and made the kernel LSU-bound at 3x its HBM time).
     const int pix = G + blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= p_end) return;
     const int rel = pix - G;
@@ -34,17 +33,22 @@ __global__ void stem_kernel(const float* __restrict__ feats, const long long* __
         const float* fb = feats + (size_t)feat_off[b] * W;
         float x[9];
 #pragma unroll
-        for (int dt = 0; dt < 3; ++dt)
+        for (int df = 0; df < 3; ++df) {
+            const int ff = f + df - 1;
+            const bool f_ok = ff >= 0 && ff < W;
+            // CMVN (InstanceNorm1d) applied on the fly to the raw log-Mel features: (x - mean) * rstd per (utterance, bin)
+            const float2 ms = f_ok ? __ldg(cmvn + (size_t)b * W + ff) : make_float2(0.f, 0.f);
 #pragma unroll
-            for (int df = 0; df < 3; ++df) {
-                const int tt = t + dt - 1, ff = f + df - 1;
-                x[dt * 3 + df] = (tt >= 0 && tt < T && ff >= 0 && ff < W) ? __ldg(fb + (size_t)tt * W + ff) : 0.f;
+            for (int dt = 0; dt < 3; ++dt) {
+                const int tt = t + dt - 1;
+                x[dt * 3 + df] = (f_ok && tt >= 0 && tt < T) ? (__ldg(fb + (size_t)tt * W + ff) - ms.x) * ms.y : 0.f;
             }
+        }
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-            float a = sw[288 + c];
+            float a = sc.b[c];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a = fmaf(sw[c * 9 + k], x[k], a);
+            for (int k = 0; k < 9; ++k) a = fmaf(sc.w[c * 9 + k], x[k], a);
             acc[c] = fmaxf(a, 0.f);
         }
     }
@@ -59,16 +63,16 @@ __global__ void stem_kernel(const float* __restrict__ feats, const long long* __
     }
 }
 
-int launch_stem(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float* w,
-                const float* bias, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
+int launch_stem(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
+                const StemConsts& sc, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
                 const int* row_b, const int* row_h, cudaStream_t st) {
     const int n = p_end - G;
     const int threads = 128;
     const int blocks = (n + threads - 1) / threads;
     if (bf16)
-        stem_kernel<true><<<blocks, threads, 0, st>>>(feats, feat_off, n_frames, w, bias, out, out_plane, G, p_end, Wp, W, row_b, row_h);
+        stem_kernel<true><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, row_b, row_h);
     else
-        stem_kernel<false><<<blocks, threads, 0, st>>>(feats, feat_off, n_frames, w, bias, out, out_plane, G, p_end, Wp, W, row_b, row_h);
+        stem_kernel<false><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, row_b, row_h);
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
 }
@@ -82,71 +86,136 @@ int launch_stem(bool bf16, const float* feats, const long long* feat_off, const 
 // Knowing the scales up front lets conv2's epilogue apply scale + residual + ReLU directly: y2 is never stored and
 // the separate "scale, add, ReLU" pass disappears.
 //
-// plane_sum_kernel: Total[b][ci] over the valid pixels, in 2^-24 fixed point.  16-bit activations times 2^24 are
-// exact integers and integer addition is associative, so the sums -- and through them every embedding -- are
-// bit-identical whatever the packing, grid shape or atomic order.
+// plane_sum_kernel: Total[b][ci] over the valid pixels, in 2^-15 FIXED POINT (each 16-bit activation is rounded to a
+// multiple of 2^-15 -- a pure function of the pixel -- and integer addition is associative), so the sums, and through
+// them every embedding, are bit-identical whatever the packing, grid shape or atomic order.
+// One warp per 256-pixel span and chunk plane.  A per-span table (span_b: the utterance when every valid pixel of the
+// span belongs to one, -1 when the span holds only pad pixels, -2 when it straddles utterances) replaces the per-pixel
+// utterance lookups, so the common path is eight independent 16-byte loads per lane followed by the arithmetic (the
+// first version looked up pix_b before every load: one load in flight per thread, 50 % of the HBM roofline).  Pad
+// pixels hold zeros and are simply added.
+constexpr float kSeFixScale = 32768.f;          // 2^15: |x| <= 65504 still fits a signed 32-bit integer
+constexpr double kSeFixInv = 1.0 / 32768.0;
+constexpr int kSpanPix = 256;
+
 template <bool BF16>
-__global__ void __launch_bounds__(256) plane_sum_kernel(const uint16_t* __restrict__ act, long long plane, int G, int p_end,
-                                                        const int* __restrict__ pix_b, int C, unsigned long long* __restrict__ sums) {
-    constexpr int PX = 8;                                   // pixels per lane
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j = blockIdx.y;
-    const int base = G + (blockIdx.x * 8 + warp) * 32 * PX;
-    long long t[8];
+__device__ __forceinline__ void fix_add8(const uint4& a, long long (&t)[8]) {
+    const uint32_t u[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) t[e] = 0ll;
-    int b_acc = -1;
-    bool mixed = false;
-#pragma unroll
-    for (int k = 0; k < PX; ++k) {
-        const int pix = base + k * 32 + lane;
-        int b = -1;
-        if (pix < p_end) b = __ldg(pix_b + (pix - G));
-        if (b >= 0) {
-            if (b_acc >= 0 && b != b_acc) {               // utterance boundary inside this lane's pixels (rare): flush
-                for (int e = 0; e < 8; ++e) {
-                    atomicAdd(sums + (size_t)b_acc * C + j * 8 + e, (unsigned long long)t[e]);
-                    t[e] = 0ll;
-                }
-                mixed = true;
-            }
-            b_acc = b;
-            const uint4 a = *reinterpret_cast<const uint4*>(act + ((size_t)j * plane + pix) * 8);
-            const uint32_t u[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 v = unpack2<BF16>(u[e]);
-                t[2 * e] += __float2ll_rn(v.x * 16777216.f);
-                t[2 * e + 1] += __float2ll_rn(v.y * 16777216.f);
-            }
-        }
-    }
-    const unsigned has = __ballot_sync(0xffffffffu, b_acc >= 0);
-    if (has == 0u) return;
-    const int b0 = __shfl_sync(0xffffffffu, b_acc, __ffs(has) - 1);
-    if (__all_sync(0xffffffffu, (b_acc < 0 || b_acc == b0) && !mixed)) {
-        // exact warp sum of 64-bit values with the 32-bit hardware reduction: 20-bit low limb + signed high limb
-        long long mine = 0ll;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int slo = __reduce_add_sync(0xffffffffu, (int)(t[e] & 0xFFFFFll));
-            const int shi = __reduce_add_sync(0xffffffffu, (int)(t[e] >> 20));
-            if (lane == e) mine = ((long long)shi << 20) + (long long)slo;
-        }
-        if (lane < 8) atomicAdd(sums + (size_t)b0 * C + j * 8 + lane, (unsigned long long)mine);
-    } else if (b_acc >= 0) {
-        for (int e = 0; e < 8; ++e) atomicAdd(sums + (size_t)b_acc * C + j * 8 + e, (unsigned long long)t[e]);
+    for (int e = 0; e < 4; ++e) {
+        float2 v = unpack2<BF16>(u[e]);
+        if (BF16) { v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f); }
+        t[2 * e] += (long long)__float2int_rn(v.x * kSeFixScale);
+        t[2 * e + 1] += (long long)__float2int_rn(v.y * kSeFixScale);
     }
 }
 
-int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, int C,
+// exact warp sum of 64-bit values with the 32-bit hardware reduction (20-bit low limb + signed high limb); lane e < 8
+// returns the total of t[e]
+__device__ __forceinline__ long long warp_sum8_i64(const long long (&t)[8], int lane) {
+    long long mine = 0ll;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int slo = __reduce_add_sync(0xffffffffu, (int)(t[e] & 0xFFFFFll));
+        const int shi = __reduce_add_sync(0xffffffffu, (int)(t[e] >> 20));
+        if (lane == e) mine = ((long long)shi << 20) + (long long)slo;
+    }
+    return mine;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256, 4) plane_sum_kernel(const uint16_t* __restrict__ act, long long plane, int G, int p_end,
+                                                        const int* __restrict__ pix_b, const int* __restrict__ span_b, int C,
+                                                        int planes_per_block, unsigned long long* __restrict__ sums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int span = blockIdx.x * 8 + warp;
+    const int base = G + span * kSpanPix;
+    if (base >= p_end) return;
+    const int sb = __ldg(span_b + span);
+    if (sb == -1) return;                                  // pad pixels only: all zeros
+    const int j0 = blockIdx.y * planes_per_block;
+    int pb[8];                                             // per-pixel utterances, only needed when the span is mixed
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        pb[k] = -1;
+        if (sb == -2 && base + k * 32 + lane < p_end) pb[k] = __ldg(pix_b + (base + k * 32 + lane - G));
+    }
+    for (int j = j0; j < j0 + planes_per_block; ++j) {
+        const uint16_t* src = act + ((size_t)j * plane + base + lane) * 8;
+        uint4 a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (base + k * 32 + lane < p_end) a[k] = *reinterpret_cast<const uint4*>(src + (size_t)k * 32 * 8);
+        }
+        if (sb >= 0) {
+            long long t[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[e] = 0ll;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) fix_add8<BF16>(a[k], t);
+            const long long mine = warp_sum8_i64(t, lane);
+            if (lane < 8) atomicAdd(sums + (size_t)sb * C + j * 8 + lane, (unsigned long long)mine);
+        } else {
+            // the span straddles utterance boundaries (the rule on the deepest level, where an utterance is a few hundred
+            // pixels): one warp-uniform pass per distinct utterance, in increasing order
+            int cur = -1;
+            while (true) {
+                int mine_b = 0x7fffffff;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (pb[k] > cur) mine_b = min(mine_b, pb[k]);
+                const int nb = __reduce_min_sync(0xffffffffu, mine_b);
+                if (nb == 0x7fffffff) break;
+                long long t[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) t[e] = 0ll;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (pb[k] == nb) fix_add8<BF16>(a[k], t);
+                const long long mine = warp_sum8_i64(t, lane);
+                if (lane < 8) atomicAdd(sums + (size_t)nb * C + j * 8 + lane, (unsigned long long)mine);
+                cur = nb;
+            }
+        }
+    }
+}
+
+// span_b table for plane_sum_kernel (built once per batch composition)
+__global__ void span_table_kernel(const int* __restrict__ pix_b, int n, int n_spans, int* __restrict__ span_b) {
+    const int span = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (span >= n_spans) return;
+    int mn = 0x7fffffff, mx = -1;
+    for (int k = 0; k < kSpanPix / 32; ++k) {
+        const int rel = span * kSpanPix + k * 32 + lane;
+        const int b = rel < n ? pix_b[rel] : -1;
+        if (b >= 0) { mn = min(mn, b); mx = max(mx, b); }
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) span_b[span] = mx < 0 ? -1 : (mn == mx ? mn : -2);
+}
+
+int span_table_size(int n_pix) { return (n_pix + kSpanPix - 1) / kSpanPix; }
+
+int launch_span_table(const int* pix_b, int n_pix, int* span_b, cudaStream_t st) {
+    const int n_spans = span_table_size(n_pix);
+    span_table_kernel<<<(n_spans + 7) / 8, 256, 0, st>>>(pix_b, n_pix, n_spans, span_b);
+    SKB_CUDA_CHECK(cudaGetLastError());
+    return SKB_OK;
+}
+
+int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, const int* span_b, int C,
                      unsigned long long* sums, cudaStream_t st) {
     const int n = p_end - G;
-    dim3 grid((n + 2047) / 2048, C / 8);
+    const int n_spans = span_table_size(n);
+    const int chunks = C / 8;
+    const int ppb = chunks >= 16 ? 4 : (chunks >= 8 ? 2 : 1);      // keep >= ~4 waves of CTAs on the small levels
+    dim3 grid((n_spans + 7) / 8, chunks / ppb);
     if (bf16)
-        plane_sum_kernel<true><<<grid, 256, 0, st>>>(act, plane, G, p_end, pix_b, C, sums);
+        plane_sum_kernel<true><<<grid, 256, 0, st>>>(act, plane, G, p_end, pix_b, span_b, C, ppb, sums);
     else
-        plane_sum_kernel<false><<<grid, 256, 0, st>>>(act, plane, G, p_end, pix_b, C, sums);
+        plane_sum_kernel<false><<<grid, 256, 0, st>>>(act, plane, G, p_end, pix_b, span_b, C, ppb, sums);
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
 }
@@ -155,10 +224,10 @@ int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int
 // One CTA per (utterance, 8-channel chunk); threads stride over the border pixels with 16-byte loads; the block
 // reduction runs in a fixed order, so the result is deterministic.  brd layout: [B][8 kinds][C].
 template <bool BF16>
-__global__ void __launch_bounds__(128) se_border_kernel(const uint16_t* __restrict__ y1, long long plane, int G, int Wp, int W,
+__global__ void __launch_bounds__(256) se_border_kernel(const uint16_t* __restrict__ y1, long long plane, int G, int Wp, int W,
                                                         const int* __restrict__ utt_row0, const int* __restrict__ utt_count, int C,
                                                         float* __restrict__ brd) {
-    __shared__ float part[128][33];
+    __shared__ float part[8][32];
     const int b = blockIdx.x, j = blockIdx.y;
     const int H = utt_count[b] / W;
     const uint16_t* base = y1 + ((size_t)j * plane + G + (size_t)utt_row0[b] * Wp) * 8;     // pixel (0, 0) of chunk j
@@ -179,18 +248,24 @@ __global__ void __launch_bounds__(128) se_border_kernel(const uint16_t* __restri
         add8(base + (size_t)w * 8, 0);
         add8(base + ((size_t)(H - 1) * Wp + w) * 8, 8);
     }
+    // unrolled: the loads of four column pixels are in flight together (the rolled loop paid one L2 round trip each)
+#pragma unroll 4
     for (int hh = threadIdx.x; hh < H; hh += blockDim.x) {
         add8(base + (size_t)hh * Wp * 8, 16);
         add8(base + ((size_t)hh * Wp + W - 1) * 8, 24);
     }
+    // fixed-order reduction: butterfly inside each warp, then the eight warp totals in warp order
 #pragma unroll
-    for (int i = 0; i < 32; ++i) part[threadIdx.x][i] = acc[i];
+    for (int i = 0; i < 32; ++i) {
+        const float v = warp_sum(acc[i]);
+        if ((threadIdx.x & 31) == i) part[threadIdx.x >> 5][i] = v;
+    }
     __syncthreads();
-    if (threadIdx.x < 32) {                         // thread i sums quantity i over the 128 partials, in order
-        double a = 0.0;
-        for (int t = 0; t < 128; ++t) a += (double)part[t][threadIdx.x];
+    if (threadIdx.x < 32) {
+        float a = 0.f;
+        for (int t = 0; t < 8; ++t) a += part[t][threadIdx.x];
         const int kind = threadIdx.x >> 3, e = threadIdx.x & 7;
-        brd[((size_t)b * 8 + kind) * C + j * 8 + e] = (float)a;
+        brd[((size_t)b * 8 + kind) * C + j * 8 + e] = a;
     }
     if (threadIdx.x >= 32 && threadIdx.x < 64) {    // corners: (0,0) (0,W-1) (H-1,0) (H-1,W-1)
         const int k = (threadIdx.x - 32) >> 3, e = threadIdx.x & 7;
@@ -202,49 +277,78 @@ __global__ void __launch_bounds__(128) se_border_kernel(const uint16_t* __restri
 
 // se_mean_partial_kernel: the mean of conv2's output through the (16-bit-rounded, BN-folded) conv2 weights, as a small
 // GEMM  partial[ks][b][co] = sum_{i in K-slice ks} W2t[i][co] * S[b][i],  i = ci * 9 + tap,  S = the nine shifted sums.
-// Grid = (K / 64 slices, utterance groups of 16): enough CTAs to cover the L2 latency of the weight stream; every
-// weight row is read once per utterance group.  Fixed summation order everywhere -> deterministic.
-constexpr int kSeRows = 64, kSeUtt = 16;
+// Grid = (Cin / 8 slices of 8 channels x 9 taps, utterance groups of 16); every weight row is read once per utterance
+// group.  Fixed summation order everywhere -> deterministic.
+constexpr int kSeCh = 8, kSeRows = 9 * kSeCh, kSeUtt = 16;
+template <int Cout>
 __global__ void __launch_bounds__(256) se_mean_partial_kernel(const unsigned long long* __restrict__ sums, const float* __restrict__ brd,
-                                                              int B, int Cin, int Cout, const float* __restrict__ w2t,
+                                                              int B, int Cin, const float* __restrict__ w2t,
                                                               float* __restrict__ partial) {
     __shared__ float sS[kSeUtt][kSeRows];
-    const int K = 9 * Cin;
+    constexpr int n_rg = 256 / Cout;               // row groups: 8 / 4 / 2 / 1 for Cout = 32 / 64 / 128 / 256
+    constexpr int RPT = kSeRows / n_rg;            // weight rows per thread: 9 / 18 / 36 / 72
+    // this thread's weights first: RPT independent loads whose latency overlaps the shifted-sum phase below
+    const int co = threadIdx.x % Cout, rg = threadIdx.x / Cout;
+    float wreg[RPT];
+    {
+        const float* wp = w2t + ((size_t)blockIdx.x * kSeRows + rg) * Cout + co;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) wreg[i] = __ldg(wp + (size_t)i * n_rg * Cout);
+    }
     const int k0 = blockIdx.x * kSeRows, b0 = blockIdx.y * kSeUtt;
-    const int nr = min(kSeRows, K - k0), nu = min(kSeUtt, B - b0);
-    for (int idx = threadIdx.x; idx < kSeUtt * kSeRows; idx += blockDim.x) {
-        const int u = idx / kSeRows, r = idx - u * kSeRows;
-        float v = 0.f;
-        if (u < nu && r < nr) {
-            const int i = k0 + r, c = i / 9, tap = i - c * 9;
-            const int dr = tap / 3 - 1, ds = tap % 3 - 1;
-            const int b = b0 + u;
+    const int nu = min(kSeUtt, B - b0);
+    // the nine shifted sums of one (utterance, input channel): nine independent loads, then arithmetic only
+    for (int idx = threadIdx.x; idx < kSeUtt * kSeCh; idx += blockDim.x) {
+        const int u = idx / kSeCh, cl = idx - u * kSeCh;
+        float v[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) v[tap] = 0.f;
+        if (u < nu) {
+            const int b = b0 + u, c = blockIdx.x * kSeCh + cl;
             const float* bb = brd + (size_t)b * 8 * Cin + c;
-            v = (float)((double)(long long)sums[(size_t)b * Cin + c] * (1.0 / 16777216.0));
-            if (dr < 0) v -= bb[Cin];                 // shifted up: the last row is never read
-            if (dr > 0) v -= bb[0];
-            if (ds < 0) v -= bb[3 * Cin];
-            if (ds > 0) v -= bb[2 * Cin];
-            if (dr < 0 && ds < 0) v += bb[7 * Cin];
-            if (dr < 0 && ds > 0) v += bb[6 * Cin];
-            if (dr > 0 && ds < 0) v += bb[5 * Cin];
-            if (dr > 0 && ds > 0) v += bb[4 * Cin];
+            const float tot = (float)((double)(long long)sums[(size_t)b * Cin + c] * kSeFixInv);
+            const float row0 = bb[0], rowL = bb[Cin], col0 = bb[2 * Cin], colL = bb[3 * Cin];
+            const float k00 = bb[4 * Cin], k0L = bb[5 * Cin], kL0 = bb[6 * Cin], kLL = bb[7 * Cin];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int dr = tap / 3 - 1, ds = tap % 3 - 1;
+                float x = tot;
+                if (dr < 0) x -= rowL;                 // shifted up: the last row is never read
+                if (dr > 0) x -= row0;
+                if (ds < 0) x -= colL;
+                if (ds > 0) x -= col0;
+                if (dr < 0 && ds < 0) x += kLL;
+                if (dr < 0 && ds > 0) x += kL0;
+                if (dr > 0 && ds < 0) x += k0L;
+                if (dr > 0 && ds > 0) x += k00;
+                v[tap] = x;
+            }
         }
-        sS[u][r] = v;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) sS[u][cl * 9 + tap] = v[tap];
     }
     __syncthreads();
-    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-        float acc[kSeUtt];
+    // thread = (output channel co, row group rg): the 256 threads split the slice's rows so that even the 32-channel
+    // layers keep 8 warps busy (one warp walking 64 dependent L2 loads was 45 us per launch); the row groups are then
+    // added in a fixed order.
+    __shared__ float sRed[256 * kSeUtt];
+    float acc[kSeUtt];
 #pragma unroll
-        for (int u = 0; u < kSeUtt; ++u) acc[u] = 0.f;
-        const float* wp = w2t + (size_t)k0 * Cout + co;
-#pragma unroll 8
-        for (int r = 0; r < nr; ++r) {
-            const float w = __ldg(wp + (size_t)r * Cout);
+    for (int u = 0; u < kSeUtt; ++u) acc[u] = 0.f;
 #pragma unroll
-            for (int u = 0; u < kSeUtt; ++u) acc[u] = fmaf(w, sS[u][r], acc[u]);
-        }
-        for (int u = 0; u < nu; ++u) partial[((size_t)blockIdx.x * B + b0 + u) * Cout + co] = acc[u];
+    for (int i = 0; i < RPT; ++i) {
+        const int r = rg + i * n_rg;
+#pragma unroll
+        for (int u = 0; u < kSeUtt; ++u) acc[u] = fmaf(wreg[i], sS[u][r], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kSeUtt; ++u) sRed[(rg * kSeUtt + u) * Cout + co] = acc[u];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nu * Cout; idx += blockDim.x) {
+        const int u = idx / Cout, c = idx - u * Cout;
+        float a = 0.f;
+        for (int g = 0; g < n_rg; ++g) a += sRed[(g * kSeUtt + u) * Cout + c];
+        partial[((size_t)blockIdx.x * B + b0 + u) * Cout + c] = a;
     }
 }
 
@@ -285,15 +389,26 @@ int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, lon
                     const int* utt_row0, const int* utt_count, int B, int Cin, int Cout, const float* w2t, const float* b2,
                     const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st) {
     // brd_ws: [B][8][Cin] border sums, followed by [n_slices][B][Cout] partial means
+    if (Cout > 256 || 256 % Cout != 0) {
+        set_last_error(__FILE__, __LINE__, "squeeze-excitation: channel count must divide 256");
+        return SKB_ERR_ARG;
+    }
     dim3 grid(B, Cin / 8);
     if (bf16)
-        se_border_kernel<true><<<grid, 128, 0, st>>>(y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws);
+        se_border_kernel<true><<<grid, 256, 0, st>>>(y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws);
     else
-        se_border_kernel<false><<<grid, 128, 0, st>>>(y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws);
-    const int n_slices = (9 * Cin + kSeRows - 1) / kSeRows;
+        se_border_kernel<false><<<grid, 256, 0, st>>>(y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws);
+    const int n_slices = Cin / kSeCh;
     float* partial = brd_ws + (size_t)B * 8 * Cin;
     dim3 g2(n_slices, (B + kSeUtt - 1) / kSeUtt);
-    se_mean_partial_kernel<<<g2, Cout < 256 ? (Cout < 32 ? 32 : Cout) : 256, 0, st>>>(sums, brd_ws, B, Cin, Cout, w2t, partial);
+    if (Cout == 32) se_mean_partial_kernel<32><<<g2, 256, 0, st>>>(sums, brd_ws, B, Cin, w2t, partial);
+    else if (Cout == 64) se_mean_partial_kernel<64><<<g2, 256, 0, st>>>(sums, brd_ws, B, Cin, w2t, partial);
+    else if (Cout == 128) se_mean_partial_kernel<128><<<g2, 256, 0, st>>>(sums, brd_ws, B, Cin, w2t, partial);
+    else if (Cout == 256) se_mean_partial_kernel<256><<<g2, 256, 0, st>>>(sums, brd_ws, B, Cin, w2t, partial);
+    else {
+        set_last_error(__FILE__, __LINE__, "squeeze-excitation: unsupported channel count");
+        return SKB_ERR_ARG;
+    }
     se_fc_kernel<<<B, 256, 0, st>>>(sums, partial, n_slices, utt_count, B, Cin, Cout, b2, fc1, fc2, scale);
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;

@@ -17,11 +17,14 @@ struct FrontendConsts {
     float* dct = nullptr;
 };
 
-int launch_stem(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float* w,
-                const float* bias, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
+struct StemConsts { float w[32 * 9]; float b[32]; };   // folded stem conv + BN, passed to the kernel by value
+int launch_stem(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
+                const StemConsts& sc, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
                 const int* row_b, const int* row_h, cudaStream_t st);
-int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, int C,
+int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, const int* span_b, int C,
                      unsigned long long* sums, cudaStream_t st);
+int span_table_size(int n_pix);
+int launch_span_table(const int* pix_b, int n_pix, int* span_b, cudaStream_t st);
 int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, long long plane, int G, int Wp, int W,
                     const int* utt_row0, const int* utt_count, int B, int Cin, int Cout, const float* w2t, const float* b2,
                     const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st);
@@ -62,8 +65,13 @@ int conv_pick_ncta(int cout);        // 32 / 64 / 128
 int frontend_consts_create(FrontendConsts* fc, int n_fft, int win, int hop, int n_mels, int n_out, const float* window,
                            const float* fb, const float* dct);
 void frontend_consts_destroy(FrontendConsts* fc);
+// Writes raw features (frame-major) and the per-(utterance, coefficient) CMVN statistics (mean, rstd) into `cmvn`
+// ([B][n_out] float2; `cmvn_part` is scratch of frontend_cmvn_scratch_bytes()).  With `normalise` the features are
+// also normalised in place (and optionally written as the (B, n_out, t_max) tensor the reference's front-end returns);
+// without it the consumer (the stem kernel) applies the statistics on the fly.
 int frontend_launch(const FrontendConsts& fc, const float* wave, const long long* wave_off, const int* wave_len,
-                    const long long* feat_off, const int* n_frames, int B, int t_max, float* feats, float* api_out,
-                    cudaStream_t stream);
+                    const long long* feat_off, const int* n_frames, int B, int t_max, float* feats, float2* cmvn,
+                    void* cmvn_part, bool normalise, float* api_out, cudaStream_t stream);
+size_t frontend_cmvn_scratch_bytes(const FrontendConsts& fc, int B, int t_max);
 
 }  // namespace skb

@@ -271,16 +271,31 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
         const float mscale = p.mul_scaled ? inv_scale : 1.f;
         int panel = panel0, nt = nt0;
         uint32_t nt_done = 0;
+        // Row terms change only with the panel; column terms are fetched BEFORE waiting for the accumulator, so their
+        // L2 latency hides behind the MMAs instead of stalling every 32x32 block (was 52 % of all stall samples).
+        int cur_panel = -1;
+        float ra = 0.f, rr = 0.f;
+        const int c4 = (lane & 7) * 4;
         for (int t = t_begin; t < t_end; ++t, ++nt_done) {
             const int buf = (int)(nt_done & 1);
             const int row0 = panel * 128 + q * 32;
             const int my_row = row0 + lane;
-            const float ra = (p.ra && my_row < p.Ne) ? p.ra[my_row] * mscale : 0.f;
-            const float rr = fmaf((p.r && my_row < p.Ne) ? p.r[my_row] : 0.f, p.rq_scale, p.c0);
+            if (panel != cur_panel) {
+                cur_panel = panel;
+                ra = (p.ra && my_row < p.Ne) ? p.ra[my_row] * mscale : 0.f;
+                rr = fmaf((p.r && my_row < p.Ne) ? p.r[my_row] : 0.f, p.rq_scale, p.c0);
+            }
             const int n_rows = min(32, p.Ne - row0);
+            float4 qpre[2];
+#pragma unroll
+            for (int cbi = 0; cbi < 2; ++cbi) {
+                const int col = nt * 128 + (half * 2 + cbi) * 32 + c4;
+                qpre[cbi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.q && vec_ok && col + 4 <= p.Nt) qpre[cbi] = __ldg(reinterpret_cast<const float4*>(p.q + col));
+            }
             mbar_wait(&acc_full[buf], (nt_done >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int cbi = 0; cbi < 2; ++cbi) {
                 const int cb = half * 2 + cbi;
                 const int col0 = nt * 128 + cb * 32;
@@ -304,9 +319,8 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                         srow[k] = make_float4(fmaf(v[4 * k], mul, rr), fmaf(v[4 * k + 1], mul, rr), fmaf(v[4 * k + 2], mul, rr),
                                               fmaf(v[4 * k + 3], mul, rr));
                     __syncwarp();
-                    const int rs = lane >> 3, c4 = (lane & 7) * 4;
-                    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.q) qv = __ldg(reinterpret_cast<const float4*>(p.q + col0 + c4));
+                    const int rs = lane >> 3;
+                    float4 qv = qpre[cbi];
                     qv.x *= p.rq_scale; qv.y *= p.rq_scale; qv.z *= p.rq_scale; qv.w *= p.rq_scale;
                     if (p.out_f64) {
                         double* o = reinterpret_cast<double*>(p.out) + (size_t)(row0 + rs) * p.ld_out + col0 + c4;
@@ -314,8 +328,8 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
 #pragma unroll
                         for (int it = 0; it < 8; ++it, o += step) {
                             const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
-                            reinterpret_cast<double2*>(o)[0] = make_double2((double)(x.x + qv.x), (double)(x.y + qv.y));
-                            reinterpret_cast<double2*>(o)[1] = make_double2((double)(x.z + qv.z), (double)(x.w + qv.w));
+                            __stcs(reinterpret_cast<double2*>(o), make_double2((double)(x.x + qv.x), (double)(x.y + qv.y)));
+                            __stcs(reinterpret_cast<double2*>(o) + 1, make_double2((double)(x.z + qv.z), (double)(x.w + qv.w)));
                         }
                     } else {
                         float* o = reinterpret_cast<float*>(p.out) + (size_t)(row0 + rs) * p.ld_out + col0 + c4;
@@ -323,7 +337,9 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
 #pragma unroll
                         for (int it = 0; it < 8; ++it, o += step) {
                             const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
-                            *reinterpret_cast<float4*>(o) = make_float4(x.x + qv.x, x.y + qv.y, x.z + qv.z, x.w + qv.w);
+                            // streaming store: the score matrix is written once and never re-read by this kernel, so it
+                            // should not evict the T operand tiles from L2
+                            __stcs(reinterpret_cast<float4*>(o), make_float4(x.x + qv.x, x.y + qv.y, x.z + qv.z, x.w + qv.w));
                         }
                     }
                     continue;

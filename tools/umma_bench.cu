@@ -56,7 +56,44 @@ __global__ void __launch_bounds__(128) bench(int N, int mode, int iters, int a_s
     if (warp == 0) tmem_dealloc<512>(tm);
 }
 
+// TMEM -> register bandwidth: `nw` warps (warp w reads lane quadrant w % 4) each issue `iters` tcgen05.ld 32x32b.x32
+// (32 lanes x 32 columns x 4 B = 4 KB per instruction) back to back.
+__global__ void __launch_bounds__(256) ldtm_bench(int iters, long long* out) {
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc<512>(&slot);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = slot;
+    float acc = 0.f;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+        float v[32];
+        tmem_ld32(tm + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((i * 32) & 511), v);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc += v[k];
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x % 32 == 0) out[blockIdx.x * 8 + warp] = (t1 - t0) + (acc == 12345.f ? 1 : 0);
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tm);
+}
+
 int main() {
+    {
+        long long* dl; cudaMalloc(&dl, 148 * 8 * 8);
+        for (int nw : {1, 4, 8}) {
+            const int iters = 4000;
+            ldtm_bench<<<148, nw * 32>>>(iters, dl);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("ldtm nw=%d: %s\n", nw, cudaGetErrorString(e)); return 1; }
+            long long h[148 * 8]; cudaMemcpy(h, dl, sizeof(h), cudaMemcpyDeviceToHost);
+            double mx = 0; for (int i = 0; i < 148; ++i) for (int w = 0; w < nw; ++w) mx = h[i * 8 + w] > mx ? h[i * 8 + w] : mx;
+            printf("tcgen05.ld 32x32b.x32 + wait, %d warps/SM: %.1f cycles per instruction per warp -> %.1f B/cycle/SM\n", nw,
+                   mx / iters, nw * 4096.0 * iters / mx);
+        }
+    }
     long long* d; cudaMalloc(&d, 148 * 8);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const char* names[4] = {"noswz", "sw32", "sw64", "sw128"};

@@ -23,6 +23,15 @@ constexpr int kNumSMs = 148;
 
 void set_last_error(const char* file, int line, const char* msg);
 
+// Launch check.  With SKB_SYNC_CHECK=1 in the environment every launch is followed by a stream synchronisation, so an
+// execution fault is reported at the kernel that caused it (compute-sanitizer is not always available).
+bool sync_check_enabled();
+#define SKB_LAUNCH_CHECK(stream)                                                              \
+    do {                                                                                      \
+        SKB_CUDA_CHECK(cudaGetLastError());                                                   \
+        if (skb::sync_check_enabled()) SKB_CUDA_CHECK(cudaStreamSynchronize(stream));         \
+    } while (0)
+
 // ----------------------------------------------------------------------------- shared-memory address
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -58,7 +58,7 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     const int n_items = p.n_tiles * (p.cout / N_CTA);
     const int grid = n_items < kNumSMs ? n_items : kNumSMs;      // persistent: one CTA per SM
     conv_umma_kernel<N_CTA, MT, BF16><<<grid, kConvThreads, smem, st>>>(p);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 

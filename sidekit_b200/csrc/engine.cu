@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -21,6 +22,10 @@ void set_last_error(const char* file, int line, const char* msg) {
     snprintf(g_err, sizeof(g_err), "%s:%d: %s", file, line, msg);
 }
 std::atomic<long long> g_launches{0};
+bool sync_check_enabled() {
+    static const bool on = [] { const char* e = getenv("SKB_SYNC_CHECK"); return e && e[0] == '1'; }();
+    return on;
+}
 
 // Optional per-category device timing (CUDA events on the launching stream) used by bench.py for the
 // roofline of the dominant kernel.  Off by default: events between launches cost a little.
@@ -503,6 +508,11 @@ struct skb_xtractor {
     Model m;
     Plan plan;
     bool plan_valid = false;
+    // Recently used plans (geometry tables live on the device): a bulk extraction cycles through a handful of length
+    // buckets, and rebuilding a plan costs a host pass over every frame plus a synchronous table upload.
+    struct CachedPlan { Plan plan; DevBuf tab32, tab64, pixmeta; unsigned long long stamp = 0; };
+    std::vector<CachedPlan> cache;
+    unsigned long long stamp = 0;
     DevBuf pixmeta, brd, cmvn, cmvn_part;
     DevBuf tab32, tab64, feats, sums, scale, poolX, poolH, poolL, gc, hb, pooled, lin, emb_pre, emb, logits, wave, dbg;
     std::vector<DevBuf> act;      // activation buffers
@@ -516,10 +526,40 @@ namespace skb {
 static int build_pixmeta(skb_xtractor* h, cudaStream_t st);
 static int num_frames(const Model& m, int64_t n) { return 1 + (int)(n / m.fe.hop); }
 
+constexpr size_t kPlanCacheEntries = 8;
+static int activate_plan(skb_xtractor* h, cudaStream_t st);
+
 static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream_t st) {
     Plan& pl = h->plan;
     if (h->plan_valid && pl.B == B && std::equal(lengths, lengths + B, pl.lengths.begin())) return SKB_OK;
-    h->plan_valid = false;
+    // park the current plan in the cache, then look the requested one up
+    if (h->plan_valid) {
+        if (h->cache.size() >= kPlanCacheEntries) {
+            size_t oldest = 0;
+            for (size_t i = 1; i < h->cache.size(); ++i)
+                if (h->cache[i].stamp < h->cache[oldest].stamp) oldest = i;
+            h->cache[oldest].tab32.release(); h->cache[oldest].tab64.release(); h->cache[oldest].pixmeta.release();
+            h->cache.erase(h->cache.begin() + oldest);
+        }
+        h->cache.emplace_back();
+        skb_xtractor::CachedPlan& c = h->cache.back();
+        std::swap(c.plan, h->plan);
+        std::swap(c.tab32, h->tab32); std::swap(c.tab64, h->tab64); std::swap(c.pixmeta, h->pixmeta);
+        c.stamp = ++h->stamp;
+        h->plan_valid = false;
+    }
+    for (size_t i = 0; i < h->cache.size(); ++i) {
+        skb_xtractor::CachedPlan& c = h->cache[i];
+        if (c.plan.B == B && std::equal(lengths, lengths + B, c.plan.lengths.begin())) {
+            std::swap(c.plan, h->plan);
+            std::swap(c.tab32, h->tab32); std::swap(c.tab64, h->tab64); std::swap(c.pixmeta, h->pixmeta);
+            h->cache.erase(h->cache.begin() + i);
+            h->d32 = (const int*)h->tab32.p;
+            h->d64 = (const long long*)h->tab64.p;
+            return activate_plan(h, st);
+        }
+    }
+    h->tab32.release(); h->tab64.release(); h->pixmeta.release();     // (moved into the cache, or left by a failed build)
     pl = Plan();
     pl.B = B;
     pl.lengths.assign(lengths, lengths + B);
@@ -612,7 +652,38 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     h->d32 = (const int*)h->tab32.p;
     h->d64 = (const long long*)h->tab64.p;
 
-    // activation buffers: zero them so pad pixels / guards are zero for this geometry
+    int rc2 = build_pixmeta(h, st);
+    if (rc2) return rc2;
+    return activate_plan(h, st);
+}
+
+// Zero what the producing convolution never writes in a phase-split buffer (the geometry of level `Lo`, four phase
+// images of cpp = C_prev/8 chunk planes each): the pad pixels, and -- when the source utterance has an odd number of
+// lines -- the last line of the two odd-row phases, which has no source line and acts as the bottom zero padding.
+__global__ void zero_ps_kernel(uint16_t* __restrict__ buf, long long plane, int cpp, int G, int n, int Wp, int W,
+                               const int* __restrict__ row_b, const int* __restrict__ row_h,
+                               const int* __restrict__ src_utt_count, int src_W) {
+    const int rel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rel >= n) return;
+    const int row = rel / Wp, w = rel - row * Wp;
+    const int b = row_b[row], hh = row_h[row];
+    int first_phase;
+    if (b < 0 || hh < 0 || w >= W) first_phase = 0;                                  // pad pixel: all four phases
+    else if (2 * hh + 1 >= src_utt_count[b] / src_W) first_phase = 2;                // no odd source line below
+    else return;
+    for (int j = first_phase * cpp; j < 4 * cpp; ++j)
+        *reinterpret_cast<uint4*>(buf + ((size_t)j * plane + G + rel) * 8) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// Make `h->plan` current: size the shared work buffers for it and re-establish the few invariants that depend on the
+// geometry.  Activation buffers are NOT cleared as a whole (5 GB of memset per plan change): every kernel writes all
+// pixels of [G, p_end) of its output (zeros at the pads), and what lies after p_end only feeds accumulator rows that
+// are discarded.
+static int activate_plan(skb_xtractor* h, cudaStream_t st) {
+    Plan& pl = h->plan;
+    const Model& m = h->m;
+    const int B = pl.B;
+    int rc;
     std::vector<size_t> need;
     if (m.archi == SKB_ARCHI_HALFRESNET34) {
         for (int l = 0; l < 4; ++l) {
@@ -626,9 +697,27 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     }
     h->act.resize(need.size());
     h->act_bytes = need;
-    for (size_t i = 0; i < need.size(); ++i) {
+    for (size_t i = 0; i < need.size(); ++i)
         if ((rc = h->act[i].ensure(need[i]))) return rc;
-        SKB_CUDA_CHECK(cudaMemsetAsync(h->act[i].p, 0, need[i], st));
+    if (m.archi == SKB_ARCHI_HALFRESNET34) {
+        // The one guard pixel that IS read into a kept accumulator row: tap (-1, -1) of the first pixel of the first
+        // line reaches pixel G - 1.  Nothing ever writes below G, but the plane stride moves with the geometry, so the
+        // guard of every chunk plane is cleared whenever the plan changes.
+        for (int l = 0; l < 4; ++l)
+            for (int k = 0; k < 5; ++k) {
+                if (k == 3 && l == 0) continue;
+                const Level& L = pl.lv[l];
+                const int n_planes = k == 3 ? 4 * (pl.lv[l - 1].C / 8) : L.C / 8;
+                SKB_CUDA_CHECK(cudaMemset2DAsync(h->act[l * 5 + k].p, (size_t)L.plane * 16, 0, (size_t)L.G * 16, n_planes, st));
+            }
+        for (int l = 1; l < 4; ++l) {
+            const Level& Lo = pl.lv[l];
+            const int n = Lo.p_end - Lo.G;
+            const Level& Ls = pl.lv[l - 1];
+            zero_ps_kernel<<<(n + 255) / 256, 256, 0, st>>>((uint16_t*)h->act[l * 5 + 3].p, Lo.plane, Ls.C / 8, Lo.G, n, Lo.Wp, Lo.W,
+                                                            h->d32 + Lo.o_row_b, h->d32 + Lo.o_row_h, h->d32 + Ls.o_utt_count, Ls.W);
+        }
+        SKB_CUDA_CHECK(cudaGetLastError());
     }
     const int Cmax = m.archi == SKB_ARCHI_HALFRESNET34 ? 256 : 0;
     if (Cmax) {
@@ -651,7 +740,6 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     if ((rc = h->pooled.ensure((size_t)B * 2 * D * sizeof(float)))) return rc;
     if ((rc = h->lin.ensure((size_t)B * m.emb * sizeof(float)))) return rc;
     if ((rc = h->emb_pre.ensure((size_t)B * m.emb * sizeof(float)))) return rc;
-    if ((rc = build_pixmeta(h, st))) return rc;
     h->plan_valid = true;
     return SKB_OK;
 }
@@ -1053,6 +1141,7 @@ void skb_xtractor_destroy(skb_xtractor_t* h) {
                       &h->cmvn_part};
     for (auto* b : bufs) b->release();
     for (auto& b : h->act) b.release();
+    for (auto& c : h->cache) { c.tab32.release(); c.tab64.release(); c.pixmeta.release(); }
     delete h;
 }
 

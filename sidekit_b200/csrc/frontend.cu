@@ -354,7 +354,7 @@ int frontend_launch(const FrontendConsts& fc, const float* wave, const long long
         set_last_error(__FILE__, __LINE__, "unsupported n_fft (1024 or 2048)");
         return SKB_ERR_ARG;
     }
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(stream);
     const int max_chunks = (t_max + kCmvnChunk - 1) / kCmvnChunk;
     cmvn_partial_kernel<<<dim3(max_chunks, B), 128, 0, stream>>>(feats, feat_off, n_frames, fc.n_out, max_chunks, (double2*)cmvn_part);
     cmvn_final_kernel<<<B, 128, 0, stream>>>((const double2*)cmvn_part, n_frames, fc.n_out, max_chunks, cmvn);
@@ -363,7 +363,7 @@ int frontend_launch(const FrontendConsts& fc, const float* wave, const long long
         cmvn_apply_kernel<<<dim3((unsigned)((per_utt + 255) / 256), B), 256, 0, stream>>>(feats, feat_off, n_frames, fc.n_out, cmvn,
                                                                                         api_out, t_max);
     }
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(stream);
     return SKB_OK;
 }
 

@@ -73,7 +73,7 @@ int launch_stem(bool bf16, const float* feats, const long long* feat_off, const 
         stem_kernel<true><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, row_b, row_h);
     else
         stem_kernel<false><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, row_b, row_h);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 
@@ -201,7 +201,7 @@ int span_table_size(int n_pix) { return (n_pix + kSpanPix - 1) / kSpanPix; }
 int launch_span_table(const int* pix_b, int n_pix, int* span_b, cudaStream_t st) {
     const int n_spans = span_table_size(n_pix);
     span_table_kernel<<<(n_spans + 7) / 8, 256, 0, st>>>(pix_b, n_pix, n_spans, span_b);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 
@@ -216,7 +216,7 @@ int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int
         plane_sum_kernel<true><<<grid, 256, 0, st>>>(act, plane, G, p_end, pix_b, span_b, C, ppb, sums);
     else
         plane_sum_kernel<false><<<grid, 256, 0, st>>>(act, plane, G, p_end, pix_b, span_b, C, ppb, sums);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 
@@ -227,7 +227,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(256) se_border_kernel(const uint16_t* __restrict__ y1, long long plane, int G, int Wp, int W,
                                                         const int* __restrict__ utt_row0, const int* __restrict__ utt_count, int C,
                                                         float* __restrict__ brd) {
-    __shared__ float part[8][32];
+    __shared__ float part[256][33];
+    __shared__ float part2[8][32];
     const int b = blockIdx.x, j = blockIdx.y;
     const int H = utt_count[b] / W;
     const uint16_t* base = y1 + ((size_t)j * plane + G + (size_t)utt_row0[b] * Wp) * 8;     // pixel (0, 0) of chunk j
@@ -249,21 +250,31 @@ __global__ void __launch_bounds__(256) se_border_kernel(const uint16_t* __restri
         add8(base + ((size_t)(H - 1) * Wp + w) * 8, 8);
     }
     // unrolled: the loads of four column pixels are in flight together (the rolled loop paid one L2 round trip each)
-#pragma unroll 4
-    for (int hh = threadIdx.x; hh < H; hh += blockDim.x) {
-        add8(base + (size_t)hh * Wp * 8, 16);
-        add8(base + ((size_t)hh * Wp + W - 1) * 8, 24);
-    }
-    // fixed-order reduction: butterfly inside each warp, then the eight warp totals in warp order
+    for (int hh0 = threadIdx.x; hh0 < H; hh0 += 4 * blockDim.x) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const float v = warp_sum(acc[i]);
-        if ((threadIdx.x & 31) == i) part[threadIdx.x >> 5][i] = v;
+        for (int u = 0; u < 4; ++u) {
+            const int hh = hh0 + u * blockDim.x;
+            if (hh < H) {
+                add8(base + (size_t)hh * Wp * 8, 16);
+                add8(base + ((size_t)hh * Wp + W - 1) * 8, 24);
+            }
+        }
+    }
+    // fixed-order two-level reduction through shared memory: thread (g, i) adds quantity i over partials 32g .. 32g+31,
+    // then thread i adds the eight group totals
+#pragma unroll
+    for (int i = 0; i < 32; ++i) part[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    {
+        const int i = threadIdx.x & 31, g = threadIdx.x >> 5;
+        float a = 0.f;
+        for (int t = 0; t < 32; ++t) a += part[g * 32 + t][i];
+        part2[g][i] = a;
     }
     __syncthreads();
     if (threadIdx.x < 32) {
         float a = 0.f;
-        for (int t = 0; t < 8; ++t) a += part[t][threadIdx.x];
+        for (int t = 0; t < 8; ++t) a += part2[t][threadIdx.x];
         const int kind = threadIdx.x >> 3, e = threadIdx.x & 7;
         brd[((size_t)b * 8 + kind) * C + j * 8 + e] = a;
     }
@@ -398,6 +409,7 @@ int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, lon
         se_border_kernel<true><<<grid, 256, 0, st>>>(y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws);
     else
         se_border_kernel<false><<<grid, 256, 0, st>>>(y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws);
+    SKB_LAUNCH_CHECK(st);
     const int n_slices = Cin / kSeCh;
     float* partial = brd_ws + (size_t)B * 8 * Cin;
     dim3 g2(n_slices, (B + kSeUtt - 1) / kSeUtt);
@@ -409,8 +421,9 @@ int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, lon
         set_last_error(__FILE__, __LINE__, "squeeze-excitation: unsupported channel count");
         return SKB_ERR_ARG;
     }
+    SKB_LAUNCH_CHECK(st);
     se_fc_kernel<<<B, 256, 0, st>>>(sums, partial, n_slices, utt_count, B, Cin, Cout, b2, fc1, fc2, scale);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 
@@ -449,7 +462,7 @@ int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C,
         gather_frames_kernel<true><<<blocks, threads, 0, st>>>(act, plane, C, W, Wp, G, frame_row, n_frames, X);
     else
         gather_frames_kernel<false><<<blocks, threads, 0, st>>>(act, plane, C, W, Wp, G, frame_row, n_frames, X);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 
@@ -486,7 +499,7 @@ int launch_meanstd(const float* X, const long long* frame_off, const int* n_fr, 
                    const float* aff_t, float* out, cudaStream_t st) {
     dim3 grid((D + 127) / 128, B);
     meanstd_kernel<<<grid, 128, 0, st>>>(X, frame_off, n_fr, D, aff_s, aff_t, out);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 
@@ -507,7 +520,7 @@ int launch_att_act(float* h, const float* hb, const int* frame_utt, const float*
     const long long total = (long long)n_frames * A;
     if (total == 0) return SKB_OK;
     att_act_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(h, hb, frame_utt, bn_s, bn_t, n_frames, A);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 
@@ -541,7 +554,7 @@ int launch_softmax_pool(const float* X, const float* logit, const long long* fra
                         float* out, cudaStream_t st) {
     dim3 grid((D + 127) / 128, B);
     softmax_pool_kernel<<<grid, 128, 0, st>>>(X, logit, frame_off, n_fr, D, out);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 
@@ -585,7 +598,7 @@ __global__ void head_norm_kernel(const float* __restrict__ x, const float* __res
 int launch_head_norm(const float* x, const float* aff_s, const float* aff_t, int B, int E, int norm_embedding,
                      float* emb_pre, float* emb, cudaStream_t st) {
     head_norm_kernel<<<B, 256, E * sizeof(float), st>>>(x, aff_s, aff_t, E, norm_embedding, emb_pre, emb);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 
@@ -649,7 +662,7 @@ int launch_sgemm_nt(const float* A, const float* B, float* C, const float* bias,
     if (M == 0 || N == 0) return SKB_OK;
     dim3 grid((N + 63) / 64, (M + 63) / 64);
     sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc, alpha);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 
@@ -683,7 +696,7 @@ int launch_pack_frames(bool bf16, const float* X, int C_src, int C_dst, int n_ro
         pack_frames_kernel<true><<<blocks, 256, 0, st>>>(X, C_src, C_dst, n_rows, row_src, out, plane, G);
     else
         pack_frames_kernel<false><<<blocks, 256, 0, st>>>(X, C_src, C_dst, n_rows, row_src, out, plane, G);
-    SKB_CUDA_CHECK(cudaGetLastError());
+    SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
 

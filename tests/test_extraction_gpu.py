@@ -113,6 +113,15 @@ def test_packing_invariance_is_bit_exact(hr34):
     assert torch.equal(packed, m.extract_varlen(waves))           # run-to-run determinism
 
 
+def test_plan_cache_switches_and_evictions_leave_no_stale_state(hr34):
+    """Geometries alternate (the engine keeps 8 plans and never clears its activation buffers): results stay bit-identical."""
+    m, _ = hr34
+    sets = [[synth.synth_wave(1, 8000 + 1777 * i + 531 * j, seed=900 + 10 * i + j)[0].cuda() for j in range(1 + i % 3)] for i in range(11)]
+    first = [m.extract_varlen(ws) for ws in sets]                 # 11 distinct plans: the oldest ones are evicted
+    for i in (0, 10, 3, 0, 7):                                    # cache hits, rebuilt plans, big-after-small and back
+        assert torch.equal(m.extract_varlen(sets[i]), first[i])
+
+
 def test_host_buffer_entry_point(hr34):
     m, _ = hr34
     x = synth.synth_wave(3, 16000, seed=7)

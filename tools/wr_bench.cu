@@ -63,7 +63,7 @@ int main() {
         struct Cfg { int TR, TC, threads, ctas_per_sm, cm; };
         const Cfg cfgs[] = {{128, 128, 256, 1, 0}, {128, 128, 512, 1, 0}, {128, 128, 256, 2, 0}, {128, 128, 256, 4, 0},
                             {128, 256, 256, 1, 0}, {128, 256, 512, 1, 0}, {128, 512, 256, 1, 0}, {256, 128, 256, 1, 0},
-                            {64, 512, 256, 1, 0},  {32, 1024, 256, 1, 0}, {128, 128, 256, 1, 1}, {128, 256, 256, 1, 1}};
+                            {64, 512, 256, 1, 0},  {32, 1024, 256, 1, 0}, {128, 32, 256, 1, 0}, {128, 64, 256, 1, 0}, {128, 128, 256, 1, 1}, {128, 256, 256, 1, 1}};
         for (const Cfg& c : cfgs) {
             cudaEventRecord(e0);
             for (int i = 0; i < 5; ++i) tile_kernel<<<148 * c.ctas_per_sm, c.threads>>>(d, rows, cols, c.TR, c.TC, c.cm);

@@ -23,16 +23,21 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace skb {
 extern std::atomic<long long> g_launches;
 
 // ----------------------------------------------------------------------------- operand preparation
-// stats[0] = max |x| (as float bits), stats[1] = max row sum of squares (float bits)
-__global__ void absmax_kernel(const float* __restrict__ X, int rows, int D, unsigned* __restrict__ stats) {
+// stats[0] = max |x| (as float bits), stats[1] = max row sum of squares (float bits).  blockIdx.y selects the operand, so
+// both matrices of a scoring call are scanned by one launch.
+struct AbsmaxArgs { const float* X[2]; int rows[2]; unsigned* stats[2]; };
+__global__ void absmax_kernel(const AbsmaxArgs a, int D) {
     // one warp per row, block-level max, a single pair of atomics per CTA
     __shared__ float smx[8], sss[8];
+    const float* __restrict__ X = a.X[blockIdx.y];
+    const int rows = a.rows[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float mx = 0.f, ssm = 0.f;
     for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
@@ -49,39 +54,43 @@ __global__ void absmax_kernel(const float* __restrict__ X, int rows, int D, unsi
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < 8; ++i) { mx = fmaxf(mx, smx[i]); ssm = fmaxf(ssm, sss[i]); }
-        atomicMax(stats, __float_as_uint(mx));          // non-negative floats order like their bit patterns
-        atomicMax(stats + 1, __float_as_uint(ssm));
+        atomicMax(a.stats[blockIdx.y], __float_as_uint(mx));          // non-negative floats order like their bit patterns
+        atomicMax(a.stats[blockIdx.y] + 1, __float_as_uint(ssm));
     }
 }
 
-// exp[0] = e such that max|x| * 2^e lies in [2^9, 2^10) (0 for an all-zero operand)
-__global__ void exponent_kernel(const unsigned* stats, int* exp_out) {
+// e such that max|x| * 2^e lies in [2^9, 2^10) (0 for an all-zero operand)
+__device__ __forceinline__ int scale_exponent(const unsigned* stats) {
     const float m = __uint_as_float(stats[0]);
     int e = 0;
     if (m > 0.f) { int fe; frexpf(m, &fe); e = 10 - fe; }
-    exp_out[0] = e;
+    return e;
 }
 
-// passes_out[0] = 1 or 3.  Single-pass error estimate: fp16 rounding 2^-11 per operand, random-sign accumulation over D terms.
-__global__ void decide_kernel(const unsigned* statsE, const unsigned* statsT, int D, float abs_alpha, int passes_req, int* passes_out) {
-    int passes = passes_req;
-    if (passes == 0) {
-        const float nE = sqrtf(__uint_as_float(statsE[1])), nT = sqrtf(__uint_as_float(statsT[1]));
-        const float est = abs_alpha * 4.8828125e-4f * nE * nT * 4.f * rsqrtf((float)D);
-        passes = est < 2.5e-4f ? 1 : 3;
-    }
-    passes_out[0] = passes;
+// 1 or 3 passes.  Single-pass error estimate: fp16 rounding 2^-11 per operand, random-sign accumulation over D terms.
+__device__ __forceinline__ int decide_passes(const unsigned* statsE, const unsigned* statsT, int D, float abs_alpha, int passes_req) {
+    if (passes_req != 0) return passes_req;
+    const float nE = sqrtf(__uint_as_float(statsE[1])), nT = sqrtf(__uint_as_float(statsT[1]));
+    const float est = abs_alpha * 4.8828125e-4f * nE * nT * 4.f * rsqrtf((float)D);
+    return est < 2.5e-4f ? 1 : 3;
 }
 
 // X (rows, D) fp32 -> hi / lo fp16 in 128-row tiles of chunk planes: [rows_pad/128][Dp/8][128][8], so that a whole
 // (tile, K range) operand image is one contiguous block = one bulk copy; rows >= `rows` and columns >= D are zero.
-__global__ void pack_split_kernel(const float* __restrict__ X, int rows, int rows_pad, int D, int Dp,
-                                  const int* __restrict__ exp_dev, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+// blockIdx.y selects the operand.  The scale exponent is derived from the operand's statistics by every thread (and
+// stored once for the GEMM epilogue).
+struct PackArgs { const float* X[2]; int rows[2], rows_pad[2]; const unsigned* stats[2]; int* exp_out[2]; uint16_t* hi[2]; uint16_t* lo[2]; };
+__global__ void pack_split_kernel(const PackArgs a, int D, int Dp) {
+    const int op = blockIdx.y;
+    const float* __restrict__ X = a.X[op];
+    const int rows = a.rows[op], rows_pad = a.rows_pad[op];
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int chunks = Dp >> 3;
+    const int e_scale = scale_exponent(a.stats[op]);
+    if (idx == 0) a.exp_out[op][0] = e_scale;
     if (idx >= (long long)rows_pad * chunks) return;
     const int row = (int)(idx % rows_pad), j = (int)(idx / rows_pad);
-    const float sc = ldexpf(1.f, exp_dev[0]);
+    const float sc = ldexpf(1.f, e_scale);
     float h[8], l[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -95,15 +104,18 @@ __global__ void pack_split_kernel(const float* __restrict__ X, int rows, int row
     oh.x = pack2<false>(h[0], h[1]); oh.y = pack2<false>(h[2], h[3]); oh.z = pack2<false>(h[4], h[5]); oh.w = pack2<false>(h[6], h[7]);
     ol.x = pack2<false>(l[0], l[1]); ol.y = pack2<false>(l[2], l[3]); ol.z = pack2<false>(l[4], l[5]); ol.w = pack2<false>(l[6], l[7]);
     const size_t o = (((size_t)(row >> 7) * chunks + j) * 128 + (row & 127)) * 8;
-    *reinterpret_cast<uint4*>(hi + o) = oh;
-    *reinterpret_cast<uint4*>(lo + o) = ol;
+    *reinterpret_cast<uint4*>(a.hi[op] + o) = oh;
+    *reinterpret_cast<uint4*>(a.lo[op] + o) = ol;
 }
 
 // ----------------------------------------------------------------------------- the GEMM
 struct ScoreParams {
     const uint16_t *Ehi, *Elo, *Thi, *Tlo;   // [rows_pad/128][Dp/8][128][8]
-    int Ne, Nt, Ne_pad, Nt_pad, Dp;
-    const int *expE, *expT, *passes;          // per-operand scale exponents and the pass count (all on the device)
+    int Ne, Nt, Ne_pad, Nt_pad, Dp, D;
+    const int *expE, *expT;                   // per-operand scale exponents (on the device)
+    const unsigned *statsE, *statsT;          // operand statistics: the pass count is decided from them on the device
+    float abs_alpha;
+    int passes_req;                           // 0 = decide on the device, 1 or 3 = forced
     const float *ra, *ca;                     // multiplicative row / column terms (may be null)
     const float *r, *q;                       // additive row / column terms (may be null)
     float a0, c0, rq_scale;                   // acc * (ra_i + ca_j + a0) * 2^-(eE+eT) + rq_scale * (r_i + q_j) + c0
@@ -148,7 +160,8 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
     uint8_t* b_smem = a_smem + SM::a_bytes(p.Dp);
     uint8_t* stage_smem = b_smem + SM::kBStages * SM::kRingStageBytes;
 
-    if (p.passes[0] != PASSES) return;   // the other instantiation handles this launch (uniform across the grid)
+    // the other instantiation handles this launch when the decision (uniform across the grid) is not ours
+    if (decide_passes(p.statsE, p.statsT, p.D, p.abs_alpha, p.passes_req) != PASSES) return;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // contiguous run of tiles for this CTA (panel-major), walked with incremental (panel, nt) counters
@@ -404,14 +417,32 @@ void packed_free(PackedOp* op) {
     *op = PackedOp();
 }
 
-// scale, split into fp16 hi / lo and lay out as 128-row tiles of chunk planes (buffers of `op` already sized)
-static int packed_fill(const float* X, PackedOp* op, cudaStream_t st) {
-    SKB_CUDA_CHECK(cudaMemsetAsync(op->stats, 0, 2 * sizeof(unsigned), st));
-    absmax_kernel<<<std::min((op->rows + 7) / 8, 4 * kNumSMs), 256, 0, st>>>(X, op->rows, op->D, op->stats);
-    exponent_kernel<<<1, 1, 0, st>>>(op->stats, op->exp);
-    const long long n = (long long)op->rows_pad * (op->Dp / 8);
-    pack_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X, op->rows, op->rows_pad, op->D, op->Dp, op->exp, op->hi, op->lo);
-    g_launches += 3;
+// scale, split into fp16 hi / lo and lay out as 128-row tiles of chunk planes (buffers of the operands already sized);
+// one or two operands (same D) per pair of launches
+static int packed_fill(const float* X0, PackedOp* op0, const float* X1, PackedOp* op1, cudaStream_t st) {
+    const int n_ops = op1 ? 2 : 1;
+    AbsmaxArgs aa;
+    PackArgs pa;
+    PackedOp* ops[2] = {op0, op1};
+    const float* Xs[2] = {X0, X1};
+    int max_rows = 0;
+    long long max_n = 0;
+    for (int i = 0; i < 2; ++i) {
+        PackedOp* o = ops[i < n_ops ? i : 0];
+        aa.X[i] = pa.X[i] = Xs[i < n_ops ? i : 0];
+        aa.rows[i] = pa.rows[i] = o->rows;
+        aa.stats[i] = o->stats;
+        pa.stats[i] = o->stats;
+        pa.rows_pad[i] = o->rows_pad; pa.exp_out[i] = o->exp; pa.hi[i] = o->hi; pa.lo[i] = o->lo;
+        if (i < n_ops) {
+            SKB_CUDA_CHECK(cudaMemsetAsync(o->stats, 0, 2 * sizeof(unsigned), st));
+            max_rows = std::max(max_rows, o->rows);
+            max_n = std::max(max_n, (long long)o->rows_pad * (o->Dp / 8));
+        }
+    }
+    absmax_kernel<<<dim3(std::min((max_rows + 7) / 8, 4 * kNumSMs), n_ops), 256, 0, st>>>(aa, op0->D);
+    pack_split_kernel<<<dim3((unsigned)((max_n + 255) / 256), n_ops), 256, 0, st>>>(pa, op0->D, op0->Dp);
+    g_launches += 2;
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
 }
@@ -419,7 +450,7 @@ static int packed_fill(const float* X, PackedOp* op, cudaStream_t st) {
 int packed_create(const float* X_dev, int rows, int D, PackedOp* op, cudaStream_t st) {
     int rc = packed_alloc(op, rows, D);
     if (rc) return rc;
-    return packed_fill(X_dev, op, st);
+    return packed_fill(X_dev, op, nullptr, nullptr, st);
 }
 
 struct ScoreWorkspace {
@@ -487,13 +518,11 @@ int gemm_packed(const PackedOp& E, const PackedOp& T, const float* ra, const flo
     }
     int rc = ws_ensure(0, 0);
     if (rc) return rc;
-    int* passes_dev = reinterpret_cast<int*>(g_ws.stats + 6);
-    decide_kernel<<<1, 1, 0, st>>>(E.stats, T.stats, E.D, abs_alpha_for_auto, passes, passes_dev);
-    g_launches++;
     ScoreParams p;
     p.Ehi = E.hi; p.Elo = E.lo; p.Thi = T.hi; p.Tlo = T.lo;
-    p.Ne = E.rows; p.Nt = T.rows; p.Ne_pad = E.rows_pad; p.Nt_pad = T.rows_pad; p.Dp = E.Dp;
-    p.expE = E.exp; p.expT = T.exp; p.passes = passes_dev;
+    p.Ne = E.rows; p.Nt = T.rows; p.Ne_pad = E.rows_pad; p.Nt_pad = T.rows_pad; p.Dp = E.Dp; p.D = E.D;
+    p.expE = E.exp; p.expT = T.exp; p.statsE = E.stats; p.statsT = T.stats;
+    p.abs_alpha = abs_alpha_for_auto; p.passes_req = passes;
     p.ra = ra; p.ca = ca; p.r = r; p.q = q; p.a0 = a0; p.c0 = c0; p.rq_scale = rq_scale;
     p.mul_scaled = 1;
     p.out = out; p.ld_out = ld_out; p.out_f64 = out_f64;
@@ -502,7 +531,8 @@ int gemm_packed(const PackedOp& E, const PackedOp& T, const float* ra, const flo
     const int grid = std::min(p.tiles_total, kNumSMs);
     // Large K (dense layers of the pooling / head) streams both operands; K <= 256 keeps the E panel resident.
     // Both pass variants are launched when the count is decided on the device; exactly one does the work.
-    const bool stream_a = E.Dp > 256;
+    static const bool force_stream = getenv("SKB_FORCE_STREAM_A") != nullptr;   // experiment knob
+    const bool stream_a = E.Dp > 256 || force_stream;
     if (passes != 3) rc = stream_a ? launch_score<1, true>(p, grid, st) : launch_score<1, false>(p, grid, st);
     if (rc) return rc;
     if (passes != 1) rc = stream_a ? launch_score<3, true>(p, grid, st) : launch_score<3, false>(p, grid, st);
@@ -522,7 +552,7 @@ int gemm_nt_split(const float* A_dev, int M, int K, const PackedOp& W, const flo
     if (rc) return rc;
     PackedOp a;
     ws_operand(&a, M, K, 0, 0);
-    if ((rc = packed_fill(A_dev, &a, st))) return rc;
+    if ((rc = packed_fill(A_dev, &a, nullptr, nullptr, st))) return rc;
     return gemm_packed(a, W, nullptr, nullptr, alpha, nullptr, bias, 0.f, 1.f, 1.f, 3, 0, C, ldc, st);
 }
 
@@ -541,8 +571,7 @@ static int score_gemm_general(const float* E, const float* T, int Ne, int Nt, in
     PackedOp e, t;
     ws_operand(&e, Ne, D, 0, 0);
     ws_operand(&t, Nt, D, 1, 2 * eh);
-    if ((rc = packed_fill(E, &e, st))) return rc;
-    if ((rc = packed_fill(T, &t, st))) return rc;
+    if ((rc = packed_fill(E, &e, T, &t, st))) return rc;
     return gemm_packed(e, t, ra, ca, a0, r, q, c0, rq_scale, abs_alpha_for_auto, passes, out_f64, out, ld_out, st);
 }
 

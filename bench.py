@@ -36,6 +36,15 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def load_traffic(kernel):
+    """Measured DRAM bytes per launch of a kernel (ncu --set full, summarised in profiles/traffic.json) or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return float(json.load(open(path))[kernel]["bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def hr34_macs(L):
     """Algorithmic MACs of one HalfResNet34 embedding of L samples (SURVEY.md 8d closed form)."""
     T1 = 1 + L // 160
@@ -276,7 +285,8 @@ def run_ours(args):
     n_conv_launches = args.steps * 36
     roofline = {"kernel": "conv_umma_kernel (tcgen05 shift-GEMM conv, 36 launches per step)", "bound": "tensor",
                 "achieved": conv_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": conv_tf / peaks["tf_sustained"],
-                "traffic": None, "peak_source": peaks["source"] + " sustained bf16",
+                "traffic": load_traffic("conv_umma_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/traffic.json)",
+                "peak_source": peaks["source"] + " sustained bf16",
                 "avg_launch_ms": conv_ms / n_conv_launches if n_conv_launches else None,
                 "flops_per_launch": 2.0 * trunk_macs / n_conv_launches,
                 "whole_step_tflops": 2.0 * all_macs / (ms / 1e3) / 1e12 / max(world, 1),
@@ -358,6 +368,7 @@ def run_extras(args, device, peaks, dist_on, rank, world):
                            "ms_per_step": ms / args.steps,
                            "roofline": {"kernel": "score_gemm_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
                                         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                        "traffic": load_traffic("score_gemm_kernel") if world == 1 else None,
                                         "tensor_tflops": 2.0 * rows * Nt * D * args.steps / (ms / 1e3) / 1e12}}
         if world == 1:
             # end to end through the reference-shaped API: StatServer / Ndx in, Scores (float64 numpy on the host) out

@@ -1,6 +1,9 @@
 // Host launcher for the tcgen05 shift-GEMM convolution (kernel in conv_umma.cuh).
 #include "sidekit_b200.h"
 #include "conv_umma.cuh"
+#include "conv3_umma.cuh"
+
+#include <cstdlib>
 #include "layers.cuh"
 
 namespace skb {
@@ -62,7 +65,48 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     return SKB_OK;
 }
 
+// Fused-tap kernel for the narrow 3x3 / stride-1 convolutions (conv3_umma.cuh).
+template <int N_CTA, int MT, bool BF16>
+static int launch_one3(const ConvParams& p_in, cudaStream_t st) {
+    using Cfg = Conv3Cfg<N_CTA, MT>;
+    static bool configured = false;
+    ConvParams p = p_in;
+    p.halo = p.Wp;                                          // one line above / below; the +-1 pixel shifts happen in the epilogue
+    p.rows_pad = (Cfg::kTileM + 2 * p.Wp + 7) / 8 * 8;
+    const int n_kc = p.cin / kConvKC;
+    const size_t a_stage = (size_t)p.rows_pad * (kConvKC / 8) * 16;
+    p.scale_smem_bytes = 0;
+    if (p.se_scale != nullptr && (size_t)p.n_utt * N_CTA * 4 <= 32 * 1024) p.scale_smem_bytes = p.n_utt * N_CTA * 4;
+    const size_t fixed = Cfg::fixed_bytes(n_kc, p.scale_smem_bytes);
+    if (fixed + 2 * a_stage > (size_t)kConvSmemBudget || p.G < p.Wp + 1) {
+        set_last_error(__FILE__, __LINE__, "fused-tap conv does not fit (shared memory or guard)");
+        return SKB_ERR_ARG;
+    }
+    int stages = (int)((kConvSmemBudget - fixed) / a_stage);
+    if (stages > kConvMaxAStages) stages = kConvMaxAStages;
+    p.a_stages = stages;
+    const size_t smem = fixed + (size_t)stages * a_stage;
+    if (!configured) {
+        SKB_CUDA_CHECK(cudaFuncSetAttribute(conv3_umma_kernel<N_CTA, MT, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const int n_pix = p.p_end - p.G;
+    p.n_tiles = (n_pix + Cfg::kTileOut - 1) / Cfg::kTileOut;
+    const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
+    conv3_umma_kernel<N_CTA, MT, BF16><<<grid, kConvThreads, smem, st>>>(p);
+    SKB_LAUNCH_CHECK(st);
+    return SKB_OK;
+}
+
 int launch_conv_umma(const ConvParams& p, int n_cta, bool bf16, cudaStream_t st) {
+    // EXPERIMENTAL, off by default (SKB_FUSED_TAPS=1 enables it): parity-green, and its MMA loop is 2.4x / 1.5x shorter on
+    // layers 1 / 2, but the lane-shifted epilogue (64 shuffles + 6 TMEM loads per 32 x 32 block) costs more than the MMAs
+    // it saves: 417 / 230 us per launch against 295 / 178 us for conv_umma_kernel (profiles/r01c_fused_taps.txt).
+    static const bool fused_taps = [] { const char* e = getenv("SKB_FUSED_TAPS"); return e && e[0] == '1'; }();
+    if (p.w3 != nullptr && fused_taps && p.cout == n_cta && p.taps == 9 && p.cin % kConvKC == 0) {
+        if (n_cta == 32) return bf16 ? launch_one3<32, 2, true>(p, st) : launch_one3<32, 2, false>(p, st);
+        if (n_cta == 64) return bf16 ? launch_one3<64, 1, true>(p, st) : launch_one3<64, 1, false>(p, st);
+    }
     if (p.cin % kConvKC != 0 || p.cout % n_cta != 0 || p.taps < 1 || p.taps > 10 || p.rows_pad % 8 != 0 || p.kc_per_grp < 1 || p.n_pairs < 1) {
         set_last_error(__FILE__, __LINE__, "conv_umma: unsupported shape");
         return SKB_ERR_ARG;

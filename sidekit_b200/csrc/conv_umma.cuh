@@ -32,6 +32,10 @@ struct ConvParams {
     const uint16_t* in;     // input planes
     long long in_plane;     // pixels per input chunk plane
     const uint16_t* w;      // packed weights: [n_split][kc][tap] images of [4][N_CTA][8]
+    const uint16_t* w3;     // or nullptr: fused-tap packing [kc][r] images of [4][3 * Cout][8] (conv3_umma.cuh)
+    int Wp;                 // pixels per padded line (fused-tap kernel)
+    int n_utt;              // utterances in the batch (rows of se_scale)
+    int scale_smem_bytes;   // fused-tap kernel: bytes of se_scale cached in shared memory (0 = read it from global memory)
     const float* bias;      // [cout] folded BN bias (fp32)
     uint16_t* out;          // output planes
     long long out_plane;

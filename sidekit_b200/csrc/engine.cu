@@ -144,6 +144,7 @@ static int bn_affine(const WeightMap& w, const std::string& prefix, std::vector<
 // ----------------------------------------------------------------------------- packed conv weights
 struct ConvW {
     uint16_t* w = nullptr;   // device, UMMA images
+    uint16_t* w3 = nullptr;  // device, fused-tap images (3x3 convs with 32 or 64 output channels), else nullptr
     float* bias = nullptr;   // device [cout]
     int cin = 0, cout = 0, taps = 0, ncta = 0;
     bool phase_split = false;   // stride-2 3x3 conv packed for a phase-split input (cin = 4 * original channels)
@@ -170,6 +171,20 @@ static int pack_conv(const std::vector<double>& wf, const std::vector<double>& b
     out->cin = cin_pad; out->cout = cout; out->taps = taps; out->ncta = ncta;
     int rc = dev_upload(img, &out->w);
     if (rc) return rc;
+    if (taps == 9 && (cout == 32 || cout == 64) && cin_pad == cin_src) {
+        // fused-tap packing (conv3_umma.cuh): per (k-chunk, vertical tap r) one image [4 planes][3 * cout rows][8], row = s * cout + co
+        std::vector<uint16_t> img3((size_t)n_kc * 3 * 4 * 3 * cout * 8);
+        size_t o3 = 0;
+        for (int kc = 0; kc < n_kc; ++kc)
+            for (int r = 0; r < 3; ++r)
+                for (int j = 0; j < 4; ++j)
+                    for (int sc = 0; sc < 3 * cout; ++sc)
+                        for (int e = 0; e < 8; ++e) {
+                            const int s_tap = sc / cout, co = sc % cout, ci = kc * kConvKC + j * 8 + e;
+                            img3[o3++] = to16((float)wf[((size_t)co * cin_src + ci) * 9 + r * 3 + s_tap], bf16);
+                        }
+        if ((rc = dev_upload(img3, &out->w3))) return rc;
+    }
     return dev_upload(bf, &out->bias);
 }
 
@@ -237,6 +252,7 @@ static int pack_conv_bn_phase_split(const WeightMap& w, const std::string& conv_
 
 static void free_conv(ConvW* c) {
     cudaFree(c->w);
+    cudaFree(c->w3);
     cudaFree(c->bias);
     *c = ConvW();
 }
@@ -812,7 +828,10 @@ static int run_conv(skb_xtractor* h, const ConvW& cw, int kind, const Level& Lg,
     for (int g = 1; g < 5; ++g) p.grp_tap[g] = cw.taps;
     p.n_pairs = n_kc * cw.taps;
     int max_shift = 0;
+    p.Wp = Lg.Wp;
+    p.n_utt = h->plan.B;
     if (kind == 1) {
+        p.w3 = cw.w3;
         p.halo = Lg.Wp + 1;
         for (int t = 0; t < 9; ++t) p.tap_shift[t] = (t / 3 - 1) * Lg.Wp + (t % 3 - 1);
         max_shift = Lg.Wp + 1;

@@ -109,6 +109,26 @@ int skb_asnorm_stats(const float* X_dev, const float* cohort_dev, int N, int C, 
 int skb_asnorm_apply(const float* X_dev, int N, int D, const float* mean_dev, const float* std_dev, float* out_dev,
                      void* stream);
 
+/* ---- evaluation tail: host functions, plain host pointers ------------------------------
+ * Pool-adjacent-violators, sidekit/bosaris/detplot.py:289-347 (`pavx`): y[n] -> ghat[n] (including the reference's
+ * wrap-around write into the last element), bin widths / heights (arrays of n, the first *n_bins entries are used). */
+int skb_pavx(const double* y, int64_t n, double* ghat, int64_t* width, double* height, int64_t* n_bins);
+/* ROC convex hull, detplot.py:391-441 (`rocch`): pmiss / pfa need room for n_tar + n_non + 1 vertices. */
+int skb_rocch(const double* tar, int64_t n_tar, const double* non, int64_t n_non, double* pmiss, double* pfa,
+              int64_t* n_points);
+/* Equal error rate by bisection, sidekit/nnet/xvector.py:101-209 (`eer(negatives, positives)`). */
+int skb_eer(const double* negatives, int64_t n_neg, const double* positives, int64_t n_pos, double* eer_out);
+
+/* z-/t-norm statistics and normalisation (sidekit/score_normalization.py:44-95) on a device-resident score matrix
+ * S_dev (M, N), leading dimension ld, float32 (is_f64 = 0) or float64.  axis 1: per row (mean(1), std(1)); axis 0: per
+ * column.  sym = 1 (znorm(sym=True), axis 1, square matrix): the diagonal is excluded, divisor N-1, and the second output
+ * is the reference's "std_per_model": row sums of (S[i][j] - mean[j])^2 without the diagonal term, over N-1.  mean_dev / std_dev: device doubles of length M (axis 1) or N (axis 0). */
+int skb_scoremat_stats(const void* S_dev, int M, int N, int64_t ld, int is_f64, int axis, int sym, double* mean_dev,
+                       double* std_dev, void* stream);
+/* out[i][j] = (S[i][j] - sub[j]) / div[j]  (numpy broadcasting of an (N,) vector, as both znorm and tnorm do). */
+int skb_scoremat_normalise(const void* S_dev, int M, int N, int64_t ld, int is_f64, const double* sub_dev,
+                           const double* div_dev, void* out_dev, int64_t ld_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

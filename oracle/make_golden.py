@@ -148,7 +148,72 @@ def golden_scoring():
     print("scoring.npz", sorted(out.keys()))
 
 
+def golden_evaltail():
+    """PAV / ROCCH / EER / minDCF / Key / z-t-norm outputs of the real reference on seeded scores."""
+    sidekit = ref_import.import_reference()
+    from sidekit.bosaris.detplot import pavx, rocch, rocch2eer, fast_minDCF
+    from sidekit.nnet.xvector import eer
+    from sidekit.score_normalization import znorm, tnorm, ztnorm
+    from sidekit.bosaris import Key, Scores
+    rng = numpy.random.default_rng(777)
+    out = {}
+    cases = {"sep": (rng.normal(2.0, 1.0, 400), rng.normal(-1.0, 1.2, 1500)),
+             "overlap": (rng.normal(0.3, 1.0, 300), rng.normal(0.0, 1.0, 900)),
+             "ties": (numpy.round(rng.normal(1.0, 1.0, 250), 1), numpy.round(rng.normal(0.0, 1.0, 700), 1)),
+             "tiny": (numpy.array([0.2, 0.9, 0.5]), numpy.array([0.1, 0.6, 0.4, 0.55]))}
+    for name, (tar, non) in cases.items():
+        out[name + "_tar"], out[name + "_non"] = tar, non
+        pm, pf = rocch(tar, non)
+        out[name + "_pmiss"], out[name + "_pfa"] = pm, pf
+        out[name + "_rocch_eer"] = numpy.array(rocch2eer(pm, pf), dtype=numpy.float64)
+        out[name + "_mindcf"] = numpy.array(fast_minDCF(tar, non, -2.0, normalize=True), dtype=numpy.float64)
+        out[name + "_eer"] = numpy.array(eer(non, tar), dtype=numpy.float64)
+    y = numpy.concatenate([rng.random(60), numpy.array([0.5, 0.5, 0.25, 0.75, 0.75])])
+    g, w, h = pavx(y)
+    out["pav_y"], out["pav_ghat"], out["pav_width"], out["pav_height"] = y, g, w, h
+    # Key built from trial lists (with a repeated pair: the last listing wins) and get_tar_non through align_with_ndx
+    models = numpy.array(["m%d" % (i % 7) for i in range(60)] + ["m0"])
+    segs = numpy.array(["s%d" % ((i * 5) % 11) for i in range(60)] + ["s0"])
+    trials = numpy.array(["target" if (i % 3 == 0) else "nontarget" for i in range(60)] + ["nontarget"])
+    key = Key(models=models, testsegs=segs, trials=trials)
+    out["key_models"], out["key_segs"], out["key_trials"] = models, segs, trials
+    out["key_modelset"], out["key_segset"], out["key_tar"], out["key_non"] = key.modelset, key.segset, key.tar, key.non
+    sc = Scores()
+    sc.modelset = numpy.array(["m%d" % i for i in (3, 0, 6, 1, 9, 2, 5)])       # m4 missing, m9 extra, other order
+    sc.segset = numpy.array(["s%d" % i for i in (10, 2, 7, 0, 5, 1, 3, 8, 6, 4)])   # s9 missing
+    sc.scoremat = rng.standard_normal((7, 10))
+    sc.scoremask = rng.random((7, 10)) < 0.8
+    out["sc_modelset"], out["sc_segset"], out["sc_mat"], out["sc_mask"] = sc.modelset, sc.segset, sc.scoremat, sc.scoremask
+    t, n = sc.get_tar_non(key)
+    out["sc_tar"], out["sc_non"] = t, n
+    # z / t / zt-norm on square score sets (the reference's znorm broadcasts per-model statistics against the last axis)
+    def scores(M, S, seed, mpre, spre):
+        r = numpy.random.default_rng(seed)
+        s_ = Scores()
+        s_.modelset = numpy.array(["%s%02d" % (mpre, i) for i in r.permutation(M)])
+        s_.segset = numpy.array(["%s%02d" % (spre, i) for i in r.permutation(S)])
+        s_.scoremat = r.standard_normal((M, S)) + 0.1 * numpy.arange(S)
+        s_.scoremask = numpy.ones((M, S), dtype=bool)
+        return s_
+    n_ = 12
+    et, ei, it, ii = scores(n_, n_, 1, "e", "t"), scores(n_, n_, 2, "e", "i"), scores(n_, n_, 3, "i", "t"), scores(n_, n_, 4, "i", "i")
+    for nm, s_ in (("et", et), ("ei", ei), ("it", it), ("ii", ii)):
+        out["zt_%s_modelset" % nm], out["zt_%s_segset" % nm], out["zt_%s_mat" % nm] = s_.modelset.copy(), s_.segset.copy(), s_.scoremat.copy()
+    out["znorm_mat"] = znorm(copy.deepcopy(et), copy.deepcopy(ei)).scoremat
+    out["znorm_sym_mat"] = znorm(copy.deepcopy(it), copy.deepcopy(ii), sym=True).scoremat
+    out["tnorm_mat"] = tnorm(copy.deepcopy(et), copy.deepcopy(it)).scoremat
+    zt = ztnorm(copy.deepcopy(et), copy.deepcopy(ei), copy.deepcopy(it), copy.deepcopy(ii))
+    out["ztnorm_mat"], out["ztnorm_modelset"], out["ztnorm_segset"] = zt.scoremat, zt.modelset, zt.segset
+    numpy.savez_compressed(os.path.join(GOLD, "evaltail.npz"), **out)
+    print("evaltail.npz", sorted(out.keys()))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    golden_scoring()
-    golden_extraction()
+    which = sys.argv[1:] or ["scoring", "extraction", "evaltail"]
+    if "scoring" in which:
+        golden_scoring()
+    if "extraction" in which:
+        golden_extraction()
+    if "evaltail" in which:
+        golden_evaltail()

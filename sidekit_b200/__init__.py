@@ -9,10 +9,12 @@ All arithmetic runs in hand-written CUDA kernels for sm_100a behind ``libsidekit
 from . import _lib
 from .nnet import Xtractor, MeanStdPooling, AttentivePooling, PreHalfResNet34, MfccFrontEnd, MelSpecFrontEnd
 
-from .bosaris import Ndx, Scores
+from .bosaris import Ndx, Scores, Key
 from .statserver import StatServer
 from .iv_scoring import cosine_scoring, PLDA_scoring, fast_PLDA_scoring, two_covariance_scoring, score_matrix
-from .score_normalization import asnorm
+from .score_normalization import asnorm, znorm, tnorm, ztnorm
+from . import detplot
+from .detplot import pavx, rocch, rocch2eer, fast_minDCF, eer
 from . import bulk
 from .bulk import extract_embeddings
 

@@ -1,8 +1,61 @@
 """Light BOSARIS containers used as argument / return types of the scoring functions
-(sidekit/bosaris/ndx.py:48-182, sidekit/bosaris/scores.py:52-81, :304-313): same attribute names,
-same ``validate()`` rules, no HDF5 / plotting (out of scope of the hot path).
+(sidekit/bosaris/ndx.py:48-182, sidekit/bosaris/key.py:49-110, sidekit/bosaris/scores.py:52-81, :157-240, :304-313,
+:469-478): same attribute names, same ``validate()`` rules, no HDF5 / plotting (out of scope of the hot path).
+Id matching is an O(N) hash join with the reference's ordering semantics (first occurrence wins).
 """
+import logging
+
 import numpy
+
+
+def _first_index(ids):
+    """id -> index of its first occurrence."""
+    table = {}
+    for i, v in enumerate(numpy.asarray(ids).tolist()):
+        table.setdefault(v, i)
+    return table
+
+
+class Key:
+    """Trial key (key.py:49-110): ``tar`` / ``non`` (M, S) bool matrices over ``modelset`` x ``segset``."""
+
+    def __init__(self, key_file_name=None, models=numpy.array([]), testsegs=numpy.array([]), trials=numpy.array([])):
+        self.modelset = numpy.empty(0, dtype="|O")
+        self.segset = numpy.empty(0, dtype="|O")
+        self.tar = numpy.array([], dtype="bool")
+        self.non = numpy.array([], dtype="bool")
+        if key_file_name is not None:
+            raise NotImplementedError("Key file IO is out of scope; pass models / testsegs / trials")
+        models, testsegs, trials = numpy.asarray(models), numpy.asarray(testsegs), numpy.asarray(trials)
+        if models.shape[0]:
+            # key.py:79-97 vectorised: the LAST trial listed for a (model, segment) pair decides (dict(zip(...)))
+            modelset, mi = numpy.unique(models, return_inverse=True)
+            segset, si = numpy.unique(testsegs, return_inverse=True)
+            tar = numpy.zeros((modelset.shape[0], segset.shape[0]), dtype="bool")
+            non = numpy.zeros((modelset.shape[0], segset.shape[0]), dtype="bool")
+            tar[mi, si] = trials == 'target'          # fancy assignment: the last write wins, like the dict
+            non[mi, si] = trials == 'nontarget'
+            self.modelset, self.segset, self.tar, self.non = modelset, segset, tar, non
+            assert self.validate(), "Wrong Key format"
+
+    @classmethod
+    def create(cls, modelset, segset, tar, non):
+        key = cls()
+        key.modelset, key.segset, key.tar, key.non = modelset, segset, tar, non
+        assert key.validate(), "Wrong Key format"
+        return key
+
+    def to_ndx(self):
+        ndx = Ndx()
+        ndx.modelset, ndx.segset, ndx.trialmask = self.modelset, self.segset, self.tar | self.non
+        return ndx
+
+    def validate(self):
+        ok = isinstance(self.modelset, numpy.ndarray) and isinstance(self.segset, numpy.ndarray)
+        ok &= isinstance(self.tar, numpy.ndarray) and isinstance(self.non, numpy.ndarray)
+        ok &= self.modelset.ndim == 1 and self.segset.ndim == 1 and self.tar.ndim == 2 and self.non.ndim == 2
+        ok &= self.tar.shape == self.non.shape == (self.modelset.shape[0], self.segset.shape[0])
+        return bool(ok)
 
 
 class Ndx:
@@ -75,3 +128,48 @@ class Scores:
         ok &= (self.scoremat.shape[0] == self.modelset.shape[0])
         ok &= (self.scoremat.shape[1] == self.segset.shape[0])
         return bool(ok)
+
+    def get_tar_non(self, key):
+        """scores.py:157-179: target and non-target score vectors selected by ``key``."""
+        if (self.modelset.shape == key.modelset.shape and self.segset.shape == key.segset.shape
+                and (key.modelset == self.modelset).all() and (key.segset == self.segset).all()
+                and self.scoremask.shape == key.tar.shape):
+            return self.scoremat[key.tar & self.scoremask], self.scoremat[key.non & self.scoremask]
+        new_score = self.align_with_ndx(key)
+        return new_score.scoremat[key.tar & new_score.scoremask], new_score.scoremat[key.non & new_score.scoremask]
+
+    def align_with_ndx(self, ndx):
+        """scores.py:181-240: resized / reordered copy that follows ``ndx`` (a Key or an Ndx)."""
+        aligned = Scores()
+        aligned.modelset, aligned.segset = ndx.modelset, ndx.segset
+        mtab, stab = _first_index(self.modelset), _first_index(self.segset)
+        mlist, slist = numpy.asarray(ndx.modelset).tolist(), numpy.asarray(ndx.segset).tolist()
+        hasmodel = numpy.fromiter((m in mtab for m in mlist), dtype=bool, count=len(mlist))
+        hasseg = numpy.fromiter((s in stab for s in slist), dtype=bool, count=len(slist))
+        rindx = numpy.array([mtab[m] for m in mlist if m in mtab], dtype=int)
+        cindx = numpy.array([stab[s] for s in slist if s in stab], dtype=int)
+        rows, cols = numpy.where(hasmodel)[0][:, None], numpy.where(hasseg)[0]
+        aligned.scoremat = numpy.zeros((len(mlist), len(slist)))
+        aligned.scoremask = numpy.zeros((len(mlist), len(slist)), dtype='bool')
+        if rindx.size and cindx.size:
+            aligned.scoremat[rows, cols] = self.scoremat[rindx[:, None], cindx]
+            aligned.scoremask[rows, cols] = self.scoremask[rindx[:, None], cindx]
+        if isinstance(ndx, Ndx):
+            aligned.scoremask = aligned.scoremask & ndx.trialmask
+        else:
+            aligned.scoremask = aligned.scoremask & (ndx.tar | ndx.non)
+        if hasmodel.sum() < len(mlist):
+            logging.info('models reduced from %d to %d', len(mlist), hasmodel.sum())
+        if hasseg.sum() < len(slist):
+            logging.info('testsegs reduced from %d to %d', len(slist), hasseg.sum())
+        assert numpy.all(numpy.isfinite(aligned.scoremat[aligned.scoremask])), 'Inifinite or Nan value in the scoremat'
+        assert aligned.validate(), 'Wrong Score format'
+        return aligned
+
+    def sort(self):
+        """scores.py:469-478: sort models and segments (in place)."""
+        mi, si = numpy.argsort(self.modelset), numpy.argsort(self.segset)
+        mask, mat = self.scoremask[mi[:, None], si], self.scoremat[mi[:, None], si]
+        self.modelset.sort()
+        self.segset.sort()
+        self.scoremat, self.scoremask, self.scoremat_device = mat, mask, None

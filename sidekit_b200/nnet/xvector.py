@@ -20,6 +20,7 @@ from .loss import ArcMarginProduct
 from .pooling import AttentivePooling, MeanStdPooling
 from .preprocessor import MelSpecFrontEnd, MfccFrontEnd
 from .res_net import PreHalfResNet34
+from ..detplot import eer  # noqa: F401  (sidekit.nnet.xvector.eer, xvector.py:101-209)
 
 _ARCHI_ID = {"halfresnet34": 0, "xvector": 1}
 

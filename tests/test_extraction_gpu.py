@@ -122,6 +122,32 @@ def test_plan_cache_switches_and_evictions_leave_no_stale_state(hr34):
         assert torch.equal(m.extract_varlen(sets[i]), first[i])
 
 
+def test_experimental_fused_tap_kernel_parity():
+    """conv3_umma_kernel (SKB_FUSED_TAPS=1, read once per process -> subprocess): oracle parity and packing invariance."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch\n"
+        "from oracle import extract_ref as R\n"
+        "from sidekit_b200 import synth\n"
+        "from tests.models import make_xtractor\n"
+        "from tests.helpers import rel_l2\n"
+        "m = make_xtractor('halfresnet34', 32, 256).cuda()\n"
+        "sd = {k: v.cpu() for k, v in m.state_dict().items()}\n"
+        "ws = [synth.synth_wave(1, L, seed=700 + i)[0] for i, L in enumerate((16000, 9000, 20321))]\n"
+        "emb = m.extract_varlen([w.cuda() for w in ws])\n"
+        "ref = torch.cat([R.forward(sd, w.unsqueeze(0), 'halfresnet34')[1] for w in ws])\n"
+        "assert rel_l2(emb.cpu(), ref) < 1e-3, rel_l2(emb.cpu(), ref)\n"
+        "solo = torch.cat([m.extract_varlen([w.cuda()]) for w in ws])\n"
+        "assert torch.equal(emb, solo)\n"
+        "print('fused-tap ok')\n")
+    env = dict(os.environ, SKB_FUSED_TAPS="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "fused-tap ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_host_buffer_entry_point(hr34):
     m, _ = hr34
     x = synth.synth_wave(3, 16000, seed=7)

@@ -8,6 +8,7 @@ All arithmetic runs in hand-written CUDA kernels for sm_100a behind ``libsidekit
 """
 from . import _lib
 from .nnet import Xtractor, MeanStdPooling, AttentivePooling, PreHalfResNet34, MfccFrontEnd, MelSpecFrontEnd
+from .nnet.xsets import IdMap, IdMapSet
 
 from .bosaris import Ndx, Scores, Key
 from .statserver import StatServer

@@ -4,3 +4,4 @@ from .pooling import MeanStdPooling, AttentivePooling
 from .res_net import PreHalfResNet34, BasicBlock, SELayer
 from .preprocessor import MfccFrontEnd, MelSpecFrontEnd, PreEmphasis
 from .loss import ArcMarginProduct, l2_norm
+from .xsets import IdMap, IdMapSet, extract_embeddings, read_wav  # noqa: F401,E402

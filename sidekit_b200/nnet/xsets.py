@@ -1,0 +1,147 @@
+"""Feed path of the extractor: ``IdMap``, ``IdMapSet`` and ``extract_embeddings`` with the
+reference's signatures (sidekit/bosaris/idmap.py:43-73, sidekit/nnet/xsets.py:368-480,
+sidekit/nnet/xvector.py:1796-1916).
+
+What changes against the reference: wav files are read with the standard library (``torchaudio.load`` needs
+torchcodec), and instead of one ``forward`` per file -- a few hundred small launches and a device-to-host sync each --
+ALL segments / sliding windows of the id map are cut on the host, length-bucketed and pushed through
+``Xtractor.extract_varlen`` as packed batches (``bulk.make_batches``): the engine's packed layout makes a batch of
+different lengths exact, so the embeddings are the same as the one-by-one loop, bit for bit.  Augmentation
+(``transform_pipeline``), resampling and HDF5 IO are out of scope and raise.
+"""
+import wave as _wave
+
+import numpy
+import torch
+
+from ..statserver import StatServer
+
+
+class IdMap:
+    """idmap.py:43-73: ``leftids`` (model ids), ``rightids`` (file ids), ``start`` / ``stop`` in centiseconds or None."""
+
+    def __init__(self, idmap_filename=''):
+        if idmap_filename != '':
+            raise NotImplementedError("IdMap file IO is out of scope; set leftids / rightids / start / stop directly")
+        self.leftids = numpy.empty(0, dtype="|O")
+        self.rightids = numpy.empty(0, dtype="|O")
+        self.start = numpy.empty(0, dtype="|O")
+        self.stop = numpy.empty(0, dtype="|O")
+
+    def validate(self, warn=False):
+        ok = self.leftids.shape == self.rightids.shape == self.start.shape == self.stop.shape
+        return bool(ok and self.leftids.ndim == 1)
+
+
+def read_wav(path, frame_offset=0, num_frames=-1):
+    """PCM wav -> (float32 tensor (n,), sample_rate), scaled like ``torchaudio.load`` (int16 / 32768); first channel."""
+    with _wave.open(path, "rb") as f:
+        rate, width, chans, total = f.getframerate(), f.getsampwidth(), f.getnchannels(), f.getnframes()
+        if width not in (2, 4):
+            raise NotImplementedError("read_wav: only 16- and 32-bit PCM is supported (%s)" % path)
+        frame_offset = min(max(0, int(frame_offset)), total)
+        f.setpos(frame_offset)
+        n = total - frame_offset if num_frames is None or num_frames < 0 else min(int(num_frames), total - frame_offset)
+        raw = f.readframes(n)
+    a = numpy.frombuffer(raw, dtype=numpy.int16 if width == 2 else numpy.int32).reshape(-1, chans)[:, 0]
+    scale = 32768.0 if width == 2 else 2147483648.0
+    return torch.from_numpy(a.astype(numpy.float32) / numpy.float32(scale)), rate
+
+
+class IdMapSet:
+    """xsets.py:368-480 without the augmentation branch: item ``index`` -> (speech, leftid, rightid, start, stop),
+    ``speech`` a (n,) tensor or, with ``sliding_window``, the (n_windows, window_len) unfolded view."""
+
+    def __init__(self, idmap_name, data_path, file_extension, transform_pipeline={}, transform_number=1,
+                 sliding_window=False, window_len=3., window_shift=1.5, sample_rate=16000, min_duration=0.165):
+        if not isinstance(idmap_name, IdMap):
+            raise NotImplementedError("IdMap file IO is out of scope; pass an IdMap object")
+        if len(transform_pipeline):
+            raise NotImplementedError("data augmentation is out of scope of the inference path")
+        self.idmap = idmap_name
+        self.data_path = data_path
+        self.file_extension = file_extension
+        self.len = self.idmap.leftids.shape[0]
+        self.min_duration = min_duration
+        self.sample_rate = sample_rate
+        self.sliding_window = sliding_window
+        self.window_len = int(window_len * self.sample_rate)
+        self.window_shift = int(window_shift * self.sample_rate)
+
+    def __len__(self):
+        return self.len
+
+    def _path(self, index):
+        return f"{self.data_path}/{self.idmap.rightids[index]}.{self.file_extension}"
+
+    def __getitem__(self, index):
+        start = 0 if self.idmap.start[index] is None else int(self.idmap.start[index] * 0.01 * self.sample_rate)
+        if self.idmap.stop[index] is None:
+            # whole file (xsets.py:430-435; note: the file is NOT cut at `start` in this branch, only `duration` is)
+            speech, fs = read_wav(self._path(index))
+            if fs != self.sample_rate:
+                raise NotImplementedError("resampling is out of scope (%d Hz file, %d Hz model)" % (fs, self.sample_rate))
+            duration = int(speech.shape[0] - start)
+        else:
+            duration = int(self.idmap.stop[index] * 0.01 * self.sample_rate) - start
+            if duration <= self.min_duration * self.sample_rate:     # too short: recentre a min_duration window (:443-446)
+                middle = start + duration // 2
+                start = int(max(0, int(middle - (self.min_duration * self.sample_rate / 2))))
+                duration = int(self.min_duration * self.sample_rate)
+            speech, fs = read_wav(self._path(index), frame_offset=start, num_frames=duration)
+            assert fs == self.sample_rate
+        stop = start + duration
+        if self.sliding_window:
+            speech = speech.unfold(0, self.window_len, self.window_shift)
+        return speech, self.idmap.leftids[index], self.idmap.rightids[index], start, stop
+
+
+def extract_embeddings(idmap_name, model_filename, data_root_name, device, batch_size=1, file_extension="wav",
+                       transform_pipeline={}, sliding_window=False, win_duration=3., win_shift=1.5, num_thread=1,
+                       sample_rate=16000, mixed_precision=False, norm_embeddings=True, max_audio_seconds=1200.0):
+    """xvector.py:1796-1916: a ``StatServer`` with one embedding per segment (or per sliding window).
+
+    ``model_filename`` must be an ``Xtractor`` (checkpoint files are out of scope); ``batch_size``, ``num_thread`` and
+    ``mixed_precision`` are accepted and ignored: batches are formed by total audio (``max_audio_seconds``) and the
+    kernels pick their own precision.  ``start`` / ``stop`` follow the reference, including its sliding-window
+    ``stop = start + <number of 100-window chunks of the last file>`` (xvector.py:1897, :1911).
+    """
+    from .. import bulk
+    model = model_filename
+    if isinstance(model, str):
+        raise NotImplementedError("checkpoint files are out of scope; pass an Xtractor")
+    dataset = IdMapSet(idmap_name, data_root_name, file_extension, transform_pipeline, 0, sliding_window, win_duration, win_shift,
+                       sample_rate, min_duration=win_duration)
+    model.eval()
+    model.to(device)
+    waves, modelset, segset, starts, stops = [], [], [], [], []
+    last_chunks = 1
+    for idx in range(len(dataset)):
+        data, mod, seg, start, stop = dataset[idx]
+        if data.dim() == 1:
+            data = data.unsqueeze(0)
+        n = data.shape[0]
+        waves.extend(data[i] for i in range(n))
+        modelset.extend([mod] * n)
+        segset.extend([seg] * n)
+        if sliding_window:
+            starts.extend((numpy.arange(0, n * win_shift, win_shift) * sample_rate + start).tolist())
+            last_chunks = len(range(0, n, max(1, n // max(1, n // 100))))          # len(torch.split(...)) of :1885
+        else:
+            starts.append(start)
+            stops.append(int(data.shape[1]))
+    lengths = numpy.array([int(w.shape[0]) for w in waves], dtype=numpy.int64)
+    order = numpy.argsort(lengths, kind="stable")
+    emb = torch.empty((len(waves), model.embedding_size), dtype=torch.float32)
+    with torch.no_grad():
+        for batch in bulk.make_batches(order.tolist(), lengths, max_audio_seconds, sample_rate=sample_rate):
+            out = model.extract_varlen([waves[i].to(device) for i in batch], norm_embedding=norm_embeddings)
+            emb[torch.as_tensor(batch)] = out.cpu()
+    embeddings = StatServer()
+    embeddings.stat1 = emb.numpy().astype(numpy.float32)
+    embeddings.modelset = numpy.array(modelset).astype('>U')
+    embeddings.segset = numpy.array(segset).astype('>U')
+    embeddings.start = numpy.array(starts).squeeze()
+    embeddings.stop = embeddings.start + (last_chunks if sliding_window else numpy.array(stops).squeeze())
+    embeddings.stat0 = numpy.ones((embeddings.modelset.shape[0], 1))
+    return embeddings

@@ -1,0 +1,92 @@
+"""Feed path: IdMap / IdMapSet / extract_embeddings with the reference's signatures, on wav files
+written by the test.  Segment logic against oracle/feed_ref.py (parity unpinned: see its header); embeddings against
+the packed extraction of the same segments (bit-exact) and the CPU oracle."""
+import os
+import wave
+
+import numpy
+import pytest
+import torch
+
+import sidekit_b200 as sk
+from oracle import extract_ref as R
+from oracle import feed_ref as F
+from sidekit_b200 import synth
+from sidekit_b200.nnet import xsets
+from tests.helpers import rel_l2
+from tests.models import make_xtractor
+
+
+def _write_wavs(tmp_path, lengths):
+    pcm = {}
+    for i, L in enumerate(lengths):
+        x = (synth.synth_wave(1, L, seed=800 + i)[0].numpy() * 32768.0).clip(-32768, 32767).astype(numpy.int16)
+        with wave.open(os.path.join(tmp_path, "f%d.wav" % i), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000)
+            f.writeframes(x.tobytes())
+        pcm["f%d" % i] = x
+    return pcm
+
+
+def _idmap(rows):
+    im = sk.IdMap()
+    im.leftids = numpy.array([r[0] for r in rows], dtype="|O")
+    im.rightids = numpy.array([r[1] for r in rows], dtype="|O")
+    im.start = numpy.array([r[2] for r in rows], dtype="|O")
+    im.stop = numpy.array([r[3] for r in rows], dtype="|O")
+    assert im.validate()
+    return im
+
+
+def test_idmapset_segments_match_oracle(tmp_path):
+    pcm = _write_wavs(str(tmp_path), (64000, 80000, 50000))
+    rows = [("spk0", "f0", None, None), ("spk1", "f1", 100, 450), ("spk1", "f1", 200, 260), ("spk2", "f2", 0, 20), ("spk0", "f0", 50, None)]
+    ds = xsets.IdMapSet(_idmap(rows), str(tmp_path), "wav", sample_rate=16000, min_duration=1.0)
+    assert len(ds) == 5
+    for i, (m, f, a, b) in enumerate(rows):
+        speech, left, right, start, stop = ds[i]
+        seg, ostart, ostop = F.cut_segment(pcm[f], a, b, 16000, 1.0)
+        assert (left, right, start, stop) == (m, f, ostart, ostop)
+        assert numpy.array_equal(speech.numpy(), seg)
+    dsw = xsets.IdMapSet(_idmap(rows[:2]), str(tmp_path), "wav", sliding_window=True, window_len=1.0, window_shift=0.5, min_duration=1.0)
+    w = dsw[1][0]
+    assert numpy.array_equal(w.numpy(), F.windows(F.cut_segment(pcm["f1"], 100, 450, 16000, 1.0)[0], 1.0, 0.5))
+    with pytest.raises(NotImplementedError):
+        xsets.IdMapSet(_idmap(rows), str(tmp_path), "wav", transform_pipeline={"add_noise": {}})
+
+
+@pytest.mark.gpu
+def test_extract_embeddings_from_wav_files(tmp_path):
+    pcm = _write_wavs(str(tmp_path), (64000, 80000, 50000))
+    m = make_xtractor("halfresnet34", 32, 256).cuda()
+    rows = [("spk0", "f0", None, None), ("spk1", "f1", 100, 450), ("spk2", "f2", 0, 20), ("spk1", "f1", 0, None)]
+    ss = sk.nnet.extract_embeddings(_idmap(rows), m, str(tmp_path), torch.device("cuda"), win_duration=1.0)
+    assert ss.validate() and ss.stat1.shape == (4, 256) and ss.stat0.shape == (4, 1)
+    assert list(ss.modelset) == [r[0] for r in rows] and list(ss.segset) == [r[1] for r in rows]
+    segs = [F.cut_segment(pcm[f], a, b, 16000, 1.0) for (_, f, a, b) in rows]
+    ostart, ostop = F.bookkeeping([(None, s[1], s[0].shape[0]) for s in segs], False, 1.0, 1.5)
+    assert numpy.array_equal(ss.start, ostart) and numpy.array_equal(ss.stop, ostop)
+    ref = torch.cat([m.extract_varlen([torch.from_numpy(s[0]).cuda()]) for s in segs]).cpu().numpy()
+    assert numpy.array_equal(ss.stat1, ref)                                   # packed batches == one-by-one, bit for bit
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    cpu = R.forward(sd, torch.from_numpy(segs[2][0]).unsqueeze(0), "halfresnet34")[1]
+    assert rel_l2(torch.from_numpy(ss.stat1[2:3]), cpu) < 1e-3
+    # sliding windows: one embedding per 1 s window every 0.5 s
+    sw = sk.nnet.extract_embeddings(_idmap(rows[:2]), m, str(tmp_path), torch.device("cuda"), sliding_window=True, win_duration=1.0,
+                                    win_shift=0.5)
+    wins = [F.windows(F.cut_segment(pcm[f], a, b, 16000, 1.0)[0], 1.0, 0.5) for (_, f, a, b) in rows[:2]]
+    assert sw.stat1.shape[0] == sum(w.shape[0] for w in wins) == sw.modelset.shape[0]
+    ostart, ostop = F.bookkeeping([(w.shape[0], F.cut_segment(pcm[f], a, b, 16000, 1.0)[1], None) for w, (_, f, a, b) in zip(wins, rows[:2])],
+                                  True, 1.0, 0.5)
+    assert numpy.array_equal(sw.start, ostart) and numpy.array_equal(sw.stop, ostop)
+    ref = m.extract_varlen([torch.from_numpy(w).cuda() for ws in wins for w in ws]).cpu().numpy()
+    assert numpy.array_equal(sw.stat1, ref)
+    # a StatServer from the feed path goes straight into the scorer
+    ndx = sk.Ndx()
+    ndx.modelset, ndx.segset = numpy.unique(ss.modelset), numpy.unique(ss.segset)
+    ndx.trialmask = numpy.ones((ndx.modelset.shape[0], ndx.segset.shape[0]), dtype=bool)
+    en = ss.mean_stat_per_model()
+    te = sk.StatServer.from_embeddings(ss.segset, ss.stat1)
+    te.modelset = te.segset
+    sc = sk.cosine_scoring(en, te, ndx)
+    assert sc.validate() and numpy.isfinite(sc.scoremat).all()

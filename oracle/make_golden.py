@@ -148,6 +148,37 @@ def golden_scoring():
     print("scoring.npz", sorted(out.keys()))
 
 
+def golden_scoring_full():
+    """full_PLDA_scoring (channel subspace G) of the real reference: closed set, scaled, open set."""
+    sidekit = ref_import.import_reference()
+    from sidekit.iv_scoring import PLDA_scoring, full_PLDA_scoring
+    rng = numpy.random.default_rng(2468)
+    D, R, Rc = 16, 8, 5
+    Ne, Nt = 23, 31
+    en_ids = ["m%02d" % i for i in range(Ne)]
+    te_ids = ["s%02d" % i for i in range(Nt)]
+    E, T = rng.standard_normal((Ne, D)), rng.standard_normal((Nt, D))
+    mu = 0.1 * rng.standard_normal(D)
+    F = 0.5 * rng.standard_normal((D, R))
+    G = 0.4 * rng.standard_normal((D, Rc))
+    A = 0.3 * rng.standard_normal((D, D))
+    Sigma = A @ A.T + numpy.eye(D)
+    ndx = sidekit.Ndx()
+    ndx.modelset = numpy.array([en_ids[i] for i in rng.permutation(Ne)[:20]] + ["missing_model"])
+    ndx.segset = numpy.array([te_ids[i] for i in rng.permutation(Nt)[:27]])
+    ndx.trialmask = rng.random((ndx.modelset.shape[0], ndx.segset.shape[0])) < 0.7
+    out = dict(en_ids=numpy.array(en_ids), te_ids=numpy.array(te_ids), E=E, T=T, mu=mu, F=F, G=G, Sigma=Sigma,
+               ndx_models=ndx.modelset, ndx_segs=ndx.segset, trialmask=ndx.trialmask)
+    mk = lambda: (_statserver(sidekit, en_ids, E), _statserver(sidekit, te_ids, T), copy.deepcopy(ndx))
+    for name, sc in (("full", PLDA_scoring(*mk(), mu, F, G, Sigma, full_model=True)),
+                     ("full_sf", full_PLDA_scoring(*mk(), mu, F, G, Sigma, scaling_factor=0.6)),
+                     ("full_open", full_PLDA_scoring(*mk(), mu, F, G, Sigma, p_known=0.25))):
+        out[name + "_modelset"], out[name + "_segset"] = numpy.array(sc.modelset), numpy.array(sc.segset)
+        out[name + "_mask"], out[name + "_mat"] = numpy.array(sc.scoremask), numpy.array(sc.scoremat)
+    numpy.savez_compressed(os.path.join(GOLD, "scoring_full.npz"), **out)
+    print("scoring_full.npz", sorted(out.keys()))
+
+
 def golden_evaltail():
     """PAV / ROCCH / EER / minDCF / Key / z-t-norm outputs of the real reference on seeded scores."""
     sidekit = ref_import.import_reference()
@@ -210,7 +241,9 @@ def golden_evaltail():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["scoring", "extraction", "evaltail"]
+    which = sys.argv[1:] or ["scoring", "scoring_full", "extraction", "evaltail"]
+    if "scoring_full" in which:
+        golden_scoring_full()
     if "scoring" in which:
         golden_scoring()
     if "extraction" in which:

@@ -109,6 +109,39 @@ def fast_plda_scoring(en_ids, E, te_ids, T, ndx_models, ndx_segs, trialmask, mu,
     return models, segs, mask, S
 
 
+def full_plda_scoring(en_ids, E, te_ids, T, ndx_models, ndx_segs, trialmask, mu, F, G, Sigma, p_known=0.0, scaling_factor=1.0):
+    """full_PLDA_scoring, iv_scoring.py:272-368 (speaker subspace F, channel subspace G); loops as in the reference."""
+    E, T = E.astype(numpy.float64), T.astype(numpy.float64)
+    models, segs, mask, ri, ci = check_missing(en_ids, te_ids, ndx_models, ndx_segs, trialmask)
+    E, T = E[ri] - mu, T[ci] - mu
+    invSigma = scipy.linalg.inv(Sigma)
+    I_iv, I_ch, I_spk = numpy.eye(mu.shape[0]), numpy.eye(G.shape[1]), numpy.eye(F.shape[1])
+    A = numpy.linalg.inv(G.T.dot(invSigma * scaling_factor).dot(G) + I_ch)
+    B = F.T.dot(invSigma * scaling_factor).dot(I_iv - G.dot(A).dot(G.T).dot(invSigma * scaling_factor))
+    K = B.dot(F)
+    K1 = scipy.linalg.inv(K + I_spk)
+    K2 = scipy.linalg.inv(2 * K + I_spk)
+    constant = numpy.linalg.slogdet(K2)[1] / 2.0 - numpy.linalg.slogdet(K1)[1]
+    test_tmp, enroll_tmp = B.dot(T.T), B.dot(E.T)
+    S1 = numpy.array([test_tmp[:, j].dot(K1).dot(test_tmp[:, j]) / 2. for j in range(T.shape[0])])
+    S = numpy.zeros((E.shape[0], T.shape[0]))
+    S2 = numpy.empty(E.shape[0])
+    for i in range(E.shape[0]):
+        both = test_tmp + enroll_tmp[:, i:i + 1]
+        S2[i] = enroll_tmp[:, i].dot(K1).dot(enroll_tmp[:, i]) / 2.
+        S[i, :] = numpy.einsum("ij, ji->i", both.T.dot(K2), both) / 2.
+    S += constant - (S1 + S2[:, numpy.newaxis])
+    S *= scaling_factor
+    if p_known != 0:
+        N = S.shape[0]
+        tmp = numpy.exp(S)
+        out = numpy.empty(S.shape)
+        for ii in range(N):
+            out[ii, :] = S[ii, :] - numpy.log(p_known * tmp[~(numpy.arange(N) == ii)].sum(axis=0) / (N - 1) + (1 - p_known))
+        S = out
+    return models, segs, mask, S
+
+
 def two_covariance_scoring(en_ids, E, te_ids, T, ndx_models, ndx_segs, trialmask, W, B):
     """two_covariance_scoring, iv_scoring.py:159-212 (no centring)."""
     E = E.astype(numpy.float64)

@@ -133,10 +133,49 @@ def fast_PLDA_scoring(enroll, test, ndx, mu, F, Sigma, test_uncertainty=None, Vt
     Tc, seg_part = _quadratic_prepare(T, mu, None, Phi)
     S = score_matrix(Ep, Tc, model_part, seg_part, cst=plda_cst, alpha=scaling_factor, passes=0, out_dtype=torch.float64)
     if p_known != 0:
-        # open-set correction (:467-475), vectorised: sum_{k != i} exp(S_kj) = colsum_j - exp(S_ij)
-        N = S.shape[0]
-        tmp = torch.exp(S)
-        S = S - torch.log(p_known * (tmp.sum(dim=0, keepdim=True) - tmp) / (N - 1) + (1 - p_known))
+        S = _open_set(S, p_known)
+    return _finish(clean_ndx, S)
+
+
+def _open_set(S, p_known):
+    """Open-set correction (iv_scoring.py:356-366, :467-475), vectorised: sum_{k != i} exp(S_kj) = colsum_j - exp(S_ij)."""
+    N = S.shape[0]
+    tmp = torch.exp(S)
+    return S - torch.log(p_known * (tmp.sum(dim=0, keepdim=True) - tmp) / (N - 1) + (1 - p_known))
+
+
+def full_PLDA_scoring(enroll, test, ndx, mu, F, G, Sigma, p_known=0.0, scaling_factor=1., check_missing=True):
+    """PLDA with a channel subspace ``G`` (iv_scoring.py:272-368); ``scoremat`` is float64 like the reference.
+
+    The reference projects the i-vectors with ``B`` (speaker space after channel compensation) and loops over the
+    models; expanding ``(e+t)' K2 (e+t)/2 - t' K1 t/2 - e' K1 e/2`` gives ``e' K2 t + e'(K2-K1)e/2 + t'(K2-K1)t/2``,
+    i.e. the same row-term / column-term / GEMM form as the simplified scorer with ``Psi = B' K2 B`` and
+    ``Phi = B' (K2 - K1) B`` (D x D algebra on the host in float64, the trial matrix on the device).  Note that --
+    unlike ``fast_PLDA_scoring`` -- duplicate enrolment models are NOT averaged (the reference has that block
+    commented out, :290-294)."""
+    enroll_copy = copy.deepcopy(enroll)
+    test_copy = copy.deepcopy(test)
+    clean_ndx = _check_missing_model(enroll_copy, test_copy, ndx) if check_missing else ndx
+    invSigma = scipy.linalg.inv(Sigma)
+    I_iv = numpy.eye(mu.shape[0], dtype='float')
+    I_ch = numpy.eye(G.shape[1], dtype='float')
+    I_spk = numpy.eye(F.shape[1], dtype='float')
+    A = numpy.linalg.inv(G.T.dot(invSigma * scaling_factor).dot(G) + I_ch)
+    B = F.T.dot(invSigma * scaling_factor).dot(I_iv - G.dot(A).dot(G.T).dot(invSigma * scaling_factor))
+    K = B.dot(F)
+    K1 = scipy.linalg.inv(K + I_spk)
+    K2 = scipy.linalg.inv(2 * K + I_spk)
+    constant = numpy.linalg.slogdet(K2)[1] / 2.0 - numpy.linalg.slogdet(K1)[1]
+    Psi = B.T.dot(K2).dot(B)
+    Phi = B.T.dot(K2 - K1).dot(B)
+    Phi = 0.5 * (Phi + Phi.T)                      # symmetric up to rounding; the device routine assumes it
+    dev = _device()
+    E, T = _dev32(enroll_copy.stat1, dev), _dev32(test_copy.stat1, dev)
+    Ep, model_part = _quadratic_prepare(E, mu, Psi, Phi)
+    Tc, seg_part = _quadratic_prepare(T, mu, None, Phi)
+    S = score_matrix(Ep, Tc, model_part, seg_part, cst=constant, alpha=scaling_factor, passes=0, out_dtype=torch.float64)
+    if p_known != 0:
+        S = _open_set(S, p_known)
     return _finish(clean_ndx, S)
 
 
@@ -152,7 +191,7 @@ def PLDA_scoring(enroll, test, ndx, mu, F, G, Sigma, test_uncertainty=None, Vtra
     if not full_model:
         return fast_PLDA_scoring(enroll, test, ndx, mu, F, Sigma, test_uncertainty, Vtrans, p_known=p_known,
                                  scaling_factor=scaling_factor, check_missing=True)
-    raise NotImplementedError("full_PLDA_scoring (G != 0) is outside the hot path (SURVEY.md 8f rank 4)")
+    return full_PLDA_scoring(enroll, test, ndx, mu, F, G, Sigma, p_known=p_known, scaling_factor=scaling_factor)
 
 
 def two_covariance_scoring(enroll, test, ndx, W, B, check_missing=True):

@@ -84,6 +84,23 @@ def test_golden_scoring(name):
     _check(sc, ref, 1e-3, ref[3].dtype)
 
 
+@pytest.mark.parametrize("name", ["full", "full_sf", "full_open"])
+def test_golden_full_plda(name):
+    """full_PLDA_scoring (channel subspace G) against the fixture recorded from the real reference."""
+    g = golden("scoring_full.npz")
+    en, te = _ss(g["en_ids"], g["E"]), _ss(g["te_ids"], g["T"])
+    ndx = _ndx(g["ndx_models"], g["ndx_segs"], g["trialmask"])
+    if name == "full":
+        sc = sk.PLDA_scoring(en, te, ndx, g["mu"], g["F"], g["G"], g["Sigma"], full_model=True)
+    elif name == "full_sf":
+        sc = sk.full_PLDA_scoring(en, te, ndx, g["mu"], g["F"], g["G"], g["Sigma"], scaling_factor=0.6)
+    else:
+        sc = sk.full_PLDA_scoring(en, te, ndx, g["mu"], g["F"], g["G"], g["Sigma"], p_known=0.25)
+    ref = (g[name + "_modelset"], g[name + "_segset"], g[name + "_mask"], g[name + "_mat"])
+    _check(sc, ref, 1e-3, ref[3].dtype)
+    assert en.modelset.tolist() == g["en_ids"].tolist()           # deep copies: the caller's objects are untouched
+
+
 @pytest.mark.parametrize("unit_norm", [True, False])
 @pytest.mark.parametrize("Ne,Nt,D", [(1000, 777, 256), (130, 3000, 256), (257, 129, 200)])
 def test_plda_and_cosine_random(Ne, Nt, D, unit_norm):

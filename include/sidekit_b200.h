@@ -109,6 +109,11 @@ int skb_asnorm_stats(const float* X_dev, const float* cohort_dev, int N, int C, 
 int skb_asnorm_apply(const float* X_dev, int N, int D, const float* mean_dev, const float* std_dev, float* out_dev,
                      void* stream);
 
+/* Multi-GPU as-norm: rows [row0, row0 + n_rows) of the normalised matrix; mean_dev / std_dev hold the
+ * statistics of all N embeddings (each rank computes its rows' with skb_asnorm_stats, one all_gather shares them). */
+int skb_asnorm_apply_panel(const float* X_dev, int N, int D, int row0, int n_rows, const float* mean_dev,
+                           const float* std_dev, float* out_dev, int64_t ld_out, void* stream);
+
 /* ---- evaluation tail: host functions, plain host pointers ------------------------------
  * Pool-adjacent-violators, sidekit/bosaris/detplot.py:289-347 (`pavx`): y[n] -> ghat[n] (including the reference's
  * wrap-around write into the last element), bin widths / heights (arrays of n, the first *n_bins entries are used). */

@@ -52,6 +52,7 @@ def _declare(lib):
         "skb_quadratic_prepare": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp]),
         "skb_asnorm_stats": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
         "skb_asnorm_apply": (i32, [vp, i32, i32, vp, vp, vp, vp]),
+        "skb_asnorm_apply_panel": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, i64, vp]),
         "skb_pavx": (i32, [vp, i64, vp, vp, vp, c_i64_p]),
         "skb_rocch": (i32, [vp, i64, vp, i64, vp, vp, c_i64_p]),
         "skb_eer": (i32, [vp, i64, vp, i64, ctypes.POINTER(f64)]),

@@ -105,3 +105,52 @@ def row_panel(n_rows, rank=None, world=None):
     world = w if world is None else world
     per = (n_rows + world - 1) // world
     return min(rank * per, n_rows), min((rank + 1) * per, n_rows)
+
+
+def _asnorm_stats_cuda(X, cohort_normalised, topk):
+    from . import _lib
+    N, D = X.shape
+    mean = torch.empty((N,), dtype=torch.float32, device=X.device)
+    std = torch.empty((N,), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.lib().skb_asnorm_stats(X.data_ptr(), cohort_normalised.data_ptr(), N, cohort_normalised.shape[0], D, int(topk),
+                                               mean.data_ptr(), std.data_ptr(), _lib.stream_ptr()))
+    return mean, std
+
+
+def _asnorm_panel_cuda(X, lo, hi, mean, std):
+    from . import _lib
+    N, D = X.shape
+    out = torch.empty((hi - lo, N), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.lib().skb_asnorm_apply_panel(X.data_ptr(), N, D, lo, hi - lo, mean.data_ptr(), std.data_ptr(), out.data_ptr(),
+                                                     out.stride(0), _lib.stream_ptr()))
+    return out
+
+
+def asnorm_sharded(enrol_xv, cohort_xv, topk=200, stats_fn=_asnorm_stats_cuda, panel_fn=_asnorm_panel_cuda):
+    """Adaptive s-norm across ranks: every rank computes the top-k cohort statistics of ITS row panel,
+    one ``all_gather`` shares the (N,) mean / std vectors (the symmetric formula needs mu_j, sigma_j of every column),
+    then every rank normalises its rows.  Returns ``(row_begin, row_end, panel)`` with ``panel`` the (rows, N) block of
+    the matrix ``asnorm`` returns; the result stays row-sharded.  ``stats_fn`` / ``panel_fn`` are the CUDA routines in
+    production and injectable so the exchange can be tested on CPU."""
+    dist, rank, world = _dist()
+    X = enrol_xv.to(torch.float32).contiguous()
+    coh = torch.nn.functional.normalize(cohort_xv.to(X.device, torch.float32), dim=1).contiguous()
+    N = X.shape[0]
+    lo, hi = row_panel(N, rank, world)
+    per = (N + world - 1) // world
+    mean = torch.zeros((world * per,), dtype=torch.float32, device=X.device)
+    std = torch.ones((world * per,), dtype=torch.float32, device=X.device)
+    if hi > lo:
+        m, s = stats_fn(X[lo:hi].contiguous(), coh, topk)
+        mean[lo:hi], std[lo:hi] = m, s
+    if world > 1:
+        both = torch.stack([mean[rank * per:(rank + 1) * per], std[rank * per:(rank + 1) * per]]).contiguous()
+        gathered = torch.empty((world * 2, per), dtype=torch.float32, device=X.device)
+        dist.all_gather_into_tensor(gathered, both)
+        gathered = gathered.view(world, 2, per)
+        mean, std = gathered[:, 0, :].reshape(-1).contiguous(), gathered[:, 1, :].reshape(-1).contiguous()
+    mean, std = mean[:N].contiguous(), std[:N].contiguous()
+    panel = panel_fn(X, lo, hi, mean, std) if hi > lo else torch.zeros((0, N), dtype=torch.float32, device=X.device)
+    return lo, hi, panel

@@ -758,4 +758,25 @@ int skb_asnorm_apply(const float* X_dev, int N, int D, const float* mean_dev, co
     return score_gemm_general(X_dev, X_dev, N, N, D, ra, ra, 0.f, r, r, 0.f, 1.f, 30.f, 3, 0, out_dev, N, tmp_bytes, st);
 }
 
+// Row panel of the as-norm matrix for the multi-GPU path: the rows [row0, row0 + n_rows) of
+// out[i][j] = 0.5*(S_ij - mean_i)/std_i + 0.5*(S_ij - mean_j)/std_j; the statistics of ALL N embeddings are needed
+// (all-gathered by the caller), the embeddings of the panel's rows are Xrows_dev = X_dev + row0 * D.
+int skb_asnorm_apply_panel(const float* X_dev, int N, int D, int row0, int n_rows, const float* mean_dev, const float* std_dev,
+                           float* out_dev, int64_t ld_out, void* stream) {
+    if (!X_dev || !mean_dev || !std_dev || !out_dev || row0 < 0 || n_rows <= 0 || row0 + n_rows > N || ld_out < N) {
+        set_last_error(__FILE__, __LINE__, "asnorm_apply_panel: bad arguments");
+        return SKB_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t tmp_bytes = (size_t)2 * N * sizeof(float);
+    int rc = ws_ensure(0, tmp_bytes);
+    if (rc) return rc;
+    float* ra = g_ws.tmp;
+    float* r = ra + N;
+    asnorm_terms_kernel<<<(N + 255) / 256, 256, 0, st>>>(mean_dev, std_dev, N, ra, r);
+    g_launches++;
+    return score_gemm_general(X_dev + (size_t)row0 * D, X_dev, n_rows, N, D, ra + row0, ra, 0.f, r + row0, r, 0.f, 1.f, 30.f, 3, 0,
+                              out_dev, ld_out, tmp_bytes, st);
+}
+
 }  // extern "C"

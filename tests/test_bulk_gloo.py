@@ -78,3 +78,51 @@ def test_make_batches_and_row_panels():
     cover = [bulk.row_panel(20000, r, 8) for r in range(8)]
     assert cover[0][0] == 0 and cover[-1][1] == 20000 and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
     assert bulk.halfresnet34_macs(64000) == 9236665216                          # SURVEY.md 8d closed form at 4 s
+
+
+# ----------------------------------------------------------------------------- as-norm exchange (world 2, gloo)
+def _stats_cpu(X, coh, topk):
+    top = torch.topk(X @ coh.T, topk, dim=1)[0]
+    return top.mean(dim=1), top.std(dim=1)
+
+
+def _panel_cpu(X, lo, hi, mean, std):
+    S = X[lo:hi] @ X.T
+    return 0.5 * (S - mean[lo:hi, None]) / std[lo:hi, None] + 0.5 * (S - mean[None, :]) / std[None, :]
+
+
+def _asnorm_inputs():
+    g = torch.Generator().manual_seed(3)
+    X = torch.nn.functional.normalize(torch.randn(45, 24, generator=g), dim=1)
+    return X, torch.randn(260, 24, generator=g)
+
+
+def _asnorm_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X, coh = _asnorm_inputs()
+    lo, hi, panel = bulk.asnorm_sharded(X, coh, topk=200, stats_fn=_stats_cpu, panel_fn=_panel_cpu)
+    q.put((rank, lo, hi, panel.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_asnorm_sharded_world2_matches_full_matrix():
+    from oracle import scoring_ref as S
+    X, coh = _asnorm_inputs()
+    full = S.asnorm(X.numpy(), coh.numpy(), 200)
+    lo, hi, panel = bulk.asnorm_sharded(X, coh, topk=200, stats_fn=_stats_cpu, panel_fn=_panel_cpu)      # single process
+    assert (lo, hi) == (0, 45) and numpy.abs(panel.numpy() - full).max() < 1e-4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_asnorm_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == 45            # contiguous row panels
+    stacked = numpy.concatenate([res[0][3], res[1][3]])
+    assert numpy.abs(stacked - full).max() < 1e-4

@@ -148,3 +148,18 @@ def test_asnorm_golden_and_oracle():
     coh = rng.standard_normal((1500, 256)).astype(numpy.float32)
     out = sk.asnorm(torch.from_numpy(X), torch.from_numpy(coh), None)
     assert numpy.abs(out - S.asnorm(X, coh)).max() < 1e-3
+
+
+def test_asnorm_row_panels_equal_full_matrix():
+    """bulk.asnorm_sharded through the CUDA routines (one process = whole matrix) and two hand-cut row panels."""
+    from sidekit_b200 import bulk
+    g = torch.Generator().manual_seed(12)
+    X = torch.nn.functional.normalize(torch.randn(300, 64, generator=g), dim=1).cuda()
+    coh = torch.randn(500, 64, generator=g).cuda()
+    full = torch.from_numpy(sk.asnorm(X, coh, None)).cuda()
+    lo, hi, panel = bulk.asnorm_sharded(X, coh, topk=200)
+    assert (lo, hi) == (0, 300) and torch.equal(panel, full)
+    mean, std = bulk._asnorm_stats_cuda(X, torch.nn.functional.normalize(coh, dim=1).contiguous(), 200)
+    top = bulk._asnorm_panel_cuda(X, 0, 130, mean, std)
+    bot = bulk._asnorm_panel_cuda(X, 130, 300, mean, std)
+    assert torch.equal(torch.cat([top, bot]), full)               # panels are bit-identical to the one-shot matrix

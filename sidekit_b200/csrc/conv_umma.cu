@@ -11,7 +11,7 @@ namespace skb {
 int conv_pick_ncta(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : 128); }
 int conv_tile_m(int n_cta) { return n_cta == 32 ? 512 : 256; }
 
-template <int N_CTA, int MT, bool BF16>
+template <int N_CTA, int MT, bool BF16, bool FUSED>
 static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     using Cfg = ConvCfg<N_CTA, MT>;
     static bool configured = false;
@@ -21,6 +21,11 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     // traffic, no barrier round trips on the MMA issue path); otherwise streamed through a ring deep enough to
     // cover the L2 latency at the rate the MMAs consume them (the ring gets what the 3-slab A ring leaves).
     p.bias_mma = p.cout <= 256 ? 1 : 0;     // wide layers (TDNN) keep the epilogue bias add: their bias images would not fit
+    // narrow layers keep the SE scale table (n_utt x cout floats) in shared memory: the epilogue's scale rows become
+    // shared-memory reads instead of dependent L2 loads
+    p.scale_smem_bytes = 0;
+    if (FUSED && N_CTA <= 64 && (size_t)p.n_utt * p.cout * 4 <= 32 * 1024) p.scale_smem_bytes = p.n_utt * p.cout * 4;
+    const int scb = p.scale_smem_bytes;
     const int n_it = p.n_pairs;
     const int n_split = p.cout / N_CTA;
     int tps = 1, bst = 1;
@@ -35,14 +40,14 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
             }
         }
         b_stage = (size_t)tps * Cfg::kBStageBytes;
-        const size_t left = kConvSmemBudget - Cfg::fixed_bytes(p.cout, p.bias_mma, 0, 0) - 3 * a_stage;
+        const size_t left = kConvSmemBudget - Cfg::fixed_bytes(p.cout, p.bias_mma, 0, 0, scb) - 3 * a_stage;
         bst = (int)(left / b_stage);
         if (bst > kConvBStages) bst = kConvBStages;
         if (bst < 2) bst = 2;
     }
     p.tps = tps;
     p.b_stages = bst;
-    const size_t fixed = Cfg::fixed_bytes(p.cout, p.bias_mma, bst, tps);
+    const size_t fixed = Cfg::fixed_bytes(p.cout, p.bias_mma, bst, tps, scb);
     int stages = (int)((kConvSmemBudget - fixed) / a_stage);
     if (stages > kConvMaxAStages) stages = kConvMaxAStages;
     if (stages < 2) {
@@ -52,7 +57,7 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     p.a_stages = stages;
     const size_t smem = fixed + (size_t)stages * a_stage;
     if (!configured) {
-        SKB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<N_CTA, MT, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SKB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<N_CTA, MT, BF16, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             227 * 1024));
         configured = true;
     }
@@ -60,7 +65,7 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     p.n_tiles = (n_pix + Cfg::kTileM - 1) / Cfg::kTileM;
     const int n_items = p.n_tiles * (p.cout / N_CTA);
     const int grid = n_items < kNumSMs ? n_items : kNumSMs;      // persistent: one CTA per SM
-    conv_umma_kernel<N_CTA, MT, BF16><<<grid, kConvThreads, smem, st>>>(p);
+    conv_umma_kernel<N_CTA, MT, BF16, FUSED><<<grid, kConvThreads, smem, st>>>(p);
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
@@ -111,11 +116,17 @@ int launch_conv_umma(const ConvParams& p, int n_cta, bool bf16, cudaStream_t st)
         set_last_error(__FILE__, __LINE__, "conv_umma: unsupported shape");
         return SKB_ERR_ARG;
     }
+    const bool fused = p.se_scale != nullptr;
+#define SKB_CONV_CASE(N, M)                                                                                   \
+    case N:                                                                                                   \
+        if (fused) return bf16 ? launch_one<N, M, true, true>(p, st) : launch_one<N, M, false, true>(p, st);  \
+        return bf16 ? launch_one<N, M, true, false>(p, st) : launch_one<N, M, false, false>(p, st);
     switch (n_cta) {
-        case 32: return bf16 ? launch_one<32, 4, true>(p, st) : launch_one<32, 4, false>(p, st);
-        case 64: return bf16 ? launch_one<64, 2, true>(p, st) : launch_one<64, 2, false>(p, st);
-        case 128: return bf16 ? launch_one<128, 2, true>(p, st) : launch_one<128, 2, false>(p, st);
+        SKB_CONV_CASE(32, 4)
+        SKB_CONV_CASE(64, 2)
+        SKB_CONV_CASE(128, 2)
     }
+#undef SKB_CONV_CASE
     set_last_error(__FILE__, __LINE__, "conv_umma: unsupported N tile");
     return SKB_ERR_ARG;
 }

@@ -82,13 +82,13 @@ struct ConvCfg {
     static constexpr int kTileM = 128 * MT;
     // ctrl | bias fp32 [cout] | ones operand (2 planes x 128 rows x 16 B) | bias images (2 planes x cout rows x 16 B) | B | A
     static constexpr int kOnesBytes = 2 * 128 * 16;
-    static size_t fixed_bytes(int cout, int bias_mma, int b_stages, int tps) {
-        return kConvCtrlBytes + (size_t)cout * 4 + kOnesBytes + (bias_mma ? (size_t)cout * 32 : 0) +
+    static size_t fixed_bytes(int cout, int bias_mma, int b_stages, int tps, int scale_bytes = 0) {
+        return kConvCtrlBytes + (size_t)cout * 4 + kOnesBytes + (bias_mma ? (size_t)cout * 32 : 0) + scale_bytes +
                (size_t)b_stages * tps * kBStageBytes;
     }
 };
 
-template <int N_CTA, int MT, bool BF16>
+template <int N_CTA, int MT, bool BF16, bool FUSED>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvParams p) {
     using Cfg = ConvCfg<N_CTA, MT>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     float* bias_s = reinterpret_cast<float*>(smem + kConvCtrlBytes);
     uint8_t* ones_smem = smem + kConvCtrlBytes + (size_t)p.cout * 4;
     uint8_t* biasimg_smem = ones_smem + Cfg::kOnesBytes;          // per N split: [2 planes][N_CTA rows][8 halves]
-    uint8_t* b_smem = biasimg_smem + (p.bias_mma ? (size_t)p.cout * 32 : 0);
+    float* scale_s = reinterpret_cast<float*>(biasimg_smem + (p.bias_mma ? (size_t)p.cout * 32 : 0));   // [n_utt][cout] SE scales
+    uint8_t* b_smem = reinterpret_cast<uint8_t*>(scale_s) + p.scale_smem_bytes;
     const uint32_t b_stage_bytes = (uint32_t)p.tps * Cfg::kBStageBytes;
     uint8_t* a_smem = b_smem + (size_t)p.b_stages * b_stage_bytes;
     const uint32_t a_stage_bytes = (uint32_t)p.rows_pad * (kConvKC / 8) * 16;
@@ -139,6 +140,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (FUSED && p.scale_smem_bytes > 0)
+        for (int i = threadIdx.x; i < p.scale_smem_bytes / 4; i += blockDim.x) scale_s[i] = p.se_scale[i];
     if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -286,6 +289,124 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             __syncwarp();
         }
     } else if (warp >= 4) {
+        if constexpr (N_CTA <= 64) {
+        // ---------------------------------------------------------------- epilogue warps (4..11), narrow layers
+        // Two warps per TMEM lane quadrant, each taking half of the item's MT accumulator tiles.  Per-pixel metadata
+        // and the residual come from HBM / L2 (~1 us away) and depend on each other (pixel -> utterance -> residual
+        // row / scale row); on these layers an item is only ~3 k cycles of MMAs, so that chain -- paid once per item --
+        // was the critical path (profiles/r01c_fused_taps.txt).  Metadata is therefore fetched TWO items ahead, the
+        // residual ONE item ahead, and the SE scale table sits in shared memory.
+        constexpr int MTH = MT / 2;
+        constexpr int NCH = N_CTA / 8;          // 8-channel chunks per pixel (4 or 8): the whole residual is one group
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int mt0 = ((warp - 4) >> 2) * MTH;
+        const size_t plane8 = (size_t)p.out_plane * 8;
+        const size_t rplane8 = (size_t)p.res_plane * 8;
+        const float slope = p.act_slope;
+        auto fetch_meta = [&](int item, int (&bidx)[MTH], int (&opix)[MTH]) {
+            const int tile = item / n_split;
+#pragma unroll
+            for (int mt = 0; mt < MTH; ++mt) {
+                const int pix = p.G + tile * Cfg::kTileM + (mt0 + mt) * 128 + q * 32 + lane;
+                const bool in_range = item < n_items && pix < p.p_end;
+                bidx[mt] = in_range ? __ldg(p.pix_b + (pix - p.G)) : -1;
+                opix[mt] = in_range ? pix : -1;
+                if (p.pix_sub != nullptr) opix[mt] = in_range ? __ldg(p.pix_sub + (pix - p.G)) : -1;
+            }
+        };
+        auto fetch_res = [&](int item, const int (&bidx)[MTH], uint4 (&rv)[MTH][NCH]) {
+            const int tile = item / n_split, n_base = (item - tile * n_split) * N_CTA;
+#pragma unroll
+            for (int mt = 0; mt < MTH; ++mt) {
+                const size_t roff = (size_t)(p.G + tile * Cfg::kTileM + (mt0 + mt) * 128 + q * 32 + lane) * 8;
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    rv[mt][k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (bidx[mt] >= 0) rv[mt][k] = *reinterpret_cast<const uint4*>(p.res + roff + (size_t)((n_base >> 3) + k) * rplane8);
+                }
+            }
+        };
+        int bidx_c[MTH], opix_c[MTH], bidx_n[MTH], opix_n[MTH], bidx_nn[MTH], opix_nn[MTH];
+        uint4 rv_c[MTH][NCH], rv_n[MTH][NCH];
+        fetch_meta(blockIdx.x, bidx_c, opix_c);
+        fetch_meta(blockIdx.x + gridDim.x, bidx_n, opix_n);
+        if (FUSED) fetch_res(blockIdx.x, bidx_c, rv_c);
+        uint32_t n_done = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+            const int tile = item / n_split;
+            const int n_base = (item - tile * n_split) * N_CTA;
+            const int buf = (int)(n_done & 1);
+            if (FUSED) fetch_res(item + gridDim.x, bidx_n, rv_n);          // its metadata arrived during the previous item
+            fetch_meta(item + 2 * gridDim.x, bidx_nn, opix_nn);
+            mbar_wait(&acc_full[buf], (n_done >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < NCH; cc += 2) {
+                const int c0 = cc * 8;
+#pragma unroll
+                for (int mt = 0; mt < MTH; ++mt) {
+                    const bool valid = bidx_c[mt] >= 0;
+                    float4 sc4[4];
+                    if (FUSED && valid) {
+                        if (p.scale_smem_bytes > 0) {
+                            const float4* sp = reinterpret_cast<const float4*>(scale_s + (size_t)bidx_c[mt] * p.cout + n_base + c0);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) sc4[k] = sp[k];
+                        } else {
+                            const float4* sp = reinterpret_cast<const float4*>(p.se_scale + (size_t)bidx_c[mt] * p.cout + n_base + c0);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) sc4[k] = __ldg(sp + k);
+                        }
+                    }
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kAccCols + (mt0 + mt) * N_CTA + c0, v);
+                    if (c0 + 16 >= N_CTA && mt == MTH - 1) {
+                        // accumulator completely read: hand this TMEM buffer back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                    }
+                    if (!p.bias_mma) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += bias_s[n_base + c0 + i];
+                    }
+                    if (FUSED && valid) {
+                        const uint32_t rw[8] = {rv_c[mt][cc].x, rv_c[mt][cc].y, rv_c[mt][cc].z, rv_c[mt][cc].w,
+                                                rv_c[mt][cc + 1].x, rv_c[mt][cc + 1].y, rv_c[mt][cc + 1].z, rv_c[mt][cc + 1].w};
+                        const float scv[16] = {sc4[0].x, sc4[0].y, sc4[0].z, sc4[0].w, sc4[1].x, sc4[1].y, sc4[1].z, sc4[1].w,
+                                               sc4[2].x, sc4[2].y, sc4[2].z, sc4[2].w, sc4[3].x, sc4[3].y, sc4[3].z, sc4[3].w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float2 r2 = unpack2<BF16>(rw[i]);
+                            v[2 * i] = fmaf(v[2 * i], scv[2 * i], r2.x);
+                            v[2 * i + 1] = fmaf(v[2 * i + 1], scv[2 * i + 1], r2.y);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * slope);
+                    if (opix_c[mt] >= 0) {
+                        uint16_t* dst = p.out + (size_t)opix_c[mt] * 8 + (size_t)((n_base + c0) >> 3) * plane8;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint4 o;
+                            o.x = valid ? pack2<BF16>(v[j * 8 + 0], v[j * 8 + 1]) : 0u;
+                            o.y = valid ? pack2<BF16>(v[j * 8 + 2], v[j * 8 + 3]) : 0u;
+                            o.z = valid ? pack2<BF16>(v[j * 8 + 4], v[j * 8 + 5]) : 0u;
+                            o.w = valid ? pack2<BF16>(v[j * 8 + 6], v[j * 8 + 7]) : 0u;
+                            *reinterpret_cast<uint4*>(dst + j * plane8) = o;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < MTH; ++mt) {
+                bidx_c[mt] = bidx_n[mt]; opix_c[mt] = opix_n[mt];
+                bidx_n[mt] = bidx_nn[mt]; opix_n[mt] = opix_nn[mt];
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) rv_c[mt][k] = rv_n[mt][k];
+            }
+        }
+        } else {
         // ---------------------------------------------------------------- epilogue warps (4..11)
         // two warps per TMEM lane quadrant; each takes half of the item's MT accumulator tiles
         constexpr int MTH = MT / 2;
@@ -318,7 +439,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             const size_t plane8 = (size_t)p.out_plane * 8;
             const size_t rplane8 = (size_t)p.res_plane * 8;
             const float slope = p.act_slope;
-            const bool fused = p.se_scale != nullptr;
+            constexpr bool fused = FUSED;
             // Fused SE tail: the residual comes from HBM/L2 (~1 us away).  Fetch it in groups of up to 8 channel chunks per
             // pixel, the first group BEFORE waiting for the accumulator so its latency hides behind the MMAs.
             constexpr int NCH = N_CTA / 8;                 // 8-channel chunks per pixel in this N slice
@@ -394,6 +515,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                     }
                 }
             }
+        }
         }
         tc_fence_before();
     }

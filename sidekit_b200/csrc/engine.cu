@@ -280,7 +280,7 @@ struct Model {
     int att_A = 0, pool_D = 0;
     // head
     float *lin_w = nullptr, *lin_b = nullptr, *be_s = nullptr, *be_t = nullptr, *spk_wn = nullptr;
-    PackedOp p_w1x, p_w1g, p_w2, p_lin, p_spk;   // dense-layer weights packed for the split-precision tcgen05 GEMM
+    PackedOp p_w1x, p_w2;       // attention projections packed for the split-precision tcgen05 GEMM (M = frames)
     // tdnn
     std::vector<ConvW> tdnn;
     std::vector<int> tdnn_k, tdnn_d;
@@ -331,9 +331,7 @@ static int build_margin_head(const WeightMap& w, Model* m) {
         const double inv = 1.0 / std::max(std::sqrt(ss), 1e-12);
         for (int k = 0; k < m->emb; ++k) wn[(size_t)i * m->emb + k] = (float)(sw->p[(size_t)i * m->emb + k] * inv);
     }
-    int rc = dev_upload(wn, &m->spk_wn);
-    if (rc) return rc;
-    return packed_create(m->spk_wn, m->n_spk, m->emb, &m->p_spk, 0);
+    return dev_upload(wn, &m->spk_wn);
 }
 
 static int build_hr34(const WeightMap& w, Model* m) {
@@ -401,10 +399,21 @@ static int build_hr34(const WeightMap& w, Model* m) {
     if ((rc = bn_affine(w, "before_speaker_embedding.bn_be", &s, &t))) return rc;
     if ((rc = upload_f(s, &m->be_s))) return rc;
     if ((rc = upload_f(t, &m->be_t))) return rc;
-    if ((rc = packed_create(m->att_w1x, A, D, &m->p_w1x, 0))) return rc;
-    if ((rc = packed_create(m->att_w1g, A, 2 * D, &m->p_w1g, 0))) return rc;
+    {
+        // K permuted to k' = f * C + c (see gather_pack_kernel): column c * F + f of the Conv1d weight moves to f * C + c
+        const int Cc = 256, Ff = D / Cc;
+        std::vector<float> w1p((size_t)A * D);
+        for (int a = 0; a < A; ++a)
+            for (int c = 0; c < Cc; ++c)
+                for (int f = 0; f < Ff; ++f) w1p[(size_t)a * D + f * Cc + c] = w1x[(size_t)a * D + c * Ff + f];
+        float* tmp = nullptr;
+        if ((rc = dev_upload(w1p, &tmp))) return rc;
+        rc = packed_create(tmp, A, D, &m->p_w1x, 0);
+        cudaDeviceSynchronize();
+        cudaFree(tmp);
+        if (rc) return rc;
+    }
     if ((rc = packed_create(m->att_w2, D, A, &m->p_w2, 0))) return rc;
-    if ((rc = packed_create(m->lin_w, m->emb, 2 * D, &m->p_lin, 0))) return rc;
     return build_margin_head(w, m);
 }
 
@@ -446,7 +455,6 @@ static int build_tdnn(const WeightMap& w, Model* m) {
     m->emb = (int)lw->shape[0];
     if ((rc = upload_raw(lw, &m->lin_w))) return rc;
     if ((rc = upload_raw(lb, &m->lin_b))) return rc;
-    if ((rc = packed_create(m->lin_w, m->emb, 2 * m->pool_D, &m->p_lin, 0))) return rc;
     return build_margin_head(w, m);
 }
 
@@ -461,7 +469,7 @@ static void free_model(Model* m) {
     cudaFree(m->att_w1x); cudaFree(m->att_w1g); cudaFree(m->att_b1); cudaFree(m->att_bn_s); cudaFree(m->att_bn_t);
     cudaFree(m->att_w2); cudaFree(m->att_b2); cudaFree(m->lin_w); cudaFree(m->lin_b); cudaFree(m->be_s); cudaFree(m->be_t);
     cudaFree(m->spk_wn); cudaFree(m->pool_s); cudaFree(m->pool_t);
-    packed_free(&m->p_w1x); packed_free(&m->p_w1g); packed_free(&m->p_w2); packed_free(&m->p_lin); packed_free(&m->p_spk);
+    packed_free(&m->p_w1x); packed_free(&m->p_w2);
 }
 
 // ----------------------------------------------------------------------------- per-batch plan
@@ -529,10 +537,12 @@ struct skb_xtractor {
     struct CachedPlan { Plan plan; DevBuf tab32, tab64, pixmeta; unsigned long long stamp = 0; };
     std::vector<CachedPlan> cache;
     unsigned long long stamp = 0;
-    DevBuf pixmeta, brd, cmvn, cmvn_part;
+    DevBuf pixmeta, brd, cmvn, cmvn_part, skinny_ws;
     DevBuf tab32, tab64, feats, sums, scale, poolX, poolH, poolL, gc, hb, pooled, lin, emb_pre, emb, logits, wave, dbg;
     std::vector<DevBuf> act;      // activation buffers
     std::vector<size_t> act_bytes;
+    PackedOp poolA;               // frames x 2560 packed fp16 operand of the first attention projection
+    int poolA_rows = 0;
     const int* d32 = nullptr;
     const long long* d64 = nullptr;
 };
@@ -919,11 +929,16 @@ static int head_and_logits(skb_xtractor* h, int norm_embedding, float* emb_out, 
     const Model& m = h->m;
     const int B = h->plan.B, D = m.pool_D;
     // before_speaker_embedding: Linear (+ folded BatchNorm1d) (xvector.py:578-581 / :489-491)
-    SKB_TRY(gemm_nt_split((const float*)h->pooled.p, B, 2 * D, m.p_lin, m.lin_b, 1.f, (float*)h->lin.p, m.emb, st));
+    // M = batch size, K = 5120 / 3072: split-K fp32 GEMM (the packed tcgen05 GEMM would run on one or two CTAs)
+    SKB_TRY(h->skinny_ws.ensure(std::max(skinny_gemm_ws_floats(B, m.emb, 2 * D), skinny_gemm_ws_floats(B, std::max(m.n_spk, 1), m.emb)) *
+                                sizeof(float)));
+    SKB_TRY(launch_skinny_gemm((const float*)h->pooled.p, B, 2 * D, m.lin_w, m.emb, m.lin_b, 1.f, (float*)h->lin.p, m.emb,
+                               (float*)h->skinny_ws.p, st));
     SKB_TRY(launch_head_norm((const float*)h->lin.p, m.be_s, m.be_t, B, m.emb, norm_embedding, (float*)h->emb_pre.p, emb_out, st));
     g_launches += 2;
     if (logits_out && m.n_spk > 0) {   // ArcMarginProduct(target=None): s * cos (loss.py:299-310)
-        SKB_TRY(gemm_nt_split(emb_out, B, m.emb, m.p_spk, nullptr, m.margin_s, logits_out, m.n_spk, st));
+        SKB_TRY(launch_skinny_gemm(emb_out, B, m.emb, m.spk_wn, m.n_spk, nullptr, m.margin_s, logits_out, m.n_spk,
+                                   (float*)h->skinny_ws.p, st));
         g_launches++;
     }
     return SKB_OK;
@@ -1010,8 +1025,21 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     ProfScope pool_scope(PROF_POOL, st);
     SKB_TRY(launch_gather_frames(m.bf16, buf(level, cur), L4.plane, L4.C, L4.W, L4.Wp, L4.G, d32 + pl.o_frame_row, F, X, st));
     SKB_TRY(launch_meanstd(X, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, nullptr, nullptr, (float*)h->gc.p, st));
-    SKB_TRY(gemm_nt_split((const float*)h->gc.p, B, 2 * D, m.p_w1g, m.att_b1, 1.f, (float*)h->hb.p, A, st));
-    SKB_TRY(gemm_nt_split(X, F, D, m.p_w1x, nullptr, 1.f, Hh, A, st));
+    SKB_TRY(h->skinny_ws.ensure(skinny_gemm_ws_floats(B, A, 2 * D) * sizeof(float)));
+    SKB_TRY(launch_skinny_gemm((const float*)h->gc.p, B, 2 * D, m.att_w1g, A, m.att_b1, 1.f, (float*)h->hb.p, A, (float*)h->skinny_ws.p, st));
+    if (F > h->poolA_rows) {
+        packed_free(&h->poolA);
+        h->poolA_rows = 0;
+        SKB_TRY(packed_alloc_zero(&h->poolA, F + F / 8 + 128, D, st));
+        h->poolA_rows = h->poolA.rows;
+    }
+    {
+        PackedOp a = h->poolA;                     // view with this batch's frame count
+        a.rows = F;
+        a.rows_pad = (F + 127) / 128 * 128;
+        SKB_TRY(launch_gather_pack(buf(level, cur), L4.plane, L4.C, L4.W, L4.Wp, L4.G, d32 + pl.o_frame_row, F, a.hi, st));
+        SKB_TRY(gemm_packed_a(a, m.p_w1x, nullptr, 1.f, Hh, A, st));
+    }
     SKB_TRY(launch_att_act(Hh, (const float*)h->hb.p, d32 + pl.o_frame_utt, m.att_bn_s, m.att_bn_t, F, A, st));
     SKB_TRY(gemm_nt_split(Hh, F, A, m.p_w2, m.att_b2, 1.f, Lg, D, st));
     SKB_TRY(launch_softmax_pool(X, Lg, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, (float*)h->pooled.p, st));
@@ -1157,10 +1185,11 @@ void skb_xtractor_destroy(skb_xtractor_t* h) {
     free_model(&h->m);
     DevBuf* bufs[] = {&h->tab32, &h->tab64, &h->feats, &h->sums, &h->scale, &h->poolX, &h->poolH, &h->poolL, &h->gc, &h->hb,
                       &h->pooled, &h->lin, &h->emb_pre, &h->emb, &h->logits, &h->wave, &h->dbg, &h->pixmeta, &h->brd, &h->cmvn,
-                      &h->cmvn_part};
+                      &h->cmvn_part, &h->skinny_ws};
     for (auto* b : bufs) b->release();
     for (auto& b : h->act) b.release();
     for (auto& c : h->cache) { c.tab32.release(); c.tab64.release(); c.pixmeta.release(); }
+    packed_free(&h->poolA);
     delete h;
 }
 

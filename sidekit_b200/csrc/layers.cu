@@ -452,6 +452,34 @@ __global__ void gather_frames_kernel(const uint16_t* __restrict__ act, long long
     }
 }
 
+// The same gather as a packed tcgen05 operand (scoring.cu layout [frame / 128][chunk][frame % 128][8] halves) with the
+// K index PERMUTED to k' = f * C + c: eight consecutive k' are eight consecutive channels of one pixel, i.e. exactly
+// one 16-byte unit of the activation planes, so the operand is a straight copy (the weight matrix is packed with the
+// same permutation).  The activations are 16-bit already: hi = the value, lo = 0 (the lo planes are zeroed once).
+__global__ void gather_pack_kernel(const uint16_t* __restrict__ act, long long plane, int C, int W, int Wp, int G,
+                                   const int* __restrict__ frame_row, int n_frames, uint16_t* __restrict__ hi) {
+    const int chunks = C >> 3;                       // per f
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n_frames * W * chunks;
+    if (idx >= total) return;
+    const int fr = (int)(idx % n_frames);            // consecutive threads = consecutive frames: contiguous 16-byte stores
+    const int kc = (int)(idx / n_frames);            // chunk of k': f * chunks + j
+    const int f = kc / chunks, j = kc - f * chunks;
+    const long long pix = (long long)G + (long long)frame_row[fr] * Wp + f;
+    const uint4 a = *reinterpret_cast<const uint4*>(act + ((size_t)j * plane + pix) * 8);
+    const size_t o = (((size_t)(fr >> 7) * (W * chunks) + kc) * 128 + (fr & 127)) * 8;
+    *reinterpret_cast<uint4*>(hi + o) = a;
+}
+
+int launch_gather_pack(const uint16_t* act, long long plane, int C, int W, int Wp, int G, const int* frame_row, int n_frames,
+                       uint16_t* hi, cudaStream_t st) {
+    const long long total = (long long)n_frames * W * (C / 8);
+    if (total == 0) return SKB_OK;
+    gather_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(act, plane, C, W, Wp, G, frame_row, n_frames, hi);
+    SKB_LAUNCH_CHECK(st);
+    return SKB_OK;
+}
+
 int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C, int W, int Wp, int G,
                          const int* frame_row, int n_frames, float* X, cudaStream_t st) {
     const long long total = (long long)n_frames * W * (C / 8);
@@ -469,26 +497,36 @@ int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C,
 // ----------------------------------------------------------------------------- mean / unbiased std over time
 // MeanStdPooling (sidekit/nnet/pooling.py:55-70): out[b] = [mean_t x ; std_t x (ddof=1)].  Optional per-channel
 // affine (s, t) applied as mean' = s*mean + t, std' = |s|*std (folds the TDNN's last BatchNorm).
-__global__ void meanstd_kernel(const float* __restrict__ X, const long long* __restrict__ frame_off,
-                               const int* __restrict__ n_fr, int D, const float* __restrict__ aff_s,
-                               const float* __restrict__ aff_t, float* __restrict__ out) {
+// One CTA = 32 consecutive features x 8 time slices (threadIdx.y); a single pass with double accumulators (sum, sum of
+// squares), the slices combined in slice order: deterministic, and in double as exact as the two-pass formula.
+__global__ void __launch_bounds__(256) meanstd_kernel(const float* __restrict__ X, const long long* __restrict__ frame_off,
+                                                      const int* __restrict__ n_fr, int D, const float* __restrict__ aff_s,
+                                                      const float* __restrict__ aff_t, float* __restrict__ out) {
+    __shared__ double ps[8][32], pss[8][32];
     const int b = blockIdx.y;
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= D) return;
+    const int d = blockIdx.x * 32 + threadIdx.x;
     const int T = n_fr[b];
-    const float* x = X + (size_t)frame_off[b] * D + d;
-    float s = 0.f;
-    for (int t = 0; t < T; ++t) s += x[(size_t)t * D];
-    const float mean = s / (float)T;
-    float v = 0.f;
-    for (int t = 0; t < T; ++t) {
-        const float dlt = x[(size_t)t * D] - mean;
-        v = fmaf(dlt, dlt, v);
+    double s = 0.0, ss = 0.0;
+    if (d < D) {
+        const float* x = X + (size_t)frame_off[b] * D + d;
+        for (int t = threadIdx.y; t < T; t += 8) {
+            const double v = (double)x[(size_t)t * D];
+            s += v;
+            ss = fma(v, v, ss);
+        }
     }
-    float sd = sqrtf(v / (float)(T - 1));
-    float mu = mean;
+    ps[threadIdx.y][threadIdx.x] = s;
+    pss[threadIdx.y][threadIdx.x] = ss;
+    __syncthreads();
+    if (threadIdx.y != 0 || d >= D) return;
+    s = 0.0; ss = 0.0;
+    for (int k = 0; k < 8; ++k) { s += ps[k][threadIdx.x]; ss += pss[k][threadIdx.x]; }
+    const double mean = s / T;
+    const double var = fmax(ss - s * mean, 0.0) / (double)(T - 1);           // unbiased; T == 1 -> NaN like torch.std
+    float sd = (float)sqrt(var);
+    float mu = (float)mean;
     if (aff_s) {
-        mu = aff_s[d] * mean + aff_t[d];
+        mu = aff_s[d] * mu + aff_t[d];
         sd = fabsf(aff_s[d]) * sd;
     }
     out[(size_t)b * 2 * D + d] = mu;
@@ -497,8 +535,8 @@ __global__ void meanstd_kernel(const float* __restrict__ X, const long long* __r
 
 int launch_meanstd(const float* X, const long long* frame_off, const int* n_fr, int B, int D, const float* aff_s,
                    const float* aff_t, float* out, cudaStream_t st) {
-    dim3 grid((D + 127) / 128, B);
-    meanstd_kernel<<<grid, 128, 0, st>>>(X, frame_off, n_fr, D, aff_s, aff_t, out);
+    dim3 grid((D + 31) / 32, B);
+    meanstd_kernel<<<grid, dim3(32, 8), 0, st>>>(X, frame_off, n_fr, D, aff_s, aff_t, out);
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
@@ -526,23 +564,55 @@ int launch_att_act(float* h, const float* hb, const int* frame_utt, const float*
 
 // ----------------------------------------------------------------------------- softmax over time + weighted stats
 // w = softmax_t(logits); mu = sum x w; rh = sqrt(clamp(sum x^2 w - mu^2, 1e-9))  (pooling.py:167-169).
-__global__ void softmax_pool_kernel(const float* __restrict__ X, const float* __restrict__ logit,
-                                    const long long* __restrict__ frame_off, const int* __restrict__ n_fr, int D,
-                                    float* __restrict__ out) {
+// One CTA = 32 consecutive features x 8 time slices; each slice runs an ONLINE softmax (running max with rescaling) over
+// its frames in one pass over X and the logits, and the eight (max, sum e, sum x e, sum x^2 e) partials are merged in
+// slice order.
+__global__ void __launch_bounds__(256) softmax_pool_kernel(const float* __restrict__ X, const float* __restrict__ logit,
+                                                           const long long* __restrict__ frame_off, const int* __restrict__ n_fr, int D,
+                                                           float* __restrict__ out) {
+    __shared__ float pm[8][32], pe[8][32], px[8][32], pxx[8][32];
     const int b = blockIdx.y;
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= D) return;
+    const int d = blockIdx.x * 32 + threadIdx.x;
     const int T = n_fr[b];
-    const size_t base = (size_t)frame_off[b] * D + d;
-    float m = -INFINITY;
-    for (int t = 0; t < T; ++t) m = fmaxf(m, logit[base + (size_t)t * D]);
-    float se = 0.f, sx = 0.f, sxx = 0.f;
-    for (int t = 0; t < T; ++t) {
-        const float e = __expf(logit[base + (size_t)t * D] - m);
-        const float x = X[base + (size_t)t * D];
-        se += e;
-        sx = fmaf(x, e, sx);
-        sxx = fmaf(x * x, e, sxx);
+    float m = -INFINITY, se = 0.f, sx = 0.f, sxx = 0.f;
+    if (d < D) {
+        const size_t base = (size_t)frame_off[b] * D + d;
+        for (int t0 = threadIdx.y; t0 < T; t0 += 32) {
+            float lv[4], xv[4];                            // four frames' loads in flight before the dependent updates
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + 8 * u;
+                lv[u] = t < T ? logit[base + (size_t)t * D] : -INFINITY;
+                xv[u] = t < T ? X[base + (size_t)t * D] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (t0 + 8 * u >= T) break;
+                const float l = lv[u], x = xv[u];
+                if (l > m) {                               // new running max: rescale what has been accumulated
+                    const float r = __expf(m - l);         // exp(-inf) = 0 on the first frame
+                    se *= r; sx *= r; sxx *= r;
+                    m = l;
+                }
+                const float e = __expf(l - m);
+                se += e;
+                sx = fmaf(x, e, sx);
+                sxx = fmaf(x * x, e, sxx);
+            }
+        }
+    }
+    pm[threadIdx.y][threadIdx.x] = m; pe[threadIdx.y][threadIdx.x] = se;
+    px[threadIdx.y][threadIdx.x] = sx; pxx[threadIdx.y][threadIdx.x] = sxx;
+    __syncthreads();
+    if (threadIdx.y != 0 || d >= D) return;
+    float gm = -INFINITY;
+    for (int k = 0; k < 8; ++k) gm = fmaxf(gm, pm[k][threadIdx.x]);
+    se = 0.f; sx = 0.f; sxx = 0.f;
+    for (int k = 0; k < 8; ++k) {
+        const float r = __expf(pm[k][threadIdx.x] - gm);   // empty slices (T < 8): exp(-inf) = 0
+        se = fmaf(pe[k][threadIdx.x], r, se);
+        sx = fmaf(px[k][threadIdx.x], r, sx);
+        sxx = fmaf(pxx[k][threadIdx.x], r, sxx);
     }
     const float mu = sx / se;
     const float var = sxx / se - mu * mu;
@@ -552,8 +622,8 @@ __global__ void softmax_pool_kernel(const float* __restrict__ X, const float* __
 
 int launch_softmax_pool(const float* X, const float* logit, const long long* frame_off, const int* n_fr, int B, int D,
                         float* out, cudaStream_t st) {
-    dim3 grid((D + 127) / 128, B);
-    softmax_pool_kernel<<<grid, 128, 0, st>>>(X, logit, frame_off, n_fr, D, out);
+    dim3 grid((D + 31) / 32, B);
+    softmax_pool_kernel<<<grid, dim3(32, 8), 0, st>>>(X, logit, frame_off, n_fr, D, out);
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
@@ -606,9 +676,11 @@ int launch_head_norm(const float* x, const float* aff_s, const float* aff_t, int
 // C[m][n] = alpha * sum_k A[m][k] * B[n][k] + bias[n];  64x64 tile, 16-deep K slices, 4x4 register micro-tiles.
 // Used for the small dense layers (attention projections, embedding and margin heads), which are
 // < 0.5 % of the network's FLOPs and need fp32 inputs for the softmax logits.
+// With gridDim.z > 1 the K range is split into slices of `k_slice` and slice z writes its partial tile to
+// C + z * M * ldc (no bias / alpha): splitk_reduce_kernel adds the slices in order.
 __global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                        float* __restrict__ C, const float* __restrict__ bias, int M, int N,
-                                                       int K, int lda, int ldb, int ldc, float alpha) {
+                                                       int K, int lda, int ldb, int ldc, float alpha, int k_slice) {
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -620,7 +692,14 @@ __global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const int lr = threadIdx.x >> 2;          // 0..63 row of the tile
     const int lk = (threadIdx.x & 3) * 4;     // 0,4,8,12
-    for (int k0 = 0; k0 < K; k0 += 16) {
+    const int k_begin = blockIdx.z * k_slice;
+    if (gridDim.z > 1) {
+        K = min(K, k_begin + k_slice);
+        C += (size_t)blockIdx.z * M * ldc;
+        bias = nullptr;
+        alpha = 1.f;
+    }
+    for (int k0 = k_begin; k0 < K; k0 += 16) {
         {
             const int m = m0 + lr, n = n0 + lr;
 #pragma unroll
@@ -661,7 +740,45 @@ int launch_sgemm_nt(const float* A, const float* B, float* C, const float* bias,
                     int ldc, float alpha, cudaStream_t st) {
     if (M == 0 || N == 0) return SKB_OK;
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc, alpha);
+    sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc, alpha, K);
+    SKB_LAUNCH_CHECK(st);
+    return SKB_OK;
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int n_slices, int M, int N, const float* __restrict__ bias,
+                                     float alpha, float* __restrict__ C, int ldc) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * N) return;
+    const int m = idx / N, n = idx - m * N;
+    float a = 0.f;
+    for (int z = 0; z < n_slices; ++z) a += part[((size_t)z * M + m) * N + n];          // fixed order: deterministic
+    C[(size_t)m * ldc + n] = alpha * a + (bias ? bias[n] : 0.f);
+}
+
+// Skinny dense layer C[m][n] = alpha * sum_k A[m][k] W[n][k] + bias[n] for M = batch size (<= a few hundred rows) and
+// large K (the 5120-wide pooled statistics): exact fp32 FMAs, K split over enough CTAs to fill the GPU, ordered
+// reduction.  `ws` needs n_slices * M * N floats (skinny_gemm_ws_floats).
+static int skinny_slices(int M, int N, int K) {
+    const int tiles = ((M + 63) / 64) * ((N + 63) / 64);
+    int z = (2 * kNumSMs + tiles - 1) / tiles;
+    const int max_z = (K + 63) / 64;
+    return z < 1 ? 1 : (z > max_z ? max_z : z);
+}
+size_t skinny_gemm_ws_floats(int M, int N, int K) { return (size_t)skinny_slices(M, N, K) * M * N; }
+
+int launch_skinny_gemm(const float* A, int M, int K, const float* W, int N, const float* bias, float alpha, float* C, int ldc,
+                       float* ws, cudaStream_t st) {
+    if (M == 0 || N == 0) return SKB_OK;
+    const int z = skinny_slices(M, N, K);
+    const int k_slice = ((K + z - 1) / z + 15) / 16 * 16;
+    const int zz = (K + k_slice - 1) / k_slice;
+    dim3 grid((N + 63) / 64, (M + 63) / 64, zz);
+    if (zz == 1) {
+        sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, W, C, bias, M, N, K, K, K, ldc, alpha, K);
+    } else {
+        sgemm_nt_kernel<<<grid, 256, 0, st>>>(A, W, ws, nullptr, M, N, K, K, K, N, 1.f, k_slice);
+        splitk_reduce_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(ws, zz, M, N, bias, alpha, C, ldc);
+    }
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }

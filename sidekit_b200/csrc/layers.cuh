@@ -30,6 +30,8 @@ int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, lon
                     const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st);
 int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C, int W, int Wp, int G,
                          const int* frame_row, int n_frames, float* X, cudaStream_t st);
+int launch_gather_pack(const uint16_t* act, long long plane, int C, int W, int Wp, int G, const int* frame_row, int n_frames,
+                       uint16_t* hi, cudaStream_t st);
 int launch_meanstd(const float* X, const long long* frame_off, const int* n_fr, int B, int D, const float* aff_s,
                    const float* aff_t, float* out, cudaStream_t st);
 int launch_att_act(float* h, const float* hb, const int* frame_utt, const float* bn_s, const float* bn_t, int n_frames,
@@ -40,6 +42,9 @@ int launch_head_norm(const float* x, const float* aff_s, const float* aff_t, int
                      float* emb_pre, float* emb, cudaStream_t st);
 int launch_sgemm_nt(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
                     int ldc, float alpha, cudaStream_t st);
+size_t skinny_gemm_ws_floats(int M, int N, int K);
+int launch_skinny_gemm(const float* A, int M, int K, const float* W, int N, const float* bias, float alpha, float* C, int ldc,
+                       float* ws, cudaStream_t st);
 int launch_pack_frames(bool bf16, const float* X, int C_src, int C_dst, int n_rows, const int* row_src, uint16_t* out,
                        long long plane, int G, cudaStream_t st);
 
@@ -55,6 +60,9 @@ int packed_create(const float* X_dev, int rows, int D, PackedOp* op, cudaStream_
 void packed_free(PackedOp* op);
 int gemm_nt_split(const float* A_dev, int M, int K, const PackedOp& W, const float* bias, float alpha, float* C, int ldc,
                   cudaStream_t st);
+// same with an A operand that is already packed (hi planes written by the caller, lo planes zero, scale exponent 0)
+int packed_alloc_zero(PackedOp* op, int rows, int D, cudaStream_t st);
+int gemm_packed_a(const PackedOp& A, const PackedOp& W, const float* bias, float alpha, float* C, int ldc, cudaStream_t st);
 
 // conv_umma.cu
 int launch_conv_umma(const ConvParams& p, int n_cta, bool bf16, cudaStream_t st);

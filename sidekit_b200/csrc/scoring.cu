@@ -556,6 +556,20 @@ int gemm_nt_split(const float* A_dev, int M, int K, const PackedOp& W, const flo
     return gemm_packed(a, W, nullptr, nullptr, alpha, nullptr, bias, 0.f, 1.f, 1.f, 3, 0, C, ldc, st);
 }
 
+// An operand whose hi planes the caller fills itself (16-bit activations gathered straight into the packed layout):
+// everything zeroed, so lo = 0 and the scale exponent is 0.
+int packed_alloc_zero(PackedOp* op, int rows, int D, cudaStream_t st) {
+    int rc = packed_alloc(op, rows, D);
+    if (rc) return rc;
+    SKB_CUDA_CHECK(cudaMemsetAsync(op->hi, 0, 2 * (size_t)op->Dp * op->rows_pad * sizeof(uint16_t), st));
+    SKB_CUDA_CHECK(cudaMemsetAsync(op->stats, 0, 2 * sizeof(unsigned) + sizeof(int), st));
+    return SKB_OK;
+}
+
+int gemm_packed_a(const PackedOp& A, const PackedOp& W, const float* bias, float alpha, float* C, int ldc, cudaStream_t st) {
+    return gemm_packed(A, W, nullptr, nullptr, alpha, nullptr, bias, 0.f, 1.f, 1.f, 3, 0, C, ldc, st);
+}
+
 // out = acc * (ra_i + ca_j + a0) + rq_scale * (r_i + q_j) + c0 from fp32 row-major operands
 static int score_gemm_general(const float* E, const float* T, int Ne, int Nt, int D, const float* ra, const float* ca, float a0,
                               const float* r, const float* q, float c0, float rq_scale, float abs_alpha_for_auto, int passes, int out_f64,

@@ -249,13 +249,8 @@ def run_ours(args):
         if dist_on:                       # the one collective of the path: embeddings all-gathered over NVLink
             dist.all_gather_into_tensor(gathered[0], emb)
 
-    def step_e2e(i):
-        pinned, _, lengths = batches[i % n_rot]
-        emb = model.extract_packed(pinned, lengths)    # H2D + forward + D2H inside the native call
-        return emb
-
     with torch.no_grad():
-        for i in range(max(3, args.warmup)):
+        for i in range(max(3, args.warmup, n_rot)):      # every rotating batch once: its geometry plan is built (and cached) here
             step_dev(i)
         sampler = ClockSampler(local)
         sampler.start()
@@ -263,9 +258,11 @@ def run_ours(args):
         ms = timed(step_dev, args.steps, dist_on)
         launches = lib.skb_kernel_launches() - l0
         clocks = sampler.stop()
-        for i in range(2):
-            step_e2e(i)
-        ms_e2e = timed(step_e2e, args.steps, dist_on)
+        # end to end: the public bulk call on pinned HOST batches -- every step's waveforms cross PCIe inside the timed
+        # region (overlapped with the previous step's compute on a second stream) and its embeddings come back to the host
+        host_batches = [(batches[i % n_rot][0], batches[i % n_rot][2]) for i in range(args.steps)]
+        model.extract_stream(host_batches[:n_rot])
+        ms_e2e = timed(lambda i: model.extract_stream(host_batches) if i == 0 else None, 1, dist_on)
         # per-category device time (separate pass with event brackets) for the roofline of the dominant kernel
         lib.skb_profile_enable(1)
         for i in range(args.steps):
@@ -308,7 +305,7 @@ def run_ours(args):
             v, sample = cpu_reference_extraction(15.0, cores)
             cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample}
         line = {"metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(3, args.warmup, n_rot), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": "HalfResNet34 x-vector extraction (256-d, random init), %d utterances 2-20 s per GPU per step, "
                                        "length-bucketed packed batch (BASELINE config 4 shard shape)" % args.utts,

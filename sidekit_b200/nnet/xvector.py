@@ -226,6 +226,49 @@ class Xtractor(torch.nn.Module):
         logits, emb = self._run(flat, [int(v) for v in lengths], norm_embedding, want_logits)
         return (logits, emb) if want_logits else emb
 
+    def extract_stream(self, batches, norm_embedding=True):
+        """Extension for bulk extraction from HOST memory with copy / compute overlap: ``batches`` is a sequence of
+        ``(flat, lengths)`` pairs as for ``extract_packed`` (``flat`` ideally pinned).  The waveforms of batch i+1 travel
+        over PCIe on a second stream while batch i is being embedded (two device staging buffers, events both ways);
+        the embeddings come back into one pinned host tensor.  Returns a list of (n_i, E) host tensors (views)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("sidekit_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        batches = list(batches)
+        device = torch.device("cuda", torch.cuda.current_device())
+        compute = torch.cuda.current_stream(device)
+        if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != device:
+            self._copy_stream = torch.cuda.Stream(device)
+            self._stage = [None, None]
+            self._out_host = None
+        copy_s = self._copy_stream
+        total = sum(len(l) for _, l in batches)
+        if self._out_host is None or self._out_host.shape[0] < total:
+            self._out_host = torch.empty((total, self.embedding_size), dtype=torch.float32, pin_memory=True)
+        free_ev = [None, None]
+        outs, row = [], 0
+        for i, (flat, lengths) in enumerate(batches):
+            k, n = i % 2, flat.numel()
+            if self._stage[k] is None or self._stage[k].numel() < n:
+                compute.synchronize()                              # (re)allocation: nothing in flight may still use the old buffer
+                copy_s.synchronize()
+                self._stage[k] = torch.empty((n + n // 8,), dtype=torch.float32, device=device)
+            with torch.cuda.stream(copy_s):
+                if free_ev[k] is not None:
+                    copy_s.wait_event(free_ev[k])                  # the forward that read this staging buffer is done
+                self._stage[k][:n].copy_(flat.reshape(-1), non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_s)
+            compute.wait_event(ready)
+            _, emb = self._run(self._stage[k][:n], [int(v) for v in lengths], norm_embedding, want_logits=False)
+            free_ev[k] = torch.cuda.Event()
+            free_ev[k].record(compute)
+            dst = self._out_host[row:row + emb.shape[0]]
+            dst.copy_(emb, non_blocking=True)
+            outs.append(dst)
+            row += emb.shape[0]
+        compute.synchronize()
+        return outs
+
     def _frontend(self, x):
         B, L = x.shape
         if not x.is_cuda:

@@ -148,6 +148,21 @@ def test_experimental_fused_tap_kernel_parity():
     assert out.returncode == 0 and "fused-tap ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_extract_stream_overlapped_copies_equal_packed_calls(hr34):
+    """extract_stream (H2D of batch i+1 overlapped with the forward of batch i) == extract_packed batch by batch."""
+    m, _ = hr34
+    batches = []
+    for i, lens in enumerate(((16000, 9000), (20321, 16000, 12345), (8000,), (30000, 11111), (9000, 16000))):
+        ws = [synth.synth_wave(1, L, seed=950 + 10 * i + j)[0] for j, L in enumerate(lens)]
+        batches.append((torch.cat(ws).pin_memory(), list(lens)))
+    outs = m.extract_stream(batches)
+    for (flat, lens), o in zip(batches, outs):
+        assert not o.is_cuda and torch.equal(o, m.extract_packed(flat.cuda(), lens).cpu())
+    again = m.extract_stream(batches[::-1])                       # staging buffers are reused, other order
+    for (flat, lens), o in zip(batches[::-1], again):
+        assert torch.equal(o, m.extract_packed(flat.cuda(), lens).cpu())
+
+
 def test_host_buffer_entry_point(hr34):
     m, _ = hr34
     x = synth.synth_wave(3, 16000, seed=7)

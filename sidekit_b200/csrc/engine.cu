@@ -756,8 +756,8 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
     if ((rc = h->cmvn.ensure((size_t)B * m.fe.n_out * sizeof(float2)))) return rc;
     if ((rc = h->cmvn_part.ensure(frontend_cmvn_scratch_bytes(m.fe, B, pl.t_max)))) return rc;
     const int D = m.pool_D;
-    if ((rc = h->poolX.ensure((size_t)pl.pool_frames * D * sizeof(float)))) return rc;
     if (m.archi == SKB_ARCHI_HALFRESNET34) {
+        if ((rc = h->poolX.ensure((size_t)pl.pool_frames * D * sizeof(float)))) return rc;
         if ((rc = h->poolH.ensure((size_t)pl.pool_frames * m.att_A * sizeof(float)))) return rc;
         if ((rc = h->poolL.ensure((size_t)pl.pool_frames * D * sizeof(float)))) return rc;
         if ((rc = h->gc.ensure((size_t)B * 2 * D * sizeof(float)))) return rc;
@@ -1089,12 +1089,13 @@ static int forward_tdnn(skb_xtractor* h, const float* wave, int norm_embedding, 
         }
     }
     const Level& L5 = pl.lv[5];
-    const int D = m.pool_D, F = pl.pool_frames;
-    float* X = (float*)h->poolX.p;
+    const int D = m.pool_D;
     ProfScope pool_scope(PROF_POOL, st);
-    SKB_TRY(launch_gather_frames(m.bf16, (const uint16_t*)h->act[5].p, L5.plane, L5.C, 1, 1, L5.G, d32 + pl.o_frame_row, F, X, st));
-    SKB_TRY(launch_meanstd(X, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, m.pool_s, m.pool_t, (float*)h->pooled.p, st));
-    g_launches += 2;
+    // mean / unbiased std over the valid frames of each utterance, read straight from the 16-bit planes (W == 1: a pixel is
+    // a frame; the first T - 14 rows of an utterance are its valid output frames)
+    SKB_TRY(launch_meanstd_planes(m.bf16, (const uint16_t*)h->act[5].p, L5.plane, L5.G, d32 + L5.o_utt_row0, d32 + pl.o_pool_nfr, B, D,
+                                  m.pool_s, m.pool_t, (float*)h->pooled.p, st));
+    g_launches += 1;
     if (stop && !strcmp(stop, "pooled")) {
         *per_utt = 2 * D;
         SKB_CUDA_CHECK(cudaMemcpyAsync(dbg_out, h->pooled.p, (size_t)B * 2 * D * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -32,6 +32,8 @@ struct FrontendParams {
     const float* dct;         // [n_mels][n_out] or nullptr (log-Mel)
     int n_mels, n_out;
     int hop, win;
+    int n_w;                  // number of (concatenated) mel filter weights
+    int dct_smem_off;         // offset (in floats, multiple of 4) of the DCT matrix inside the kernel's shared memory
     float preemph;
 };
 
@@ -98,13 +100,23 @@ __device__ __forceinline__ int rev_index<1024>(int k) {    // 8 x 8 x 8 x 2: k =
 // shared memory and the passes are separated by __syncwarp only, so the WPC warps of a CTA never wait for each other
 // (the first version used 64 threads per frame and 8 CTA-wide barriers per frame, and was barrier-stall-bound).
 template <int NC, int WPC>
-__global__ void __launch_bounds__(WPC * 32, 1024 / (WPC * 32)) frontend_kernel(const FrontendParams p, int frames_per_cta) {
+__global__ void __launch_bounds__(WPC * 32, (1024 / (WPC * 32)) > 0 ? 1024 / (WPC * 32) : 1) frontend_kernel(const FrontendParams p, int frames_per_cta) {
     constexpr int ZS = NC + NC / 8 + 8;         // padded complex points per frame buffer
     constexpr int NB = NC / 8;                  // butterflies per radix-8 stage
+    // Every table a frame touches lives in shared memory (twiddles, window, sparse mel filterbank, DCT): read through
+    // L1 / L2 they were 52 KB per frame on the MFCC front-end, 2.8 GB of L2 reads for 0.38 GB of audio, and the kernel's
+    // largest stall (profiles/r01c_ncu_frontend_mfcc_before.txt).
     extern __shared__ __align__(16) uint8_t fsm[];
     float2* tw = reinterpret_cast<float2*>(fsm);                 // [NC]
-    float2* zall = tw + NC;                                      // [WPC][ZS]
+    float2* twf = tw + NC;                                       // [NC + 1] (+1 pad)
+    float2* zall = twf + NC + 2;                                 // [WPC][ZS]
     float* melall = reinterpret_cast<float*>(zall + WPC * ZS);   // [WPC][n_mels]
+    float* s_win = melall + WPC * p.n_mels;                      // [win]
+    float* s_melw = s_win + p.win;                               // [n_w]
+    int* s_lo = reinterpret_cast<int*>(s_melw + p.n_w);          // [n_mels] x 3: first bin, count, weight offset
+    int* s_cnt = s_lo + p.n_mels;
+    int* s_ofs = s_cnt + p.n_mels;
+    float* s_dct = reinterpret_cast<float*>(fsm) + p.dct_smem_off;   // [n_mels][n_out], 16-byte aligned, or unused
     const int b = blockIdx.y;
     const int T = p.n_frames[b];
     const int t_begin = blockIdx.x * frames_per_cta;
@@ -112,6 +124,12 @@ __global__ void __launch_bounds__(WPC * 32, 1024 / (WPC * 32)) frontend_kernel(c
     const int t_end = min(T, t_begin + frames_per_cta);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < NC; i += blockDim.x) tw[i] = p.tw_half[i];
+    for (int i = threadIdx.x; i <= NC; i += blockDim.x) twf[i] = p.tw_full[i];
+    for (int i = threadIdx.x; i < p.win; i += blockDim.x) s_win[i] = p.window[i];
+    for (int i = threadIdx.x; i < p.n_w; i += blockDim.x) s_melw[i] = p.mel_w[i];
+    for (int i = threadIdx.x; i < p.n_mels; i += blockDim.x) { s_lo[i] = p.mel_lo[i]; s_cnt[i] = p.mel_cnt[i]; s_ofs[i] = p.mel_ofs[i]; }
+    if (p.dct != nullptr)
+        for (int i = threadIdx.x; i < p.n_mels * p.n_out; i += blockDim.x) s_dct[i] = p.dct[i];
     __syncthreads();
     const float* x = p.wave + p.wave_off[b];
     const int L = p.wave_len[b];
@@ -133,7 +151,7 @@ __global__ void __launch_bounds__(WPC * 32, 1024 / (WPC * 32)) frontend_kernel(c
                     if (i >= L) i = 2 * (L - 1) - i;
                     const float cur = __ldg(x + i);
                     const float prev = __ldg(x + (i == 0 ? 1 : i - 1));
-                    val = (cur - p.preemph * prev) * __ldg(p.window + n);
+                    val = (cur - p.preemph * prev) * s_win[n];
                 }
                 v[e] = val;
             }
@@ -172,7 +190,7 @@ __global__ void __launch_bounds__(WPC * 32, 1024 / (WPC * 32)) frontend_kernel(c
                 const float2 zr = z[zp(rev_index<NC>((NC - k) & (NC - 1)))];
                 const float2 zc = make_float2(zr.x, -zr.y);
                 const float2 s = cadd(zk, zc), d = csub(zk, zc);
-                const float2 wd = cmul(__ldg(p.tw_full + k), d);      // e^{-2 pi i k / n_fft} (Z[k] - conj Z[N-k])
+                const float2 wd = cmul(twf[k], d);                    // e^{-2 pi i k / n_fft} (Z[k] - conj Z[N-k])
                 const float re = 0.5f * (s.x + wd.y);                   // (-i/2) wd = (wd.y - i wd.x) / 2
                 const float im = 0.5f * (s.y - wd.x);
                 pw[c] = re * re + im * im;
@@ -188,20 +206,38 @@ __global__ void __launch_bounds__(WPC * 32, 1024 / (WPC * 32)) frontend_kernel(c
         __syncwarp();
         float* dst = p.out + (size_t)(p.feat_off[b] + frame) * p.n_out;
         for (int m = lane; m < p.n_mels; m += 32) {
-            const int lo = p.mel_lo[m], c = p.mel_cnt[m];
-            const float* w = p.mel_w + p.mel_ofs[m];
+            const int lo = s_lo[m], c = s_cnt[m];
+            const float* w = s_melw + s_ofs[m];
             float acc = 0.f;
-            for (int i = 0; i < c; ++i) acc = fmaf(pwr[lo + i], __ldg(w + i), acc);
+            for (int i = 0; i < c; ++i) acc = fmaf(pwr[lo + i], w[i], acc);
             const float lm = logf(acc + 1e-6f);
             if (p.dct == nullptr) dst[m] = lm;
             else mel[m] = lm;
         }
         if (p.dct != nullptr) {
             __syncwarp();
-            for (int c = lane; c < p.n_out; c += 32) {
-                float acc = 0.f;
-                for (int m = 0; m < p.n_mels; ++m) acc = fmaf(mel[m], __ldg(p.dct + m * p.n_out + c), acc);
-                dst[c] = acc;
+            // lane l computes the four consecutive outputs 4l .. 4l+3: one 16-byte load of a DCT row per mel bin (rows are
+            // 16-byte aligned when n_out is a multiple of 4), the log-Mel value broadcast from shared memory
+            if ((p.n_out & 3) == 0) {
+                const int c4 = lane * 4;
+                if (c4 < p.n_out) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int m = 0; m < p.n_mels; ++m) {
+                        const float lm = mel[m];
+                        const float4 d = *reinterpret_cast<const float4*>(s_dct + (size_t)m * p.n_out + c4);
+                        acc.x = fmaf(lm, d.x, acc.x); acc.y = fmaf(lm, d.y, acc.y);
+                        acc.z = fmaf(lm, d.z, acc.z); acc.w = fmaf(lm, d.w, acc.w);
+                    }
+                    *reinterpret_cast<float4*>(dst + c4) = acc;
+                }
+                if (p.n_out > 128) {      // (never: frontend_launch rejects it)
+                }
+            } else {
+                for (int c = lane; c < p.n_out; c += 32) {
+                    float acc = 0.f;
+                    for (int m = 0; m < p.n_mels; ++m) acc = fmaf(mel[m], s_dct[m * p.n_out + c], acc);
+                    dst[c] = acc;
+                }
             }
         }
         __syncwarp();     // the next frame's fill overwrites z / pwr / mel
@@ -293,6 +329,7 @@ int frontend_consts_create(FrontendConsts* fc, int n_fft, int win, int hop, int 
         for (int k = 0; k < cnt[m]; ++k) w.push_back(fb[(size_t)(lo[m] + k) * n_mels + m]);
     }
     if (w.empty()) w.push_back(0.f);
+    fc->n_w = (int)w.size();
     SKB_CUDA_CHECK(cudaMalloc(&fc->window, win * sizeof(float)));
     SKB_CUDA_CHECK(cudaMemcpy(fc->window, window, win * sizeof(float), cudaMemcpyHostToDevice));
     SKB_CUDA_CHECK(cudaMalloc(&fc->tw_half, NC * sizeof(float2)));
@@ -338,17 +375,45 @@ int frontend_launch(const FrontendConsts& fc, const float* wave, const long long
         set_last_error(__FILE__, __LINE__, "front-end: more than 128 output coefficients");
         return SKB_ERR_ARG;
     }
+    p.n_w = fc.n_w;
+    auto smem_bytes = [&](int NC, int WPC, int* dct_off) {
+        size_t floats = 2 * (size_t)NC + 2 * ((size_t)NC + 2) + 2 * (size_t)WPC * (NC + NC / 8 + 8) + (size_t)WPC * fc.n_mels + fc.win + fc.n_w +
+                        3 * (size_t)fc.n_mels;
+        floats = (floats + 3) / 4 * 4;
+        *dct_off = (int)floats;
+        if (fc.dct) floats += (size_t)fc.n_mels * fc.n_out;
+        return floats * sizeof(float);
+    };
     if (fc.n_fft == 1024) {
         constexpr int NC = 512, WPC = 8;
         const int frames_per_cta = 4 * WPC;
         dim3 grid((t_max + frames_per_cta - 1) / frames_per_cta, B);
-        const size_t smem = NC * sizeof(float2) + WPC * (NC + NC / 8 + 8) * sizeof(float2) + WPC * fc.n_mels * sizeof(float);
+        const size_t smem = smem_bytes(NC, WPC, &p.dct_smem_off);
+        static bool configured = false;
+        if (!configured) {
+            SKB_CUDA_CHECK(cudaFuncSetAttribute(frontend_kernel<NC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            configured = true;
+        }
+        if (smem > 227 * 1024) {
+            set_last_error(__FILE__, __LINE__, "front-end: tables do not fit in shared memory");
+            return SKB_ERR_ARG;
+        }
         frontend_kernel<NC, WPC><<<grid, WPC * 32, smem, stream>>>(p, frames_per_cta);
     } else if (fc.n_fft == 2048) {
-        constexpr int NC = 1024, WPC = 4;
-        const int frames_per_cta = 4 * WPC;
+        // a frame needs 9.3 KB of shared memory and the tables 52 KB: 16 frame-warps in one CTA per SM
+        constexpr int NC = 1024, WPC = 16;
+        const int frames_per_cta = 2 * WPC;
         dim3 grid((t_max + frames_per_cta - 1) / frames_per_cta, B);
-        const size_t smem = NC * sizeof(float2) + WPC * (NC + NC / 8 + 8) * sizeof(float2) + WPC * fc.n_mels * sizeof(float);
+        const size_t smem = smem_bytes(NC, WPC, &p.dct_smem_off);
+        static bool configured = false;
+        if (!configured) {
+            SKB_CUDA_CHECK(cudaFuncSetAttribute(frontend_kernel<NC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            configured = true;
+        }
+        if (smem > 227 * 1024) {
+            set_last_error(__FILE__, __LINE__, "front-end: tables do not fit in shared memory");
+            return SKB_ERR_ARG;
+        }
         frontend_kernel<NC, WPC><<<grid, WPC * 32, smem, stream>>>(p, frames_per_cta);
     } else {
         set_last_error(__FILE__, __LINE__, "unsupported n_fft (1024 or 2048)");

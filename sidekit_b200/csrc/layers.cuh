@@ -8,7 +8,7 @@ namespace skb {
 struct ConvParams;
 
 struct FrontendConsts {
-    int n_fft = 0, win = 0, hop = 0, n_mels = 0, n_out = 0;
+    int n_fft = 0, win = 0, hop = 0, n_mels = 0, n_out = 0, n_w = 0;
     float* window = nullptr;
     float2* tw_half = nullptr;
     float2* tw_full = nullptr;
@@ -32,6 +32,8 @@ int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C,
                          const int* frame_row, int n_frames, float* X, cudaStream_t st);
 int launch_gather_pack(const uint16_t* act, long long plane, int C, int W, int Wp, int G, const int* frame_row, int n_frames,
                        uint16_t* hi, cudaStream_t st);
+int launch_meanstd_planes(bool bf16, const uint16_t* act, long long plane, int G, const int* utt_row0, const int* n_fr, int B, int D,
+                          const float* aff_s, const float* aff_t, float* out, cudaStream_t st);
 int launch_meanstd(const float* X, const long long* frame_off, const int* n_fr, int B, int D, const float* aff_s,
                    const float* aff_t, float* out, cudaStream_t st);
 int launch_att_act(float* h, const float* hb, const int* frame_utt, const float* bn_s, const float* bn_t, int n_frames,

@@ -179,6 +179,32 @@ def golden_scoring_full():
     print("scoring_full.npz", sorted(out.keys()))
 
 
+def golden_plda_training():
+    """FactorAnalyser.plda of the real reference on a seeded synthetic StatServer (no file output)."""
+    sidekit = ref_import.import_reference()
+    from sidekit.factor_analyser import FactorAnalyser
+    rng = numpy.random.default_rng(1357)
+    D, R, n_spk = 24, 6, 40
+    spk_means = rng.standard_normal((n_spk, R)) @ (0.8 * rng.standard_normal((R, D)))
+    counts = rng.integers(2, 7, size=n_spk)
+    ids, X = [], []
+    for s_, n in enumerate(counts):
+        for _ in range(int(n)):
+            ids.append("spk%02d" % s_)
+            X.append(spk_means[s_] + 0.5 * rng.standard_normal(D) + 0.2)
+    perm = rng.permutation(len(ids))
+    ids, X = numpy.array(ids)[perm], numpy.array(X)[perm]
+    ss = _statserver(sidekit, ids, X)
+    ss.segset = numpy.array(["seg%03d" % i for i in range(len(ids))])
+    out = dict(ids=ids, X=X)
+    for name, kw in (("it3", dict(nb_iter=3)), ("it5_sf", dict(nb_iter=5, scaling_factor=0.5))):
+        fa = FactorAnalyser()
+        fa.plda(copy.deepcopy(ss), R, save_final=False, **kw)
+        out[name + "_mean"], out[name + "_F"], out[name + "_Sigma"] = fa.mean, fa.F, fa.Sigma
+    numpy.savez_compressed(os.path.join(GOLD, "plda_training.npz"), **out)
+    print("plda_training.npz", sorted(out.keys()))
+
+
 def golden_evaltail():
     """PAV / ROCCH / EER / minDCF / Key / z-t-norm outputs of the real reference on seeded scores."""
     sidekit = ref_import.import_reference()
@@ -241,7 +267,9 @@ def golden_evaltail():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["scoring", "scoring_full", "extraction", "evaltail"]
+    which = sys.argv[1:] or ["scoring", "scoring_full", "extraction", "evaltail", "plda_training"]
+    if "plda_training" in which:
+        golden_plda_training()
     if "scoring_full" in which:
         golden_scoring_full()
     if "scoring" in which:

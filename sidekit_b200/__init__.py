@@ -16,6 +16,7 @@ from .iv_scoring import cosine_scoring, PLDA_scoring, fast_PLDA_scoring, full_PL
 from .score_normalization import asnorm, znorm, tnorm, ztnorm
 from . import detplot
 from .detplot import pavx, rocch, rocch2eer, fast_minDCF, eer
+from .factor_analyser import FactorAnalyser
 from . import bulk
 from .bulk import extract_embeddings
 

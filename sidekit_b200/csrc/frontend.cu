@@ -42,73 +42,64 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
 
-// 8-point DFT (forward, e^{-2 pi i qr/8}), natural order in and out.
-__device__ __forceinline__ void dft8(float2 (&a)[8]) {
-    const float r = 0.70710678118654752440f;
-    float2 e0 = cadd(a[0], a[4]), e1 = csub(a[0], a[4]);
-    float2 e2 = cadd(a[2], a[6]), e3 = cmul_mi(csub(a[2], a[6]));
-    float2 o0 = cadd(a[1], a[5]), o1 = csub(a[1], a[5]);
-    float2 o2 = cadd(a[3], a[7]), o3 = cmul_mi(csub(a[3], a[7]));
-    float2 E0 = cadd(e0, e2), E2 = csub(e0, e2), E1 = cadd(e1, e3), E3 = csub(e1, e3);
-    float2 O0 = cadd(o0, o2), O2 = csub(o0, o2), O1 = cadd(o1, o3), O3 = csub(o1, o3);
-    // twiddles w8^k: k=1: (1-i)/sqrt2, k=2: -i, k=3: (-1-i)/sqrt2
-    float2 t1 = make_float2((O1.x + O1.y) * r, (O1.y - O1.x) * r);
-    float2 t2 = cmul_mi(O2);
-    float2 t3 = make_float2((-O3.x + O3.y) * r, (-O3.y - O3.x) * r);
-    a[0] = cadd(E0, O0); a[4] = csub(E0, O0);
-    a[1] = cadd(E1, t1); a[5] = csub(E1, t1);
-    a[2] = cadd(E2, t2); a[6] = csub(E2, t2);
-    a[3] = cadd(E3, t3); a[7] = csub(E3, t3);
+// ---- register-resident FFT of N = 16 / 32 points (radix-2 DIF, fully unrolled; output in bit-reversed order) ------------
+// cos / sin of 2 pi j / 32, j = 0 .. 15 (w_32^j = cos - i sin); w_16^j = w_32^{2j}
+__device__ constexpr float kCos32[16] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                                         0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                                         0.19509032201612826785f, 0.f, -0.19509032201612826785f, -0.38268343236508977173f,
+                                         -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                                         -0.92387953251128675613f, -0.98078528040323044913f};
+__device__ constexpr float kSin32[16] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                                         0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+                                         0.98078528040323044913f, 1.f, 0.98078528040323044913f, 0.92387953251128675613f,
+                                         0.83146961230254523708f, 0.70710678118654752440f, 0.55557023301960222474f,
+                                         0.38268343236508977173f, 0.19509032201612826785f};
+
+template <int N>
+__host__ __device__ constexpr int brev(int i) {      // bit reversal over log2(N) bits
+    int r = 0;
+    for (int b = 1; b < N; b <<= 1) { r = (r << 1) | (i & 1); i >>= 1; }
+    return r;
 }
 
-// Shared-memory index of complex point i: one pad slot every 8 points, so that the stride-8 (second stage), stride-64
-// (first stage) and contiguous-group (last stage) access patterns of the radix-8 passes all spread over the banks.
-__device__ __forceinline__ int zp(int i) { return i + (i >> 3); }
-
-// One radix-8 DIF butterfly of the stage whose sub-transforms have length LEN (LEN = 8 * sub); t = butterfly index.
-template <int NC, int LEN>
-__device__ __forceinline__ void stage8(float2* z, const float2* tw, int t) {
-    constexpr int sub = LEN >> 3;
-    const int blk = t / sub, j = t - blk * sub;
-    const int e0 = blk * LEN + j;
-    float2 a[8];
+template <int N>
+__device__ __forceinline__ void fft_dif(float2 (&a)[N]) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] = z[zp(e0 + q * sub)];
-    dft8(a);
-    const int tstep = (NC / LEN) * j;       // w_len^{j r} = w_NC^{(NC/len) j r}
+    for (int half = N / 2; half >= 1; half >>= 1) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        float2 v = a[r];
-        if (sub > 1 && r > 0) v = cmul(v, tw[(tstep * r) & (NC - 1)]);
-        z[zp(e0 + r * sub)] = v;
+        for (int blk = 0; blk < N; blk += 2 * half) {
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const float2 u = a[blk + j], v = a[blk + j + half];
+                a[blk + j] = cadd(u, v);
+                const float2 d = csub(u, v);
+                const int t = j * (16 / half);           // twiddle w_{2 half}^j = w_32^t
+                if (t == 0) a[blk + j + half] = d;
+                else if (t == 8) a[blk + j + half] = cmul_mi(d);
+                else a[blk + j + half] = cmul(d, make_float2(kCos32[t], -kSin32[t]));
+            }
+        }
     }
 }
 
-// position of natural-order output k in the digit-reversed result of the DIF stages
-template <int NC>
-__device__ __forceinline__ int rev_index(int k);
-template <>
-__device__ __forceinline__ int rev_index<512>(int k) {     // 8 x 8 x 8
-    return ((k & 7) << 6) | (((k >> 3) & 7) << 3) | (k >> 6);
-}
-template <>
-__device__ __forceinline__ int rev_index<1024>(int k) {    // 8 x 8 x 8 x 2: k = r1 + 8 r2 + 64 r3 + 512 r4
-    return ((k & 7) << 7) | (((k >> 3) & 7) << 4) | (((k >> 6) & 7) << 1) | (k >> 9);
-}
-
-// NC complex points per frame.  One WARP per frame: the whole transform of a frame lives in a warp-private slice of
-// shared memory and the passes are separated by __syncwarp only, so the WPC warps of a CTA never wait for each other
-// (the first version used 64 threads per frame and 8 CTA-wide barriers per frame, and was barrier-stall-bound).
+// NC complex points per frame, one WARP per frame, NC = A x 32 with A = NC / 32 (16 or 32), four-step FFT:
+//   1. lane n2 takes the A points z[n1 * 32 + n2] STRAIGHT FROM THE WAVEFORM (pre-emphasis, reflect padding and window
+//      applied on the fly: no staging pass) and transforms them in registers (fft_dif<A>);
+//   2. multiplies by the twiddles w_NC^{n2 k1} (a [k1][n2] table in shared memory: conflict-free) and writes
+//      S[k1][n2] (row stride 33: conflict-free both ways);
+//   3. lane k1 < A reads its row, transforms the 32 points in registers (fft_dif<32>) and stores Z[k1 + A k2] in natural order.
+// Two trips through shared memory instead of the five of the radix-8 in-place version; the passes are separated by
+// __syncwarp only, so the WPC warps of a CTA never wait for each other.
 template <int NC, int WPC>
-__global__ void __launch_bounds__(WPC * 32, (1024 / (WPC * 32)) > 0 ? 1024 / (WPC * 32) : 1) frontend_kernel(const FrontendParams p, int frames_per_cta) {
-    constexpr int ZS = NC + NC / 8 + 8;         // padded complex points per frame buffer
-    constexpr int NB = NC / 8;                  // butterflies per radix-8 stage
+__global__ void __launch_bounds__(WPC * 32, (640 / (WPC * 32)) > 0 ? 640 / (WPC * 32) : 1) frontend_kernel(const FrontendParams p, int frames_per_cta) {
+    constexpr int A = NC / 32;
+    constexpr int ZS = (A * 33 > NC + 2 ? A * 33 : NC + 2);      // complex slots per frame buffer: S[A][33] or Z[NC] / pwr[NC + 1]
     // Every table a frame touches lives in shared memory (twiddles, window, sparse mel filterbank, DCT): read through
-    // L1 / L2 they were 52 KB per frame on the MFCC front-end, 2.8 GB of L2 reads for 0.38 GB of audio, and the kernel's
-    // largest stall (profiles/r01c_ncu_frontend_mfcc_before.txt).
+    // L1 / L2 they were 52 KB per frame on the MFCC front-end, 2.8 GB of L2 reads for 0.38 GB of audio
+    // (profiles/r01c_ncu_frontend_mfcc_before.txt).
     extern __shared__ __align__(16) uint8_t fsm[];
-    float2* tw = reinterpret_cast<float2*>(fsm);                 // [NC]
-    float2* twf = tw + NC;                                       // [NC + 1] (+1 pad)
+    float2* tw = reinterpret_cast<float2*>(fsm);                 // [A][32]: w_NC^{n2 k1}
+    float2* twf = tw + NC;                                       // [NC + 1] (+1 pad): e^{-2 pi i k / n_fft}
     float2* zall = twf + NC + 2;                                 // [WPC][ZS]
     float* melall = reinterpret_cast<float*>(zall + WPC * ZS);   // [WPC][n_mels]
     float* s_win = melall + WPC * p.n_mels;                      // [win]
@@ -123,7 +114,7 @@ __global__ void __launch_bounds__(WPC * 32, (1024 / (WPC * 32)) > 0 ? 1024 / (WP
     if (t_begin >= T) return;
     const int t_end = min(T, t_begin + frames_per_cta);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < NC; i += blockDim.x) tw[i] = p.tw_half[i];
+    for (int i = threadIdx.x; i < NC; i += blockDim.x) tw[i] = p.tw_half[((i >> 5) * (i & 31)) & (NC - 1)];   // k1 = i / 32, n2 = i % 32
     for (int i = threadIdx.x; i <= NC; i += blockDim.x) twf[i] = p.tw_full[i];
     for (int i = threadIdx.x; i < p.win; i += blockDim.x) s_win[i] = p.window[i];
     for (int i = threadIdx.x; i < p.n_w; i += blockDim.x) s_melw[i] = p.mel_w[i];
@@ -138,45 +129,55 @@ __global__ void __launch_bounds__(WPC * 32, (1024 / (WPC * 32)) > 0 ? 1024 / (WP
     const int half_win = p.win >> 1;
 
     for (int frame = t_begin + warp; frame < t_end; frame += WPC) {
-        // windowed, pre-emphasised frame: sample n <-> y[hop*frame - win/2 + n] with reflect padding of y
-        for (int n2 = lane; n2 < NC; n2 += 32) {
-            float v[2];
+        // ---- step 1: A points per lane straight from the waveform, transformed in registers
+        {
+            float2 a[A];
+            const int i_base = p.hop * frame - half_win;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int n = 2 * n2 + e;
-                float val = 0.f;
-                if (n < p.win) {
-                    int i = p.hop * frame - half_win + n;
-                    if (i < 0) i = -i;
-                    if (i >= L) i = 2 * (L - 1) - i;
-                    const float cur = __ldg(x + i);
-                    const float prev = __ldg(x + (i == 0 ? 1 : i - 1));
-                    val = (cur - p.preemph * prev) * s_win[n];
+            for (int n1 = 0; n1 < A; ++n1) {
+                float v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = 2 * (n1 * 32 + lane) + e;      // sample n of the frame <-> y[hop*frame - win/2 + n], reflect padded
+                    float val = 0.f;
+                    if (n < p.win) {
+                        int i = i_base + n;
+                        if (i < 0) i = -i;
+                        if (i >= L) i = 2 * (L - 1) - i;
+                        const float cur = __ldg(x + i);
+                        const float prev = __ldg(x + (i == 0 ? 1 : i - 1));
+                        val = (cur - p.preemph * prev) * s_win[n];
+                    }
+                    v[e] = val;
                 }
-                v[e] = val;
+                a[n1] = make_float2(v[0], v[1]);
             }
-            z[zp(n2)] = make_float2(v[0], v[1]);
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int tt = 0; tt < NB / 32; ++tt) stage8<NC, NC>(z, tw, lane + 32 * tt);
-        __syncwarp();
-#pragma unroll 1
-        for (int tt = 0; tt < NB / 32; ++tt) stage8<NC, NC / 8>(z, tw, lane + 32 * tt);
-        __syncwarp();
-#pragma unroll 1
-        for (int tt = 0; tt < NB / 32; ++tt) stage8<NC, NC / 64>(z, tw, lane + 32 * tt);
-        __syncwarp();
-        if (NC == 1024) {   // final radix-2 stage on pairs
+            fft_dif<A>(a);
+            // ---- step 2: twiddle and transpose through shared memory
 #pragma unroll
-            for (int u = 0; u < NC / 64; ++u) {
-                const int i = (lane + 32 * u) * 2;
-                const float2 a0 = z[zp(i)], a1 = z[zp(i + 1)];
-                z[zp(i)] = cadd(a0, a1);
-                z[zp(i + 1)] = csub(a0, a1);
+            for (int r = 0; r < A; ++r) {
+                const int k1 = brev<A>(r);                       // a[r] = Y[k1]
+                float2 y = a[r];
+                if (k1 != 0) y = cmul(y, tw[k1 * 32 + lane]);
+                z[k1 * 33 + lane] = y;
             }
-            __syncwarp();
         }
+        __syncwarp();
+        // ---- step 3: 32 points per lane (lanes k1 < A), natural-order store
+        {
+            float2 c[32];
+            if (lane < A) {
+#pragma unroll
+                for (int n2 = 0; n2 < 32; ++n2) c[n2] = z[lane * 33 + n2];
+            }
+            __syncwarp();                                        // every row is in registers before Z overwrites S
+            if (lane < A) {
+                fft_dif<32>(c);
+#pragma unroll
+                for (int r = 0; r < 32; ++r) z[lane + A * brev<32>(r)] = c[r];     // Z[k1 + A k2]
+            }
+        }
+        __syncwarp();
         // unpack the real spectrum, take |X|^2 for k = 0..NC and store it in natural order into a power buffer
         // that aliases z (all reads first).
         constexpr int kPer = NC / 32 + 1;           // ceil((NC + 1) / 32)
@@ -186,8 +187,8 @@ __global__ void __launch_bounds__(WPC * 32, (1024 / (WPC * 32)) > 0 ? 1024 / (WP
             const int k = lane + c * 32;
             pw[c] = 0.f;
             if (k <= NC) {
-                const float2 zk = z[zp(rev_index<NC>(k & (NC - 1)))];
-                const float2 zr = z[zp(rev_index<NC>((NC - k) & (NC - 1)))];
+                const float2 zk = z[k & (NC - 1)];
+                const float2 zr = z[(NC - k) & (NC - 1)];
                 const float2 zc = make_float2(zr.x, -zr.y);
                 const float2 s = cadd(zk, zc), d = csub(zk, zc);
                 const float2 wd = cmul(twf[k], d);                    // e^{-2 pi i k / n_fft} (Z[k] - conj Z[N-k])
@@ -299,6 +300,7 @@ __global__ void cmvn_apply_kernel(float* __restrict__ feats, const long long* __
 
 }  // namespace skb
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -377,7 +379,8 @@ int frontend_launch(const FrontendConsts& fc, const float* wave, const long long
     }
     p.n_w = fc.n_w;
     auto smem_bytes = [&](int NC, int WPC, int* dct_off) {
-        size_t floats = 2 * (size_t)NC + 2 * ((size_t)NC + 2) + 2 * (size_t)WPC * (NC + NC / 8 + 8) + (size_t)WPC * fc.n_mels + fc.win + fc.n_w +
+        const size_t zs = std::max<size_t>((size_t)(NC / 32) * 33, (size_t)NC + 2);      // complex slots per frame buffer (kernel: ZS)
+        size_t floats = 2 * (size_t)NC + 2 * ((size_t)NC + 2) + 2 * (size_t)WPC * zs + (size_t)WPC * fc.n_mels + fc.win + fc.n_w +
                         3 * (size_t)fc.n_mels;
         floats = (floats + 3) / 4 * 4;
         *dct_off = (int)floats;

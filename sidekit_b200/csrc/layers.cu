@@ -110,17 +110,34 @@ __device__ __forceinline__ void fix_add8(const uint4& a, long long (&t)[8]) {
     }
 }
 
-// exact warp sum of 64-bit values with the 32-bit hardware reduction (20-bit low limb + signed high limb); lane e < 8
-// returns the total of t[e]
+// Exact warp sums of eight 64-bit values: a shuffle transpose-reduce (each step halves the values a lane carries), 18
+// 64-bit shuffles in all.  Lane l ends up with the total of value e = 4*b4 + 2*b3 + b2 (bits of l); the result is
+// returned by the lanes with b1 = b0 = 0, i.e. lane 4*e' ... see `sum8_slot`.  __reduce_add_sync (REDUX) measured
+// ~20 cycles per instruction per SM here and made this kernel REDUX-bound on the small levels.
+__device__ __forceinline__ long long shfl_xor_ll(long long v, int off) {
+    const int lo = __shfl_xor_sync(0xffffffffu, (int)(v & 0xffffffffll), off);
+    const int hi = __shfl_xor_sync(0xffffffffu, (int)(v >> 32), off);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
+__device__ __forceinline__ int sum8_slot(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
 __device__ __forceinline__ long long warp_sum8_i64(const long long (&t)[8], int lane) {
-    long long mine = 0ll;
+    long long v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int slo = __reduce_add_sync(0xffffffffu, (int)(t[e] & 0xFFFFFll));
-        const int shi = __reduce_add_sync(0xffffffffu, (int)(t[e] >> 20));
-        if (lane == e) mine = ((long long)shi << 20) + (long long)slo;
+    for (int e = 0; e < 8; ++e) v[e] = t[e];
+#pragma unroll
+    for (int step = 0; step < 3; ++step) {               // offsets 16, 8, 4: keep 4, 2, 1 values
+        const int off = 16 >> step, keep = 4 >> step;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < keep; ++i) {
+            const long long send = upper ? v[i] : v[i + keep];
+            const long long mine = upper ? v[i + keep] : v[i];
+            v[i] = mine + shfl_xor_ll(send, off);
+        }
     }
-    return mine;
+    v[0] += shfl_xor_ll(v[0], 2);
+    v[0] += shfl_xor_ll(v[0], 1);
+    return v[0];                                          // total of value sum8_slot(lane), replicated over 4 lanes
 }
 
 template <bool BF16>
@@ -155,7 +172,7 @@ __global__ void __launch_bounds__(256, 4) plane_sum_kernel(const uint16_t* __res
 #pragma unroll
             for (int k = 0; k < 8; ++k) fix_add8<BF16>(a[k], t);
             const long long mine = warp_sum8_i64(t, lane);
-            if (lane < 8) atomicAdd(sums + (size_t)sb * C + j * 8 + lane, (unsigned long long)mine);
+            if ((lane & 3) == 0) atomicAdd(sums + (size_t)sb * C + j * 8 + sum8_slot(lane), (unsigned long long)mine);
         } else {
             // the span straddles utterance boundaries (the rule on the deepest level, where an utterance is a few hundred
             // pixels): one warp-uniform pass per distinct utterance, in increasing order
@@ -174,7 +191,7 @@ __global__ void __launch_bounds__(256, 4) plane_sum_kernel(const uint16_t* __res
                 for (int k = 0; k < 8; ++k)
                     if (pb[k] == nb) fix_add8<BF16>(a[k], t);
                 const long long mine = warp_sum8_i64(t, lane);
-                if (lane < 8) atomicAdd(sums + (size_t)nb * C + j * 8 + lane, (unsigned long long)mine);
+                if ((lane & 3) == 0) atomicAdd(sums + (size_t)nb * C + j * 8 + sum8_slot(lane), (unsigned long long)mine);
                 cur = nb;
             }
         }

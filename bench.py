@@ -385,6 +385,98 @@ def run_extras(args, device, peaks, dist_on, rank, world):
             t2 = time.perf_counter()
             out["plda_20k"]["e2e"] = {"value": float(Ne) * Nt / (t2 - t0), "unit": "trials/s", "api_call_s": t1 - t0,
                                       "d2h_float64_s": t2 - t1, "d2h_bytes": int(mat.nbytes)}
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        out["plda_20k"]["cpu_baseline"] = cpu_reference_plda(2000, 256)
+        out["vox1o_pipeline"] = run_vox1o_pipeline(device)
+    return out
+
+
+def cpu_reference_plda(n, D):
+    """The reference's fast-PLDA algorithm (oracle port, numpy float64, id matching included) on a bounded n x n sample."""
+    from oracle import scoring_ref as S
+    from sidekit_b200 import synth
+    E, T = synth.synth_embeddings(n, D, seed=6), synth.synth_embeddings(n, D, seed=7)
+    mu, F, Sigma = synth.synth_plda(D, D, seed=8)
+    ids_e = numpy.array(["m%06d" % i for i in range(n)])
+    ids_t = numpy.array(["s%06d" % i for i in range(n)])
+    mask = numpy.ones((n, n), dtype=bool)
+    t0 = time.perf_counter()
+    S.fast_plda_scoring(ids_e, E, ids_t, T, ids_e, ids_t, mask, mu, F, Sigma)
+    dt = time.perf_counter() - t0
+    return {"value": n * n / dt, "unit": "trials/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "%d x %d x %d trials, numpy float64 (BLAS threads as configured), %.2f s" % (n, n, D, dt)}
+
+
+def run_vox1o_pipeline(device):
+    """BASELINE config 5: vox1-O-shaped pipeline on one GPU -- 4 708 utterances -> log-Mel -> HalfResNet34 embeddings ->
+    cosine + PLDA scoring of 37 720 trials -> as-norm (cohort = the 7 205 margin-head rows) -> EER / minDCF.
+    Wall-clock per stage (host + device, synchronised), everything through the public API."""
+    import sidekit_b200 as sk
+    from sidekit_b200 import synth
+    N, n_trials = 4708, 37720
+    rng = numpy.random.default_rng(55)
+    model = build_model("halfresnet34", 256, device)
+    lengths = numpy.sort(synth.synth_lengths(N, 4.0, 12.0, seed=21))[::-1].copy()     # longest first: work buffers are sized once
+    audio_s = float(lengths.sum()) / 16000.0
+    batches = []
+    for lo in range(0, N, 128):                                    # 128 utterances (~1000 audio-s) per packed batch, pinned host memory
+        ls = [int(v) for v in lengths[lo:lo + 128]]
+        g = torch.Generator(device="cpu").manual_seed(7000 + lo)
+        batches.append(((torch.randn(sum(ls), generator=g) * 0.1).pin_memory(), ls))
+    out = {"workload": "vox1-O-shaped: %d utterances 4-12 s (%.0f audio-s), %d trials, cohort 7205 (BASELINE config 5)" % (N, audio_s, n_trials)}
+    sync = torch.cuda.synchronize
+    with torch.no_grad():
+        model.extract_stream(batches[:2])                          # warm-up (plans of later batches are built inside the timed call)
+        sync(); t0 = time.perf_counter()
+        emb = torch.cat(model.extract_stream(batches)).numpy().copy()
+        sync(); t1 = time.perf_counter()
+    out["extract_s"] = t1 - t0
+    out["extract_rate"] = {"value": audio_s / (t1 - t0), "unit": "audio-s/s", "note": "37 distinct batch geometries, each planned once"}
+    ids = numpy.array(["utt%05d" % i for i in range(N)])
+    # trial list: 18 860 "target" + 18 860 "non-target" pairs over the same 4 708 files (labels are arbitrary for random weights)
+    mi, si = rng.integers(0, N, n_trials), rng.integers(0, N, n_trials)
+    labels = numpy.where(numpy.arange(n_trials) % 2 == 0, "target", "nontarget")
+    t0 = time.perf_counter()
+    key = sk.Key(models=ids[mi], testsegs=ids[si], trials=labels)
+    ndx = key.to_ndx()
+    enroll = sk.StatServer.from_embeddings(ids, emb)
+    test = sk.StatServer.from_embeddings(ids, emb)
+    out["key_ndx_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cos = sk.cosine_scoring(enroll, test, ndx)
+    tar, non = cos.get_tar_non(key)
+    sync(); out["cosine_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    fa = sk.FactorAnalyser().plda(sk.StatServer.from_embeddings(numpy.array(["spk%04d" % (i % 1177) for i in range(N)]), emb), 128,
+                                  nb_iter=5, save_final=False)
+    sync(); out["plda_train_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pl = sk.PLDA_scoring(enroll, test, ndx, fa.mean, fa.F, numpy.zeros((256, 0)), fa.Sigma)
+    ptar, pnon = pl.get_tar_non(key)
+    sync(); out["plda_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cohort = model.after_speaker_embedding.weight.detach()
+    S = sk.asnorm(torch.from_numpy(emb).to(device), cohort, None)
+    sync(); out["asnorm_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    sn = sk.Scores()
+    sn.modelset, sn.segset, sn.scoremat, sn.scoremask = ids, ids, S, numpy.ones(S.shape, dtype=bool)
+    atar, anon = sn.get_tar_non(key)
+    res = {"cosine": sk.fast_minDCF(tar, non, numpy.log(0.01 / 0.99), normalize=True), "plda": sk.fast_minDCF(ptar, pnon, numpy.log(0.01 / 0.99), normalize=True),
+           "asnorm": sk.fast_minDCF(atar, anon, numpy.log(0.01 / 0.99), normalize=True)}
+    out["eer_mindcf_s"] = time.perf_counter() - t0
+    out["eer"] = {k: float(v[4]) for k, v in res.items()}
+    out["n_trials_scored"] = int(tar.shape[0] + non.shape[0])
+    out["total_s"] = sum(v for k, v in out.items() if k.endswith("_s") and isinstance(v, float))
+    # the same tail with the reference's algorithm on the host (oracle port): id matching + cosine + as-norm + ROCCH
+    from oracle import scoring_ref as SR, eval_ref as ER
+    t0 = time.perf_counter()
+    SR.cosine_scoring(ids, emb.astype(numpy.float64), ids, emb.astype(numpy.float64), ndx.modelset, ndx.segset, ndx.trialmask)
+    SR.asnorm(emb, cohort.cpu().numpy(), 200)
+    ER.rocch(tar.astype(numpy.float64), non.astype(numpy.float64))
+    out["cpu_baseline"] = {"value": time.perf_counter() - t0, "unit": "s", "cores": os.cpu_count() or 1, "kind": "port",
+                           "sample": "the same scoring tail on the host: id matching + cosine scoring of the full trial list + as-norm "
+                                     "of all %d rows + ROCCH of all %d trials (compare with cosine_s + asnorm_s + eer_mindcf_s / 3)" % (N, tar.shape[0] + non.shape[0])}
     return out
 
 

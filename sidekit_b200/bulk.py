@@ -67,11 +67,12 @@ def extract_embeddings_sharded(extract_fn, waves, embedding_size, max_audio_seco
     shards = plan_shards(lengths, world)
     mine = shards[rank]
     out_dev = device
-    parts = []
-    for batch in make_batches(mine, lengths, max_audio_seconds):
-        e = extract_fn([waves[i] for i in batch])
+    batches = make_batches(mine, lengths, max_audio_seconds)
+    parts = [None] * len(batches)
+    for k in reversed(range(len(batches))):        # largest batch first: the engine sizes its work buffers once
+        e = extract_fn([waves[i] for i in batches[k]])
         out_dev = e.device if out_dev is None else out_dev
-        parts.append(e.to(torch.float32))
+        parts[k] = e.to(torch.float32)
     if out_dev is None:
         out_dev = torch.device("cpu")
     local = torch.cat(parts) if parts else torch.zeros((0, embedding_size), dtype=torch.float32, device=out_dev)

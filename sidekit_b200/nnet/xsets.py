@@ -134,7 +134,8 @@ def extract_embeddings(idmap_name, model_filename, data_root_name, device, batch
     order = numpy.argsort(lengths, kind="stable")
     emb = torch.empty((len(waves), model.embedding_size), dtype=torch.float32)
     with torch.no_grad():
-        for batch in bulk.make_batches(order.tolist(), lengths, max_audio_seconds, sample_rate=sample_rate):
+        # largest batch first: the engine sizes its work buffers once instead of growing them batch after batch
+        for batch in reversed(bulk.make_batches(order.tolist(), lengths, max_audio_seconds, sample_rate=sample_rate)):
             out = model.extract_varlen([waves[i].to(device) for i in batch], norm_embedding=norm_embeddings)
             emb[torch.as_tensor(batch)] = out.cpu()
     embeddings = StatServer()

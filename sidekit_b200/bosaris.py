@@ -7,6 +7,12 @@ import logging
 
 import numpy
 
+try:
+    import torch as _torch
+    _NP_DTYPE = {_torch.float32: numpy.float32, _torch.float64: numpy.float64, _torch.float16: numpy.float16}
+except ImportError:          # the containers themselves do not need torch
+    _NP_DTYPE = {}
+
 
 def _first_index(ids):
     """id -> index of its first occurrence."""
@@ -14,6 +20,42 @@ def _first_index(ids):
     for i, v in enumerate(numpy.asarray(ids).tolist()):
         table.setdefault(v, i)
     return table
+
+
+def _device_to_numpy(t, chunk_bytes=128 << 20):
+    """Device tensor -> numpy array through two pinned staging buffers: the PCIe copy of chunk k+1 overlaps the host
+    copy of chunk k into the (pageable) result.  A plain ``.cpu()`` of a 20k x 20k float64 matrix takes 1.5 s."""
+    import torch
+    t = t.contiguous()
+    out = numpy.empty(tuple(t.shape), dtype=_NP_DTYPE[t.dtype])
+    if t.numel() * t.element_size() < 4 * chunk_bytes or t.dim() != 2:
+        out[...] = t.cpu().numpy()
+        return out
+    rows_per = max(1, chunk_bytes // (t.shape[1] * t.element_size()))
+    stage = [torch.empty((rows_per, t.shape[1]), dtype=t.dtype, pin_memory=True) for _ in range(2)]
+    stream = torch.cuda.Stream(t.device)
+    stream.wait_stream(torch.cuda.current_stream(t.device))
+    events, spans = [], []
+    starts = list(range(0, t.shape[0], rows_per))
+
+    def issue(k):
+        lo = starts[k]
+        hi = min(t.shape[0], lo + rows_per)
+        with torch.cuda.stream(stream):
+            stage[k % 2][:hi - lo].copy_(t[lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        events.append(ev)
+        spans.append((lo, hi))
+
+    issue(0)
+    for k in range(len(starts)):
+        if k + 1 < len(starts):
+            issue(k + 1)                  # its staging buffer was drained in the previous iteration
+        events[k].synchronize()
+        lo, hi = spans[k]
+        numpy.copyto(out[lo:hi], stage[k % 2][:hi - lo].numpy())
+    return out
 
 
 class Key:
@@ -116,7 +158,7 @@ class Scores:
     @property
     def scoremat(self):
         if self._scoremat is None:
-            self._scoremat = self.scoremat_device.cpu().numpy()
+            self._scoremat = _device_to_numpy(self.scoremat_device)
         return self._scoremat
 
     @scoremat.setter
@@ -134,6 +176,14 @@ class Scores:
         if (self.modelset.shape == key.modelset.shape and self.segset.shape == key.segset.shape
                 and (key.modelset == self.modelset).all() and (key.segset == self.segset).all()
                 and self.scoremask.shape == key.tar.shape):
+            if self._scoremat is None and self.scoremat_device is not None:
+                # the matrix is still on the device: gather the trials there instead of copying the whole matrix
+                # (3.2 GB of float64 at 20k x 20k) to the host first; same row-major order as numpy's boolean indexing
+                import torch
+                dev = self.scoremat_device.device
+                tar = self.scoremat_device[torch.from_numpy(key.tar & self.scoremask).to(dev)]
+                non = self.scoremat_device[torch.from_numpy(key.non & self.scoremask).to(dev)]
+                return tar.cpu().numpy(), non.cpu().numpy()
             return self.scoremat[key.tar & self.scoremask], self.scoremat[key.non & self.scoremask]
         new_score = self.align_with_ndx(key)
         return new_score.scoremat[key.tar & new_score.scoremask], new_score.scoremat[key.non & new_score.scoremask]

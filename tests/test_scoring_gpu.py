@@ -163,3 +163,24 @@ def test_asnorm_row_panels_equal_full_matrix():
     top = bulk._asnorm_panel_cuda(X, 0, 130, mean, std)
     bot = bulk._asnorm_panel_cuda(X, 130, 300, mean, std)
     assert torch.equal(torch.cat([top, bot]), full)               # panels are bit-identical to the one-shot matrix
+
+
+def test_scores_device_gather_and_pipelined_copy_equal_the_plain_paths():
+    from sidekit_b200.bosaris import _device_to_numpy
+    g = torch.Generator().manual_seed(5)
+    t = torch.randn(777, 333, generator=g, dtype=torch.float64).cuda()
+    assert numpy.array_equal(_device_to_numpy(t, chunk_bytes=1 << 16), t.cpu().numpy())       # many chunks, ragged last one
+    assert numpy.array_equal(_device_to_numpy(t.float()), t.float().cpu().numpy())             # small: direct copy
+    rng = numpy.random.default_rng(8)
+    ids_m = numpy.array(["m%03d" % i for i in range(120)])
+    ids_s = numpy.array(["s%03d" % i for i in range(90)])
+    en, te = _ss(ids_m, rng.standard_normal((120, 64))), _ss(ids_s, rng.standard_normal((90, 64)))
+    ndx = _ndx(ids_m, ids_s, rng.random((120, 90)) < 0.7)
+    key = sk.Key.create(ids_m, ids_s, rng.random((120, 90)) < 0.2, rng.random((120, 90)) < 0.5)
+    a = sk.cosine_scoring(en, te, ndx)
+    tar_d, non_d = a.get_tar_non(key)                 # matrix still on the device: gathered there
+    assert a._scoremat is None
+    b = sk.cosine_scoring(en, te, ndx)
+    _ = b.scoremat                                    # materialise on the host first
+    tar_h, non_h = b.get_tar_non(key)
+    assert numpy.array_equal(tar_d, tar_h) and numpy.array_equal(non_d, non_h) and tar_d.dtype == tar_h.dtype

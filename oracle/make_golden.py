@@ -205,6 +205,33 @@ def golden_plda_training():
     print("plda_training.npz", sorted(out.keys()))
 
 
+def golden_conditioning():
+    """StatServer conditioning functions of the real reference (covariances, LDA, WCCN, whitening, spectral norm)."""
+    sidekit = ref_import.import_reference()
+    g = numpy.load(os.path.join(GOLD, "plda_training.npz"))
+    ids, X = g["ids"], g["X"]
+    ss = _statserver(sidekit, ids, X)
+    out = {}
+    out["mean"] = ss.get_mean_stat1()
+    out["total_cov"] = ss.get_total_covariance_stat1()
+    out["within_cov"] = ss.get_within_covariance_stat1()
+    out["between_cov"] = ss.get_between_covariance_stat1()
+    out["lda"] = ss.get_lda_matrix_stat1(5)
+    out["mahalanobis"] = ss.get_mahalanobis_matrix_stat1()
+    out["wccn"] = ss.get_wccn_choleski_stat1()
+    summed, sessions = ss.sum_stat_per_model()
+    out["sum_modelset"], out["sum_stat1"], out["sum_sessions"] = summed.modelset, summed.stat1, sessions
+    w = copy.deepcopy(ss); w.whiten_stat1(out["mean"], out["total_cov"]); out["whiten_full"] = w.stat1
+    w = copy.deepcopy(ss); w.whiten_stat1(out["mean"], numpy.diag(out["total_cov"]).copy()); out["whiten_diag"] = w.stat1
+    w = copy.deepcopy(ss); w.whiten_cholesky_stat1(out["mean"], out["total_cov"]); out["whiten_chol"] = w.stat1
+    for mode in ("efr", "sphNorm"):
+        m_, c_ = copy.deepcopy(ss).estimate_spectral_norm_stat1(2, mode)
+        out["sn_%s_mean" % mode], out["sn_%s_cov" % mode] = numpy.stack(m_), numpy.stack(c_)
+        w = copy.deepcopy(ss); w.spectral_norm_stat1(m_, c_); out["sn_%s_out" % mode] = w.stat1
+    numpy.savez_compressed(os.path.join(GOLD, "conditioning.npz"), **out)
+    print("conditioning.npz", sorted(out.keys()))
+
+
 def golden_evaltail():
     """PAV / ROCCH / EER / minDCF / Key / z-t-norm outputs of the real reference on seeded scores."""
     sidekit = ref_import.import_reference()
@@ -270,6 +297,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["scoring", "scoring_full", "extraction", "evaltail", "plda_training"]
     if "plda_training" in which:
         golden_plda_training()
+    if "conditioning" in which or "plda_training" in which:
+        golden_conditioning()
     if "scoring_full" in which:
         golden_scoring_full()
     if "scoring" in which:

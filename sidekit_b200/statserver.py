@@ -1,10 +1,14 @@
-"""``StatServer`` as the container the scoring functions take (sidekit/statserver.py:202-304) plus the six
-helpers on the hot path (:656-684 align_*, :797-817 norm / rotate / center, :1357-1374 mean per model).
+"""``StatServer`` as the container the scoring functions take (sidekit/statserver.py:202-304) plus the helpers on the
+hot path (:656-684 align_*, :797-817 norm / rotate / center, :1357-1374 mean per model) and the embedding-conditioning
+functions that feed PLDA (:789-795 mean, :852-918 whitening, :920-1054 covariances / LDA / WCCN /
+Mahalanobis, :1279-1333 spectral normalisation, :1335-1355 sums per model).  The per-speaker Python loops of the reference
+are replaced by one pass over ``numpy.unique(..., return_inverse=True)`` (same float64 results up to summation order).
 GMM / i-vector statistics, EM and HDF5 IO are out of scope.
 """
 import copy
 
 import numpy
+import scipy.linalg
 
 STAT_TYPE = numpy.float64
 
@@ -90,3 +94,131 @@ class StatServer:
         out.start = numpy.empty(out.segset.shape, "|O")
         out.stop = numpy.empty(out.segset.shape, "|O")
         return out
+
+    # ------------------------------------------------------------------ embedding conditioning
+    def get_mean_stat1(self):
+        """statserver.py:789-795."""
+        return numpy.mean(self.stat1, axis=0)
+
+    def get_model_stat0(self, mod_id):
+        return self.stat0[self.modelset == mod_id, :]
+
+    def get_model_stat1(self, mod_id):
+        return self.stat1[self.modelset == mod_id, :]
+
+    def _classes(self):
+        """(sorted unique models, class index of every session, sessions per class, class means)."""
+        models, inv = numpy.unique(self.modelset, return_inverse=True)
+        counts = numpy.bincount(inv, minlength=models.shape[0]).astype(STAT_TYPE)
+        sums = numpy.zeros((models.shape[0], self.stat1.shape[1]), dtype=STAT_TYPE)
+        numpy.add.at(sums, inv, self.stat1)
+        return models, inv, counts, sums / counts[:, None]
+
+    def sum_stat_per_model(self):
+        """statserver.py:1335-1355: ``(StatServer of per-model sums, sessions per model)``."""
+        out = StatServer()
+        out.modelset, inv = numpy.unique(self.modelset, return_inverse=True)
+        out.segset = copy.deepcopy(out.modelset)
+        n = out.modelset.shape[0]
+        out.stat0 = numpy.zeros((n, self.stat0.shape[1]), dtype=STAT_TYPE)
+        out.stat1 = numpy.zeros((n, self.stat1.shape[1]), dtype=STAT_TYPE)
+        numpy.add.at(out.stat0, inv, self.stat0)
+        numpy.add.at(out.stat1, inv, self.stat1)
+        out.start = numpy.empty(out.segset.shape, "|O")
+        out.stop = numpy.empty(out.segset.shape, "|O")
+        return out, numpy.bincount(inv, minlength=n).astype(STAT_TYPE)
+
+    def whiten_stat1(self, mu, sigma, isSqrInvSigma=False):
+        """statserver.py:852-896: diagonal (1-D sigma) or full-covariance (2-D) whitening."""
+        if sigma.ndim == 1:
+            self.center_stat1(mu)
+            self.stat1 = self.stat1 / numpy.sqrt(sigma.astype(STAT_TYPE))
+        elif sigma.ndim == 2:
+            sqr_inv_sigma = sigma
+            if not isSqrInvSigma:
+                eigen_values, eigen_vectors = scipy.linalg.eigh(sigma)
+                ind = eigen_values.real.argsort()[::-1]
+                eigen_values = eigen_values.real[ind]
+                eigen_vectors = eigen_vectors.real[:, ind]
+                sqr_inv_sigma = numpy.dot(eigen_vectors, numpy.diag(1 / numpy.sqrt(eigen_values.real)))
+            self.center_stat1(mu)
+            self.rotate_stat1(sqr_inv_sigma)
+        else:
+            raise Exception('Wrong dimension of Sigma, must be 1 or 2')
+
+    def whiten_cholesky_stat1(self, mu, sigma):
+        """statserver.py:898-918."""
+        if sigma.ndim == 2:
+            chol_invcov = scipy.linalg.cholesky(scipy.linalg.inv(sigma)).T
+            self.center_stat1(mu)
+            self.stat1 = self.stat1.dot(chol_invcov)
+        elif sigma.ndim == 1:
+            self.center_stat1(mu)
+            self.stat1 = self.stat1 / numpy.sqrt(sigma)
+        else:
+            raise Exception('Wrong dimension of Sigma, must be 1 or 2')
+
+    def get_total_covariance_stat1(self):
+        """statserver.py:920-928."""
+        C = self.stat1 - self.stat1.mean(axis=0)
+        return numpy.dot(C.transpose(), C) / self.stat1.shape[0]
+
+    def get_within_covariance_stat1(self):
+        """statserver.py:940-956: sum_c sum_{x in c} (x - m_c)(x - m_c)' / N."""
+        _, inv, _, means = self._classes()
+        C = self.stat1 - means[inv]
+        return numpy.dot(C.transpose(), C) / self.stat1.shape[0]
+
+    def get_between_covariance_stat1(self):
+        """statserver.py:958-980: sum_c n_c (m_c - mu)(m_c - mu)' / N."""
+        _, _, counts, means = self._classes()
+        D = means - self.get_mean_stat1()
+        return numpy.dot(D.transpose() * counts, D) / self.stat1.shape[0]
+
+    def _class_normalised_scatter(self):
+        """sum_c (1 / n_c) sum_{x in c} (x - m_c)(x - m_c)' (the Sw of the LDA / the WCCN accumulator)."""
+        models, inv, counts, means = self._classes()
+        C = (self.stat1 - means[inv]) / numpy.sqrt(counts[inv])[:, None]
+        return models, means, numpy.dot(C.transpose(), C)
+
+    def get_lda_matrix_stat1(self, rank):
+        """statserver.py:982-1018 (including its ``eigh`` of the non-symmetric discrimination matrix)."""
+        _, means, Sw = self._class_normalised_scatter()
+        class_means = means - self.get_mean_stat1()
+        Sb = numpy.dot(class_means.transpose(), class_means)
+        disc = numpy.dot(Sb, scipy.linalg.inv(Sw)).transpose()
+        eigen_values, eigen_vectors = scipy.linalg.eigh(disc)
+        idx = eigen_values.real.argsort()[-rank:][::-1]
+        return eigen_vectors.real[:, idx]
+
+    def get_mahalanobis_matrix_stat1(self):
+        """statserver.py:1020-1028."""
+        return scipy.linalg.inv(self.get_within_covariance_stat1())
+
+    def get_wccn_choleski_stat1(self):
+        """statserver.py:1030-1054."""
+        models, _, scatter = self._class_normalised_scatter()
+        WCCN = scatter / models.shape[0]
+        return scipy.linalg.cholesky(scipy.linalg.inv(WCCN)).T
+
+    def estimate_spectral_norm_stat1(self, it=1, mode='efr'):
+        """statserver.py:1279-1314: the (mean, covariance) lists of ``it`` whiten + length-norm iterations."""
+        spectral_norm_mean, spectral_norm_cov = [], []
+        tmp_iv = copy.deepcopy(self)
+        for i in range(it):
+            spectral_norm_mean.append(tmp_iv.get_mean_stat1())
+            if mode == 'efr':
+                spectral_norm_cov.append(tmp_iv.get_total_covariance_stat1())
+            elif mode == 'sphNorm':
+                spectral_norm_cov.append(tmp_iv.get_within_covariance_stat1())
+            tmp_iv.whiten_stat1(spectral_norm_mean[i], spectral_norm_cov[i])
+            tmp_iv.norm_stat1()
+        return spectral_norm_mean, spectral_norm_cov
+
+    def spectral_norm_stat1(self, spectral_norm_mean, spectral_norm_cov, is_sqr_inv_sigma=False):
+        """statserver.py:1316-1333."""
+        assert len(spectral_norm_mean) == len(spectral_norm_cov), \
+            'Number of mean vectors and covariance matrices is different'
+        for mu, Cov in zip(spectral_norm_mean, spectral_norm_cov):
+            self.whiten_stat1(mu, Cov, is_sqr_inv_sigma)
+            self.norm_stat1()

@@ -27,6 +27,8 @@ extern "C" {
 
 #define SKB_ARCHI_HALFRESNET34 0 /* Xtractor(model_archi="halfresnet34"), sidekit/nnet/xvector.py:569-599 */
 #define SKB_ARCHI_XVECTOR 1      /* Xtractor(model_archi="xvector") TDNN,  sidekit/nnet/xvector.py:453-498 */
+#define SKB_ARCHI_RESNET34 2     /* Xtractor(model_archi="resnet34"): PreResNet34 trunk (128/256 channels, 7 layers),
+                                    sidekit/nnet/res_net.py:430-498, sidekit/nnet/xvector.py:516-540 */
 
 typedef struct skb_xtractor skb_xtractor_t;
 

@@ -152,16 +152,19 @@ def basic_block(sd, prefix, x, stride):
 
 
 HALFRESNET34_STAGES = ((3, 1), (4, 2), (6, 2), (3, 2))       # (num_blocks, first stride), res_net.py:520-523
+# PreResNet34, res_net.py:455-462: layer7 is built with num_blocks[5], i.e. ONE block
+RESNET34_STAGES = ((3, 1), (1, 2), (3, 1), (1, 2), (5, 1), (1, 2), (1, 1))
 
 
-def halfresnet34_trunk(sd, feats, collect=None):
-    """PreHalfResNet34.forward, nnet/res_net.py:539-554.  feats (B, 80, T) -> (B, 256, T4, 10)."""
+def halfresnet34_trunk(sd, feats, collect=None, stages=HALFRESNET34_STAGES):
+    """PreHalfResNet34.forward, nnet/res_net.py:539-554 (PreResNet34.forward, :476-498, with ``RESNET34_STAGES``).
+    feats (B, 80, T) -> (B, 256, T4, 10).  Whether a block has a 1x1 shortcut is read off the state_dict."""
     x = feats.unsqueeze(1).permute(0, 1, 3, 2)                # (B, 1, T, F)
     p = "sequence_network"
     x = F.relu(_bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv1.weight"].to(x.dtype), padding=1)))
     if collect is not None:
         collect["stem"] = x
-    for li, (nb, stride) in enumerate(HALFRESNET34_STAGES, start=1):
+    for li, (nb, stride) in enumerate(stages, start=1):
         for bi in range(nb):
             x = basic_block(sd, "%s.layer%d.%d" % (p, li, bi), x, stride if bi == 0 else 1)
             if collect is not None:
@@ -219,6 +222,23 @@ def halfresnet34_forward(sd, wave, norm_embedding=True, s=30.0, collect=None):
     return logits, F.normalize(x, dim=1)
 
 
+def resnet34_forward(sd, wave, norm_embedding=True, s=30.0, collect=None):
+    """Xtractor('resnet34').forward(x, is_eval=True), nnet/xvector.py:516-540 + :876-907 (pooling patched to
+    AttentivePooling(256, 10, global_context=True), like halfresnet34)."""
+    feats = logmel_frontend(sd, wave)
+    if collect is not None:
+        collect["feats"] = feats
+    x = halfresnet34_trunk(sd, feats, collect, RESNET34_STAGES)
+    x = attentive_pooling(sd, x)
+    if collect is not None:
+        collect["pooled"] = x
+    x = F.linear(x, sd["before_speaker_embedding.weight"].to(x.dtype), sd["before_speaker_embedding.bias"].to(x.dtype))
+    if norm_embedding:
+        x = l2_norm(x)
+    logits = arc_margin_eval(sd["after_speaker_embedding.weight"], x, s)
+    return logits, F.normalize(x, dim=1)
+
+
 # ----------------------------------------------------------------------------- TDNN ("xvector")
 TDNN_LAYERS = ((5, 1), (3, 2), (3, 3), (1, 1), (1, 1))       # (kernel, dilation), xvector.py:467-483
 
@@ -253,6 +273,8 @@ def forward(sd, wave, model_archi, **kw):
             return halfresnet34_forward(sd, wave, **kw)
         if model_archi == "xvector":
             return tdnn_forward(sd, wave, **kw)
+        if model_archi == "resnet34":
+            return resnet34_forward(sd, wave, **kw)
     raise NotImplementedError(model_archi)
 
 

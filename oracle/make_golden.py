@@ -80,6 +80,25 @@ def golden_extraction():
     print("extraction.npz", {k: v.shape for k, v in out.items()})
 
 
+def golden_extraction_resnet34():
+    """The full-width ResNet34 trunk (xvector.py:515-537): a batched pair and one odd length, outputs only."""
+    torch.set_num_threads(8)
+    out = {}
+    m = _ref_model("resnet34", 256)
+    lengths = [16000, 16000, 20321]
+    waves = [synth.synth_wave(1, L, seed=400 + i)[0] for i, L in enumerate(lengths)]
+    with torch.no_grad():
+        lo01, em01 = m(torch.stack(waves[:2]), is_eval=True)
+        lo2, em2 = m(waves[2], is_eval=True)
+    out["r34_lengths"] = numpy.array(lengths)
+    out["r34_seeds"] = numpy.array([400, 401, 402])
+    out["r34_emb"] = torch.cat([em01, em2]).numpy()
+    out["r34_logits"] = torch.cat([lo01, lo2]).numpy()
+    out["r34_blocks"] = numpy.array([len(getattr(m.sequence_network, "layer%d" % i)) for i in range(1, 8)])
+    numpy.savez_compressed(os.path.join(GOLD, "extraction_resnet34.npz"), **out)
+    print("extraction_resnet34.npz", {k: v.shape for k, v in out.items()}, out["r34_blocks"])
+
+
 def _statserver(sidekit, ids, X):
     s = sidekit.StatServer()
     s.modelset = numpy.array(ids)
@@ -294,9 +313,11 @@ def golden_evaltail():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["scoring", "scoring_full", "extraction", "evaltail", "plda_training"]
+    which = sys.argv[1:] or ["scoring", "scoring_full", "extraction", "extraction_resnet34", "evaltail", "plda_training"]
     if "plda_training" in which:
         golden_plda_training()
+    if "extraction_resnet34" in which:
+        golden_extraction_resnet34()
     if "conditioning" in which or "plda_training" in which:
         golden_conditioning()
     if "scoring_full" in which:

@@ -65,8 +65,8 @@ def build_xtractor(speaker_number, model_archi, embedding_size, loss="aam"):
     from sidekit.nnet import preprocessor as _pp
     with contextlib.redirect_stdout(io.StringIO()):
         model = Xtractor(speaker_number, model_archi, loss=loss, embedding_size=embedding_size)
-    if model_archi == "halfresnet34":
-        model.stat_pooling = AttentivePooling(256, 10, global_context=True)       # P1
+    if model_archi in ("halfresnet34", "resnet34"):
+        model.stat_pooling = AttentivePooling(256, 10, global_context=True)       # P1 (same defect in both constructors)
     if model_archi == "xvector":
         fe = model.preprocessor
         orig = _pp.MfccFrontEnd.forward

@@ -262,6 +262,7 @@ struct BlockW {
     ConvW conv1, conv2, sc;
     bool has_sc = false;
     int stride = 1, C = 0;
+    int layer = 1, index = 0;  // "layer<layer>.<index>" in the reference's module tree (debug stage names)
     float *se_w1 = nullptr, *se_w2 = nullptr;
     float* w2t = nullptr;      // conv2's folded weights as the tensor cores see them (16-bit rounded), fp32 [9*Cin][Cout]
 };
@@ -274,6 +275,9 @@ struct Model {
     FrontendConsts fe;
     // halfresnet34
     StemConsts stem;            // folded stem conv + BN (host copy: passed to the kernel by value)
+    int stem_c = 32;            // stem output channels: 32 (halfresnet34) or 128 (resnet34)
+    int level_C[4] = {32, 64, 128, 256};   // channels of the four resolution levels (W = 80, 40, 20, 10)
+    bool head_bn = true;        // before_speaker_embedding = Linear(no bias) + BatchNorm1d (halfresnet34) or a plain Linear (resnet34)
     std::vector<BlockW> blocks;
     float *att_w1x = nullptr, *att_w1g = nullptr, *att_b1 = nullptr, *att_bn_s = nullptr, *att_bn_t = nullptr;
     float *att_w2 = nullptr, *att_b2 = nullptr;
@@ -287,6 +291,8 @@ struct Model {
     float *pool_s = nullptr, *pool_t = nullptr;
 };
 
+static inline bool is_resnet(int archi) { return archi == SKB_ARCHI_HALFRESNET34 || archi == SKB_ARCHI_RESNET34; }
+
 static int upload_f(const std::vector<double>& v, float** out) {
     std::vector<float> f(v.begin(), v.end());
     return dev_upload(f, out);
@@ -297,7 +303,7 @@ static int upload_raw(const HostTensor* t, float** out) {
 }
 
 static int build_frontend(const WeightMap& w, Model* m) {
-    if (m->archi == SKB_ARCHI_HALFRESNET34) {
+    if (m->archi != SKB_ARCHI_XVECTOR) {
         const HostTensor *win = find(w, "preprocessor.MelSpec.spectrogram.window"), *fb = find(w, "preprocessor.MelSpec.mel_scale.fb");
         if (!win || !fb) return SKB_ERR_WEIGHTS;
         if (win->numel() != 400 || fb->shape.size() != 2 || fb->shape[0] != 513) {
@@ -337,23 +343,41 @@ static int build_margin_head(const WeightMap& w, Model* m) {
 static int build_hr34(const WeightMap& w, Model* m) {
     int rc;
     const std::string sn = "sequence_network";
-    {   // stem: conv1 (32,1,3,3) + bn1 -> fp32 folded
+    // Trunk tables.  halfresnet34 (res_net.py:504-554): 4 layers (3,4,6,3) at 32/64/128/256 channels, strides 1,2,2,2 given
+    // as TUPLES, so that `stride != 1` is true even for layer1.0 and it gets a 1x1 shortcut.  resnet34 (PreResNet34,
+    // res_net.py:430-498): 7 layers (3,1,3,1,5,1,1 as built) at 128,128,128,256,256,256,256 channels with INT strides 1,2,1,2,1,2,1.
+    // The shortcut of a block is simply whatever the state_dict holds.
+    const bool half = m->archi == SKB_ARCHI_HALFRESNET34;
+    const int n_layers = half ? 4 : 7;
+    const int nblocks_h[4] = {3, 4, 6, 3}, planes_h[4] = {32, 64, 128, 256}, strides_h[4] = {1, 2, 2, 2};
+    const int nblocks_r[7] = {3, 1, 3, 1, 5, 1, 1} /* layer7 is built with num_blocks[5] (res_net.py:462) */, planes_r[7] = {128, 128, 128, 256, 256, 256, 256}, strides_r[7] = {1, 2, 1, 2, 1, 2, 1};
+    const int* nblocks = half ? nblocks_h : nblocks_r;
+    const int* planes = half ? planes_h : planes_r;
+    const int* lstrides = half ? strides_h : strides_r;
+    m->stem_c = half ? 32 : 128;
+    {   // stem: conv1 (C,1,3,3) + bn1 -> fp32 folded
         const HostTensor* cw = find(w, sn + ".conv1.weight");
-        if (!cw || cw->numel() != 32 * 9) return SKB_ERR_WEIGHTS;
+        if (!cw || cw->numel() != m->stem_c * 9) return SKB_ERR_WEIGHTS;
         std::vector<double> s, t;
         if ((rc = bn_affine(w, sn + ".bn1", &s, &t))) return rc;
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < m->stem_c; ++c) {
             for (int k = 0; k < 9; ++k) m->stem.w[c * 9 + k] = (float)((double)cw->p[c * 9 + k] * s[c]);
             m->stem.b[c] = (float)t[c];
         }
     }
-    const int nblocks[4] = {3, 4, 6, 3}, planes[4] = {32, 64, 128, 256};
-    for (int li = 0; li < 4; ++li)
+    int level = 0;
+    m->level_C[0] = m->stem_c;
+    for (int li = 0; li < n_layers; ++li)
         for (int bi = 0; bi < nblocks[li]; ++bi) {
             const std::string p = sn + ".layer" + std::to_string(li + 1) + "." + std::to_string(bi);
             BlockW b;
             b.C = planes[li];
-            b.stride = (bi == 0 && li > 0) ? 2 : 1;
+            b.layer = li + 1;
+            b.index = bi;
+            b.stride = bi == 0 ? lstrides[li] : 1;
+            if (b.stride == 2) ++level;
+            if (level > 3) return SKB_ERR_WEIGHTS;
+            m->level_C[level] = b.C;
             if (b.stride == 2) {
                 if ((rc = pack_conv_bn_phase_split(w, p + ".conv1.weight", p + ".bn1", m->bf16, &b.conv1))) return rc;
             } else if ((rc = pack_conv_bn(w, p + ".conv1.weight", p + ".bn1", m->bf16, &b.conv1))) return rc;
@@ -391,14 +415,22 @@ static int build_hr34(const WeightMap& w, Model* m) {
     if ((rc = upload_f(t, &m->att_bn_t))) return rc;
     if ((rc = upload_raw(a4w, &m->att_w2))) return rc;
     if ((rc = upload_raw(a4b, &m->att_b2))) return rc;
-    // embedding head: Linear(5120 -> E, no bias) + BatchNorm1d(E)
-    const HostTensor* lw = find(w, "before_speaker_embedding.lin_be.weight");
+    // embedding head: Linear(5120 -> E, no bias) + BatchNorm1d(E) (halfresnet34, xvector.py:578-581) or a plain
+    // Linear(5120 -> E) with bias (resnet34, xvector.py:522-523)
+    m->head_bn = half;
+    const HostTensor* lw = find(w, half ? "before_speaker_embedding.lin_be.weight" : "before_speaker_embedding.weight");
     if (!lw || lw->shape.size() != 2 || lw->shape[1] != 2 * D) return SKB_ERR_WEIGHTS;
     m->emb = (int)lw->shape[0];
     if ((rc = upload_raw(lw, &m->lin_w))) return rc;
-    if ((rc = bn_affine(w, "before_speaker_embedding.bn_be", &s, &t))) return rc;
-    if ((rc = upload_f(s, &m->be_s))) return rc;
-    if ((rc = upload_f(t, &m->be_t))) return rc;
+    if (half) {
+        if ((rc = bn_affine(w, "before_speaker_embedding.bn_be", &s, &t))) return rc;
+        if ((rc = upload_f(s, &m->be_s))) return rc;
+        if ((rc = upload_f(t, &m->be_t))) return rc;
+    } else {
+        const HostTensor* lb = find(w, "before_speaker_embedding.bias");
+        if (!lb || lb->numel() != m->emb) return SKB_ERR_WEIGHTS;
+        if ((rc = upload_raw(lb, &m->lin_b))) return rc;
+    }
     {
         // K permuted to k' = f * C + c (see gather_pack_kernel): column c * F + f of the Conv1d weight moves to f * C + c
         const int Cc = 256, Ff = D / Cc;
@@ -614,13 +646,13 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     std::vector<int> pool_nfr(B);
     std::vector<long long> pool_off(B);
     std::vector<int> frame_row, frame_utt;
-    if (m.archi == SKB_ARCHI_HALFRESNET34) {
+    if (is_resnet(m.archi)) {
         pl.lv.resize(4);
         std::vector<int> H = pl.T;
-        const int Ws[4] = {80, 40, 20, 10}, Cs[4] = {32, 64, 128, 256};
+        const int Ws[4] = {80, 40, 20, 10};
         for (int l = 0; l < 4; ++l) {
             if (l > 0) for (auto& x : H) x = (x - 1) / 2 + 1;
-            plan_level(&pl, &pl.lv[l], Ws[l], Cs[l], H, true, Ws[l] + 2);
+            plan_level(&pl, &pl.lv[l], Ws[l], m.level_C[l], H, true, Ws[l] + 2);
         }
         const Level& L4 = pl.lv[3];
         long long off = 0;
@@ -711,12 +743,13 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
     const int B = pl.B;
     int rc;
     std::vector<size_t> need;
-    if (m.archi == SKB_ARCHI_HALFRESNET34) {
+    if (is_resnet(m.archi)) {
         for (int l = 0; l < 4; ++l) {
             const size_t bytes = (size_t)(pl.lv[l].C / 8) * pl.lv[l].plane * 16;
             // A, B (block in/out ping-pong), Y1, PS (phase-split copy of the previous level's output: 4 * C_prev/8 planes
             // = twice this level's plane count), SC (shortcut conv output)
-            for (int k = 0; k < 5; ++k) need.push_back(k == 3 ? (l == 0 ? 256 : 2 * bytes) : bytes);
+            const size_t ps_bytes = l == 0 ? 256 : (size_t)4 * (pl.lv[l - 1].C / 8) * pl.lv[l].plane * 16;
+            for (int k = 0; k < 5; ++k) need.push_back(k == 3 ? ps_bytes : bytes);
         }
     } else {
         for (int l = 0; l < 6; ++l) need.push_back((size_t)(pl.lv[l].C / 8) * pl.lv[l].plane * 16);
@@ -725,7 +758,7 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
     h->act_bytes = need;
     for (size_t i = 0; i < need.size(); ++i)
         if ((rc = h->act[i].ensure(need[i]))) return rc;
-    if (m.archi == SKB_ARCHI_HALFRESNET34) {
+    if (is_resnet(m.archi)) {
         // The one guard pixel that IS read into a kept accumulator row: tap (-1, -1) of the first pixel of the first
         // line reaches pixel G - 1.  Nothing ever writes below G, but the plane stride moves with the geometry, so the
         // guard of every chunk plane is cleared whenever the plan changes.
@@ -745,7 +778,7 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
         }
         SKB_CUDA_CHECK(cudaGetLastError());
     }
-    const int Cmax = m.archi == SKB_ARCHI_HALFRESNET34 ? 256 : 0;
+    const int Cmax = is_resnet(m.archi) ? 256 : 0;
     if (Cmax) {
         if ((rc = h->sums.ensure((size_t)B * Cmax * sizeof(unsigned long long)))) return rc;
         if ((rc = h->scale.ensure((size_t)B * Cmax * sizeof(float)))) return rc;
@@ -756,7 +789,7 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
     if ((rc = h->cmvn.ensure((size_t)B * m.fe.n_out * sizeof(float2)))) return rc;
     if ((rc = h->cmvn_part.ensure(frontend_cmvn_scratch_bytes(m.fe, B, pl.t_max)))) return rc;
     const int D = m.pool_D;
-    if (m.archi == SKB_ARCHI_HALFRESNET34) {
+    if (is_resnet(m.archi)) {
         if ((rc = h->poolX.ensure((size_t)pl.pool_frames * D * sizeof(float)))) return rc;
         if ((rc = h->poolH.ensure((size_t)pl.pool_frames * m.att_A * sizeof(float)))) return rc;
         if ((rc = h->poolL.ensure((size_t)pl.pool_frames * D * sizeof(float)))) return rc;
@@ -791,7 +824,7 @@ __global__ void pixmeta_kernel(int n, int Wp, int W, const int* __restrict__ row
 static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
     Plan& pl = h->plan;
     size_t total = 0;
-    const bool hr = h->m.archi == SKB_ARCHI_HALFRESNET34;
+    const bool hr = is_resnet(h->m.archi);
     for (size_t l = 0; l < pl.lv.size(); ++l) {
         Level& L = pl.lv[l];
         const size_t n = (size_t)(L.p_end - L.G);
@@ -963,19 +996,18 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     const Level& L1 = pl.lv[0];
     {
         ProfScope ps(PROF_STEM, st);
-        SKB_TRY(launch_stem(m.bf16, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, (const float2*)h->cmvn.p, m.stem, buf(0, 0),
+        SKB_TRY(launch_stem(m.bf16, m.stem_c, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, (const float2*)h->cmvn.p, m.stem, buf(0, 0),
                             L1.plane, L1.G, L1.p_end, L1.Wp, L1.W, d32 + L1.o_row_b, d32 + L1.o_row_h, st));
     }
     g_launches++;
     int level = 0, cur = 0;   // current activation = buf(level, cur), cur in {0, 1}
     if (stop && !strcmp(stop, "stem")) return export_stage(h, buf(0, 0), L1, h_max, dbg_out, per_utt, st);
-    int bi_in_layer = 0, layer = 1;
     bool x_is_ps = false;     // the current activation lives phase-split in buf(level + 1, 3) instead of buf(level, cur)
     for (size_t i = 0; i < m.blocks.size(); ++i) {
         const BlockW& bw = m.blocks[i];
         char name[32];
-        if (bw.stride == 2) { level++; layer++; bi_in_layer = 0; cur = 1; }   // this block's output goes to buf(level, 0)
-        snprintf(name, sizeof(name), "layer%d.%d", layer, bi_in_layer);
+        if (bw.stride == 2) { level++; cur = 1; }   // this block's output goes to buf(level, 0)
+        snprintf(name, sizeof(name), "layer%d.%d", bw.layer, bw.index);
         const Level& L = pl.lv[level];
         // the block after this one strides: write this block's output phase-split in the next level's geometry
         const bool next_strides = i + 1 < m.blocks.size() && m.blocks[i + 1].stride == 2 && !(stop && !strcmp(stop, name));
@@ -1016,7 +1048,6 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
         g_launches += 4;
         cur ^= 1;
         if (stop && !strcmp(stop, name)) return export_stage(h, buf(level, cur), L, h_max, dbg_out, per_utt, st);
-        bi_in_layer++;
     }
     // attentive statistics pooling with global context (pooling.py:151-171)
     const Level& L4 = pl.lv[3];
@@ -1115,7 +1146,7 @@ static int forward_any(skb_xtractor* h, const float* wave, const int64_t* length
         return SKB_ERR_ARG;
     }
     SKB_TRY(build_plan(h, lengths, B, st));
-    if (h->m.archi == SKB_ARCHI_HALFRESNET34) return forward_hr34(h, wave, norm_embedding, emb, logits, stop, h_max, dbg, per_utt, st);
+    if (is_resnet(h->m.archi)) return forward_hr34(h, wave, norm_embedding, emb, logits, stop, h_max, dbg, per_utt, st);
     return forward_tdnn(h, wave, norm_embedding, emb, logits, stop, h_max, dbg, per_utt, st);
 }
 
@@ -1151,7 +1182,7 @@ int skb_profile_read(float* ms_by_category, int n_categories) {
 int skb_xtractor_create(int archi, int n_tensors, const char* const* names, const float* const* data,
                         const int64_t* const* shapes, const int* ndims, int compute_dtype, float margin_s,
                         skb_xtractor_t** out) {
-    if (!out || !names || !data || !shapes || !ndims || (archi != SKB_ARCHI_HALFRESNET34 && archi != SKB_ARCHI_XVECTOR)) {
+    if (!out || !names || !data || !shapes || !ndims || (archi != SKB_ARCHI_HALFRESNET34 && archi != SKB_ARCHI_XVECTOR && archi != SKB_ARCHI_RESNET34)) {
         set_last_error(__FILE__, __LINE__, "bad arguments");
         return SKB_ERR_ARG;
     }
@@ -1172,7 +1203,7 @@ int skb_xtractor_create(int archi, int n_tensors, const char* const* names, cons
     h->m.bf16 = compute_dtype == 1;
     h->m.margin_s = margin_s;
     int rc = build_frontend(w, &h->m);
-    if (!rc) rc = archi == SKB_ARCHI_HALFRESNET34 ? build_hr34(w, &h->m) : build_tdnn(w, &h->m);
+    if (!rc) rc = is_resnet(archi) ? build_hr34(w, &h->m) : build_tdnn(w, &h->m);
     if (rc) {
         skb_xtractor_destroy(h);
         return rc;

@@ -11,7 +11,7 @@ namespace skb {
 // sidekit/nnet/res_net.py:549 (relu(bn1(conv1(x)))) on the (B,1,T,F) view of the features.
 // One thread per level-1 pixel; the normalised features are frame-major so a warp reads contiguous
 // mel bins.  fp32 math on CUDA cores (0.1 % of the trunk's FLOPs), 16-bit chunk-plane output.
-template <bool BF16>
+template <bool BF16, int COUT>
 __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemConsts sc, const float* __restrict__ feats,
                                                    const long long* __restrict__ feat_off, const int* __restrict__ n_frames,
                                                    const float2* __restrict__ cmvn /*[B][W] (mean, rstd)*/,
@@ -24,14 +24,13 @@ __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemC
     const int rel = pix - G;
     const int row = rel / Wp, f = rel - row * Wp;
     const int b = row_b[row], t = row_h[row];
-    float acc[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
     const bool valid = (b >= 0) && (f < W);
+    float x[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) x[k] = 0.f;
     if (valid) {
         const int T = n_frames[b];
         const float* fb = feats + (size_t)feat_off[b] * W;
-        float x[9];
 #pragma unroll
         for (int df = 0; df < 3; ++df) {
             const int ff = f + df - 1;
@@ -44,35 +43,43 @@ __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemC
                 x[dt * 3 + df] = (f_ok && tt >= 0 && tt < T) ? (__ldg(fb + (size_t)tt * W + ff) - ms.x) * ms.y : 0.f;
             }
         }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            float a = sc.b[c];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) a = fmaf(sc.w[c * 9 + k], x[k], a);
-            acc[c] = fmaxf(a, 0.f);
-        }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack2<BF16>(acc[j * 8 + 0], acc[j * 8 + 1]);
-        o.y = pack2<BF16>(acc[j * 8 + 2], acc[j * 8 + 3]);
-        o.z = pack2<BF16>(acc[j * 8 + 4], acc[j * 8 + 5]);
-        o.w = pack2<BF16>(acc[j * 8 + 6], acc[j * 8 + 7]);
-        *reinterpret_cast<uint4*>(out + ((size_t)j * out_plane + pix) * 8) = o;
+    for (int g = 0; g < COUT / 32; ++g) {          // 32 output channels (four 16-byte chunks) at a time
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            float a = sc.b[g * 32 + c];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a = fmaf(sc.w[(g * 32 + c) * 9 + k], x[k], a);
+            acc[c] = valid ? fmaxf(a, 0.f) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack2<BF16>(acc[j * 8 + 0], acc[j * 8 + 1]);
+            o.y = pack2<BF16>(acc[j * 8 + 2], acc[j * 8 + 3]);
+            o.z = pack2<BF16>(acc[j * 8 + 4], acc[j * 8 + 5]);
+            o.w = pack2<BF16>(acc[j * 8 + 6], acc[j * 8 + 7]);
+            *reinterpret_cast<uint4*>(out + ((size_t)(g * 4 + j) * out_plane + pix) * 8) = o;
+        }
     }
 }
 
-int launch_stem(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
+int launch_stem(bool bf16, int cout, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
                 const StemConsts& sc, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
                 const int* row_b, const int* row_h, cudaStream_t st) {
     const int n = p_end - G;
     const int threads = 128;
     const int blocks = (n + threads - 1) / threads;
-    if (bf16)
-        stem_kernel<true><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, row_b, row_h);
-    else
-        stem_kernel<false><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, row_b, row_h);
+#define SKB_STEM(BF, C) stem_kernel<BF, C><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, row_b, row_h)
+    if (cout == 32) { if (bf16) SKB_STEM(true, 32); else SKB_STEM(false, 32); }
+    else if (cout == 128) { if (bf16) SKB_STEM(true, 128); else SKB_STEM(false, 128); }
+    else {
+        set_last_error(__FILE__, __LINE__, "stem: 32 or 128 output channels");
+        return SKB_ERR_ARG;
+    }
+#undef SKB_STEM
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }

@@ -17,8 +17,8 @@ struct FrontendConsts {
     float* dct = nullptr;
 };
 
-struct StemConsts { float w[32 * 9]; float b[32]; };   // folded stem conv + BN, passed to the kernel by value
-int launch_stem(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
+struct StemConsts { float w[128 * 9]; float b[128]; };   // folded stem conv + BN (<= 128 channels), passed to the kernel by value
+int launch_stem(bool bf16, int cout, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
                 const StemConsts& sc, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
                 const int* row_b, const int* row_h, cudaStream_t st);
 int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, const int* span_b, int C,

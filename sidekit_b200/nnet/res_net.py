@@ -59,3 +59,30 @@ class PreHalfResNet34(torch.nn.Module):
     def forward(self, x):
         raise RuntimeError("the trunk runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True) "
                            "(Xtractor.debug_stage exposes per-block activations for tests)")
+
+
+class PreResNet34(torch.nn.Module):
+    """sidekit/nnet/res_net.py:430-498: 128-channel stem, seven layers (3, 1, 3, 1, 5, 1, 2) at 128 / 128 / 128 / 256 /
+    256 / 256 / 256 channels with INT strides 1, 2, 1, 2, 1, 2, 1 (so only the three stride-2 / widening blocks have a
+    1x1 shortcut).  As in the reference, layer7 is built with ``num_blocks[5]`` and therefore has ONE block."""
+
+    def __init__(self, block=BasicBlock, num_blocks=(3, 1, 3, 1, 5, 1, 2), speaker_number=10):
+        super().__init__()
+        if tuple(num_blocks) != (3, 1, 3, 1, 5, 1, 2) or block is not BasicBlock:
+            raise NotImplementedError("the CUDA engine implements the (3, 1, 3, 1, 5, 1, 2) BasicBlock ResNet34")
+        self.in_planes = 128
+        self.speaker_number = speaker_number
+        self.conv1 = torch.nn.Conv2d(1, 128, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn1 = torch.nn.BatchNorm2d(128)
+        self.layer1 = self._make_layer(block, 128, num_blocks[0], stride=1)
+        self.layer2 = self._make_layer(block, 128, num_blocks[1], stride=2)
+        self.layer3 = self._make_layer(block, 128, num_blocks[2], stride=1)
+        self.layer4 = self._make_layer(block, 256, num_blocks[3], stride=2)
+        self.layer5 = self._make_layer(block, 256, num_blocks[4], stride=1)
+        self.layer6 = self._make_layer(block, 256, num_blocks[5], stride=2)
+        self.layer7 = self._make_layer(block, 256, num_blocks[5], stride=1)     # num_blocks[5] as in the reference (:455)
+
+    _make_layer = PreHalfResNet34._make_layer
+
+    def forward(self, x):
+        raise RuntimeError("the trunk runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True)")

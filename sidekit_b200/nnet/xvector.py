@@ -19,10 +19,10 @@ from .. import _lib
 from .loss import ArcMarginProduct
 from .pooling import AttentivePooling, MeanStdPooling
 from .preprocessor import MelSpecFrontEnd, MfccFrontEnd
-from .res_net import PreHalfResNet34
+from .res_net import PreHalfResNet34, PreResNet34
 from ..detplot import eer  # noqa: F401  (sidekit.nnet.xvector.eer, xvector.py:101-209)
 
-_ARCHI_ID = {"halfresnet34": 0, "xvector": 1}
+_ARCHI_ID = {"halfresnet34": 0, "xvector": 1, "resnet34": 2}
 
 
 class _NativeHandle:
@@ -128,8 +128,20 @@ class Xtractor(torch.nn.Module):
                 self._margin_s = 30.0
             else:
                 raise NotImplementedError("only loss='aam' is implemented for halfresnet34 (inference hot path)")
+        elif model_archi == "resnet34":
+            # xvector.py:516-540.  Same deviation as halfresnet34: the shipped AttentivePooling(256, 80, ...) cannot consume
+            # the trunk's 256 x 10 output; the 5120-wide Linear that follows shows the intended pooling.
+            self.preprocessor = MelSpecFrontEnd(n_fft=1024, win_length=400, hop_length=160, n_mels=80)
+            self.sequence_network = PreResNet34()
+            self.embedding_size = embedding_size
+            self.before_speaker_embedding = torch.nn.Linear(in_features=5120, out_features=self.embedding_size)
+            self.stat_pooling = AttentivePooling(256, 10, global_context=True)
+            self.loss = "aam"
+            self.after_speaker_embedding = ArcMarginProduct(self.embedding_size, int(self.speaker_number), s=30.0, m=0.20,
+                                                            easy_margin=False)
+            self._margin_s = 30.0
         else:
-            raise NotImplementedError("model_archi %r: the B200 engine implements 'halfresnet34' and 'xvector'"
+            raise NotImplementedError("model_archi %r: the B200 engine implements 'halfresnet34', 'resnet34' and 'xvector'"
                                       % (model_archi,))
         self.preprocessor.__dict__["_owner"] = weakref.ref(self)
 
@@ -291,15 +303,20 @@ class Xtractor(torch.nn.Module):
         if stage == "pooled":
             numel, shape = None, None
         per = ctypes.c_int64(0)
-        if self.model_archi == "halfresnet34":
-            li = 0 if stage == "stem" else int(stage[5]) - 1 if stage.startswith("layer") else 3
-            C, W = (32, 64, 128, 256)[li], (80, 40, 20, 10)[li]
+        if self.model_archi in ("halfresnet34", "resnet34"):
+            if self.model_archi == "halfresnet34":
+                li = 0 if stage == "stem" else int(stage[5]) - 1 if stage.startswith("layer") else 3
+                C = (32, 64, 128, 256)[li]
+            else:                                                  # resolution level of layer1..layer7 (strides 1,2,1,2,1,2,1)
+                li = 0 if stage == "stem" else (0, 1, 1, 2, 2, 3, 3)[int(stage[5]) - 1] if stage.startswith("layer") else 3
+                C = (128, 128, 256, 256)[li]
+            W = (80, 40, 20, 10)[li]
             Hm = max(T)
             for _ in range(li):
                 Hm = (Hm - 1) // 2 + 1
         else:
             C, W, Hm = (1536 if stage in ("tdnn5",) else 512), 1, max(T)
-        size = B * (2 * 2560 if self.model_archi == "halfresnet34" else 3072) if stage == "pooled" else B * C * Hm * W
+        size = B * (2 * 2560 if self.model_archi in ("halfresnet34", "resnet34") else 3072) if stage == "pooled" else B * C * Hm * W
         out = torch.zeros(size, dtype=torch.float32, device=flat.device)
         with torch.cuda.device(flat.device):
             _lib.check(_lib.lib().skb_xtractor_debug_stage(h, flat.data_ptr(), _lib.i64_array(lengths), B, stage.encode(), Hm,

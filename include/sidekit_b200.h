@@ -29,6 +29,8 @@ extern "C" {
 #define SKB_ARCHI_XVECTOR 1      /* Xtractor(model_archi="xvector") TDNN,  sidekit/nnet/xvector.py:453-498 */
 #define SKB_ARCHI_RESNET34 2     /* Xtractor(model_archi="resnet34"): PreResNet34 trunk (128/256 channels, 7 layers),
                                     sidekit/nnet/res_net.py:430-498, sidekit/nnet/xvector.py:516-540 */
+#define SKB_ARCHI_FASTRESNET34 3 /* Xtractor(model_archi="fastresnet34"): PreFastResNet34 trunk (7x7 stride-(1,2) stem, 16/32/64/128
+                                    channels), sidekit/nnet/res_net.py:557-610, sidekit/nnet/xvector.py:539-567 */
 
 typedef struct skb_xtractor skb_xtractor_t;
 

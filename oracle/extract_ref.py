@@ -137,7 +137,7 @@ def se_layer(sd, prefix, x):
 
 
 def basic_block(sd, prefix, x, stride):
-    """BasicBlock.forward, nnet/res_net.py:309-320; shortcut rule :301-307."""
+    """BasicBlock.forward, nnet/res_net.py:309-320; shortcut rule :301-307 (the shortcut conv uses the block's stride)."""
     out = F.conv2d(x, sd[prefix + ".conv1.weight"].to(x.dtype), stride=stride, padding=1)
     out = F.relu(_bn(sd, prefix + ".bn1", out))
     out = F.conv2d(out, sd[prefix + ".conv2.weight"].to(x.dtype), stride=1, padding=1)
@@ -154,14 +154,15 @@ def basic_block(sd, prefix, x, stride):
 HALFRESNET34_STAGES = ((3, 1), (4, 2), (6, 2), (3, 2))       # (num_blocks, first stride), res_net.py:520-523
 # PreResNet34, res_net.py:455-462: layer7 is built with num_blocks[5], i.e. ONE block
 RESNET34_STAGES = ((3, 1), (1, 2), (3, 1), (1, 2), (5, 1), (1, 2), (1, 1))
+FASTRESNET34_STAGES = ((3, 1), (4, 2), (6, 2), (3, 1))       # PreFastResNet34, res_net.py:575-578
 
 
-def halfresnet34_trunk(sd, feats, collect=None, stages=HALFRESNET34_STAGES):
+def halfresnet34_trunk(sd, feats, collect=None, stages=HALFRESNET34_STAGES, stem_stride=1, stem_pad=1):
     """PreHalfResNet34.forward, nnet/res_net.py:539-554 (PreResNet34.forward, :476-498, with ``RESNET34_STAGES``).
     feats (B, 80, T) -> (B, 256, T4, 10).  Whether a block has a 1x1 shortcut is read off the state_dict."""
     x = feats.unsqueeze(1).permute(0, 1, 3, 2)                # (B, 1, T, F)
     p = "sequence_network"
-    x = F.relu(_bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv1.weight"].to(x.dtype), padding=1)))
+    x = F.relu(_bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv1.weight"].to(x.dtype), stride=stem_stride, padding=stem_pad)))
     if collect is not None:
         collect["stem"] = x
     for li, (nb, stride) in enumerate(stages, start=1):
@@ -180,12 +181,14 @@ def mean_std_pooling(x):
     return torch.cat([x.mean(dim=2), x.std(dim=2)], dim=1)
 
 
-def attentive_pooling(sd, x, prefix="stat_pooling"):
-    """AttentivePooling(256, 10, global_context=True).forward, nnet/pooling.py:151-171."""
+def attentive_pooling(sd, x, prefix="stat_pooling", global_context=True):
+    """AttentivePooling(C, 10, global_context=...).forward, nnet/pooling.py:151-171."""
     if x.dim() == 4:
         x = x.permute(0, 1, 3, 2).flatten(1, 2)               # (B, C*F, T), channel = c*F + f
-    gc = mean_std_pooling(x).unsqueeze(2).repeat(1, 1, x.shape[-1])
-    h = torch.cat([x, gc], dim=1)
+    h = x
+    if global_context:
+        gc = mean_std_pooling(x).unsqueeze(2).repeat(1, 1, x.shape[-1])
+        h = torch.cat([x, gc], dim=1)
     h = F.conv1d(h, sd[prefix + ".attention.0.weight"].to(x.dtype), sd[prefix + ".attention.0.bias"].to(x.dtype))
     h = torch.tanh(_bn(sd, prefix + ".attention.2", F.relu(h)))
     h = F.conv1d(h, sd[prefix + ".attention.4.weight"].to(x.dtype), sd[prefix + ".attention.4.bias"].to(x.dtype))
@@ -239,6 +242,23 @@ def resnet34_forward(sd, wave, norm_embedding=True, s=30.0, collect=None):
     return logits, F.normalize(x, dim=1)
 
 
+def fastresnet34_forward(sd, wave, norm_embedding=True, s=30.0, collect=None):
+    """Xtractor('fastresnet34', loss='aam').forward(x, is_eval=True), nnet/xvector.py:539-567 + :876-907 (pooling patched
+    to AttentivePooling(128, 10, global_context=False)).  Stem: 7x7, stride (1, 2), padding 3 (res_net.py:566-571)."""
+    feats = logmel_frontend(sd, wave)
+    if collect is not None:
+        collect["feats"] = feats
+    x = halfresnet34_trunk(sd, feats, collect, FASTRESNET34_STAGES, stem_stride=(1, 2), stem_pad=3)
+    x = attentive_pooling(sd, x, global_context=False)
+    if collect is not None:
+        collect["pooled"] = x
+    x = F.linear(x, sd["before_speaker_embedding.weight"].to(x.dtype), sd["before_speaker_embedding.bias"].to(x.dtype))
+    if norm_embedding:
+        x = l2_norm(x)
+    logits = arc_margin_eval(sd["after_speaker_embedding.weight"], x, s)
+    return logits, F.normalize(x, dim=1)
+
+
 # ----------------------------------------------------------------------------- TDNN ("xvector")
 TDNN_LAYERS = ((5, 1), (3, 2), (3, 3), (1, 1), (1, 1))       # (kernel, dilation), xvector.py:467-483
 
@@ -275,6 +295,8 @@ def forward(sd, wave, model_archi, **kw):
             return tdnn_forward(sd, wave, **kw)
         if model_archi == "resnet34":
             return resnet34_forward(sd, wave, **kw)
+        if model_archi == "fastresnet34":
+            return fastresnet34_forward(sd, wave, **kw)
     raise NotImplementedError(model_archi)
 
 

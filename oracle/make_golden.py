@@ -95,6 +95,18 @@ def golden_extraction_resnet34():
     out["r34_emb"] = torch.cat([em01, em2]).numpy()
     out["r34_logits"] = torch.cat([lo01, lo2]).numpy()
     out["r34_blocks"] = numpy.array([len(getattr(m.sequence_network, "layer%d" % i)) for i in range(1, 8)])
+    # FastResNet34 (xvector.py:539-567): 7x7 stride-(1,2) stem, 16/32/64/128 channels, attentive pooling without global context
+    m = _ref_model("fastresnet34", 256)
+    lengths = [16000, 16000, 24160, 11111]
+    waves = [synth.synth_wave(1, L, seed=500 + i)[0] for i, L in enumerate(lengths)]
+    with torch.no_grad():
+        lo01, em01 = m(torch.stack(waves[:2]), is_eval=True)
+        res = [m(w, is_eval=True) for w in waves[2:]]
+    out["f34_lengths"] = numpy.array(lengths)
+    out["f34_seeds"] = numpy.array([500, 501, 502, 503])
+    out["f34_emb"] = torch.cat([em01] + [r[1] for r in res]).numpy()
+    out["f34_logits"] = torch.cat([lo01] + [r[0] for r in res]).numpy()
+    out["f34_shortcuts"] = numpy.array([int(len(getattr(m.sequence_network, "layer%d" % i)[0].shortcut) > 0) for i in range(1, 5)])
     numpy.savez_compressed(os.path.join(GOLD, "extraction_resnet34.npz"), **out)
     print("extraction_resnet34.npz", {k: v.shape for k, v in out.items()}, out["r34_blocks"])
 

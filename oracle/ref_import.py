@@ -67,6 +67,8 @@ def build_xtractor(speaker_number, model_archi, embedding_size, loss="aam"):
         model = Xtractor(speaker_number, model_archi, loss=loss, embedding_size=embedding_size)
     if model_archi in ("halfresnet34", "resnet34"):
         model.stat_pooling = AttentivePooling(256, 10, global_context=True)       # P1 (same defect in both constructors)
+    if model_archi == "fastresnet34":
+        model.stat_pooling = AttentivePooling(128, 10, global_context=False)      # P1: shipped num_freqs=80 -> 10240 inputs
     if model_archi == "xvector":
         fe = model.preprocessor
         orig = _pp.MfccFrontEnd.forward

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <string>
 #include <vector>
@@ -263,6 +264,7 @@ struct BlockW {
     bool has_sc = false;
     int stride = 1, C = 0;
     int layer = 1, index = 0;  // "layer<layer>.<index>" in the reference's module tree (debug stage names)
+    bool level_up = false;     // first block of a layer that widens WITHOUT striding (fastresnet34 layer4): next level, same geometry
     float *se_w1 = nullptr, *se_w2 = nullptr;
     float* w2t = nullptr;      // conv2's folded weights as the tensor cores see them (16-bit rounded), fp32 [9*Cin][Cout]
 };
@@ -278,6 +280,9 @@ struct Model {
     int stem_c = 32;            // stem output channels: 32 (halfresnet34) or 128 (resnet34)
     int level_C[4] = {32, 64, 128, 256};   // channels of the four resolution levels (W = 80, 40, 20, 10)
     bool head_bn = true;        // before_speaker_embedding = Linear(no bias) + BatchNorm1d (halfresnet34) or a plain Linear (resnet34)
+    int level_W[4] = {80, 40, 20, 10};     // width (frequency bins) of the four levels
+    bool level_halves[4] = {false, true, true, true};   // does level l halve the time axis of level l-1
+    bool global_context = true; // attentive pooling input = [x ; mean ; std] (halfresnet34 / resnet34) or x alone (fastresnet34)
     std::vector<BlockW> blocks;
     float *att_w1x = nullptr, *att_w1g = nullptr, *att_b1 = nullptr, *att_bn_s = nullptr, *att_bn_t = nullptr;
     float *att_w2 = nullptr, *att_b2 = nullptr;
@@ -291,7 +296,9 @@ struct Model {
     float *pool_s = nullptr, *pool_t = nullptr;
 };
 
-static inline bool is_resnet(int archi) { return archi == SKB_ARCHI_HALFRESNET34 || archi == SKB_ARCHI_RESNET34; }
+static inline bool is_resnet(int archi) {
+    return archi == SKB_ARCHI_HALFRESNET34 || archi == SKB_ARCHI_RESNET34 || archi == SKB_ARCHI_FASTRESNET34;
+}
 
 static int upload_f(const std::vector<double>& v, float** out) {
     std::vector<float> f(v.begin(), v.end());
@@ -340,33 +347,90 @@ static int build_margin_head(const WeightMap& w, Model* m) {
     return dev_upload(wn, &m->spk_wn);
 }
 
-static int build_hr34(const WeightMap& w, Model* m) {
+// fastresnet34 carries its 16-channel level with 32 channels (one K chunk of the tensor-core convolutions): the tensors of
+// layer1 and the input side of layer2.0 are zero-padded here, so that the padded channels stay exactly 0 everywhere
+// (zero weights, BN scale and shift 0 -> relu(0) = 0; zero SE rows) and the packing code sees ordinary 32-channel layers.
+static void pad_tensor(WeightMap* w, std::deque<std::vector<float>>* store, const std::string& key, std::vector<int64_t> shape) {
+    auto it = w->find(key);
+    if (it == w->end()) return;
+    const HostTensor src = it->second;
+    if (src.shape.size() != shape.size()) return;
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    store->emplace_back((size_t)n, 0.f);
+    std::vector<float>& dst = store->back();
+    const size_t nd = shape.size();
+    std::vector<int64_t> idx(nd, 0);
+    for (int64_t i = 0; i < src.numel(); ++i) {
+        int64_t o = 0;
+        for (size_t d = 0; d < nd; ++d) o = o * shape[d] + idx[d];
+        dst[(size_t)o] = src.p[i];
+        for (int d = (int)nd - 1; d >= 0; --d) {
+            if (++idx[d] < src.shape[d]) break;
+            idx[d] = 0;
+        }
+    }
+    HostTensor t;
+    t.p = dst.data();
+    t.shape = shape;
+    (*w)[key] = t;
+}
+
+static void pad_fastresnet_weights(WeightMap* w, std::deque<std::vector<float>>* store) {
+    const std::string sn = "sequence_network";
+    for (int bi = 0; bi < 3; ++bi) {
+        const std::string p = sn + ".layer1." + std::to_string(bi);
+        for (const char* c : {".conv1.weight", ".conv2.weight"}) pad_tensor(w, store, p + c, {32, 32, 3, 3});
+        for (const char* bn : {".bn1", ".bn2"})
+            for (const char* f : {".weight", ".bias", ".running_mean", ".running_var"}) pad_tensor(w, store, p + bn + f, {32});
+        pad_tensor(w, store, p + ".se.fc.0.weight", {2, 32});
+        pad_tensor(w, store, p + ".se.fc.2.weight", {32, 2});
+    }
+    pad_tensor(w, store, sn + ".layer2.0.conv1.weight", {32, 32, 3, 3});
+    pad_tensor(w, store, sn + ".layer2.0.shortcut.0.weight", {32, 32, 1, 1});
+}
+
+static int build_hr34(const WeightMap& w_in, Model* m) {
     int rc;
+    WeightMap w = w_in;
+    std::deque<std::vector<float>> padded;
+    if (m->archi == SKB_ARCHI_FASTRESNET34) pad_fastresnet_weights(&w, &padded);
     const std::string sn = "sequence_network";
     // Trunk tables.  halfresnet34 (res_net.py:504-554): 4 layers (3,4,6,3) at 32/64/128/256 channels, strides 1,2,2,2 given
     // as TUPLES, so that `stride != 1` is true even for layer1.0 and it gets a 1x1 shortcut.  resnet34 (PreResNet34,
     // res_net.py:430-498): 7 layers (3,1,3,1,5,1,1 as built) at 128,128,128,256,256,256,256 channels with INT strides 1,2,1,2,1,2,1.
     // The shortcut of a block is simply whatever the state_dict holds.
-    const bool half = m->archi == SKB_ARCHI_HALFRESNET34;
-    const int n_layers = half ? 4 : 7;
+    // fastresnet34 (PreFastResNet34, res_net.py:557-610): 7x7 stem with stride (1, 2) to 16 channels, 4 layers (3,4,6,3) at
+    // 16/32/64/128 channels with strides 1 (int: no shortcut in layer1.0), (2,2), (2,2), (1,1) -- layer4 widens at the
+    // resolution of layer3 (its first block has a 1x1 shortcut because the stride is the tuple (1,1)).
+    const bool half = m->archi == SKB_ARCHI_HALFRESNET34, fast = m->archi == SKB_ARCHI_FASTRESNET34;
+    const int n_layers = (half || fast) ? 4 : 7;
+    const int planes_f[4] = {32 /* 16 padded */, 32, 64, 128}, strides_f[4] = {1, 2, 2, 1};
     const int nblocks_h[4] = {3, 4, 6, 3}, planes_h[4] = {32, 64, 128, 256}, strides_h[4] = {1, 2, 2, 2};
     const int nblocks_r[7] = {3, 1, 3, 1, 5, 1, 1} /* layer7 is built with num_blocks[5] (res_net.py:462) */, planes_r[7] = {128, 128, 128, 256, 256, 256, 256}, strides_r[7] = {1, 2, 1, 2, 1, 2, 1};
-    const int* nblocks = half ? nblocks_h : nblocks_r;
-    const int* planes = half ? planes_h : planes_r;
-    const int* lstrides = half ? strides_h : strides_r;
-    m->stem_c = half ? 32 : 128;
-    {   // stem: conv1 (C,1,3,3) + bn1 -> fp32 folded
+    const int* nblocks = (half || fast) ? nblocks_h : nblocks_r;
+    const int* planes = half ? planes_h : (fast ? planes_f : planes_r);
+    const int* lstrides = half ? strides_h : (fast ? strides_f : strides_r);
+    m->stem_c = half ? 32 : (fast ? 16 : 128);
+    const int stem_taps = fast ? 49 : 9;
+    {   // stem: conv1 (C,1,k,k) + bn1 -> fp32 folded
         const HostTensor* cw = find(w, sn + ".conv1.weight");
-        if (!cw || cw->numel() != m->stem_c * 9) return SKB_ERR_WEIGHTS;
+        if (!cw || cw->numel() != m->stem_c * stem_taps) return SKB_ERR_WEIGHTS;
         std::vector<double> s, t;
         if ((rc = bn_affine(w, sn + ".bn1", &s, &t))) return rc;
         for (int c = 0; c < m->stem_c; ++c) {
-            for (int k = 0; k < 9; ++k) m->stem.w[c * 9 + k] = (float)((double)cw->p[c * 9 + k] * s[c]);
+            for (int k = 0; k < stem_taps; ++k) m->stem.w[c * stem_taps + k] = (float)((double)cw->p[c * stem_taps + k] * s[c]);
             m->stem.b[c] = (float)t[c];
         }
     }
     int level = 0;
-    m->level_C[0] = m->stem_c;
+    m->level_C[0] = fast ? 32 : m->stem_c;
+    if (fast) {
+        const int wf[4] = {40, 20, 10, 10};
+        const bool hf[4] = {false, true, true, false};
+        for (int l = 0; l < 4; ++l) { m->level_W[l] = wf[l]; m->level_halves[l] = hf[l]; }
+    }
+    m->global_context = !fast;
     for (int li = 0; li < n_layers; ++li)
         for (int bi = 0; bi < nblocks[li]; ++bi) {
             const std::string p = sn + ".layer" + std::to_string(li + 1) + "." + std::to_string(bi);
@@ -375,7 +439,8 @@ static int build_hr34(const WeightMap& w, Model* m) {
             b.layer = li + 1;
             b.index = bi;
             b.stride = bi == 0 ? lstrides[li] : 1;
-            if (b.stride == 2) ++level;
+            b.level_up = bi == 0 && b.stride == 1 && b.C != m->level_C[level];
+            if (b.stride == 2 || b.level_up) ++level;
             if (level > 3) return SKB_ERR_WEIGHTS;
             m->level_C[level] = b.C;
             if (b.stride == 2) {
@@ -395,19 +460,21 @@ static int build_hr34(const WeightMap& w, Model* m) {
                      *a4w = find(w, "stat_pooling.attention.4.weight"), *a4b = find(w, "stat_pooling.attention.4.bias");
     if (!a0w || !a0b || !a4w || !a4b) return SKB_ERR_WEIGHTS;
     const int A = (int)a0w->shape[0], D = (int)a4w->shape[0];
-    if (a0w->shape[1] != 3 * D || D != 2560) {
-        set_last_error(__FILE__, __LINE__, "stat_pooling.attention must be AttentivePooling(256, 10, global_context=True) (7680 -> 128 -> 2560)");
+    const int in_factor = m->global_context ? 3 : 1;
+    if (a0w->shape[1] != in_factor * D || D != m->level_C[3] * m->level_W[3]) {
+        set_last_error(__FILE__, __LINE__, "stat_pooling.attention must be AttentivePooling(C, 10) over the trunk's C x 10 output "
+                                           "(global_context=True for halfresnet34 / resnet34, False for fastresnet34)");
         return SKB_ERR_WEIGHTS;
     }
     m->att_A = A;
     m->pool_D = D;
     std::vector<float> w1x((size_t)A * D), w1g((size_t)A * 2 * D);
     for (int a = 0; a < A; ++a) {
-        memcpy(&w1x[(size_t)a * D], a0w->p + (size_t)a * 3 * D, D * sizeof(float));
-        memcpy(&w1g[(size_t)a * 2 * D], a0w->p + (size_t)a * 3 * D + D, 2 * D * sizeof(float));
+        memcpy(&w1x[(size_t)a * D], a0w->p + (size_t)a * in_factor * D, D * sizeof(float));
+        if (m->global_context) memcpy(&w1g[(size_t)a * 2 * D], a0w->p + (size_t)a * 3 * D + D, 2 * D * sizeof(float));
     }
     if ((rc = dev_upload(w1x, &m->att_w1x))) return rc;
-    if ((rc = dev_upload(w1g, &m->att_w1g))) return rc;
+    if (m->global_context && (rc = dev_upload(w1g, &m->att_w1g))) return rc;
     if ((rc = upload_raw(a0b, &m->att_b1))) return rc;
     std::vector<double> s, t;
     if ((rc = bn_affine(w, "stat_pooling.attention.2", &s, &t))) return rc;
@@ -433,7 +500,7 @@ static int build_hr34(const WeightMap& w, Model* m) {
     }
     {
         // K permuted to k' = f * C + c (see gather_pack_kernel): column c * F + f of the Conv1d weight moves to f * C + c
-        const int Cc = 256, Ff = D / Cc;
+        const int Cc = m->level_C[3], Ff = D / Cc;
         std::vector<float> w1p((size_t)A * D);
         for (int a = 0; a < A; ++a)
             for (int c = 0; c < Cc; ++c)
@@ -649,10 +716,9 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     if (is_resnet(m.archi)) {
         pl.lv.resize(4);
         std::vector<int> H = pl.T;
-        const int Ws[4] = {80, 40, 20, 10};
         for (int l = 0; l < 4; ++l) {
-            if (l > 0) for (auto& x : H) x = (x - 1) / 2 + 1;
-            plan_level(&pl, &pl.lv[l], Ws[l], m.level_C[l], H, true, Ws[l] + 2);
+            if (l > 0 && m.level_halves[l]) for (auto& x : H) x = (x - 1) / 2 + 1;
+            plan_level(&pl, &pl.lv[l], m.level_W[l], m.level_C[l], H, true, m.level_W[l] + 2);
         }
         const Level& L4 = pl.lv[3];
         long long off = 0;
@@ -748,7 +814,7 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
             const size_t bytes = (size_t)(pl.lv[l].C / 8) * pl.lv[l].plane * 16;
             // A, B (block in/out ping-pong), Y1, PS (phase-split copy of the previous level's output: 4 * C_prev/8 planes
             // = twice this level's plane count), SC (shortcut conv output)
-            const size_t ps_bytes = l == 0 ? 256 : (size_t)4 * (pl.lv[l - 1].C / 8) * pl.lv[l].plane * 16;
+            const size_t ps_bytes = (l == 0 || !m.level_halves[l]) ? 256 : (size_t)4 * (pl.lv[l - 1].C / 8) * pl.lv[l].plane * 16;
             for (int k = 0; k < 5; ++k) need.push_back(k == 3 ? ps_bytes : bytes);
         }
     } else {
@@ -764,12 +830,13 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
         // guard of every chunk plane is cleared whenever the plan changes.
         for (int l = 0; l < 4; ++l)
             for (int k = 0; k < 5; ++k) {
-                if (k == 3 && l == 0) continue;
+                if (k == 3 && (l == 0 || !m.level_halves[l])) continue;      // no phase-split buffer on this level
                 const Level& L = pl.lv[l];
                 const int n_planes = k == 3 ? 4 * (pl.lv[l - 1].C / 8) : L.C / 8;
                 SKB_CUDA_CHECK(cudaMemset2DAsync(h->act[l * 5 + k].p, (size_t)L.plane * 16, 0, (size_t)L.G * 16, n_planes, st));
             }
         for (int l = 1; l < 4; ++l) {
+            if (!m.level_halves[l]) continue;
             const Level& Lo = pl.lv[l];
             const int n = Lo.p_end - Lo.G;
             const Level& Ls = pl.lv[l - 1];
@@ -829,7 +896,7 @@ static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
         Level& L = pl.lv[l];
         const size_t n = (size_t)(L.p_end - L.G);
         L.o_pix_b = total; total += n;
-        L.has_sub = hr && l + 1 < pl.lv.size();
+        L.has_sub = hr && l + 1 < pl.lv.size() && h->m.level_halves[l + 1];   // the next level strides: phase-split destinations
         if (L.has_sub) { L.o_pix_sub = total; total += n; }
         if (hr) { L.o_span = total; total += (size_t)span_table_size((int)n); }
     }
@@ -996,8 +1063,12 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     const Level& L1 = pl.lv[0];
     {
         ProfScope ps(PROF_STEM, st);
-        SKB_TRY(launch_stem(m.bf16, m.stem_c, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, (const float2*)h->cmvn.p, m.stem, buf(0, 0),
-                            L1.plane, L1.G, L1.p_end, L1.Wp, L1.W, d32 + L1.o_row_b, d32 + L1.o_row_h, st));
+        if (m.archi == SKB_ARCHI_FASTRESNET34)
+            SKB_TRY(launch_stem7(m.bf16, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, (const float2*)h->cmvn.p, m.stem, buf(0, 0),
+                                 L1.plane, L1.G, L1.p_end, L1.Wp, L1.W, m.fe.n_out, d32 + L1.o_row_b, d32 + L1.o_row_h, st));
+        else
+            SKB_TRY(launch_stem(m.bf16, m.stem_c, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, (const float2*)h->cmvn.p, m.stem, buf(0, 0),
+                                L1.plane, L1.G, L1.p_end, L1.Wp, L1.W, d32 + L1.o_row_b, d32 + L1.o_row_h, st));
     }
     g_launches++;
     int level = 0, cur = 0;   // current activation = buf(level, cur), cur in {0, 1}
@@ -1006,12 +1077,14 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     for (size_t i = 0; i < m.blocks.size(); ++i) {
         const BlockW& bw = m.blocks[i];
         char name[32];
-        if (bw.stride == 2) { level++; cur = 1; }   // this block's output goes to buf(level, 0)
+        // a widening block without stride reads the previous level's buffer (same geometry) and writes the next level's
+        const uint16_t* x_up = bw.level_up ? buf(level, cur) : nullptr;
+        if (bw.stride == 2 || bw.level_up) { level++; cur = 1; }   // this block's output goes to buf(level, 0)
         snprintf(name, sizeof(name), "layer%d.%d", bw.layer, bw.index);
         const Level& L = pl.lv[level];
         // the block after this one strides: write this block's output phase-split in the next level's geometry
         const bool next_strides = i + 1 < m.blocks.size() && m.blocks[i + 1].stride == 2 && !(stop && !strcmp(stop, name));
-        const uint16_t* x = bw.stride == 2 ? buf(level, 3) : buf(level, cur);
+        const uint16_t* x = bw.stride == 2 ? buf(level, 3) : (x_up ? x_up : buf(level, cur));
         if (bw.stride == 2 && !x_is_ps) {
             set_last_error(__FILE__, __LINE__, "internal: stride-2 block without a phase-split input");
             return SKB_ERR_STATE;
@@ -1055,9 +1128,13 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     float *X = (float*)h->poolX.p, *Hh = (float*)h->poolH.p, *Lg = (float*)h->poolL.p;
     ProfScope pool_scope(PROF_POOL, st);
     SKB_TRY(launch_gather_frames(m.bf16, buf(level, cur), L4.plane, L4.C, L4.W, L4.Wp, L4.G, d32 + pl.o_frame_row, F, X, st));
-    SKB_TRY(launch_meanstd(X, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, nullptr, nullptr, (float*)h->gc.p, st));
-    SKB_TRY(h->skinny_ws.ensure(skinny_gemm_ws_floats(B, A, 2 * D) * sizeof(float)));
-    SKB_TRY(launch_skinny_gemm((const float*)h->gc.p, B, 2 * D, m.att_w1g, A, m.att_b1, 1.f, (float*)h->hb.p, A, (float*)h->skinny_ws.p, st));
+    if (m.global_context) {
+        SKB_TRY(launch_meanstd(X, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, nullptr, nullptr, (float*)h->gc.p, st));
+        SKB_TRY(h->skinny_ws.ensure(skinny_gemm_ws_floats(B, A, 2 * D) * sizeof(float)));
+        SKB_TRY(launch_skinny_gemm((const float*)h->gc.p, B, 2 * D, m.att_w1g, A, m.att_b1, 1.f, (float*)h->hb.p, A, (float*)h->skinny_ws.p, st));
+    } else {
+        SKB_TRY(launch_broadcast_rows(m.att_b1, B, A, (float*)h->hb.p, st));
+    }
     if (F > h->poolA_rows) {
         packed_free(&h->poolA);
         h->poolA_rows = 0;
@@ -1182,7 +1259,7 @@ int skb_profile_read(float* ms_by_category, int n_categories) {
 int skb_xtractor_create(int archi, int n_tensors, const char* const* names, const float* const* data,
                         const int64_t* const* shapes, const int* ndims, int compute_dtype, float margin_s,
                         skb_xtractor_t** out) {
-    if (!out || !names || !data || !shapes || !ndims || (archi != SKB_ARCHI_HALFRESNET34 && archi != SKB_ARCHI_XVECTOR && archi != SKB_ARCHI_RESNET34)) {
+    if (!out || !names || !data || !shapes || !ndims || (archi != SKB_ARCHI_XVECTOR && !is_resnet(archi))) {
         set_last_error(__FILE__, __LINE__, "bad arguments");
         return SKB_ERR_ARG;
     }

@@ -84,6 +84,84 @@ int launch_stem(bool bf16, int cout, const float* feats, const long long* feat_o
     return SKB_OK;
 }
 
+// ----------------------------------------------------------------------------- fastresnet34 stem: 7x7 conv 1->16, stride (1, 2)
+// sidekit/nnet/res_net.py:566-572, :605: relu(bn1(conv1(x))) on the (B,1,T,F=80) view, padding 3, stride 1 along time and 2
+// along frequency -> (B,16,T,40).  One thread per output pixel; the 16 real channels are written as chunks 0-1 and the
+// level is carried with 32 channels (chunks 2-3 = 0) so that the K = 32 tensor-core convolutions need no special case.
+template <bool BF16>
+__global__ void __launch_bounds__(128) stem7_kernel(const __grid_constant__ StemConsts sc, const float* __restrict__ feats,
+                                                    const long long* __restrict__ feat_off, const int* __restrict__ n_frames,
+                                                    const float2* __restrict__ cmvn /*[B][F] (mean, rstd)*/,
+                                                    uint16_t* __restrict__ out, long long out_plane, int G, int p_end, int Wp,
+                                                    int W, int F, const int* __restrict__ row_b, const int* __restrict__ row_h) {
+    const int pix = G + blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p_end) return;
+    const int rel = pix - G;
+    const int row = rel / Wp, wo = rel - row * Wp;
+    const int b = row_b[row], t = row_h[row];
+    const bool valid = (b >= 0) && (wo < W);
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = sc.b[c];
+    if (valid) {
+        const int T = n_frames[b];
+        const float* fb = feats + (size_t)feat_off[b] * F;
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+            const int ff = 2 * wo + s - 3;
+            if (ff < 0 || ff >= F) continue;
+            const float2 ms = __ldg(cmvn + (size_t)b * F + ff);
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+                const int tt = t + r - 3;
+                if (tt < 0 || tt >= T) continue;
+                const float x = (__ldg(fb + (size_t)tt * F + ff) - ms.x) * ms.y;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] = fmaf(sc.w[c * 49 + r * 7 + s], x, acc[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = valid ? fmaxf(acc[c], 0.f) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (j < 2) {
+            o.x = pack2<BF16>(acc[j * 8 + 0], acc[j * 8 + 1]);
+            o.y = pack2<BF16>(acc[j * 8 + 2], acc[j * 8 + 3]);
+            o.z = pack2<BF16>(acc[j * 8 + 4], acc[j * 8 + 5]);
+            o.w = pack2<BF16>(acc[j * 8 + 6], acc[j * 8 + 7]);
+        }
+        *reinterpret_cast<uint4*>(out + ((size_t)j * out_plane + pix) * 8) = o;
+    }
+}
+
+int launch_stem7(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
+                 const StemConsts& sc, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W, int F,
+                 const int* row_b, const int* row_h, cudaStream_t st) {
+    const int n = p_end - G;
+    const int threads = 128;
+    const int blocks = (n + threads - 1) / threads;
+    if (bf16)
+        stem7_kernel<true><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, F, row_b, row_h);
+    else
+        stem7_kernel<false><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, F, row_b, row_h);
+    SKB_LAUNCH_CHECK(st);
+    return SKB_OK;
+}
+
+// out[b][a] = bias[a]: the per-utterance attention bias when the pooling has no global context
+__global__ void broadcast_rows_kernel(const float* __restrict__ bias, int B, int A, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * A) out[i] = bias[i % A];
+}
+
+int launch_broadcast_rows(const float* bias, int B, int A, float* out, cudaStream_t st) {
+    broadcast_rows_kernel<<<(B * A + 255) / 256, 256, 0, st>>>(bias, B, A, out);
+    SKB_LAUNCH_CHECK(st);
+    return SKB_OK;
+}
+
 // ----------------------------------------------------------------------------- SE squeeze, computed BEFORE conv2 runs
 // The SE layer needs mean_{h,w}(bn2(conv2(y1))) per (utterance, channel) (sidekit/nnet/res_net.py:272-281, :316-317).
 // conv2 is linear, so that mean follows from sums of its INPUT y1:

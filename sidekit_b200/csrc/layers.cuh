@@ -21,6 +21,10 @@ struct StemConsts { float w[128 * 9]; float b[128]; };   // folded stem conv + B
 int launch_stem(bool bf16, int cout, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
                 const StemConsts& sc, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
                 const int* row_b, const int* row_h, cudaStream_t st);
+int launch_stem7(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
+                 const StemConsts& sc, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W, int F,
+                 const int* row_b, const int* row_h, cudaStream_t st);
+int launch_broadcast_rows(const float* bias, int B, int A, float* out, cudaStream_t st);
 int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, const int* span_b, int C,
                      unsigned long long* sums, cudaStream_t st);
 int span_table_size(int n_pix);

@@ -1,7 +1,7 @@
 """Inference-path subset of ``sidekit.nnet`` (sidekit/nnet/__init__.py:31-47)."""
 from .xvector import Xtractor
 from .pooling import MeanStdPooling, AttentivePooling
-from .res_net import PreHalfResNet34, PreResNet34, BasicBlock, SELayer
+from .res_net import PreHalfResNet34, PreResNet34, PreFastResNet34, BasicBlock, SELayer
 from .preprocessor import MfccFrontEnd, MelSpecFrontEnd, PreEmphasis
 from .loss import ArcMarginProduct, l2_norm
 from .xsets import IdMap, IdMapSet, extract_embeddings, read_wav  # noqa: F401,E402

@@ -86,3 +86,27 @@ class PreResNet34(torch.nn.Module):
 
     def forward(self, x):
         raise RuntimeError("the trunk runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True)")
+
+
+class PreFastResNet34(torch.nn.Module):
+    """sidekit/nnet/res_net.py:557-610: 7x7 stem with stride (1, 2) to 16 channels, layers (3, 4, 6, 3) at 16 / 32 / 64 /
+    128 channels with strides 1 (an int: layer1.0 has no shortcut), (2, 2), (2, 2), (1, 1) -- layer4 widens at the
+    resolution of layer3 and, its stride being a tuple, its first block has a 1x1 shortcut."""
+
+    def __init__(self, block=BasicBlock, num_blocks=(3, 4, 6, 3), speaker_number=10):
+        super().__init__()
+        if tuple(num_blocks) != (3, 4, 6, 3) or block is not BasicBlock:
+            raise NotImplementedError("the CUDA engine implements the (3, 4, 6, 3) BasicBlock FastResNet34")
+        self.in_planes = 16
+        self.speaker_number = speaker_number
+        self.conv1 = torch.nn.Conv2d(1, 16, kernel_size=7, stride=(1, 2), padding=3, bias=False)
+        self.bn1 = torch.nn.BatchNorm2d(16)
+        self.layer1 = self._make_layer(block, 16, num_blocks[0], stride=1)
+        self.layer2 = self._make_layer(block, 32, num_blocks[1], stride=(2, 2))
+        self.layer3 = self._make_layer(block, 64, num_blocks[2], stride=(2, 2))
+        self.layer4 = self._make_layer(block, 128, num_blocks[3], stride=(1, 1))
+
+    _make_layer = PreHalfResNet34._make_layer
+
+    def forward(self, x):
+        raise RuntimeError("the trunk runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True)")

@@ -19,10 +19,11 @@ from .. import _lib
 from .loss import ArcMarginProduct
 from .pooling import AttentivePooling, MeanStdPooling
 from .preprocessor import MelSpecFrontEnd, MfccFrontEnd
-from .res_net import PreHalfResNet34, PreResNet34
+from .res_net import PreHalfResNet34, PreResNet34, PreFastResNet34
 from ..detplot import eer  # noqa: F401  (sidekit.nnet.xvector.eer, xvector.py:101-209)
 
-_ARCHI_ID = {"halfresnet34": 0, "xvector": 1, "resnet34": 2}
+_ARCHI_ID = {"halfresnet34": 0, "xvector": 1, "resnet34": 2, "fastresnet34": 3}
+_RESNETS = ("halfresnet34", "resnet34", "fastresnet34")
 
 
 class _NativeHandle:
@@ -140,9 +141,24 @@ class Xtractor(torch.nn.Module):
             self.after_speaker_embedding = ArcMarginProduct(self.embedding_size, int(self.speaker_number), s=30.0, m=0.20,
                                                             easy_margin=False)
             self._margin_s = 30.0
+        elif model_archi == "fastresnet34":
+            # xvector.py:539-567.  The shipped AttentivePooling(128, 80, global_context=False) expects 10240 inputs while the
+            # trunk emits 128 x 10 and the Linear that follows has 2560 = 2 * 1280 inputs: num_freqs = 10 is what runs.
+            self.preprocessor = MelSpecFrontEnd()
+            self.sequence_network = PreFastResNet34()
+            self.embedding_size = embedding_size
+            self.before_speaker_embedding = torch.nn.Linear(in_features=2560, out_features=self.embedding_size)
+            self.stat_pooling = AttentivePooling(128, 10, global_context=False)
+            self.loss = loss
+            if self.loss == "aam":
+                self.after_speaker_embedding = ArcMarginProduct(self.embedding_size, int(self.speaker_number), s=30, m=0.2,
+                                                                easy_margin=False)
+                self._margin_s = 30.0
+            else:
+                raise NotImplementedError("only loss='aam' is implemented for fastresnet34 (inference hot path)")
         else:
-            raise NotImplementedError("model_archi %r: the B200 engine implements 'halfresnet34', 'resnet34' and 'xvector'"
-                                      % (model_archi,))
+            raise NotImplementedError("model_archi %r: the B200 engine implements 'halfresnet34', 'resnet34', 'fastresnet34' "
+                                      "and 'xvector'" % (model_archi,))
         self.preprocessor.__dict__["_owner"] = weakref.ref(self)
 
     # ------------------------------------------------------------------ native engine management
@@ -303,20 +319,28 @@ class Xtractor(torch.nn.Module):
         if stage == "pooled":
             numel, shape = None, None
         per = ctypes.c_int64(0)
-        if self.model_archi in ("halfresnet34", "resnet34"):
+        if self.model_archi in _RESNETS:
+            halves = (False, True, True, True)
+            Ws = (80, 40, 20, 10)
             if self.model_archi == "halfresnet34":
                 li = 0 if stage == "stem" else int(stage[5]) - 1 if stage.startswith("layer") else 3
                 C = (32, 64, 128, 256)[li]
+            elif self.model_archi == "fastresnet34":               # level 0 is carried with 32 channels (16 real + 16 zero)
+                li = 0 if stage == "stem" else int(stage[5]) - 1 if stage.startswith("layer") else 3
+                C = (32, 32, 64, 128)[li]
+                Ws, halves = (40, 20, 10, 10), (False, True, True, False)
             else:                                                  # resolution level of layer1..layer7 (strides 1,2,1,2,1,2,1)
                 li = 0 if stage == "stem" else (0, 1, 1, 2, 2, 3, 3)[int(stage[5]) - 1] if stage.startswith("layer") else 3
                 C = (128, 128, 256, 256)[li]
-            W = (80, 40, 20, 10)[li]
+            W = Ws[li]
             Hm = max(T)
-            for _ in range(li):
-                Hm = (Hm - 1) // 2 + 1
+            for l in range(1, li + 1):
+                if halves[l]:
+                    Hm = (Hm - 1) // 2 + 1
         else:
             C, W, Hm = (1536 if stage in ("tdnn5",) else 512), 1, max(T)
-        size = B * (2 * 2560 if self.model_archi in ("halfresnet34", "resnet34") else 3072) if stage == "pooled" else B * C * Hm * W
+        size = B * {"halfresnet34": 5120, "resnet34": 5120, "fastresnet34": 2560, "xvector": 3072}[self.model_archi] \
+            if stage == "pooled" else B * C * Hm * W
         out = torch.zeros(size, dtype=torch.float32, device=flat.device)
         with torch.cuda.device(flat.device):
             _lib.check(_lib.lib().skb_xtractor_debug_stage(h, flat.data_ptr(), _lib.i64_array(lengths), B, stage.encode(), Hm,

@@ -101,37 +101,42 @@ def test_embeddings_and_logits_match_oracle_and_golden(hr34):
     assert torch.allclose(emb.norm(dim=1).cpu(), torch.ones(4), atol=1e-5)
 
 
-R34_STAGES = ["stem"] + ["layer%d.%d" % (l + 1, b) for l, (n, _) in enumerate(R.RESNET34_STAGES) for b in range(n)]
+def _stages(table):
+    return ["stem"] + ["layer%d.%d" % (l + 1, b) for l, (n, _) in enumerate(table) for b in range(n)]
 
 
-def test_resnet34_blocks_embeddings_and_packing():
-    """The full-width ResNet34 trunk (128/256 channels, 7 layers): every block against the oracle, embeddings/logits
-    against the oracle and the recorded reference outputs, packing invariance bit for bit."""
-    m = make_xtractor("resnet34", 32, 256).cuda()
+@pytest.mark.parametrize("archi,prefix,table,real_c0", [("resnet34", "r34", R.RESNET34_STAGES, 128),
+                                                        ("fastresnet34", "f34", R.FASTRESNET34_STAGES, 16)])
+def test_other_resnet_trunks_blocks_embeddings_and_packing(archi, prefix, table, real_c0):
+    """The trunks that share the HalfResNet34 kernels -- ResNet34 (128/256 channels, 7 layers) and FastResNet34 (7x7
+    stride-(1,2) stem, 16..128 channels, layer4 widening without stride, pooling without global context): every block
+    against the oracle, embeddings/logits against the oracle and the recorded reference outputs, packing invariance."""
+    m = make_xtractor(archi, 32, 256).cuda()
     sd = {k: v.cpu() for k, v in m.state_dict().items()}
     g = golden("extraction_resnet34.npz")
-    waves = [synth.synth_wave(1, int(L), seed=int(s))[0] for L, s in zip(g["r34_lengths"], g["r34_seeds"])]
+    waves = [synth.synth_wave(1, int(L), seed=int(s))[0] for L, s in zip(g[prefix + "_lengths"], g[prefix + "_seeds"])]
     refs, outs = [], []
     for w in waves:
         col = {}
-        outs.append(R.resnet34_forward(sd, w.unsqueeze(0), collect=col))
+        outs.append(R.forward(sd, w.unsqueeze(0), archi, collect=col))
         refs.append(col)
     cw = [w.cuda() for w in waves]
-    for st in R34_STAGES:
+    for st in _stages(table):
         out = m.debug_stage(cw, st).cpu()
         for i, r in enumerate(refs):
             ref = r[st][0]
-            H = ref.shape[1]
-            assert out.shape[1] == ref.shape[0] and out.shape[3] == ref.shape[2], (st, out.shape, ref.shape)
-            err = ((out[i, :, :H, :].double() - ref.double()).norm() / ref.double().norm()).item()
+            C, H = ref.shape[0], ref.shape[1]
+            assert out.shape[1] >= C and out.shape[3] == ref.shape[2], (st, out.shape, ref.shape)
+            err = ((out[i, :C, :H, :].double() - ref.double()).norm() / ref.double().norm()).item()
             assert err < 2e-3, (st, i, err)
+            assert out[i, C:].abs().max().item() == 0.0 if out.shape[1] > C else True      # channel padding stays zero
     assert rel_l2(m.debug_stage(cw, "pooled").cpu(), torch.cat([r["pooled"] for r in refs])) < 2e-3
     logits, emb = m.extract_varlen(cw, want_logits=True)
     ref_emb, ref_logits = torch.cat([o[1] for o in outs]), torch.cat([o[0] for o in outs])
     assert rel_l2(emb.cpu(), ref_emb) < 1e-3 and min_cosine(emb.cpu(), ref_emb) >= 0.9999
-    assert rel_l2(emb.cpu(), g["r34_emb"]) < 1e-3
+    assert rel_l2(emb.cpu(), g[prefix + "_emb"]) < 1e-3
     assert (logits.cpu() - ref_logits).abs().max().item() < 3e-2
-    assert numpy.abs(logits.cpu().numpy() - g["r34_logits"]).max() < 3e-2
+    assert numpy.abs(logits.cpu().numpy() - g[prefix + "_logits"]).max() < 3e-2
     solo = torch.cat([m.extract_varlen([w]) for w in cw])
     assert torch.equal(emb, solo) and torch.equal(emb, m.extract_varlen(cw[::-1]).flip(0))
     lo2, em2 = m(torch.stack(waves[:2]).cuda(), is_eval=True)

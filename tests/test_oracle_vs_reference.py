@@ -13,7 +13,8 @@ from tests import kat
 pytestmark = pytest.mark.reference
 
 
-@pytest.mark.parametrize("archi,emb,L", [("halfresnet34", 256, 20000), ("xvector", 512, 40000)])
+@pytest.mark.parametrize("archi,emb,L", [("halfresnet34", 256, 20000), ("xvector", 512, 40000), ("resnet34", 256, 12000),
+                                         ("fastresnet34", 256, 20000)])
 def test_extraction_restatement_matches_reference(archi, emb, L):
     from oracle import ref_import
     m = ref_import.build_xtractor(32, archi, emb)
@@ -25,9 +26,27 @@ def test_extraction_restatement_matches_reference(archi, emb, L):
         lo, em = m(x, is_eval=True)
     lo2, em2 = R.forward(sd, x, archi)
     assert (em - em2).abs().max().item() < 2e-6 and (lo - lo2).abs().max().item() < 5e-5
-    fb = R.mel_filterbank(513, 90.0, 7600.0, 80, 16000) if archi == "halfresnet34" else R.mel_filterbank(1025, 133.333, 6855.4976, 100, 16000)
-    key = "preprocessor.MelSpec.mel_scale.fb" if archi == "halfresnet34" else "preprocessor.MFCC.MelSpectrogram.mel_scale.fb"
+    fb = R.mel_filterbank(513, 90.0, 7600.0, 80, 16000) if archi != "xvector" else R.mel_filterbank(1025, 133.333, 6855.4976, 100, 16000)
+    key = "preprocessor.MelSpec.mel_scale.fb" if archi != "xvector" else "preprocessor.MFCC.MelSpectrogram.mel_scale.fb"
     assert torch.equal(fb, sd[key])
+
+
+def test_resblock_is_unreachable_in_the_reference():
+    """`ResBlock` is only instantiated by the YAML / dict branch of Xtractor.__init__ (xvector.py:786-790), and
+    that branch cannot construct a model: a `conv2D` entry hits an undefined name (:763) and a `resblock` entry appends
+    a bare module to the list an OrderedDict is built from (:786, :792).  No model on the hot path contains a ResBlock;
+    the B200 engine therefore has no ResBlock operator (out of scope)."""
+    import contextlib, io
+    from oracle import ref_import
+    ref_import.import_reference()
+    from sidekit.nnet.xvector import Xtractor
+    base = {"loss": {"type": "aam", "aam_margin": 0.2, "aam_s": 30}, "preprocessor": {"type": "none", "feature_size": 80},
+            "activation": "ReLU", "stat_pooling": {"type": "mean_std", "weight_decay": 0.0},
+            "before_embedding": {"weight_decay": 0.0}, "embedding": {}, "after_embedding": {"weight_decay": 0.0}}
+    res = {"resblock1": {"input_channel": 32, "output_channel": 32}, "weight_decay": 0.0}
+    for seg, err in ((dict(res), TypeError), (dict({"conv2D": {}}, **res), NameError)):
+        with pytest.raises(err), contextlib.redirect_stdout(io.StringIO()):
+            Xtractor(10, dict(base, segmental=seg))
 
 
 def test_scoring_kat_recorded_from_reference():

@@ -346,6 +346,21 @@ def run_extras(args, device, peaks, dist_on, rank, world):
                                "ms_per_step": ms / args.steps,
                                "tflops": 2.0 * sum(tdnn_macs(L) for i in range(args.steps) for L in tb[i % 2][2]) / (ms / 1e3) / 1e12}
         del tdnn, tb
+        # ---- the other trunks that run on the HalfResNet34 kernels: ResNet34 (128/256 channels) and
+        # FastResNet34 (16..128 channels, frequency axis halved by the stem), single GPU only
+        if world == 1:
+            ob = make_batches(2, 32, seed=950, lo_s=2.0, hi_s=20.0, device=device)
+            for archi in ("resnet34", "fastresnet34"):
+                om = build_model(archi, 256, device)
+                fo = lambda i: om.extract_packed(ob[i % 2][1], ob[i % 2][2])
+                for i in range(3):
+                    fo(i)
+                ms = timed(fo, args.steps, False)
+                aud = sum(sum(ob[i % 2][2]) for i in range(args.steps)) / 16000.0
+                out[archi] = {"metric": "audio_seconds_per_second", "value": aud / (ms / 1e3), "unit": "audio-s/s",
+                              "workload": "%s 256-d, 32 utterances 2-20 s per step" % archi, "ms_per_step": ms / args.steps}
+                del om
+            del ob
         # ---- PLDA two-covariance scoring, 20k x 20k x 256 (rows sharded over ranks, no collective)
         Ne = Nt = 20000
         D = 256

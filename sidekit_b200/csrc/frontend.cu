@@ -129,29 +129,40 @@ __global__ void __launch_bounds__(WPC * 32, (640 / (WPC * 32)) > 0 ? 640 / (WPC 
     const int half_win = p.win >> 1;
 
     for (int frame = t_begin + warp; frame < t_end; frame += WPC) {
-        // ---- step 1: A points per lane straight from the waveform, transformed in registers
+        // ---- step 0: the frame's samples (pre-emphasis, reflect padding, window) into the frame buffer.  All the loads
+        // of the loop are independent, so eight of them are in flight per lane; fetched inside step 1 the compiler
+        // serialised them behind the FFT's registers (one L2 / HBM round trip per pair of points: 32 % of the MFCC
+        // kernel's stall samples, profiles/r01d_ncu_frontend_mfcc.txt).
+        float* ybuf = reinterpret_cast<float*>(z);
+        {
+            const int i_base = p.hop * frame - half_win;
+#pragma unroll 8
+            for (int n = lane; n < p.win; n += 32) {
+                int i = i_base + n;
+                if (i < 0) i = -i;
+                if (i >= L) i = 2 * (L - 1) - i;
+                const float cur = __ldg(x + i);
+                const float prev = __ldg(x + (i == 0 ? 1 : i - 1));
+                ybuf[n] = (cur - p.preemph * prev) * s_win[n];
+            }
+        }
+        __syncwarp();
+        // ---- step 1: A points per lane (sample pairs 2 (n1 * 32 + lane), +1), transformed in registers
         {
             float2 a[A];
-            const int i_base = p.hop * frame - half_win;
 #pragma unroll
             for (int n1 = 0; n1 < A; ++n1) {
-                float v[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int n = 2 * (n1 * 32 + lane) + e;      // sample n of the frame <-> y[hop*frame - win/2 + n], reflect padded
-                    float val = 0.f;
-                    if (n < p.win) {
-                        int i = i_base + n;
-                        if (i < 0) i = -i;
-                        if (i >= L) i = 2 * (L - 1) - i;
-                        const float cur = __ldg(x + i);
-                        const float prev = __ldg(x + (i == 0 ? 1 : i - 1));
-                        val = (cur - p.preemph * prev) * s_win[n];
-                    }
-                    v[e] = val;
+                // win <= n_fft / 2 (checked by frontend_launch): the upper half of the points is the zero padding, a
+                // compile-time fact that removes the first butterfly stage
+                const int n = 2 * (n1 * 32 + lane);
+                float2 v = make_float2(0.f, 0.f);
+                if (n1 < A / 2) {
+                    if (n + 1 < p.win) v = *reinterpret_cast<const float2*>(ybuf + n);
+                    else if (n < p.win) v.x = ybuf[n];
                 }
-                a[n1] = make_float2(v[0], v[1]);
+                a[n1] = v;
             }
+            __syncwarp();                                        // step 2 overwrites the buffer
             fft_dif<A>(a);
             // ---- step 2: twiddle and transpose through shared memory
 #pragma unroll
@@ -302,6 +313,7 @@ __global__ void cmvn_apply_kernel(float* __restrict__ feats, const long long* __
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace skb {
@@ -365,6 +377,16 @@ size_t frontend_cmvn_scratch_bytes(const FrontendConsts& fc, int B, int t_max) {
 }
 
 // feats: frame-major [sum T][n_out]; api_out optional (B, n_out, t_max).
+// frames per warp of a CTA (experiment knob: SKB_FE_FPW)
+static int fpw_override(int dflt) {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SKB_FE_FPW");
+        v = e ? atoi(e) : 0;
+    }
+    return v > 0 ? v : dflt;
+}
+
 int frontend_launch(const FrontendConsts& fc, const float* wave, const long long* wave_off, const int* wave_len,
                     const long long* feat_off, const int* n_frames, int B, int t_max, float* feats, float2* cmvn,
                     void* cmvn_part, bool normalise, float* api_out, cudaStream_t stream) {
@@ -378,6 +400,10 @@ int frontend_launch(const FrontendConsts& fc, const float* wave, const long long
         return SKB_ERR_ARG;
     }
     p.n_w = fc.n_w;
+    if (fc.win > fc.n_fft / 2) {
+        set_last_error(__FILE__, __LINE__, "front-end: the window must not exceed n_fft / 2");
+        return SKB_ERR_ARG;
+    }
     auto smem_bytes = [&](int NC, int WPC, int* dct_off) {
         const size_t zs = std::max<size_t>((size_t)(NC / 32) * 33, (size_t)NC + 2);      // complex slots per frame buffer (kernel: ZS)
         size_t floats = 2 * (size_t)NC + 2 * ((size_t)NC + 2) + 2 * (size_t)WPC * zs + (size_t)WPC * fc.n_mels + fc.win + fc.n_w +
@@ -389,7 +415,7 @@ int frontend_launch(const FrontendConsts& fc, const float* wave, const long long
     };
     if (fc.n_fft == 1024) {
         constexpr int NC = 512, WPC = 8;
-        const int frames_per_cta = 4 * WPC;
+        const int frames_per_cta = fpw_override(8) * WPC;
         dim3 grid((t_max + frames_per_cta - 1) / frames_per_cta, B);
         const size_t smem = smem_bytes(NC, WPC, &p.dct_smem_off);
         static bool configured = false;
@@ -405,7 +431,7 @@ int frontend_launch(const FrontendConsts& fc, const float* wave, const long long
     } else if (fc.n_fft == 2048) {
         // a frame needs 9.3 KB of shared memory and the tables 52 KB: 16 frame-warps in one CTA per SM
         constexpr int NC = 1024, WPC = 16;
-        const int frames_per_cta = 2 * WPC;
+        const int frames_per_cta = fpw_override(8) * WPC;
         dim3 grid((t_max + frames_per_cta - 1) / frames_per_cta, B);
         const size_t smem = smem_bytes(NC, WPC, &p.dct_smem_off);
         static bool configured = false;

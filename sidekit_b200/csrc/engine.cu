@@ -1175,12 +1175,13 @@ static int forward_tdnn(skb_xtractor* h, const float* wave, int norm_embedding, 
     {
         ProfScope ps(PROF_FRONTEND, st);
         SKB_TRY(frontend_launch(m.fe, wave, d64 + pl.o_wave_off, d32 + pl.o_wave_len, d64 + pl.o_feat_off, d32 + pl.o_nframes, B,
-                                pl.t_max, feats, (float2*)h->cmvn.p, h->cmvn_part.p, true, nullptr, st));
+                                pl.t_max, feats, (float2*)h->cmvn.p, h->cmvn_part.p, false, nullptr, st));
     }
+    // raw MFCCs + CMVN statistics; the pack kernel normalises on the fly (no separate pass over the features)
     const Level& L0 = pl.lv[0];
-    SKB_TRY(launch_pack_frames(m.bf16, feats, m.fe.n_out, L0.C, (int)pl.total_frames, d32 + pl.o_row_src, (uint16_t*)h->act[0].p,
-                               L0.plane, L0.G, st));
-    g_launches += 5;
+    SKB_TRY(launch_pack_frames(m.bf16, feats, m.fe.n_out, L0.C, (int)pl.total_frames, d32 + pl.o_row_src, d32 + L0.o_row_b,
+                               (const float2*)h->cmvn.p, (uint16_t*)h->act[0].p, L0.plane, L0.G, st));
+    g_launches += 4;
     for (int i = 0; i < 5; ++i) {
         int shifts[10];
         for (int k = 0; k < m.tdnn_k[i]; ++k) shifts[k] = k * m.tdnn_d[i];

@@ -929,8 +929,11 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int n_slice
 // Skinny dense layer C[m][n] = alpha * sum_k A[m][k] W[n][k] + bias[n] for M = batch size (<= a few hundred rows) and
 // large K (the 5120-wide pooled statistics): exact fp32 FMAs, K split over enough CTAs to fill the GPU, ordered
 // reduction.  `ws` needs n_slices * M * N floats (skinny_gemm_ws_floats).
+// The K split depends on N and K only -- never on the batch size M -- so that a row's summation order, and with it every
+// embedding bit, is the same whatever batch the utterance travels in.
 static int skinny_slices(int M, int N, int K) {
-    const int tiles = ((M + 63) / 64) * ((N + 63) / 64);
+    (void)M;
+    const int tiles = (N + 63) / 64;
     int z = (2 * kNumSMs + tiles - 1) / tiles;
     const int max_z = (K + 63) / 64;
     return z < 1 ? 1 : (z > max_z ? max_z : z);
@@ -958,32 +961,38 @@ int launch_skinny_gemm(const float* A, int M, int K, const float* W, int N, cons
 // Used by the TDNN path: (frames, C) features -> act[c/8][G + frame][8] (Wp == 1 geometry), zero padded channels.
 template <bool BF16>
 __global__ void pack_frames_kernel(const float* __restrict__ X, int C_src, int C_dst, int n_rows, const int* __restrict__ row_src,
+                                   const int* __restrict__ row_b, const float2* __restrict__ cmvn /* [B][C_src] (mean, rstd) or null */,
                                    uint16_t* __restrict__ out, long long plane, int G) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int chunks = C_dst >> 3;
     if (idx >= (long long)n_rows * chunks) return;
     const int row = (int)(idx % n_rows), j = (int)(idx / n_rows);
     const int src = row_src[row];
+    const int b = (cmvn != nullptr && src >= 0) ? row_b[row] : -1;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int c = j * 8 + e;
         v[e] = (src >= 0 && c < C_src) ? X[(size_t)src * C_src + c] : 0.f;
+        if (b >= 0 && c < C_src) {                     // CMVN on the fly, same arithmetic as cmvn_apply_kernel
+            const float2 ms = __ldg(cmvn + (size_t)b * C_src + c);
+            v[e] = (v[e] - ms.x) * ms.y;
+        }
     }
     uint4 o;
     o.x = pack2<BF16>(v[0], v[1]); o.y = pack2<BF16>(v[2], v[3]); o.z = pack2<BF16>(v[4], v[5]); o.w = pack2<BF16>(v[6], v[7]);
     *reinterpret_cast<uint4*>(out + ((size_t)j * plane + G + row) * 8) = o;
 }
 
-int launch_pack_frames(bool bf16, const float* X, int C_src, int C_dst, int n_rows, const int* row_src, uint16_t* out,
-                       long long plane, int G, cudaStream_t st) {
+int launch_pack_frames(bool bf16, const float* X, int C_src, int C_dst, int n_rows, const int* row_src, const int* row_b,
+                       const float2* cmvn, uint16_t* out, long long plane, int G, cudaStream_t st) {
     const long long total = (long long)n_rows * (C_dst / 8);
     if (total == 0) return SKB_OK;
     const int blocks = (int)((total + 255) / 256);
     if (bf16)
-        pack_frames_kernel<true><<<blocks, 256, 0, st>>>(X, C_src, C_dst, n_rows, row_src, out, plane, G);
+        pack_frames_kernel<true><<<blocks, 256, 0, st>>>(X, C_src, C_dst, n_rows, row_src, row_b, cmvn, out, plane, G);
     else
-        pack_frames_kernel<false><<<blocks, 256, 0, st>>>(X, C_src, C_dst, n_rows, row_src, out, plane, G);
+        pack_frames_kernel<false><<<blocks, 256, 0, st>>>(X, C_src, C_dst, n_rows, row_src, row_b, cmvn, out, plane, G);
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }

@@ -51,8 +51,8 @@ int launch_sgemm_nt(const float* A, const float* B, float* C, const float* bias,
 size_t skinny_gemm_ws_floats(int M, int N, int K);
 int launch_skinny_gemm(const float* A, int M, int K, const float* W, int N, const float* bias, float alpha, float* C, int ldc,
                        float* ws, cudaStream_t st);
-int launch_pack_frames(bool bf16, const float* X, int C_src, int C_dst, int n_rows, const int* row_src, uint16_t* out,
-                       long long plane, int G, cudaStream_t st);
+int launch_pack_frames(bool bf16, const float* X, int C_src, int C_dst, int n_rows, const int* row_src, const int* row_b,
+                       const float2* cmvn, uint16_t* out, long long plane, int G, cudaStream_t st);
 
 // scoring.cu: split-precision tcgen05 GEMM on packed fp16 operands (also used for the dense layers of the extractor)
 struct PackedOp {

@@ -155,6 +155,20 @@ def test_packing_invariance_is_bit_exact(hr34):
     assert torch.equal(packed, m.extract_varlen(waves))           # run-to-run determinism
 
 
+@pytest.mark.parametrize("which", ["hr34", "tdnn"])
+def test_packing_invariance_holds_across_batch_sizes(which, hr34, tdnn):
+    """An utterance's embedding must not depend on HOW MANY utterances share its batch (the dense head's K split, the
+    span tables and the work partition all change with the batch size): 150 utterances packed == the same ones in small
+    batches, bit for bit."""
+    m, _ = hr34 if which == "hr34" else tdnn
+    lo = 8000 if which == "hr34" else 12000
+    waves = [synth.synth_wave(1, lo + 37 * i, seed=700 + i)[0].cuda() for i in range(150)]
+    big = m.extract_varlen(waves)
+    small = torch.cat([m.extract_varlen(waves[i:i + 7]) for i in range(0, 150, 7)])
+    assert torch.equal(big, small)
+    assert torch.equal(big[[0, 77, 149]], torch.cat([m.extract_varlen([waves[i]]) for i in (0, 77, 149)]))
+
+
 def test_plan_cache_switches_and_evictions_leave_no_stale_state(hr34):
     """Geometries alternate (the engine keeps 8 plans and never clears its activation buffers): results stay bit-identical."""
     m, _ = hr34

@@ -84,6 +84,31 @@ struct DevBuf {
     }
 };
 
+// Pinned host staging (table uploads must not block the host: the copy is enqueued and the host goes on planning)
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return SKB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) {
+            set_last_error(__FILE__, __LINE__, cudaGetErrorString(e));
+            return SKB_ERR_CUDA;
+        }
+        cap = want;
+        return SKB_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 template <typename T>
 static int dev_upload(const std::vector<T>& v, T** out) {
     *out = nullptr;
@@ -633,11 +658,29 @@ struct skb_xtractor {
     bool plan_valid = false;
     // Recently used plans (geometry tables live on the device): a bulk extraction cycles through a handful of length
     // buckets, and rebuilding a plan costs a host pass over every frame plus a synchronous table upload.
-    struct CachedPlan { Plan plan; DevBuf tab32, tab64, pixmeta; unsigned long long stamp = 0; };
+    // A plan's device tables, their pinned staging copies and the event that marks the upload as done travel together as
+    // one SLOT.  A new geometry takes over the slot of the least recently used plan: no cudaFree / cudaMalloc (both
+    // synchronise the device) and no host wait -- the tables are copied asynchronously from the pinned staging, in stream
+    // order behind the kernels that may still be reading the slot's previous contents, so the host can plan the next
+    // batches while the GPU works on this one.
+    struct Slot {
+        DevBuf tab32, tab64, pixmeta;
+        PinnedBuf stage32, stage64;
+        cudaEvent_t uploaded = nullptr;
+        void release() {
+            tab32.release(); tab64.release(); pixmeta.release(); stage32.release(); stage64.release();
+            if (uploaded) cudaEventDestroy(uploaded);
+            uploaded = nullptr;
+        }
+    };
+    struct CachedPlan { Plan plan; Slot slot; unsigned long long stamp = 0; };
     std::vector<CachedPlan> cache;
     unsigned long long stamp = 0;
-    DevBuf pixmeta, brd, cmvn, cmvn_part, skinny_ws;
-    DevBuf tab32, tab64, feats, sums, scale, poolX, poolH, poolL, gc, hb, pooled, lin, emb_pre, emb, logits, wave, dbg;
+    Slot slot;                    // of the active plan
+    cudaStream_t last_stream = nullptr;
+    bool have_last_stream = false;
+    DevBuf brd, cmvn, cmvn_part, skinny_ws;
+    DevBuf feats, sums, scale, poolX, poolH, poolL, gc, hb, pooled, lin, emb_pre, emb, logits, wave, dbg;
     std::vector<DevBuf> act;      // activation buffers
     std::vector<size_t> act_bytes;
     PackedOp poolA;               // frames x 2560 packed fp16 operand of the first attention projection
@@ -657,19 +700,16 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st);
 static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream_t st) {
     Plan& pl = h->plan;
     if (h->plan_valid && pl.B == B && std::equal(lengths, lengths + B, pl.lengths.begin())) return SKB_OK;
-    // park the current plan in the cache, then look the requested one up
+    // the slots are reused in stream order: a change of stream needs one device-wide join
+    if (h->have_last_stream && h->last_stream != st) SKB_CUDA_CHECK(cudaDeviceSynchronize());
+    h->last_stream = st;
+    h->have_last_stream = true;
+    // park the current plan (with its slot) in the cache, then look the requested one up
     if (h->plan_valid) {
-        if (h->cache.size() >= kPlanCacheEntries) {
-            size_t oldest = 0;
-            for (size_t i = 1; i < h->cache.size(); ++i)
-                if (h->cache[i].stamp < h->cache[oldest].stamp) oldest = i;
-            h->cache[oldest].tab32.release(); h->cache[oldest].tab64.release(); h->cache[oldest].pixmeta.release();
-            h->cache.erase(h->cache.begin() + oldest);
-        }
         h->cache.emplace_back();
         skb_xtractor::CachedPlan& c = h->cache.back();
         std::swap(c.plan, h->plan);
-        std::swap(c.tab32, h->tab32); std::swap(c.tab64, h->tab64); std::swap(c.pixmeta, h->pixmeta);
+        std::swap(c.slot, h->slot);
         c.stamp = ++h->stamp;
         h->plan_valid = false;
     }
@@ -677,14 +717,23 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
         skb_xtractor::CachedPlan& c = h->cache[i];
         if (c.plan.B == B && std::equal(lengths, lengths + B, c.plan.lengths.begin())) {
             std::swap(c.plan, h->plan);
-            std::swap(c.tab32, h->tab32); std::swap(c.tab64, h->tab64); std::swap(c.pixmeta, h->pixmeta);
+            std::swap(c.slot, h->slot);
             h->cache.erase(h->cache.begin() + i);
-            h->d32 = (const int*)h->tab32.p;
-            h->d64 = (const long long*)h->tab64.p;
+            h->d32 = (const int*)h->slot.tab32.p;
+            h->d64 = (const long long*)h->slot.tab64.p;
             return activate_plan(h, st);
         }
     }
-    h->tab32.release(); h->tab64.release(); h->pixmeta.release();     // (moved into the cache, or left by a failed build)
+    // a new geometry: take over the slot of the least recently used plan once the cache is full (h->slot is empty here
+    // unless a previous build failed half-way, in which case it is simply reused)
+    if (h->cache.size() > kPlanCacheEntries) {
+        size_t oldest = 0;
+        for (size_t i = 1; i < h->cache.size(); ++i)
+            if (h->cache[i].stamp < h->cache[oldest].stamp) oldest = i;
+        h->slot.release();
+        std::swap(h->slot, h->cache[oldest].slot);
+        h->cache.erase(h->cache.begin() + oldest);
+    }
     pl = Plan();
     pl.B = B;
     pl.lengths.assign(lengths, lengths + B);
@@ -767,14 +816,23 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     pl.o_pool_off = pl.tab64.size(); pl.tab64.insert(pl.tab64.end(), pool_off.begin(), pool_off.end());
 
     int rc;
-    if ((rc = h->tab32.ensure(pl.tab32.size() * sizeof(int)))) return rc;
-    if ((rc = h->tab64.ensure(pl.tab64.size() * sizeof(long long)))) return rc;
-    // (synchronous copies: the host vectors are pageable and the plan is cached across calls)
-    SKB_CUDA_CHECK(cudaStreamSynchronize(st));
-    SKB_CUDA_CHECK(cudaMemcpy(h->tab32.p, pl.tab32.data(), pl.tab32.size() * sizeof(int), cudaMemcpyHostToDevice));
-    SKB_CUDA_CHECK(cudaMemcpy(h->tab64.p, pl.tab64.data(), pl.tab64.size() * sizeof(long long), cudaMemcpyHostToDevice));
-    h->d32 = (const int*)h->tab32.p;
-    h->d64 = (const long long*)h->tab64.p;
+    skb_xtractor::Slot& sl = h->slot;
+    const size_t b32 = pl.tab32.size() * sizeof(int), b64 = pl.tab64.size() * sizeof(long long);
+    if ((rc = sl.tab32.ensure(b32))) return rc;
+    if ((rc = sl.tab64.ensure(b64))) return rc;
+    // the staging copies of this slot's previous plan must have left the host before they are overwritten (they did,
+    // unless the host is a whole cache of batches ahead of the device)
+    if (sl.uploaded) SKB_CUDA_CHECK(cudaEventSynchronize(sl.uploaded));
+    else SKB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming));
+    if ((rc = sl.stage32.ensure(b32))) return rc;
+    if ((rc = sl.stage64.ensure(b64))) return rc;
+    memcpy(sl.stage32.p, pl.tab32.data(), b32);
+    memcpy(sl.stage64.p, pl.tab64.data(), b64);
+    SKB_CUDA_CHECK(cudaMemcpyAsync(sl.tab32.p, sl.stage32.p, b32, cudaMemcpyHostToDevice, st));
+    SKB_CUDA_CHECK(cudaMemcpyAsync(sl.tab64.p, sl.stage64.p, b64, cudaMemcpyHostToDevice, st));
+    SKB_CUDA_CHECK(cudaEventRecord(sl.uploaded, st));
+    h->d32 = (const int*)sl.tab32.p;
+    h->d64 = (const long long*)sl.tab64.p;
 
     int rc2 = build_pixmeta(h, st);
     if (rc2) return rc2;
@@ -900,9 +958,9 @@ static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
         if (L.has_sub) { L.o_pix_sub = total; total += n; }
         if (hr) { L.o_span = total; total += (size_t)span_table_size((int)n); }
     }
-    int rc = h->pixmeta.ensure(total * sizeof(int));
+    int rc = h->slot.pixmeta.ensure(total * sizeof(int));
     if (rc) return rc;
-    int* base = (int*)h->pixmeta.p;
+    int* base = (int*)h->slot.pixmeta.p;
     for (size_t l = 0; l < pl.lv.size(); ++l) {
         const Level& L = pl.lv[l];
         const int n = L.p_end - L.G;
@@ -965,7 +1023,7 @@ static int run_conv(skb_xtractor* h, const ConvW& cw, int kind, const Level& Lg,
     const int tile_m = conv_tile_m(cw.ncta);
     p.rows_pad = (tile_m + p.halo + max_shift + 7) / 8 * 8;
     p.act_slope = act == 1 ? 0.f : (act == 2 ? 0.2f : 1.f);
-    const int* pm = (const int*)h->pixmeta.p;
+    const int* pm = (const int*)h->slot.pixmeta.p;
     // the validity table of `pix_level` decides what is stored as non-zero (TDNN: same geometry, fewer frames per layer)
     p.pix_b = pm + (pix_level ? pix_level->o_pix_b : Lg.o_pix_b);
     p.pix_sub = Lnext ? pm + Lg.o_pix_sub : nullptr;
@@ -1103,7 +1161,7 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
         {
             // SE scales from conv2's INPUT (linearity of the convolution): one bandwidth-bound pass over y1 + small kernels
             ProfScope ps(PROF_SE, st);
-            const int* pm = (const int*)h->pixmeta.p;
+            const int* pm = (const int*)h->slot.pixmeta.p;
             SKB_TRY(launch_plane_sum(m.bf16, y1, L.plane, L.G, L.p_end, pm + L.o_pix_b, pm + L.o_span, bw.C,
                                      (unsigned long long*)h->sums.p, st));
             SKB_TRY(launch_se_scale(m.bf16, (unsigned long long*)h->sums.p, y1, L.plane, L.G, L.Wp, L.W, d32 + L.o_utt_row0,
@@ -1293,12 +1351,13 @@ int skb_xtractor_create(int archi, int n_tensors, const char* const* names, cons
 void skb_xtractor_destroy(skb_xtractor_t* h) {
     if (!h) return;
     free_model(&h->m);
-    DevBuf* bufs[] = {&h->tab32, &h->tab64, &h->feats, &h->sums, &h->scale, &h->poolX, &h->poolH, &h->poolL, &h->gc, &h->hb,
-                      &h->pooled, &h->lin, &h->emb_pre, &h->emb, &h->logits, &h->wave, &h->dbg, &h->pixmeta, &h->brd, &h->cmvn,
+    h->slot.release();
+    DevBuf* bufs[] = {&h->feats, &h->sums, &h->scale, &h->poolX, &h->poolH, &h->poolL, &h->gc, &h->hb,
+                      &h->pooled, &h->lin, &h->emb_pre, &h->emb, &h->logits, &h->wave, &h->dbg, &h->brd, &h->cmvn,
                       &h->cmvn_part, &h->skinny_ws};
     for (auto* b : bufs) b->release();
     for (auto& b : h->act) b.release();
-    for (auto& c : h->cache) { c.tab32.release(); c.tab64.release(); c.pixmeta.release(); }
+    for (auto& c : h->cache) c.slot.release();
     packed_free(&h->poolA);
     delete h;
 }

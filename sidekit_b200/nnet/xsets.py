@@ -134,10 +134,14 @@ def extract_embeddings(idmap_name, model_filename, data_root_name, device, batch
     order = numpy.argsort(lengths, kind="stable")
     emb = torch.empty((len(waves), model.embedding_size), dtype=torch.float32)
     with torch.no_grad():
-        # largest batch first: the engine sizes its work buffers once instead of growing them batch after batch
+        # largest batch first: the engine sizes its work buffers once instead of growing them batch after batch; the
+        # embeddings stay on the device until the end, so the host plans and enqueues batch k+1 while batch k runs
+        outs, index = [], []
         for batch in reversed(bulk.make_batches(order.tolist(), lengths, max_audio_seconds, sample_rate=sample_rate)):
-            out = model.extract_varlen([waves[i].to(device) for i in batch], norm_embedding=norm_embeddings)
-            emb[torch.as_tensor(batch)] = out.cpu()
+            outs.append(model.extract_varlen([waves[i].to(device, non_blocking=True) for i in batch], norm_embedding=norm_embeddings))
+            index.extend(batch)
+        if outs:
+            emb[torch.as_tensor(index)] = torch.cat(outs).cpu()
     embeddings = StatServer()
     embeddings.stat1 = emb.numpy().astype(numpy.float32)
     embeddings.modelset = numpy.array(modelset).astype('>U')

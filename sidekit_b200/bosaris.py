@@ -179,11 +179,14 @@ class Scores:
             if self._scoremat is None and self.scoremat_device is not None:
                 # the matrix is still on the device: gather the trials there instead of copying the whole matrix
                 # (3.2 GB of float64 at 20k x 20k) to the host first; same row-major order as numpy's boolean indexing
+                # (flat indices found on the host: a few 10^4 int64 cross PCIe instead of two M x S boolean masks)
                 import torch
                 dev = self.scoremat_device.device
-                tar = self.scoremat_device[torch.from_numpy(key.tar & self.scoremask).to(dev)]
-                non = self.scoremat_device[torch.from_numpy(key.non & self.scoremask).to(dev)]
-                return tar.cpu().numpy(), non.cpu().numpy()
+                flat = self.scoremat_device.reshape(-1)
+                it = torch.from_numpy(numpy.flatnonzero(key.tar & self.scoremask)).to(dev)
+                inn = torch.from_numpy(numpy.flatnonzero(key.non & self.scoremask)).to(dev)
+                both = flat[torch.cat([it, inn])].cpu().numpy()
+                return both[:it.numel()], both[it.numel():]
             return self.scoremat[key.tar & self.scoremask], self.scoremat[key.non & self.scoremask]
         new_score = self.align_with_ndx(key)
         return new_score.scoremat[key.tar & new_score.scoremask], new_score.scoremat[key.non & new_score.scoremask]

@@ -720,7 +720,10 @@ __global__ void att_act_kernel(float* __restrict__ h, const float* __restrict__ 
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)n_frames * A) return;
     const int fr = (int)(idx / A), a = (int)(idx % A);
-    const float v = fmaxf(h[idx] + hb[(size_t)frame_utt[fr] * A + a], 0.f);
+    // ReLU that lets a NaN through like torch's does (fmaxf would turn it into 0): an utterance with a single pooled frame
+    // has a NaN global-context std in the reference (unbiased estimator, pooling.py:68) and so a NaN embedding
+    const float x = h[idx] + hb[(size_t)frame_utt[fr] * A + a];
+    const float v = x > 0.f ? x : (x == x ? 0.f : x);
     h[idx] = tanhf(fmaf(v, bn_s[a], bn_t[a]));
 }
 

@@ -169,6 +169,23 @@ def test_packing_invariance_holds_across_batch_sizes(which, hr34, tdnn):
     assert torch.equal(big[[0, 77, 149]], torch.cat([m.extract_varlen([waves[i]]) for i in (0, 77, 149)]))
 
 
+def test_extreme_lengths_in_one_batch(hr34):
+    """The shortest utterance with two lines on the last level (1 280 samples: 9 frames) next to a 45 s one (4 501 frames)
+    in the same packed batch, against the oracle.  With a single pooled frame the reference's global-context std is NaN
+    (unbiased estimator over one sample, pooling.py:68): the engine returns NaN for that utterance too, and only for it."""
+    m, sd = hr34
+    waves = [synth.synth_wave(1, L, seed=900 + i)[0] for i, L in enumerate((1280, 720000, 1500))]
+    emb = m.extract_varlen([w.cuda() for w in waves]).cpu()
+    ref = torch.cat([R.forward(sd, w.unsqueeze(0), "halfresnet34")[1] for w in waves])
+    assert rel_l2(emb, ref) < 1e-3 and min_cosine(emb, ref) >= 0.9999
+    one = synth.synth_wave(1, 513, seed=903)[0]
+    assert not torch.isfinite(R.forward(sd, one.unsqueeze(0), "halfresnet34")[1]).any()
+    both = m.extract_varlen([one.cuda(), waves[0].cuda()]).cpu()
+    assert not torch.isfinite(both[0]).any() and torch.equal(both[1], emb[0])
+    with pytest.raises(RuntimeError):
+        m.extract_varlen([synth.synth_wave(1, 512, seed=1)[0].cuda()])        # torch.stft(reflect) needs L > n_fft / 2
+
+
 def test_plan_cache_switches_and_evictions_leave_no_stale_state(hr34):
     """Geometries alternate (the engine keeps 8 plans and never clears its activation buffers): results stay bit-identical."""
     m, _ = hr34

@@ -169,6 +169,20 @@ def test_packing_invariance_holds_across_batch_sizes(which, hr34, tdnn):
     assert torch.equal(big[[0, 77, 149]], torch.cat([m.extract_varlen([waves[i]]) for i in (0, 77, 149)]))
 
 
+def test_baseline_config1_dense_batch(hr34):
+    """BASELINE.json configs[0]: 64 synthetic 4 s utterances through ``Xtractor(...)(x, is_eval=True)`` (the reference's own
+    CPU-runnable case; SURVEY 8d: ``torch.randn(64, 64000, generator=seed 3) * 0.1``), every row against the oracle."""
+    m, sd = hr34
+    x = torch.randn(64, 64000, generator=torch.Generator().manual_seed(3)) * 0.1
+    logits, emb = m(x.cuda(), is_eval=True)
+    ref_lo, ref_em = R.forward(sd, x, "halfresnet34")
+    assert emb.shape == (64, 256) and logits.shape == (64, 32)
+    assert rel_l2(emb.cpu(), ref_em) < 1e-3 and min_cosine(emb.cpu(), ref_em) >= 0.9999
+    assert (logits.cpu() - ref_lo).abs().max().item() < 3e-2
+    one = m(x[5].cuda(), is_eval=True)[1]                      # 1-D input, as extract_xvectors.py feeds it
+    assert torch.equal(one[0], emb[5])
+
+
 def test_extreme_lengths_in_one_batch(hr34):
     """The shortest utterance with two lines on the last level (1 280 samples: 9 frames) next to a 45 s one (4 501 frames)
     in the same packed batch, against the oracle.  With a single pooled frame the reference's global-context std is NaN

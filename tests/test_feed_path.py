@@ -90,3 +90,34 @@ def test_extract_embeddings_from_wav_files(tmp_path):
     te.modelset = te.segset
     sc = sk.cosine_scoring(en, te, ndx)
     assert sc.validate() and numpy.isfinite(sc.scoremat).all()
+
+
+def test_kaldi_ark_scp_round_trip(tmp_path):
+    """x-vector tables in Kaldi's binary ark / scp layout (what extract_xvectors.py writes through kaldiio): header bytes
+    as published, scp offsets pointing at the binary marker, row matrices and vectors, speaker means."""
+    import numpy
+    from sidekit_b200 import kaldi_io
+    from sidekit_b200.statserver import StatServer
+    rng = numpy.random.default_rng(0)
+    X = rng.standard_normal((5, 16)).astype(numpy.float32)
+    ss = StatServer.from_embeddings(numpy.array(["utt%d" % i for i in range(5)]), X)
+    scp = str(tmp_path / "xv.scp")
+    ark = kaldi_io.write_xvectors(ss, scp)
+    raw = open(ark, "rb").read()
+    assert raw.startswith(b"utt0 \0BFM \4" + (1).to_bytes(4, "little") + b"\4" + (16).to_bytes(4, "little") + X[0].tobytes())
+    lines = open(scp).read().split("\n")
+    assert lines[0] == "utt0 %s:5" % ark and lines[1].startswith("utt1 %s:" % ark)
+    got = list(kaldi_io.read_scp(scp))
+    assert [k for k, _ in got] == list(ss.segset) and all(a.shape == (1, 16) for _, a in got)
+    assert numpy.array_equal(numpy.concatenate([a for _, a in got]), X)
+    assert [k for k, _ in kaldi_io.read_ark(ark)] == list(ss.segset)
+    kaldi_io.speaker_means(scp, {"spkA": ["utt0", "utt1"], "spkB": ["utt4"]}, str(tmp_path / "spk.scp"))
+    spk = dict(kaldi_io.read_scp(str(tmp_path / "spk.scp")))
+    m = X[:2].mean(0, keepdims=True)
+    assert numpy.allclose(spk["spkA"], m / numpy.linalg.norm(m)) and abs(numpy.linalg.norm(spk["spkB"]) - 1) < 1e-6
+    with kaldi_io.ArkScpWriter(str(tmp_path / "v.ark"), str(tmp_path / "v.scp")) as w:
+        w("vec", X[3])
+    assert numpy.array_equal(dict(kaldi_io.read_scp(str(tmp_path / "v.scp")))["vec"], X[3])
+    import pytest
+    with pytest.raises(ValueError):
+        kaldi_io.ArkScpWriter(str(tmp_path / "bad.ark"))("two words", X[0])

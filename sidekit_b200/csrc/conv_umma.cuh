@@ -65,6 +65,10 @@ struct ConvParams {
     const float* se_scale;         // [B][cout] or nullptr
     const uint16_t* res;           // residual planes in the INPUT pixel geometry (block input or shortcut conv), or nullptr
     long long res_plane;
+    // Per-(utterance, channel) totals of the STORED 16-bit outputs in 2^-15 fixed point (what plane_sum_kernel computes with
+    // one more pass over the tensor), accumulated by the epilogue: [n_utt][cout] or nullptr.  Only the N_CTA == 32 kernels
+    // with cout == 32 support it (32 per-thread 64-bit accumulators, flushed with atomics when the utterance changes).
+    unsigned long long* sums;
 };
 
 constexpr int kConvKC = 32;            // input channels per A/B stage (two K=16 MMAs)
@@ -113,6 +117,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     const int n_split = p.cout / N_CTA;
     const int n_items = p.n_tiles * n_split;
     const int n_kc = p.cin / kConvKC;
+    // Every CTA walks a CONTIGUOUS range of work items (item = tile * n_split + N split): the N splits of a tile follow each
+    // other on the same SM (the slab comes back from L2), and an epilogue thread stays inside one utterance for hundreds of
+    // tiles.
+    const int item_begin = (int)((long long)n_items * blockIdx.x / gridDim.x);
+    const int item_end = (int)((long long)n_items * (blockIdx.x + 1) / gridDim.x);
 
     if (threadIdx.x == 0) {
         // two MMA-issuing warps (one half of the accumulator tiles each) arrive on the "consumed" barriers
@@ -154,12 +163,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             const uint32_t plane_bytes = (uint32_t)p.rows_pad * 16;
             int s = 0;
             uint32_t ph = 1;     // ring position / parity kept incrementally (no divisions on the critical paths)
-            int tile = blockIdx.x / n_split, ns_ctr = blockIdx.x % n_split;
-            const int tile_step = gridDim.x / n_split, ns_step = gridDim.x % n_split;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int tile = item_begin / n_split, ns_ctr = item_begin % n_split;
+            for (int item = item_begin; item < item_end; ++item) {
                 const long long q0 = (long long)p.G + (long long)tile * Cfg::kTileM - p.halo;   // >= 0 thanks to the guard G
-                tile += tile_step; ns_ctr += ns_step;
-                if (ns_ctr >= n_split) { ns_ctr -= n_split; ++tile; }
+                if (++ns_ctr == n_split) { ns_ctr = 0; ++tile; }
                 for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(&a_empty[s], ph);
                     mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
@@ -186,12 +193,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                 const int n_st = n_it / p.tps;             // weight stages per item
                 int s = 0;
                 uint32_t ph = 1;
-                int ns = blockIdx.x % n_split;
-                const int ns_step = gridDim.x % n_split;
-                for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int ns = item_begin % n_split;
+                for (int item = item_begin; item < item_end; ++item) {
                     const uint16_t* wbase = p.w + (size_t)ns * n_it * (Cfg::kBStageBytes / 2);
-                    ns += ns_step;
-                    if (ns >= n_split) ns -= n_split;
+                    if (++ns == n_split) ns = 0;
                     for (int it = 0; it < n_st; ++it) {
                         mbar_wait(&b_empty[s], ph);
                         mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
@@ -216,21 +221,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                                    (static_cast<uint64_t>(1) << 46);
         const uint64_t desc_hi_b = (static_cast<uint64_t>((b_lbo >> 4) & 0x3FFF) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
                                    (static_cast<uint64_t>(1) << 46);
-        int as = 0, bs = 0, ns = blockIdx.x % n_split;
-        const int ns_step = gridDim.x % n_split;
+        int as = 0, bs = 0, ns = item_begin % n_split;
         uint32_t a_ph = 0, b_ph = 0, n_done = 0;
         if (p.b_resident) {
             mbar_wait(&b_full[0], 0);
             tc_fence_after();
         }
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+        for (int item = item_begin; item < item_end; ++item, ++n_done) {
             const int buf = (int)(n_done & 1);
             mbar_wait(&acc_empty[buf], ((n_done >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * Cfg::kAccCols;
             const int ns_item = ns;
-            ns += ns_step;
-            if (ns >= n_split) ns -= n_split;
+            if (++ns == n_split) ns = 0;
             if (p.bias_mma && elect_one()) {
                 const uint64_t ones_desc = (static_cast<uint64_t>(2048 >> 4) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
                                            (static_cast<uint64_t>(1) << 46) | ((smem_u32(ones_smem) >> 4) & 0x3FFF);
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
 #pragma unroll
             for (int mt = 0; mt < MTH; ++mt) {
                 const int pix = p.G + tile * Cfg::kTileM + (mt0 + mt) * 128 + q * 32 + lane;
-                const bool in_range = item < n_items && pix < p.p_end;
+                const bool in_range = item < item_end && pix < p.p_end;
                 bidx[mt] = in_range ? __ldg(p.pix_b + (pix - p.G)) : -1;
                 opix[mt] = in_range ? pix : -1;
                 if (p.pix_sub != nullptr) opix[mt] = in_range ? __ldg(p.pix_sub + (pix - p.G)) : -1;
@@ -328,16 +331,34 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         };
         int bidx_c[MTH], opix_c[MTH], bidx_n[MTH], opix_n[MTH], bidx_nn[MTH], opix_nn[MTH];
         uint4 rv_c[MTH][NCH], rv_n[MTH][NCH];
-        fetch_meta(blockIdx.x, bidx_c, opix_c);
-        fetch_meta(blockIdx.x + gridDim.x, bidx_n, opix_n);
-        if (FUSED) fetch_res(blockIdx.x, bidx_c, rv_c);
+        fetch_meta(item_begin, bidx_c, opix_c);
+        fetch_meta(item_begin + 1, bidx_n, opix_n);
+        if (FUSED) fetch_res(item_begin, bidx_c, rv_c);
         uint32_t n_done = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+        // fused channel totals (see ConvParams::sums): this thread's pixels stay inside one utterance for hundreds of
+        // consecutive tiles, so the totals live in registers and reach memory only when the utterance changes
+        constexpr bool kCanSum = (N_CTA == 32) && !FUSED;
+        constexpr int kSumRegs = kCanSum ? 32 : 1;
+        long long sacc[kSumRegs];
+        int sum_b = -1;
+#pragma unroll
+        for (int i = 0; i < kSumRegs; ++i) sacc[i] = 0ll;
+        const bool do_sums = kCanSum && p.sums != nullptr;
+        auto flush_sums = [&]() {
+            if (sum_b >= 0) {
+#pragma unroll
+                for (int i = 0; i < kSumRegs; ++i) {
+                    if (sacc[i] != 0ll) atomicAdd(p.sums + (size_t)sum_b * p.cout + i, (unsigned long long)sacc[i]);
+                    sacc[i] = 0ll;
+                }
+            }
+        };
+        for (int item = item_begin; item < item_end; ++item, ++n_done) {
             const int tile = item / n_split;
             const int n_base = (item - tile * n_split) * N_CTA;
             const int buf = (int)(n_done & 1);
-            if (FUSED) fetch_res(item + gridDim.x, bidx_n, rv_n);          // its metadata arrived during the previous item
-            fetch_meta(item + 2 * gridDim.x, bidx_nn, opix_nn);
+            if (FUSED) fetch_res(item + 1, bidx_n, rv_n);                  // its metadata arrived during the previous item
+            fetch_meta(item + 2, bidx_nn, opix_nn);
             mbar_wait(&acc_full[buf], (n_done >> 1) & 1);
             tc_fence_after();
 #pragma unroll
@@ -346,6 +367,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
 #pragma unroll
                 for (int mt = 0; mt < MTH; ++mt) {
                     const bool valid = bidx_c[mt] >= 0;
+                    if (kCanSum && do_sums && valid && bidx_c[mt] != sum_b) {
+                        flush_sums();
+                        sum_b = bidx_c[mt];
+                    }
                     float4 sc4[4];
                     if (FUSED && valid) {
                         if (p.scale_smem_bytes > 0) {
@@ -394,6 +419,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                             o.z = valid ? pack2<BF16>(v[j * 8 + 4], v[j * 8 + 5]) : 0u;
                             o.w = valid ? pack2<BF16>(v[j * 8 + 6], v[j * 8 + 7]) : 0u;
                             *reinterpret_cast<uint4*>(dst + j * plane8) = o;
+                            if constexpr (kCanSum) {
+                                if (do_sums && valid) {
+                                    // exactly plane_sum_kernel's arithmetic on the value just stored
+                                    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        float2 f = unpack2<BF16>(ow[e]);
+                                        if (BF16) { f.x = fminf(fmaxf(f.x, -65504.f), 65504.f); f.y = fminf(fmaxf(f.y, -65504.f), 65504.f); }
+                                        sacc[(c0 + j * 8 + 2 * e) % kSumRegs] += (long long)__float2int_rn(f.x * 32768.f);
+                                        sacc[(c0 + j * 8 + 2 * e + 1) % kSumRegs] += (long long)__float2int_rn(f.y * 32768.f);
+                                    }
+                                }
+                            }
                         }
                     }
                 }
@@ -406,6 +444,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                 for (int k = 0; k < NCH; ++k) rv_c[mt][k] = rv_n[mt][k];
             }
         }
+        if (kCanSum && do_sums) flush_sums();
         } else {
         // ---------------------------------------------------------------- epilogue warps (4..11)
         // two warps per TMEM lane quadrant; each takes half of the item's MT accumulator tiles
@@ -413,12 +452,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
         const int mt0 = ((warp - 4) >> 2) * MTH;
         uint32_t n_done = 0;
-        int tile_next = blockIdx.x / n_split, ns_next = blockIdx.x % n_split;
-        const int tile_step = gridDim.x / n_split, ns_step = gridDim.x % n_split;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+        int tile_next = item_begin / n_split, ns_next = item_begin % n_split;
+        for (int item = item_begin; item < item_end; ++item, ++n_done) {
             const int tile = tile_next, ns = ns_next;
-            tile_next += tile_step; ns_next += ns_step;
-            if (ns_next >= n_split) { ns_next -= n_split; ++tile_next; }
+            if (++ns_next == n_split) { ns_next = 0; ++tile_next; }
             const int buf = (int)(n_done & 1);
             const int p0 = p.G + tile * Cfg::kTileM;
             const int n_base = ns * N_CTA;

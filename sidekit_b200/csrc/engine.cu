@@ -983,7 +983,7 @@ static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
 // phase-split buffer of the next level (`Lnext`).
 static int run_conv(skb_xtractor* h, const ConvW& cw, int kind, const Level& Lg, const uint16_t* in, uint16_t* out, int act,
                     const int* tdnn_shifts, const float* se_scale, const uint16_t* res, const Level* pix_level,
-                    const Level* Lnext, cudaStream_t st) {
+                    const Level* Lnext, cudaStream_t st, unsigned long long* sums = nullptr) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
     p.in = in; p.in_plane = Lg.plane; p.w = cw.w; p.bias = cw.bias; p.out = out;
@@ -1030,6 +1030,7 @@ static int run_conv(skb_xtractor* h, const ConvW& cw, int kind, const Level& Lg,
     p.se_scale = se_scale;
     p.res = res;
     p.res_plane = Lg.plane;
+    p.sums = (sums != nullptr && cw.ncta == 32 && cw.cout == 32 && se_scale == nullptr) ? sums : nullptr;
     g_launches++;
     return launch_conv_umma(p, cw.ncta, h->m.bf16, st);
 }
@@ -1102,6 +1103,16 @@ static int head_and_logits(skb_xtractor* h, int norm_embedding, float* emb_out, 
     return SKB_OK;
 }
 
+// SKB_NO_FUSED_SUMS=1: keep the separate plane_sum pass on the 32-channel layers (A/B knob)
+static bool no_fused_sums() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SKB_NO_FUSED_SUMS");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, float* emb_out, float* logits_out,
                         const char* stop, int h_max, float* dbg_out, int64_t* per_utt, cudaStream_t st) {
     const Model& m = h->m;
@@ -1148,10 +1159,13 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
             return SKB_ERR_STATE;
         }
         uint16_t *y1 = buf(level, 2), *scb = buf(level, 4), *nxt = buf(level, cur ^ 1);
+        const bool sums_in_conv1 = bw.conv1.ncta == 32 && bw.conv1.cout == 32 && !no_fused_sums();
         const uint16_t* res = x;
         {
             ProfScope ps(PROF_CONV, st);
-            SKB_TRY(run_conv(h, bw.conv1, bw.stride == 2 ? 3 : 1, L, x, y1, 1, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+            // 32-channel layers: conv1's epilogue also accumulates the per-utterance channel totals of y1 (no plane_sum pass)
+            SKB_TRY(run_conv(h, bw.conv1, bw.stride == 2 ? 3 : 1, L, x, y1, 1, nullptr, nullptr, nullptr, nullptr, nullptr, st,
+                             sums_in_conv1 ? (unsigned long long*)h->sums.p : nullptr));
             if (bw.has_sc) {
                 // 1x1 shortcut; with stride 2 it reads phase (0, 0) = the first C_prev/8 planes of the phase-split input
                 SKB_TRY(run_conv(h, bw.sc, 0, L, x, scb, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st));
@@ -1162,8 +1176,9 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
             // SE scales from conv2's INPUT (linearity of the convolution): one bandwidth-bound pass over y1 + small kernels
             ProfScope ps(PROF_SE, st);
             const int* pm = (const int*)h->slot.pixmeta.p;
-            SKB_TRY(launch_plane_sum(m.bf16, y1, L.plane, L.G, L.p_end, pm + L.o_pix_b, pm + L.o_span, bw.C,
-                                     (unsigned long long*)h->sums.p, st));
+            if (!sums_in_conv1)
+                SKB_TRY(launch_plane_sum(m.bf16, y1, L.plane, L.G, L.p_end, pm + L.o_pix_b, pm + L.o_span, bw.C,
+                                         (unsigned long long*)h->sums.p, st));
             SKB_TRY(launch_se_scale(m.bf16, (unsigned long long*)h->sums.p, y1, L.plane, L.G, L.Wp, L.W, d32 + L.o_utt_row0,
                                     d32 + L.o_utt_count, B, bw.C, bw.C, bw.w2t, bw.conv2.bias, bw.se_w1, bw.se_w2,
                                     (float*)h->brd.p, (float*)h->scale.p, st));

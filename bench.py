@@ -310,6 +310,23 @@ def run_ours(args):
                                    "value": sum(sum(b[2]) for b in fresh) / 16000.0 / (ms_f / 1e3), "ms_per_step": ms_f / len(fresh),
                                    "workload": "%d batches of %d utterances, every batch a new length composition" % (len(fresh), args.utts)}
         del fresh
+        # feed path: 44.1 kHz files brought to the model's 16 kHz on the device (torchaudio.transforms.Resample of
+        # xsets.py:435 / extract_xvectors.py:144), 256 utterances 2-20 s; HBM-bound: 4 B read + 4 B written per sample
+        from sidekit_b200.nnet.preprocessor import Resample
+        rs = Resample(44100, 16000)
+        rl = numpy.round(44100 * numpy.random.default_rng(11).uniform(2.0, 20.0, size=256)).astype(numpy.int64)
+        rx = [torch.randn(int(rl.sum()), device=device) * 0.1 for _ in range(2)]          # 2 x 0.5 GB: larger than L2
+        for i in range(3):
+            ry = rs.resample_packed(rx[i % 2], rl)
+        ms_r = timed(lambda i: rs.resample_packed(rx[i % 2], rl), args.steps, False)
+        gbs = (rx[0].numel() + ry.numel()) * 4 * args.steps / (ms_r / 1e3) / 1e9
+        extra["resample_44k1_to_16k"] = {"metric": "audio_seconds_per_second", "unit": "audio-s/s",
+                                         "value": float(rl.sum()) / 44100.0 * args.steps / (ms_r / 1e3), "ms_per_step": ms_r / args.steps,
+                                         "workload": "256 utterances 2-20 s at 44.1 kHz -> 16 kHz, packed ragged batch",
+                                         "roofline": {"kernel": "resample_kernel", "bound": "hbm", "achieved": gbs,
+                                                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                                      "traffic": None}}
+        del rx, ry
 
     if rank == 0:
         cores = os.cpu_count() or 1

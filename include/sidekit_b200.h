@@ -138,6 +138,17 @@ int skb_scoremat_stats(const void* S_dev, int M, int N, int64_t ld, int is_f64, 
 int skb_scoremat_normalise(const void* S_dev, int M, int N, int64_t ld, int is_f64, const double* sub_dev,
                            const double* div_dev, void* out_dev, int64_t ld_out, void* stream);
 
+/* ---- feed path: sample-rate conversion ---------------------------------------------------
+ * torchaudio.transforms.Resample(orig_freq, new_freq)(speech) as sidekit/nnet/xsets.py:435, :452 and
+ * sidekit/bin/extract_xvectors.py:144 call it (Hann-windowed sinc, lowpass_filter_width 6, rolloff 0.99), on a packed
+ * batch: in_dev = the waveforms back to back, out_dev receives them back to back with ceil(new_r * L / orig_r) samples
+ * each.  wave_meta_dev: n_wav rows of four int64 {input offset, input length L, output offset, output length} (device);
+ * max_out = the largest output length.  orig_r / new_r are the rates divided by their gcd, width the filter half-width in
+ * input samples.  bank_dev / start_dev (device) are the compact polyphase filter bank: bank[k][ph] (ntap x new_r,
+ * tap-major) multiplies input sample q * orig_r - width + start[ph] + k of output q * new_r + ph. */
+int skb_resample(const float* in_dev, const int64_t* wave_meta_dev, int n_wav, int64_t max_out, int orig_r, int new_r,
+                 int width, const float* bank_dev, const int32_t* start_dev, int ntap, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

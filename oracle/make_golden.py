@@ -323,6 +323,23 @@ def golden_evaltail():
     print("evaltail.npz", sorted(out.keys()))
 
 
+def golden_resample():
+    """torchaudio.transforms.Resample outputs (the third-party call of xsets.py:435 / extract_xvectors.py:144) on seeded
+    Gaussian audio: the rate pairs a 16 kHz model meets in practice plus an upsampling and an awkward ratio."""
+    import torchaudio
+    out = {"torchaudio_version": numpy.array(torchaudio.__version__)}
+    cases = [(44100, 16000, 3001), (48000, 16000, 2500), (8000, 16000, 1999), (22050, 16000, 4410), (16000, 8000, 777),
+             (11025, 16000, 1500), (44100, 16000, 5)]
+    for i, (fo, fn, n) in enumerate(cases):
+        x = synth.synth_wave(2, n, seed=300 + i)
+        y = torchaudio.transforms.Resample(fo, fn)(x)
+        out["case%d_rates" % i] = numpy.array([fo, fn, n])
+        out["case%d_y" % i] = y.numpy()
+    out["n_cases"] = numpy.array(len(cases))
+    numpy.savez_compressed(os.path.join(GOLD, "resample.npz"), **out)
+    print("resample.npz", len(cases), "cases, torchaudio", torchaudio.__version__)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["scoring", "scoring_full", "extraction", "extraction_resnet34", "evaltail", "plda_training"]
@@ -340,3 +357,5 @@ if __name__ == "__main__":
         golden_extraction()
     if "evaltail" in which:
         golden_evaltail()
+    if "resample" in which:
+        golden_resample()

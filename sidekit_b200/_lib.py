@@ -58,6 +58,7 @@ def _declare(lib):
         "skb_eer": (i32, [vp, i64, vp, i64, ctypes.POINTER(f64)]),
         "skb_scoremat_stats": (i32, [vp, i32, i32, i64, i32, i32, i32, vp, vp, vp]),
         "skb_scoremat_normalise": (i32, [vp, i32, i32, i64, i32, vp, vp, vp, i64, vp]),
+        "skb_resample": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, vp, i32, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)       # AttributeError here = header / library mismatch: fail loudly

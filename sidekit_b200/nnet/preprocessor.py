@@ -124,3 +124,103 @@ class MfccFrontEnd(_FrontEndBase):
 
     def forward(self, x, is_eval=True):
         return self._run(x)
+
+
+def sinc_resample_bank(orig_freq, new_freq, lowpass_filter_width=6, rolloff=0.99):
+    """The polyphase filter bank of ``torchaudio.functional.resample`` (``sinc_interp_hann``), float64 -> float32 exactly
+    as torchaudio builds it, in the compact form the kernel takes: ``(orig_r, new_r, width, bank[ntap][new_r], start[new_r])``.
+
+    Taps whose argument is clamped to the edge of the window carry ``cos(pi / 2) ** 2 ~ 4e-33`` and are dropped; the
+    remaining ones of phase ``ph`` are the ``ntap`` consecutive taps from ``start[ph]`` on (zero padded at the end)."""
+    import numpy
+    if int(orig_freq) != orig_freq or int(new_freq) != new_freq:
+        raise Exception("Frequencies must be of integer type to ensure quality resampling computation.")
+    if lowpass_filter_width <= 0:
+        raise ValueError("Low pass filter width should be positive.")
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig_r, new_r = int(orig_freq) // g, int(new_freq) // g
+    base = min(orig_r, new_r) * rolloff
+    width = math.ceil(lowpass_filter_width * orig_r / base)
+    idx = numpy.arange(-width, width + orig_r, dtype=numpy.float64)[None, :] / orig_r
+    # torchaudio's phase offsets -ph / new are float32 (int64 arange / int under torch's true division), then float64
+    phase = (numpy.arange(0, -new_r, -1).astype(numpy.float32) / numpy.float32(new_r)).astype(numpy.float64)
+    t = (phase[:, None] + idx) * base
+    inside = numpy.abs(t) < lowpass_filter_width
+    t = numpy.clip(t, -lowpass_filter_width, lowpass_filter_width)
+    window = numpy.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    with numpy.errstate(invalid="ignore", divide="ignore"):
+        kern = numpy.where(t == 0, 1.0, numpy.sin(t) / t)
+    kern = (kern * window * (base / orig_r)).astype(numpy.float32)          # (new_r, 2 * width + orig_r)
+    start = numpy.array([int(numpy.argmax(row)) if row.any() else 0 for row in inside], dtype=numpy.int32)
+    count = inside.sum(axis=1)
+    ntap = int(count.max())
+    start = numpy.minimum(start, kern.shape[1] - ntap).astype(numpy.int32)
+    bank = numpy.zeros((ntap, new_r), dtype=numpy.float32)
+    for ph in range(new_r):
+        seg = kern[ph, start[ph]:start[ph] + ntap].copy()
+        seg[~inside[ph, start[ph]:start[ph] + ntap]] = 0.0
+        bank[:, ph] = seg
+    return orig_r, new_r, width, bank, start
+
+
+class Resample(torch.nn.Module):
+    """``torchaudio.transforms.Resample(orig_freq, new_freq)`` as the reference's feed path applies it to files whose rate
+    differs from the model's (sidekit/nnet/xsets.py:435, :452; sidekit/bin/extract_xvectors.py:144), on the device
+    (csrc/resample.cu).  ``forward`` takes a CUDA tensor ``(..., L)`` and returns ``(..., ceil(L * new / orig))``;
+    ``resample_packed`` takes utterances of different lengths back to back."""
+
+    def __init__(self, orig_freq=16000, new_freq=16000, resampling_method="sinc_interp_hann", lowpass_filter_width=6,
+                 rolloff=0.99):
+        super().__init__()
+        if resampling_method not in ("sinc_interp_hann", "sinc_interpolation"):
+            raise NotImplementedError("the CUDA resampler implements the Hann-windowed sinc (torchaudio's default)")
+        self.orig_freq, self.new_freq = orig_freq, new_freq
+        self.lowpass_filter_width, self.rolloff = lowpass_filter_width, rolloff
+        self._bank = sinc_resample_bank(orig_freq, new_freq, lowpass_filter_width, rolloff) if orig_freq != new_freq else None
+        self._dev = {}          # device -> (bank, start) tensors, uploaded once
+
+    def out_length(self, n):
+        if self._bank is None:
+            return int(n)
+        orig_r, new_r = self._bank[0], self._bank[1]
+        return (int(n) * new_r + orig_r - 1) // orig_r
+
+    def _device_bank(self, device):
+        if device not in self._dev:
+            bank, start = self._bank[3], self._bank[4]
+            self._dev[device] = (torch.from_numpy(bank).to(device), torch.from_numpy(start).to(device))
+        return self._dev[device]
+
+    def resample_packed(self, wave, lengths):
+        """``wave``: 1-D float32 CUDA tensor, the utterances back to back; ``lengths``: their sample counts."""
+        import numpy
+        from .. import _lib
+        if self._bank is None:
+            return wave
+        if not wave.is_cuda:
+            raise RuntimeError("sidekit_b200 has no CPU path: the waveform must be a CUDA tensor")
+        orig_r, new_r, width = self._bank[:3]
+        wave = wave.contiguous().float()
+        n_in = numpy.asarray(lengths, dtype=numpy.int64).reshape(-1)
+        assert wave.dim() == 1 and int(n_in.sum()) == wave.shape[0] and (n_in >= 0).all()
+        n_out = (n_in * new_r + orig_r - 1) // orig_r
+        out = torch.empty(int(n_out.sum()), dtype=torch.float32, device=wave.device)
+        if out.numel() == 0:
+            return out
+        meta = numpy.stack([numpy.cumsum(n_in) - n_in, n_in, numpy.cumsum(n_out) - n_out, n_out], axis=1)
+        bank, start = self._device_bank(wave.device)
+        with torch.cuda.device(wave.device):
+            meta_dev = torch.from_numpy(meta).pin_memory().to(wave.device, non_blocking=True)
+            _lib.check(_lib.lib().skb_resample(wave.data_ptr(), meta_dev.data_ptr(), len(n_in), int(n_out.max()), orig_r, new_r,
+                                               width, bank.data_ptr(), start.data_ptr(), bank.shape[0], out.data_ptr(),
+                                               _lib.stream_ptr()))
+        return out
+
+    def forward(self, waveform):
+        if self._bank is None:
+            return waveform
+        shape = waveform.shape
+        rows = waveform.reshape(-1, shape[-1])
+        out = self.resample_packed(rows.reshape(-1), [shape[-1]] * rows.shape[0])
+        return out.reshape(shape[:-1] + (self.out_length(shape[-1]),))

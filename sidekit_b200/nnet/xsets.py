@@ -67,9 +67,16 @@ class IdMapSet:
         self.sliding_window = sliding_window
         self.window_len = int(window_len * self.sample_rate)
         self.window_shift = int(window_shift * self.sample_rate)
+        self._resamplers = {}
 
     def __len__(self):
         return self.len
+
+    def _resampler(self, fs):
+        if fs not in self._resamplers:
+            from .preprocessor import Resample
+            self._resamplers[fs] = Resample(fs, self.sample_rate)
+        return self._resamplers[fs]
 
     def _path(self, index):
         return f"{self.data_path}/{self.idmap.rightids[index]}.{self.file_extension}"
@@ -80,7 +87,8 @@ class IdMapSet:
             # whole file (xsets.py:430-435; note: the file is NOT cut at `start` in this branch, only `duration` is)
             speech, fs = read_wav(self._path(index))
             if fs != self.sample_rate:
-                raise NotImplementedError("resampling is out of scope (%d Hz file, %d Hz model)" % (fs, self.sample_rate))
+                # torchaudio.transforms.Resample(nfo.sample_rate, self.sample_rate) of :434-435, on the device
+                speech = self._resampler(fs)(speech.cuda(non_blocking=True))
             duration = int(speech.shape[0] - start)
         else:
             duration = int(self.idmap.stop[index] * 0.01 * self.sample_rate) - start

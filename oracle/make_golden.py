@@ -323,6 +323,62 @@ def golden_evaltail():
     print("evaltail.npz", sorted(out.keys()))
 
 
+def text_io_reference(out_dir, objects):
+    """Write ``objects`` (tests/test_text_io.py:_objects, sidekit_b200 containers) with the REFERENCE's writers and read the
+    files back with its readers -> dict of arrays.  ``check_path_existance`` (sidekit_wrappers.py:73-89) drops the
+    return value of the decorated readers, so the undecorated functions are taken from the wrapper's closure."""
+    ref_import.import_reference()
+    from sidekit.bosaris import IdMap, Key, Ndx, Scores
+    key, ndx, sc, sc32, im = objects
+
+    def raw(method):
+        f = getattr(method, "__func__", method)
+        return f.__closure__[0].cell_contents if f.__closure__ else f
+
+    def fill(dst, src, names):
+        for n in names:
+            setattr(dst, n, getattr(src, n))
+        return dst
+
+    p = lambda n: os.path.join(out_dir, n)
+    fill(Key(), key, ("modelset", "segset", "tar", "non")).write_txt(p("key.txt"))
+    fill(Ndx(), ndx, ("modelset", "segset", "trialmask")).save_txt(p("ndx.txt"))
+    fill(Scores(), sc, ("modelset", "segset", "scoremask", "scoremat")).write_txt(p("scores64.txt"))
+    fill(Scores(), sc32, ("modelset", "segset", "scoremask", "scoremat")).write_txt(p("scores32.txt"))
+    rim = fill(IdMap(), im, ("leftids", "rightids", "start", "stop"))
+    rim.write_txt(p("idmap4.txt"))
+    rim.start = numpy.array([None] * len(im.leftids), dtype="|O")
+    rim.stop = numpy.array([None] * len(im.leftids), dtype="|O")
+    rim.write_txt(p("idmap_none.txt"))
+    with open(p("idmap2.txt"), "w") as f:
+        f.writelines("%s %s\n" % (a, b) for a, b in zip(im.leftids, im.rightids))
+    out = {}
+    k = Key.read_txt(p("key.txt"))
+    out.update(key_modelset=k.modelset.astype("U"), key_segset=k.segset.astype("U"), key_tar=k.tar, key_non=k.non)
+    n = raw(Ndx.read_txt)(Ndx, p("ndx.txt"))
+    out.update(ndx_modelset=n.modelset.astype("U"), ndx_segset=n.segset.astype("U"), ndx_trialmask=n.trialmask)
+    for name in ("scores64", "scores32"):
+        s_ = raw(Scores.read_txt)(Scores, p(name + ".txt"))
+        out.update({name + "_modelset": s_.modelset.astype("U"), name + "_segset": s_.segset.astype("U"),
+                    name + "_scoremask": s_.scoremask, name + "_scoremat": s_.scoremat})
+    i4 = raw(IdMap.read_txt)(IdMap, p("idmap4.txt"))
+    out.update(idmap4_leftids=i4.leftids.astype("U"), idmap4_rightids=i4.rightids.astype("U"), idmap4_start=i4.start, idmap4_stop=i4.stop)
+    i2 = raw(IdMap.read_txt)(IdMap, p("idmap2.txt"))
+    assert all(v is None for v in i2.start)
+    out.update(idmap2_leftids=i2.leftids.astype("U"))
+    return out
+
+
+def golden_text_io():
+    sys.path.insert(0, os.path.join(ROOT))
+    from tests.test_text_io import _objects
+    d = os.path.join(GOLD, "text_io")
+    os.makedirs(d, exist_ok=True)
+    out = text_io_reference(d, _objects())
+    numpy.savez_compressed(os.path.join(d, "read_back.npz"), **out)
+    print("text_io/", sorted(os.listdir(d)))
+
+
 def golden_resample():
     """torchaudio.transforms.Resample outputs (the third-party call of xsets.py:435 / extract_xvectors.py:144) on seeded
     Gaussian audio: the rate pairs a 16 kHz model meets in practice plus an upsampling and an awkward ratio."""
@@ -359,3 +415,5 @@ if __name__ == "__main__":
         golden_evaltail()
     if "resample" in which:
         golden_resample()
+    if "text_io" in which:
+        golden_text_io()

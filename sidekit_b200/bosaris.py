@@ -5,6 +5,8 @@ Id matching is an O(N) hash join with the reference's ordering semantics (first 
 """
 import logging
 
+import os
+
 import numpy
 
 try:
@@ -58,6 +60,23 @@ def _device_to_numpy(t, chunk_bytes=128 << 20):
     return out
 
 
+def _read_columns(path, n_min):
+    """Whitespace-separated columns of a text file (lines are ``rstrip().split()`` like ndx.py:216 / scores.py:379)."""
+    with open(path, "r") as f:
+        rows = [l.rstrip().split() for l in f]
+    rows = [r for r in rows if len(r)]
+    for r in rows:
+        if len(r) < n_min:
+            raise IndexError("list index out of range")            # what the reference's lines[ii][k] raises
+    return rows
+
+
+def _makedirs_for(path):
+    d = os.path.dirname(path)
+    if d != "" and not os.path.exists(d):
+        os.makedirs(d)
+
+
 class Key:
     """Trial key (key.py:49-110): ``tar`` / ``non`` (M, S) bool matrices over ``modelset`` x ``segset``."""
 
@@ -67,7 +86,7 @@ class Key:
         self.tar = numpy.array([], dtype="bool")
         self.non = numpy.array([], dtype="bool")
         if key_file_name is not None:
-            raise NotImplementedError("Key file IO is out of scope; pass models / testsegs / trials")
+            raise NotImplementedError("HDF5 Key files need h5py (not in this image); use Key.read_txt or pass models / testsegs / trials")
         models, testsegs, trials = numpy.asarray(models), numpy.asarray(testsegs), numpy.asarray(trials)
         if models.shape[0]:
             # key.py:79-97 vectorised: the LAST trial listed for a (model, segment) pair decides (dict(zip(...)))
@@ -86,6 +105,21 @@ class Key:
         key.modelset, key.segset, key.tar, key.non = modelset, segset, tar, non
         assert key.validate(), "Wrong Key format"
         return key
+
+    @staticmethod
+    def read_txt(input_file_name):
+        """``model segment target|nontarget`` lines -> Key (key.py:262-304): sorted-unique model / segment sets, the LAST
+        line of a (model, segment) pair decides, anything but the two labels leaves the trial unset."""
+        rows = _read_columns(input_file_name, 3)
+        col = lambda k: numpy.array([r[k] for r in rows], dtype="U")
+        return Key(models=col(0), testsegs=col(1), trials=col(2)) if rows else Key()
+
+    def write_txt(self, output_file_name):
+        """key.py:151-164: per model, its target trials then its non-target trials, in ``segset`` order."""
+        with open(output_file_name, "w") as fid:
+            for m in range(self.modelset.shape[0]):
+                for label, mask in (("target", self.tar), ("nontarget", self.non)):
+                    fid.writelines("{} {} {}\n".format(self.modelset[m], seg, label) for seg in self.segset[mask[m, ]])
 
     def to_ndx(self):
         ndx = Ndx()
@@ -108,7 +142,7 @@ class Ndx:
         self.segset = numpy.empty(0, dtype="|O")
         self.trialmask = numpy.array([], dtype="bool")
         if ndx_file_name != "":
-            raise NotImplementedError("Ndx file IO is out of scope; set modelset / segset / trialmask directly")
+            raise NotImplementedError("HDF5 Ndx files need h5py (not in this image); use Ndx.read_txt or set the fields directly")
         if len(models):
             # every (model, segment) pair listed is a trial (ndx.py:73-79), vectorised
             modelset, mi = numpy.unique(models, return_inverse=True)
@@ -116,6 +150,21 @@ class Ndx:
             mask = numpy.zeros((modelset.shape[0], segset.shape[0]), dtype="bool")
             mask[mi, si] = True
             self.modelset, self.segset, self.trialmask = modelset, segset, mask
+
+    @classmethod
+    def read_txt(cls, input_filename):
+        """``model segment`` lines -> Ndx with sorted-unique sets (ndx.py:208-236).  Returns the object: the reference's
+        ``check_path_existance`` decorator swallows the return value, so its own ``Ndx.read_txt`` yields None."""
+        rows = _read_columns(input_filename, 2)
+        ndx = cls(models=numpy.array([r[0] for r in rows], dtype="|O"), testsegs=numpy.array([r[1] for r in rows], dtype="|O"))
+        assert ndx.validate(), "Wrong Ndx format"
+        return ndx
+
+    def save_txt(self, output_file_name):
+        """ndx.py:115-126: one ``model segment`` line per trial, row by row."""
+        with open(output_file_name, "w") as fid:
+            for m in range(self.modelset.shape[0]):
+                fid.writelines("{} {}\n".format(self.modelset[m], s) for s in self.segset[self.trialmask[m, ]])
 
     def filter(self, modlist, seglist, keep):
         """Same semantics as ndx.py:128-165 (order of the Ndx kept, every occurrence kept), O(N) with hash sets."""
@@ -148,7 +197,7 @@ class Scores:
 
     def __init__(self, scores_file_name=""):
         if scores_file_name != "":
-            raise NotImplementedError("Scores file IO is out of scope")
+            raise NotImplementedError("HDF5 Scores files need h5py (not in this image); use Scores.read_txt")
         self.modelset = numpy.empty(0, dtype="|O")
         self.segset = numpy.empty(0, dtype="|O")
         self.scoremask = numpy.array([], dtype="bool")
@@ -164,6 +213,37 @@ class Scores:
     @scoremat.setter
     def scoremat(self, value):
         self._scoremat = value
+
+    def write_txt(self, output_file_name):
+        """scores.py:118-131: one ``model segment score`` line per scored trial, scores printed as ``str`` of the
+        matrix's own dtype (float32 for cosine / as-norm, float64 for PLDA).  The directory is created when missing (the
+        reference also tries to create ``''`` for a bare file name and fails there; not reproduced)."""
+        _makedirs_for(output_file_name)
+        mat = self.scoremat
+        with open(output_file_name, "w") as fid:
+            for m in range(self.modelset.shape[0]):
+                sel = self.scoremask[m, ]
+                fid.writelines("{} {} {}\n".format(self.modelset[m], seg, sc) for seg, sc in zip(self.segset[sel], mat[m, sel]))
+
+    @classmethod
+    def read_txt(cls, input_file_name):
+        """``model segment score`` lines -> Scores over the sorted-unique sets, float64, then ``sort()`` (scores.py:371-412).
+        Returns the object (the reference's decorator swallows it, see ``Ndx.read_txt``)."""
+        rows = _read_columns(input_file_name, 3)
+        s = cls()
+        models = numpy.array([r[0] for r in rows], dtype="|O")
+        testsegs = numpy.array([r[1] for r in rows], dtype="|O")
+        scores = numpy.array([float(r[2]) for r in rows], dtype=numpy.float64)
+        modelset, mi = numpy.unique(models, return_inverse=True)
+        segset, si = numpy.unique(testsegs, return_inverse=True)
+        mask = numpy.zeros((modelset.shape[0], segset.shape[0]), dtype="bool")
+        mat = numpy.zeros((modelset.shape[0], segset.shape[0]))
+        mask[mi, si] = True
+        mat[mi, si] = scores
+        s.modelset, s.segset, s.scoremask, s.scoremat = modelset, segset, mask, mat
+        assert s.validate(), "Wrong Scores format"
+        s.sort()
+        return s
 
     def validate(self):
         ok = self.scoremat.shape == self.scoremask.shape

@@ -7,7 +7,8 @@ torchcodec), and instead of one ``forward`` per file -- a few hundred small laun
 ALL segments / sliding windows of the id map are cut on the host, length-bucketed and pushed through
 ``Xtractor.extract_varlen`` as packed batches (``bulk.make_batches``): the engine's packed layout makes a batch of
 different lengths exact, so the embeddings are the same as the one-by-one loop, bit for bit.  Augmentation
-(``transform_pipeline``), resampling and HDF5 IO are out of scope and raise.
+(``transform_pipeline``) and HDF5 IO are out of scope and raise; files at another sample rate are resampled on the
+device (``preprocessor.Resample``); ``IdMap`` reads / writes the reference's text format.
 """
 import wave as _wave
 
@@ -22,7 +23,7 @@ class IdMap:
 
     def __init__(self, idmap_filename=''):
         if idmap_filename != '':
-            raise NotImplementedError("IdMap file IO is out of scope; set leftids / rightids / start / stop directly")
+            raise NotImplementedError("HDF5 IdMap files need h5py (not in this image); use IdMap.read_txt or set the fields directly")
         self.leftids = numpy.empty(0, dtype="|O")
         self.rightids = numpy.empty(0, dtype="|O")
         self.start = numpy.empty(0, dtype="|O")
@@ -31,6 +32,40 @@ class IdMap:
     def validate(self, warn=False):
         ok = self.leftids.shape == self.rightids.shape == self.start.shape == self.stop.shape
         return bool(ok and self.leftids.ndim == 1)
+
+    def write_txt(self, output_file_name):
+        """idmap.py:118-126: ``left right start stop`` per line; absent boundaries are written as the string ``None``
+        (which ``read_txt`` cannot parse back -- a reference quirk kept as is)."""
+        with open(output_file_name, "w") as f:
+            for left, right, start, stop in zip(self.leftids, self.rightids, self.start, self.stop):
+                f.write(" ".join(filter(None, (left, right, str(start), str(stop)))) + "\n")
+
+    @classmethod
+    def read_txt(cls, input_file_name):
+        """idmap.py:312-340: two columns (ids only, ``start`` / ``stop`` = None) or four (integer boundaries); the column
+        count is taken from the first line split on single spaces, like the reference.  Returns the object (the
+        reference's ``check_path_existance`` decorator swallows the return value)."""
+        idmap = cls()
+        with open(input_file_name, "r") as f:
+            columns = len(f.readline().split(" "))
+        with open(input_file_name, "r") as f:
+            rows = [l.split() for l in f if l.strip()]
+        if columns == 2:
+            idmap.leftids = numpy.array([r[0] for r in rows], dtype="|O")
+            idmap.rightids = numpy.array([r[1] for r in rows], dtype="|O")
+            idmap.start = numpy.empty(idmap.rightids.shape, "|O")
+            idmap.stop = numpy.empty(idmap.rightids.shape, "|O")
+        elif columns == 4:
+            idmap.leftids = numpy.array([r[0] for r in rows], dtype="|O")
+            idmap.rightids = numpy.array([r[1] for r in rows], dtype="|O")
+            try:
+                idmap.start = numpy.array([int(r[2]) for r in rows], dtype="int")
+                idmap.stop = numpy.array([int(r[3]) for r in rows], dtype="int")
+            except ValueError as e:
+                raise ValueError("could not convert string to int64: %s" % e)
+        if not idmap.validate():
+            raise Exception("Wrong format of IdMap")
+        return idmap
 
 
 def read_wav(path, frame_offset=0, num_frames=-1):
@@ -55,7 +90,7 @@ class IdMapSet:
     def __init__(self, idmap_name, data_path, file_extension, transform_pipeline={}, transform_number=1,
                  sliding_window=False, window_len=3., window_shift=1.5, sample_rate=16000, min_duration=0.165):
         if not isinstance(idmap_name, IdMap):
-            raise NotImplementedError("IdMap file IO is out of scope; pass an IdMap object")
+            raise NotImplementedError("HDF5 IdMap files need h5py (not in this image); pass an IdMap object (IdMap.read_txt)")
         if len(transform_pipeline):
             raise NotImplementedError("data augmentation is out of scope of the inference path")
         self.idmap = idmap_name

@@ -142,6 +142,21 @@ def full_plda_scoring(en_ids, E, te_ids, T, ndx_models, ndx_segs, trialmask, mu,
     return models, segs, mask, S
 
 
+def mahalanobis_scoring(en_ids, E, te_ids, T, ndx_models, ndx_segs, trialmask, m):
+    """mahalanobis_scoring, iv_scoring.py:116-156 (check_missing=True: both sets aligned with the cleaned ndx)."""
+    E = E.astype(numpy.float64)
+    T = T.astype(numpy.float64)
+    if numpy.unique(en_ids).shape != en_ids.shape:
+        en_ids, E = mean_per_model(en_ids, E)
+    models, segs, mask, ri, ci = check_missing(en_ids, te_ids, ndx_models, ndx_segs, trialmask)
+    E, T = E[ri], T[ci]
+    S = numpy.zeros((E.shape[0], T.shape[0]))
+    for i in range(E.shape[0]):
+        diff = E[i, :] - T
+        S[i, :] = -0.5 * numpy.sum(numpy.dot(diff, m) * diff, axis=1)
+    return models, segs, mask, S
+
+
 def two_covariance_scoring(en_ids, E, te_ids, T, ndx_models, ndx_segs, trialmask, W, B):
     """two_covariance_scoring, iv_scoring.py:159-212 (no centring)."""
     E = E.astype(numpy.float64)

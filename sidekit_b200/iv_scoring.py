@@ -194,6 +194,28 @@ def PLDA_scoring(enroll, test, ndx, mu, F, G, Sigma, test_uncertainty=None, Vtra
     return full_PLDA_scoring(enroll, test, ndx, mu, F, G, Sigma, p_known=p_known, scaling_factor=scaling_factor)
 
 
+def mahalanobis_scoring(enroll, test, ndx, m, check_missing=True):
+    """``-0.5 (e_i - t_j)' m (e_i - t_j)`` (iv_scoring.py:116-156), float64 like the reference.
+
+    Like the reference it aligns (reorders / shrinks) the caller's ``enroll`` / ``test`` in place.  Expanded for the score GEMM: ``0.5 e'(m + m')t - 0.5 e'me - 0.5 t'mt``."""
+    assert isinstance(enroll, StatServer), 'First parameter should be a StatServer'
+    assert isinstance(test, StatServer), 'Second parameter should be a StatServer'
+    assert isinstance(ndx, Ndx), 'Third parameter should be an Ndx'
+    assert enroll.stat1.shape[1] == test.stat1.shape[1], 'I-vectors dimension mismatch'
+    assert enroll.stat1.shape[1] == m.shape[0], 'I-vectors and Mahalanobis matrix dimension mismatch'
+    if not numpy.unique(enroll.modelset).shape == enroll.modelset.shape:
+        logging.warning("Enrollment models are not unique, average i-vectors")
+        enroll = enroll.mean_stat_per_model()
+    clean_ndx = _check_missing_model(enroll, test, ndx) if check_missing else ndx
+    m = numpy.asarray(m, dtype=numpy.float64)
+    dev = _device()
+    E, T = _dev32(enroll.stat1, dev), _dev32(test.stat1, dev)
+    Ep, model_part = _quadratic_prepare(E, None, 0.5 * (m + m.T), -m)          # rowterm = 0.5 * e'(-m)e
+    Tc, seg_part = _quadratic_prepare(T, None, None, -m)
+    S = score_matrix(Ep, Tc, model_part, seg_part, passes=0, out_dtype=torch.float64)
+    return _finish(clean_ndx, S)
+
+
 def two_covariance_scoring(enroll, test, ndx, W, B, check_missing=True):
     """Two-covariance scores (iv_scoring.py:159-212).  Like the reference it works on the caller's objects:
     ``enroll`` / ``test`` are aligned (reordered / shrunk) in place."""

@@ -34,3 +34,6 @@ KAT = {
     "twocov": dict(row0=[-1.8489118997, -2.4999501581, -0.2869733666], total=-14.617168376538972, dtype="float64"),
     "cosine": dict(row0=[0.41571918, 0.021552714, -0.10463461], total=1.7147858142852783, dtype="float32"),
 }
+
+# mahalanobis_scoring with m = inv(Sigma) + 0.05 * triu(F F') (not symmetric): row 0 of the (4, 3) matrix
+KAT_MAHALANOBIS_ROW0 = [-3.6858964595, -5.0085152223, -1.9150206526]

@@ -53,7 +53,7 @@ def test_scoring_kat_recorded_from_reference():
     """Re-derive SURVEY.md Appendix B from the unmodified reference and compare with tests/kat.py and the oracle."""
     from oracle import ref_import
     sidekit = ref_import.import_reference()
-    from sidekit.iv_scoring import cosine_scoring, PLDA_scoring, two_covariance_scoring
+    from sidekit.iv_scoring import cosine_scoring, PLDA_scoring, two_covariance_scoring, mahalanobis_scoring
     k = kat.kat_inputs()
 
     def ss(ids, X):
@@ -78,6 +78,14 @@ def test_scoring_kat_recorded_from_reference():
         "cosine": (cosine_scoring(ss(k["en_ids"], k["en"]), ss(k["te_ids"], k["te"]), ndx(), device=torch.device("cpu")),
                    S.cosine_scoring(*a)),
     }
+    # mahalanobis_scoring (iv_scoring.py:116-156); pinned by tests/kat.py too
+    M = numpy.linalg.inv(k["Sigma"]) + 0.05 * numpy.triu(k["F"] @ k["F"].T)          # not symmetric on purpose
+    ref = mahalanobis_scoring(ss(k["en_ids"], k["en"]), ss(k["te_ids"], k["te"]), ndx(), M)
+    mine = S.mahalanobis_scoring(*a, M)
+    assert ref.modelset.tolist() == mine[0].tolist() and ref.segset.tolist() == mine[1].tolist()
+    assert numpy.array_equal(ref.scoremask, mine[2]) and ref.scoremat.shape == mine[3].shape
+    assert numpy.abs(ref.scoremat - mine[3]).max() < 1e-9
+    assert numpy.abs(ref.scoremat[0] - numpy.array(kat.KAT_MAHALANOBIS_ROW0)).max() < 1e-8 and ref.scoremat.shape == (4, 3)
     for name, (ref, mine) in cases.items():
         assert ref.modelset.tolist() == mine[0].tolist() == kat.KAT_MODELSET
         assert ref.segset.tolist() == mine[1].tolist() == kat.KAT_SEGSET

@@ -52,6 +52,29 @@ def test_kat_vectors():
         assert abs(float(sc.scoremat.sum()) - exp["total"]) < 1e-3, name
 
 
+def test_mahalanobis_scoring_kat_and_random():
+    # iv_scoring.py:116-156, float64
+    k = kat.kat_inputs()
+    M = numpy.linalg.inv(k["Sigma"]) + 0.05 * numpy.triu(k["F"] @ k["F"].T)
+    a = (k["en_ids"], k["en"], k["te_ids"], k["te"], k["ndx_models"], k["ndx_segs"], k["trialmask"])
+    sc = sk.mahalanobis_scoring(_ss(k["en_ids"], k["en"]), _ss(k["te_ids"], k["te"]), _ndx(k["ndx_models"], k["ndx_segs"], k["trialmask"]), M)
+    ref = S.mahalanobis_scoring(*a, M)
+    assert sc.modelset.tolist() == kat.KAT_MODELSET and sc.segset.tolist() == kat.KAT_SEGSET
+    assert numpy.array_equal(sc.scoremask, ref[2]) and sc.scoremat.dtype == numpy.float64 and sc.scoremat.shape == (4, 3)
+    assert numpy.abs(sc.scoremat - ref[3]).max() < 1e-3
+    assert numpy.abs(sc.scoremat[0] - numpy.array(kat.KAT_MAHALANOBIS_ROW0)).max() < 1e-3
+    rng = numpy.random.default_rng(31)
+    D, Ne, Nt = 256, 333, 517
+    E, T = synth.synth_embeddings(Ne, D, seed=41), synth.synth_embeddings(Nt, D, seed=42)
+    A = rng.standard_normal((D, D)) * 0.05
+    M = A @ A.T + numpy.eye(D) + 0.01 * rng.standard_normal((D, D))
+    ids_e = numpy.array(["m%04d" % i for i in range(Ne)])
+    ids_t = numpy.array(["s%04d" % i for i in range(Nt)])
+    mask = rng.random((Ne, Nt)) < 0.5
+    sc = sk.mahalanobis_scoring(_ss(ids_e, E), _ss(ids_t, T), _ndx(ids_e, ids_t, mask), M)
+    _check(sc, S.mahalanobis_scoring(ids_e, E, ids_t, T, ids_e, ids_t, mask, M), 1e-3, numpy.float64)
+
+
 def test_two_covariance_mutates_callers_objects_like_the_reference():
     k = kat.kat_inputs()
     en, te = _ss(k["en_ids"], k["en"]), _ss(k["te_ids"], k["te"])

@@ -29,7 +29,7 @@
 namespace skb {
 extern std::atomic<long long> g_launches;
 
-constexpr int kOutPerCta = 4096;       // target outputs per CTA (rounded down to whole periods)
+constexpr int kOutPerCta = 2048;       // target outputs per CTA (rounded down to whole periods); sweep in profiles/r01g_resample.txt
 constexpr int kResThreads = 256;
 constexpr int kResBlock = 4;           // outputs per thread and coefficient load
 

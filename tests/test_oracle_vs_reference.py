@@ -94,3 +94,21 @@ def test_scoring_kat_recorded_from_reference():
         tol = 1e-9 if ref.scoremat.dtype == numpy.float64 else 1e-6
         assert numpy.abs(ref.scoremat - mine[3]).max() < tol
         assert numpy.abs(ref.scoremat[0] - numpy.array(kat.KAT[name]["row0"])).max() < max(tol, 1e-9) * 10
+
+
+def test_plda_scoring_uncertainty_is_unreachable_in_the_reference():
+    """``PLDA_scoring`` hands ``test_uncertainty`` / ``Vtrans`` to ``fast_PLDA_scoring``, which ignores them
+    (iv_scoring.py:256-268); ``PLDA_scoring_uncertainty`` itself asserts on an undefined name ``G`` (:513) and raises
+    NameError before computing anything, so uncertainty propagation is not part of any runnable path."""
+    from oracle import ref_import
+    sidekit = ref_import.import_reference()
+    from sidekit.iv_scoring import PLDA_scoring_uncertainty
+    k = kat.kat_inputs()
+    s = sidekit.StatServer()
+    s.modelset = numpy.array(k["en_ids"]); s.segset = numpy.array(k["en_ids"])
+    s.start = numpy.empty(7, dtype="|O"); s.stop = numpy.empty(7, dtype="|O")
+    s.stat0 = numpy.ones((7, 1)); s.stat1 = numpy.array(k["en"], dtype=numpy.float64)
+    n = sidekit.Ndx()
+    n.modelset, n.segset, n.trialmask = k["en_ids"][:2].copy(), k["en_ids"][:3].copy(), numpy.ones((2, 3), dtype=bool)
+    with pytest.raises(NameError):
+        PLDA_scoring_uncertainty(s, s, n, k["mu"], k["F"], k["Sigma"], test_uncertainty=numpy.ones((7, 8)), Vtrans=numpy.eye(8))

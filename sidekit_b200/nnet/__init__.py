@@ -2,6 +2,6 @@
 from .xvector import Xtractor
 from .pooling import MeanStdPooling, AttentivePooling
 from .res_net import PreHalfResNet34, PreResNet34, PreFastResNet34, BasicBlock, SELayer
-from .preprocessor import MfccFrontEnd, MelSpecFrontEnd, PreEmphasis
+from .preprocessor import MfccFrontEnd, MelSpecFrontEnd, PreEmphasis, Resample
 from .loss import ArcMarginProduct, l2_norm
-from .xsets import IdMap, IdMapSet, extract_embeddings, read_wav  # noqa: F401,E402
+from .xsets import IdMap, IdMapSet, extract_embeddings, load_checkpoint, read_wav  # noqa: F401,E402

@@ -139,12 +139,30 @@ class IdMapSet:
         return speech, self.idmap.leftids[index], self.idmap.rightids[index], start, stop
 
 
+def load_checkpoint(model_path, device, embedding_size=None):
+    """Checkpoint file -> ``Xtractor`` in eval mode on ``device``, as ``extract_embeddings`` (xvector.py:1834-1843) and
+    ``extract_xvectors.py:load_model`` (:74-91) do it: ``torch.load`` of a dict holding ``speaker_number``,
+    ``model_archi`` (``model_type``, ``loss.type``, optional ``embedding_size``) and ``model_state_dict``, loaded with
+    ``strict=True``.  ``embedding_size=None`` takes the checkpoint's value (256 when absent, like ``load_model``)."""
+    from .xvector import Xtractor
+    checkpoint = torch.load(model_path, map_location="cpu", weights_only=False)
+    model_opts = checkpoint["model_archi"]
+    if embedding_size is None:
+        embedding_size = model_opts.get("embedding_size", 256)
+    model = Xtractor(checkpoint["speaker_number"], model_archi=model_opts["model_type"], loss=model_opts["loss"]["type"],
+                     embedding_size=embedding_size)
+    model.load_state_dict(checkpoint["model_state_dict"], strict=True)
+    model.eval()
+    return model.to(device)
+
+
 def extract_embeddings(idmap_name, model_filename, data_root_name, device, batch_size=1, file_extension="wav",
                        transform_pipeline={}, sliding_window=False, win_duration=3., win_shift=1.5, num_thread=1,
                        sample_rate=16000, mixed_precision=False, norm_embeddings=True, max_audio_seconds=1200.0):
     """xvector.py:1796-1916: a ``StatServer`` with one embedding per segment (or per sliding window).
 
-    ``model_filename`` must be an ``Xtractor`` (checkpoint files are out of scope); ``batch_size``, ``num_thread`` and
+    ``model_filename`` is an ``Xtractor`` or the path of a checkpoint written by the reference's training loop
+    (``speaker_number`` / ``model_archi`` / ``model_state_dict``, xvector.py:1834-1843); ``batch_size``, ``num_thread`` and
     ``mixed_precision`` are accepted and ignored: batches are formed by total audio (``max_audio_seconds``) and the
     kernels pick their own precision.  ``start`` / ``stop`` follow the reference, including its sliding-window
     ``stop = start + <number of 100-window chunks of the last file>`` (xvector.py:1897, :1911).
@@ -152,7 +170,7 @@ def extract_embeddings(idmap_name, model_filename, data_root_name, device, batch
     from .. import bulk
     model = model_filename
     if isinstance(model, str):
-        raise NotImplementedError("checkpoint files are out of scope; pass an Xtractor")
+        model = load_checkpoint(model, device, embedding_size=256)          # xvector.py:1838: the size is forced to 256
     dataset = IdMapSet(idmap_name, data_root_name, file_extension, transform_pipeline, 0, sliding_window, win_duration, win_shift,
                        sample_rate, min_duration=win_duration)
     model.eval()

@@ -92,6 +92,38 @@ def test_extract_embeddings_from_wav_files(tmp_path):
     assert sc.validate() and numpy.isfinite(sc.scoremat).all()
 
 
+@pytest.mark.reference
+def test_reference_checkpoint_loads_strictly(tmp_path):
+    """A checkpoint in the layout the reference's training loop saves (xvector.py: ``speaker_number``, ``model_archi``,
+    ``model_state_dict``), built from the REFERENCE's own Xtractor, loads with strict=True into ours (no GPU needed:
+    the modules only hold the weights until the first forward)."""
+    from oracle import ref_import
+    ref = ref_import.build_xtractor(32, "halfresnet34", 256)
+    sd = ref.state_dict()
+    synth.fill_state_dict(sd, 3)
+    path = os.path.join(tmp_path, "best_model.pt")
+    torch.save({"speaker_number": 32, "model_archi": {"model_type": "halfresnet34", "loss": {"type": "aam"}},
+                "model_state_dict": sd, "epoch": 7, "accuracy": 0.5}, path)
+    m = xsets.load_checkpoint(path, torch.device("cpu"))
+    assert m.speaker_number == 32 and m.embedding_size == 256 and not m.training
+    mine = m.state_dict()
+    assert list(mine.keys()) == list(sd.keys())
+    assert all(torch.equal(mine[k].cpu(), sd[k]) for k in sd)
+
+
+@pytest.mark.gpu
+def test_extract_embeddings_from_checkpoint_file(tmp_path):
+    _write_wavs(str(tmp_path), (40000, 52000))
+    m = make_xtractor("halfresnet34", 32, 256).cuda()
+    path = os.path.join(tmp_path, "model.pt")
+    torch.save({"speaker_number": 32, "model_archi": {"model_type": "halfresnet34", "loss": {"type": "aam"}, "embedding_size": 256},
+                "model_state_dict": {k: v.cpu() for k, v in m.state_dict().items()}}, path)
+    rows = [("a", "f0", None, None), ("b", "f1", 20, 250)]
+    a = sk.nnet.extract_embeddings(_idmap(rows), path, str(tmp_path), torch.device("cuda"), win_duration=1.0)
+    b = sk.nnet.extract_embeddings(_idmap(rows), m, str(tmp_path), torch.device("cuda"), win_duration=1.0)
+    assert numpy.array_equal(a.stat1, b.stat1) and a.stat1.shape == (2, 256)
+
+
 def test_kaldi_ark_scp_round_trip(tmp_path):
     """x-vector tables in Kaldi's binary ark / scp layout (what extract_xvectors.py writes through kaldiio): header bytes
     as published, scp offsets pointing at the binary marker, row matrices and vectors, speaker means."""

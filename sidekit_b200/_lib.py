@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libsidekit_b200.so")
+LIB_PATH = os.environ.get("SKB_LIB_PATH") or os.path.join(_HERE, "libsidekit_b200.so")      # override: A/B builds
 _lib = None
 
 c_float_p = ctypes.c_void_p      # device / host pointers are passed as integers

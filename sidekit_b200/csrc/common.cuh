@@ -32,6 +32,41 @@ bool sync_check_enabled();
         if (skb::sync_check_enabled()) SKB_CUDA_CHECK(cudaStreamSynchronize(stream));         \
     } while (0)
 
+// ----------------------------------------------------------------------------- programmatic dependent launch (PDL)
+// The kernels of the per-block chain (conv1 -> channel sums -> border sums -> SE partial means -> SE FC -> conv2) depend on
+// each other one after the other.  Launched with the programmatic-stream-serialization attribute, kernel k+1 is scheduled
+// as soon as the CTAs of kernel k have exited (without waiting for the end-of-grid flush), its CTAs run their prologue
+// (barrier init, TMEM allocation, constant weights), and pdl_wait() -- executed by every such kernel before it reads or
+// writes anything another kernel touches -- blocks until kernel k has completed and its writes are visible.
+// Measured (profiles/r01g_pdl.txt): 8.53 -> 8.45 ms per HalfResNet34 step, e2e +1.5 %.  An EARLY trigger
+// (griddepcontrol.launch_dependents at the top of every kernel, SKB_PDL_EARLY_TRIGGER=1) lets the whole chain park on the
+// SMs while conv1 still runs and is slower (8.7-8.8 ms), so the implicit trigger at CTA exit is what ships.
+// SKB_NO_PDL=1 launches everything with plain stream order (A/B knob); pdl_wait() is then a no-op.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef SKB_PDL_EARLY_TRIGGER
+#define SKB_PDL_EARLY_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if SKB_PDL_EARLY_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ----------------------------------------------------------------------------- shared-memory address
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

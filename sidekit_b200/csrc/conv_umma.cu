@@ -65,7 +65,7 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     p.n_tiles = (n_pix + Cfg::kTileM - 1) / Cfg::kTileM;
     const int n_items = p.n_tiles * (p.cout / N_CTA);
     const int grid = n_items < kNumSMs ? n_items : kNumSMs;      // persistent: one CTA per SM
-    conv_umma_kernel<N_CTA, MT, BF16, FUSED><<<grid, kConvThreads, smem, st>>>(p);
+    SKB_CUDA_CHECK(launch_pdl(conv_umma_kernel<N_CTA, MT, BF16, FUSED>, dim3(grid), dim3(kConvThreads), smem, st, p));
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }

@@ -149,9 +149,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    // everything above touches only constants (weights, bias) and this CTA's shared / tensor memory: it overlaps the tail of
+    // the previous kernel of the stream.  From here on the kernel reads what that kernel wrote.
+    pdl_trigger();
+    pdl_wait();
     if (FUSED && p.scale_smem_bytes > 0)
         for (int i = threadIdx.x; i < p.scale_smem_bytes / 4; i += blockDim.x) scale_s[i] = p.se_scale[i];
-    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

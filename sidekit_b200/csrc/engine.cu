@@ -23,6 +23,11 @@ void set_last_error(const char* file, int line, const char* msg) {
     snprintf(g_err, sizeof(g_err), "%s:%d: %s", file, line, msg);
 }
 std::atomic<long long> g_launches{0};
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SKB_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 bool sync_check_enabled() {
     static const bool on = [] { const char* e = getenv("SKB_SYNC_CHECK"); return e && e[0] == '1'; }();
     return on;

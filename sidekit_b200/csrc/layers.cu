@@ -229,6 +229,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(256, 4) plane_sum_kernel(const uint16_t* __restrict__ act, long long plane, int G, int p_end,
                                                         const int* __restrict__ pix_b, const int* __restrict__ span_b, int C,
                                                         int planes_per_block, unsigned long long* __restrict__ sums) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int span = blockIdx.x * 8 + warp;
     const int base = G + span * kSpanPix;
@@ -315,9 +317,9 @@ int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int
     const int ppb = chunks >= 16 ? 4 : (chunks >= 8 ? 2 : 1);      // keep >= ~4 waves of CTAs on the small levels
     dim3 grid((n_spans + 7) / 8, chunks / ppb);
     if (bf16)
-        plane_sum_kernel<true><<<grid, 256, 0, st>>>(act, plane, G, p_end, pix_b, span_b, C, ppb, sums);
+        SKB_CUDA_CHECK(launch_pdl(plane_sum_kernel<true>, grid, dim3(256), 0, st, act, plane, G, p_end, pix_b, span_b, C, ppb, sums));
     else
-        plane_sum_kernel<false><<<grid, 256, 0, st>>>(act, plane, G, p_end, pix_b, span_b, C, ppb, sums);
+        SKB_CUDA_CHECK(launch_pdl(plane_sum_kernel<false>, grid, dim3(256), 0, st, act, plane, G, p_end, pix_b, span_b, C, ppb, sums));
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
@@ -331,6 +333,8 @@ __global__ void __launch_bounds__(256) se_border_kernel(const uint16_t* __restri
                                                         float* __restrict__ brd) {
     __shared__ float part[256][33];
     __shared__ float part2[8][32];
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x, j = blockIdx.y;
     const int H = utt_count[b] / W;
     const uint16_t* base = y1 + ((size_t)j * plane + G + (size_t)utt_row0[b] * Wp) * 8;     // pixel (0, 0) of chunk j
@@ -408,6 +412,8 @@ __global__ void __launch_bounds__(256) se_mean_partial_kernel(const unsigned lon
 #pragma unroll
         for (int i = 0; i < RPT; ++i) wreg[i] = __ldg(wp + (size_t)i * n_rg * Cout);
     }
+    pdl_trigger();
+    pdl_wait();                                    // the weight loads above are constants: they overlap the previous kernel
     const int k0 = blockIdx.x * kSeRows, b0 = blockIdx.y * kSeUtt;
     const int nu = min(kSeUtt, B - b0);
     // the nine shifted sums of one (utterance, input channel): nine independent loads, then arithmetic only
@@ -473,6 +479,8 @@ __global__ void __launch_bounds__(256) se_fc_kernel(unsigned long long* __restri
                                                     const float* __restrict__ fc2 /*[Cout][Cout/16]*/, float* __restrict__ scale) {
     __shared__ float mean[256];
     __shared__ float hid[16];
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x;
     const float inv_n = 1.f / (float)utt_count[b];
     for (int c = threadIdx.x; c < Cin; c += blockDim.x) sums[(size_t)b * Cin + c] = 0ull;
@@ -508,23 +516,23 @@ int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, lon
     }
     dim3 grid(B, Cin / 8);
     if (bf16)
-        se_border_kernel<true><<<grid, 256, 0, st>>>(y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws);
+        SKB_CUDA_CHECK(launch_pdl(se_border_kernel<true>, grid, dim3(256), 0, st, y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws));
     else
-        se_border_kernel<false><<<grid, 256, 0, st>>>(y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws);
+        SKB_CUDA_CHECK(launch_pdl(se_border_kernel<false>, grid, dim3(256), 0, st, y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws));
     SKB_LAUNCH_CHECK(st);
     const int n_slices = Cin / kSeCh;
     float* partial = brd_ws + (size_t)B * 8 * Cin;
     dim3 g2(n_slices, (B + kSeUtt - 1) / kSeUtt);
-    if (Cout == 32) se_mean_partial_kernel<32><<<g2, 256, 0, st>>>(sums, brd_ws, B, Cin, w2t, partial);
-    else if (Cout == 64) se_mean_partial_kernel<64><<<g2, 256, 0, st>>>(sums, brd_ws, B, Cin, w2t, partial);
-    else if (Cout == 128) se_mean_partial_kernel<128><<<g2, 256, 0, st>>>(sums, brd_ws, B, Cin, w2t, partial);
-    else if (Cout == 256) se_mean_partial_kernel<256><<<g2, 256, 0, st>>>(sums, brd_ws, B, Cin, w2t, partial);
+    if (Cout == 32) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<32>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
+    else if (Cout == 64) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<64>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
+    else if (Cout == 128) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<128>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
+    else if (Cout == 256) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<256>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
     else {
         set_last_error(__FILE__, __LINE__, "squeeze-excitation: unsupported channel count");
         return SKB_ERR_ARG;
     }
     SKB_LAUNCH_CHECK(st);
-    se_fc_kernel<<<B, 256, 0, st>>>(sums, partial, n_slices, utt_count, B, Cin, Cout, b2, fc1, fc2, scale);
+    SKB_CUDA_CHECK(launch_pdl(se_fc_kernel, dim3(B), dim3(256), 0, st, sums, partial, n_slices, utt_count, B, Cin, Cout, b2, fc1, fc2, scale));
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }

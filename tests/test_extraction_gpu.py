@@ -235,6 +235,46 @@ def test_experimental_fused_tap_kernel_parity():
     assert out.returncode == 0 and "fused-tap ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_fused_channel_totals_equal_the_separate_pass(tmp_path):
+    """conv1's epilogue accumulates the SE channel totals on the 32-channel layers (fixed point, per-thread accumulators
+    flushed with 64-bit atomics); SKB_NO_FUSED_SUMS=1 (read once per process -> subprocess) runs the separate plane_sum
+    pass instead.  Same integers, so the embeddings must agree bit for bit -- also when the first blocks of layers 1 and 2
+    are scaled up so that most of their activations exceed 128 (the range a cheaper 32-bit variant could not hold)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch\n"
+        "from sidekit_b200 import synth\n"
+        "from tests.models import make_xtractor\n"
+        "outs = []\n"
+        "for scale in (1.0, 64.0):\n"
+        "    m = make_xtractor('halfresnet34', 32, 256)\n"
+        "    sd = m.state_dict()\n"
+        "    for blk in ('layer1.0', 'layer2.1'):\n"
+        "        for k in ('weight', 'bias'):\n"
+        "            sd['sequence_network.%s.bn1.%s' % (blk, k)] *= scale\n"
+        "    m.load_state_dict(sd)\n"
+        "    m = m.cuda()\n"
+        "    ws = [synth.synth_wave(1, L, seed=1700 + i)[0].cuda() for i, L in enumerate((16000, 9000, 40321, 8000, 25000))]\n"
+        "    outs.append(m.extract_varlen(ws).cpu())\n"
+        "    outs.append(torch.cat([m.extract_varlen([w]) for w in ws]).cpu())\n"
+        "torch.save(outs, sys.argv[1])\n"
+        "print('sums ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for name, env in (("fused", {}), ("separate", {"SKB_NO_FUSED_SUMS": "1"})):
+        path = os.path.join(tmp_path, name + ".pt")
+        out = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True,
+                             timeout=300)
+        assert out.returncode == 0 and "sums ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+        res[name] = torch.load(path)
+    for a, b in zip(res["fused"], res["separate"]):
+        assert torch.isfinite(a).all() and torch.equal(a, b)
+    assert torch.equal(res["fused"][0], res["fused"][1]) and torch.equal(res["fused"][2], res["fused"][3])      # packing invariance
+    assert not torch.equal(res["fused"][0], res["fused"][2])
+
+
 def test_extract_stream_overlapped_copies_equal_packed_calls(hr34):
     """extract_stream (H2D of batch i+1 overlapped with the forward of batch i) == extract_packed batch by batch."""
     m, _ = hr34

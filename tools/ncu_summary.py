@@ -48,5 +48,8 @@ for k, row in enumerate(rows[2:]):
         pass
 tot = sum(d[0] for d in data) or 1
 print("top stall instructions (%d samples):" % tot)
+ctx = int(__import__("os").environ.get("NCU_CTX", "0"))        # SASS lines of context before each hot instruction
 for s, k, t in sorted(data, reverse=True)[:22]:
+    for kk in range(max(0, k - ctx), k):
+        print("                 | %s" % rows[2 + kk][i_src][:100])
     print("  %5.1f%%  #%4d  %s" % (100.0 * s / tot, k, t[:100]))

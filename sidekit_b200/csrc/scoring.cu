@@ -36,6 +36,7 @@ struct AbsmaxArgs { const float* X[2]; int rows[2]; unsigned* stats[2]; };
 __global__ void absmax_kernel(const AbsmaxArgs a, int D) {
     // one warp per row, block-level max, a single pair of atomics per CTA
     __shared__ float smx[8], sss[8];
+    pdl_wait();                                        // launched with launch_pdl (common.cuh): stats were zeroed in stream order
     const float* __restrict__ X = a.X[blockIdx.y];
     const int rows = a.rows[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,6 +82,7 @@ __device__ __forceinline__ int decide_passes(const unsigned* statsE, const unsig
 // stored once for the GEMM epilogue).
 struct PackArgs { const float* X[2]; int rows[2], rows_pad[2]; const unsigned* stats[2]; int* exp_out[2]; uint16_t* hi[2]; uint16_t* lo[2]; };
 __global__ void pack_split_kernel(const PackArgs a, int D, int Dp) {
+    pdl_wait();
     const int op = blockIdx.y;
     const float* __restrict__ X = a.X[op];
     const int rows = a.rows[op], rows_pad = a.rows_pad[op];
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
     uint8_t* b_smem = a_smem + SM::a_bytes(p.Dp);
     uint8_t* stage_smem = b_smem + SM::kBStages * SM::kRingStageBytes;
 
+    pdl_wait();                                        // the operand statistics / planes come from the kernels before this one
     // the other instantiation handles this launch when the decision (uniform across the grid) is not ours
     if (decide_passes(p.statsE, p.statsT, p.D, p.abs_alpha, p.passes_req) != PASSES) return;
 
@@ -440,8 +443,8 @@ static int packed_fill(const float* X0, PackedOp* op0, const float* X1, PackedOp
             max_n = std::max(max_n, (long long)o->rows_pad * (o->Dp / 8));
         }
     }
-    absmax_kernel<<<dim3(std::min((max_rows + 7) / 8, 4 * kNumSMs), n_ops), 256, 0, st>>>(aa, op0->D);
-    pack_split_kernel<<<dim3((unsigned)((max_n + 255) / 256), n_ops), 256, 0, st>>>(pa, op0->D, op0->Dp);
+    SKB_CUDA_CHECK(launch_pdl(absmax_kernel, dim3(std::min((max_rows + 7) / 8, 4 * kNumSMs), n_ops), dim3(256), 0, st, aa, op0->D));
+    SKB_CUDA_CHECK(launch_pdl(pack_split_kernel, dim3((unsigned)((max_n + 255) / 256), n_ops), dim3(256), 0, st, pa, op0->D, op0->Dp));
     g_launches += 2;
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
@@ -502,7 +505,7 @@ static int launch_score(const ScoreParams& p, int grid, cudaStream_t st) {
         SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<PASSES, STREAM_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    score_gemm_kernel<PASSES, STREAM_A><<<grid, kScThreads, smem, st>>>(p);
+    SKB_CUDA_CHECK(launch_pdl(score_gemm_kernel<PASSES, STREAM_A>, dim3(grid), dim3(kScThreads), smem, st, p));
     g_launches++;
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;

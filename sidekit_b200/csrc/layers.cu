@@ -9,8 +9,9 @@ namespace skb {
 
 // ----------------------------------------------------------------------------- stem: 3x3 conv 1->32 + BN + ReLU
 // sidekit/nnet/res_net.py:549 (relu(bn1(conv1(x)))) on the (B,1,T,F) view of the features.
-// One thread per level-1 pixel; the normalised features are frame-major so a warp reads contiguous
+// One thread per kStemPix level-1 pixels; the normalised features are frame-major so a warp reads contiguous
 // mel bins.  fp32 math on CUDA cores (0.1 % of the trunk's FLOPs), 16-bit chunk-plane output.
+constexpr int kStemPix = 2;            // pixels per thread
 template <bool BF16, int COUT>
 __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemConsts sc, const float* __restrict__ feats,
                                                    const long long* __restrict__ feat_off, const int* __restrict__ n_frames,
@@ -18,50 +19,67 @@ __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemC
                                                    uint16_t* __restrict__ out, long long out_plane, int G, int p_end, int Wp,
                                                    int W, const int* __restrict__ row_b, const int* __restrict__ row_h) {
     // The folded weights arrive as a kernel parameter: every FFMA takes its weight straight from the constant bank
-    // (a shared-memory copy costs one LDS per FMA and made the kernel LSU-bound at 3x its HBM time).
-    const int pix = G + blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= p_end) return;
-    const int rel = pix - G;
-    const int row = rel / Wp, f = rel - row * Wp;
-    const int b = row_b[row], t = row_h[row];
-    const bool valid = (b >= 0) && (f < W);
-    float x[9];
+    // (a shared-memory copy costs one LDS per FMA and made the kernel LSU-bound at 3x its HBM time).  Each thread computes
+    // kStemPix pixels (blockDim apart, so loads and stores stay coalesced): a weight fetched into a uniform register feeds
+    // kStemPix FMAs (one pixel per thread spent a quarter of its 840 instructions per pixel on those fetches).
+    const int pix0 = G + blockIdx.x * (blockDim.x * kStemPix) + threadIdx.x;
+    float x[kStemPix][9];
+    bool valid[kStemPix];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) x[k] = 0.f;
-    if (valid) {
-        const int T = n_frames[b];
-        const float* fb = feats + (size_t)feat_off[b] * W;
+    for (int q = 0; q < kStemPix; ++q) {
+        const int pix = pix0 + q * blockDim.x;
 #pragma unroll
-        for (int df = 0; df < 3; ++df) {
-            const int ff = f + df - 1;
-            const bool f_ok = ff >= 0 && ff < W;
-            // CMVN (InstanceNorm1d) applied on the fly to the raw log-Mel features: (x - mean) * rstd per (utterance, bin)
-            const float2 ms = f_ok ? __ldg(cmvn + (size_t)b * W + ff) : make_float2(0.f, 0.f);
+        for (int k = 0; k < 9; ++k) x[q][k] = 0.f;
+        valid[q] = false;
+        if (pix >= p_end) continue;
+        const int rel = pix - G;
+        const int row = rel / Wp, f = rel - row * Wp;
+        const int b = row_b[row], t = row_h[row];
+        valid[q] = (b >= 0) && (f < W);
+        if (valid[q]) {
+            const int T = n_frames[b];
+            const float* fb = feats + (size_t)feat_off[b] * W;
 #pragma unroll
-            for (int dt = 0; dt < 3; ++dt) {
-                const int tt = t + dt - 1;
-                x[dt * 3 + df] = (f_ok && tt >= 0 && tt < T) ? (__ldg(fb + (size_t)tt * W + ff) - ms.x) * ms.y : 0.f;
+            for (int df = 0; df < 3; ++df) {
+                const int ff = f + df - 1;
+                const bool f_ok = ff >= 0 && ff < W;
+                // CMVN (InstanceNorm1d) applied on the fly to the raw log-Mel features: (x - mean) * rstd per (utterance, bin)
+                const float2 ms = f_ok ? __ldg(cmvn + (size_t)b * W + ff) : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int dt = 0; dt < 3; ++dt) {
+                    const int tt = t + dt - 1;
+                    x[q][dt * 3 + df] = (f_ok && tt >= 0 && tt < T) ? (__ldg(fb + (size_t)tt * W + ff) - ms.x) * ms.y : 0.f;
+                }
             }
         }
     }
 #pragma unroll
-    for (int g = 0; g < COUT / 32; ++g) {          // 32 output channels (four 16-byte chunks) at a time
-        float acc[32];
+    for (int g = 0; g < COUT / 8; ++g) {           // 8 output channels (one 16-byte chunk) at a time, for every pixel of the thread
+        float acc[kStemPix][8];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            float a = sc.b[g * 32 + c];
+        for (int c = 0; c < 8; ++c) {
+            float a[kStemPix];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a = fmaf(sc.w[(g * 32 + c) * 9 + k], x[k], a);
-            acc[c] = valid ? fmaxf(a, 0.f) : 0.f;
+            for (int q = 0; q < kStemPix; ++q) a[q] = sc.b[g * 8 + c];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float w = sc.w[(g * 8 + c) * 9 + k];
+#pragma unroll
+                for (int q = 0; q < kStemPix; ++q) a[q] = fmaf(w, x[q][k], a[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < kStemPix; ++q) acc[q][c] = valid[q] ? fmaxf(a[q], 0.f) : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int q = 0; q < kStemPix; ++q) {
+            const int pix = pix0 + q * blockDim.x;
+            if (pix >= p_end) continue;
             uint4 o;
-            o.x = pack2<BF16>(acc[j * 8 + 0], acc[j * 8 + 1]);
-            o.y = pack2<BF16>(acc[j * 8 + 2], acc[j * 8 + 3]);
-            o.z = pack2<BF16>(acc[j * 8 + 4], acc[j * 8 + 5]);
-            o.w = pack2<BF16>(acc[j * 8 + 6], acc[j * 8 + 7]);
-            *reinterpret_cast<uint4*>(out + ((size_t)(g * 4 + j) * out_plane + pix) * 8) = o;
+            o.x = pack2<BF16>(acc[q][0], acc[q][1]);
+            o.y = pack2<BF16>(acc[q][2], acc[q][3]);
+            o.z = pack2<BF16>(acc[q][4], acc[q][5]);
+            o.w = pack2<BF16>(acc[q][6], acc[q][7]);
+            *reinterpret_cast<uint4*>(out + ((size_t)g * out_plane + pix) * 8) = o;
         }
     }
 }
@@ -71,7 +89,7 @@ int launch_stem(bool bf16, int cout, const float* feats, const long long* feat_o
                 const int* row_b, const int* row_h, cudaStream_t st) {
     const int n = p_end - G;
     const int threads = 128;
-    const int blocks = (n + threads - 1) / threads;
+    const int blocks = (n + threads * kStemPix - 1) / (threads * kStemPix);
 #define SKB_STEM(BF, C) stem_kernel<BF, C><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, row_b, row_h)
     if (cout == 32) { if (bf16) SKB_STEM(true, 32); else SKB_STEM(false, 32); }
     else if (cout == 128) { if (bf16) SKB_STEM(true, 128); else SKB_STEM(false, 128); }

@@ -40,6 +40,8 @@ def resample(x, orig_freq, new_freq, lowpass_filter_width=6, rolloff=0.99):
     if orig_freq == new_freq:
         return x
     squeeze = x.ndim == 1
+    if x.shape[-1] == 0:
+        return x                                   # nothing to resample (torchaudio returns an empty tensor as well)
     x2 = x.reshape(-1, x.shape[-1])
     orig_r, new_r, width, kern = sinc_bank(orig_freq, new_freq, lowpass_filter_width, rolloff)
     L = x2.shape[1]

@@ -67,7 +67,7 @@ def test_kernel_matches_golden_and_oracle():
 @pytest.mark.gpu
 def test_kernel_ragged_packed_batch_and_long_waves():
     # utterances of very different lengths back to back (several CTAs per wave, waves shorter than one filter)
-    lengths = [3, 44100 * 7 + 13, 1000, 441, 200001, 1]
+    lengths = [3, 44100 * 7 + 13, 0, 1000, 441, 200001, 1]
     waves = [synth.synth_wave(1, L, seed=900 + k)[0] for k, L in enumerate(lengths)]
     r = Resample(44100, 16000)
     out = r.resample_packed(torch.cat(waves).cuda(), lengths).cpu().numpy()
@@ -79,6 +79,9 @@ def test_kernel_ragged_packed_batch_and_long_waves():
         assert numpy.abs(got - ref).max() < TOL, (L, numpy.abs(got - ref).max())
         off += r.out_length(L)
     assert off == out.shape[0]
+    assert r.resample_packed(torch.empty(0, device="cuda"), [0, 0]).numel() == 0          # nothing to do: no launch
+    with pytest.raises(RuntimeError):
+        r.resample_packed(torch.zeros(10), [10])                                          # no CPU path
     # leading dimensions are kept, like torchaudio
     x = synth.synth_wave(6, 2000, seed=7).reshape(2, 3, 2000)
     y = Resample(8000, 16000)(x.cuda())

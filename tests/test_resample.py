@@ -76,7 +76,7 @@ def test_kernel_ragged_packed_batch_and_long_waves():
         ref = RR.resample(w.numpy(), 44100, 16000)
         got = out[off:off + r.out_length(L)]
         assert got.shape == ref.shape
-        assert numpy.abs(got - ref).max() < TOL, (L, numpy.abs(got - ref).max())
+        assert L == 0 or numpy.abs(got - ref).max() < TOL, (L, numpy.abs(got - ref).max())
         off += r.out_length(L)
     assert off == out.shape[0]
     assert r.resample_packed(torch.empty(0, device="cuda"), [0, 0]).numel() == 0          # nothing to do: no launch

@@ -153,3 +153,61 @@ def test_kaldi_ark_scp_round_trip(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         kaldi_io.ArkScpWriter(str(tmp_path / "bad.ark"))("two words", X[0])
+
+
+def _xv_setup(tmp_path):
+    """Three utterances: a plain 16 kHz path, an 8 kHz file (resampled on the device) and a `cat file |` pipe entry."""
+    import wave as wavmod
+    d = str(tmp_path)
+    pcm = {}
+    for name, rate, n, seed in (("a", 16000, 30000, 1), ("b", 8000, 12000, 2), ("c", 16000, 21000, 3)):
+        x = (synth.synth_wave(1, n, seed=1800 + seed)[0].numpy() * 32768.0).clip(-32768, 32767).astype(numpy.int16)
+        with wavmod.open(os.path.join(d, name + ".wav"), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(rate)
+            f.writeframes(x.tobytes())
+        pcm[name] = (x.astype(numpy.float32) / 32768.0, rate)
+    with open(os.path.join(d, "wav.scp"), "w") as f:
+        f.write("utt-a %s/a.wav\nutt-b %s/b.wav\nutt-c cat %s/c.wav |\n" % (d, d, d))
+    with open(os.path.join(d, "spk2utt"), "w") as f:
+        f.write("spk1 utt-a utt-c\nspk2 utt-b\n")
+    return d, pcm
+
+
+def test_wav_scp_entries_paths_and_pipes(tmp_path):
+    from sidekit_b200 import extract_xvectors as X
+    d, pcm = _xv_setup(tmp_path)
+    scp = X.read_wav_scp(os.path.join(d, "wav.scp"))
+    assert list(scp.keys()) == ["utt-a", "utt-b", "utt-c"] and scp["utt-c"][0] == "cat" and scp["utt-c"][-1] == "|"
+    for key, name in (("utt-a", "a"), ("utt-b", "b"), ("utt-c", "c")):
+        sig, sr = X.prepare(scp[key])
+        assert sr == pcm[name][1] and numpy.array_equal(sig.numpy(), pcm[name][0])
+    with pytest.raises(IOError):
+        X.prepare(["cat", os.path.join(d, "missing.wav"), "|"])
+
+
+@pytest.mark.gpu
+def test_extract_xvectors_main_writes_kaldi_tables(tmp_path):
+    """extract_xvectors.py:93-173 end to end: checkpoint file -> load_model -> wav.scp (path / other rate / pipe) -> ark + scp
+    + speaker means; vectors equal the direct extraction of the same (resampled) signals bit for bit."""
+    from oracle import resample_ref as RR
+    from sidekit_b200 import extract_xvectors as X, kaldi_io
+    d, pcm = _xv_setup(tmp_path)
+    m = make_xtractor("halfresnet34", 32, 256).cuda()
+    ckpt = os.path.join(d, "model.pt")
+    torch.save({"speaker_number": 32, "model_archi": {"model_type": "halfresnet34", "loss": {"type": "aam"}},
+                "model_state_dict": {k: v.cpu() for k, v in m.state_dict().items()}}, ckpt)
+    model, cfg = X.load_model(ckpt, "cuda")
+    assert cfg["speaker_number"] == 32
+    out_scp, spk_scp = os.path.join(d, "xv.scp"), os.path.join(d, "spk_xv.scp")
+    X.main(model, os.path.join(d, "wav.scp"), out_scp, "cuda", False, 2000, 1500, 16000, spk_scp, os.path.join(d, "spk2utt"))
+    table = dict(kaldi_io.read_scp(out_scp))
+    assert list(table.keys()) == ["utt-a", "utt-b", "utt-c"] and all(v.shape == (1, 256) for v in table.values())
+    b16 = sk.nnet.Resample(8000, 16000)(torch.from_numpy(pcm["b"][0]).cuda())
+    assert numpy.abs(b16.cpu().numpy() - RR.resample(pcm["b"][0], 8000, 16000)).max() < 2e-6
+    direct = m.extract_varlen([torch.from_numpy(pcm["a"][0]).cuda(), b16, torch.from_numpy(pcm["c"][0]).cuda()]).cpu().numpy()
+    assert numpy.array_equal(numpy.concatenate([table[k] for k in ("utt-a", "utt-b", "utt-c")]), direct)
+    spk = dict(kaldi_io.read_scp(spk_scp))
+    mean = direct[[0, 2]].mean(axis=0)
+    assert numpy.allclose(spk["spk1"], mean / numpy.linalg.norm(mean), atol=1e-6) and abs(numpy.linalg.norm(spk["spk2"]) - 1) < 1e-6
+    with pytest.raises(NotImplementedError):
+        X.main(model, os.path.join(d, "wav.scp"), out_scp, "cuda", True)

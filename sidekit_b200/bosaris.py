@@ -121,6 +121,17 @@ class Key:
                 for label, mask in (("target", self.tar), ("nontarget", self.non)):
                     fid.writelines("{} {} {}\n".format(self.modelset[m], seg, label) for seg in self.segset[mask[m, ]])
 
+    def filter(self, modlist, seglist, keep):
+        """key.py:166-205: keep (or drop) the listed models / segments; the order of the Key is kept."""
+        mods, segs = set(numpy.asarray(modlist).tolist()), set(numpy.asarray(seglist).tolist())
+        km = numpy.fromiter(((m in mods) == bool(keep) for m in self.modelset.tolist()), dtype=bool, count=self.modelset.shape[0])
+        ks = numpy.fromiter(((x in segs) == bool(keep) for x in self.segset.tolist()), dtype=bool, count=self.segset.shape[0])
+        out = Key()
+        out.modelset, out.segset = self.modelset[km], self.segset[ks]
+        out.tar, out.non = self.tar[km, :][:, ks], self.non[km, :][:, ks]
+        assert out.validate()
+        return out
+
     def to_ndx(self):
         ndx = Ndx()
         ndx.modelset, ndx.segset, ndx.trialmask = self.modelset, self.segset, self.tar | self.non
@@ -213,6 +224,26 @@ class Scores:
     @scoremat.setter
     def scoremat(self, value):
         self._scoremat = value
+
+    def filter(self, modlist, seglist, keep):
+        """scores.py:262-302: keep (or drop) the listed models / segments with their scores; order kept."""
+        mods, segs = set(numpy.asarray(modlist).tolist()), set(numpy.asarray(seglist).tolist())
+        km = numpy.fromiter(((m in mods) == bool(keep) for m in self.modelset.tolist()), dtype=bool, count=self.modelset.shape[0])
+        ks = numpy.fromiter(((x in segs) == bool(keep) for x in self.segset.tolist()), dtype=bool, count=self.segset.shape[0])
+        out = Scores()
+        out.modelset, out.segset = self.modelset[km], self.segset[ks]
+        out.scoremat, out.scoremask = self.scoremat[km, :][:, ks], self.scoremask[km, :][:, ks]
+        return out
+
+    def get_score(self, modelID, segID):
+        """scores.py:480-495: the (1, 1) block of the trial; raises when the model or the segment is unknown."""
+        model_idx = numpy.argwhere(self.modelset == modelID)
+        seg_idx = numpy.argwhere(self.segset == segID)
+        if model_idx.shape[0] == 0:
+            raise Exception('No such model as: %s', modelID)
+        if seg_idx.shape[0] == 0:
+            raise Exception('No such segment as: %s', segID)
+        return self.scoremat[model_idx, seg_idx]
 
     def write_txt(self, output_file_name):
         """scores.py:118-131: one ``model segment score`` line per scored trial, scores printed as ``str`` of the

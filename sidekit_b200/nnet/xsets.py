@@ -33,6 +33,73 @@ class IdMap:
         ok = self.leftids.shape == self.rightids.shape == self.start.shape == self.stop.shape
         return bool(ok and self.leftids.ndim == 1)
 
+    def set(self, left, right, start=None, stop=None):
+        """idmap.py:261-280: fill the map from arrays (deep copies); absent boundaries become None."""
+        import copy
+        self.leftids, self.rightids = copy.deepcopy(left), copy.deepcopy(right)
+        self.start = copy.deepcopy(start) if start is not None else numpy.empty(self.rightids.shape, "|O")
+        self.stop = copy.deepcopy(stop) if stop is not None else numpy.empty(self.rightids.shape, "|O")
+
+    def _map(self, keys, values, wanted):
+        # idmap.py:128-188: ids of `wanted` found in `keys`, in the order of `wanted`, mapped through the LAST pair of a key
+        table = dict(zip(keys, values))
+        inter = set(numpy.intersect1d(keys, wanted).tolist())
+        out = [table[w] for w in numpy.asarray(wanted).tolist() if w in inter]
+        if len(out) > len(inter):
+            raise IndexError("index %d is out of bounds for axis 0 with size %d" % (len(inter), len(inter)))   # duplicates in the query
+        res = numpy.empty(len(inter), "|O")
+        res[:len(out)] = out
+        return res
+
+    def map_left_to_right(self, leftidlist):
+        return self._map(self.leftids, self.rightids, leftidlist)
+
+    def map_right_to_left(self, rightidlist):
+        return self._map(self.rightids, self.leftids, rightidlist)
+
+    def _filter(self, ids, idlist, keep):
+        keepids = numpy.unique(idlist) if keep else numpy.setdiff1d(ids, idlist)
+        keep_idx = numpy.isin(ids, keepids)
+        out = IdMap()
+        out.leftids, out.rightids = self.leftids[keep_idx], self.rightids[keep_idx]
+        out.start, out.stop = self.start[keep_idx], self.stop[keep_idx]
+        return out
+
+    def filter_on_left(self, idlist, keep):
+        """idmap.py:190-215: the sessions whose left id is (keep=True) / is not (keep=False) in ``idlist``, in map order."""
+        return self._filter(self.leftids, idlist, keep)
+
+    def filter_on_right(self, idlist, keep):
+        """idmap.py:217-241."""
+        return self._filter(self.rightids, idlist, keep)
+
+    @staticmethod
+    def merge(self, idmap2):
+        """idmap.py:341-373 (a static method taking both maps, as in the reference): ``self`` followed by the sessions of
+        ``idmap2`` whose (left, right) pair is not in ``self``."""
+        idmap = IdMap()
+        if not (self.validate() and idmap2.validate()):
+            raise Exception("Cannot merge IdMaps, wrong type")
+        have = set(zip(self.leftids.tolist(), self.rightids.tolist()))
+        new = numpy.array([p not in have for p in zip(idmap2.leftids.tolist(), idmap2.rightids.tolist())], dtype=bool)
+        idmap.leftids = numpy.concatenate((self.leftids, idmap2.leftids[new]), axis=0)
+        idmap.rightids = numpy.concatenate((self.rightids, idmap2.rightids[new]), axis=0)
+        idmap.start = numpy.concatenate((self.start, idmap2.start[new]), axis=0)
+        idmap.stop = numpy.concatenate((self.stop, idmap2.stop[new]), axis=0)
+        if not idmap.validate():
+            raise Exception("Wrong format of IdMap")
+        return idmap
+
+    def split(self, N):
+        """idmap.py:375-392: N maps of (nearly) equal size, ``numpy.array_split`` order."""
+        out = []
+        for idx in numpy.array_split(numpy.arange(self.leftids.shape[0]), N):
+            im = IdMap()
+            im.leftids, im.rightids, im.start, im.stop = self.leftids[idx], self.rightids[idx], self.start[idx], self.stop[idx]
+            assert im.validate(), "Error: wrong IdMap format"
+            out.append(im)
+        return out
+
     def write_txt(self, output_file_name):
         """idmap.py:118-126: ``left right start stop`` per line; absent boundaries are written as the string ``None``
         (which ``read_txt`` cannot parse back -- a reference quirk kept as is)."""

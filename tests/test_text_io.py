@@ -110,3 +110,60 @@ def test_live_reference_agrees(tmp_path):
     assert sorted(g.keys()) == sorted(committed.files)
     for k in g:
         assert numpy.array_equal(numpy.asarray(g[k]), committed[k]), k
+
+
+@pytest.mark.reference
+def test_container_utilities_match_the_reference():
+    """IdMap.set / map_* / filter_on_* / merge / split, Key.filter, Scores.filter / get_score against the reference's own
+    methods (bosaris/idmap.py:128-392, key.py:166-205, scores.py:262-302, :480-495) on the same objects."""
+    from oracle import ref_import
+    ref_import.import_reference()
+    from sidekit.bosaris import IdMap as RIdMap, Key as RKey, Scores as RScores
+    key, ndx, sc, sc32, im = _objects()
+
+    def pair(cls_ref, mine, names):
+        r = cls_ref()
+        for n in names:
+            setattr(r, n, getattr(mine, n).copy())
+        return r
+
+    f = ("leftids", "rightids", "start", "stop")
+    rim = pair(RIdMap, im, f)
+    same = lambda a, b: all(numpy.array_equal(numpy.asarray(getattr(a, n)), numpy.asarray(getattr(b, n))) for n in f)
+    q = numpy.array(["spk2", "nobody", "spk0"], dtype="|O")
+    assert numpy.array_equal(im.map_left_to_right(q), rim.map_left_to_right(q))
+    q = numpy.array(["dir/file4", "dir/file1", "zzz"], dtype="|O")
+    assert numpy.array_equal(im.map_right_to_left(q), rim.map_right_to_left(q))
+    for keep in (True, False):
+        assert same(im.filter_on_left(["spk1", "spk9"], keep), rim.filter_on_left(["spk1", "spk9"], keep))
+        assert same(im.filter_on_right(["dir/file0", "dir/file5"], keep), rim.filter_on_right(["dir/file0", "dir/file5"], keep))
+    other = sk.IdMap()
+    other.set(numpy.array(["spk0", "new"], dtype="|O"), numpy.array(["dir/file0", "dir/file9"], dtype="|O"),
+              numpy.array([0, 5]), numpy.array([300, 90]))
+    rother = pair(RIdMap, other, f)
+    assert same(sk.IdMap.merge(im, other), RIdMap.merge(rim, rother))
+    for a, b in zip(im.split(4), rim.split(4)):
+        assert same(a, b)
+    rkey = pair(RKey, key, ("modelset", "segset", "tar", "non"))
+    rsc = pair(RScores, sc, ("modelset", "segset", "scoremask", "scoremat"))
+    mods, segs = ["m03", "m05", "zz"], ["seg_001", "seg_007", "seg_010", "qq"]
+    for keep in (True, False):
+        a, b = key.filter(mods, segs, keep), rkey.filter(mods, segs, keep)
+        assert all(numpy.array_equal(getattr(a, n), getattr(b, n)) for n in ("modelset", "segset", "tar", "non"))
+        a, b = sc.filter(mods, segs, keep), rsc.filter(mods, segs, keep)
+        assert all(numpy.array_equal(getattr(a, n), getattr(b, n)) for n in ("modelset", "segset", "scoremask", "scoremat"))
+    assert numpy.array_equal(sc.get_score("m03", "seg_007"), rsc.get_score("m03", "seg_007"))
+    with pytest.raises(Exception):
+        sc.get_score("nope", "seg_007")
+
+
+def test_container_utilities_basic():
+    key, ndx, sc, sc32, im = _objects()
+    assert list(im.filter_on_left(["spk1"], True).rightids) == ["dir/file1", "dir/file4"]
+    assert list(im.map_left_to_right(numpy.array(["spk2"], dtype="|O"))) == ["dir/file5"]          # the LAST pair of a left id
+    assert [m.leftids.shape[0] for m in im.split(4)] == [2, 2, 1, 1]
+    k = key.filter(key.modelset[:2], key.segset[:3], True)
+    assert k.tar.shape == (2, 3) and numpy.array_equal(k.tar, key.tar[:2, :3])
+    s = sc.filter(sc.modelset[:2], sc.segset[:3], False)
+    assert s.scoremat.shape == (5, 8) and numpy.array_equal(s.scoremat, sc.scoremat[2:, 3:])
+    assert sc.get_score(sc.modelset[1], sc.segset[2]).shape == (1, 1)

@@ -71,6 +71,20 @@ def _read_columns(path, n_min):
     return rows
 
 
+def _expand(mat, own_models, own_segs, new_models, new_segs, dtype):
+    """Place ``mat`` (own_models x own_segs) into the (new_models x new_segs) grid the way the merge methods of the
+    reference do (ndx.py:262-269, key.py:333-344, scores.py:441-448): the k-th own row goes to the k-th position of
+    ``new_models`` that holds an own model.  That is the right row when the own sets are sorted (``new_*`` are sorted
+    unions); with unsorted sets the reference permutes rows, and so does this."""
+    out = numpy.zeros((new_models.shape[0], new_segs.shape[0]), dtype=dtype)
+    ma = numpy.flatnonzero(numpy.isin(new_models, own_models))
+    mb = numpy.flatnonzero(numpy.isin(own_models, new_models))
+    sa = numpy.flatnonzero(numpy.isin(new_segs, own_segs))
+    sb = numpy.flatnonzero(numpy.isin(own_segs, new_segs))
+    out[ma[:, None], sa] = mat[mb[:, None], sb]
+    return out
+
+
 def _makedirs_for(path):
     d = os.path.dirname(path)
     if d != "" and not os.path.exists(d):
@@ -132,6 +146,19 @@ class Key:
         assert out.validate()
         return out
 
+    def merge(self, key_list):
+        """key.py:305-367: union of the model / segment sets (sorted), target / non-target marks OR-ed; a trial that is a
+        target in one key and a non-target in another is an error."""
+        assert isinstance(key_list, list), "Input is not a list"
+        for key2 in key_list:
+            models = numpy.union1d(self.modelset, key2.modelset)
+            segs = numpy.union1d(self.segset, key2.segset)
+            tar = _expand(self.tar, self.modelset, self.segset, models, segs, bool) | _expand(key2.tar, key2.modelset, key2.segset, models, segs, bool)
+            non = _expand(self.non, self.modelset, self.segset, models, segs, bool) | _expand(key2.non, key2.modelset, key2.segset, models, segs, bool)
+            assert numpy.sum(tar & non) == 0, "Conflict in the new Key"
+            self.modelset, self.segset, self.tar, self.non = models, segs, tar, non
+            self.validate()
+
     def to_ndx(self):
         ndx = Ndx()
         ndx.modelset, ndx.segset, ndx.trialmask = self.modelset, self.segset, self.tar | self.non
@@ -170,6 +197,17 @@ class Ndx:
         ndx = cls(models=numpy.array([r[0] for r in rows], dtype="|O"), testsegs=numpy.array([r[1] for r in rows], dtype="|O"))
         assert ndx.validate(), "Wrong Ndx format"
         return ndx
+
+    def merge(self, ndx_list):
+        """ndx.py:239-283: union of the sets (sorted); a trial of any input is a trial of the result."""
+        assert isinstance(ndx_list, list), "Input is not a list"
+        self.validate()
+        for ndx2 in ndx_list:
+            models = numpy.union1d(self.modelset, ndx2.modelset)
+            segs = numpy.union1d(self.segset, ndx2.segset)
+            mask = _expand(self.trialmask, self.modelset, self.segset, models, segs, bool) | \
+                _expand(ndx2.trialmask, ndx2.modelset, ndx2.segset, models, segs, bool)
+            self.modelset, self.segset, self.trialmask = models, segs, mask
 
     def save_txt(self, output_file_name):
         """ndx.py:115-126: one ``model segment`` line per trial, row by row."""
@@ -234,6 +272,25 @@ class Scores:
         out.modelset, out.segset = self.modelset[km], self.segset[ks]
         out.scoremat, out.scoremask = self.scoremat[km, :][:, ks], self.scoremask[km, :][:, ks]
         return out
+
+    def merge(self, score_list):
+        """scores.py:414-467: both sides are sorted first (in place, like the reference), then laid out over the union of
+        the sets; two scores for one trial are an error; the result is float64."""
+        assert isinstance(score_list, list), "Input is not a list"
+        self.validate()
+        for scr2 in score_list:
+            self.sort()
+            scr2.sort()
+            models = numpy.union1d(self.modelset, scr2.modelset)
+            segs = numpy.union1d(self.segset, scr2.segset)
+            mat1 = _expand(self.scoremat, self.modelset, self.segset, models, segs, numpy.float64)
+            mask1 = _expand(self.scoremask, self.modelset, self.segset, models, segs, bool)
+            mat2 = _expand(scr2.scoremat, scr2.modelset, scr2.segset, models, segs, numpy.float64)
+            mask2 = _expand(scr2.scoremask, scr2.modelset, scr2.segset, models, segs, bool)
+            assert numpy.sum(mask1 & mask2) == 0, "Conflict in the new scoremask"
+            self.scoremat, self.scoremask, self.scoremat_device = mat1 + mat2, mask1 | mask2, None
+            self.modelset, self.segset = models, segs
+            assert self.validate(), 'Wrong Scores format'
 
     def get_score(self, modelID, segID):
         """scores.py:480-495: the (1, 1) block of the trial; raises when the model or the segment is unknown."""

@@ -167,3 +167,51 @@ def test_container_utilities_basic():
     s = sc.filter(sc.modelset[:2], sc.segset[:3], False)
     assert s.scoremat.shape == (5, 8) and numpy.array_equal(s.scoremat, sc.scoremat[2:, 3:])
     assert sc.get_score(sc.modelset[1], sc.segset[2]).shape == (1, 1)
+
+
+@pytest.mark.reference
+def test_merges_match_the_reference():
+    """Ndx.merge / Key.merge / Scores.merge (ndx.py:239-283, key.py:305-367, scores.py:414-467), sorted and unsorted sets."""
+    import copy
+    from oracle import ref_import
+    ref_import.import_reference()
+    from sidekit.bosaris import Key as RKey, Ndx as RNdx, Scores as RScores
+    rng = numpy.random.default_rng(77)
+
+    def fill(cls, src, names):
+        o = cls()
+        for n in names:
+            setattr(o, n, copy.deepcopy(getattr(src, n)))
+        return o
+
+    def objects(models, segs, seed):
+        r = numpy.random.default_rng(seed).random((len(models), len(segs)))
+        k = sk.Key()
+        k.modelset, k.segset = numpy.array(models, dtype="|O"), numpy.array(segs, dtype="|O")
+        k.tar, k.non = r < 0.3, (r >= 0.3) & (r < 0.7)
+        s = sk.Scores()
+        s.modelset, s.segset, s.scoremask = k.modelset.copy(), k.segset.copy(), r < 0.7
+        s.scoremat = numpy.random.default_rng(seed + 1).standard_normal(r.shape)
+        return k, k.to_ndx(), s
+
+    for shuffle in (False, True):
+        m1, s1 = ["m%d" % i for i in range(5)], ["s%d" % i for i in range(6)]
+        m2, s2 = ["m%d" % i for i in range(3, 9)], ["s%d" % i for i in range(6, 11)]          # disjoint segments: no clashes
+        if shuffle:
+            m1, s1 = list(rng.permutation(m1)), list(rng.permutation(s1))
+        (k1, n1, c1), (k2, n2, c2) = objects(m1, s1, 5), objects(m2, s2, 9)
+        rn1, rn2 = fill(RNdx, n1, ("modelset", "segset", "trialmask")), fill(RNdx, n2, ("modelset", "segset", "trialmask"))
+        n1.merge([n2]); rn1.merge([rn2])
+        assert all(numpy.array_equal(getattr(n1, a), getattr(rn1, a)) for a in ("modelset", "segset", "trialmask"))
+        rk1, rk2 = fill(RKey, k1, ("modelset", "segset", "tar", "non")), fill(RKey, k2, ("modelset", "segset", "tar", "non"))
+        k1.merge([k2]); rk1.merge([rk2])
+        assert all(numpy.array_equal(getattr(k1, a), getattr(rk1, a)) for a in ("modelset", "segset", "tar", "non"))
+        f = ("modelset", "segset", "scoremask", "scoremat")
+        rc1, rc2 = fill(RScores, c1, f), fill(RScores, c2, f)
+        c1.merge([c2]); rc1.merge([rc2])
+        assert all(numpy.array_equal(getattr(c1, a), getattr(rc1, a)) for a in f)
+    ka, _, _ = objects(["a"], ["x"], 1)
+    kb, _, _ = objects(["a"], ["x"], 1)
+    ka.tar[:], ka.non[:], kb.tar[:], kb.non[:] = True, False, False, True
+    with pytest.raises(AssertionError):
+        ka.merge([kb])

@@ -106,6 +106,61 @@ class StatServer:
     def get_model_stat1(self, mod_id):
         return self.stat1[self.modelset == mod_id, :]
 
+    # accessors of statserver.py:574-654 (the k-th model is the k-th SORTED unique model id, a segment index is a row)
+    def get_model_stat0_by_index(self, mod_idx):
+        return self.stat0[self.modelset == numpy.unique(self.modelset)[mod_idx], :]
+
+    def get_model_stat1_by_index(self, mod_idx):
+        return self.stat1[self.modelset == numpy.unique(self.modelset)[mod_idx], :]
+
+    def get_segment_stat0(self, seg_id):
+        return self.stat0[self.segset == seg_id, :]
+
+    def get_segment_stat1(self, seg_id):
+        return self.stat1[self.segset == seg_id, :]
+
+    def get_segment_stat0_by_index(self, seg_idx):
+        return self.stat0[seg_idx, :]
+
+    def get_segment_stat1_by_index(self, seg_idx):
+        return self.stat1[seg_idx, :]
+
+    def get_model_segments(self, mod_id):
+        return self.segset[self.modelset == mod_id]
+
+    def get_model_segments_by_index(self, mod_idx):
+        # the reference indexes the 1-D segset with [mask, :] here (statserver.py:654) and raises IndexError; the intent is clear
+        return self.segset[self.modelset == numpy.unique(self.modelset)[mod_idx]]
+
+    def merge(*arg):
+        """statserver.py:337-388: one StatServer with every distinct (model, segment, start, stop) session of the arguments
+        (the later one wins when a session is repeated).  Rows come in first-occurrence order; the reference's row order is
+        the iteration order of a Python ``set`` of strings, i.e. unspecified."""
+        assert all(isinstance(ss, StatServer) and ss.validate() for ss in arg), "Arguments must be proper StatServers"
+        d0, d1 = arg[0].stat0.shape[1], arg[0].stat1.shape[1]
+        assert all(ss.stat0.shape[1] == d0 and ss.stat1.shape[1] == d1 for ss in arg), "Stat dimensions are not consistent"
+        index, rows = {}, []
+        for k, ss in enumerate(arg):
+            for i, key in enumerate(zip(ss.modelset.tolist(), ss.segset.tolist(), map(str, ss.start), map(str, ss.stop))):
+                if key not in index:
+                    index[key] = len(rows)
+                    rows.append((k, i))
+                else:
+                    rows[index[key]] = (k, i)
+        if len(rows) != sum(ss.modelset.shape[0] for ss in arg):
+            print("WARNING: duplicated segmentID in input StatServers")
+        out = StatServer()
+        n = len(rows)
+        out.modelset, out.segset = numpy.empty(n, dtype="object"), numpy.empty(n, dtype="object")
+        out.start, out.stop = numpy.empty(n, dtype="object"), numpy.empty(n, dtype="object")
+        out.stat0, out.stat1 = numpy.zeros((n, d0), dtype=STAT_TYPE), numpy.zeros((n, d1), dtype=STAT_TYPE)
+        for r, (k, i) in enumerate(rows):
+            ss = arg[k]
+            out.modelset[r], out.segset[r], out.start[r], out.stop[r] = ss.modelset[i], ss.segset[i], ss.start[i], ss.stop[i]
+            out.stat0[r], out.stat1[r] = ss.stat0[i], ss.stat1[i]
+        assert out.validate(), "Problem in StatServer Merging"
+        return out
+
     def _classes(self):
         """(sorted unique models, class index of every session, sessions per class, class means)."""
         models, inv = numpy.unique(self.modelset, return_inverse=True)

@@ -4,6 +4,7 @@ Host (numpy float64) code: the reference's per-speaker loops are vectorised, so 
 import copy
 
 import numpy
+import pytest
 
 import sidekit_b200 as sk
 from tests.helpers import golden
@@ -53,3 +54,44 @@ def test_whitening_and_spectral_norm_match_reference():
         assert _close(ss.stat1 * sign, ref, 1e-8)
         assert _close(ss.stat1 @ ss.stat1.T, ref @ ref.T, 1e-8)   # what every scorer sees (inner products) is identical
         assert numpy.allclose(numpy.linalg.norm(ss.stat1, axis=1), 1.0)
+
+
+@pytest.mark.reference
+def test_statserver_accessors_and_merge_match_the_reference():
+    """statserver.py:337-388 (merge) and :555-654 (accessors) on the same sessions; merge is compared as a set of sessions
+    because the reference's row order is the iteration order of a Python set."""
+    import numpy
+    import sidekit_b200 as sk
+    from oracle import ref_import
+    sidekit = ref_import.import_reference()
+    rng = numpy.random.default_rng(3)
+
+    def make(cls, models, segs, X):
+        s = cls()
+        s.modelset, s.segset = numpy.array(models, dtype="|O"), numpy.array(segs, dtype="|O")
+        s.start, s.stop = numpy.empty(len(models), dtype="|O"), numpy.empty(len(models), dtype="|O")
+        s.stat0, s.stat1 = numpy.ones((len(models), 1)), numpy.array(X, dtype=numpy.float64)
+        return s
+
+    Xa, Xb = rng.standard_normal((5, 4)), rng.standard_normal((4, 4))
+    ma, sa = ["b", "a", "b", "c", "a"], ["s0", "s1", "s2", "s3", "s4"]
+    mb, sb = ["a", "d", "b", "d"], ["s1", "s5", "s6", "s7"]                     # ("a", "s1") repeats a session of the first
+    mine_a, mine_b = make(sk.StatServer, ma, sa, Xa), make(sk.StatServer, mb, sb, Xb)
+    ref_a, ref_b = make(sidekit.StatServer, ma, sa, Xa), make(sidekit.StatServer, mb, sb, Xb)
+    for k in range(3):
+        assert numpy.array_equal(mine_a.get_model_stat1_by_index(k), ref_a.get_model_stat1_by_index(k))
+        assert numpy.array_equal(mine_a.get_model_stat0_by_index(k), ref_a.get_model_stat0_by_index(k))
+    assert numpy.array_equal(mine_a.get_segment_stat1("s3"), ref_a.get_segment_stat1("s3"))
+    assert numpy.array_equal(mine_a.get_segment_stat0("s3"), ref_a.get_segment_stat0("s3"))
+    assert numpy.array_equal(mine_a.get_segment_stat1_by_index(2), ref_a.get_segment_stat1_by_index(2))
+    assert numpy.array_equal(mine_a.get_segment_stat0_by_index(2), ref_a.get_segment_stat0_by_index(2))
+    assert numpy.array_equal(mine_a.get_model_segments("b"), ref_a.get_model_segments("b"))
+    assert list(mine_a.get_model_segments_by_index(0)) == ["s1", "s4"]
+    with pytest.raises(IndexError):
+        ref_a.get_model_segments_by_index(0)
+    mine = sk.StatServer.merge(mine_a, mine_b)
+    ref = sidekit.StatServer.merge(ref_a, ref_b)
+    assert mine.validate() and mine.modelset.shape[0] == ref.modelset.shape[0] == 8
+    key = lambda s: sorted((m, g, tuple(x)) for m, g, x in zip(s.modelset.tolist(), s.segset.tolist(), s.stat1.tolist()))
+    assert key(mine) == key(ref)
+    assert list(mine.segset[:5]) == sa and numpy.array_equal(mine.stat1[1], Xb[0])          # first-occurrence order, the later session wins

@@ -325,7 +325,7 @@ def run_ours(args):
                                          "workload": "256 utterances 2-20 s at 44.1 kHz -> 16 kHz, packed ragged batch",
                                          "roofline": {"kernel": "resample_kernel", "bound": "hbm", "achieved": gbs,
                                                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                                                      "traffic": None}}
+                                                      "traffic": load_traffic("resample_kernel")}}
         del rx, ry
 
     if rank == 0:

@@ -920,7 +920,7 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
     if ((rc = h->cmvn_part.ensure(frontend_cmvn_scratch_bytes(m.fe, B, pl.t_max)))) return rc;
     const int D = m.pool_D;
     if (is_resnet(m.archi)) {
-        if ((rc = h->poolX.ensure((size_t)pl.pool_frames * D * sizeof(float)))) return rc;
+        if ((rc = h->poolX.ensure((size_t)pl.pool_frames * D * sizeof(uint16_t)))) return rc;
         if ((rc = h->poolH.ensure((size_t)pl.pool_frames * m.att_A * sizeof(float)))) return rc;
         if ((rc = h->poolL.ensure((size_t)pl.pool_frames * D * sizeof(float)))) return rc;
         if ((rc = h->gc.ensure((size_t)B * 2 * D * sizeof(float)))) return rc;
@@ -1203,11 +1203,12 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     // attentive statistics pooling with global context (pooling.py:151-171)
     const Level& L4 = pl.lv[3];
     const int D = m.pool_D, A = m.att_A, F = pl.pool_frames;
-    float *X = (float*)h->poolX.p, *Hh = (float*)h->poolH.p, *Lg = (float*)h->poolL.p;
+    uint16_t* X = (uint16_t*)h->poolX.p;           // frames x D in the activations' 16-bit format
+    float *Hh = (float*)h->poolH.p, *Lg = (float*)h->poolL.p;
     ProfScope pool_scope(PROF_POOL, st);
     SKB_TRY(launch_gather_frames(m.bf16, buf(level, cur), L4.plane, L4.C, L4.W, L4.Wp, L4.G, d32 + pl.o_frame_row, F, X, st));
     if (m.global_context) {
-        SKB_TRY(launch_meanstd(X, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, nullptr, nullptr, (float*)h->gc.p, st));
+        SKB_TRY(launch_meanstd(m.bf16, X, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, nullptr, nullptr, (float*)h->gc.p, st));
         SKB_TRY(h->skinny_ws.ensure(skinny_gemm_ws_floats(B, A, 2 * D) * sizeof(float)));
         SKB_TRY(launch_skinny_gemm((const float*)h->gc.p, B, 2 * D, m.att_w1g, A, m.att_b1, 1.f, (float*)h->hb.p, A, (float*)h->skinny_ws.p, st));
     } else {
@@ -1228,7 +1229,7 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
     }
     SKB_TRY(launch_att_act(Hh, (const float*)h->hb.p, d32 + pl.o_frame_utt, m.att_bn_s, m.att_bn_t, F, A, st));
     SKB_TRY(gemm_nt_split(Hh, F, A, m.p_w2, m.att_b2, 1.f, Lg, D, st));
-    SKB_TRY(launch_softmax_pool(X, Lg, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, (float*)h->pooled.p, st));
+    SKB_TRY(launch_softmax_pool(m.bf16, X, Lg, d64 + pl.o_pool_off, d32 + pl.o_pool_nfr, B, D, (float*)h->pooled.p, st));
     g_launches += 7;
     if (stop && !strcmp(stop, "pooled")) {
         *per_utt = 2 * D;

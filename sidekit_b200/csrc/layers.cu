@@ -555,12 +555,14 @@ int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, lon
     return SKB_OK;
 }
 
-// ----------------------------------------------------------------------------- planes -> dense fp32 frames
+// ----------------------------------------------------------------------------- planes -> dense 16-bit frames
 // X[frame][c * W + f] = act[c/8][G + (row0_b + t) * Wp + f][c%8]: the (B, C*F, T) view of
-// sidekit/nnet/pooling.py:160-163, stored frame-major.  Thread per (frame, f, chunk).
+// sidekit/nnet/pooling.py:160-163, stored frame-major.  Thread per (frame, f, chunk).  The values stay in the 16-bit
+// format of the activations (the statistics kernels widen them on the fly, which is exact): half the bytes of the
+// former fp32 copy on the gather's write and on both readers.
 template <bool BF16>
 __global__ void gather_frames_kernel(const uint16_t* __restrict__ act, long long plane, int C, int W, int Wp, int G,
-                                     const int* __restrict__ frame_row, int n_frames, float* __restrict__ X) {
+                                     const int* __restrict__ frame_row, int n_frames, uint16_t* __restrict__ X) {
     const int chunks = C >> 3;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)n_frames * W * chunks;
@@ -571,12 +573,11 @@ __global__ void gather_frames_kernel(const uint16_t* __restrict__ act, long long
     const long long pix = (long long)G + (long long)frame_row[fr] * Wp + f;
     const uint4 a = *reinterpret_cast<const uint4*>(act + ((size_t)j * plane + pix) * 8);
     const uint32_t u[4] = {a.x, a.y, a.z, a.w};
-    float* dst = X + (size_t)fr * C * W;
+    uint16_t* dst = X + (size_t)fr * C * W;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float2 v = unpack2<BF16>(u[e]);
-        dst[(j * 8 + 2 * e) * W + f] = v.x;
-        dst[(j * 8 + 2 * e + 1) * W + f] = v.y;
+        dst[(j * 8 + 2 * e) * W + f] = (uint16_t)(u[e] & 0xffffu);
+        dst[(j * 8 + 2 * e + 1) * W + f] = (uint16_t)(u[e] >> 16);
     }
 }
 
@@ -609,7 +610,7 @@ int launch_gather_pack(const uint16_t* act, long long plane, int C, int W, int W
 }
 
 int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C, int W, int Wp, int G,
-                         const int* frame_row, int n_frames, float* X, cudaStream_t st) {
+                         const int* frame_row, int n_frames, uint16_t* X, cudaStream_t st) {
     const long long total = (long long)n_frames * W * (C / 8);
     const int threads = 256;
     const int blocks = (int)((total + threads - 1) / threads);
@@ -627,7 +628,8 @@ int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C,
 // affine (s, t) applied as mean' = s*mean + t, std' = |s|*std (folds the TDNN's last BatchNorm).
 // One CTA = 32 consecutive features x 8 time slices (threadIdx.y); a single pass with double accumulators (sum, sum of
 // squares), the slices combined in slice order: deterministic, and in double as exact as the two-pass formula.
-__global__ void __launch_bounds__(256) meanstd_kernel(const float* __restrict__ X, const long long* __restrict__ frame_off,
+template <bool BF16>
+__global__ void __launch_bounds__(256) meanstd_kernel(const uint16_t* __restrict__ X, const long long* __restrict__ frame_off,
                                                       const int* __restrict__ n_fr, int D, const float* __restrict__ aff_s,
                                                       const float* __restrict__ aff_t, float* __restrict__ out) {
     __shared__ double ps[8][32], pss[8][32];
@@ -636,9 +638,9 @@ __global__ void __launch_bounds__(256) meanstd_kernel(const float* __restrict__ 
     const int T = n_fr[b];
     double s = 0.0, ss = 0.0;
     if (d < D) {
-        const float* x = X + (size_t)frame_off[b] * D + d;
+        const uint16_t* x = X + (size_t)frame_off[b] * D + d;
         for (int t = threadIdx.y; t < T; t += 8) {
-            const double v = (double)x[(size_t)t * D];
+            const double v = (double)unpack2<BF16>((uint32_t)x[(size_t)t * D]).x;
             s += v;
             ss = fma(v, v, ss);
         }
@@ -730,10 +732,11 @@ int launch_meanstd_planes(bool bf16, const uint16_t* act, long long plane, int G
     return SKB_OK;
 }
 
-int launch_meanstd(const float* X, const long long* frame_off, const int* n_fr, int B, int D, const float* aff_s,
+int launch_meanstd(bool bf16, const uint16_t* X, const long long* frame_off, const int* n_fr, int B, int D, const float* aff_s,
                    const float* aff_t, float* out, cudaStream_t st) {
     dim3 grid((D + 31) / 32, B);
-    meanstd_kernel<<<grid, dim3(32, 8), 0, st>>>(X, frame_off, n_fr, D, aff_s, aff_t, out);
+    if (bf16) meanstd_kernel<true><<<grid, dim3(32, 8), 0, st>>>(X, frame_off, n_fr, D, aff_s, aff_t, out);
+    else meanstd_kernel<false><<<grid, dim3(32, 8), 0, st>>>(X, frame_off, n_fr, D, aff_s, aff_t, out);
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
@@ -767,7 +770,8 @@ int launch_att_act(float* h, const float* hb, const int* frame_utt, const float*
 // One CTA = 32 consecutive features x 8 time slices; each slice runs an ONLINE softmax (running max with rescaling) over
 // its frames in one pass over X and the logits, and the eight (max, sum e, sum x e, sum x^2 e) partials are merged in
 // slice order.
-__global__ void __launch_bounds__(256) softmax_pool_kernel(const float* __restrict__ X, const float* __restrict__ logit,
+template <bool BF16>
+__global__ void __launch_bounds__(256) softmax_pool_kernel(const uint16_t* __restrict__ X, const float* __restrict__ logit,
                                                            const long long* __restrict__ frame_off, const int* __restrict__ n_fr, int D,
                                                            float* __restrict__ out) {
     __shared__ float pm[8][32], pe[8][32], px[8][32], pxx[8][32];
@@ -783,7 +787,7 @@ __global__ void __launch_bounds__(256) softmax_pool_kernel(const float* __restri
             for (int u = 0; u < 4; ++u) {
                 const int t = t0 + 8 * u;
                 lv[u] = t < T ? logit[base + (size_t)t * D] : -INFINITY;
-                xv[u] = t < T ? X[base + (size_t)t * D] : 0.f;
+                xv[u] = t < T ? unpack2<BF16>((uint32_t)X[base + (size_t)t * D]).x : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -820,10 +824,11 @@ __global__ void __launch_bounds__(256) softmax_pool_kernel(const float* __restri
     out[(size_t)b * 2 * D + D + d] = sqrtf(fmaxf(var, 1e-9f));
 }
 
-int launch_softmax_pool(const float* X, const float* logit, const long long* frame_off, const int* n_fr, int B, int D,
+int launch_softmax_pool(bool bf16, const uint16_t* X, const float* logit, const long long* frame_off, const int* n_fr, int B, int D,
                         float* out, cudaStream_t st) {
     dim3 grid((D + 31) / 32, B);
-    softmax_pool_kernel<<<grid, dim3(32, 8), 0, st>>>(X, logit, frame_off, n_fr, D, out);
+    if (bf16) softmax_pool_kernel<true><<<grid, dim3(32, 8), 0, st>>>(X, logit, frame_off, n_fr, D, out);
+    else softmax_pool_kernel<false><<<grid, dim3(32, 8), 0, st>>>(X, logit, frame_off, n_fr, D, out);
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }

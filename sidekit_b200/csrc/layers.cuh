@@ -33,16 +33,16 @@ int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, lon
                     const int* utt_row0, const int* utt_count, int B, int Cin, int Cout, const float* w2t, const float* b2,
                     const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st);
 int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C, int W, int Wp, int G,
-                         const int* frame_row, int n_frames, float* X, cudaStream_t st);
+                         const int* frame_row, int n_frames, uint16_t* X, cudaStream_t st);
 int launch_gather_pack(const uint16_t* act, long long plane, int C, int W, int Wp, int G, const int* frame_row, int n_frames,
                        uint16_t* hi, cudaStream_t st);
 int launch_meanstd_planes(bool bf16, const uint16_t* act, long long plane, int G, const int* utt_row0, const int* n_fr, int B, int D,
                           const float* aff_s, const float* aff_t, float* out, cudaStream_t st);
-int launch_meanstd(const float* X, const long long* frame_off, const int* n_fr, int B, int D, const float* aff_s,
+int launch_meanstd(bool bf16, const uint16_t* X, const long long* frame_off, const int* n_fr, int B, int D, const float* aff_s,
                    const float* aff_t, float* out, cudaStream_t st);
 int launch_att_act(float* h, const float* hb, const int* frame_utt, const float* bn_s, const float* bn_t, int n_frames,
                    int A, cudaStream_t st);
-int launch_softmax_pool(const float* X, const float* logit, const long long* frame_off, const int* n_fr, int B, int D,
+int launch_softmax_pool(bool bf16, const uint16_t* X, const float* logit, const long long* frame_off, const int* n_fr, int B, int D,
                         float* out, cudaStream_t st);
 int launch_head_norm(const float* x, const float* aff_s, const float* aff_t, int B, int E, int norm_embedding,
                      float* emb_pre, float* emb, cudaStream_t st);

@@ -626,41 +626,49 @@ int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C,
 // ----------------------------------------------------------------------------- mean / unbiased std over time
 // MeanStdPooling (sidekit/nnet/pooling.py:55-70): out[b] = [mean_t x ; std_t x (ddof=1)].  Optional per-channel
 // affine (s, t) applied as mean' = s*mean + t, std' = |s|*std (folds the TDNN's last BatchNorm).
-// One CTA = 32 consecutive features x 8 time slices (threadIdx.y); a single pass with double accumulators (sum, sum of
+// One CTA = 64 consecutive features (two per thread) x 8 time slices (threadIdx.y); a single pass with double accumulators (sum, sum of
 // squares), the slices combined in slice order: deterministic, and in double as exact as the two-pass formula.
 template <bool BF16>
 __global__ void __launch_bounds__(256) meanstd_kernel(const uint16_t* __restrict__ X, const long long* __restrict__ frame_off,
                                                       const int* __restrict__ n_fr, int D, const float* __restrict__ aff_s,
                                                       const float* __restrict__ aff_t, float* __restrict__ out) {
-    __shared__ double ps[8][32], pss[8][32];
+    // a thread owns TWO consecutive features (one 32-bit load per frame: a warp reads 128 contiguous bytes); D is even
+    __shared__ double ps[8][64], pss[8][64];
     const int b = blockIdx.y;
-    const int d = blockIdx.x * 32 + threadIdx.x;
+    const int d = (blockIdx.x * 32 + threadIdx.x) * 2;
     const int T = n_fr[b];
-    double s = 0.0, ss = 0.0;
+    double s[2] = {0.0, 0.0}, ss[2] = {0.0, 0.0};
     if (d < D) {
         const uint16_t* x = X + (size_t)frame_off[b] * D + d;
         for (int t = threadIdx.y; t < T; t += 8) {
-            const double v = (double)unpack2<BF16>((uint32_t)x[(size_t)t * D]).x;
-            s += v;
-            ss = fma(v, v, ss);
+            const float2 v2 = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(x + (size_t)t * D));
+            const double v0 = (double)v2.x, v1 = (double)v2.y;
+            s[0] += v0; ss[0] = fma(v0, v0, ss[0]);
+            s[1] += v1; ss[1] = fma(v1, v1, ss[1]);
         }
     }
-    ps[threadIdx.y][threadIdx.x] = s;
-    pss[threadIdx.y][threadIdx.x] = ss;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        ps[threadIdx.y][2 * threadIdx.x + q] = s[q];
+        pss[threadIdx.y][2 * threadIdx.x + q] = ss[q];
+    }
     __syncthreads();
     if (threadIdx.y != 0 || d >= D) return;
-    s = 0.0; ss = 0.0;
-    for (int k = 0; k < 8; ++k) { s += ps[k][threadIdx.x]; ss += pss[k][threadIdx.x]; }
-    const double mean = s / T;
-    const double var = fmax(ss - s * mean, 0.0) / (double)(T - 1);           // unbiased; T == 1 -> NaN like torch.std
-    float sd = (float)sqrt(var);
-    float mu = (float)mean;
-    if (aff_s) {
-        mu = aff_s[d] * mu + aff_t[d];
-        sd = fabsf(aff_s[d]) * sd;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        double a = 0.0, aa = 0.0;
+        for (int k = 0; k < 8; ++k) { a += ps[k][2 * threadIdx.x + q]; aa += pss[k][2 * threadIdx.x + q]; }
+        const double mean = a / T;
+        const double var = fmax(aa - a * mean, 0.0) / (double)(T - 1);           // unbiased; T == 1 -> NaN like torch.std
+        float sd = (float)sqrt(var);
+        float mu = (float)mean;
+        if (aff_s) {
+            mu = aff_s[d + q] * mu + aff_t[d + q];
+            sd = fabsf(aff_s[d + q]) * sd;
+        }
+        out[(size_t)b * 2 * D + d + q] = mu;
+        out[(size_t)b * 2 * D + D + d + q] = sd;
     }
-    out[(size_t)b * 2 * D + d] = mu;
-    out[(size_t)b * 2 * D + D + d] = sd;
 }
 
 // MeanStdPooling straight from the 16-bit chunk planes of a W == 1 (TDNN) activation: one CTA per (utterance, 8-channel
@@ -734,7 +742,11 @@ int launch_meanstd_planes(bool bf16, const uint16_t* act, long long plane, int G
 
 int launch_meanstd(bool bf16, const uint16_t* X, const long long* frame_off, const int* n_fr, int B, int D, const float* aff_s,
                    const float* aff_t, float* out, cudaStream_t st) {
-    dim3 grid((D + 31) / 32, B);
+    if (D % 2 != 0) {
+        set_last_error(__FILE__, __LINE__, "meanstd: the feature count must be even");
+        return SKB_ERR_ARG;
+    }
+    dim3 grid((D + 63) / 64, B);
     if (bf16) meanstd_kernel<true><<<grid, dim3(32, 8), 0, st>>>(X, frame_off, n_fr, D, aff_s, aff_t, out);
     else meanstd_kernel<false><<<grid, dim3(32, 8), 0, st>>>(X, frame_off, n_fr, D, aff_s, aff_t, out);
     SKB_LAUNCH_CHECK(st);
@@ -774,59 +786,76 @@ template <bool BF16>
 __global__ void __launch_bounds__(256) softmax_pool_kernel(const uint16_t* __restrict__ X, const float* __restrict__ logit,
                                                            const long long* __restrict__ frame_off, const int* __restrict__ n_fr, int D,
                                                            float* __restrict__ out) {
-    __shared__ float pm[8][32], pe[8][32], px[8][32], pxx[8][32];
+    // a thread owns TWO consecutive features: one 32-bit load of X and one 64-bit load of the logits per frame (D is even)
+    __shared__ float pm[8][64], pe[8][64], px[8][64], pxx[8][64];
     const int b = blockIdx.y;
-    const int d = blockIdx.x * 32 + threadIdx.x;
+    const int d = (blockIdx.x * 32 + threadIdx.x) * 2;
     const int T = n_fr[b];
-    float m = -INFINITY, se = 0.f, sx = 0.f, sxx = 0.f;
+    float m[2] = {-INFINITY, -INFINITY}, se[2] = {0.f, 0.f}, sx[2] = {0.f, 0.f}, sxx[2] = {0.f, 0.f};
     if (d < D) {
         const size_t base = (size_t)frame_off[b] * D + d;
         for (int t0 = threadIdx.y; t0 < T; t0 += 32) {
-            float lv[4], xv[4];                            // four frames' loads in flight before the dependent updates
+            float2 lv[4], xv[4];                           // four frames' loads in flight before the dependent updates
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int t = t0 + 8 * u;
-                lv[u] = t < T ? logit[base + (size_t)t * D] : -INFINITY;
-                xv[u] = t < T ? unpack2<BF16>((uint32_t)X[base + (size_t)t * D]).x : 0.f;
+                lv[u] = t < T ? *reinterpret_cast<const float2*>(logit + base + (size_t)t * D) : make_float2(-INFINITY, -INFINITY);
+                xv[u] = t < T ? unpack2<BF16>(*reinterpret_cast<const uint32_t*>(X + base + (size_t)t * D)) : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (t0 + 8 * u >= T) break;
-                const float l = lv[u], x = xv[u];
-                if (l > m) {                               // new running max: rescale what has been accumulated
-                    const float r = __expf(m - l);         // exp(-inf) = 0 on the first frame
-                    se *= r; sx *= r; sxx *= r;
-                    m = l;
+                const float lq[2] = {lv[u].x, lv[u].y}, xq[2] = {xv[u].x, xv[u].y};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float l = lq[q], x = xq[q];
+                    if (l > m[q]) {                        // new running max: rescale what has been accumulated
+                        const float r = __expf(m[q] - l);  // exp(-inf) = 0 on the first frame
+                        se[q] *= r; sx[q] *= r; sxx[q] *= r;
+                        m[q] = l;
+                    }
+                    const float e = __expf(l - m[q]);
+                    se[q] += e;
+                    sx[q] = fmaf(x, e, sx[q]);
+                    sxx[q] = fmaf(x * x, e, sxx[q]);
                 }
-                const float e = __expf(l - m);
-                se += e;
-                sx = fmaf(x, e, sx);
-                sxx = fmaf(x * x, e, sxx);
             }
         }
     }
-    pm[threadIdx.y][threadIdx.x] = m; pe[threadIdx.y][threadIdx.x] = se;
-    px[threadIdx.y][threadIdx.x] = sx; pxx[threadIdx.y][threadIdx.x] = sxx;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int c = 2 * threadIdx.x + q;
+        pm[threadIdx.y][c] = m[q]; pe[threadIdx.y][c] = se[q];
+        px[threadIdx.y][c] = sx[q]; pxx[threadIdx.y][c] = sxx[q];
+    }
     __syncthreads();
     if (threadIdx.y != 0 || d >= D) return;
-    float gm = -INFINITY;
-    for (int k = 0; k < 8; ++k) gm = fmaxf(gm, pm[k][threadIdx.x]);
-    se = 0.f; sx = 0.f; sxx = 0.f;
-    for (int k = 0; k < 8; ++k) {
-        const float r = __expf(pm[k][threadIdx.x] - gm);   // empty slices (T < 8): exp(-inf) = 0
-        se = fmaf(pe[k][threadIdx.x], r, se);
-        sx = fmaf(px[k][threadIdx.x], r, sx);
-        sxx = fmaf(pxx[k][threadIdx.x], r, sxx);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int c = 2 * threadIdx.x + q;
+        float gm = -INFINITY;
+        for (int k = 0; k < 8; ++k) gm = fmaxf(gm, pm[k][c]);
+        float a = 0.f, ax = 0.f, axx = 0.f;
+        for (int k = 0; k < 8; ++k) {
+            const float r = __expf(pm[k][c] - gm);         // empty slices (T < 8): exp(-inf) = 0
+            a = fmaf(pe[k][c], r, a);
+            ax = fmaf(px[k][c], r, ax);
+            axx = fmaf(pxx[k][c], r, axx);
+        }
+        const float mu = ax / a;
+        const float var = axx / a - mu * mu;
+        out[(size_t)b * 2 * D + d + q] = mu;
+        out[(size_t)b * 2 * D + D + d + q] = sqrtf(fmaxf(var, 1e-9f));
     }
-    const float mu = sx / se;
-    const float var = sxx / se - mu * mu;
-    out[(size_t)b * 2 * D + d] = mu;
-    out[(size_t)b * 2 * D + D + d] = sqrtf(fmaxf(var, 1e-9f));
 }
 
 int launch_softmax_pool(bool bf16, const uint16_t* X, const float* logit, const long long* frame_off, const int* n_fr, int B, int D,
                         float* out, cudaStream_t st) {
-    dim3 grid((D + 31) / 32, B);
+    if (D % 2 != 0) {
+        set_last_error(__FILE__, __LINE__, "softmax_pool: the feature count must be even");
+        return SKB_ERR_ARG;
+    }
+    dim3 grid((D + 63) / 64, B);
     if (bf16) softmax_pool_kernel<true><<<grid, dim3(32, 8), 0, st>>>(X, logit, frame_off, n_fr, D, out);
     else softmax_pool_kernel<false><<<grid, dim3(32, 8), 0, st>>>(X, logit, frame_off, n_fr, D, out);
     SKB_LAUNCH_CHECK(st);

@@ -68,6 +68,12 @@ int skb_xtractor_forward(skb_xtractor_t* h, const float* wave_dev, const int64_t
 /* The embedding BEFORE the final F.normalize of the most recent forward call (what the reference
  * returns for loss='cce' with is_eval=True, xvector.py:896-898): out_dev (n_utt, E). */
 int skb_xtractor_pre_embedding(skb_xtractor_t* h, int n_utt, float* out_dev, void* stream);
+/* fp16 range guard.  With fp16 operands (compute_dtype 0) every stored activation is converted with saturation
+ * (|x| > 65504 becomes +-65504 instead of +-inf) and the storing kernels count the threads that saw a saturated value.
+ * Returns the CUMULATIVE count for this handle in *count after synchronising `stream`; a caller compares it with the
+ * value it saw before its forward calls: any increase means the weights / inputs do not fit fp16 and the embeddings
+ * of those calls are wrong -- rebuild the handle with compute_dtype 1 (bf16).  Always 0 for bf16 handles. */
+int skb_xtractor_overflow_count(skb_xtractor_t* h, void* stream, int64_t* count);
 /* Same call with HOST buffers: H2D of the waveforms, forward, D2H of the results, synchronous. */
 int skb_xtractor_forward_host(skb_xtractor_t* h, const float* wave_host, const int64_t* lengths, int n_utt,
                               int norm_embedding, float* emb_host, float* logits_host, void* stream);
@@ -97,6 +103,20 @@ int skb_meanstd_pool(const float* x_dev, int n_utt, int D, int T, float* out_dev
 int skb_score_gemm(const float* E_dev, const float* T_dev, int Ne, int Nt, int D, const float* rowterm_dev,
                    const float* colterm_dev, double cst, double alpha, int passes, int out_dtype, void* out_dev,
                    int64_t ld_out, void* stream);
+
+/* The same with the test-side operand PACKED ONCE (scaled, split into fp16 hi / lo planes, tiled): scoring a test set
+ * against many enrol panels -- the row-panel sharding of a 20k x 20k trial matrix over GPUs, or repeated calls --
+ * then costs only the enrol panel's preparation and the GEMM.  T_dev (rows, D) fp32 row-major is read once. */
+typedef struct skb_packed skb_packed_t;
+int skb_packed_create(const float* T_dev, int rows, int D, skb_packed_t** out, void* stream);
+void skb_packed_destroy(skb_packed_t* p);
+int skb_score_gemm_packed(const float* E_dev, int Ne, const skb_packed_t* T, const float* rowterm_dev,
+                          const float* colterm_dev, double cst, double alpha, int passes, int out_dtype, void* out_dev,
+                          int64_t ld_out, void* stream);
+
+/* dst[i] = (double)src[i]: the float64 view of a float32 score matrix, produced chunk by chunk on its way to the host
+ * (sidekit's PLDA / two-covariance scorers return float64, iv_scoring.py:205, :462). */
+int skb_widen_f32_f64(const float* src_dev, double* dst_dev, int64_t n, void* stream);
 
 /* Operand preparation for the quadratic scorers (center_stat1 statserver.py:810-817, then the
  * model_part / seg_part / Psi fold of iv_scoring.py:451-462): xc = X - mu (mu may be NULL);

@@ -22,7 +22,11 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SIDEKIT_REFERENCE_ROOT", "/root/reference")
+# /root/reference in the build container; on the GPU box the unmodified install made by oracle/build_ref.py (git-ignored,
+# travels with the snapshot)
+_INSTALLED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("SIDEKIT_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/sidekit") else _INSTALLED)
 
 
 def available():

@@ -24,40 +24,38 @@ def _first_index(ids):
     return table
 
 
-def _device_to_numpy(t, chunk_bytes=128 << 20):
-    """Device tensor -> numpy array through two pinned staging buffers: the PCIe copy of chunk k+1 overlaps the host
-    copy of chunk k into the (pageable) result.  A plain ``.cpu()`` of a 20k x 20k float64 matrix takes 1.5 s."""
+def _device_to_numpy(t, np_dtype=None, chunk_bytes=256 << 20):
+    """Device tensor -> numpy array.  Large matrices land in a PINNED host block taken from torch's caching host allocator
+    (the numpy array is a view of it and gives the block back to the cache when it is garbage collected, so a scoring loop
+    re-uses one block): the copy runs at PCIe speed straight into the result, with no pageable bounce (a plain ``.cpu()`` of a
+    20k x 20k float64 matrix takes 1.5 s).  ``np_dtype=float64`` on a float32 tensor widens on the DEVICE, chunk by chunk
+    (``skb_widen_f32_f64``), on the way out: the reference's PLDA scorers return float64, the score GEMM keeps float32."""
     import torch
+    from . import _lib
     t = t.contiguous()
-    out = numpy.empty(tuple(t.shape), dtype=_NP_DTYPE[t.dtype])
-    if t.numel() * t.element_size() < 4 * chunk_bytes or t.dim() != 2:
-        out[...] = t.cpu().numpy()
-        return out
-    rows_per = max(1, chunk_bytes // (t.shape[1] * t.element_size()))
-    stage = [torch.empty((rows_per, t.shape[1]), dtype=t.dtype, pin_memory=True) for _ in range(2)]
-    stream = torch.cuda.Stream(t.device)
-    stream.wait_stream(torch.cuda.current_stream(t.device))
-    events, spans = [], []
-    starts = list(range(0, t.shape[0], rows_per))
-
-    def issue(k):
-        lo = starts[k]
-        hi = min(t.shape[0], lo + rows_per)
-        with torch.cuda.stream(stream):
-            stage[k % 2][:hi - lo].copy_(t[lo:hi], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(stream)
-        events.append(ev)
-        spans.append((lo, hi))
-
-    issue(0)
-    for k in range(len(starts)):
-        if k + 1 < len(starts):
-            issue(k + 1)                  # its staging buffer was drained in the previous iteration
-        events[k].synchronize()
-        lo, hi = spans[k]
-        numpy.copyto(out[lo:hi], stage[k % 2][:hi - lo].numpy())
-    return out
+    np_dtype = numpy.dtype(np_dtype or _NP_DTYPE[t.dtype])
+    widen = t.dtype == torch.float32 and np_dtype == numpy.float64
+    if not widen and np_dtype != numpy.dtype(_NP_DTYPE[t.dtype]):
+        raise TypeError("unsupported conversion %s -> %s" % (t.dtype, np_dtype))
+    nbytes = t.numel() * np_dtype.itemsize
+    if nbytes < (32 << 20) or t.dim() != 2:
+        out = t.cpu().numpy()
+        return out.astype(np_dtype) if widen else out
+    host = torch.empty(tuple(t.shape), dtype=torch.float64 if widen else t.dtype, pin_memory=True)
+    if not widen:
+        host.copy_(t, non_blocking=True)
+    else:
+        rows_per = max(1, chunk_bytes // (t.shape[1] * 8))
+        stage = [torch.empty((min(rows_per, t.shape[0]), t.shape[1]), dtype=torch.float64, device=t.device) for _ in range(2)]
+        lib = _lib.lib()
+        with torch.cuda.device(t.device):
+            for k, lo in enumerate(range(0, t.shape[0], rows_per)):
+                hi = min(t.shape[0], lo + rows_per)
+                st = stage[k % 2][:hi - lo]
+                _lib.check(lib.skb_widen_f32_f64(t[lo:hi].data_ptr(), st.data_ptr(), (hi - lo) * t.shape[1], _lib.stream_ptr()))
+                host[lo:hi].copy_(st, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
 
 
 def _read_columns(path, n_min):
@@ -225,7 +223,17 @@ class Ndx:
         out = Ndx()
         out.modelset = self.modelset[keepmod]
         out.segset = self.segset[keepseg]
-        out.trialmask = self.trialmask[keepmod, :][:, keepseg]
+        all_m, all_s = bool(keepmod.all()), bool(keepseg.all())
+        if all_m and all_s:
+            # nothing is dropped (the usual case): the (M, S) mask is SHARED, not copied twice through boolean indexing
+            # (2 x 400 MB at 20k x 20k); nothing in this package writes into a trialmask / scoremask in place
+            out.trialmask = self.trialmask
+        elif all_s:
+            out.trialmask = self.trialmask[keepmod]
+        elif all_m:
+            out.trialmask = self.trialmask[:, keepseg]
+        else:
+            out.trialmask = self.trialmask[numpy.ix_(numpy.flatnonzero(keepmod), numpy.flatnonzero(keepseg))]
         assert out.validate(), "Wrong Ndx format"
         return out
 
@@ -252,11 +260,12 @@ class Scores:
         self.scoremask = numpy.array([], dtype="bool")
         self._scoremat = numpy.array([])
         self.scoremat_device = None
+        self.scoremat_dtype = None          # numpy dtype of the materialised matrix when it differs from the device tensor's
 
     @property
     def scoremat(self):
         if self._scoremat is None:
-            self._scoremat = _device_to_numpy(self.scoremat_device)
+            self._scoremat = _device_to_numpy(self.scoremat_device, self.scoremat_dtype)
         return self._scoremat
 
     @scoremat.setter
@@ -354,6 +363,8 @@ class Scores:
                 it = torch.from_numpy(numpy.flatnonzero(key.tar & self.scoremask)).to(dev)
                 inn = torch.from_numpy(numpy.flatnonzero(key.non & self.scoremask)).to(dev)
                 both = flat[torch.cat([it, inn])].cpu().numpy()
+                if self.scoremat_dtype is not None:
+                    both = both.astype(self.scoremat_dtype)
                 return both[:it.numel()], both[it.numel():]
             return self.scoremat[key.tar & self.scoremask], self.scoremat[key.non & self.scoremask]
         new_score = self.align_with_ndx(key)

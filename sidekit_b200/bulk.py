@@ -1,9 +1,16 @@
 """Bulk extraction / scoring across GPUs: one process per GPU, utterances sharded by length
-bucket with greedy FLOP balancing, embeddings all-gathered with NCCL (the path's only collective); score
-matrices are sharded by row panel with no collective at all.  Host logic only -- the per-rank work goes through
-``Xtractor.extract_packed`` / ``score_matrix`` (CUDA).  Mirrors what the reference does one utterance at a time in
-``extract_embeddings`` (sidekit/nnet/xvector.py:1796-1916) and returns the same ``StatServer`` layout.
+bucket with greedy FLOP balancing, embeddings all-gathered with NCCL ONCE per shard (the path's only collective);
+score matrices are sharded by row panel against a test operand that is packed once.  Host logic only -- the
+per-rank work goes through ``Xtractor.extract_packed`` / ``extract_stream`` / ``score_matrix`` (CUDA).  Mirrors what
+the reference does one utterance at a time in ``extract_embeddings`` (sidekit/nnet/xvector.py:1796-1916) and returns
+the same ``StatServer`` layout.
+
+Nothing here needs the whole corpus in memory: a rank only ever touches the waveforms of the batch it is working on
+(``waves`` may be a callable ``i -> 1-D tensor`` or a ``load_batch`` function that returns a packed batch), so one
+million utterances (704 GB of fp32 audio, BASELINE config 4) are streamed.
 """
+import heapq
+
 import numpy
 import torch
 
@@ -11,7 +18,8 @@ from .statserver import StatServer
 
 
 def halfresnet34_macs(n_samples):
-    """Algorithmic MACs of one HalfResNet34 embedding (SURVEY.md 8d closed form); used as the balancing weight."""
+    """Algorithmic MACs of one HalfResNet34 embedding (SURVEY.md 8d closed form); used as the balancing weight.
+    Accepts a scalar or an integer array."""
     t1 = 1 + n_samples // 160
     t2 = (t1 - 1) // 2 + 1
     t3 = (t2 - 1) // 2 + 1
@@ -19,18 +27,36 @@ def halfresnet34_macs(n_samples):
     return 80 * t1 * 56608 + 40 * t2 * 278528 + 20 * t3 * 1703936 + 10 * t4 * 3276800 + 1310720 * t4 + 1350016
 
 
-def plan_shards(lengths, world_size, cost=halfresnet34_macs):
-    """Deterministic assignment of utterances to ranks: longest-first greedy on the MAC count.
-    Returns ``world_size`` index arrays, each sorted by length (so consecutive batches are length buckets)."""
+def _costs(lengths, cost):
     lengths = numpy.asarray(lengths, dtype=numpy.int64)
+    try:
+        c = numpy.asarray(cost(lengths), dtype=numpy.float64)
+        if c.shape == lengths.shape:
+            return c
+    except Exception:
+        pass
+    return numpy.array([float(cost(int(v))) for v in lengths], dtype=numpy.float64)
+
+
+def plan_shards(lengths, world_size, cost=halfresnet34_macs):
+    """Deterministic assignment of utterances to ranks: longest-first greedy on the MAC count (ties -> lowest rank).
+    Returns ``world_size`` index arrays, each sorted by length (so consecutive batches are length buckets).  A pure
+    function of ``(lengths, world_size)``: every rank computes the same plan, so no index exchange is ever needed."""
+    lengths = numpy.asarray(lengths, dtype=numpy.int64)
+    c = _costs(lengths, cost)
     order = numpy.argsort(-lengths, kind="stable")
-    load = numpy.zeros(world_size, dtype=numpy.float64)
-    shards = [[] for _ in range(world_size)]
-    for i in order:
-        r = int(numpy.argmin(load))            # ties -> lowest rank: deterministic
-        shards[r].append(int(i))
-        load[r] += float(cost(int(lengths[i])))
-    return [numpy.array(sorted(s, key=lambda i: (int(lengths[i]), i)), dtype=numpy.int64) for s in shards]
+    heap = [(0.0, r) for r in range(world_size)]
+    owner = numpy.empty(lengths.shape[0], dtype=numpy.int64)
+    for i in order.tolist():
+        load, r = heap[0]
+        owner[i] = r
+        heapq.heapreplace(heap, (load + c[i], r))
+    shards = []
+    idx = numpy.arange(lengths.shape[0], dtype=numpy.int64)
+    for r in range(world_size):
+        s = idx[owner == r]
+        shards.append(s[numpy.lexsort((s, lengths[s]))])
+    return shards
 
 
 def make_batches(indices, lengths, max_audio_seconds=1200.0, max_utts=256, sample_rate=16000):
@@ -48,6 +74,19 @@ def make_batches(indices, lengths, max_audio_seconds=1200.0, max_utts=256, sampl
     return batches
 
 
+def make_batches_equal_cost(indices, lengths, n_batches, cost=halfresnet34_macs):
+    """Split a length-sorted index list into exactly ``n_batches`` contiguous batches of (nearly) equal MAC count:
+    every batch is a length bucket and takes the same time on the GPU.  Empty batches only when there are fewer
+    utterances than batches."""
+    indices = numpy.asarray(indices, dtype=numpy.int64)
+    if indices.shape[0] == 0:
+        return [[] for _ in range(n_batches)]
+    c = numpy.cumsum(_costs(numpy.asarray(lengths, dtype=numpy.int64)[indices], cost))
+    cuts = numpy.searchsorted(c, c[-1] * numpy.arange(1, n_batches) / n_batches, side="left") + 1
+    cuts = numpy.minimum(numpy.maximum.accumulate(cuts), indices.shape[0])
+    return [[int(v) for v in part] for part in numpy.split(indices, cuts)]
+
+
 def _dist():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
@@ -55,47 +94,77 @@ def _dist():
     return None, 0, 1
 
 
-def extract_embeddings_sharded(extract_fn, waves, embedding_size, max_audio_seconds=1200.0, device=None):
-    """Embeddings of ``waves`` (list of 1-D tensors) on every rank, in input order.
+def _collective_device(device=None):
+    """Device the collectives of this process run on: the given one, else the current CUDA device under NCCL, else CPU."""
+    if device is not None:
+        return torch.device(device)
+    dist, _, _ = _dist()
+    if dist is not None and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return None
 
-    ``extract_fn(list_of_waves) -> (n, E) tensor`` is ``model.extract_varlen`` in production.  Each rank extracts
-    its shard in length-bucketed packed batches; one ``all_gather`` of the padded (n_max, E) blocks plus the index
-    vectors restores the global order.  With a single process this is just the batched local extraction.
-    """
+
+def gather_embeddings(local, shards, embedding_size, device=None):
+    """The one collective of the extraction path: every rank contributes the (n_r, E) embeddings of ITS shard (rows in
+    shard order) and receives all N embeddings in input order.  One ``all_gather_into_tensor`` of the padded blocks; the
+    shard plan is a pure function of the lengths, so the index vectors are known everywhere.  Single process: a scatter."""
     dist, rank, world = _dist()
-    lengths = numpy.array([int(w.shape[-1]) for w in waves], dtype=numpy.int64)
-    shards = plan_shards(lengths, world)
-    mine = shards[rank]
-    out_dev = device
-    batches = make_batches(mine, lengths, max_audio_seconds)
-    parts = [None] * len(batches)
-    for k in reversed(range(len(batches))):        # largest batch first: the engine sizes its work buffers once
-        e = extract_fn([waves[i] for i in batches[k]])
-        out_dev = e.device if out_dev is None else out_dev
-        parts[k] = e.to(torch.float32)
-    if out_dev is None:
-        out_dev = torch.device("cpu")
-    local = torch.cat(parts) if parts else torch.zeros((0, embedding_size), dtype=torch.float32, device=out_dev)
-    n = len(waves)
-    result = torch.empty((n, embedding_size), dtype=torch.float32, device=out_dev)
+    dev = _collective_device(device) or (local.device if local is not None and local.numel() else torch.device("cpu"))
+    n = int(sum(len(s) for s in shards))
+    if local is None:
+        local = torch.zeros((0, embedding_size), dtype=torch.float32, device=dev)
+    local = local.to(dev, torch.float32)
+    result = torch.empty((n, embedding_size), dtype=torch.float32, device=dev)
     if world == 1:
-        result[torch.as_tensor(mine, device=out_dev)] = local
+        result[torch.as_tensor(shards[0], device=dev)] = local
         return result
     n_max = max(len(s) for s in shards)
-    block = torch.zeros((n_max, embedding_size), dtype=torch.float32, device=out_dev)
+    block = torch.zeros((n_max, embedding_size), dtype=torch.float32, device=dev)
     block[: local.shape[0]] = local
-    gathered = torch.empty((world * n_max, embedding_size), dtype=torch.float32, device=out_dev)
+    gathered = torch.empty((world * n_max, embedding_size), dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(gathered, block)
-    for r, s in enumerate(shards):             # shards are a pure function of (lengths, world): no index exchange needed
-        result[torch.as_tensor(s, device=out_dev)] = gathered[r * n_max: r * n_max + len(s)]
+    for r, s in enumerate(shards):
+        if len(s):
+            result[torch.as_tensor(s, device=dev)] = gathered[r * n_max: r * n_max + len(s)]
     return result
 
 
-def extract_embeddings(ids, waves, model, max_audio_seconds=1200.0):
+def extract_embeddings_sharded(extract_fn, waves, embedding_size, max_audio_seconds=1200.0, device=None, lengths=None,
+                               max_utts=256, n_batches=None):
+    """Embeddings of all utterances on every rank, in input order.
+
+    ``waves`` is a list of 1-D tensors, or a callable ``i -> 1-D tensor`` together with ``lengths`` (so that a rank only
+    ever materialises the utterances of the batch it is working on).  ``extract_fn(list_of_waves) -> (n, E) tensor`` is
+    ``model.extract_varlen`` in production.  Each rank extracts its shard in length-bucketed packed batches, largest
+    first (the engine sizes its work buffers once); ONE ``all_gather`` at the end restores the global order.  With a
+    single process this is just the batched local extraction."""
+    dist, rank, world = _dist()
+    get = waves if callable(waves) else (lambda i: waves[i])
+    if lengths is None:
+        if callable(waves):
+            raise ValueError("a callable wave source needs `lengths`")
+        lengths = [int(w.shape[-1]) for w in waves]
+    lengths = numpy.asarray(lengths, dtype=numpy.int64)
+    shards = plan_shards(lengths, world)
+    mine = shards[rank]
+    if n_batches is not None:
+        batches = [b for b in make_batches_equal_cost(mine, lengths, n_batches) if b]
+    else:
+        batches = make_batches(mine, lengths, max_audio_seconds, max_utts)
+    parts = [None] * len(batches)
+    for k in reversed(range(len(batches))):
+        parts[k] = extract_fn([get(i) for i in batches[k]]).to(torch.float32)
+    dev = _collective_device(device) or (parts[0].device if parts else torch.device("cpu"))
+    local = torch.cat([p.to(dev) for p in parts]) if parts else None
+    return gather_embeddings(local, shards, embedding_size, dev)
+
+
+def extract_embeddings(ids, waves, model, max_audio_seconds=1200.0, lengths=None):
     """In-memory counterpart of the reference's ``extract_embeddings``: returns a ``StatServer`` whose ``stat1`` holds
     the embeddings and ``stat0`` ones (xvector.py:1905-1914)."""
-    emb = extract_embeddings_sharded(lambda ws: model.extract_varlen([w.to(next(model.parameters()).device) for w in ws]),
-                                     waves, model.embedding_size, max_audio_seconds)
+    dev = next(model.parameters()).device
+    emb = extract_embeddings_sharded(lambda ws: model.extract_varlen([w.to(dev) for w in ws]), waves, model.embedding_size,
+                                     max_audio_seconds, lengths=lengths)
     return StatServer.from_embeddings(numpy.asarray(ids), emb.cpu().numpy())
 
 
@@ -106,6 +175,21 @@ def row_panel(n_rows, rank=None, world=None):
     world = w if world is None else world
     per = (n_rows + world - 1) // world
     return min(rank * per, n_rows), min((rank + 1) * per, n_rows)
+
+
+def gather_rows(local_rows, n_rows, device=None):
+    """All-gather of a row-sharded (``row_panel`` split) matrix: every rank passes ITS rows and gets all ``n_rows``.
+    Used to replicate the test embeddings before tile-sharded scoring."""
+    dist, rank, world = _dist()
+    if world == 1:
+        return local_rows
+    per = (n_rows + world - 1) // world
+    dev = _collective_device(device) or local_rows.device
+    block = torch.zeros((per,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=dev)
+    block[: local_rows.shape[0]] = local_rows.to(dev)
+    out = torch.empty((world * per,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=dev)
+    dist.all_gather_into_tensor(out, block)
+    return out[:n_rows]
 
 
 def _asnorm_stats_cuda(X, cohort_normalised, topk):

@@ -12,6 +12,24 @@ namespace skb {
 
 constexpr int kNumSMs = 148;
 
+// Per-device one-time configuration (cudaFuncSetAttribute is per device / context) and per-device workspaces:
+// a process may use several GPUs one after the other (cosine_scoring(device=...), Xtractor.to("cuda:1")).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+    return d;
+}
+struct PerDeviceOnce {
+    bool done[kMaxDevices] = {};
+    bool first() {                       // true exactly once per device (a benign race repeats an idempotent call)
+        const int d = current_device();
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 #define SKB_CUDA_CHECK(expr)                                                                  \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \
@@ -216,15 +234,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // ----------------------------------------------------------------------------- 16-bit packing
+// fp16 range guard (SURVEY.md 7 "Precision"): the fp16 conversion SATURATES (F2FP.SATFINITE, same cost as the plain
+// convert) instead of producing +-inf, and the kernels that store activations keep a running max |x| of what they stored
+// (one HMNMX2 per two values); a thread that saw a saturated value bumps a device counter at its exit, which the host
+// surfaces as an error (skb_xtractor_overflow_count).  bf16 has the fp32 exponent range and needs neither.
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     if (kBf16) {
         __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
         return *reinterpret_cast<uint32_t*>(&t);
     } else {
-        __half2 t = __floats2half2_rn(lo, hi);
-        return *reinterpret_cast<uint32_t*>(&t);
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+        return r;
     }
+}
+__device__ __forceinline__ void track16(uint32_t packed, uint32_t& running_max) {      // fp16 pairs only
+    const __half2 m = __hmax2(__habs2(*reinterpret_cast<const __half2*>(&packed)), *reinterpret_cast<const __half2*>(&running_max));
+    running_max = *reinterpret_cast<const uint32_t*>(&m);
+}
+__device__ __forceinline__ void track16(const uint4& o, uint32_t& running_max) {
+    track16(o.x, running_max); track16(o.y, running_max); track16(o.z, running_max); track16(o.w, running_max);
+}
+__device__ __forceinline__ bool saturated16(uint32_t running_max) {                     // 0x7BFF = 65504, the largest finite fp16
+    return (running_max & 0x7fffu) >= 0x7bffu || ((running_max >> 16) & 0x7fffu) >= 0x7bffu;
 }
 template <bool kBf16>
 __device__ __forceinline__ float2 unpack2(uint32_t u) {

@@ -14,7 +14,7 @@ int conv_tile_m(int n_cta) { return n_cta == 32 ? 512 : 256; }
 template <int N_CTA, int MT, bool BF16, bool FUSED>
 static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     using Cfg = ConvCfg<N_CTA, MT>;
-    static bool configured = false;
+    static PerDeviceOnce configured;
     ConvParams p = p_in;
     const size_t a_stage = (size_t)p.rows_pad * (kConvKC / 8) * 16;
     // Weights: resident for the life of the CTA when one N split's images fit in <= 96 KB (no per-item weight
@@ -56,10 +56,9 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
     }
     p.a_stages = stages;
     const size_t smem = fixed + (size_t)stages * a_stage;
-    if (!configured) {
+    if (configured.first()) {
         SKB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<N_CTA, MT, BF16, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             227 * 1024));
-        configured = true;
     }
     const int n_pix = p.p_end - p.G;
     p.n_tiles = (n_pix + Cfg::kTileM - 1) / Cfg::kTileM;
@@ -74,7 +73,7 @@ static int launch_one(const ConvParams& p_in, cudaStream_t st) {
 template <int N_CTA, int MT, bool BF16>
 static int launch_one3(const ConvParams& p_in, cudaStream_t st) {
     using Cfg = Conv3Cfg<N_CTA, MT>;
-    static bool configured = false;
+    static PerDeviceOnce configured;
     ConvParams p = p_in;
     p.halo = p.Wp;                                          // one line above / below; the +-1 pixel shifts happen in the epilogue
     p.rows_pad = (Cfg::kTileM + 2 * p.Wp + 7) / 8 * 8;
@@ -91,9 +90,8 @@ static int launch_one3(const ConvParams& p_in, cudaStream_t st) {
     if (stages > kConvMaxAStages) stages = kConvMaxAStages;
     p.a_stages = stages;
     const size_t smem = fixed + (size_t)stages * a_stage;
-    if (!configured) {
+    if (configured.first()) {
         SKB_CUDA_CHECK(cudaFuncSetAttribute(conv3_umma_kernel<N_CTA, MT, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
     }
     const int n_pix = p.p_end - p.G;
     p.n_tiles = (n_pix + Cfg::kTileOut - 1) / Cfg::kTileOut;

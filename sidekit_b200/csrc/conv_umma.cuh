@@ -69,6 +69,7 @@ struct ConvParams {
     // one more pass over the tensor), accumulated by the epilogue: [n_utt][cout] or nullptr.  Only the N_CTA == 32 kernels
     // with cout == 32 support it (32 per-thread 64-bit accumulators, flushed with atomics when the utterance changes).
     unsigned long long* sums;
+    unsigned* overflow;     // fp16 range guard: number of threads that stored a saturated (|x| >= 65504) value, or nullptr
 };
 
 constexpr int kConvKC = 32;            // input channels per A/B stage (two K=16 MMAs)
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                 }
             }
         };
+        uint32_t omax = 0u;                     // fp16 range guard: max |x| of what this thread stored
         int bidx_c[MTH], opix_c[MTH], bidx_n[MTH], opix_n[MTH], bidx_nn[MTH], opix_nn[MTH];
         uint4 rv_c[MTH][NCH], rv_n[MTH][NCH];
         fetch_meta(item_begin, bidx_c, opix_c);
@@ -423,6 +425,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                             o.z = valid ? pack2<BF16>(v[j * 8 + 4], v[j * 8 + 5]) : 0u;
                             o.w = valid ? pack2<BF16>(v[j * 8 + 6], v[j * 8 + 7]) : 0u;
                             *reinterpret_cast<uint4*>(dst + j * plane8) = o;
+                            if (!BF16) track16(o, omax);
                             if constexpr (kCanSum) {
                                 if (do_sums && valid) {
                                     // exactly plane_sum_kernel's arithmetic on the value just stored
@@ -449,6 +452,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             }
         }
         if (kCanSum && do_sums) flush_sums();
+        if (!BF16 && p.overflow != nullptr && saturated16(omax)) atomicAdd(p.overflow, 1u);
         } else {
         // ---------------------------------------------------------------- epilogue warps (4..11)
         // two warps per TMEM lane quadrant; each takes half of the item's MT accumulator tiles
@@ -456,6 +460,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
         const int mt0 = ((warp - 4) >> 2) * MTH;
         uint32_t n_done = 0;
+        uint32_t omax = 0u;                     // fp16 range guard: max |x| of what this thread stored
         int tile_next = item_begin / n_split, ns_next = item_begin % n_split;
         for (int item = item_begin; item < item_end; ++item, ++n_done) {
             const int tile = tile_next, ns = ns_next;
@@ -551,12 +556,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                                 o.z = valid ? pack2<BF16>(v[j * 8 + 4], v[j * 8 + 5]) : 0u;
                                 o.w = valid ? pack2<BF16>(v[j * 8 + 6], v[j * 8 + 7]) : 0u;
                                 *reinterpret_cast<uint4*>(dst + j * plane8) = o;
+                                if (!BF16) track16(o, omax);
                             }
                         }
                     }
                 }
             }
         }
+        if (!BF16 && p.overflow != nullptr && saturated16(omax)) atomicAdd(p.overflow, 1u);
         }
         tc_fence_before();
     }

@@ -318,7 +318,8 @@ struct Model {
     float *att_w2 = nullptr, *att_b2 = nullptr;
     int att_A = 0, pool_D = 0;
     // head
-    float *lin_w = nullptr, *lin_b = nullptr, *be_s = nullptr, *be_t = nullptr, *spk_wn = nullptr;
+    float *lin_w = nullptr, *lin_b = nullptr, *be_s = nullptr, *be_t = nullptr, *spk_wn = nullptr, *spk_b = nullptr;
+    bool head_linear = false;   // loss='aps': logits = Linear(x) on the pre-normalisation embedding instead of s * cos(x, W)
     PackedOp p_w1x, p_w2;       // attention projections packed for the split-precision tcgen05 GEMM (M = frames)
     // tdnn
     std::vector<ConvW> tdnn;
@@ -340,6 +341,15 @@ static int upload_raw(const HostTensor* t, float** out) {
 }
 
 static int build_frontend(const WeightMap& w, Model* m) {
+    // PreEmphasis.flipped_filter = [-coef, 1] (augmentation.py:59-62): a checkpoint trained with another coefficient is honoured
+    auto pf = w.find("preprocessor.PreEmphasis.flipped_filter");
+    if (pf != w.end() && pf->second.numel() == 2) {
+        if (pf->second.p[1] != 1.f) {
+            set_last_error(__FILE__, __LINE__, "unexpected PreEmphasis.flipped_filter (want [-coef, 1])");
+            return SKB_ERR_WEIGHTS;
+        }
+        m->fe.preemph = -pf->second.p[0];
+    }
     if (m->archi != SKB_ARCHI_XVECTOR) {
         const HostTensor *win = find(w, "preprocessor.MelSpec.spectrogram.window"), *fb = find(w, "preprocessor.MelSpec.mel_scale.fb");
         if (!win || !fb) return SKB_ERR_WEIGHTS;
@@ -360,7 +370,19 @@ static int build_frontend(const WeightMap& w, Model* m) {
 }
 
 static int build_margin_head(const WeightMap& w, Model* m) {
-    if (!w.count("after_speaker_embedding.weight")) {   // loss='cce': no margin head at inference time
+    if (w.count("after_speaker_embedding.cce_backend.linear8.weight")) {
+        // loss='aps' (SoftmaxAngularProto.forward(x, target=None), sidekit/nnet/loss.py:347-359): a plain Linear on the
+        // (l2-normalised) embedding
+        const HostTensor *lw = find(w, "after_speaker_embedding.cce_backend.linear8.weight"),
+                         *lb = find(w, "after_speaker_embedding.cce_backend.linear8.bias");
+        if (!lw || !lb || lw->shape.size() != 2 || lw->shape[1] != m->emb || lb->numel() != lw->shape[0]) return SKB_ERR_WEIGHTS;
+        m->n_spk = (int)lw->shape[0];
+        m->head_linear = true;
+        int rc = upload_raw(lw, &m->spk_wn);
+        if (rc) return rc;
+        return upload_raw(lb, &m->spk_b);
+    }
+    if (!w.count("after_speaker_embedding.weight")) {   // loss='cce' / None: no head at inference time
         m->n_spk = 0;
         return SKB_OK;
     }
@@ -597,7 +619,7 @@ static void free_model(Model* m) {
     for (auto& c : m->tdnn) free_conv(&c);
     cudaFree(m->att_w1x); cudaFree(m->att_w1g); cudaFree(m->att_b1); cudaFree(m->att_bn_s); cudaFree(m->att_bn_t);
     cudaFree(m->att_w2); cudaFree(m->att_b2); cudaFree(m->lin_w); cudaFree(m->lin_b); cudaFree(m->be_s); cudaFree(m->be_t);
-    cudaFree(m->spk_wn); cudaFree(m->pool_s); cudaFree(m->pool_t);
+    cudaFree(m->spk_wn); cudaFree(m->spk_b); cudaFree(m->pool_s); cudaFree(m->pool_t);
     packed_free(&m->p_w1x); packed_free(&m->p_w2);
 }
 
@@ -685,6 +707,8 @@ struct skb_xtractor {
     cudaStream_t last_stream = nullptr;
     bool have_last_stream = false;
     DevBuf brd, cmvn, cmvn_part, skinny_ws;
+    DevBuf ovf;                   // fp16 range guard: cumulative count of threads that stored a saturated activation (common.cuh)
+    int device = 0;               // the CUDA device the weights and work buffers live on
     DevBuf feats, sums, scale, poolX, poolH, poolL, gc, hb, pooled, lin, emb_pre, emb, logits, wave, dbg;
     std::vector<DevBuf> act;      // activation buffers
     std::vector<size_t> act_bytes;
@@ -1036,6 +1060,7 @@ static int run_conv(skb_xtractor* h, const ConvW& cw, int kind, const Level& Lg,
     p.res = res;
     p.res_plane = Lg.plane;
     p.sums = (sums != nullptr && cw.ncta == 32 && cw.cout == 32 && se_scale == nullptr) ? sums : nullptr;
+    p.overflow = (unsigned*)h->ovf.p;
     g_launches++;
     return launch_conv_umma(p, cw.ncta, h->m.bf16, st);
 }
@@ -1100,8 +1125,9 @@ static int head_and_logits(skb_xtractor* h, int norm_embedding, float* emb_out, 
                                (float*)h->skinny_ws.p, st));
     SKB_TRY(launch_head_norm((const float*)h->lin.p, m.be_s, m.be_t, B, m.emb, norm_embedding, (float*)h->emb_pre.p, emb_out, st));
     g_launches += 2;
-    if (logits_out && m.n_spk > 0) {   // ArcMarginProduct(target=None): s * cos (loss.py:299-310)
-        SKB_TRY(launch_skinny_gemm(emb_out, B, m.emb, m.spk_wn, m.n_spk, nullptr, m.margin_s, logits_out, m.n_spk,
+    if (logits_out && m.n_spk > 0) {   // ArcMarginProduct(target=None): s * cos (loss.py:299-310); 'aps': Linear(x) (loss.py:356-359)
+        SKB_TRY(launch_skinny_gemm(m.head_linear ? (const float*)h->emb_pre.p : emb_out, B, m.emb, m.spk_wn, m.n_spk,
+                                   m.head_linear ? m.spk_b : nullptr, m.head_linear ? 1.f : m.margin_s, logits_out, m.n_spk,
                                    (float*)h->skinny_ws.p, st));
         g_launches++;
     }
@@ -1139,10 +1165,10 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
         ProfScope ps(PROF_STEM, st);
         if (m.archi == SKB_ARCHI_FASTRESNET34)
             SKB_TRY(launch_stem7(m.bf16, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, (const float2*)h->cmvn.p, m.stem, buf(0, 0),
-                                 L1.plane, L1.G, L1.p_end, L1.Wp, L1.W, m.fe.n_out, d32 + L1.o_row_b, d32 + L1.o_row_h, st));
+                                 L1.plane, L1.G, L1.p_end, L1.Wp, L1.W, m.fe.n_out, d32 + L1.o_row_b, d32 + L1.o_row_h, (unsigned*)h->ovf.p, st));
         else
             SKB_TRY(launch_stem(m.bf16, m.stem_c, feats, d64 + pl.o_feat_off, d32 + pl.o_nframes, (const float2*)h->cmvn.p, m.stem, buf(0, 0),
-                                L1.plane, L1.G, L1.p_end, L1.Wp, L1.W, d32 + L1.o_row_b, d32 + L1.o_row_h, st));
+                                L1.plane, L1.G, L1.p_end, L1.Wp, L1.W, d32 + L1.o_row_b, d32 + L1.o_row_h, (unsigned*)h->ovf.p, st));
     }
     g_launches++;
     int level = 0, cur = 0;   // current activation = buf(level, cur), cur in {0, 1}
@@ -1302,6 +1328,10 @@ static int forward_any(skb_xtractor* h, const float* wave, const int64_t* length
         set_last_error(__FILE__, __LINE__, "bad arguments");
         return SKB_ERR_ARG;
     }
+    if (current_device() != h->device) {
+        set_last_error(__FILE__, __LINE__, "this extractor handle lives on another CUDA device than the current one");
+        return SKB_ERR_STATE;
+    }
     SKB_TRY(build_plan(h, lengths, B, st));
     if (is_resnet(h->m.archi)) return forward_hr34(h, wave, norm_embedding, emb, logits, stop, h_max, dbg, per_utt, st);
     return forward_tdnn(h, wave, norm_embedding, emb, logits, stop, h_max, dbg, per_utt, st);
@@ -1356,6 +1386,12 @@ int skb_xtractor_create(int archi, int n_tensors, const char* const* names, cons
         w[names[i]] = t;
     }
     skb_xtractor* h = new skb_xtractor();
+    h->device = current_device();
+    if (h->ovf.ensure(sizeof(unsigned)) != SKB_OK || cudaMemset(h->ovf.p, 0, sizeof(unsigned)) != cudaSuccess) {
+        delete h;
+        set_last_error(__FILE__, __LINE__, "cannot allocate the overflow counter");
+        return SKB_ERR_CUDA;
+    }
     h->m.archi = archi;
     h->m.bf16 = compute_dtype == 1;
     h->m.margin_s = margin_s;
@@ -1375,7 +1411,7 @@ void skb_xtractor_destroy(skb_xtractor_t* h) {
     h->slot.release();
     DevBuf* bufs[] = {&h->feats, &h->sums, &h->scale, &h->poolX, &h->poolH, &h->poolL, &h->gc, &h->hb,
                       &h->pooled, &h->lin, &h->emb_pre, &h->emb, &h->logits, &h->wave, &h->dbg, &h->brd, &h->cmvn,
-                      &h->cmvn_part, &h->skinny_ws};
+                      &h->cmvn_part, &h->skinny_ws, &h->ovf};
     for (auto* b : bufs) b->release();
     for (auto& b : h->act) b.release();
     for (auto& c : h->cache) c.slot.release();
@@ -1419,6 +1455,18 @@ int skb_xtractor_forward_host(skb_xtractor_t* h, const float* wave_host, const i
     return SKB_OK;
 }
 
+int skb_xtractor_overflow_count(skb_xtractor_t* h, void* stream, int64_t* count) {
+    if (!h || !count) {
+        set_last_error(__FILE__, __LINE__, "bad arguments");
+        return SKB_ERR_ARG;
+    }
+    unsigned v = 0;
+    SKB_CUDA_CHECK(cudaMemcpyAsync(&v, h->ovf.p, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    SKB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    *count = (int64_t)v;
+    return SKB_OK;
+}
+
 int skb_xtractor_pre_embedding(skb_xtractor_t* h, int n_utt, float* out_dev, void* stream) {
     if (!h || !out_dev || !h->plan_valid || n_utt != h->plan.B) {
         set_last_error(__FILE__, __LINE__, "pre_embedding: no matching forward call");
@@ -1436,6 +1484,10 @@ int skb_xtractor_frontend(skb_xtractor_t* h, const float* wave_dev, const int64_
         return SKB_ERR_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (current_device() != h->device) {
+        set_last_error(__FILE__, __LINE__, "this extractor handle lives on another CUDA device than the current one");
+        return SKB_ERR_STATE;
+    }
     SKB_TRY(build_plan(h, lengths, n_utt, st));
     Plan& pl = h->plan;
     if (t_max < pl.t_max) {

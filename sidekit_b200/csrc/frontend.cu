@@ -431,7 +431,7 @@ int frontend_launch(const FrontendConsts& fc, const float* wave, const long long
     p.wave = wave; p.wave_off = wave_off; p.wave_len = wave_len; p.feat_off = feat_off; p.n_frames = n_frames;
     p.out = feats; p.window = fc.window; p.tw_half = fc.tw_half; p.tw_full = fc.tw_full;
     p.mel_lo = fc.mel_lo; p.mel_cnt = fc.mel_cnt; p.mel_ofs = fc.mel_ofs; p.mel_w = fc.mel_w; p.dct = fc.dct;
-    p.n_mels = fc.n_mels; p.n_out = fc.n_out; p.hop = fc.hop; p.win = fc.win; p.preemph = 0.97f;
+    p.n_mels = fc.n_mels; p.n_out = fc.n_out; p.hop = fc.hop; p.win = fc.win; p.preemph = fc.preemph;
     if (fc.n_out > 128) {
         set_last_error(__FILE__, __LINE__, "front-end: more than 128 output coefficients");
         return SKB_ERR_ARG;
@@ -455,10 +455,9 @@ int frontend_launch(const FrontendConsts& fc, const float* wave, const long long
         const int frames_per_cta = fpw_override(8) * WPC;
         dim3 grid((t_max + frames_per_cta - 1) / frames_per_cta, B);
         const size_t smem = smem_bytes(NC, WPC, &p.dct_smem_off);
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce configured;
+        if (configured.first()) {
             SKB_CUDA_CHECK(cudaFuncSetAttribute(frontend_kernel<NC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            configured = true;
         }
         if (smem > 227 * 1024) {
             set_last_error(__FILE__, __LINE__, "front-end: tables do not fit in shared memory");
@@ -471,10 +470,9 @@ int frontend_launch(const FrontendConsts& fc, const float* wave, const long long
         const int frames_per_cta = fpw_override(8) * WPC;
         dim3 grid((t_max + frames_per_cta - 1) / frames_per_cta, B);
         const size_t smem = smem_bytes(NC, WPC, &p.dct_smem_off);
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce configured;
+        if (configured.first()) {
             SKB_CUDA_CHECK(cudaFuncSetAttribute(frontend_kernel<NC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            configured = true;
         }
         if (smem > 227 * 1024) {
             set_last_error(__FILE__, __LINE__, "front-end: tables do not fit in shared memory");

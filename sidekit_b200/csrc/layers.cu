@@ -17,7 +17,9 @@ __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemC
                                                    const long long* __restrict__ feat_off, const int* __restrict__ n_frames,
                                                    const float2* __restrict__ cmvn /*[B][W] (mean, rstd)*/,
                                                    uint16_t* __restrict__ out, long long out_plane, int G, int p_end, int Wp,
-                                                   int W, const int* __restrict__ row_b, const int* __restrict__ row_h) {
+                                                   int W, const int* __restrict__ row_b, const int* __restrict__ row_h,
+                                                   unsigned* __restrict__ overflow) {
+    uint32_t omax = 0u;                    // fp16 range guard (common.cuh)
     // The folded weights arrive as a kernel parameter: every FFMA takes its weight straight from the constant bank
     // (a shared-memory copy costs one LDS per FMA and made the kernel LSU-bound at 3x its HBM time).  Each thread computes
     // kStemPix pixels (blockDim apart, so loads and stores stay coalesced): a weight fetched into a uniform register feeds
@@ -80,17 +82,19 @@ __global__ void __launch_bounds__(128) stem_kernel(const __grid_constant__ StemC
             o.z = pack2<BF16>(acc[q][4], acc[q][5]);
             o.w = pack2<BF16>(acc[q][6], acc[q][7]);
             *reinterpret_cast<uint4*>(out + ((size_t)g * out_plane + pix) * 8) = o;
+            if (!BF16) track16(o, omax);
         }
     }
+    if (!BF16 && overflow != nullptr && saturated16(omax)) atomicAdd(overflow, 1u);
 }
 
 int launch_stem(bool bf16, int cout, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
                 const StemConsts& sc, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
-                const int* row_b, const int* row_h, cudaStream_t st) {
+                const int* row_b, const int* row_h, unsigned* overflow, cudaStream_t st) {
     const int n = p_end - G;
     const int threads = 128;
     const int blocks = (n + threads * kStemPix - 1) / (threads * kStemPix);
-#define SKB_STEM(BF, C) stem_kernel<BF, C><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, row_b, row_h)
+#define SKB_STEM(BF, C) stem_kernel<BF, C><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, row_b, row_h, overflow)
     if (cout == 32) { if (bf16) SKB_STEM(true, 32); else SKB_STEM(false, 32); }
     else if (cout == 128) { if (bf16) SKB_STEM(true, 128); else SKB_STEM(false, 128); }
     else {
@@ -111,7 +115,8 @@ __global__ void __launch_bounds__(128) stem7_kernel(const __grid_constant__ Stem
                                                     const long long* __restrict__ feat_off, const int* __restrict__ n_frames,
                                                     const float2* __restrict__ cmvn /*[B][F] (mean, rstd)*/,
                                                     uint16_t* __restrict__ out, long long out_plane, int G, int p_end, int Wp,
-                                                    int W, int F, const int* __restrict__ row_b, const int* __restrict__ row_h) {
+                                                    int W, int F, const int* __restrict__ row_b, const int* __restrict__ row_h,
+                                                    unsigned* __restrict__ overflow) {
     const int pix = G + blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= p_end) return;
     const int rel = pix - G;
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(128) stem7_kernel(const __grid_constant__ Stem
     }
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[c] = valid ? fmaxf(acc[c], 0.f) : 0.f;
+    uint32_t omax = 0u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
@@ -149,21 +155,23 @@ __global__ void __launch_bounds__(128) stem7_kernel(const __grid_constant__ Stem
             o.y = pack2<BF16>(acc[j * 8 + 2], acc[j * 8 + 3]);
             o.z = pack2<BF16>(acc[j * 8 + 4], acc[j * 8 + 5]);
             o.w = pack2<BF16>(acc[j * 8 + 6], acc[j * 8 + 7]);
+            if (!BF16) track16(o, omax);
         }
         *reinterpret_cast<uint4*>(out + ((size_t)j * out_plane + pix) * 8) = o;
     }
+    if (!BF16 && overflow != nullptr && saturated16(omax)) atomicAdd(overflow, 1u);
 }
 
 int launch_stem7(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
                  const StemConsts& sc, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W, int F,
-                 const int* row_b, const int* row_h, cudaStream_t st) {
+                 const int* row_b, const int* row_h, unsigned* overflow, cudaStream_t st) {
     const int n = p_end - G;
     const int threads = 128;
     const int blocks = (n + threads - 1) / threads;
     if (bf16)
-        stem7_kernel<true><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, F, row_b, row_h);
+        stem7_kernel<true><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, F, row_b, row_h, overflow);
     else
-        stem7_kernel<false><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, F, row_b, row_h);
+        stem7_kernel<false><<<blocks, threads, 0, st>>>(sc, feats, feat_off, n_frames, cmvn, out, out_plane, G, p_end, Wp, W, F, row_b, row_h, overflow);
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }

@@ -9,6 +9,7 @@ struct ConvParams;
 
 struct FrontendConsts {
     int n_fft = 0, win = 0, hop = 0, n_mels = 0, n_out = 0, n_w = 0;
+    float preemph = 0.97f;         // PreEmphasis coefficient (sidekit/nnet/augmentation.py:59-74), read from the checkpoint's flipped_filter
     float* window = nullptr;
     float2* tw_half = nullptr;
     float2* tw_full = nullptr;
@@ -20,10 +21,10 @@ struct FrontendConsts {
 struct StemConsts { float w[128 * 9]; float b[128]; };   // folded stem conv + BN (<= 128 channels), passed to the kernel by value
 int launch_stem(bool bf16, int cout, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
                 const StemConsts& sc, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W,
-                const int* row_b, const int* row_h, cudaStream_t st);
+                const int* row_b, const int* row_h, unsigned* overflow, cudaStream_t st);
 int launch_stem7(bool bf16, const float* feats, const long long* feat_off, const int* n_frames, const float2* cmvn,
                  const StemConsts& sc, uint16_t* out, long long out_plane, int G, int p_end, int Wp, int W, int F,
-                 const int* row_b, const int* row_h, cudaStream_t st);
+                 const int* row_b, const int* row_h, unsigned* overflow, cudaStream_t st);
 int launch_broadcast_rows(const float* bias, int B, int A, float* out, cudaStream_t st);
 int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, const int* span_b, int C,
                      unsigned long long* sums, cudaStream_t st);

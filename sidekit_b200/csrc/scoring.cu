@@ -463,7 +463,9 @@ struct ScoreWorkspace {
     float* tmp = nullptr;        // scratch score matrix (as-norm cohort scores)
     size_t tmp_cap = 0;
 };
-static thread_local ScoreWorkspace g_ws;
+// one workspace per (host thread, device): the buffers are cudaMalloc'd on the device that is current at first use
+static thread_local ScoreWorkspace g_ws_dev[kMaxDevices];
+#define g_ws (g_ws_dev[current_device()])
 
 static int ws_ensure(size_t plane_bytes, size_t tmp_bytes) {
     if (!g_ws.stats) SKB_CUDA_CHECK(cudaMalloc(&g_ws.stats, 8 * sizeof(unsigned)));
@@ -495,15 +497,14 @@ static void ws_operand(PackedOp* op, int rows, int D, int slot, size_t offset_ha
 
 template <int PASSES, bool STREAM_A>
 static int launch_score(const ScoreParams& p, int grid, cudaStream_t st) {
-    static bool configured = false;
+    static PerDeviceOnce configured;
     const size_t smem = ScoreSmem<PASSES, STREAM_A>::total(p.Dp);
     if (smem > 227 * 1024) {
         set_last_error(__FILE__, __LINE__, "score_gemm: operand panel does not fit in shared memory");
         return SKB_ERR_ARG;
     }
-    if (!configured) {
+    if (configured.first()) {
         SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<PASSES, STREAM_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
     }
     SKB_CUDA_CHECK(launch_pdl(score_gemm_kernel<PASSES, STREAM_A>, dim3(grid), dim3(kScThreads), smem, st, p));
     g_launches++;
@@ -693,6 +694,18 @@ __global__ void half_rowdot_kernel(const float* __restrict__ A, const float* __r
     if (lane == 0) out[row] = 0.5f * s;
 }
 
+// float32 -> float64 on the way to the host (the reference's PLDA scorers return float64; the GEMM keeps float32)
+__global__ void widen_kernel(const float* __restrict__ src, double* __restrict__ dst, long long n) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 4 <= n && (reinterpret_cast<uintptr_t>(src + i) & 15) == 0) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(src + i));
+        __stcs(reinterpret_cast<double2*>(dst + i), make_double2((double)v.x, (double)v.y));
+        __stcs(reinterpret_cast<double2*>(dst + i) + 1, make_double2((double)v.z, (double)v.w));
+    } else {
+        for (long long k = i; k < n && k < i + 4; ++k) dst[k] = (double)src[k];
+    }
+}
+
 }  // namespace skb
 
 using namespace skb;
@@ -737,6 +750,66 @@ int skb_score_gemm(const float* E_dev, const float* T_dev, int Ne, int Nt, int D
                               (cudaStream_t)stream);
 }
 
+// ---- a test-side operand packed ONCE and scored against many enrol panels (multi-GPU row panels, repeated calls)
+struct skb_packed { skb::PackedOp op; int device; };
+
+int skb_packed_create(const float* X_dev, int rows, int D, skb_packed_t** out, void* stream) {
+    if (!X_dev || !out || rows <= 0 || D <= 0) {
+        set_last_error(__FILE__, __LINE__, "packed_create: bad arguments");
+        return SKB_ERR_ARG;
+    }
+    skb_packed* p = new skb_packed();
+    p->device = current_device();
+    int rc = packed_create(X_dev, rows, D, &p->op, (cudaStream_t)stream);
+    if (rc) {
+        packed_free(&p->op);
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return SKB_OK;
+}
+
+void skb_packed_destroy(skb_packed_t* p) {
+    if (!p) return;
+    packed_free(&p->op);
+    delete p;
+}
+
+int skb_score_gemm_packed(const float* E_dev, int Ne, const skb_packed_t* T, const float* rowterm_dev, const float* colterm_dev,
+                          double cst, double alpha, int passes, int out_dtype, void* out_dev, int64_t ld_out, void* stream) {
+    if (!E_dev || !T || !out_dev || Ne <= 0 || ld_out < T->op.rows) {
+        set_last_error(__FILE__, __LINE__, "score_gemm_packed: bad arguments");
+        return SKB_ERR_ARG;
+    }
+    if (T->device != current_device()) {
+        set_last_error(__FILE__, __LINE__, "score_gemm_packed: the packed operand lives on another CUDA device");
+        return SKB_ERR_STATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = T->op.D, Dp = T->op.Dp;
+    const size_t eh = (size_t)Dp * ((Ne + 127) / 128 * 128);
+    int rc = ws_ensure(2 * eh * sizeof(uint16_t), 0);
+    if (rc) return rc;
+    PackedOp e;
+    ws_operand(&e, Ne, D, 0, 0);
+    if ((rc = packed_fill(E_dev, &e, nullptr, nullptr, st))) return rc;
+    return gemm_packed(e, T->op, nullptr, nullptr, (float)alpha, rowterm_dev, colterm_dev, (float)(alpha * cst), (float)alpha,
+                       (float)fabs(alpha), passes, out_dtype, out_dev, ld_out, st);
+}
+
+int skb_widen_f32_f64(const float* src_dev, double* dst_dev, int64_t n, void* stream) {
+    if (!src_dev || !dst_dev || n < 0) {
+        set_last_error(__FILE__, __LINE__, "widen: bad arguments");
+        return SKB_ERR_ARG;
+    }
+    if (n == 0) return SKB_OK;
+    widen_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, (cudaStream_t)stream>>>(src_dev, dst_dev, (long long)n);
+    g_launches++;
+    SKB_CUDA_CHECK(cudaGetLastError());
+    return SKB_OK;
+}
+
 int skb_asnorm_stats(const float* X_dev, const float* cohort_dev, int N, int C, int D, int top_k, float* mean_dev,
                      float* std_dev, void* stream) {
     if (top_k < 2 || C < top_k || C * sizeof(unsigned) > 200 * 1024) {
@@ -751,10 +824,9 @@ int skb_asnorm_stats(const float* X_dev, const float* cohort_dev, int N, int C, 
     rc = score_gemm_general(X_dev, cohort_dev, N, C, D, nullptr, nullptr, 1.f, nullptr, nullptr, 0.f, 1.f, 1.f, 3, 0, g_ws.tmp, ld,
                             tmp_bytes, st);
     if (rc) return rc;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         SKB_CUDA_CHECK(cudaFuncSetAttribute(topk_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
     }
     topk_stats_kernel<<<N, 256, C * sizeof(unsigned), st>>>(g_ws.tmp, C, ld, top_k, mean_dev, std_dev);
     g_launches++;

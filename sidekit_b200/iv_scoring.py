@@ -8,6 +8,7 @@ side (CUDA, csrc/scoring.cu): centring, the Psi / Phi folds, the quadratic row /
 Ne x Nt score matrix.  The result stays on the device until ``Scores.scoremat`` is read.
 """
 import copy
+import ctypes
 import logging
 
 import numpy
@@ -42,15 +43,44 @@ def _dev32(a, device):
 def score_matrix(E, T, rowterm=None, colterm=None, cst=0.0, alpha=1.0, passes=0, out_dtype=torch.float32, out=None):
     """S = alpha*(rowterm_i + colterm_j + cst) + alpha * E T^T on the device (all arguments torch CUDA fp32)."""
     Ne, D = E.shape
-    Nt = T.shape[0]
+    Nt = T.rows if isinstance(T, PackedEmbeddings) else T.shape[0]
     if out is None:
         out = torch.empty((Ne, Nt), dtype=out_dtype, device=E.device)
+    if isinstance(T, PackedEmbeddings):
+        with torch.cuda.device(E.device):
+            _lib.check(_lib.lib().skb_score_gemm_packed(
+                E.data_ptr(), Ne, T._ptr, None if rowterm is None else rowterm.data_ptr(),
+                None if colterm is None else colterm.data_ptr(), float(cst), float(alpha), int(passes),
+                1 if out.dtype == torch.float64 else 0, out.data_ptr(), out.stride(0), _lib.stream_ptr()))
+        return out
     with torch.cuda.device(E.device):
         _lib.check(_lib.lib().skb_score_gemm(
             E.data_ptr(), T.data_ptr(), Ne, Nt, D, None if rowterm is None else rowterm.data_ptr(),
             None if colterm is None else colterm.data_ptr(), float(cst), float(alpha), int(passes),
             1 if out.dtype == torch.float64 else 0, out.data_ptr(), out.stride(0), _lib.stream_ptr()))
     return out
+
+
+class PackedEmbeddings:
+    """A test-side operand prepared once for ``score_matrix`` (``skb_packed_create``): scaled, split into fp16 hi / lo
+    planes and tiled for the tcgen05 GEMM.  Scoring many enrol panels against it (row-panel sharding over GPUs, repeated
+    calls) then pays only for the enrol side."""
+
+    def __init__(self, T):
+        T = T.to(torch.float32).contiguous()
+        self.rows, self.D, self.device = int(T.shape[0]), int(T.shape[1]), T.device
+        self._ptr = ctypes.c_void_p()
+        with torch.cuda.device(T.device):
+            _lib.check(_lib.lib().skb_packed_create(T.data_ptr(), self.rows, self.D, ctypes.byref(self._ptr), _lib.stream_ptr()))
+            torch.cuda.current_stream().synchronize()          # T may be freed by the caller after this returns
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                _lib.lib().skb_packed_destroy(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
 
 
 def _quadratic_prepare(X, mu, Psi, Phi):
@@ -68,12 +98,17 @@ def _quadratic_prepare(X, mu, Psi, Phi):
     return Xout, rowterm
 
 
-def _finish(clean_ndx, mat_dev):
+def _finish(clean_ndx, mat_dev, np_dtype=None):
+    """``Scores`` whose matrix stays on the device until ``scoremat`` is read.  ``np_dtype=float64``: the reference's PLDA /
+    two-covariance / Mahalanobis scorers return float64; the GEMM writes float32 (its accuracy class: fp32 accumulation
+    of split fp16 products, <= 1e-3 absolute against the reference as north_star asks, typically 4e-5) and the widening
+    happens on the way to the host, so the HBM-bound kernel does not write 8 bytes per trial."""
     score = Scores()
     score.modelset = clean_ndx.modelset
     score.segset = clean_ndx.segset
     score.scoremask = clean_ndx.trialmask
     score.scoremat_device = mat_dev
+    score.scoremat_dtype = np_dtype
     score.scoremat = None           # materialised lazily from the device tensor
     return score
 
@@ -99,7 +134,8 @@ def cosine_scoring(enroll, test, ndx, wccn=None, check_missing=True, device=None
 
 def fast_PLDA_scoring(enroll, test, ndx, mu, F, Sigma, test_uncertainty=None, Vtrans=None, p_known=0.0,
                       scaling_factor=1., check_missing=True):
-    """Simplified PLDA log-likelihood ratios (iv_scoring.py:370-477); ``scoremat`` is float64 like the reference."""
+    """Simplified PLDA log-likelihood ratios (iv_scoring.py:370-477); ``scoremat`` is float64 like the reference
+    (fp32-class precision, see ``_finish``)."""
     enroll_ctr = copy.deepcopy(enroll)
     test_ctr = copy.deepcopy(test)
     if not numpy.unique(enroll_ctr.modelset).shape == enroll_ctr.modelset.shape:
@@ -131,10 +167,10 @@ def fast_PLDA_scoring(enroll, test, ndx, mu, F, Sigma, test_uncertainty=None, Vt
     E, T = _dev32(enroll_ctr.stat1, dev), _dev32(test_ctr.stat1, dev)
     Ep, model_part = _quadratic_prepare(E, mu, Psi, Phi)           # (E - mu) Psi ; 0.5 diag((E-mu) Phi (E-mu)^T)
     Tc, seg_part = _quadratic_prepare(T, mu, None, Phi)
-    S = score_matrix(Ep, Tc, model_part, seg_part, cst=plda_cst, alpha=scaling_factor, passes=0, out_dtype=torch.float64)
+    S = score_matrix(Ep, Tc, model_part, seg_part, cst=plda_cst, alpha=scaling_factor, passes=0)
     if p_known != 0:
-        S = _open_set(S, p_known)
-    return _finish(clean_ndx, S)
+        S = _open_set(S.double(), p_known)
+    return _finish(clean_ndx, S, numpy.float64)
 
 
 def _open_set(S, p_known):
@@ -173,10 +209,10 @@ def full_PLDA_scoring(enroll, test, ndx, mu, F, G, Sigma, p_known=0.0, scaling_f
     E, T = _dev32(enroll_copy.stat1, dev), _dev32(test_copy.stat1, dev)
     Ep, model_part = _quadratic_prepare(E, mu, Psi, Phi)
     Tc, seg_part = _quadratic_prepare(T, mu, None, Phi)
-    S = score_matrix(Ep, Tc, model_part, seg_part, cst=constant, alpha=scaling_factor, passes=0, out_dtype=torch.float64)
+    S = score_matrix(Ep, Tc, model_part, seg_part, cst=constant, alpha=scaling_factor, passes=0)
     if p_known != 0:
-        S = _open_set(S, p_known)
-    return _finish(clean_ndx, S)
+        S = _open_set(S.double(), p_known)
+    return _finish(clean_ndx, S, numpy.float64)
 
 
 def PLDA_scoring(enroll, test, ndx, mu, F, G, Sigma, test_uncertainty=None, Vtrans=None, p_known=0.0,
@@ -212,8 +248,9 @@ def mahalanobis_scoring(enroll, test, ndx, m, check_missing=True):
     E, T = _dev32(enroll.stat1, dev), _dev32(test.stat1, dev)
     Ep, model_part = _quadratic_prepare(E, None, 0.5 * (m + m.T), -m)          # rowterm = 0.5 * e'(-m)e
     Tc, seg_part = _quadratic_prepare(T, None, None, -m)
-    S = score_matrix(Ep, Tc, model_part, seg_part, passes=0, out_dtype=torch.float64)
-    return _finish(clean_ndx, S)
+    # split mode always: e'me + t'mt - 2 e'mt cancels when e is close to t, so the cross term needs fp32-class products
+    S = score_matrix(Ep, Tc, model_part, seg_part, passes=3)
+    return _finish(clean_ndx, S, numpy.float64)
 
 
 def two_covariance_scoring(enroll, test, ndx, W, B, check_missing=True):
@@ -238,5 +275,5 @@ def two_covariance_scoring(enroll, test, ndx, W, B, check_missing=True):
     E, T = _dev32(enroll.stat1, dev), _dev32(test.stat1, dev)
     Ep, model_part = _quadratic_prepare(E, None, 2.0 * G, 2.0 * (G - H))
     Tc, seg_part = _quadratic_prepare(T, None, None, 2.0 * (G - H))
-    S = score_matrix(Ep, Tc, model_part, seg_part, passes=0, out_dtype=torch.float64)
-    return _finish(clean_ndx, S)
+    S = score_matrix(Ep, Tc, model_part, seg_part, passes=0)
+    return _finish(clean_ndx, S, numpy.float64)

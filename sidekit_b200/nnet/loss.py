@@ -26,3 +26,21 @@ class ArcMarginProduct(torch.nn.Module):
         if target is not None:
             raise NotImplementedError("training-time margin is out of scope (inference hot path only)")
         raise RuntimeError("the margin head runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True)")
+
+
+class SoftmaxAngularProto(torch.nn.Module):
+    """Parameter container of the 'aps' head (sidekit/nnet/loss.py:329-373); ``forward(x, target=None)`` =
+    ``cce_backend(x)``, a plain Linear on the embedding, runs in the engine's head GEMM."""
+
+    def __init__(self, spk_count, emb_dim=256, init_w=10.0, init_b=-5.0, **kwargs):
+        super().__init__()
+        from collections import OrderedDict
+        self.test_normalize = True
+        self.w = torch.nn.Parameter(torch.tensor(init_w))
+        self.b = torch.nn.Parameter(torch.tensor(init_b))
+        self.cce_backend = torch.nn.Sequential(OrderedDict([("linear8", torch.nn.Linear(emb_dim, spk_count))]))
+
+    def forward(self, x, target=None):
+        if target is not None:
+            raise NotImplementedError("the angular-prototypical training loss is out of scope (inference hot path only)")
+        raise RuntimeError("the 'aps' head runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True)")

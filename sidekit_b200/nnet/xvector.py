@@ -16,7 +16,7 @@ from collections import OrderedDict
 import torch
 
 from .. import _lib
-from .loss import ArcMarginProduct
+from .loss import ArcMarginProduct, SoftmaxAngularProto
 from .pooling import AttentivePooling, MeanStdPooling
 from .preprocessor import MelSpecFrontEnd, MfccFrontEnd
 from .res_net import PreHalfResNet34, PreResNet34, PreFastResNet34
@@ -46,6 +46,7 @@ class _NativeHandle:
         _lib.check(_lib.lib().skb_xtractor_create(_ARCHI_ID[archi], n, c_names, c_data, c_shapes, c_ndims,
                                                   compute_dtype, float(margin_s), ctypes.byref(out)))
         self.ptr = out
+        self.overflow_seen = 0          # cumulative fp16-saturation count already reported (skb_xtractor_overflow_count)
 
     def __del__(self):
         try:
@@ -123,12 +124,15 @@ class Xtractor(torch.nn.Module):
                 ("bn_be", torch.nn.BatchNorm1d(self.embedding_size))]))
             self.stat_pooling = AttentivePooling(256, 10, global_context=True)
             self.loss = loss
+            # xvector.py:585-593: 'aam' -> ArcMarginProduct, 'aps' -> SoftmaxAngularProto, anything else (None, 'cce') builds NO
+            # after_speaker_embedding; forward then returns the bare embedding (:896-907)
+            self._margin_s = 0.0
             if self.loss == "aam":
                 self.after_speaker_embedding = ArcMarginProduct(self.embedding_size, int(self.speaker_number),
                                                                 s=30, m=0.2, easy_margin=False)
                 self._margin_s = 30.0
-            else:
-                raise NotImplementedError("only loss='aam' is implemented for halfresnet34 (inference hot path)")
+            elif self.loss == "aps":
+                self.after_speaker_embedding = SoftmaxAngularProto(int(self.speaker_number), emb_dim=self.embedding_size)
         elif model_archi == "resnet34":
             # xvector.py:516-540.  Same deviation as halfresnet34: the shipped AttentivePooling(256, 80, ...) cannot consume
             # the trunk's 256 x 10 output; the 5120-wide Linear that follows shows the intended pooling.
@@ -190,9 +194,26 @@ class Xtractor(torch.nn.Module):
         flat = torch.cat([w.reshape(-1) for w in waves]) if len(waves) > 1 else waves[0].reshape(-1)
         return flat.contiguous().float(), lengths
 
-    def _run(self, flat, lengths, norm_embedding, want_logits=True):
+    def check_overflow(self):
+        """fp16 range guard: raises ``OverflowError`` when an activation stored since the last check saturated the fp16 range
+        (|x| >= 65504; the kernels clamp instead of producing inf, so the embeddings of those calls are wrong, not NaN).
+        Synchronises the current stream.  ``forward`` / ``extract_varlen`` / ``extract_stream`` call it themselves;
+        ``extract_packed`` does not (bulk loops check once at the end)."""
+        nat = self._native
+        if nat is None or self.compute_dtype != "fp16":
+            return
+        count = ctypes.c_int64(0)
+        with torch.cuda.device(self._native_device):
+            _lib.check(_lib.lib().skb_xtractor_overflow_count(nat.ptr, _lib.stream_ptr(), ctypes.byref(count)))
+        if count.value > nat.overflow_seen:
+            n = count.value - nat.overflow_seen
+            nat.overflow_seen = count.value
+            raise OverflowError("sidekit_b200: %d kernel threads stored activations beyond the fp16 range (65504); these weights "
+                                "need Xtractor(..., compute_dtype='bf16')" % n)
+
+    def _run(self, flat, lengths, norm_embedding, want_logits=True, emb_out=None):
         B = len(lengths)
-        if self.loss == "cce":
+        if self.loss not in ("aam", "aps"):
             want_logits = False
         on_cpu = not flat.is_cuda
         if not torch.cuda.is_available():
@@ -209,7 +230,8 @@ class Xtractor(torch.nn.Module):
                                                                emb.data_ptr(), logits.data_ptr() if want_logits else None,
                                                                _lib.stream_ptr()))
             else:
-                emb = torch.empty((B, E), dtype=torch.float32, device=device)
+                emb = emb_out if emb_out is not None else torch.empty((B, E), dtype=torch.float32, device=device)
+                assert emb.is_contiguous() and tuple(emb.shape) == (B, E) and emb.dtype == torch.float32 and emb.device == device
                 logits = torch.empty((B, S), dtype=torch.float32, device=device) if want_logits else None
                 _lib.check(_lib.lib().skb_xtractor_forward(h, flat.data_ptr(), lens, B, int(norm_embedding),
                                                           emb.data_ptr(), logits.data_ptr() if want_logits else None,
@@ -227,7 +249,8 @@ class Xtractor(torch.nn.Module):
         B, L = x.shape
         flat = x.contiguous().float().reshape(-1)
         logits, emb = self._run(flat, [L] * B, norm_embedding)
-        if self.loss == "cce":            # xvector.py:896-898: the bare (l2-normalised or raw) embedding
+        self.check_overflow()
+        if self.loss not in ("aam", "aps"):   # xvector.py:896-907: 'cce' at eval time, or no loss: the bare (l2-normalised or raw) embedding
             return self._pre_embedding(B, flat)
         return logits, emb
 
@@ -245,20 +268,25 @@ class Xtractor(torch.nn.Module):
         (every reduction in the engine is per utterance, so results equal one-by-one extraction)."""
         flat, lengths = self._pack(list(waves))
         logits, emb = self._run(flat, lengths, norm_embedding, want_logits)
+        self.check_overflow()
         return (logits, emb) if want_logits else emb
 
-    def extract_packed(self, flat, lengths, norm_embedding=True, want_logits=False):
+    def extract_packed(self, flat, lengths, norm_embedding=True, want_logits=False, out=None):
         """Extension for bulk extraction: ``flat`` already holds the utterances back to back (1-D fp32, CUDA or
         -- ideally pinned -- host memory), ``lengths`` their sample counts.  Host input goes through
-        ``skb_xtractor_forward_host`` (H2D, forward, D2H inside one native call)."""
-        logits, emb = self._run(flat, [int(v) for v in lengths], norm_embedding, want_logits)
+        ``skb_xtractor_forward_host`` (H2D, forward, D2H inside one native call).  ``out``: a (n, E) CUDA tensor (e.g. a
+        slice of the shard's embedding block) that receives the embeddings instead of a fresh allocation.
+        Asynchronous: the fp16 range guard is NOT checked here, call ``check_overflow()`` after the loop."""
+        logits, emb = self._run(flat, [int(v) for v in lengths], norm_embedding, want_logits, emb_out=out if flat.is_cuda else None)
         return (logits, emb) if want_logits else emb
 
-    def extract_stream(self, batches, norm_embedding=True):
+    def extract_stream(self, batches, norm_embedding=True, device_out=None):
         """Extension for bulk extraction from HOST memory with copy / compute overlap: ``batches`` is a sequence of
         ``(flat, lengths)`` pairs as for ``extract_packed`` (``flat`` ideally pinned).  The waveforms of batch i+1 travel
         over PCIe on a second stream while batch i is being embedded (two device staging buffers, events both ways);
-        the embeddings come back into one pinned host tensor.  Returns a list of (n_i, E) host tensors (views)."""
+        the embeddings come back into one pinned host tensor.  Returns a list of (n_i, E) host tensors (views).
+        ``device_out``: optional (sum n_i, E) CUDA tensor that also keeps the embeddings on the device, in batch order
+        (what the multi-GPU all-gather consumes)."""
         if not torch.cuda.is_available():
             raise RuntimeError("sidekit_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         batches = list(batches)
@@ -287,7 +315,8 @@ class Xtractor(torch.nn.Module):
                 ready = torch.cuda.Event()
                 ready.record(copy_s)
             compute.wait_event(ready)
-            _, emb = self._run(self._stage[k][:n], [int(v) for v in lengths], norm_embedding, want_logits=False)
+            _, emb = self._run(self._stage[k][:n], [int(v) for v in lengths], norm_embedding, want_logits=False,
+                               emb_out=None if device_out is None else device_out[row:row + len(lengths)])
             free_ev[k] = torch.cuda.Event()
             free_ev[k].record(compute)
             dst = self._out_host[row:row + emb.shape[0]]
@@ -295,6 +324,7 @@ class Xtractor(torch.nn.Module):
             outs.append(dst)
             row += emb.shape[0]
         compute.synchronize()
+        self.check_overflow()
         return outs
 
     def _frontend(self, x):

@@ -16,12 +16,19 @@ def _stub_extract(ws):
     return torch.stack([torch.stack([w.sum(), (w * w).sum(), w[0], w[-1], torch.tensor(float(w.numel()))]) for w in ws])
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, n_utt=37):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lengths = synth.synth_lengths(37, 0.2, 2.0, seed=11)
-    waves = [synth.synth_wave(1, int(L), seed=100 + i)[0] for i, L in enumerate(lengths)]
-    out = bulk.extract_embeddings_sharded(_stub_extract, waves, 5, max_audio_seconds=6.0)
+    lengths = synth.synth_lengths(n_utt, 0.2, 2.0, seed=11)
+    touched = []
+
+    def wave(i):                         # streamed source: a rank must only ever load ITS utterances
+        touched.append(i)
+        return synth.synth_wave(1, int(lengths[i]), seed=100 + i)[0]
+
+    out = bulk.extract_embeddings_sharded(_stub_extract, wave, 5, max_audio_seconds=6.0, lengths=lengths)
+    mine = bulk.plan_shards(lengths, world)[rank]
+    assert sorted(touched) == sorted(mine.tolist())
     q.put((rank, out.numpy()))
     dist.barrier()
     dist.destroy_process_group()
@@ -52,6 +59,35 @@ def test_sharded_extraction_world2_matches_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert numpy.array_equal(res[0], ref) and numpy.array_equal(res[1], ref)     # bit-for-bit, every rank
+
+
+def test_sharded_extraction_more_ranks_than_utterances():
+    """A rank with an EMPTY shard must still take part in the collective (it used to fall back to a CPU tensor)."""
+    lengths = synth.synth_lengths(1, 0.2, 2.0, seed=11)
+    ref = _stub_extract([synth.synth_wave(1, int(lengths[0]), seed=100)[0]]).numpy()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, 1)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert numpy.array_equal(res[0], ref) and numpy.array_equal(res[1], ref)
+
+
+def test_equal_cost_batches():
+    lengths = synth.synth_lengths(1000, 2.0, 20.0, seed=5)
+    shard = bulk.plan_shards(lengths, 4)[1]
+    batches = bulk.make_batches_equal_cost(shard, lengths, 7)
+    assert len(batches) == 7 and [i for b in batches for i in b] == shard.tolist()
+    loads = [sum(bulk.halfresnet34_macs(int(lengths[i])) for i in b) for b in batches]
+    assert max(loads) / (sum(loads) / 7) < 1.05
+    assert [len(b) for b in bulk.make_batches_equal_cost(shard[:3], lengths, 5)].count(0) == 2
+    assert bulk.make_batches_equal_cost([], lengths, 3) == [[], [], []]
+    assert numpy.array_equal(bulk.halfresnet34_macs(lengths), [bulk.halfresnet34_macs(int(v)) for v in lengths])
 
 
 def test_plan_shards_balanced_and_deterministic():

@@ -350,3 +350,74 @@ def test_errors_are_loud(hr34):
         m(torch.zeros(1, 300).cuda(), is_eval=True)
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 16000).cuda(), is_eval=False)
+
+
+def test_halfresnet34_return_conventions_for_every_loss(hr34):
+    """xvector.py:585-593, :896-907: 'aam' -> (s*cos logits, normalised emb); 'aps' -> (Linear logits, normalised emb);
+    None / 'cce' build no after_speaker_embedding and return the bare (l2-normalised) embedding."""
+    import contextlib, io
+    from sidekit_b200.nnet import Xtractor
+    m_aam, sd = hr34
+    x = synth.synth_wave(3, 20000, seed=9)
+    ref_emb = R.forward(sd, x, "halfresnet34")[1]
+    for loss in (None, "cce", "aps"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = Xtractor(32, "halfresnet34", loss=loss, embedding_size=256)
+        own = m.state_dict()
+        for k in own:
+            if k in sd:
+                own[k] = sd[k].clone()
+        synth.fill_state_dict({k: v for k, v in own.items() if k.startswith("after_speaker_embedding.cce_backend")}, 0)
+        m.load_state_dict(own)
+        m = m.eval().cuda()
+        out = m(x.cuda(), is_eval=True)
+        if loss == "aps":
+            logits, emb = out
+            W, b = own["after_speaker_embedding.cce_backend.linear8.weight"], own["after_speaker_embedding.cce_backend.linear8.bias"]
+            assert logits.shape == (3, 32)
+            assert (logits.cpu() - (ref_emb @ W.T + b)).abs().max().item() < 2e-3
+        else:
+            assert torch.is_tensor(out) and out.shape == (3, 256)
+            assert not hasattr(m, "after_speaker_embedding")
+            emb = out
+        assert rel_l2(emb.cpu(), ref_emb) < 1e-3
+
+
+def test_fp16_range_guard_fails_loudly_and_bf16_runs():
+    """SURVEY.md 7 "Precision": weights whose activations exceed 65504 must not yield silent inf / NaN embeddings."""
+    x = synth.synth_wave(2, 16000, seed=5)
+    for dtype in ("fp16", "bf16"):
+        m = make_xtractor("halfresnet34", 16, 256, compute_dtype=dtype)
+        sd = m.state_dict()
+        sd["sequence_network.conv1.weight"] *= 3.0e5             # stem output far beyond the fp16 range
+        m.load_state_dict(sd)
+        m = m.cuda()
+        if dtype == "fp16":
+            with pytest.raises(OverflowError):
+                m(x.cuda(), is_eval=True)
+            m.extract_packed(x.reshape(-1).cuda(), [16000, 16000])       # the bulk primitive defers the check ...
+            with pytest.raises(OverflowError):
+                m.check_overflow()                                       # ... to the caller
+        else:
+            emb = m(x.cuda(), is_eval=True)[1]
+            assert torch.isfinite(emb).all()
+    ok = make_xtractor("halfresnet34", 16, 256).cuda()
+    ok(x.cuda(), is_eval=True)                                           # ordinary weights: no error
+    ok.check_overflow()
+
+
+def test_pre_emphasis_coefficient_comes_from_the_checkpoint(hr34):
+    """PreEmphasis.flipped_filter of the state_dict is honoured (it was hard-coded to 0.97)."""
+    m, sd = hr34
+    m2 = make_xtractor("halfresnet34", 32, 256)
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2["preprocessor.PreEmphasis.flipped_filter"] = torch.tensor([[[-0.5, 1.0]]])
+    m2.load_state_dict(sd2)
+    m2 = m2.cuda()
+    x = synth.synth_wave(2, 16000, seed=1)
+    got = m2.preprocessor(x.cuda(), is_eval=True).cpu()
+    y = R.pre_emphasis(x, 0.5)
+    spec = R.power_spectrogram(y, 1024, 400, 160)
+    fb = sd["preprocessor.MelSpec.mel_scale.fb"]
+    ref = R.instance_norm(torch.log(torch.matmul(spec.transpose(1, 2), fb).transpose(1, 2) + 1e-6))
+    assert (got - ref).abs().max().item() < 1e-4

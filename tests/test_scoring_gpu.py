@@ -241,3 +241,43 @@ def test_scores_device_gather_and_pipelined_copy_equal_the_plain_paths():
     _ = b.scoremat                                    # materialise on the host first
     tar_h, non_h = b.get_tar_non(key)
     assert numpy.array_equal(tar_d, tar_h) and numpy.array_equal(non_d, non_h) and tar_d.dtype == tar_h.dtype
+
+
+def test_cosine_scoring_with_wccn():
+    """iv_scoring.py:99-101: both sides rotated by the WCCN matrix before the length normalisation."""
+    rng = numpy.random.default_rng(8)
+    D, Ne, Nt = 64, 150, 170
+    E, T = synth.synth_embeddings(Ne, D, seed=51, unit_norm=False), synth.synth_embeddings(Nt, D, seed=52, unit_norm=False)
+    Wc = numpy.linalg.cholesky(numpy.cov(rng.standard_normal((D, 4 * D))) + numpy.eye(D))
+    ids_e = numpy.array(["m%04d" % i for i in range(Ne)])
+    ids_t = numpy.array(["s%04d" % i for i in range(Nt)])
+    mask = rng.random((Ne, Nt)) < 0.5
+    sc = sk.cosine_scoring(_ss(ids_e, E), _ss(ids_t, T), _ndx(ids_e[::-1], ids_t, mask), wccn=Wc)
+    _check(sc, S.cosine_scoring(ids_e, E, ids_t, T, ids_e[::-1], ids_t, mask, wccn=Wc), 1e-3, numpy.float32)
+
+
+def test_packed_test_operand_equals_the_plain_call():
+    from sidekit_b200.iv_scoring import PackedEmbeddings, score_matrix
+    for unit in (True, False):
+        E = torch.from_numpy(synth.synth_embeddings(700, 256, seed=61, unit_norm=unit)).float().cuda()
+        T = torch.from_numpy(synth.synth_embeddings(900, 256, seed=62, unit_norm=unit)).float().cuda()
+        r, q = torch.randn(700, device="cuda"), torch.randn(900, device="cuda")
+        plain = score_matrix(E, T, r, q, cst=0.25, alpha=1.5, passes=0)
+        Tp = PackedEmbeddings(T)
+        for lo, hi in ((0, 700), (128, 391)):                        # the whole matrix and a row panel
+            got = score_matrix(E[lo:hi].contiguous(), Tp, r[lo:hi].contiguous(), q, cst=0.25, alpha=1.5, passes=3 if not unit else 1)
+            assert (got - plain[lo:hi]).abs().max().item() < 2e-4
+        assert torch.equal(score_matrix(E, Tp, r, q, cst=0.25, alpha=1.5, passes=0), plain)      # same arithmetic, same bits
+
+
+def test_large_matrix_reaches_the_host_through_the_pinned_path_widened():
+    """Scores.scoremat of the PLDA family: float32 on the device, float64 on the host (widened on the way out)."""
+    from sidekit_b200.bosaris import _device_to_numpy
+    g = torch.Generator(device="cuda").manual_seed(3)
+    t = torch.randn((5000, 2048), device="cuda", generator=g)           # 80 MB as float64: pinned, chunked path
+    out64 = _device_to_numpy(t, numpy.float64, chunk_bytes=16 << 20)
+    assert out64.dtype == numpy.float64 and numpy.array_equal(out64, t.cpu().numpy().astype(numpy.float64))
+    out32 = _device_to_numpy(t)
+    assert out32.dtype == numpy.float32 and numpy.array_equal(out32, t.cpu().numpy())
+    small = _device_to_numpy(t[:7].contiguous(), numpy.float64)
+    assert small.dtype == numpy.float64 and numpy.array_equal(small, t[:7].cpu().numpy().astype(numpy.float64))

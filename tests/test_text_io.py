@@ -215,3 +215,24 @@ def test_merges_match_the_reference():
     ka.tar[:], ka.non[:], kb.tar[:], kb.non[:] = True, False, False, True
     with pytest.raises(AssertionError):
         ka.merge([kb])
+
+
+def test_ndx_filter_fast_paths_keep_the_reference_semantics():
+    """Ndx.filter (ndx.py:128-165): identity / rows-only / columns-only / general selections give what two-step boolean
+    indexing gives; the identity case shares the mask instead of copying it twice."""
+    import sidekit_b200 as sk
+    rng = numpy.random.default_rng(0)
+    n = sk.Ndx()
+    n.modelset = numpy.array(["m%d" % i for i in range(7)])
+    n.segset = numpy.array(["s%d" % i for i in range(5)])
+    n.trialmask = rng.random((7, 5)) < 0.5
+    for mods, segs in ((n.modelset, n.segset), (n.modelset[[4, 1, 2]], n.segset), (n.modelset, n.segset[[3, 0]]),
+                       (n.modelset[[6, 0]], n.segset[[1, 4, 2]]), (numpy.array(["zz"]), n.segset)):
+        for keep in (True, False):
+            out = n.filter(mods, segs, keep)
+            km = numpy.isin(n.modelset, mods) == keep
+            ks = numpy.isin(n.segset, segs) == keep
+            assert numpy.array_equal(out.modelset, n.modelset[km]) and numpy.array_equal(out.segset, n.segset[ks])
+            assert numpy.array_equal(out.trialmask, n.trialmask[km, :][:, ks]) and out.validate()
+    same = n.filter(n.modelset, n.segset, True)
+    assert numpy.shares_memory(same.trialmask, n.trialmask) and not numpy.shares_memory(same.modelset, n.modelset)

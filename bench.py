@@ -383,6 +383,10 @@ def run_ours(args):
         return bulk.gather_embeddings(local_emb, shards, 256, device)          # the one collective of the path
 
     with torch.no_grad():
+        # the bulk run's batch budget is known up front (what bulk.make_batches is given): every work buffer and plan-cache
+        # slot is allocated now, none inside the run
+        model.reserve(int(1.1 * max(len(b) for b in blens + [wb[k] for k in range(W)])),
+                      1.1 * max(sum(bl) for bl in blens) / 16000.0, device)
         for k in reversed(range(W)):
             wls = [int(wl[i]) for i in wb[k]]
             model.extract_packed(device_audio(wls, 5 + k, device), wls)

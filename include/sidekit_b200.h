@@ -68,6 +68,11 @@ int skb_xtractor_forward(skb_xtractor_t* h, const float* wave_dev, const int64_t
 /* The embedding BEFORE the final F.normalize of the most recent forward call (what the reference
  * returns for loss='cce' with is_eval=True, xvector.py:896-898): out_dev (n_utt, E). */
 int skb_xtractor_pre_embedding(skb_xtractor_t* h, int n_utt, float* out_dev, void* stream);
+/* Bulk extraction: size every work buffer and every slot of the geometry-plan cache for batches of up to `max_utts`
+ * utterances and `max_total_samples` samples, so that nothing is allocated (cudaMalloc / cudaFree synchronise the device)
+ * once the run has started.  Optional: without it the buffers grow on demand. */
+int skb_xtractor_reserve(skb_xtractor_t* h, int max_utts, int64_t max_total_samples, void* stream);
+
 /* fp16 range guard.  With fp16 operands (compute_dtype 0) every stored activation is converted with saturation
  * (|x| > 65504 becomes +-65504 instead of +-inf) and the storing kernels count the threads that saw a saturated value.
  * Returns the CUMULATIVE count for this handle in *count after synchronising `stream`; a caller compares it with the

@@ -47,6 +47,7 @@ def _declare(lib):
         "skb_xtractor_frontend": (i32, [vp, vp, c_i64_p, i32, i32, vp, vp]),
         "skb_xtractor_debug_stage": (i32, [vp, vp, c_i64_p, i32, ctypes.c_char_p, i32, vp, c_i64_p, vp]),
         "skb_xtractor_pre_embedding": (i32, [vp, i32, vp, vp]),
+        "skb_xtractor_reserve": (i32, [vp, i32, i64, vp]),
         "skb_xtractor_overflow_count": (i32, [vp, vp, c_i64_p]),
         "skb_meanstd_pool": (i32, [vp, i32, i32, i32, vp, vp]),
         "skb_score_gemm": (i32, [vp, vp, i32, i32, i32, vp, vp, f64, f64, i32, i32, vp, i64, vp]),

@@ -163,6 +163,8 @@ def extract_embeddings(ids, waves, model, max_audio_seconds=1200.0, lengths=None
     """In-memory counterpart of the reference's ``extract_embeddings``: returns a ``StatServer`` whose ``stat1`` holds
     the embeddings and ``stat0`` ones (xvector.py:1905-1914)."""
     dev = next(model.parameters()).device
+    if dev.type == "cuda":
+        model.reserve(256, max_audio_seconds, dev)      # the batch budget of make_batches below: no allocation inside the run
     emb = extract_embeddings_sharded(lambda ws: model.extract_varlen([w.to(dev) for w in ws]), waves, model.embedding_size,
                                      max_audio_seconds, lengths=lengths)
     return StatServer.from_embeddings(numpy.asarray(ids), emb.cpu().numpy())

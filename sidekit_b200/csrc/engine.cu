@@ -709,6 +709,7 @@ struct skb_xtractor {
     DevBuf brd, cmvn, cmvn_part, skinny_ws;
     DevBuf ovf;                   // fp16 range guard: cumulative count of threads that stored a saturated activation (common.cuh)
     int device = 0;               // the CUDA device the weights and work buffers live on
+    size_t hw_tab32 = 0, hw_tab64 = 0, hw_pixmeta = 0;   // high-water marks of the plan tables: every cache slot is sized for them
     DevBuf feats, sums, scale, poolX, poolH, poolL, gc, hb, pooled, lin, emb_pre, emb, logits, wave, dbg;
     std::vector<DevBuf> act;      // activation buffers
     std::vector<size_t> act_bytes;
@@ -847,14 +848,16 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     int rc;
     skb_xtractor::Slot& sl = h->slot;
     const size_t b32 = pl.tab32.size() * sizeof(int), b64 = pl.tab64.size() * sizeof(long long);
-    if ((rc = sl.tab32.ensure(b32))) return rc;
-    if ((rc = sl.tab64.ensure(b64))) return rc;
+    h->hw_tab32 = std::max(h->hw_tab32, b32);
+    h->hw_tab64 = std::max(h->hw_tab64, b64);
+    if ((rc = sl.tab32.ensure(h->hw_tab32))) return rc;
+    if ((rc = sl.tab64.ensure(h->hw_tab64))) return rc;
     // the staging copies of this slot's previous plan must have left the host before they are overwritten (they did,
     // unless the host is a whole cache of batches ahead of the device)
     if (sl.uploaded) SKB_CUDA_CHECK(cudaEventSynchronize(sl.uploaded));
     else SKB_CUDA_CHECK(cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming));
-    if ((rc = sl.stage32.ensure(b32))) return rc;
-    if ((rc = sl.stage64.ensure(b64))) return rc;
+    if ((rc = sl.stage32.ensure(h->hw_tab32))) return rc;
+    if ((rc = sl.stage64.ensure(h->hw_tab64))) return rc;
     memcpy(sl.stage32.p, pl.tab32.data(), b32);
     memcpy(sl.stage64.p, pl.tab64.data(), b64);
     SKB_CUDA_CHECK(cudaMemcpyAsync(sl.tab32.p, sl.stage32.p, b32, cudaMemcpyHostToDevice, st));
@@ -868,22 +871,50 @@ static int build_plan(skb_xtractor* h, const int64_t* lengths, int B, cudaStream
     return activate_plan(h, st);
 }
 
-// Zero what the producing convolution never writes in a phase-split buffer (the geometry of level `Lo`, four phase
-// images of cpp = C_prev/8 chunk planes each): the pad pixels, and -- when the source utterance has an odd number of
-// lines -- the last line of the two odd-row phases, which has no source line and acts as the bottom zero padding.
-__global__ void zero_ps_kernel(uint16_t* __restrict__ buf, long long plane, int cpp, int G, int n, int Wp, int W,
-                               const int* __restrict__ row_b, const int* __restrict__ row_h,
-                               const int* __restrict__ src_utt_count, int src_W) {
-    const int rel = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rel >= n) return;
-    const int row = rel / Wp, w = rel - row * Wp;
-    const int b = row_b[row], hh = row_h[row];
+// Everything a plan activation has to (re)establish in the shared work buffers, in ONE launch (it used to be up to 19
+// cudaMemset2DAsync + 3 kernels + 1 memset per new batch geometry, ~0.3 ms of launch gaps per step of a bulk extraction):
+//  * guards: the G pixels before the first computed pixel of every chunk plane of every activation buffer (tap (-1, -1)
+//    of the first pixel reads pixel G - 1; the plane stride moves with the geometry);
+//  * phase-split buffers: what the producing convolution never writes -- the pad pixels, and, when the source utterance
+//    has an odd number of lines, the last line of the two odd-row phases (it has no source line and acts as the bottom
+//    zero padding);
+//  * the fixed-point SE channel totals.
+struct ActGuard { uint16_t* p; long long plane; int n_planes, G; };
+struct ActPs { uint16_t* buf; long long plane; int cpp, G, n, Wp, W, src_W, first_block; const int *row_b, *row_h, *src_utt_count; };
+struct ActArgs {
+    ActGuard g[20]; int n_guards;
+    ActPs ps[3]; int n_ps;
+    unsigned long long* sums; int n_sums, sums_first_block;
+};
+__global__ void __launch_bounds__(256) plan_activate_kernel(const __grid_constant__ ActArgs a) {
+    const int blk = blockIdx.x;
+    if (blk < a.n_guards) {
+        const ActGuard& g = a.g[blk];
+        const int per = g.G;                                    // 16-byte units per plane
+        for (int i = threadIdx.x; i < g.n_planes * per; i += blockDim.x) {
+            const int j = i / per, q = i - j * per;
+            *reinterpret_cast<uint4*>(g.p + ((size_t)j * g.plane + q) * 8) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        return;
+    }
+    if (blk >= a.sums_first_block) {
+        const int i = (blk - a.sums_first_block) * blockDim.x + threadIdx.x;
+        if (i < a.n_sums) a.sums[i] = 0ull;
+        return;
+    }
+    int k = 0;
+    while (k + 1 < a.n_ps && blk >= a.ps[k + 1].first_block) ++k;
+    const ActPs& z = a.ps[k];
+    const int rel = (blk - z.first_block) * blockDim.x + threadIdx.x;
+    if (rel >= z.n) return;
+    const int row = rel / z.Wp, w = rel - row * z.Wp;
+    const int b = z.row_b[row], hh = z.row_h[row];
     int first_phase;
-    if (b < 0 || hh < 0 || w >= W) first_phase = 0;                                  // pad pixel: all four phases
-    else if (2 * hh + 1 >= src_utt_count[b] / src_W) first_phase = 2;                // no odd source line below
+    if (b < 0 || hh < 0 || w >= z.W) first_phase = 0;                                    // pad pixel: all four phases
+    else if (2 * hh + 1 >= z.src_utt_count[b] / z.src_W) first_phase = 2;                // no odd source line below
     else return;
-    for (int j = first_phase * cpp; j < 4 * cpp; ++j)
-        *reinterpret_cast<uint4*>(buf + ((size_t)j * plane + G + rel) * 8) = make_uint4(0u, 0u, 0u, 0u);
+    for (int j = first_phase * z.cpp; j < 4 * z.cpp; ++j)
+        *reinterpret_cast<uint4*>(z.buf + ((size_t)j * z.plane + z.G + rel) * 8) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // Make `h->plan` current: size the shared work buffers for it and re-establish the few invariants that depend on the
@@ -911,33 +942,45 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
     h->act_bytes = need;
     for (size_t i = 0; i < need.size(); ++i)
         if ((rc = h->act[i].ensure(need[i]))) return rc;
-    if (is_resnet(m.archi)) {
-        // The one guard pixel that IS read into a kept accumulator row: tap (-1, -1) of the first pixel of the first
-        // line reaches pixel G - 1.  Nothing ever writes below G, but the plane stride moves with the geometry, so the
-        // guard of every chunk plane is cleared whenever the plan changes.
-        for (int l = 0; l < 4; ++l)
-            for (int k = 0; k < 5; ++k) {
-                if (k == 3 && (l == 0 || !m.level_halves[l])) continue;      // no phase-split buffer on this level
-                const Level& L = pl.lv[l];
-                const int n_planes = k == 3 ? 4 * (pl.lv[l - 1].C / 8) : L.C / 8;
-                SKB_CUDA_CHECK(cudaMemset2DAsync(h->act[l * 5 + k].p, (size_t)L.plane * 16, 0, (size_t)L.G * 16, n_planes, st));
-            }
-        for (int l = 1; l < 4; ++l) {
-            if (!m.level_halves[l]) continue;
-            const Level& Lo = pl.lv[l];
-            const int n = Lo.p_end - Lo.G;
-            const Level& Ls = pl.lv[l - 1];
-            zero_ps_kernel<<<(n + 255) / 256, 256, 0, st>>>((uint16_t*)h->act[l * 5 + 3].p, Lo.plane, Ls.C / 8, Lo.G, n, Lo.Wp, Lo.W,
-                                                            h->d32 + Lo.o_row_b, h->d32 + Lo.o_row_h, h->d32 + Ls.o_utt_count, Ls.W);
-        }
-        SKB_CUDA_CHECK(cudaGetLastError());
-    }
     const int Cmax = is_resnet(m.archi) ? 256 : 0;
     if (Cmax) {
         if ((rc = h->sums.ensure((size_t)B * Cmax * sizeof(unsigned long long)))) return rc;
         if ((rc = h->scale.ensure((size_t)B * Cmax * sizeof(float)))) return rc;
         if ((rc = h->brd.ensure((size_t)B * (8 + 36) * Cmax * sizeof(float)))) return rc;   // border sums + K-slice partial means
-        SKB_CUDA_CHECK(cudaMemsetAsync(h->sums.p, 0, (size_t)B * Cmax * sizeof(unsigned long long), st));
+    }
+    if (is_resnet(m.archi)) {
+        // The one guard pixel that IS read into a kept accumulator row: tap (-1, -1) of the first pixel of the first
+        // line reaches pixel G - 1.  Nothing ever writes below G, but the plane stride moves with the geometry, so the
+        // guard of every chunk plane is cleared whenever the plan changes.
+        ActArgs a;
+        memset(&a, 0, sizeof(a));
+        for (int l = 0; l < 4; ++l)
+            for (int k = 0; k < 5; ++k) {
+                if (k == 3 && (l == 0 || !m.level_halves[l])) continue;      // no phase-split buffer on this level
+                const Level& L = pl.lv[l];
+                ActGuard& g = a.g[a.n_guards++];
+                g.p = (uint16_t*)h->act[l * 5 + k].p;
+                g.plane = L.plane;
+                g.n_planes = k == 3 ? 4 * (pl.lv[l - 1].C / 8) : L.C / 8;
+                g.G = L.G;
+            }
+        int blocks = a.n_guards;
+        for (int l = 1; l < 4; ++l) {
+            if (!m.level_halves[l]) continue;
+            const Level& Lo = pl.lv[l];
+            const Level& Ls = pl.lv[l - 1];
+            ActPs& z = a.ps[a.n_ps++];
+            z.buf = (uint16_t*)h->act[l * 5 + 3].p; z.plane = Lo.plane; z.cpp = Ls.C / 8; z.G = Lo.G; z.n = Lo.p_end - Lo.G;
+            z.Wp = Lo.Wp; z.W = Lo.W; z.src_W = Ls.W; z.first_block = blocks;
+            z.row_b = h->d32 + Lo.o_row_b; z.row_h = h->d32 + Lo.o_row_h; z.src_utt_count = h->d32 + Ls.o_utt_count;
+            blocks += (z.n + 255) / 256;
+        }
+        a.sums = (unsigned long long*)h->sums.p;
+        a.n_sums = B * Cmax;
+        a.sums_first_block = blocks;
+        blocks += (a.n_sums + 255) / 256;
+        plan_activate_kernel<<<blocks, 256, 0, st>>>(a);
+        SKB_CUDA_CHECK(cudaGetLastError());
     }
     if ((rc = h->feats.ensure((size_t)pl.total_frames * m.fe.n_out * sizeof(float)))) return rc;
     if ((rc = h->cmvn.ensure((size_t)B * m.fe.n_out * sizeof(float2)))) return rc;
@@ -957,28 +1000,57 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
     return SKB_OK;
 }
 
-// Per-pixel tables for the conv epilogue (one coalesced read instead of a division and two dependent gathers):
+// Per-pixel tables for the conv epilogue (one coalesced read instead of a division and two dependent gathers), for ALL
+// levels of a plan in one launch:
 // pix_b[rel] = utterance of pixel G + rel or -1 for pad / invalid; pix_ps[rel] = destination of the pixel in the
 // PHASE-SPLIT copy that feeds the next level's stride-2 block: four phase images (h & 1, w & 1) in the next level's
-// geometry, stacked as groups of C/8 chunk planes:  dest = phase * (C/8) * plane' + G' + (row0'[b] + h/2) * Wp' + w/2.
-__global__ void pixmeta_kernel(int n, int Wp, int W, const int* __restrict__ row_b, const int* __restrict__ row_h,
-                               int* __restrict__ pix_b, int* __restrict__ pix_ps, int out_G, int out_Wp,
-                               const int* __restrict__ out_utt_row0, long long phase_stride) {
-    const int rel = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rel >= n) return;
-    const int row = rel / Wp, w = rel - row * Wp;
-    const int b = row_b[row], hh = row_h[row];
-    const bool valid = b >= 0 && hh >= 0 && w < W;
-    pix_b[rel] = valid ? b : -1;
-    if (pix_ps)
-        pix_ps[rel] = valid ? (int)(((hh & 1) * 2 + (w & 1)) * phase_stride + out_G + (long long)(out_utt_row0[b] + (hh >> 1)) * out_Wp + (w >> 1))
-                            : -1;
+// geometry, stacked as groups of C/8 chunk planes:  dest = phase * (C/8) * plane' + G' + (row0'[b] + h/2) * Wp' + w/2;
+// span_b[span] = the utterance of a 256-pixel span when every valid pixel belongs to one, -1 when it holds only pad
+// pixels, -2 when it straddles utterances (plane_sum_kernel).  One warp per span.
+struct MetaLevel {
+    int n, Wp, W, out_G, out_Wp, first_block;
+    const int *row_b, *row_h, *out_utt_row0;
+    int *pix_b, *pix_ps, *span_b;
+    long long phase_stride;
+};
+struct MetaArgs { MetaLevel lv[6]; int n_levels; };
+__global__ void __launch_bounds__(256) planmeta_kernel(const __grid_constant__ MetaArgs a) {
+    int k = 0;
+    while (k + 1 < a.n_levels && (int)blockIdx.x >= a.lv[k + 1].first_block) ++k;
+    const MetaLevel& L = a.lv[k];
+    const int lane = threadIdx.x & 31;
+    const int span = ((int)blockIdx.x - L.first_block) * 8 + (threadIdx.x >> 5);
+    if (span * 256 >= L.n) return;
+    int mn = 0x7fffffff, mx = -1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int rel = span * 256 + q * 32 + lane;
+        if (rel >= L.n) continue;
+        const int row = rel / L.Wp, w = rel - row * L.Wp;
+        const int b = L.row_b[row], hh = L.row_h[row];
+        const bool valid = b >= 0 && hh >= 0 && w < L.W;
+        L.pix_b[rel] = valid ? b : -1;
+        if (L.pix_ps)
+            L.pix_ps[rel] = valid ? (int)(((hh & 1) * 2 + (w & 1)) * L.phase_stride + L.out_G +
+                                          (long long)(L.out_utt_row0[b] + (hh >> 1)) * L.out_Wp + (w >> 1))
+                                  : -1;
+        if (valid) { mn = min(mn, b); mx = max(mx, b); }
+    }
+    if (L.span_b) {
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) L.span_b[span] = mx < 0 ? -1 : (mn == mx ? mn : -2);
+    }
 }
 
 static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
     Plan& pl = h->plan;
     size_t total = 0;
     const bool hr = is_resnet(h->m.archi);
+    if (pl.lv.size() > 6) {
+        set_last_error(__FILE__, __LINE__, "internal: more than 6 geometry levels");
+        return SKB_ERR_STATE;
+    }
     for (size_t l = 0; l < pl.lv.size(); ++l) {
         Level& L = pl.lv[l];
         const size_t n = (size_t)(L.p_end - L.G);
@@ -987,21 +1059,31 @@ static int build_pixmeta(skb_xtractor* h, cudaStream_t st) {
         if (L.has_sub) { L.o_pix_sub = total; total += n; }
         if (hr) { L.o_span = total; total += (size_t)span_table_size((int)n); }
     }
-    int rc = h->slot.pixmeta.ensure(total * sizeof(int));
+    // every slot of the plan cache is sized for the largest table set seen so far (a slot that had to grow would cost a
+    // cudaFree / cudaMalloc pair, i.e. a device-wide synchronisation, in the middle of a bulk extraction)
+    h->hw_pixmeta = std::max(h->hw_pixmeta, total * sizeof(int));
+    int rc = h->slot.pixmeta.ensure(h->hw_pixmeta);
     if (rc) return rc;
     int* base = (int*)h->slot.pixmeta.p;
+    MetaArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_levels = (int)pl.lv.size();
+    int blocks = 0;
     for (size_t l = 0; l < pl.lv.size(); ++l) {
         const Level& L = pl.lv[l];
-        const int n = L.p_end - L.G;
         const Level* Lo = L.has_sub ? &pl.lv[l + 1] : nullptr;
-        pixmeta_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, L.Wp, L.W, h->d32 + L.o_row_b, h->d32 + L.o_row_h, base + L.o_pix_b,
-                                                        Lo ? base + L.o_pix_sub : nullptr, Lo ? Lo->G : 0, Lo ? Lo->Wp : 0,
-                                                        Lo ? h->d32 + Lo->o_utt_row0 : nullptr, Lo ? (long long)(L.C / 8) * Lo->plane : 0);
-        if (hr) {
-            int rc2 = launch_span_table(base + L.o_pix_b, n, base + L.o_span, st);
-            if (rc2) return rc2;
-        }
+        MetaLevel& M = a.lv[l];
+        M.n = L.p_end - L.G; M.Wp = L.Wp; M.W = L.W; M.first_block = blocks;
+        M.row_b = h->d32 + L.o_row_b; M.row_h = h->d32 + L.o_row_h;
+        M.pix_b = base + L.o_pix_b;
+        M.pix_ps = Lo ? base + L.o_pix_sub : nullptr;
+        M.span_b = hr ? base + L.o_span : nullptr;
+        M.out_G = Lo ? Lo->G : 0; M.out_Wp = Lo ? Lo->Wp : 0;
+        M.out_utt_row0 = Lo ? h->d32 + Lo->o_utt_row0 : nullptr;
+        M.phase_stride = Lo ? (long long)(L.C / 8) * Lo->plane : 0;
+        blocks += (span_table_size(M.n) + 7) / 8;
     }
+    if (blocks > 0) planmeta_kernel<<<blocks, 256, 0, st>>>(a);
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
 }
@@ -1451,6 +1533,40 @@ int skb_xtractor_forward_host(skb_xtractor_t* h, const float* wave_host, const i
     SKB_CUDA_CHECK(cudaMemcpyAsync(emb_host, h->emb.p, (size_t)n_utt * h->m.emb * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (logits_host)
         SKB_CUDA_CHECK(cudaMemcpyAsync(logits_host, h->logits.p, (size_t)n_utt * h->m.n_spk * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SKB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SKB_OK;
+}
+
+int skb_xtractor_reserve(skb_xtractor_t* h, int max_utts, int64_t max_total_samples, void* stream) {
+    if (!h || max_utts <= 0 || max_total_samples <= 0) {
+        set_last_error(__FILE__, __LINE__, "reserve: bad arguments");
+        return SKB_ERR_ARG;
+    }
+    if (current_device() != h->device) {
+        set_last_error(__FILE__, __LINE__, "this extractor handle lives on another CUDA device than the current one");
+        return SKB_ERR_STATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    // The largest tables / work buffers any batch within the budget can need: `max_utts` utterances sharing the audio
+    // evenly (most lines, most pad lines, most pixels on every level), plus a few per cent for rounding.
+    const int64_t min_len = h->m.fe.n_fft / 2 + 1 + 14 * (int64_t)h->m.fe.hop;
+    const int64_t total = max_total_samples + max_total_samples / 20;
+    const int64_t each = std::max<int64_t>(total / max_utts + 1, min_len);
+    std::vector<int64_t> lengths((size_t)max_utts, each);
+    SKB_TRY(build_plan(h, lengths.data(), max_utts, st));
+    h->hw_tab32 += h->hw_tab32 / 16; h->hw_tab64 += h->hw_tab64 / 16; h->hw_pixmeta += h->hw_pixmeta / 16;
+    // every slot of the plan cache now, at the high-water sizes: nothing is allocated once the bulk run has started
+    while (h->cache.size() <= kPlanCacheEntries) {
+        h->cache.emplace_back();
+        skb_xtractor::CachedPlan& c = h->cache.back();       // an empty plan (B = 0) never matches a request; stamp 0 = recycled first
+        SKB_TRY(c.slot.tab32.ensure(h->hw_tab32));
+        SKB_TRY(c.slot.tab64.ensure(h->hw_tab64));
+        SKB_TRY(c.slot.pixmeta.ensure(h->hw_pixmeta));
+        SKB_TRY(c.slot.stage32.ensure(h->hw_tab32));
+        SKB_TRY(c.slot.stage64.ensure(h->hw_tab64));
+        SKB_CUDA_CHECK(cudaEventCreateWithFlags(&c.slot.uploaded, cudaEventDisableTiming));
+        SKB_CUDA_CHECK(cudaEventRecord(c.slot.uploaded, st));
+    }
     SKB_CUDA_CHECK(cudaStreamSynchronize(st));
     return SKB_OK;
 }

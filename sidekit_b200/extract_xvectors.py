@@ -3,9 +3,11 @@ means) out, with the reference's function names and arguments (``read_wav_scp`` 
 ``load_model`` :74-91, ``main`` :93-173, the argparse block :175-203).
 
 What changes against the reference: the utterances are not pushed through the model one by one (a few hundred small
-launches and a device-to-host copy each) but read first, resampled on the device where their rate differs from the
-model's (``preprocessor.Resample``) and embedded in length-bucketed packed batches (``bulk.make_batches`` +
-``Xtractor.extract_varlen``); the packed engine is exact per utterance, so the vectors are those of the one-by-one loop.
+launches and a device-to-host copy each) but streamed in windows of ~80 minutes of audio (host memory), and each window
+is embedded in length-bucketed packed batches (``bulk.make_batches`` + ``Xtractor.extract_varlen``), resampled on the
+device where a file's rate differs from the model's (``preprocessor.Resample``); only the batch being embedded is on
+the device, and the ark is written window by window.  The packed engine is exact per utterance, so the vectors are
+those of the one-by-one loop.
 ``--vad`` needs the silero model that the reference fetches with ``torch.hub`` at run time (no network here): it raises.
 Tables are written with ``sidekit_b200.kaldi_io`` in the layout ``kaldiio.WriteHelper('ark,scp:...')`` produces.
 """
@@ -65,38 +67,56 @@ def load_model(model_path, device):
 
 @torch.no_grad()
 def main(xtractor, kaldi_wav_scp, out_file, device, vad=False, num_samples_per_window=2000, min_silence_samples=1500,
-         model_sample_rate=16000, out_file_spk="", spk2utt_file="", max_audio_seconds=1200.0):
+         model_sample_rate=16000, out_file_spk="", spk2utt_file="", max_audio_seconds=1200.0, window_audio_seconds=4800.0):
     """Embed every utterance of ``kaldi_wav_scp`` and write ``<out_file stem>.ark`` + ``out_file`` (scp); with
     ``out_file_spk`` also the L2-normalised mean x-vector of every speaker of ``spk2utt_file`` (:93-173)."""
     if vad:
         raise NotImplementedError("--vad loads snakers4/silero-vad through torch.hub (network); run VAD upstream")
     device = torch.device(device)
     utt2wav = read_wav_scp(kaldi_wav_scp)
-    keys, waves, resamplers = [], [], {}
-    for key, wav in utt2wav.items():
-        signal, sr = prepare(wav)
-        signal = signal.to(device, non_blocking=True)
-        if sr != model_sample_rate:
-            if sr not in resamplers:
-                resamplers[sr] = Resample(orig_freq=sr, new_freq=model_sample_rate)
-            signal = resamplers[sr](signal)
-        keys.append(key)
-        waves.append(signal)
     xtractor.eval()
     xtractor.to(device)
-    lengths = numpy.array([int(w.shape[0]) for w in waves], dtype=numpy.int64)
-    order = numpy.argsort(lengths, kind="stable")
-    emb = torch.empty((len(waves), xtractor.embedding_size), dtype=torch.float32)
-    outs, index = [], []
-    for batch in reversed(bulk.make_batches(order.tolist(), lengths, max_audio_seconds, sample_rate=model_sample_rate)):
-        outs.append(xtractor.extract_varlen([waves[i] for i in batch]))
-        index.extend(batch)
-    if outs:
-        emb[torch.as_tensor(index)] = torch.cat(outs).cpu()
+    resamplers = {}
     out_ark = os.path.realpath(os.path.join(os.path.dirname(out_file), os.path.splitext(os.path.basename(out_file))[0])) + ".ark"
-    with kaldi_io.ArkScpWriter(out_ark, os.path.realpath(out_file)) as writer:
-        for key, vec in zip(keys, emb.numpy()):
+    all_emb = []
+
+    def flush(window, writer):
+        """Embed one window of utterances (host tensors) in length-bucketed packed batches and write its entries in file
+        order.  Only the batch being embedded lives on the device."""
+        if not window:
+            return
+        lengths = numpy.array([-(-int(sig.shape[0]) * model_sample_rate // sr) for _, sig, sr in window], dtype=numpy.int64)
+        order = numpy.argsort(lengths, kind="stable")
+        emb = torch.empty((len(window), xtractor.embedding_size), dtype=torch.float32)
+        for batch in reversed(bulk.make_batches(order.tolist(), lengths, max_audio_seconds, sample_rate=model_sample_rate)):
+            waves = []
+            for i in batch:
+                _, sig, sr = window[i]
+                sig = sig.to(device, non_blocking=True)
+                if sr != model_sample_rate:
+                    if sr not in resamplers:
+                        resamplers[sr] = Resample(orig_freq=sr, new_freq=model_sample_rate)
+                    sig = resamplers[sr](sig)
+                waves.append(sig)
+            emb[torch.as_tensor(batch)] = xtractor.extract_varlen(waves).cpu()
+        for (key, _, _), vec in zip(window, emb.numpy()):
             writer(key, vec[None, :])                      # the reference writes the (1, E) output of the model
+        all_emb.append(emb)
+
+    # The wav.scp is STREAMED in windows of `window_audio_seconds` of audio (host memory; a pipe entry has no length until
+    # it has been read): a corpus of hundreds of hours never sits in memory, and the ark grows window by window in file
+    # order, like the reference's one-file-at-a-time loop.
+    with kaldi_io.ArkScpWriter(out_ark, os.path.realpath(out_file)) as writer:
+        window, window_s = [], 0.0
+        for key, wav in utt2wav.items():
+            signal, sr = prepare(wav)
+            window.append((key, signal, sr))
+            window_s += float(signal.shape[0]) / sr
+            if window_s >= window_audio_seconds:
+                flush(window, writer)
+                window, window_s = [], 0.0
+        flush(window, writer)
+    emb = torch.cat(all_emb) if all_emb else torch.empty((0, xtractor.embedding_size), dtype=torch.float32)
     if out_file_spk:
         spk2utt = {}
         with open(spk2utt_file) as f:

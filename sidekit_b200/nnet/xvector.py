@@ -194,6 +194,15 @@ class Xtractor(torch.nn.Module):
         flat = torch.cat([w.reshape(-1) for w in waves]) if len(waves) > 1 else waves[0].reshape(-1)
         return flat.contiguous().float(), lengths
 
+    def reserve(self, max_utts, max_audio_seconds, device=None, sample_rate=16000):
+        """Extension for bulk extraction: allocate every work buffer and geometry-plan slot for packed batches of up to
+        ``max_utts`` utterances / ``max_audio_seconds`` of audio now (``skb_xtractor_reserve``), so the run itself never
+        allocates."""
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        h = self._handle(device)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().skb_xtractor_reserve(h, int(max_utts), int(max_audio_seconds * sample_rate), _lib.stream_ptr()))
+
     def check_overflow(self):
         """fp16 range guard: raises ``OverflowError`` when an activation stored since the last check saturated the fp16 range
         (|x| >= 65504; the kernels clamp instead of producing inf, so the embeddings of those calls are wrong, not NaN).

@@ -209,5 +209,10 @@ def test_extract_xvectors_main_writes_kaldi_tables(tmp_path):
     spk = dict(kaldi_io.read_scp(spk_scp))
     mean = direct[[0, 2]].mean(axis=0)
     assert numpy.allclose(spk["spk1"], mean / numpy.linalg.norm(mean), atol=1e-6) and abs(numpy.linalg.norm(spk["spk2"]) - 1) < 1e-6
+    # streamed in windows (the corpus is never resident): one utterance per window gives the same tables
+    out2 = os.path.join(d, "xv_windowed.scp")
+    X.main(model, os.path.join(d, "wav.scp"), out2, "cuda", window_audio_seconds=0.01)
+    table2 = dict(kaldi_io.read_scp(out2))
+    assert list(table2.keys()) == list(table.keys()) and all(numpy.array_equal(table2[k], table[k]) for k in table)
     with pytest.raises(NotImplementedError):
         X.main(model, os.path.join(d, "wav.scp"), out_scp, "cuda", True)

@@ -176,7 +176,7 @@ def test_baseline_config3_full_size_plda():
     ndx = _ndx(en_ids, te_ids, numpy.ones((Ne, Nt), dtype=bool))
     sc = sk.PLDA_scoring(_ss(en_ids, E), _ss(te_ids, T), ndx, mu, F, numpy.zeros((D, 0)), Sigma)
     dev = sc.scoremat_device
-    assert dev.shape == (Ne, Nt) and dev.dtype == torch.float64
+    assert dev.shape == (Ne, Nt) and dev.dtype == torch.float32 and sc.scoremat_dtype == numpy.float64      # widened on the way to the host
     assert sc.modelset.tolist() == en_ids.tolist() and sc.segset.tolist() == te_ids.tolist()
     rng = numpy.random.default_rng(3)
     ri, ci = numpy.sort(rng.choice(Ne, 300, replace=False)), numpy.sort(rng.choice(Nt, 300, replace=False))

@@ -707,6 +707,7 @@ struct skb_xtractor {
     cudaStream_t last_stream = nullptr;
     bool have_last_stream = false;
     DevBuf brd, cmvn, cmvn_part, skinny_ws;
+    DevBuf se_cnt;                // ticket counters of the SE gate kernel (ceil(B / 16) ints, zero between launches)
     DevBuf ovf;                   // fp16 range guard: cumulative count of threads that stored a saturated activation (common.cuh)
     int device = 0;               // the CUDA device the weights and work buffers live on
     size_t hw_tab32 = 0, hw_tab64 = 0, hw_pixmeta = 0;   // high-water marks of the plan tables: every cache slot is sized for them
@@ -947,6 +948,9 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
         if ((rc = h->sums.ensure((size_t)B * Cmax * sizeof(unsigned long long)))) return rc;
         if ((rc = h->scale.ensure((size_t)B * Cmax * sizeof(float)))) return rc;
         if ((rc = h->brd.ensure((size_t)B * (8 + 36) * Cmax * sizeof(float)))) return rc;   // border sums + K-slice partial means
+        bool grew = false;
+        if ((rc = h->se_cnt.ensure((size_t)(B / 16 + 2) * sizeof(int), &grew))) return rc;
+        if (grew) SKB_CUDA_CHECK(cudaMemsetAsync(h->se_cnt.p, 0, h->se_cnt.cap, st));
     }
     if (is_resnet(m.archi)) {
         // The one guard pixel that IS read into a kept accumulator row: tap (-1, -1) of the first pixel of the first
@@ -1289,12 +1293,10 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
             // SE scales from conv2's INPUT (linearity of the convolution): one bandwidth-bound pass over y1 + small kernels
             ProfScope ps(PROF_SE, st);
             const int* pm = (const int*)h->slot.pixmeta.p;
-            if (!sums_in_conv1)
-                SKB_TRY(launch_plane_sum(m.bf16, y1, L.plane, L.G, L.p_end, pm + L.o_pix_b, pm + L.o_span, bw.C,
-                                         (unsigned long long*)h->sums.p, st));
-            SKB_TRY(launch_se_scale(m.bf16, (unsigned long long*)h->sums.p, y1, L.plane, L.G, L.Wp, L.W, d32 + L.o_utt_row0,
+            SKB_TRY(launch_se_scale(m.bf16, (unsigned long long*)h->sums.p, y1, L.plane, L.G, L.p_end, L.Wp, L.W, d32 + L.o_utt_row0,
                                     d32 + L.o_utt_count, B, bw.C, bw.C, bw.w2t, bw.conv2.bias, bw.se_w1, bw.se_w2,
-                                    (float*)h->brd.p, (float*)h->scale.p, st));
+                                    (float*)h->brd.p, (float*)h->scale.p, pm + L.o_pix_b, sums_in_conv1 ? nullptr : pm + L.o_span,
+                                    (int*)h->se_cnt.p, st));
         }
         {
             // conv2 with the fused SE tail: out = relu(bn2(conv2(y1)) * scale + residual)
@@ -1304,7 +1306,7 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
                              next_strides ? &pl.lv[level + 1] : nullptr, st));
         }
         x_is_ps = next_strides;
-        g_launches += 4;
+        g_launches += 2;
         cur ^= 1;
         if (stop && !strcmp(stop, name)) return export_stage(h, buf(level, cur), L, h_max, dbg_out, per_utt, st);
     }
@@ -1493,7 +1495,7 @@ void skb_xtractor_destroy(skb_xtractor_t* h) {
     h->slot.release();
     DevBuf* bufs[] = {&h->feats, &h->sums, &h->scale, &h->poolX, &h->poolH, &h->poolL, &h->gc, &h->hb,
                       &h->pooled, &h->lin, &h->emb_pre, &h->emb, &h->logits, &h->wave, &h->dbg, &h->brd, &h->cmvn,
-                      &h->cmvn_part, &h->skinny_ws, &h->ovf};
+                      &h->cmvn_part, &h->skinny_ws, &h->ovf, &h->se_cnt};
     for (auto* b : bufs) b->release();
     for (auto& b : h->act) b.release();
     for (auto& c : h->cache) c.slot.release();

@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include "layers.cuh"
 
+#include <algorithm>
+
 namespace skb {
 
 // ----------------------------------------------------------------------------- stem: 3x3 conv 1->32 + BN + ReLU
@@ -252,18 +254,16 @@ __device__ __forceinline__ long long warp_sum8_i64(const long long (&t)[8], int 
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(256, 4) plane_sum_kernel(const uint16_t* __restrict__ act, long long plane, int G, int p_end,
-                                                        const int* __restrict__ pix_b, const int* __restrict__ span_b, int C,
-                                                        int planes_per_block, unsigned long long* __restrict__ sums) {
-    pdl_trigger();
-    pdl_wait();
+__device__ __forceinline__ void plane_sum_body(const uint16_t* __restrict__ act, long long plane, int G, int p_end,
+                                               const int* __restrict__ pix_b, const int* __restrict__ span_b, int C,
+                                               int planes_per_block, unsigned long long* __restrict__ sums, int span_block, int plane_block) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int span = blockIdx.x * 8 + warp;
+    const int span = span_block * 8 + warp;
     const int base = G + span * kSpanPix;
     if (base >= p_end) return;
     const int sb = __ldg(span_b + span);
     if (sb == -1) return;                                  // pad pixels only: all zeros
-    const int j0 = blockIdx.y * planes_per_block;
+    const int j0 = plane_block * planes_per_block;
     int pb[8];                                             // per-pixel utterances, only needed when the span is mixed
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -335,33 +335,13 @@ int launch_span_table(const int* pix_b, int n_pix, int* span_b, cudaStream_t st)
     return SKB_OK;
 }
 
-int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, const int* span_b, int C,
-                     unsigned long long* sums, cudaStream_t st) {
-    const int n = p_end - G;
-    const int n_spans = span_table_size(n);
-    const int chunks = C / 8;
-    const int ppb = chunks >= 16 ? 4 : (chunks >= 8 ? 2 : 1);      // keep >= ~4 waves of CTAs on the small levels
-    dim3 grid((n_spans + 7) / 8, chunks / ppb);
-    if (bf16)
-        SKB_CUDA_CHECK(launch_pdl(plane_sum_kernel<true>, grid, dim3(256), 0, st, act, plane, G, p_end, pix_b, span_b, C, ppb, sums));
-    else
-        SKB_CUDA_CHECK(launch_pdl(plane_sum_kernel<false>, grid, dim3(256), 0, st, act, plane, G, p_end, pix_b, span_b, C, ppb, sums));
-    SKB_LAUNCH_CHECK(st);
-    return SKB_OK;
-}
-
 // se_border_kernel: sums of the first / last row and column of y1 and its four corner pixels, per (utterance, channel).
 // One CTA per (utterance, 8-channel chunk); threads stride over the border pixels with 16-byte loads; the block
 // reduction runs in a fixed order, so the result is deterministic.  brd layout: [B][8 kinds][C].
 template <bool BF16>
-__global__ void __launch_bounds__(256) se_border_kernel(const uint16_t* __restrict__ y1, long long plane, int G, int Wp, int W,
-                                                        const int* __restrict__ utt_row0, const int* __restrict__ utt_count, int C,
-                                                        float* __restrict__ brd) {
-    __shared__ float part[256][33];
-    __shared__ float part2[8][32];
-    pdl_trigger();
-    pdl_wait();
-    const int b = blockIdx.x, j = blockIdx.y;
+__device__ __forceinline__ void se_border_body(const uint16_t* __restrict__ y1, long long plane, int G, int Wp, int W,
+                                               const int* __restrict__ utt_row0, const int* __restrict__ utt_count, int C,
+                                               float* __restrict__ brd, int b, int j, float (*part)[33], float (*part2)[32]) {
     const int H = utt_count[b] / W;
     const uint16_t* base = y1 + ((size_t)j * plane + G + (size_t)utt_row0[b] * Wp) * 8;     // pixel (0, 0) of chunk j
     float acc[32];                                  // [row0 | rowL | col0 | colL][8 channels]
@@ -418,16 +398,44 @@ __global__ void __launch_bounds__(256) se_border_kernel(const uint16_t* __restri
     }
 }
 
+// One launch for everything the SE gate needs from y1 itself: blocks [0, n_border) = border sums (one CTA per utterance and
+// 8-channel chunk), the rest = the fixed-point channel totals (plane_sum; none on the 32-channel layers, whose conv1
+// epilogue accumulates them).  Both only read y1, so they run side by side instead of one after the other (the border
+// kernel alone is latency-bound: 17 us at 10 % issue utilisation).
+template <bool BF16>
+__global__ void __launch_bounds__(256, 4) se_stats_kernel(const uint16_t* __restrict__ y1, long long plane, int G, int p_end, int Wp, int W,
+                                                          const int* __restrict__ utt_row0, const int* __restrict__ utt_count, int C,
+                                                          float* __restrict__ brd, int n_border, const int* __restrict__ pix_b,
+                                                          const int* __restrict__ span_b, int planes_per_block, int n_span_blocks,
+                                                          unsigned long long* __restrict__ sums) {
+    __shared__ float part[256][33];
+    __shared__ float part2[8][32];
+    pdl_trigger();
+    pdl_wait();
+    const int blk = blockIdx.x;
+    if (blk < n_border) {
+        const int chunks = C >> 3;
+        se_border_body<BF16>(y1, plane, G, Wp, W, utt_row0, utt_count, C, brd, blk / chunks, blk % chunks, part, part2);
+    } else {
+        const int r = blk - n_border;
+        plane_sum_body<BF16>(y1, plane, G, p_end, pix_b, span_b, C, planes_per_block, sums, r % n_span_blocks, r / n_span_blocks);
+    }
+}
+
 // se_mean_partial_kernel: the mean of conv2's output through the (16-bit-rounded, BN-folded) conv2 weights, as a small
 // GEMM  partial[ks][b][co] = sum_{i in K-slice ks} W2t[i][co] * S[b][i],  i = ci * 9 + tap,  S = the nine shifted sums.
 // Grid = (Cin / 8 slices of 8 channels x 9 taps, utterance groups of 16); every weight row is read once per utterance
 // group.  Fixed summation order everywhere -> deterministic.
 constexpr int kSeCh = 8, kSeRows = 9 * kSeCh, kSeUtt = 16;
 template <int Cout>
-__global__ void __launch_bounds__(256) se_mean_partial_kernel(const unsigned long long* __restrict__ sums, const float* __restrict__ brd,
+__global__ void __launch_bounds__(256) se_mean_partial_kernel(unsigned long long* __restrict__ sums, const float* __restrict__ brd,
                                                               int B, int Cin, const float* __restrict__ w2t,
-                                                              float* __restrict__ partial) {
+                                                              float* __restrict__ partial, int* __restrict__ counters,
+                                                              const int* __restrict__ utt_count, const float* __restrict__ b2,
+                                                              const float* __restrict__ fc1 /*[Cout/16][Cout]*/,
+                                                              const float* __restrict__ fc2 /*[Cout][Cout/16]*/, float* __restrict__ scale) {
     __shared__ float sS[kSeUtt][kSeRows];
+    __shared__ int s_last;
     constexpr int n_rg = 256 / Cout;               // row groups: 8 / 4 / 2 / 1 for Cout = 32 / 64 / 128 / 256
     constexpr int RPT = kSeRows / n_rg;            // weight rows per thread: 9 / 18 / 36 / 72
     // this thread's weights first: RPT independent loads whose latency overlaps the shifted-sum phase below
@@ -495,70 +503,91 @@ __global__ void __launch_bounds__(256) se_mean_partial_kernel(const unsigned lon
         for (int g = 0; g < n_rg; ++g) a += sRed[(g * kSeUtt + u) * Cout + c];
         partial[((size_t)blockIdx.x * B + b0 + u) * Cout + c] = a;
     }
-}
-
-// se_fc_kernel: mean = b2 + (1/N) * sum of the K-slice partials (in slice order); scale = sigmoid(W2 relu(W1 mean))
-// (sidekit/nnet/res_net.py:272-281).  One CTA per utterance; re-zeroes the fixed-point channel sums for the next block.
-__global__ void __launch_bounds__(256) se_fc_kernel(unsigned long long* __restrict__ sums, const float* __restrict__ partial, int n_slices,
-                                                    const int* __restrict__ utt_count, int B, int Cin, int Cout,
-                                                    const float* __restrict__ b2, const float* __restrict__ fc1 /*[Cout/16][Cout]*/,
-                                                    const float* __restrict__ fc2 /*[Cout][Cout/16]*/, float* __restrict__ scale) {
-    __shared__ float mean[256];
-    __shared__ float hid[16];
-    pdl_trigger();
-    pdl_wait();
-    const int b = blockIdx.x;
-    const float inv_n = 1.f / (float)utt_count[b];
-    for (int c = threadIdx.x; c < Cin; c += blockDim.x) sums[(size_t)b * Cin + c] = 0ull;
-    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-        float a = 0.f;
-        for (int k = 0; k < n_slices; ++k) a += partial[((size_t)k * B + b) * Cout + co];
-        mean[co] = fmaf(a, inv_n, b2[co]);
-    }
+    // The CTA that finishes LAST for this group of utterances turns the K-slice partials into the gate (the former
+    // se_fc_kernel: one more dependent launch per block): mean = b2 + (1/N) * sum of the partials in slice order (fixed
+    // order -> deterministic whichever CTA happens to be last); scale = sigmoid(W2 relu(W1 mean))
+    // (sidekit/nnet/res_net.py:272-281).  It also re-zeroes the group's fixed-point channel totals for the next block
+    // (every CTA of the group has read them before taking its ticket) and the ticket counter itself.
+    __threadfence();
     __syncthreads();
-    const int R = Cout / 16;
+    if (threadIdx.x == 0) s_last = (atomicAdd(counters + blockIdx.y, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) counters[blockIdx.y] = 0;
+    float* mean = sRed;                 // [Cout]
+    float* hid = sRed + 256;            // [16]
+    const int n_slices = gridDim.x, R = Cout / 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int jj = warp; jj < R; jj += blockDim.x >> 5) {
-        float a = 0.f;
-        for (int c = lane; c < Cout; c += 32) a = fmaf(fc1[jj * Cout + c], mean[c], a);
-        a = warp_sum(a);
-        if (lane == 0) hid[jj] = fmaxf(a, 0.f);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
-        float a = 0.f;
-        for (int jj = 0; jj < R; ++jj) a = fmaf(fc2[c * R + jj], hid[jj], a);
-        scale[(size_t)b * Cout + c] = 1.f / (1.f + __expf(-a));
+    for (int u = 0; u < nu; ++u) {
+        const int b = b0 + u;
+        __syncthreads();
+        for (int c = threadIdx.x; c < Cin; c += blockDim.x) sums[(size_t)b * Cin + c] = 0ull;
+        if (threadIdx.x < Cout) {
+            float a = 0.f;
+            for (int k = 0; k < n_slices; ++k) a += __ldcg(partial + ((size_t)k * B + b) * Cout + threadIdx.x);
+            mean[threadIdx.x] = fmaf(a, 1.f / (float)utt_count[b], b2[threadIdx.x]);
+        }
+        __syncthreads();
+        for (int jj = warp; jj < R; jj += 8) {
+            float a = 0.f;
+            for (int c = lane; c < Cout; c += 32) a = fmaf(fc1[jj * Cout + c], mean[c], a);
+            a = warp_sum(a);
+            if (lane == 0) hid[jj] = fmaxf(a, 0.f);
+        }
+        __syncthreads();
+        if (threadIdx.x < Cout) {
+            float a = 0.f;
+            for (int jj = 0; jj < R; ++jj) a = fmaf(fc2[threadIdx.x * R + jj], hid[jj], a);
+            scale[(size_t)b * Cout + threadIdx.x] = 1.f / (1.f + __expf(-a));
+        }
     }
 }
 
-int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, long long plane, int G, int Wp, int W,
+// The SE gate of one BasicBlock in TWO dependent launches (it used to be four: plane_sum -> se_border -> se_mean_partial
+// -> se_fc, each a few microseconds of work behind a launch gap, 16 times per forward): se_stats_kernel, then
+// se_mean_partial_kernel whose last CTA per utterance group applies the two FC layers.
+// `span_b` == nullptr: the channel totals are already in `sums` (accumulated by conv1's epilogue), only the border sums
+// are computed.  `counters`: ceil(B / 16) zero-initialised ints (self-resetting).
+int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, long long plane, int G, int p_end, int Wp, int W,
                     const int* utt_row0, const int* utt_count, int B, int Cin, int Cout, const float* w2t, const float* b2,
-                    const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st) {
+                    const float* fc1, const float* fc2, float* brd_ws, float* scale, const int* pix_b, const int* span_b,
+                    int* counters, cudaStream_t st) {
     // brd_ws: [B][8][Cin] border sums, followed by [n_slices][B][Cout] partial means
     if (Cout > 256 || 256 % Cout != 0) {
         set_last_error(__FILE__, __LINE__, "squeeze-excitation: channel count must divide 256");
         return SKB_ERR_ARG;
     }
-    dim3 grid(B, Cin / 8);
+    const int chunks = Cin / 8;
+    const int n_border = B * chunks;
+    int n_span_blocks = 0, ppb = 1, n_sum_blocks = 0;
+    if (span_b != nullptr) {
+        const int n_spans = span_table_size(p_end - G);
+        ppb = chunks >= 16 ? 4 : (chunks >= 8 ? 2 : 1);      // keep >= ~4 waves of CTAs on the small levels
+        n_span_blocks = (n_spans + 7) / 8;
+        n_sum_blocks = n_span_blocks * (chunks / ppb);
+    }
+    const dim3 grid(n_border + n_sum_blocks);
     if (bf16)
-        SKB_CUDA_CHECK(launch_pdl(se_border_kernel<true>, grid, dim3(256), 0, st, y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws));
+        SKB_CUDA_CHECK(launch_pdl(se_stats_kernel<true>, grid, dim3(256), 0, st, y1, plane, G, p_end, Wp, W, utt_row0, utt_count, Cin,
+                                  brd_ws, n_border, pix_b, span_b, ppb, std::max(n_span_blocks, 1), sums));
     else
-        SKB_CUDA_CHECK(launch_pdl(se_border_kernel<false>, grid, dim3(256), 0, st, y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws));
+        SKB_CUDA_CHECK(launch_pdl(se_stats_kernel<false>, grid, dim3(256), 0, st, y1, plane, G, p_end, Wp, W, utt_row0, utt_count, Cin,
+                                  brd_ws, n_border, pix_b, span_b, ppb, std::max(n_span_blocks, 1), sums));
     SKB_LAUNCH_CHECK(st);
     const int n_slices = Cin / kSeCh;
     float* partial = brd_ws + (size_t)B * 8 * Cin;
     dim3 g2(n_slices, (B + kSeUtt - 1) / kSeUtt);
-    if (Cout == 32) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<32>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
-    else if (Cout == 64) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<64>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
-    else if (Cout == 128) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<128>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
-    else if (Cout == 256) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<256>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
+#define SKB_SE_GATE(C) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<C>, g2, dim3(256), 0, st, sums, (const float*)brd_ws, B, Cin, w2t, partial, counters, utt_count, b2, fc1, fc2, scale))
+    if (Cout == 32) SKB_SE_GATE(32);
+    else if (Cout == 64) SKB_SE_GATE(64);
+    else if (Cout == 128) SKB_SE_GATE(128);
+    else if (Cout == 256) SKB_SE_GATE(256);
     else {
         set_last_error(__FILE__, __LINE__, "squeeze-excitation: unsupported channel count");
         return SKB_ERR_ARG;
     }
-    SKB_LAUNCH_CHECK(st);
-    SKB_CUDA_CHECK(launch_pdl(se_fc_kernel, dim3(B), dim3(256), 0, st, sums, partial, n_slices, utt_count, B, Cin, Cout, b2, fc1, fc2, scale));
+#undef SKB_SE_GATE
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }

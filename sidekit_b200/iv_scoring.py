@@ -118,8 +118,8 @@ def cosine_scoring(enroll, test, ndx, wccn=None, check_missing=True, device=None
     assert isinstance(enroll, StatServer), 'First parameter should be a StatServer'
     assert isinstance(test, StatServer), 'Second parameter should be a StatServer'
     assert isinstance(ndx, Ndx), 'Third parameter should be an Ndx'
-    enroll_copy = copy.deepcopy(enroll)
-    test_copy = copy.deepcopy(test)
+    enroll_copy = copy.copy(enroll)            # shallow: every StatServer method used below REBINDS its arrays, none writes in place,
+    test_copy = copy.copy(test)                # so the caller's objects are untouched without two (N, D) float64 copies
     clean_ndx = _check_missing_model(enroll_copy, test_copy, ndx) if check_missing else ndx
     if wccn is not None:
         enroll_copy.rotate_stat1(wccn)
@@ -136,8 +136,8 @@ def fast_PLDA_scoring(enroll, test, ndx, mu, F, Sigma, test_uncertainty=None, Vt
                       scaling_factor=1., check_missing=True):
     """Simplified PLDA log-likelihood ratios (iv_scoring.py:370-477); ``scoremat`` is float64 like the reference
     (fp32-class precision, see ``_finish``)."""
-    enroll_ctr = copy.deepcopy(enroll)
-    test_ctr = copy.deepcopy(test)
+    enroll_ctr = copy.copy(enroll)             # shallow: every StatServer method used below REBINDS its arrays, none writes in place,
+    test_ctr = copy.copy(test)                 # so the caller's objects are untouched without two (N, D) float64 copies
     if not numpy.unique(enroll_ctr.modelset).shape == enroll_ctr.modelset.shape:
         logging.warning("Enrollment models are not unique, average i-vectors")
         enroll_ctr = enroll_ctr.mean_stat_per_model()
@@ -189,8 +189,8 @@ def full_PLDA_scoring(enroll, test, ndx, mu, F, G, Sigma, p_known=0.0, scaling_f
     ``Phi = B' (K2 - K1) B`` (D x D algebra on the host in float64, the trial matrix on the device).  Note that --
     unlike ``fast_PLDA_scoring`` -- duplicate enrolment models are NOT averaged (the reference has that block
     commented out, :290-294)."""
-    enroll_copy = copy.deepcopy(enroll)
-    test_copy = copy.deepcopy(test)
+    enroll_copy = copy.copy(enroll)            # shallow: every StatServer method used below REBINDS its arrays, none writes in place,
+    test_copy = copy.copy(test)                # so the caller's objects are untouched without two (N, D) float64 copies
     clean_ndx = _check_missing_model(enroll_copy, test_copy, ndx) if check_missing else ndx
     invSigma = scipy.linalg.inv(Sigma)
     I_iv = numpy.eye(mu.shape[0], dtype='float')

@@ -86,4 +86,7 @@ def asnorm(enrol_xv, cohort_xv, ndx=None, topk=200, return_device=False):
         _lib.check(l.skb_asnorm_stats(X.data_ptr(), coh.data_ptr(), N, C, D, int(topk), mean.data_ptr(), std.data_ptr(),
                                       _lib.stream_ptr()))
         _lib.check(l.skb_asnorm_apply(X.data_ptr(), N, D, mean.data_ptr(), std.data_ptr(), out.data_ptr(), _lib.stream_ptr()))
-    return out if return_device else out.cpu().numpy()
+    if return_device:
+        return out
+    from .bosaris import _device_to_numpy
+    return _device_to_numpy(out)                     # pinned, PCIe-speed path for large matrices

@@ -95,6 +95,39 @@ int skb_xtractor_num_frames(const skb_xtractor_t* h, int64_t n_samples);
 int skb_xtractor_debug_stage(skb_xtractor_t* h, const float* wave_dev, const int64_t* lengths, int n_utt,
                              const char* stage, int h_max, float* out_dev, int64_t* per_utt, void* stream);
 
+/* ---- stand-alone module operators: the engine's kernels on DENSE fp32 tensors ------------------------
+ * Conv2d (3x3 pad 1 or 1x1 pad 0, stride 1 or 2, no dilation) with the following BatchNorm folded into w / bias by the
+ * caller, the activation max(v, slope * v) (0 = ReLU, 1 = identity, 0.01 = LeakyReLU), and optionally the tail of a
+ * BasicBlock fused into the epilogue: y = act(conv(x) * se_scale[b][c] + residual).  Replaces conv + bn + relu of
+ * sidekit/nnet/res_net.py:309-320 (BasicBlock), :238-255 (ResBlock; its pre-activation BatchNorm + LeakyReLU is the
+ * optional prologue x <- lrelu(x * pre_scale[c] + pre_shift[c], pre_slope)), :549 (stem).
+ * x_dev (B, Cin, H, W), residual_dev / y_dev (B, Cout, Ho, Wo) fp32 NCHW contiguous, Ho = (H - 1) / stride + 1;
+ * w_host (Cout, Cin, k, k) and bias_host (Cout) are HOST arrays; pre_scale / pre_shift (Cin) and se_scale (B, Cout) device.
+ * Runs on the tcgen05 convolution kernel with 16-bit operands (compute_dtype as skb_xtractor_create). */
+int skb_conv2d_bn_act(const float* x_dev, int B, int Cin, int H, int W, const float* w_host, const float* bias_host, int Cout,
+                      int ksize, int stride, const float* pre_scale_dev, const float* pre_shift_dev, float pre_slope,
+                      float act_slope, const float* se_scale_dev, const float* residual_dev, int compute_dtype, float* y_dev,
+                      void* stream);
+/* fp16 range guard of the stand-alone operators: cumulative saturation count of this thread's operator context. */
+int skb_ops_overflow_count(void* stream, int64_t* count);
+/* AdaptiveAvgPool2d(1): x_dev (B, C, hw) -> out_dev (B, C)  (SELayer, res_net.py:264, :279). */
+int skb_channel_mean(const float* x_dev, int B, int C, int64_t hw, float* out_dev, void* stream);
+/* SELayer.fc: scale = sigmoid(fc2 . relu(fc1 . mean)); fc1 (R, C), fc2 (C, R) row-major, no biases (res_net.py:265-270). */
+int skb_se_gate(const float* mean_dev, const float* fc1_dev, const float* fc2_dev, int B, int C, int R, float* scale_dev,
+                void* stream);
+/* out = act(y * scale[b][c] + res): SELayer.forward (res NULL, slope 1) and the tail of BasicBlock.forward
+ * (res_net.py:316-319); scale_dev / res_dev may be NULL. */
+int skb_scale_residual_act(const float* y_dev, const float* scale_dev, const float* res_dev, int B, int C, int64_t hw,
+                           float slope, float* out_dev, void* stream);
+/* torch.nn.functional.normalize(x, dim=1): rows of x_dev (N, D) divided by max(||row||, eps)  (loss.py:304-305). */
+int skb_l2_normalize(const float* x_dev, int N, int D, float eps, float* out_dev, void* stream);
+/* AttentivePooling.forward (sidekit/nnet/pooling.py:151-171) on x_dev (B, D, T) fp32, D = channels * frequencies:
+ * w1 (A, 3D or D) / b1 (A), BatchNorm1d(A) as scale / shift, w2 (D, A) / b2 (D), all device fp32;
+ * out_dev (B, 2D) = [weighted mean ; weighted std]. */
+int skb_attentive_pool(const float* x_dev, int B, int D, int T, const float* w1_dev, const float* b1_dev,
+                       const float* bn_s_dev, const float* bn_t_dev, const float* w2_dev, const float* b2_dev, int A,
+                       int global_context, float* out_dev, void* stream);
+
 /* ---- pooling ops: replace MeanStdPooling.forward (sidekit/nnet/pooling.py:55-70) ---------------------- */
 /* x_dev (n_utt, D, T) fp32 contiguous -> out_dev (n_utt, 2*D) = [mean ; unbiased std]. */
 int skb_meanstd_pool(const float* x_dev, int n_utt, int D, int T, float* out_dev, void* stream);

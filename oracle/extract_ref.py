@@ -151,6 +151,21 @@ def basic_block(sd, prefix, x, stride):
     return F.relu(out + sc)
 
 
+def res_block(sd, prefix, x, is_first=False, slope=0.01):
+    """ResBlock.forward, nnet/res_net.py:229-255 (eval mode, stride 1): pre-activation BN + LeakyReLU unless ``is_first``;
+    conv1 (bias) -> batch_norm2 -> LeakyReLU -> conv2 (bias) -> the SAME batch_norm2 -> + identity (1x1 conv with bias +
+    BN when the width changes, :201-208) -> LeakyReLU."""
+    identity = x
+    out = x if is_first else F.leaky_relu(_bn(sd, prefix + ".batch_norm1", x), slope)
+    out = F.conv2d(out, sd[prefix + ".conv1.weight"], sd[prefix + ".conv1.bias"], padding=1)
+    out = F.leaky_relu(_bn(sd, prefix + ".batch_norm2", out), slope)
+    out = F.conv2d(out, sd[prefix + ".conv2.weight"], sd[prefix + ".conv2.bias"], padding=1)
+    out = _bn(sd, prefix + ".batch_norm2", out)
+    if prefix + ".resample.0.weight" in sd:
+        identity = _bn(sd, prefix + ".resample.1", F.conv2d(x, sd[prefix + ".resample.0.weight"], sd[prefix + ".resample.0.bias"]))
+    return F.leaky_relu(out + identity, slope)
+
+
 HALFRESNET34_STAGES = ((3, 1), (4, 2), (6, 2), (3, 2))       # (num_blocks, first stride), res_net.py:520-523
 # PreResNet34, res_net.py:455-462: layer7 is built with num_blocks[5], i.e. ONE block
 RESNET34_STAGES = ((3, 1), (1, 2), (3, 1), (1, 2), (5, 1), (1, 2), (1, 1))

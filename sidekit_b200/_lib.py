@@ -49,6 +49,13 @@ def _declare(lib):
         "skb_xtractor_pre_embedding": (i32, [vp, i32, vp, vp]),
         "skb_xtractor_reserve": (i32, [vp, i32, i64, vp]),
         "skb_xtractor_overflow_count": (i32, [vp, vp, c_i64_p]),
+        "skb_conv2d_bn_act": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, f32, f32, vp, vp, i32, vp, vp]),
+        "skb_ops_overflow_count": (i32, [vp, c_i64_p]),
+        "skb_channel_mean": (i32, [vp, i32, i32, i64, vp, vp]),
+        "skb_se_gate": (i32, [vp, vp, vp, i32, i32, i32, vp, vp]),
+        "skb_scale_residual_act": (i32, [vp, vp, vp, i32, i32, i64, f32, vp, vp]),
+        "skb_l2_normalize": (i32, [vp, i32, i32, f32, vp, vp]),
+        "skb_attentive_pool": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]),
         "skb_meanstd_pool": (i32, [vp, i32, i32, i32, vp, vp]),
         "skb_score_gemm": (i32, [vp, vp, i32, i32, i32, vp, vp, f64, f64, i32, i32, vp, i64, vp]),
         "skb_packed_create": (i32, [vp, i32, i32, ctypes.POINTER(vp), vp]),

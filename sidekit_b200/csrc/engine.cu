@@ -64,11 +64,19 @@ struct HostTensor {
 };
 typedef std::map<std::string, HostTensor> WeightMap;
 
+// SKB_TRACE_ALLOC=1: report every (re)allocation of a work buffer on stderr (they synchronise the device: none may
+// happen in the steady state of a bulk extraction)
+static bool trace_alloc() {
+    static const bool on = [] { const char* e = getenv("SKB_TRACE_ALLOC"); return e && e[0] == '1'; }();
+    return on;
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes, bool* grew = nullptr) {
         if (bytes <= cap) return SKB_OK;
+        if (trace_alloc()) fprintf(stderr, "skb: device buffer grows %zu -> %zu bytes\n", cap, bytes);
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -95,6 +103,7 @@ struct PinnedBuf {
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return SKB_OK;
+        if (trace_alloc()) fprintf(stderr, "skb: pinned buffer grows %zu -> %zu bytes\n", cap, bytes);
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
@@ -248,18 +257,12 @@ static int pack_conv_bn(const WeightMap& w, const std::string& conv_key, const s
 static const int kPhaseTaps[9][2] = {{1, 1}, {1, 0}, {1, 2}, {0, 1}, {2, 1}, {0, 0}, {0, 2}, {2, 0}, {2, 2}};
 static const int kPhaseTapBegin[5] = {0, 1, 3, 5, 9};
 
-static int pack_conv_bn_phase_split(const WeightMap& w, const std::string& conv_key, const std::string& bn_prefix, bool bf16,
-                                    ConvW* out) {
-    const HostTensor* cw = find(w, conv_key);
-    if (!cw || cw->shape.size() != 4 || cw->shape[2] != 3 || cw->shape[3] != 3) return SKB_ERR_WEIGHTS;
-    const int cout = (int)cw->shape[0], cin = (int)cw->shape[1];
+// wf: folded weights [cout][cin][9] (double), bias [cout]
+static int pack_conv_phase_split(const std::vector<double>& wf, const std::vector<double>& bias, int cout, int cin, bool bf16, ConvW* out) {
     if (cin % kConvKC != 0) {
         set_last_error(__FILE__, __LINE__, "phase-split conv needs input channels in multiples of 32");
         return SKB_ERR_WEIGHTS;
     }
-    std::vector<double> s, t;
-    int rc = bn_affine(w, bn_prefix, &s, &t);
-    if (rc) return rc;
     const int ncta = conv_pick_ncta(cout), n_split = cout / ncta, cpp = cin / kConvKC;   // chunks per phase
     std::vector<uint16_t> img((size_t)n_split * cpp * 9 * 4 * ncta * 8);
     size_t o = 0;
@@ -272,13 +275,28 @@ static int pack_conv_bn_phase_split(const WeightMap& w, const std::string& conv_
                         for (int n = 0; n < ncta; ++n)
                             for (int e = 0; e < 8; ++e) {
                                 const int co = ns * ncta + n, ci = ch * kConvKC + j * 8 + e;
-                                img[o++] = to16((float)((double)cw->p[((size_t)co * cin + ci) * 9 + tap] * s[co]), bf16);
+                                img[o++] = to16((float)wf[((size_t)co * cin + ci) * 9 + tap], bf16);
                             }
                 }
-    std::vector<float> bf(t.begin(), t.end());
+    std::vector<float> bf(bias.begin(), bias.end());
     out->cin = 4 * cin; out->cout = cout; out->taps = 9; out->ncta = ncta; out->phase_split = true;
+    int rc;
     if ((rc = dev_upload(img, &out->w))) return rc;
     return dev_upload(bf, &out->bias);
+}
+
+static int pack_conv_bn_phase_split(const WeightMap& w, const std::string& conv_key, const std::string& bn_prefix, bool bf16,
+                                    ConvW* out) {
+    const HostTensor* cw = find(w, conv_key);
+    if (!cw || cw->shape.size() != 4 || cw->shape[2] != 3 || cw->shape[3] != 3) return SKB_ERR_WEIGHTS;
+    const int cout = (int)cw->shape[0], cin = (int)cw->shape[1];
+    std::vector<double> s, t;
+    int rc = bn_affine(w, bn_prefix, &s, &t);
+    if (rc) return rc;
+    std::vector<double> wf((size_t)cout * cin * 9);
+    for (int co = 0; co < cout; ++co)
+        for (size_t i = 0; i < (size_t)cin * 9; ++i) wf[(size_t)co * cin * 9 + i] = (double)cw->p[(size_t)co * cin * 9 + i] * s[co];
+    return pack_conv_phase_split(wf, t, cout, cin, bf16, out);
 }
 
 static void free_conv(ConvW* c) {
@@ -710,6 +728,7 @@ struct skb_xtractor {
     DevBuf se_cnt;                // ticket counters of the SE gate kernel (ceil(B / 16) ints, zero between launches)
     DevBuf ovf;                   // fp16 range guard: cumulative count of threads that stored a saturated activation (common.cuh)
     int device = 0;               // the CUDA device the weights and work buffers live on
+    float slope_override = -1.f;  // >= 0: activation slope of the next run_conv (stand-alone operators)
     size_t hw_tab32 = 0, hw_tab64 = 0, hw_pixmeta = 0;   // high-water marks of the plan tables: every cache slot is sized for them
     DevBuf feats, sums, scale, poolX, poolH, poolL, gc, hb, pooled, lin, emb_pre, emb, logits, wave, dbg;
     std::vector<DevBuf> act;      // activation buffers
@@ -1138,6 +1157,7 @@ static int run_conv(skb_xtractor* h, const ConvW& cw, int kind, const Level& Lg,
     const int tile_m = conv_tile_m(cw.ncta);
     p.rows_pad = (tile_m + p.halo + max_shift + 7) / 8 * 8;
     p.act_slope = act == 1 ? 0.f : (act == 2 ? 0.2f : 1.f);
+    if (h->slope_override >= 0.f) p.act_slope = h->slope_override;
     const int* pm = (const int*)h->slot.pixmeta.p;
     // the validity table of `pix_level` decides what is stored as non-zero (TDNN: same geometry, fewer frames per layer)
     p.pix_b = pm + (pix_level ? pix_level->o_pix_b : Lg.o_pix_b);
@@ -1306,7 +1326,7 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
                              next_strides ? &pl.lv[level + 1] : nullptr, st));
         }
         x_is_ps = next_strides;
-        g_launches += 2;
+        g_launches += 3;
         cur ^= 1;
         if (stop && !strcmp(stop, name)) return export_stage(h, buf(level, cur), L, h_max, dbg_out, per_utt, st);
     }
@@ -1325,6 +1345,7 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
         SKB_TRY(launch_broadcast_rows(m.att_b1, B, A, (float*)h->hb.p, st));
     }
     if (F > h->poolA_rows) {
+        if (trace_alloc()) fprintf(stderr, "skb: pooling operand grows %d -> %d frames\n", h->poolA_rows, F);
         packed_free(&h->poolA);
         h->poolA_rows = 0;
         SKB_TRY(packed_alloc_zero(&h->poolA, F + F / 8 + 128, D, st));
@@ -1557,6 +1578,23 @@ int skb_xtractor_reserve(skb_xtractor_t* h, int max_utts, int64_t max_total_samp
     std::vector<int64_t> lengths((size_t)max_utts, each);
     SKB_TRY(build_plan(h, lengths.data(), max_utts, st));
     h->hw_tab32 += h->hw_tab32 / 16; h->hw_tab64 += h->hw_tab64 / 16; h->hw_pixmeta += h->hw_pixmeta / 16;
+    {   // the buffers the forward pass itself sizes on demand (by pooled frames / batch size)
+        const Model& m = h->m;
+        const int B = max_utts, D = m.pool_D;
+        size_t sk = std::max(skinny_gemm_ws_floats(B, m.emb, 2 * D), skinny_gemm_ws_floats(B, std::max(m.n_spk, 1), m.emb));
+        if (is_resnet(m.archi)) {
+            const int F = h->plan.pool_frames;
+            sk = std::max(sk, skinny_gemm_ws_floats(B, m.att_A, 2 * D));
+            if (F > h->poolA_rows) {
+                packed_free(&h->poolA);
+                h->poolA_rows = 0;
+                SKB_TRY(packed_alloc_zero(&h->poolA, F + F / 8 + 128, D, st));
+                h->poolA_rows = h->poolA.rows;
+            }
+            SKB_TRY(gemm_workspace_reserve(F + F / 8 + 128, std::max(m.att_A, 64)));
+        }
+        SKB_TRY(h->skinny_ws.ensure(sk * sizeof(float)));
+    }
     // every slot of the plan cache now, at the high-water sizes: nothing is allocated once the bulk run has started
     while (h->cache.size() <= kPlanCacheEntries) {
         h->cache.emplace_back();
@@ -1629,3 +1667,5 @@ int skb_xtractor_debug_stage(skb_xtractor_t* h, const float* wave_dev, const int
 }
 
 }  // extern "C"
+
+#include "module_ops.cuh"

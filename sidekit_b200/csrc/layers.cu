@@ -403,7 +403,7 @@ __device__ __forceinline__ void se_border_body(const uint16_t* __restrict__ y1, 
 // epilogue accumulates them).  Both only read y1, so they run side by side instead of one after the other (the border
 // kernel alone is latency-bound: 17 us at 10 % issue utilisation).
 template <bool BF16>
-__global__ void __launch_bounds__(256, 4) se_stats_kernel(const uint16_t* __restrict__ y1, long long plane, int G, int p_end, int Wp, int W,
+__global__ void __launch_bounds__(256, 2) se_stats_kernel(const uint16_t* __restrict__ y1, long long plane, int G, int p_end, int Wp, int W,
                                                           const int* __restrict__ utt_row0, const int* __restrict__ utt_count, int C,
                                                           float* __restrict__ brd, int n_border, const int* __restrict__ pix_b,
                                                           const int* __restrict__ span_b, int planes_per_block, int n_span_blocks,
@@ -428,14 +428,10 @@ __global__ void __launch_bounds__(256, 4) se_stats_kernel(const uint16_t* __rest
 // group.  Fixed summation order everywhere -> deterministic.
 constexpr int kSeCh = 8, kSeRows = 9 * kSeCh, kSeUtt = 16;
 template <int Cout>
-__global__ void __launch_bounds__(256) se_mean_partial_kernel(unsigned long long* __restrict__ sums, const float* __restrict__ brd,
+__global__ void __launch_bounds__(256) se_mean_partial_kernel(const unsigned long long* __restrict__ sums, const float* __restrict__ brd,
                                                               int B, int Cin, const float* __restrict__ w2t,
-                                                              float* __restrict__ partial, int* __restrict__ counters,
-                                                              const int* __restrict__ utt_count, const float* __restrict__ b2,
-                                                              const float* __restrict__ fc1 /*[Cout/16][Cout]*/,
-                                                              const float* __restrict__ fc2 /*[Cout][Cout/16]*/, float* __restrict__ scale) {
+                                                              float* __restrict__ partial) {
     __shared__ float sS[kSeUtt][kSeRows];
-    __shared__ int s_last;
     constexpr int n_rg = 256 / Cout;               // row groups: 8 / 4 / 2 / 1 for Cout = 32 / 64 / 128 / 256
     constexpr int RPT = kSeRows / n_rg;            // weight rows per thread: 9 / 18 / 36 / 72
     // this thread's weights first: RPT independent loads whose latency overlaps the shifted-sum phase below
@@ -503,52 +499,49 @@ __global__ void __launch_bounds__(256) se_mean_partial_kernel(unsigned long long
         for (int g = 0; g < n_rg; ++g) a += sRed[(g * kSeUtt + u) * Cout + c];
         partial[((size_t)blockIdx.x * B + b0 + u) * Cout + c] = a;
     }
-    // The CTA that finishes LAST for this group of utterances turns the K-slice partials into the gate (the former
-    // se_fc_kernel: one more dependent launch per block): mean = b2 + (1/N) * sum of the partials in slice order (fixed
-    // order -> deterministic whichever CTA happens to be last); scale = sigmoid(W2 relu(W1 mean))
-    // (sidekit/nnet/res_net.py:272-281).  It also re-zeroes the group's fixed-point channel totals for the next block
-    // (every CTA of the group has read them before taking its ticket) and the ticket counter itself.
-    __threadfence();
+}
+
+// se_fc_kernel: mean = b2 + (1/N) * sum of the K-slice partials (in slice order); scale = sigmoid(W2 relu(W1 mean))
+// (sidekit/nnet/res_net.py:272-281).  One CTA per utterance; re-zeroes the fixed-point channel sums for the next block.
+__global__ void __launch_bounds__(256) se_fc_kernel(unsigned long long* __restrict__ sums, const float* __restrict__ partial, int n_slices,
+                                                    const int* __restrict__ utt_count, int B, int Cin, int Cout,
+                                                    const float* __restrict__ b2, const float* __restrict__ fc1 /*[Cout/16][Cout]*/,
+                                                    const float* __restrict__ fc2 /*[Cout][Cout/16]*/, float* __restrict__ scale) {
+    __shared__ float mean[256];
+    __shared__ float hid[16];
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.x;
+    const float inv_n = 1.f / (float)utt_count[b];
+    for (int c = threadIdx.x; c < Cin; c += blockDim.x) sums[(size_t)b * Cin + c] = 0ull;
+    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+        float a = 0.f;
+        for (int k = 0; k < n_slices; ++k) a += partial[((size_t)k * B + b) * Cout + co];
+        mean[co] = fmaf(a, inv_n, b2[co]);
+    }
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(counters + blockIdx.y, 1) == (int)gridDim.x - 1) ? 1 : 0;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) counters[blockIdx.y] = 0;
-    float* mean = sRed;                 // [Cout]
-    float* hid = sRed + 256;            // [16]
-    const int n_slices = gridDim.x, R = Cout / 16;
+    const int R = Cout / 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int u = 0; u < nu; ++u) {
-        const int b = b0 + u;
-        __syncthreads();
-        for (int c = threadIdx.x; c < Cin; c += blockDim.x) sums[(size_t)b * Cin + c] = 0ull;
-        if (threadIdx.x < Cout) {
-            float a = 0.f;
-            for (int k = 0; k < n_slices; ++k) a += __ldcg(partial + ((size_t)k * B + b) * Cout + threadIdx.x);
-            mean[threadIdx.x] = fmaf(a, 1.f / (float)utt_count[b], b2[threadIdx.x]);
-        }
-        __syncthreads();
-        for (int jj = warp; jj < R; jj += 8) {
-            float a = 0.f;
-            for (int c = lane; c < Cout; c += 32) a = fmaf(fc1[jj * Cout + c], mean[c], a);
-            a = warp_sum(a);
-            if (lane == 0) hid[jj] = fmaxf(a, 0.f);
-        }
-        __syncthreads();
-        if (threadIdx.x < Cout) {
-            float a = 0.f;
-            for (int jj = 0; jj < R; ++jj) a = fmaf(fc2[threadIdx.x * R + jj], hid[jj], a);
-            scale[(size_t)b * Cout + threadIdx.x] = 1.f / (1.f + __expf(-a));
-        }
+    for (int jj = warp; jj < R; jj += blockDim.x >> 5) {
+        float a = 0.f;
+        for (int c = lane; c < Cout; c += 32) a = fmaf(fc1[jj * Cout + c], mean[c], a);
+        a = warp_sum(a);
+        if (lane == 0) hid[jj] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
+        float a = 0.f;
+        for (int jj = 0; jj < R; ++jj) a = fmaf(fc2[c * R + jj], hid[jj], a);
+        scale[(size_t)b * Cout + c] = 1.f / (1.f + __expf(-a));
     }
 }
 
-// The SE gate of one BasicBlock in TWO dependent launches (it used to be four: plane_sum -> se_border -> se_mean_partial
-// -> se_fc, each a few microseconds of work behind a launch gap, 16 times per forward): se_stats_kernel, then
-// se_mean_partial_kernel whose last CTA per utterance group applies the two FC layers.
+// The SE gate of one BasicBlock: se_stats_kernel (border sums and channel totals side by side; they used to be two
+// dependent launches), se_mean_partial_kernel, se_fc_kernel.  A variant whose last-arriving partial CTA also applied the
+// FC layers (one launch less) measured SLOWER (SE time 1.0 -> 1.4 ms per step): one CTA walking 16 utterances' K-slice
+// partials is a serial tail, where se_fc_kernel spreads them over B CTAs (profiles/r02_se_merge.txt).
 // `span_b` == nullptr: the channel totals are already in `sums` (accumulated by conv1's epilogue), only the border sums
-// are computed.  `counters`: ceil(B / 16) zero-initialised ints (self-resetting).
+// are computed.
 int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, long long plane, int G, int p_end, int Wp, int W,
                     const int* utt_row0, const int* utt_count, int B, int Cin, int Cout, const float* w2t, const float* b2,
                     const float* fc1, const float* fc2, float* brd_ws, float* scale, const int* pix_b, const int* span_b,
@@ -578,7 +571,7 @@ int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, lon
     const int n_slices = Cin / kSeCh;
     float* partial = brd_ws + (size_t)B * 8 * Cin;
     dim3 g2(n_slices, (B + kSeUtt - 1) / kSeUtt);
-#define SKB_SE_GATE(C) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<C>, g2, dim3(256), 0, st, sums, (const float*)brd_ws, B, Cin, w2t, partial, counters, utt_count, b2, fc1, fc2, scale))
+#define SKB_SE_GATE(C) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<C>, g2, dim3(256), 0, st, (const unsigned long long*)sums, (const float*)brd_ws, B, Cin, w2t, partial))
     if (Cout == 32) SKB_SE_GATE(32);
     else if (Cout == 64) SKB_SE_GATE(64);
     else if (Cout == 128) SKB_SE_GATE(128);
@@ -589,6 +582,9 @@ int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, lon
     }
 #undef SKB_SE_GATE
     SKB_LAUNCH_CHECK(st);
+    SKB_CUDA_CHECK(launch_pdl(se_fc_kernel, dim3(B), dim3(256), 0, st, sums, (const float*)partial, n_slices, utt_count, B, Cin, Cout, b2, fc1, fc2, scale));
+    SKB_LAUNCH_CHECK(st);
+    (void)counters;
     return SKB_OK;
 }
 

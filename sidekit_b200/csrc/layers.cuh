@@ -68,6 +68,7 @@ int gemm_nt_split(const float* A_dev, int M, int K, const PackedOp& W, const flo
                   cudaStream_t st);
 // same with an A operand that is already packed (hi planes written by the caller, lo planes zero, scale exponent 0)
 int packed_alloc_zero(PackedOp* op, int rows, int D, cudaStream_t st);
+int gemm_workspace_reserve(int M, int K);
 int gemm_packed_a(const PackedOp& A, const PackedOp& W, const float* bias, float alpha, float* C, int ldc, cudaStream_t st);
 
 // conv_umma.cu

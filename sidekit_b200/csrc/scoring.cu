@@ -470,18 +470,26 @@ static thread_local ScoreWorkspace g_ws_dev[kMaxDevices];
 static int ws_ensure(size_t plane_bytes, size_t tmp_bytes) {
     if (!g_ws.stats) SKB_CUDA_CHECK(cudaMalloc(&g_ws.stats, 8 * sizeof(unsigned)));
     if (plane_bytes > g_ws.planes_cap) {
+        if (getenv("SKB_TRACE_ALLOC")) fprintf(stderr, "skb: scoring plane workspace grows %zu -> %zu bytes\n", g_ws.planes_cap, plane_bytes);
         if (g_ws.planes) cudaFree(g_ws.planes);
         g_ws.planes = nullptr; g_ws.planes_cap = 0;
         SKB_CUDA_CHECK(cudaMalloc(&g_ws.planes, plane_bytes));
         g_ws.planes_cap = plane_bytes;
     }
     if (tmp_bytes > g_ws.tmp_cap) {
+        if (getenv("SKB_TRACE_ALLOC")) fprintf(stderr, "skb: scoring scratch grows %zu -> %zu bytes\n", g_ws.tmp_cap, tmp_bytes);
         if (g_ws.tmp) cudaFree(g_ws.tmp);
         g_ws.tmp = nullptr; g_ws.tmp_cap = 0;
         SKB_CUDA_CHECK(cudaMalloc(&g_ws.tmp, tmp_bytes));
         g_ws.tmp_cap = tmp_bytes;
     }
     return SKB_OK;
+}
+
+// pre-size the workspace of gemm_nt_split for A operands of up to M rows x K columns (skb_xtractor_reserve)
+int gemm_workspace_reserve(int M, int K) {
+    const int Dp = (K + kScKChunk - 1) / kScKChunk * kScKChunk, Mp = (M + 127) / 128 * 128;
+    return ws_ensure(2 * (size_t)Dp * Mp * sizeof(uint16_t), 0);
 }
 
 // workspace-backed operand view (slot 0 / 1 of the plane buffer, stats slots in g_ws.stats)

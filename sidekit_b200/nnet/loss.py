@@ -10,7 +10,8 @@ def l2_norm(input, axis=1):
 
 
 class ArcMarginProduct(torch.nn.Module):
-    """Parameter container; ``forward(target=None)`` = s * cos(x, W) is computed by the engine's head GEMM."""
+    """``forward(x, target=None)`` = s * cos(x, W) (sidekit/nnet/loss.py:299-310).  Inside an ``Xtractor`` the engine's
+    head GEMM computes it; on its own it runs ``skb_l2_normalize`` + the split-precision tcgen05 score GEMM."""
 
     def __init__(self, in_features, out_features, s=30.0, m=0.50, easy_margin=False):
         super().__init__()
@@ -25,7 +26,11 @@ class ArcMarginProduct(torch.nn.Module):
     def forward(self, input, target=None):
         if target is not None:
             raise NotImplementedError("training-time margin is out of scope (inference hot path only)")
-        raise RuntimeError("the margin head runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True)")
+        from . import functional as Fn
+        from ..iv_scoring import score_matrix
+        x = Fn.l2_normalize(input)
+        w = Fn.l2_normalize(self.weight.detach().to(x.device))
+        return score_matrix(x, w, alpha=float(self.s), passes=3)
 
 
 class SoftmaxAngularProto(torch.nn.Module):

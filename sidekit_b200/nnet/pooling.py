@@ -23,8 +23,8 @@ class MeanStdPooling(torch.nn.Module):
 
 
 class AttentivePooling(torch.nn.Module):
-    """Attentive statistics pooling; parameters only, the arithmetic runs in the extractor engine
-    (global-context term hoisted to a per-utterance bias, softmax over time, weighted mean / std)."""
+    """Attentive statistics pooling (global-context term hoisted to a per-utterance bias, softmax over time, weighted
+    mean / std)."""
 
     def __init__(self, num_channels, num_freqs=10, attention_channels=128, global_context=False):
         super().__init__()
@@ -40,4 +40,11 @@ class AttentivePooling(torch.nn.Module):
         self.gc = MeanStdPooling()
 
     def forward(self, x):
-        raise RuntimeError("attentive pooling runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True)")
+        """pooling.py:151-171 (eval mode): ``x`` (B, C, T, F) or (B, C*F, T) -> (B, 2*C*F) = [weighted mean ; weighted std].
+        Inside an ``Xtractor`` the fused engine runs this from its plane layout; on its own it goes through
+        ``skb_attentive_pool``."""
+        from . import functional as Fn
+        if len(x.shape) == 4:
+            x = x.permute(0, 1, 3, 2).flatten(start_dim=1, end_dim=2)
+        a = self.attention
+        return Fn.attentive_pool(x, a[0].weight, a[0].bias, a[2], a[4].weight, a[4].bias, self.global_context)

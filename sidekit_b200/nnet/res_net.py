@@ -1,9 +1,14 @@
-"""Parameter containers for the HalfResNet34 trunk with the reference's module tree and state_dict
-keys (sidekit/nnet/res_net.py:258-320, :500-554).  They hold torch Parameters / BatchNorm statistics
-only; the arithmetic (conv + folded BN + ReLU + SE + residual) runs in csrc/conv_umma.cuh and
-csrc/layers.cu, driven by the extractor engine.
+"""The ResNet trunks with the reference's module tree and state_dict keys (sidekit/nnet/res_net.py:186-320, :430-610).
+
+Inside an ``Xtractor`` these modules are parameter containers: the fused engine (csrc/engine.cu) runs the whole trunk
+without leaving its plane layout.  On their own -- ``BasicBlock(...)(x)``, ``SELayer``, ``ResBlock``,
+``PreHalfResNet34()(feats)`` -- their ``forward`` composes the stand-alone operators of ``nnet/functional.py`` (the same
+tcgen05 convolution kernel behind ``skb_conv2d_bn_act``), eval-mode semantics (BatchNorm running statistics), dense fp32
+CUDA tensors in and out.  Training is out of scope.
 """
 import torch
+
+from . import functional as Fn
 
 
 class SELayer(torch.nn.Module):
@@ -14,6 +19,56 @@ class SELayer(torch.nn.Module):
             torch.nn.ReLU(inplace=True),
             torch.nn.Linear(channel // reduction, channel, bias=False),
             torch.nn.Sigmoid())
+
+    def gate(self, mean):
+        """(B, C) channel means -> (B, C) gates (res_net.py:265-270, :280)."""
+        return Fn.se_gate(mean, self.fc[0].weight, self.fc[2].weight)
+
+    def forward(self, x):
+        """res_net.py:272-281: ``x * sigmoid(fc(mean_{h,w}(x)))``."""
+        return Fn.scale_residual_act(x, self.gate(Fn.channel_mean(x)), None, 1.0)
+
+
+class ResBlock(torch.nn.Module):
+    """Pre-activation residual block (sidekit/nnet/res_net.py:186-255): [BN + LeakyReLU unless ``is_first``] -> conv1 ->
+    BN2 -> LeakyReLU -> conv2 -> the SAME BN2 again -> + identity (1x1 conv + BN when the width changes) -> LeakyReLU.
+    Both convolutions carry a bias and take ``stride``; as in the reference only ``stride=1`` yields shapes that can be
+    added to the identity."""
+
+    def __init__(self, in_channels, out_channels, stride, is_first=False):
+        super().__init__()
+        self.is_first = is_first
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.expansion = self.out_channels // self.in_channels
+        self.resample = None
+        if not self.in_channels == self.out_channels:
+            self.resample = torch.nn.Sequential(
+                torch.nn.Conv2d(in_channels=self.in_channels, out_channels=self.out_channels, kernel_size=1),
+                torch.nn.BatchNorm2d(self.in_channels * self.expansion))
+        if not self.is_first:
+            self.batch_norm1 = torch.nn.BatchNorm2d(num_features=self.in_channels)
+        self.activation = torch.nn.LeakyReLU()
+        self.conv1 = torch.nn.Conv2d(in_channels=self.in_channels, out_channels=self.out_channels, kernel_size=(3, 3), stride=stride,
+                                     padding=1, padding_mode='zeros', dilation=1)
+        self.conv2 = torch.nn.Conv2d(in_channels=self.out_channels, out_channels=self.out_channels, stride=stride, kernel_size=(3, 3),
+                                     padding=1, padding_mode='zeros', dilation=1)
+        self.batch_norm2 = torch.nn.BatchNorm2d(num_features=self.out_channels)
+
+    def forward(self, x, compute_dtype="fp16"):
+        slope = self.activation.negative_slope
+        stride = self.conv1.stride
+        pre = None if self.is_first else Fn.bn_affine(self.batch_norm1, x.device)
+        w1, b1 = Fn.fold_conv_bn(self.conv1, self.batch_norm2)
+        w2, b2 = Fn.fold_conv_bn(self.conv2, self.batch_norm2)
+        out = Fn.conv2d_bn_act(x, w1, b1, stride, slope, pre=pre, pre_slope=slope, compute_dtype=compute_dtype)
+        identity = x
+        if not self.expansion == 1:
+            wr, br = Fn.fold_conv_bn(self.resample[0], self.resample[1])
+            identity = Fn.conv2d_bn_act(x, wr, br, 1, 1.0, compute_dtype=compute_dtype)
+        out = Fn.conv2d_bn_act(out, w2, b2, stride, slope, residual=identity, compute_dtype=compute_dtype)
+        Fn.check_overflow(x.device)
+        return out
 
 
 class BasicBlock(torch.nn.Module):
@@ -32,6 +87,23 @@ class BasicBlock(torch.nn.Module):
             self.shortcut = torch.nn.Sequential(
                 torch.nn.Conv2d(in_planes, self.expansion * planes, kernel_size=1, stride=stride, bias=False),
                 torch.nn.BatchNorm2d(self.expansion * planes))
+
+    def forward(self, x, compute_dtype="fp16", check=True):
+        """res_net.py:309-320: ``relu(se(bn2(conv2(relu(bn1(conv1(x)))))) + shortcut(x))``."""
+        stride = self.conv1.stride
+        w1, b1 = Fn.fold_conv_bn(self.conv1, self.bn1)
+        w2, b2 = Fn.fold_conv_bn(self.conv2, self.bn2)
+        y1 = Fn.conv2d_bn_act(x, w1, b1, stride, 0.0, compute_dtype=compute_dtype)
+        y2 = Fn.conv2d_bn_act(y1, w2, b2, 1, 1.0, compute_dtype=compute_dtype)
+        scale = self.se.gate(Fn.channel_mean(y2))
+        res = x
+        if len(self.shortcut):
+            ws, bs = Fn.fold_conv_bn(self.shortcut[0], self.shortcut[1])
+            res = Fn.conv2d_bn_act(x, ws, bs, stride, 1.0, compute_dtype=compute_dtype)
+        out = Fn.scale_residual_act(y2, scale, res, 0.0)
+        if check:
+            Fn.check_overflow(x.device)
+        return out
 
 
 class PreHalfResNet34(torch.nn.Module):
@@ -56,9 +128,18 @@ class PreHalfResNet34(torch.nn.Module):
             self.in_planes = planes * block.expansion
         return torch.nn.Sequential(*layers)
 
-    def forward(self, x):
-        raise RuntimeError("the trunk runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True) "
-                           "(Xtractor.debug_stage exposes per-block activations for tests)")
+    def forward(self, x, compute_dtype="fp16"):
+        """res_net.py:539-554 (eval mode): (B, F, T) features -> (B, 1, T, F) -> stem -> layers; returns (B, C, T', F')."""
+        if len(x.shape) == 3:
+            x = x.unsqueeze(1).permute(0, 1, 3, 2)
+        w, b = Fn.fold_conv_bn(self.conv1, self.bn1)
+        x = Fn.conv2d_bn_act(x.contiguous(), w, b, 1, 0.0, compute_dtype=compute_dtype)
+        for name, layer in self.named_children():
+            if name.startswith("layer"):
+                for block in layer:
+                    x = block(x, compute_dtype=compute_dtype, check=False)
+        Fn.check_overflow(x.device)
+        return x
 
 
 class PreResNet34(torch.nn.Module):
@@ -83,9 +164,7 @@ class PreResNet34(torch.nn.Module):
         self.layer7 = self._make_layer(block, 256, num_blocks[5], stride=1)     # num_blocks[5] as in the reference (:455)
 
     _make_layer = PreHalfResNet34._make_layer
-
-    def forward(self, x):
-        raise RuntimeError("the trunk runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True)")
+    forward = PreHalfResNet34.forward
 
 
 class PreFastResNet34(torch.nn.Module):
@@ -109,4 +188,5 @@ class PreFastResNet34(torch.nn.Module):
     _make_layer = PreHalfResNet34._make_layer
 
     def forward(self, x):
-        raise RuntimeError("the trunk runs inside the fused CUDA engine: call Xtractor.forward(x, is_eval=True)")
+        raise RuntimeError("the 7x7 stride-(1, 2) stem only exists inside the fused CUDA engine: call "
+                           "Xtractor('fastresnet34').forward(x, is_eval=True)")

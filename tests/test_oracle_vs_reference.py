@@ -49,6 +49,26 @@ def test_resblock_is_unreachable_in_the_reference():
             Xtractor(10, dict(base, segmental=seg))
 
 
+def test_resblock_restatement_matches_the_reference_class():
+    """The module itself IS constructible (only the Xtractor branch that would use it is not): the oracle's `res_block`
+    follows the reference's `ResBlock.forward` (res_net.py:229-255) for the identity and the widening variant."""
+    from oracle import ref_import, extract_ref as R
+    from sidekit_b200 import synth
+    ref_import.import_reference()
+    from sidekit.nnet.res_net import ResBlock
+    for cin, cout, first in ((32, 32, False), (32, 64, False), (16, 16, True)):
+        torch.manual_seed(cin + cout)
+        blk = ResBlock(cin, cout, 1, is_first=first).eval()
+        sd = blk.state_dict()
+        synth.fill_state_dict(sd, 3)
+        blk.load_state_dict(sd)
+        x = torch.randn(2, cin, 9, 7)
+        with torch.no_grad():
+            ref = blk(x.clone())
+        got = R.res_block({"b." + k: v for k, v in sd.items()}, "b", x, is_first=first)
+        assert (got - ref).abs().max().item() < 1e-5
+
+
 def test_scoring_kat_recorded_from_reference():
     """Re-derive SURVEY.md Appendix B from the unmodified reference and compare with tests/kat.py and the oracle."""
     from oracle import ref_import

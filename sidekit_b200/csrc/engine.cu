@@ -725,7 +725,6 @@ struct skb_xtractor {
     cudaStream_t last_stream = nullptr;
     bool have_last_stream = false;
     DevBuf brd, cmvn, cmvn_part, skinny_ws;
-    DevBuf se_cnt;                // ticket counters of the SE gate kernel (ceil(B / 16) ints, zero between launches)
     DevBuf ovf;                   // fp16 range guard: cumulative count of threads that stored a saturated activation (common.cuh)
     int device = 0;               // the CUDA device the weights and work buffers live on
     float slope_override = -1.f;  // >= 0: activation slope of the next run_conv (stand-alone operators)
@@ -967,9 +966,7 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
         if ((rc = h->sums.ensure((size_t)B * Cmax * sizeof(unsigned long long)))) return rc;
         if ((rc = h->scale.ensure((size_t)B * Cmax * sizeof(float)))) return rc;
         if ((rc = h->brd.ensure((size_t)B * (8 + 36) * Cmax * sizeof(float)))) return rc;   // border sums + K-slice partial means
-        bool grew = false;
-        if ((rc = h->se_cnt.ensure((size_t)(B / 16 + 2) * sizeof(int), &grew))) return rc;
-        if (grew) SKB_CUDA_CHECK(cudaMemsetAsync(h->se_cnt.p, 0, h->se_cnt.cap, st));
+
     }
     if (is_resnet(m.archi)) {
         // The one guard pixel that IS read into a kept accumulator row: tap (-1, -1) of the first pixel of the first
@@ -1313,10 +1310,14 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
             // SE scales from conv2's INPUT (linearity of the convolution): one bandwidth-bound pass over y1 + small kernels
             ProfScope ps(PROF_SE, st);
             const int* pm = (const int*)h->slot.pixmeta.p;
-            SKB_TRY(launch_se_scale(m.bf16, (unsigned long long*)h->sums.p, y1, L.plane, L.G, L.p_end, L.Wp, L.W, d32 + L.o_utt_row0,
+            // Measured and rejected in round 2 (profiles/r02_se_merge.txt): border sums + channel totals in one launch, and the FC
+            // layers done by the last-arriving partial-mean CTA -- fewer launches, but both variants were slower.
+            if (!sums_in_conv1)
+                SKB_TRY(launch_plane_sum(m.bf16, y1, L.plane, L.G, L.p_end, pm + L.o_pix_b, pm + L.o_span, bw.C,
+                                         (unsigned long long*)h->sums.p, st));
+            SKB_TRY(launch_se_scale(m.bf16, (unsigned long long*)h->sums.p, y1, L.plane, L.G, L.Wp, L.W, d32 + L.o_utt_row0,
                                     d32 + L.o_utt_count, B, bw.C, bw.C, bw.w2t, bw.conv2.bias, bw.se_w1, bw.se_w2,
-                                    (float*)h->brd.p, (float*)h->scale.p, pm + L.o_pix_b, sums_in_conv1 ? nullptr : pm + L.o_span,
-                                    (int*)h->se_cnt.p, st));
+                                    (float*)h->brd.p, (float*)h->scale.p, st));
         }
         {
             // conv2 with the fused SE tail: out = relu(bn2(conv2(y1)) * scale + residual)
@@ -1326,7 +1327,7 @@ static int forward_hr34(skb_xtractor* h, const float* wave, int norm_embedding, 
                              next_strides ? &pl.lv[level + 1] : nullptr, st));
         }
         x_is_ps = next_strides;
-        g_launches += 3;
+        g_launches += 4;
         cur ^= 1;
         if (stop && !strcmp(stop, name)) return export_stage(h, buf(level, cur), L, h_max, dbg_out, per_utt, st);
     }
@@ -1516,7 +1517,7 @@ void skb_xtractor_destroy(skb_xtractor_t* h) {
     h->slot.release();
     DevBuf* bufs[] = {&h->feats, &h->sums, &h->scale, &h->poolX, &h->poolH, &h->poolL, &h->gc, &h->hb,
                       &h->pooled, &h->lin, &h->emb_pre, &h->emb, &h->logits, &h->wave, &h->dbg, &h->brd, &h->cmvn,
-                      &h->cmvn_part, &h->skinny_ws, &h->ovf, &h->se_cnt};
+                      &h->cmvn_part, &h->skinny_ws, &h->ovf};
     for (auto* b : bufs) b->release();
     for (auto& b : h->act) b.release();
     for (auto& c : h->cache) c.slot.release();

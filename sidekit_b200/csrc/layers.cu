@@ -5,8 +5,6 @@
 #include "common.cuh"
 #include "layers.cuh"
 
-#include <algorithm>
-
 namespace skb {
 
 // ----------------------------------------------------------------------------- stem: 3x3 conv 1->32 + BN + ReLU
@@ -254,16 +252,18 @@ __device__ __forceinline__ long long warp_sum8_i64(const long long (&t)[8], int 
 }
 
 template <bool BF16>
-__device__ __forceinline__ void plane_sum_body(const uint16_t* __restrict__ act, long long plane, int G, int p_end,
-                                               const int* __restrict__ pix_b, const int* __restrict__ span_b, int C,
-                                               int planes_per_block, unsigned long long* __restrict__ sums, int span_block, int plane_block) {
+__global__ void __launch_bounds__(256, 4) plane_sum_kernel(const uint16_t* __restrict__ act, long long plane, int G, int p_end,
+                                                        const int* __restrict__ pix_b, const int* __restrict__ span_b, int C,
+                                                        int planes_per_block, unsigned long long* __restrict__ sums) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int span = span_block * 8 + warp;
+    const int span = blockIdx.x * 8 + warp;
     const int base = G + span * kSpanPix;
     if (base >= p_end) return;
     const int sb = __ldg(span_b + span);
     if (sb == -1) return;                                  // pad pixels only: all zeros
-    const int j0 = plane_block * planes_per_block;
+    const int j0 = blockIdx.y * planes_per_block;
     int pb[8];                                             // per-pixel utterances, only needed when the span is mixed
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -335,13 +335,33 @@ int launch_span_table(const int* pix_b, int n_pix, int* span_b, cudaStream_t st)
     return SKB_OK;
 }
 
+int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, const int* span_b, int C,
+                     unsigned long long* sums, cudaStream_t st) {
+    const int n = p_end - G;
+    const int n_spans = span_table_size(n);
+    const int chunks = C / 8;
+    const int ppb = chunks >= 16 ? 4 : (chunks >= 8 ? 2 : 1);      // keep >= ~4 waves of CTAs on the small levels
+    dim3 grid((n_spans + 7) / 8, chunks / ppb);
+    if (bf16)
+        SKB_CUDA_CHECK(launch_pdl(plane_sum_kernel<true>, grid, dim3(256), 0, st, act, plane, G, p_end, pix_b, span_b, C, ppb, sums));
+    else
+        SKB_CUDA_CHECK(launch_pdl(plane_sum_kernel<false>, grid, dim3(256), 0, st, act, plane, G, p_end, pix_b, span_b, C, ppb, sums));
+    SKB_LAUNCH_CHECK(st);
+    return SKB_OK;
+}
+
 // se_border_kernel: sums of the first / last row and column of y1 and its four corner pixels, per (utterance, channel).
 // One CTA per (utterance, 8-channel chunk); threads stride over the border pixels with 16-byte loads; the block
 // reduction runs in a fixed order, so the result is deterministic.  brd layout: [B][8 kinds][C].
 template <bool BF16>
-__device__ __forceinline__ void se_border_body(const uint16_t* __restrict__ y1, long long plane, int G, int Wp, int W,
-                                               const int* __restrict__ utt_row0, const int* __restrict__ utt_count, int C,
-                                               float* __restrict__ brd, int b, int j, float (*part)[33], float (*part2)[32]) {
+__global__ void __launch_bounds__(256) se_border_kernel(const uint16_t* __restrict__ y1, long long plane, int G, int Wp, int W,
+                                                        const int* __restrict__ utt_row0, const int* __restrict__ utt_count, int C,
+                                                        float* __restrict__ brd) {
+    __shared__ float part[256][33];
+    __shared__ float part2[8][32];
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.x, j = blockIdx.y;
     const int H = utt_count[b] / W;
     const uint16_t* base = y1 + ((size_t)j * plane + G + (size_t)utt_row0[b] * Wp) * 8;     // pixel (0, 0) of chunk j
     float acc[32];                                  // [row0 | rowL | col0 | colL][8 channels]
@@ -395,30 +415,6 @@ __device__ __forceinline__ void se_border_body(const uint16_t* __restrict__ y1, 
         const int hh = (k >> 1) ? H - 1 : 0, ww = (k & 1) ? W - 1 : 0;
         const uint16_t u = base[((size_t)hh * Wp + ww) * 8 + e];
         brd[((size_t)b * 8 + 4 + k) * C + j * 8 + e] = unpack2<BF16>((uint32_t)u).x;
-    }
-}
-
-// One launch for everything the SE gate needs from y1 itself: blocks [0, n_border) = border sums (one CTA per utterance and
-// 8-channel chunk), the rest = the fixed-point channel totals (plane_sum; none on the 32-channel layers, whose conv1
-// epilogue accumulates them).  Both only read y1, so they run side by side instead of one after the other (the border
-// kernel alone is latency-bound: 17 us at 10 % issue utilisation).
-template <bool BF16>
-__global__ void __launch_bounds__(256, 2) se_stats_kernel(const uint16_t* __restrict__ y1, long long plane, int G, int p_end, int Wp, int W,
-                                                          const int* __restrict__ utt_row0, const int* __restrict__ utt_count, int C,
-                                                          float* __restrict__ brd, int n_border, const int* __restrict__ pix_b,
-                                                          const int* __restrict__ span_b, int planes_per_block, int n_span_blocks,
-                                                          unsigned long long* __restrict__ sums) {
-    __shared__ float part[256][33];
-    __shared__ float part2[8][32];
-    pdl_trigger();
-    pdl_wait();
-    const int blk = blockIdx.x;
-    if (blk < n_border) {
-        const int chunks = C >> 3;
-        se_border_body<BF16>(y1, plane, G, Wp, W, utt_row0, utt_count, C, brd, blk / chunks, blk % chunks, part, part2);
-    } else {
-        const int r = blk - n_border;
-        plane_sum_body<BF16>(y1, plane, G, p_end, pix_b, span_b, C, planes_per_block, sums, r % n_span_blocks, r / n_span_blocks);
     }
 }
 
@@ -536,55 +532,34 @@ __global__ void __launch_bounds__(256) se_fc_kernel(unsigned long long* __restri
     }
 }
 
-// The SE gate of one BasicBlock: se_stats_kernel (border sums and channel totals side by side; they used to be two
-// dependent launches), se_mean_partial_kernel, se_fc_kernel.  A variant whose last-arriving partial CTA also applied the
-// FC layers (one launch less) measured SLOWER (SE time 1.0 -> 1.4 ms per step): one CTA walking 16 utterances' K-slice
-// partials is a serial tail, where se_fc_kernel spreads them over B CTAs (profiles/r02_se_merge.txt).
-// `span_b` == nullptr: the channel totals are already in `sums` (accumulated by conv1's epilogue), only the border sums
-// are computed.
-int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, long long plane, int G, int p_end, int Wp, int W,
+int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, long long plane, int G, int Wp, int W,
                     const int* utt_row0, const int* utt_count, int B, int Cin, int Cout, const float* w2t, const float* b2,
-                    const float* fc1, const float* fc2, float* brd_ws, float* scale, const int* pix_b, const int* span_b,
-                    int* counters, cudaStream_t st) {
+                    const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st) {
     // brd_ws: [B][8][Cin] border sums, followed by [n_slices][B][Cout] partial means
     if (Cout > 256 || 256 % Cout != 0) {
         set_last_error(__FILE__, __LINE__, "squeeze-excitation: channel count must divide 256");
         return SKB_ERR_ARG;
     }
-    const int chunks = Cin / 8;
-    const int n_border = B * chunks;
-    int n_span_blocks = 0, ppb = 1, n_sum_blocks = 0;
-    if (span_b != nullptr) {
-        const int n_spans = span_table_size(p_end - G);
-        ppb = chunks >= 16 ? 4 : (chunks >= 8 ? 2 : 1);      // keep >= ~4 waves of CTAs on the small levels
-        n_span_blocks = (n_spans + 7) / 8;
-        n_sum_blocks = n_span_blocks * (chunks / ppb);
-    }
-    const dim3 grid(n_border + n_sum_blocks);
+    dim3 grid(B, Cin / 8);
     if (bf16)
-        SKB_CUDA_CHECK(launch_pdl(se_stats_kernel<true>, grid, dim3(256), 0, st, y1, plane, G, p_end, Wp, W, utt_row0, utt_count, Cin,
-                                  brd_ws, n_border, pix_b, span_b, ppb, std::max(n_span_blocks, 1), sums));
+        SKB_CUDA_CHECK(launch_pdl(se_border_kernel<true>, grid, dim3(256), 0, st, y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws));
     else
-        SKB_CUDA_CHECK(launch_pdl(se_stats_kernel<false>, grid, dim3(256), 0, st, y1, plane, G, p_end, Wp, W, utt_row0, utt_count, Cin,
-                                  brd_ws, n_border, pix_b, span_b, ppb, std::max(n_span_blocks, 1), sums));
+        SKB_CUDA_CHECK(launch_pdl(se_border_kernel<false>, grid, dim3(256), 0, st, y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws));
     SKB_LAUNCH_CHECK(st);
     const int n_slices = Cin / kSeCh;
     float* partial = brd_ws + (size_t)B * 8 * Cin;
     dim3 g2(n_slices, (B + kSeUtt - 1) / kSeUtt);
-#define SKB_SE_GATE(C) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<C>, g2, dim3(256), 0, st, (const unsigned long long*)sums, (const float*)brd_ws, B, Cin, w2t, partial))
-    if (Cout == 32) SKB_SE_GATE(32);
-    else if (Cout == 64) SKB_SE_GATE(64);
-    else if (Cout == 128) SKB_SE_GATE(128);
-    else if (Cout == 256) SKB_SE_GATE(256);
+    if (Cout == 32) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<32>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
+    else if (Cout == 64) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<64>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
+    else if (Cout == 128) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<128>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
+    else if (Cout == 256) SKB_CUDA_CHECK(launch_pdl(se_mean_partial_kernel<256>, g2, dim3(256), 0, st, sums, brd_ws, B, Cin, w2t, partial));
     else {
         set_last_error(__FILE__, __LINE__, "squeeze-excitation: unsupported channel count");
         return SKB_ERR_ARG;
     }
-#undef SKB_SE_GATE
     SKB_LAUNCH_CHECK(st);
-    SKB_CUDA_CHECK(launch_pdl(se_fc_kernel, dim3(B), dim3(256), 0, st, sums, (const float*)partial, n_slices, utt_count, B, Cin, Cout, b2, fc1, fc2, scale));
+    SKB_CUDA_CHECK(launch_pdl(se_fc_kernel, dim3(B), dim3(256), 0, st, sums, partial, n_slices, utt_count, B, Cin, Cout, b2, fc1, fc2, scale));
     SKB_LAUNCH_CHECK(st);
-    (void)counters;
     return SKB_OK;
 }
 

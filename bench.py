@@ -552,6 +552,42 @@ def run_extras(args, device, peaks, dist_on, rank, world, lib):
                                             traffic=load_traffic("score_gemm_kernel") if world == 1 else None,
                                             tensor_tflops=2.0 * rows * Nt * D * args.steps / (ms / 1e3) / 1e12,
                                             tensor_frac_sustained=2.0 * rows * Nt * D * args.steps / (ms / 1e3) / 1e12 / peaks["tf_sustained"])}
+    if world == 1:
+        # consumers that keep the matrix out of HBM: (i) trial-list mode -- only the trials of a sparse mask
+        # are written (config-5 density: 37 720 trials per 4 708^2 pairs), the GEMM is then bound by the tensor pipe / the L2
+        # operand stream; (ii) float16 output -- half the write
+        from sidekit_b200.iv_scoring import TrialIndex, score_trials
+        gm = torch.Generator(device=device).manual_seed(99)
+        mask = torch.rand((Ne, Nt), device=device, generator=gm) < (37720.0 / 4708.0 ** 2)
+        t0 = time.perf_counter()
+        tidx = TrialIndex(mask, device)
+        torch.cuda.synchronize()
+        tidx_ms = (time.perf_counter() - t0) * 1e3
+        del mask
+        T_full = T_all if T_all.shape[0] == Nt else T_all[:Nt]
+        gt = lambda i: score_trials(E, T_full, tidx, r, q, cst=0.5, alpha=1.0, passes=0)
+        for i in range(3):
+            gt(i)
+        ms_t = timed(gt, args.steps, False)
+        tf = 2.0 * Ne * Nt * D * args.steps / (ms_t / 1e3) / 1e12
+        out["plda_20k_trial_list"] = {"metric": "trials_per_second", "value": float(Ne) * Nt * args.steps / (ms_t / 1e3), "unit": "trials/s",
+                                      "workload": "the same 20k x 20k GEMM, only the %d trials of a sparse mask written (row-major, as "
+                                                  "scoremat[trialmask]); trial index built once in %.2f ms" % (tidx.n_trials, tidx_ms),
+                                      "ms_per_step": ms_t / args.steps,
+                                      "roofline": roofline("score_gemm_kernel, trial-list epilogue (+ operand packing)", "tensor", tf, peaks)}
+        out16 = torch.empty((rows, Nt), dtype=torch.float16, device=device)
+        gh = lambda i: sk.score_matrix(E, Tp, r, q, cst=0.5, alpha=1.0, passes=0, out=out16)
+        for i in range(3):
+            gh(i)
+        ms_h = timed(gh, args.steps, False)
+        gbs_h = (rows * Nt * 2 + 4 * (rows + Nt) * D) * args.steps / (ms_h / 1e3) / 1e9
+        out["plda_20k_fp16_out"] = {"metric": "trials_per_second", "value": trials / (ms_h / 1e3), "unit": "trials/s",
+                                    "workload": "the same 20k x 20k scoring with a float16 score matrix (2 bytes per trial)",
+                                    "ms_per_step": ms_h / args.steps,
+                                    "roofline": roofline("score_gemm_kernel, float16 epilogue", "hbm", gbs_h, peaks,
+                                                         tensor_tflops=2.0 * rows * Nt * D * args.steps / (ms_h / 1e3) / 1e12,
+                                                         tensor_frac_sustained=2.0 * rows * Nt * D * args.steps / (ms_h / 1e3) / 1e12 / peaks["tf_sustained"])}
+        del out16, tidx
     del outm, Tp, T_all
     # ---- as-norm across ranks (config 5 shape: N = 4708 unit-norm embeddings, cohort 7205): top-200 cohort statistics of
     # this rank's rows, ONE all-gather of the (N,) mean / std vectors, then the rank's rows of the normalised matrix

@@ -137,7 +137,8 @@ int skb_meanstd_pool(const float* x_dev, int n_utt, int D, int T, float* out_dev
  * E_dev (Ne, D), T_dev (Nt, D) fp32 row-major; rowterm/colterm may be NULL (treated as 0).
  * passes: 1 = single 16-bit pass, 3 = split (hi*hi + hi*lo + lo*hi) for fp32-class accuracy,
  * 0 = choose from the operand magnitudes so that the absolute error stays below 2.5e-4.
- * out_dtype: 0 = float32, 1 = float64.  out_dev is (Ne, Nt) row-major with leading dimension ld_out. */
+ * out_dtype: 0 = float32, 1 = float64, 2 = float16 (halves the HBM-bound write; 11-bit mantissa: meant for cosine-range
+ * scores).  out_dev is (Ne, Nt) row-major with leading dimension ld_out. */
 int skb_score_gemm(const float* E_dev, const float* T_dev, int Ne, int Nt, int D, const float* rowterm_dev,
                    const float* colterm_dev, double cst, double alpha, int passes, int out_dtype, void* out_dev,
                    int64_t ld_out, void* stream);
@@ -151,6 +152,19 @@ void skb_packed_destroy(skb_packed_t* p);
 int skb_score_gemm_packed(const float* E_dev, int Ne, const skb_packed_t* T, const float* rowterm_dev,
                           const float* colterm_dev, double cst, double alpha, int passes, int out_dtype, void* out_dev,
                           int64_t ld_out, void* stream);
+
+/* Trial-list mode: only the trials a mask selects are scored INTO MEMORY, compacted in row-major order -- exactly what the
+ * reference extracts with `scores.scoremat[ndx.trialmask]` (sidekit/nnet/xvector.py:243-245) -- so the Ne x Nt matrix never
+ * reaches HBM and the GEMM is no longer write-bound.  skb_trial_index_create turns a (Ne, Nt) byte mask (non-zero = trial,
+ * leading dimension ld_mask, device) into bit words and prefix counts and returns the number of trials;
+ * skb_score_gemm_trials writes out_trials_dev[k] = score of the k-th trial (float32), same formula as skb_score_gemm. */
+typedef struct skb_trial_index skb_trial_index_t;
+int skb_trial_index_create(const uint8_t* mask_dev, int Ne, int Nt, int64_t ld_mask, skb_trial_index_t** out, int64_t* n_trials,
+                           void* stream);
+void skb_trial_index_destroy(skb_trial_index_t* t);
+int skb_score_gemm_trials(const float* E_dev, const float* T_dev, int Ne, int Nt, int D, const float* rowterm_dev,
+                          const float* colterm_dev, double cst, double alpha, int passes, const skb_trial_index_t* trials,
+                          float* out_trials_dev, void* stream);
 
 /* dst[i] = (double)src[i]: the float64 view of a float32 score matrix, produced chunk by chunk on its way to the host
  * (sidekit's PLDA / two-covariance scorers return float64, iv_scoring.py:205, :462). */

@@ -56,6 +56,7 @@ int launch_pack_frames(bool bf16, const float* X, int C_src, int C_dst, int n_ro
                        const float2* cmvn, uint16_t* out, long long plane, int G, cudaStream_t st);
 
 // scoring.cu: split-precision tcgen05 GEMM on packed fp16 operands (also used for the dense layers of the extractor)
+struct TrialTables;
 struct PackedOp {
     uint16_t* hi = nullptr;      // [rows_pad/128][Dp/8][128][8] fp16 high parts (lo follows in the same allocation)
     uint16_t* lo = nullptr;

@@ -124,9 +124,18 @@ struct ScoreParams {
     int mul_scaled;                           // 1: ra / ca are also divided by the operand scales
     void* out;
     long long ld_out;
-    int out_f64;
+    int out_f64;                              // == (out_mode == 1); kept for the epilogue's existing tests
+    int out_mode;                             // 0 = float32 matrix, 1 = float64 matrix, 2 = float16 matrix, 3 = trial list
+    // trial-list mode: only the trials of a mask are written, compacted in row-major order (what the reference selects with
+    // scoremat[trialmask], sidekit/nnet/xvector.py:243-245): bit j of mask_words[row][w] = trial (row, 32 w + j),
+    // word_off[row][w] = number of trials before (row, 32 w).  out = float32 [n_trials].
+    const uint32_t* mask_words;
+    const uint32_t* word_off;
+    int mask_ld;
     int tiles_total, n_ntiles;
 };
+
+struct TrialTables { const uint32_t* words; const uint32_t* offsets; int ld, Ne, Nt; };
 
 constexpr int kScEpiWarps = 8;
 constexpr int kScThreads = (2 + kScEpiWarps) * 32;   // warps: 0 producer, 1 MMA, 2..9 epilogue (2 per TMEM quadrant)
@@ -279,9 +288,11 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;                  // which two of the four 32-column blocks
         float* stg = reinterpret_cast<float*>(stage_smem) + (warp - 2) * 32 * 36;   // warp-private [32][36] transpose buffer
-        const int esz = p.out_f64 ? 8 : 4;
-        const bool vec_ok = ((p.ld_out * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
-                            (p.q == nullptr || (reinterpret_cast<uintptr_t>(p.q) & 15) == 0);
+        const int esz = p.out_mode == 1 ? 8 : (p.out_mode == 2 ? 2 : 4);
+        const bool out_ok = p.out_mode == 3 ? true
+                          : p.out_mode == 2 ? ((p.ld_out * 2) % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 7) == 0)
+                                            : ((p.ld_out * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+        const bool vec_ok = out_ok && (p.q == nullptr || (reinterpret_cast<uintptr_t>(p.q) & 15) == 0);
         const float inv_scale = ldexpf(1.f, -(p.expE[0] + p.expT[0]));
         const float a0 = p.a0 * inv_scale;
         const float mscale = p.mul_scaled ? inv_scale : 1.f;
@@ -338,7 +349,36 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                     const int rs = lane >> 3;
                     float4 qv = qpre[cbi];
                     qv.x *= p.rq_scale; qv.y *= p.rq_scale; qv.z *= p.rq_scale; qv.w *= p.rq_scale;
-                    if (p.out_f64) {
+                    if (p.out_mode == 3) {
+                        // trial list: this lane's four columns of every fourth row; the eight lanes of a row write one
+                        // contiguous run of the compacted output.  A sparse mask writes (almost) nothing: the kernel
+                        // is then bound by the tensor pipe / the operand stream, not by HBM writes.
+                        float* o = reinterpret_cast<float*>(p.out);
+                        const uint32_t lt = (1u << c4) - 1u;
+                        const size_t wcol = (size_t)(col0 >> 5);
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const size_t widx = (size_t)(row0 + it * 4 + rs) * p.mask_ld + wcol;
+                            const uint32_t word = __ldg(p.mask_words + widx);
+                            const uint32_t m4 = (word >> c4) & 0xFu;
+                            if (m4 == 0u) continue;
+                            const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
+                            const float xs[4] = {x.x + qv.x, x.y + qv.y, x.z + qv.z, x.w + qv.w};
+                            size_t dst = (size_t)__ldg(p.word_off + widx) + __popc(word & lt);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (m4 & (1u << e)) o[dst++] = xs[e];
+                        }
+                    } else if (p.out_mode == 2) {
+                        __half* o = reinterpret_cast<__half*>(p.out) + (size_t)(row0 + rs) * p.ld_out + col0 + c4;
+                        const size_t step = (size_t)4 * p.ld_out;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it, o += step) {
+                            const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
+                            const __half2 h0 = __floats2half2_rn(x.x + qv.x, x.y + qv.y), h1 = __floats2half2_rn(x.z + qv.z, x.w + qv.w);
+                            __stcs(reinterpret_cast<uint2*>(o), make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1)));
+                        }
+                    } else if (p.out_f64) {
                         double* o = reinterpret_cast<double*>(p.out) + (size_t)(row0 + rs) * p.ld_out + col0 + c4;
                         const size_t step = (size_t)4 * p.ld_out;
 #pragma unroll
@@ -377,6 +417,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                 const float ca = (p.ca && col_ok) ? __ldg(p.ca + col) * mscale : 0.f;
                 float* o = reinterpret_cast<float*>(p.out) + (size_t)row0 * p.ld_out + col;
                 double* od = reinterpret_cast<double*>(p.out) + (size_t)row0 * p.ld_out + col;
+                __half* oh = reinterpret_cast<__half*>(p.out) + (size_t)row0 * p.ld_out + col;
 #pragma unroll 4
                 for (int r = 0; r < 32; ++r) {
                     float sv = stg[r * 36 + lane];
@@ -386,7 +427,13 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                     }
                     sv += qq;
                     if (r < n_rows && col_ok) {
-                        if (p.out_f64) od[(size_t)r * p.ld_out] = (double)sv;
+                        if (p.out_mode == 3) {
+                            const size_t widx = (size_t)(row0 + r) * p.mask_ld + (size_t)(col0 >> 5);
+                            const uint32_t word = __ldg(p.mask_words + widx);
+                            if (word & (1u << lane))
+                                reinterpret_cast<float*>(p.out)[(size_t)__ldg(p.word_off + widx) + __popc(word & ((1u << lane) - 1u))] = sv;
+                        } else if (p.out_mode == 2) oh[(size_t)r * p.ld_out] = __float2half_rn(sv);
+                        else if (p.out_f64) od[(size_t)r * p.ld_out] = (double)sv;
                         else o[(size_t)r * p.ld_out] = sv;
                     }
                 }
@@ -522,9 +569,10 @@ static int launch_score(const ScoreParams& p, int grid, cudaStream_t st) {
 
 // out = acc * (ra_i + ca_j + a0) + rq_scale * (r_i + q_j) + c0 on two packed operands
 int gemm_packed(const PackedOp& E, const PackedOp& T, const float* ra, const float* ca, float a0, const float* r, const float* q,
-                float c0, float rq_scale, float abs_alpha_for_auto, int passes, int out_f64, void* out, long long ld_out,
-                cudaStream_t st) {
-    if (E.Dp != T.Dp || !out || ld_out < T.rows || (passes != 0 && passes != 1 && passes != 3)) {
+                float c0, float rq_scale, float abs_alpha_for_auto, int passes, int out_mode, void* out, long long ld_out,
+                cudaStream_t st, const TrialTables* trials) {
+    if (E.Dp != T.Dp || !out || (out_mode != 3 && ld_out < T.rows) || (passes != 0 && passes != 1 && passes != 3) || out_mode < 0 ||
+        out_mode > 3 || (out_mode == 3 && (trials == nullptr || trials->Ne != E.rows || trials->Nt != T.rows || ca != nullptr))) {
         set_last_error(__FILE__, __LINE__, "gemm_packed: bad arguments");
         return SKB_ERR_ARG;
     }
@@ -537,7 +585,10 @@ int gemm_packed(const PackedOp& E, const PackedOp& T, const float* ra, const flo
     p.abs_alpha = abs_alpha_for_auto; p.passes_req = passes;
     p.ra = ra; p.ca = ca; p.r = r; p.q = q; p.a0 = a0; p.c0 = c0; p.rq_scale = rq_scale;
     p.mul_scaled = 1;
-    p.out = out; p.ld_out = ld_out; p.out_f64 = out_f64;
+    p.out = out; p.ld_out = ld_out; p.out_f64 = out_mode == 1 ? 1 : 0; p.out_mode = out_mode;
+    p.mask_words = trials ? trials->words : nullptr;
+    p.word_off = trials ? trials->offsets : nullptr;
+    p.mask_ld = trials ? trials->ld : 0;
     p.n_ntiles = T.rows_pad / 128;
     p.tiles_total = (E.rows_pad / 128) * p.n_ntiles;
     const int grid = std::min(p.tiles_total, kNumSMs);
@@ -565,7 +616,7 @@ int gemm_nt_split(const float* A_dev, int M, int K, const PackedOp& W, const flo
     PackedOp a;
     ws_operand(&a, M, K, 0, 0);
     if ((rc = packed_fill(A_dev, &a, nullptr, nullptr, st))) return rc;
-    return gemm_packed(a, W, nullptr, nullptr, alpha, nullptr, bias, 0.f, 1.f, 1.f, 3, 0, C, ldc, st);
+    return gemm_packed(a, W, nullptr, nullptr, alpha, nullptr, bias, 0.f, 1.f, 1.f, 3, 0, C, ldc, st, nullptr);
 }
 
 // An operand whose hi planes the caller fills itself (16-bit activations gathered straight into the packed layout):
@@ -579,14 +630,14 @@ int packed_alloc_zero(PackedOp* op, int rows, int D, cudaStream_t st) {
 }
 
 int gemm_packed_a(const PackedOp& A, const PackedOp& W, const float* bias, float alpha, float* C, int ldc, cudaStream_t st) {
-    return gemm_packed(A, W, nullptr, nullptr, alpha, nullptr, bias, 0.f, 1.f, 1.f, 3, 0, C, ldc, st);
+    return gemm_packed(A, W, nullptr, nullptr, alpha, nullptr, bias, 0.f, 1.f, 1.f, 3, 0, C, ldc, st, nullptr);
 }
 
 // out = acc * (ra_i + ca_j + a0) + rq_scale * (r_i + q_j) + c0 from fp32 row-major operands
 static int score_gemm_general(const float* E, const float* T, int Ne, int Nt, int D, const float* ra, const float* ca, float a0,
                               const float* r, const float* q, float c0, float rq_scale, float abs_alpha_for_auto, int passes, int out_f64,
-                              void* out, long long ld_out, size_t tmp_bytes, cudaStream_t st) {
-    if (!E || !T || !out || Ne <= 0 || Nt <= 0 || D <= 0 || ld_out < Nt) {
+                              void* out, long long ld_out, size_t tmp_bytes, cudaStream_t st, const TrialTables* trials = nullptr) {
+    if (!E || !T || !out || Ne <= 0 || Nt <= 0 || D <= 0 || (out_f64 != 3 && ld_out < Nt)) {
         set_last_error(__FILE__, __LINE__, "score_gemm: bad arguments");
         return SKB_ERR_ARG;
     }
@@ -598,7 +649,78 @@ static int score_gemm_general(const float* E, const float* T, int Ne, int Nt, in
     ws_operand(&e, Ne, D, 0, 0);
     ws_operand(&t, Nt, D, 1, 2 * eh);
     if ((rc = packed_fill(E, &e, T, &t, st))) return rc;
-    return gemm_packed(e, t, ra, ca, a0, r, q, c0, rq_scale, abs_alpha_for_auto, passes, out_f64, out, ld_out, st);
+    return gemm_packed(e, t, ra, ca, a0, r, q, c0, rq_scale, abs_alpha_for_auto, passes, out_f64, out, ld_out, st, trials);
+}
+
+// ----------------------------------------------------------------------------- trial index (trial-list mode)
+// mask (Ne, Nt) bytes -> bit words + exclusive row-major prefix counts.  One warp per row: 128 mask bytes per step (a
+// 32-bit load per lane), ballots assemble four words, the in-row offsets follow from a running popcount.
+__global__ void trial_words_kernel(const uint8_t* __restrict__ mask, int Ne, int Nt, long long ld, uint32_t* __restrict__ words,
+                                   uint32_t* __restrict__ offs, int mask_ld, uint32_t* __restrict__ row_total) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= Ne) return;
+    const uint8_t* m = mask + (size_t)row * ld;
+    uint32_t running = 0;
+    for (int w0 = 0; w0 < mask_ld; w0 += 32) {
+        // lane handles word w0 + lane: its 32 mask bytes
+        const int w = w0 + lane;
+        uint32_t word = 0u;
+        if (w < mask_ld) {
+            const int c0 = w * 32;
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {
+                const int c = c0 + j;
+                if (c < Nt && m[c]) word |= 1u << j;
+            }
+        }
+        const uint32_t cnt = __popc(word);
+        uint32_t incl = cnt;                       // warp inclusive scan of the 32 word counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (w < mask_ld) {
+            words[(size_t)row * mask_ld + w] = word;
+            offs[(size_t)row * mask_ld + w] = running + incl - cnt;
+        }
+        running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) row_total[row] = running;
+}
+
+// exclusive scan of the row totals (one CTA; Ne is at most a few 10^5) -> row_base; total -> *n_trials
+__global__ void __launch_bounds__(1024) trial_rowscan_kernel(const uint32_t* __restrict__ row_total, int Ne, uint32_t* __restrict__ row_base,
+                                                             unsigned long long* __restrict__ n_trials) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < Ne; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = i < Ne ? row_total[i] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned long long before = carry;
+        for (int k = 0; k < warp; ++k) before += warp_tot[k];
+        if (i < Ne) row_base[i] = (uint32_t)(before + incl - v);
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_trials = carry;
+}
+
+__global__ void trial_addbase_kernel(uint32_t* __restrict__ offs, const uint32_t* __restrict__ row_base, long long n, int mask_ld) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) offs[i] += row_base[i / mask_ld];
 }
 
 // ----------------------------------------------------------------------------- as-norm: top-k statistics per row
@@ -803,7 +925,70 @@ int skb_score_gemm_packed(const float* E_dev, int Ne, const skb_packed_t* T, con
     ws_operand(&e, Ne, D, 0, 0);
     if ((rc = packed_fill(E_dev, &e, nullptr, nullptr, st))) return rc;
     return gemm_packed(e, T->op, nullptr, nullptr, (float)alpha, rowterm_dev, colterm_dev, (float)(alpha * cst), (float)alpha,
-                       (float)fabs(alpha), passes, out_dtype, out_dev, ld_out, st);
+                       (float)fabs(alpha), passes, out_dtype, out_dev, ld_out, st, nullptr);
+}
+
+struct skb_trial_index { uint32_t *words = nullptr, *offsets = nullptr, *row_total = nullptr, *row_base = nullptr;
+                         unsigned long long* n_dev = nullptr; int Ne = 0, Nt = 0, ld = 0, device = 0; long long n_trials = 0; };
+
+void skb_trial_index_destroy(skb_trial_index_t* t) {
+    if (!t) return;
+    cudaFree(t->words); cudaFree(t->offsets); cudaFree(t->row_total); cudaFree(t->row_base); cudaFree(t->n_dev);
+    delete t;
+}
+
+int skb_trial_index_create(const uint8_t* mask_dev, int Ne, int Nt, int64_t ld_mask, skb_trial_index_t** out, int64_t* n_trials,
+                           void* stream) {
+    if (!mask_dev || !out || !n_trials || Ne <= 0 || Nt <= 0 || ld_mask < Nt) {
+        set_last_error(__FILE__, __LINE__, "trial_index_create: bad arguments");
+        return SKB_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    skb_trial_index* t = new skb_trial_index();
+    t->Ne = Ne; t->Nt = Nt; t->ld = (Nt + 31) / 32; t->device = current_device();
+    const size_t nw = (size_t)Ne * t->ld;
+    unsigned long long total = 0;
+    if (cudaMalloc(&t->words, nw * 4) != cudaSuccess || cudaMalloc(&t->offsets, nw * 4) != cudaSuccess ||
+        cudaMalloc(&t->row_total, (size_t)Ne * 4) != cudaSuccess || cudaMalloc(&t->row_base, (size_t)Ne * 4) != cudaSuccess ||
+        cudaMalloc(&t->n_dev, 8) != cudaSuccess) {
+        set_last_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+        skb_trial_index_destroy(t);
+        return SKB_ERR_CUDA;
+    }
+    trial_words_kernel<<<(Ne + 7) / 8, 256, 0, st>>>(mask_dev, Ne, Nt, (long long)ld_mask, t->words, t->offsets, t->ld, t->row_total);
+    trial_rowscan_kernel<<<1, 1024, 0, st>>>(t->row_total, Ne, t->row_base, t->n_dev);
+    trial_addbase_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(t->offsets, t->row_base, (long long)nw, t->ld);
+    g_launches += 3;
+    if (cudaMemcpyAsync(&total, t->n_dev, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        set_last_error(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+        skb_trial_index_destroy(t);
+        return SKB_ERR_CUDA;
+    }
+    if (total >= 0xffffffffull) {
+        set_last_error(__FILE__, __LINE__, "trial_index_create: more than 2^32 - 1 trials");
+        skb_trial_index_destroy(t);
+        return SKB_ERR_ARG;
+    }
+    t->n_trials = (long long)total;
+    *n_trials = (int64_t)total;
+    *out = t;
+    return SKB_OK;
+}
+
+int skb_score_gemm_trials(const float* E_dev, const float* T_dev, int Ne, int Nt, int D, const float* rowterm_dev,
+                          const float* colterm_dev, double cst, double alpha, int passes, const skb_trial_index_t* trials,
+                          float* out_trials_dev, void* stream) {
+    if (!trials || trials->Ne != Ne || trials->Nt != Nt || !out_trials_dev) {
+        set_last_error(__FILE__, __LINE__, "score_gemm_trials: the trial index does not match the operands");
+        return SKB_ERR_ARG;
+    }
+    if (trials->device != current_device()) {
+        set_last_error(__FILE__, __LINE__, "score_gemm_trials: the trial index lives on another CUDA device");
+        return SKB_ERR_STATE;
+    }
+    TrialTables tt{trials->words, trials->offsets, trials->ld, Ne, Nt};
+    return score_gemm_general(E_dev, T_dev, Ne, Nt, D, nullptr, nullptr, (float)alpha, rowterm_dev, colterm_dev, (float)(alpha * cst),
+                              (float)alpha, (float)fabs(alpha), passes, 3, out_trials_dev, 0, 0, (cudaStream_t)stream, &tt);
 }
 
 int skb_widen_f32_f64(const float* src_dev, double* dst_dev, int64_t n, void* stream) {

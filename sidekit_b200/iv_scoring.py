@@ -41,7 +41,8 @@ def _dev32(a, device):
 
 
 def score_matrix(E, T, rowterm=None, colterm=None, cst=0.0, alpha=1.0, passes=0, out_dtype=torch.float32, out=None):
-    """S = alpha*(rowterm_i + colterm_j + cst) + alpha * E T^T on the device (all arguments torch CUDA fp32)."""
+    """S = alpha*(rowterm_i + colterm_j + cst) + alpha * E T^T on the device (all arguments torch CUDA fp32; ``T`` may be a
+    ``PackedEmbeddings``).  ``out_dtype`` float32, float64 or float16 (half the HBM-bound write; 11-bit mantissa)."""
     Ne, D = E.shape
     Nt = T.rows if isinstance(T, PackedEmbeddings) else T.shape[0]
     if out is None:
@@ -51,13 +52,13 @@ def score_matrix(E, T, rowterm=None, colterm=None, cst=0.0, alpha=1.0, passes=0,
             _lib.check(_lib.lib().skb_score_gemm_packed(
                 E.data_ptr(), Ne, T._ptr, None if rowterm is None else rowterm.data_ptr(),
                 None if colterm is None else colterm.data_ptr(), float(cst), float(alpha), int(passes),
-                1 if out.dtype == torch.float64 else 0, out.data_ptr(), out.stride(0), _lib.stream_ptr()))
+                _OUT_DTYPE[out.dtype], out.data_ptr(), out.stride(0), _lib.stream_ptr()))
         return out
     with torch.cuda.device(E.device):
         _lib.check(_lib.lib().skb_score_gemm(
             E.data_ptr(), T.data_ptr(), Ne, Nt, D, None if rowterm is None else rowterm.data_ptr(),
             None if colterm is None else colterm.data_ptr(), float(cst), float(alpha), int(passes),
-            1 if out.dtype == torch.float64 else 0, out.data_ptr(), out.stride(0), _lib.stream_ptr()))
+            _OUT_DTYPE[out.dtype], out.data_ptr(), out.stride(0), _lib.stream_ptr()))
     return out
 
 
@@ -81,6 +82,50 @@ class PackedEmbeddings:
                 self._ptr = None
         except Exception:
             pass
+
+
+_OUT_DTYPE = {torch.float32: 0, torch.float64: 1, torch.float16: 2}
+
+
+class TrialIndex:
+    """Bit words + prefix counts of an (Ne, Nt) trial mask on the device (``skb_trial_index_create``), for
+    ``score_trials``.  ``n_trials`` = number of selected trials; their order is numpy's ``mask.nonzero()`` order."""
+
+    def __init__(self, mask, device=None):
+        dev = _device(device)
+        m = torch.as_tensor(numpy.ascontiguousarray(mask, dtype=numpy.uint8) if not torch.is_tensor(mask) else mask)
+        m = m.to(dev, torch.uint8).contiguous()
+        self.Ne, self.Nt, self.device = int(m.shape[0]), int(m.shape[1]), dev
+        self._ptr = ctypes.c_void_p()
+        n = ctypes.c_int64(0)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().skb_trial_index_create(m.data_ptr(), self.Ne, self.Nt, m.stride(0), ctypes.byref(self._ptr),
+                                                         ctypes.byref(n), _lib.stream_ptr()))
+        self.n_trials = int(n.value)
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                _lib.lib().skb_trial_index_destroy(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
+def score_trials(E, T, trials, rowterm=None, colterm=None, cst=0.0, alpha=1.0, passes=0):
+    """The scores of the trials of a mask only, as a 1-D float32 CUDA tensor in row-major mask order -- what the reference
+    selects with ``scoremat[trialmask]`` (xvector.py:243-245) -- without the Ne x Nt matrix ever reaching HBM.
+    ``trials``: a ``TrialIndex`` or an (Ne, Nt) bool mask."""
+    if not isinstance(trials, TrialIndex):
+        trials = TrialIndex(trials, E.device)
+    Ne, D = E.shape
+    out = torch.empty((max(trials.n_trials, 1),), dtype=torch.float32, device=E.device)
+    with torch.cuda.device(E.device):
+        _lib.check(_lib.lib().skb_score_gemm_trials(
+            E.data_ptr(), T.data_ptr(), Ne, T.shape[0], D, None if rowterm is None else rowterm.data_ptr(),
+            None if colterm is None else colterm.data_ptr(), float(cst), float(alpha), int(passes), trials._ptr, out.data_ptr(),
+            _lib.stream_ptr()))
+    return out[:trials.n_trials]
 
 
 def _quadratic_prepare(X, mu, Psi, Phi):

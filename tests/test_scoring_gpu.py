@@ -281,3 +281,23 @@ def test_large_matrix_reaches_the_host_through_the_pinned_path_widened():
     assert out32.dtype == numpy.float32 and numpy.array_equal(out32, t.cpu().numpy())
     small = _device_to_numpy(t[:7].contiguous(), numpy.float64)
     assert small.dtype == numpy.float64 and numpy.array_equal(small, t[:7].cpu().numpy().astype(numpy.float64))
+
+
+def test_trial_list_mode_and_fp16_output():
+    """the epilogue writes only the masked trials (row-major, the order of scoremat[trialmask]) or a
+    16-bit matrix."""
+    from sidekit_b200.iv_scoring import TrialIndex, score_matrix, score_trials
+    rng = numpy.random.default_rng(12)
+    for Ne, Nt, dens, unit in ((700, 900, 0.5, True), (333, 517, 0.01, False), (128, 128, 1.0, True), (1, 33, 0.3, True), (257, 31, 0.0, True)):
+        E = torch.from_numpy(synth.synth_embeddings(Ne, 256, seed=71, unit_norm=unit)).float().cuda()
+        T = torch.from_numpy(synth.synth_embeddings(Nt, 256, seed=72, unit_norm=unit)).float().cuda()
+        r, q = torch.randn(Ne, device="cuda"), torch.randn(Nt, device="cuda")
+        mask = rng.random((Ne, Nt)) < dens
+        full = score_matrix(E, T, r, q, cst=0.25, alpha=1.5, passes=0)
+        idx = TrialIndex(mask)
+        assert idx.n_trials == int(mask.sum())
+        got = score_trials(E, T, idx, r, q, cst=0.25, alpha=1.5, passes=0)
+        assert got.shape == (int(mask.sum()),)
+        assert torch.equal(got, full[torch.from_numpy(mask).cuda()])            # same arithmetic, same order
+        half = score_matrix(E, T, r, q, cst=0.25, alpha=1.5, passes=0, out_dtype=torch.float16)
+        assert half.dtype == torch.float16 and torch.equal(half, full.half())

@@ -320,6 +320,25 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                 qpre[cbi] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.q && vec_ok && col + 4 <= p.Nt) qpre[cbi] = __ldg(reinterpret_cast<const float4*>(p.q + col));
             }
+            // trial-list mode: this lane's mask words (rows rs, rs + 4, ... of both 32-column blocks) and, for the non-empty
+            // ones, their output offsets -- fetched before the accumulator wait like the column terms
+            uint32_t mw[2][8], mo[2][8];
+            if (p.out_mode == 3) {
+#pragma unroll
+                for (int cbi = 0; cbi < 2; ++cbi) {
+                    const int wcol = nt * 4 + half * 2 + cbi;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = row0 + it * 4 + (lane >> 3);
+                        mw[cbi][it] = (row < p.Ne && wcol < p.mask_ld) ? __ldg(p.mask_words + (size_t)row * p.mask_ld + wcol) : 0u;
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = row0 + it * 4 + (lane >> 3);
+                        mo[cbi][it] = mw[cbi][it] != 0u ? __ldg(p.word_off + (size_t)row * p.mask_ld + wcol) : 0u;
+                    }
+                }
+            }
             mbar_wait(&acc_full[buf], (nt_done >> 1) & 1);
             tc_fence_after();
 #pragma unroll
@@ -337,7 +356,9 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                 // Transpose through shared memory: lane = row before the transpose (row terms applied there),
                 // lane = 4 columns x 1 of 4 rows after it, so every store instruction writes four 128-byte row segments.
                 __syncwarp();
-                const bool fast = (p.ca == nullptr) && n_rows == 32 && col0 + 32 <= p.Nt && vec_ok;
+                // rows beyond Ne (the last panel of a ragged matrix) are simply not stored: the ragged panel used to take the
+                // scalar path and its CTA finished several times later than all the others
+                const bool fast = (p.ca == nullptr) && col0 + 32 <= p.Nt && vec_ok;
                 if (fast) {
                     const float mul = ra + a0;
                     float4* srow = reinterpret_cast<float4*>(stg + lane * 36);
@@ -355,16 +376,14 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                         // is then bound by the tensor pipe / the operand stream, not by HBM writes.
                         float* o = reinterpret_cast<float*>(p.out);
                         const uint32_t lt = (1u << c4) - 1u;
-                        const size_t wcol = (size_t)(col0 >> 5);
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
-                            const size_t widx = (size_t)(row0 + it * 4 + rs) * p.mask_ld + wcol;
-                            const uint32_t word = __ldg(p.mask_words + widx);
+                            const uint32_t word = mw[cbi][it];
                             const uint32_t m4 = (word >> c4) & 0xFu;
                             if (m4 == 0u) continue;
                             const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
                             const float xs[4] = {x.x + qv.x, x.y + qv.y, x.z + qv.z, x.w + qv.w};
-                            size_t dst = (size_t)__ldg(p.word_off + widx) + __popc(word & lt);
+                            size_t dst = (size_t)mo[cbi][it] + __popc(word & lt);
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
                                 if (m4 & (1u << e)) o[dst++] = xs[e];
@@ -374,6 +393,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                         const size_t step = (size_t)4 * p.ld_out;
 #pragma unroll
                         for (int it = 0; it < 8; ++it, o += step) {
+                            if (it * 4 + rs >= n_rows) break;
                             const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
                             const __half2 h0 = __floats2half2_rn(x.x + qv.x, x.y + qv.y), h1 = __floats2half2_rn(x.z + qv.z, x.w + qv.w);
                             __stcs(reinterpret_cast<uint2*>(o), make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1)));
@@ -383,6 +403,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                         const size_t step = (size_t)4 * p.ld_out;
 #pragma unroll
                         for (int it = 0; it < 8; ++it, o += step) {
+                            if (it * 4 + rs >= n_rows) break;
                             const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
                             __stcs(reinterpret_cast<double2*>(o), make_double2((double)(x.x + qv.x), (double)(x.y + qv.y)));
                             __stcs(reinterpret_cast<double2*>(o) + 1, make_double2((double)(x.z + qv.z), (double)(x.w + qv.w)));
@@ -392,6 +413,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                         const size_t step = (size_t)4 * p.ld_out;
 #pragma unroll
                         for (int it = 0; it < 8; ++it, o += step) {
+                            if (it * 4 + rs >= n_rows) break;
                             const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
                             // streaming store: the score matrix is written once and never re-read by this kernel, so it
                             // should not evict the T operand tiles from L2

@@ -389,7 +389,8 @@ def run_ours(args):
         return bulk.gather_embeddings(local_emb, shards, 256, device)          # the one collective of the path
 
     sampler = ClockSampler(local)
-    sampler.start()
+    if not args.no_clock_sampler:
+        sampler.start()
     with torch.no_grad():
         # the bulk run's batch budget is known up front (what bulk.make_batches is given): every work buffer and plan-cache
         # slot is allocated now, none inside the run
@@ -835,6 +836,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts", type=int, default=96, help="mean utterances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not run nvidia-smi beside the timed region")
     args = ap.parse_args()
     with StdoutToStderr():
         line = run_reference(args) if args.impl == "reference" else run_ours(args)

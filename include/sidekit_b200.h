@@ -210,6 +210,20 @@ int skb_scoremat_stats(const void* S_dev, int M, int N, int64_t ld, int is_f64, 
 int skb_scoremat_normalise(const void* S_dev, int M, int N, int64_t ld, int is_f64, const double* sub_dev,
                            const double* div_dev, void* out_dev, int64_t ld_out, void* stream);
 
+/* ---- PLDA training: FactorAnalyser.plda, sidekit/factor_analyser.py:830-932 -------------------
+ * All arrays are device float64, row-major.  skb_plda_stats: mean (D), total covariance sigma_obs (D, D) and the
+ * scaled per-class sums S1 (n_cls, D) of the training vectors X (n_sess, D); the classes are given as CSR lists
+ * (cls_ptr (n_cls + 1), cls_rows (n_sess): the rows of class c in input order).  Synchronises the stream. */
+int skb_plda_stats(const double* X_dev, int n_sess, int D, const int* cls_ptr_dev, const int* cls_rows_dev, int n_cls,
+                   double scaling, double* mean_dev, double* sigma_obs_dev, double* S1_dev, void* stream);
+/* skb_plda_em: nb_iter EM iterations with no host round trip (Cholesky factorisations, batched over the distinct session
+ * counts, and GEMMs on the device).  cls_n (n_cls) scaled session count of each class, cls_u (n_cls) index of that count
+ * in uniq_n (U), cnt_u (U) classes per count, sum_n = sum of cls_n.  F_dev (D, R): in the eigenvoice initialisation, out
+ * the trained matrix; Sigma_dev (D, D): in sigma_obs, out the residual covariance.  Synchronises the stream. */
+int skb_plda_em(const double* S1_dev, const double* cls_n_dev, const int* cls_u_dev, int n_cls, const double* uniq_n_dev,
+                const double* cnt_u_dev, int U, const double* mean_dev, const double* sigma_obs_dev, int D, int R, int nb_iter,
+                double sum_n, double* F_dev, double* Sigma_dev, void* stream);
+
 /* ---- feed path: sample-rate conversion ---------------------------------------------------
  * torchaudio.transforms.Resample(orig_freq, new_freq)(speech) as sidekit/nnet/xsets.py:435, :452 and
  * sidekit/bin/extract_xvectors.py:144 call it (Hann-windowed sinc, lowpass_filter_width 6, rolloff 0.99), on a packed

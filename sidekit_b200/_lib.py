@@ -74,6 +74,8 @@ def _declare(lib):
         "skb_eer": (i32, [vp, i64, vp, i64, ctypes.POINTER(f64)]),
         "skb_scoremat_stats": (i32, [vp, i32, i32, i64, i32, i32, i32, vp, vp, vp]),
         "skb_scoremat_normalise": (i32, [vp, i32, i32, i64, i32, vp, vp, vp, i64, vp]),
+        "skb_plda_stats": (i32, [vp, i32, i32, vp, vp, i32, f64, vp, vp, vp, vp]),
+        "skb_plda_em": (i32, [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, f64, vp, vp, vp]),
         "skb_resample": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, vp, i32, vp, vp]),
     }
     for name, (res, args) in sigs.items():

@@ -381,8 +381,38 @@ class Scores:
                 return both[:it.shape[0]], both[it.shape[0]:]
             flat = self.scoremat.reshape(-1)
             return flat[it], flat[inn]
-        new_score = self.align_with_ndx(key)
-        return new_score.scoremat[key.tar & new_score.scoremask], new_score.scoremat[key.non & new_score.scoremask]
+        # The key lists other (or differently ordered) models / segments than the scores (scores.py:172-179 aligns a copy
+        # of the whole matrix with the key first): map the key's rows / columns onto the score matrix with a hash join
+        # and gather only the trials -- same vectors, in the key's row-major order, without an (M, S) intermediate.
+        mtab, stab = _first_index(self.modelset), _first_index(self.segset)
+        rows = numpy.array([mtab.get(m, -1) for m in numpy.asarray(key.modelset).tolist()], dtype=numpy.int64)
+        cols = numpy.array([stab.get(x, -1) for x in numpy.asarray(key.segset).tolist()], dtype=numpy.int64)
+        if (rows < 0).any():
+            logging.info('models reduced from %d to %d', rows.shape[0], int((rows >= 0).sum()))
+        if (cols < 0).any():
+            logging.info('testsegs reduced from %d to %d', cols.shape[0], int((cols >= 0).sum()))
+        n_seg = key.segset.shape[0]
+        out = []
+        for idx in key.trial_indices():
+            r, c = rows[idx // n_seg], cols[idx % n_seg]
+            ok = (r >= 0) & (c >= 0)
+            r, c = r[ok], c[ok]
+            keep = self.scoremask[r, c]
+            out.append((r[keep], c[keep]))
+        if self._scoremat is None and self.scoremat_device is not None:
+            import torch
+            dev = self.scoremat_device.device
+            flat = self.scoremat_device.reshape(-1)
+            n_col = self.scoremat_device.shape[1]
+            lin = numpy.concatenate([o[0] * n_col + o[1] for o in out])
+            both = flat[torch.from_numpy(lin).to(dev)].cpu().numpy()
+            if self.scoremat_dtype is not None:
+                both = both.astype(self.scoremat_dtype)
+            tar, non = both[:out[0][0].shape[0]], both[out[0][0].shape[0]:]
+        else:
+            tar, non = self.scoremat[out[0]], self.scoremat[out[1]]
+        assert numpy.all(numpy.isfinite(tar)) and numpy.all(numpy.isfinite(non)), 'Inifinite or Nan value in the scoremat'
+        return tar, non
 
     def align_with_ndx(self, ndx):
         """scores.py:181-240: resized / reordered copy that follows ``ndx`` (a Key or an Ndx)."""

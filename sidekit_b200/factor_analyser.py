@@ -1,15 +1,15 @@
 """PLDA training: ``FactorAnalyser.plda`` of sidekit/factor_analyser.py:830-932, the simplified
 PLDA (speaker subspace ``F``, full residual covariance ``Sigma``) whose ``(mean, F, Sigma)`` the scorers consume.
 
-The reference loops over the speakers in Python (``fa_model_loop``, :166-205).  Here the E-step is closed-form linear
-algebra over ALL classes at once: with ``L_n = (n F'F + I)^-1`` (one inverse per distinct session count ``n``),
-``E[h_i] = (s_i F) L_{n_i}`` and ``E[h_i h_i'] = L_{n_i} + E[h_i] E[h_i]'``, so the accumulators are
-
-    R = (sum_i L_{n_i} + Eh' Eh) / C        A = sum_i n_i L_{n_i} + Eh' diag(n) Eh        C = Eh' S (sqrt(Sigma)^-1)^-1
-
-i.e. three GEMMs over the (classes x D) statistics -- float64 on the device (plain library GEMMs: there is nothing to
-fuse) -- and D x D / R x R factorizations on the host exactly as the reference does them (scipy).  HDF5 output
-(``write`` / ``save_partial`` / ``save_final``) is out of scope.
+The reference whitens the statistics with ``sqrt(Sigma)^-1`` (an eigendecomposition per iteration), loops over the
+speakers in Python (``fa_model_loop``, :166-205) and inverts one ``R x R`` matrix per speaker.  Here the whole EM loop
+runs on the device in float64 (``csrc/plda_train.cu``: ``skb_plda_stats`` + ``skb_plda_em``) with no host round trip
+inside it: the E- and M-step only depend on the whitening through ``Sigma^-1``, so there is one Cholesky factorisation
+of ``Sigma`` per iteration, one of ``n F' Sigma^-1 F + I`` per DISTINCT session count ``n`` (batched), GEMMs over all
+classes at once and Cholesky solves for the M-step.  The host only groups the sessions by class and computes the
+eigenvoice initialisation (``scipy.linalg.eigh`` of the total covariance, as the reference does: the trained ``F``
+depends on the sign convention of those eigenvectors).  HDF5 output (``write`` / ``save_partial`` / ``save_final``) is
+out of scope.
 """
 import logging
 
@@ -17,20 +17,13 @@ import numpy
 import scipy.linalg
 import torch
 
+from . import _lib
 
-def _dev(a):
+
+def _dev(a, dtype=numpy.float64):
     if not torch.cuda.is_available():
         raise RuntimeError("sidekit_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    return torch.from_numpy(numpy.ascontiguousarray(a, dtype=numpy.float64)).cuda()
-
-
-def _sqr_inv(sigma):
-    """sqrt(Sigma)^-1 as the reference builds it (statserver.py:872-878): eigenvectors scaled by 1/sqrt(eigenvalue)."""
-    eigen_values, eigen_vectors = scipy.linalg.eigh(sigma)
-    ind = eigen_values.real.argsort()[::-1]
-    eigen_values = eigen_values.real[ind]
-    eigen_vectors = eigen_vectors.real[:, ind]
-    return numpy.dot(eigen_vectors, numpy.diag(1 / numpy.sqrt(eigen_values.real)))
+    return torch.from_numpy(numpy.ascontiguousarray(a, dtype=dtype)).cuda()
 
 
 class FactorAnalyser:
@@ -46,52 +39,34 @@ class FactorAnalyser:
         """factor_analyser.py:830-932.  Sets ``self.mean``, ``self.F`` (D, rank_f) and ``self.Sigma`` (D, D)."""
         if output_file_name is not None or save_partial:
             logging.warning("sidekit_b200: FactorAnalyser.plda does not write HDF5 files; the model stays in memory")
-        stat1 = numpy.asarray(stat_server.stat1, dtype=numpy.float64)
-        X = _dev(stat1)
-        n_sess = X.shape[0]
-        # mean and total covariance of the training data (statserver.py:789-795, :920-928)
-        mean_d = X.mean(dim=0)
-        Cd = X - mean_d
-        sigma_obs = (Cd.T @ Cd / n_sess).cpu().numpy()
-        self.mean = mean_d.cpu().numpy()
-        self.Sigma = sigma_obs.copy()
-        # statistics summed per (sorted unique) model (statserver.py:1335-1355)
+        lib = _lib.lib()
+        X = _dev(stat_server.stat1)
+        n_sess, D = X.shape
+        # sessions grouped by (sorted unique) model, in input order inside a class (sum_stat_per_model, statserver.py:1335-1355)
         modelset, inv = numpy.unique(stat_server.modelset, return_inverse=True)
-        class_nb = modelset.shape[0]
-        inv_d = torch.from_numpy(inv.astype(numpy.int64)).cuda()
-        S1 = torch.zeros((class_nb, X.shape[1]), dtype=torch.float64, device=X.device).index_add_(0, inv_d, X)
-        sessions = numpy.bincount(inv, minlength=class_nb).astype(numpy.float64)
-        S1 = S1 * scaling_factor
-        stat0 = sessions * scaling_factor                      # model_shifted_stat.stat0 (one Gaussian) == scaled session count
-        session_per_model = sessions * scaling_factor
-        n_d = _dev(stat0)
-        # eigenvoice initialisation: leading eigenvectors of the total covariance (:862-866)
-        evals, evecs = scipy.linalg.eigh(sigma_obs)
+        n_cls = modelset.shape[0]
+        order = numpy.argsort(inv, kind="stable").astype(numpy.int32)
+        sessions = numpy.bincount(inv, minlength=n_cls)
+        cls_ptr = numpy.concatenate([[0], numpy.cumsum(sessions)]).astype(numpy.int32)
+        mean = torch.empty((D,), dtype=torch.float64, device=X.device)
+        sigma_obs = torch.empty((D, D), dtype=torch.float64, device=X.device)
+        S1 = torch.empty((n_cls, D), dtype=torch.float64, device=X.device)
+        ptr_d, rows_d = _dev(cls_ptr, numpy.int32), _dev(order, numpy.int32)
+        _lib.check(lib.skb_plda_stats(X.data_ptr(), n_sess, D, ptr_d.data_ptr(), rows_d.data_ptr(), n_cls, float(scaling_factor),
+                                      mean.data_ptr(), sigma_obs.data_ptr(), S1.data_ptr(), _lib.stream_ptr()))
+        # eigenvoice initialisation: leading eigenvectors of the total covariance (:862-866), on the host like the reference
+        evals, evecs = scipy.linalg.eigh(sigma_obs.cpu().numpy())
         idx = numpy.argsort(evals)[::-1]
-        self.F = evecs.real[:, idx[:rank_f]][:, :rank_f]
+        F = _dev(evecs.real[:, idx[:rank_f]][:, :rank_f])
+        # model_shifted_stat.stat0 (one Gaussian) == scaled session count; one R x R factorisation per DISTINCT count
+        stat0 = sessions.astype(numpy.float64) * scaling_factor
         uniq_n, n_index = numpy.unique(stat0, return_inverse=True)
         counts = numpy.bincount(n_index, minlength=uniq_n.shape[0]).astype(numpy.float64)
-        n_index_d = torch.from_numpy(n_index.astype(numpy.int64)).cuda()
-        for it in range(nb_iter):
-            logging.info('Estimate between class covariance, it %d / %d', it + 1, nb_iter)
-            # whiten the statistics and the eigenvoice matrix with the current (mean, Sigma) (:878-893)
-            sqr_inv_sigma = _sqr_inv(self.Sigma)
-            W = _dev(sqr_inv_sigma)
-            local = (S1 - n_d[:, None] * _dev(self.mean)[None, :]) @ W                  # center_stat1 (stat0-weighted) + rotate
-            F = sqr_inv_sigma.T.dot(self.F)
-            # E-step over all classes (fa_model_loop, :166-205)
-            A0 = F.T.dot(F)
-            inv_lambda = numpy.stack([scipy.linalg.inv(n * A0 + numpy.eye(rank_f)) for n in uniq_n])       # (U, R, R)
-            L = _dev(inv_lambda)
-            aux = local @ _dev(F)                                                        # (C, R)
-            e_h = torch.bmm(aux.unsqueeze(1), L[n_index_d]).squeeze(1)                   # aux_i . L_{n_i}
-            sum_L = numpy.einsum('u,ujk->jk', counts, inv_lambda)
-            sum_nL = numpy.einsum('u,ujk->jk', counts * uniq_n, inv_lambda)
-            _R = (sum_L + (e_h.T @ e_h).cpu().numpy()) / session_per_model.shape[0]
-            _C = (e_h.T @ local).cpu().numpy().dot(scipy.linalg.inv(sqr_inv_sigma))
-            _A = sum_nL + (e_h.T @ (e_h * n_d[:, None])).cpu().numpy()
-            # M-step, residual covariance, minimum divergence (:914-922)
-            self.F = scipy.linalg.solve(_A, _C).T
-            self.Sigma = sigma_obs - self.F.dot(_C) / session_per_model.sum()
-            self.F = self.F.dot(scipy.linalg.cholesky(_R))
+        Sigma = sigma_obs.clone()
+        n_d, u_d, uq_d, cnt_d = _dev(stat0), _dev(n_index, numpy.int32), _dev(uniq_n), _dev(counts)
+        logging.info('Estimate between class covariance, %d iterations on the device', nb_iter)
+        _lib.check(lib.skb_plda_em(S1.data_ptr(), n_d.data_ptr(), u_d.data_ptr(), n_cls, uq_d.data_ptr(), cnt_d.data_ptr(),
+                                   int(uniq_n.shape[0]), mean.data_ptr(), sigma_obs.data_ptr(), D, int(rank_f), int(nb_iter),
+                                   float(stat0.sum()), F.data_ptr(), Sigma.data_ptr(), _lib.stream_ptr()))
+        self.mean, self.F, self.Sigma = mean.cpu().numpy(), F.cpu().numpy(), Sigma.cpu().numpy()
         return self

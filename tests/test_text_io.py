@@ -236,3 +236,24 @@ def test_ndx_filter_fast_paths_keep_the_reference_semantics():
             assert numpy.array_equal(out.trialmask, n.trialmask[km, :][:, ks]) and out.validate()
     same = n.filter(n.modelset, n.segset, True)
     assert numpy.shares_memory(same.trialmask, n.trialmask) and not numpy.shares_memory(same.modelset, n.modelset)
+
+
+def test_get_tar_non_with_a_key_over_other_sets_equals_the_aligned_matrix():
+    """scores.py:157-179: ``get_tar_non`` with a key whose model / segment sets differ from the scores' (other order, ids
+    missing on both sides) returns what indexing the ``align_with_ndx`` copy returns -- gathered trial by trial here."""
+    import sidekit_b200 as sk
+    rng = numpy.random.default_rng(1)
+    ids = numpy.array(["u%03d" % i for i in range(50)])
+    S = sk.Scores()
+    S.modelset, S.segset = ids[rng.permutation(50)][:40], ids[rng.permutation(50)][:45]
+    S.scoremat, S.scoremask = rng.standard_normal((40, 45)), rng.random((40, 45)) < 0.8
+    key = sk.Key(models=ids[rng.integers(0, 50, 300)], testsegs=ids[rng.integers(0, 50, 300)],
+                 trials=numpy.where(rng.random(300) < 0.5, "target", "nontarget"))
+    tar, non = S.get_tar_non(key)
+    al = S.align_with_ndx(key)
+    assert numpy.array_equal(tar, al.scoremat[key.tar & al.scoremask]) and numpy.array_equal(non, al.scoremat[key.non & al.scoremask])
+    same = sk.Scores()
+    same.modelset, same.segset = key.modelset, key.segset
+    same.scoremat, same.scoremask = rng.standard_normal(key.tar.shape), rng.random(key.tar.shape) < 0.7
+    tar, non = same.get_tar_non(key)
+    assert numpy.array_equal(tar, same.scoremat[key.tar & same.scoremask]) and numpy.array_equal(non, same.scoremat[key.non & same.scoremask])

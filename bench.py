@@ -401,9 +401,7 @@ def run_ours(args):
             model.extract_packed(device_audio(wls, 5 + k, device), wls)
         if dist_on:
             bulk.gather_embeddings(local_emb, shards, 256, device)
-        torch.cuda.synchronize()
-        time.sleep(0.25)                                       # nvidia-smi is up and sampling by now
-        sampler.mark()
+        sampler.mark()                                         # nvidia-smi came up during the reserve / warm-up above
         l0 = lib.skb_kernel_launches()
         ms = timed(job_dev, 1, dist_on)
         launches = lib.skb_kernel_launches() - l0

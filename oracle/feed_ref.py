@@ -1,9 +1,10 @@
 """CPU restatement of the segment / sliding-window logic of the reference's feed path
 (sidekit/nnet/xsets.py:419-464 ``IdMapSet.__getitem__`` and sidekit/nnet/xvector.py:1877-1914).
 
-TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  PARITY UNPINNED for this row: ``IdMapSet`` reads audio through
-``torchaudio.load`` (needs torchcodec, absent here) and the reference ships no test for it, so the restatement below is
-checked against the reference's source by reading only; it works on in-memory int16 arrays.
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  Pinned by tests/golden/feed_path.npz: outputs of the reference's own
+``IdMapSet.__getitem__`` recorded by oracle/make_golden_feed.py with only the file decoder replaced (``torchaudio.load``
+needs torchcodec, absent here; a stdlib ``wave`` reader with the same conventions stands in).  Works on in-memory int16
+arrays.
 """
 import numpy
 

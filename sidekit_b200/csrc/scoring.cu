@@ -320,24 +320,19 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                 qpre[cbi] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.q && vec_ok && col + 4 <= p.Nt) qpre[cbi] = __ldg(reinterpret_cast<const float4*>(p.q + col));
             }
-            // trial-list mode: this lane's mask words (rows rs, rs + 4, ... of both 32-column blocks) and, for the non-empty
-            // ones, their output offsets -- fetched before the accumulator wait like the column terms
-            uint32_t mw[2][8], mo[2][8];
-            if (p.out_mode == 3) {
+            // trial-list mode: lane = row (the accumulator's native layout, no transpose): this row's mask word of both
+            // 32-column blocks and, for the non-empty ones, their output offsets -- fetched before the accumulator wait
+            // like the column terms
+            uint32_t mw[2] = {0u, 0u}, mo[2] = {0u, 0u};
+            if (p.out_mode == 3 && my_row < p.Ne) {
 #pragma unroll
                 for (int cbi = 0; cbi < 2; ++cbi) {
                     const int wcol = nt * 4 + half * 2 + cbi;
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int row = row0 + it * 4 + (lane >> 3);
-                        mw[cbi][it] = (row < p.Ne && wcol < p.mask_ld) ? __ldg(p.mask_words + (size_t)row * p.mask_ld + wcol) : 0u;
-                    }
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int row = row0 + it * 4 + (lane >> 3);
-                        mo[cbi][it] = mw[cbi][it] != 0u ? __ldg(p.word_off + (size_t)row * p.mask_ld + wcol) : 0u;
-                    }
+                    if (wcol < p.mask_ld) mw[cbi] = __ldg(p.mask_words + (size_t)my_row * p.mask_ld + wcol);
                 }
+#pragma unroll
+                for (int cbi = 0; cbi < 2; ++cbi)
+                    if (mw[cbi] != 0u) mo[cbi] = __ldg(p.word_off + (size_t)my_row * p.mask_ld + nt * 4 + half * 2 + cbi);
             }
             mbar_wait(&acc_full[buf], (nt_done >> 1) & 1);
             tc_fence_after();
@@ -353,6 +348,24 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
                 if (col0 >= p.Nt || n_rows <= 0) continue;
+                if (p.out_mode == 3) {
+                    // Only the trials of the mask are written, compacted in row-major order: each lane walks the set bits
+                    // of ITS row's word.  No transpose, no shared memory, (almost) no stores for a sparse mask: the kernel
+                    // is then bound by the tensor pipe / the operand stream instead of the HBM write.
+                    uint32_t word = mw[cbi];
+                    if (word != 0u) {
+                        const float mul = ra + a0;
+                        float* o = reinterpret_cast<float*>(p.out) + mo[cbi];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (word & (1u << j)) {
+                                const float qq = p.q ? __ldg(p.q + col0 + j) * p.rq_scale : 0.f;
+                                *o++ = fmaf(v[j], mul, rr) + qq;
+                            }
+                        }
+                    }
+                    continue;
+                }
                 // Transpose through shared memory: lane = row before the transpose (row terms applied there),
                 // lane = 4 columns x 1 of 4 rows after it, so every store instruction writes four 128-byte row segments.
                 __syncwarp();
@@ -370,25 +383,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                     const int rs = lane >> 3;
                     float4 qv = qpre[cbi];
                     qv.x *= p.rq_scale; qv.y *= p.rq_scale; qv.z *= p.rq_scale; qv.w *= p.rq_scale;
-                    if (p.out_mode == 3) {
-                        // trial list: this lane's four columns of every fourth row; the eight lanes of a row write one
-                        // contiguous run of the compacted output.  A sparse mask writes (almost) nothing: the kernel
-                        // is then bound by the tensor pipe / the operand stream, not by HBM writes.
-                        float* o = reinterpret_cast<float*>(p.out);
-                        const uint32_t lt = (1u << c4) - 1u;
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const uint32_t word = mw[cbi][it];
-                            const uint32_t m4 = (word >> c4) & 0xFu;
-                            if (m4 == 0u) continue;
-                            const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
-                            const float xs[4] = {x.x + qv.x, x.y + qv.y, x.z + qv.z, x.w + qv.w};
-                            size_t dst = (size_t)mo[cbi][it] + __popc(word & lt);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (m4 & (1u << e)) o[dst++] = xs[e];
-                        }
-                    } else if (p.out_mode == 2) {
+                    if (p.out_mode == 2) {
                         __half* o = reinterpret_cast<__half*>(p.out) + (size_t)(row0 + rs) * p.ld_out + col0 + c4;
                         const size_t step = (size_t)4 * p.ld_out;
 #pragma unroll
@@ -449,12 +444,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                     }
                     sv += qq;
                     if (r < n_rows && col_ok) {
-                        if (p.out_mode == 3) {
-                            const size_t widx = (size_t)(row0 + r) * p.mask_ld + (size_t)(col0 >> 5);
-                            const uint32_t word = __ldg(p.mask_words + widx);
-                            if (word & (1u << lane))
-                                reinterpret_cast<float*>(p.out)[(size_t)__ldg(p.word_off + widx) + __popc(word & ((1u << lane) - 1u))] = sv;
-                        } else if (p.out_mode == 2) oh[(size_t)r * p.ld_out] = __float2half_rn(sv);
+                        if (p.out_mode == 2) oh[(size_t)r * p.ld_out] = __float2half_rn(sv);
                         else if (p.out_f64) od[(size_t)r * p.ld_out] = (double)sv;
                         else o[(size_t)r * p.ld_out] = sv;
                     }
@@ -1033,18 +1023,26 @@ int skb_asnorm_stats(const float* X_dev, const float* cohort_dev, int N, int C, 
     }
     cudaStream_t st = (cudaStream_t)stream;
     const long long ld = (C + 3) / 4 * 4;
-    const size_t tmp_bytes = (size_t)N * ld * sizeof(float);
+    // The N x C cohort score matrix never exists as a whole: the rows go through a bounded scratch panel (at most
+    // kAsnormChunkRows x C scores, 473 MB at C = 7205) -- GEMM of the panel, radix-select statistics of its rows, next
+    // panel -- so a million embeddings need the same workspace as twenty thousand.
+    constexpr int kAsnormChunkRows = 16384;
+    const int chunk = std::min(N, kAsnormChunkRows);
+    const size_t tmp_bytes = (size_t)chunk * ld * sizeof(float);
     int rc = ws_ensure(0, tmp_bytes);
-    if (rc) return rc;
-    rc = score_gemm_general(X_dev, cohort_dev, N, C, D, nullptr, nullptr, 1.f, nullptr, nullptr, 0.f, 1.f, 1.f, 3, 0, g_ws.tmp, ld,
-                            tmp_bytes, st);
     if (rc) return rc;
     static PerDeviceOnce configured;
     if (configured.first()) {
         SKB_CUDA_CHECK(cudaFuncSetAttribute(topk_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    topk_stats_kernel<<<N, 256, C * sizeof(unsigned), st>>>(g_ws.tmp, C, ld, top_k, mean_dev, std_dev);
-    g_launches++;
+    for (int r0 = 0; r0 < N; r0 += chunk) {
+        const int rows = std::min(chunk, N - r0);
+        rc = score_gemm_general(X_dev + (size_t)r0 * D, cohort_dev, rows, C, D, nullptr, nullptr, 1.f, nullptr, nullptr, 0.f, 1.f, 1.f, 3, 0,
+                                g_ws.tmp, ld, tmp_bytes, st);
+        if (rc) return rc;
+        topk_stats_kernel<<<rows, 256, C * sizeof(unsigned), st>>>(g_ws.tmp, C, ld, top_k, mean_dev + r0, std_dev + r0);
+        g_launches++;
+    }
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
 }

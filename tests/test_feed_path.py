@@ -216,3 +216,61 @@ def test_extract_xvectors_main_writes_kaldi_tables(tmp_path):
     assert list(table2.keys()) == list(table.keys()) and all(numpy.array_equal(table2[k], table[k]) for k in table)
     with pytest.raises(NotImplementedError):
         X.main(model, os.path.join(d, "wav.scp"), out_scp, "cuda", True)
+
+
+# ----------------------------------------------------------------------------- IdMapSet against the reference's recorded outputs
+FEED_CASES = [("whole", "f16k_a", None, None, False), ("whole_start_only", "f16k_a", 50, None, False),
+              ("segment", "f16k_a", 30, 150, False), ("too_short_recentred", "f16k_a", 100, 105, False),
+              ("too_short_at_file_start", "f16k_b", 0, 4, False), ("whole_8k_resampled", "f8k", None, None, False),
+              ("sliding", "f16k_b", None, None, True), ("sliding_segment", "f16k_b", 20, 330, True)]
+FEED_RATES = {"f16k_a": 16000, "f16k_b": 16000, "f8k": 8000}
+
+
+from tests.helpers import golden  # noqa: E402
+
+
+def _feed_files(tmp_path, g):
+    import wave as wavmod
+    for name, rate in FEED_RATES.items():
+        with wavmod.open(os.path.join(str(tmp_path), name + ".wav"), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(rate)
+            f.writeframes(g["pcm_" + name].tobytes())
+
+
+def _feed_item(tmp_path, fname, start, stop, sliding):
+    im = sk.IdMap()
+    im.leftids, im.rightids = numpy.array(["spk"], dtype="|O"), numpy.array([fname], dtype="|O")
+    im.start, im.stop = numpy.array([start], dtype="|O"), numpy.array([stop], dtype="|O")
+    ds = sk.IdMapSet(im, str(tmp_path), "wav", sliding_window=sliding, window_len=1.0, window_shift=0.5, sample_rate=16000,
+                     min_duration=0.165)
+    return ds[0]
+
+
+def test_idmapset_items_match_the_reference_recordings(tmp_path):
+    """tests/golden/feed_path.npz = the reference's IdMapSet.__getitem__ (xsets.py:419-464) on these files: whole file,
+    start only, segment, too-short segment (recentred min_duration window, also clamped at the file start), sliding windows."""
+    from oracle import feed_ref as FR
+    g = golden("feed_path.npz")
+    _feed_files(tmp_path, g)
+    for name, fname, start, stop, sliding in FEED_CASES:
+        if FEED_RATES[fname] != 16000:
+            continue                                             # needs the device resampler: GPU test below
+        speech, left, right, s0, s1 = _feed_item(tmp_path, fname, start, stop, sliding)
+        assert (left, right) == ("spk", fname)
+        assert [int(s0), int(s1)] == g[name + "_bounds"].tolist(), name
+        assert numpy.array_equal(speech.numpy(), g[name + "_speech"]), name
+        # and the oracle's restatement of the same arithmetic
+        seg, o0, o1 = FR.cut_segment(g["pcm_" + fname], start, stop, 16000, 0.165)
+        if sliding:
+            seg = FR.windows(seg, 1.0, 0.5)
+        assert [o0, o1] == g[name + "_bounds"].tolist() and numpy.array_equal(seg, g[name + "_speech"]), name
+
+
+@pytest.mark.gpu
+def test_idmapset_resamples_like_the_reference(tmp_path):
+    g = golden("feed_path.npz")
+    _feed_files(tmp_path, g)
+    speech, _, _, s0, s1 = _feed_item(tmp_path, "f8k", None, None, False)
+    assert [int(s0), int(s1)] == g["whole_8k_resampled_bounds"].tolist()
+    assert speech.shape == g["whole_8k_resampled_speech"].shape
+    assert numpy.abs(speech.cpu().numpy() - g["whole_8k_resampled_speech"]).max() < 2e-6

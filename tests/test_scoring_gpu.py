@@ -301,3 +301,14 @@ def test_trial_list_mode_and_fp16_output():
         assert torch.equal(got, full[torch.from_numpy(mask).cuda()])            # same arithmetic, same order
         half = score_matrix(E, T, r, q, cst=0.25, alpha=1.5, passes=0, out_dtype=torch.float16)
         assert half.dtype == torch.float16 and torch.equal(half, full.half())
+
+
+def test_asnorm_statistics_over_more_rows_than_one_scratch_panel():
+    """The cohort score matrix is produced in panels of at most 16384 rows: 20000 rows cross a panel boundary."""
+    from sidekit_b200.bulk import _asnorm_stats_cuda
+    X = torch.nn.functional.normalize(torch.from_numpy(synth.synth_embeddings(20000, 32, seed=81, unit_norm=False)).float(), dim=1).cuda()
+    coh = torch.nn.functional.normalize(torch.from_numpy(synth.synth_embeddings(333, 32, seed=82, unit_norm=False)).float(), dim=1).cuda()
+    mean, std = _asnorm_stats_cuda(X, coh, 200)
+    top = torch.topk(X.double() @ coh.double().T, 200, dim=1)[0]
+    assert (mean.double() - top.mean(dim=1)).abs().max().item() < 1e-5
+    assert (std.double() - top.std(dim=1)).abs().max().item() < 1e-5

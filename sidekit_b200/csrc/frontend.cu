@@ -93,6 +93,10 @@ __device__ __forceinline__ void fft_dif(float2 (&a)[N]) {
 template <int NC, int WPC>
 __global__ void __launch_bounds__(WPC * 32, (640 / (WPC * 32)) > 0 ? 640 / (WPC * 32) : 1) frontend_kernel(const FrontendParams p, int frames_per_cta) {
     constexpr int A = NC / 32;
+    // Frames per warp and trip.  With A = 16 (log-Mel, n_fft 1024) the 32-point transforms of step 3 occupy only 16 lanes:
+    // the warp takes TWO frames per trip and runs both frames' step 3 together (lanes 0-15 / 16-31), which halves the
+    // issue slots of the heaviest step (the kernel is issue-bound, profiles/r01f_ncu_frontend_logmel.txt).
+    constexpr int FPW = A == 16 ? 2 : 1;
     constexpr int ZS = (A * 33 > NC + 2 ? A * 33 : NC + 2);      // complex slots per frame buffer: S[A][33] or Z[NC] / pwr[NC + 1]
     // Every table a frame touches lives in shared memory (twiddles, window, sparse mel filterbank, DCT): read through
     // L1 / L2 they were 52 KB per frame on the MFCC front-end, 2.8 GB of L2 reads for 0.38 GB of audio
@@ -100,8 +104,8 @@ __global__ void __launch_bounds__(WPC * 32, (640 / (WPC * 32)) > 0 ? 640 / (WPC 
     extern __shared__ __align__(16) uint8_t fsm[];
     float2* tw = reinterpret_cast<float2*>(fsm);                 // [A][32]: w_NC^{n2 k1}
     float2* twf = tw + NC;                                       // [NC + 1] (+1 pad): e^{-2 pi i k / n_fft}
-    float2* zall = twf + NC + 2;                                 // [WPC][ZS]
-    float* melall = reinterpret_cast<float*>(zall + WPC * ZS);   // [WPC][n_mels]
+    float2* zall = twf + NC + 2;                                 // [WPC][FPW][ZS]
+    float* melall = reinterpret_cast<float*>(zall + WPC * FPW * ZS);   // [WPC][n_mels]
     float* s_win = melall + WPC * p.n_mels;                      // [win]
     float* s_melw = s_win + p.win;                               // [n_w]
     int* s_lo = reinterpret_cast<int*>(s_melw + p.n_w);          // [n_mels] x 3: first bin, count, weight offset
@@ -124,11 +128,17 @@ __global__ void __launch_bounds__(WPC * 32, (640 / (WPC * 32)) > 0 ? 640 / (WPC 
     __syncthreads();
     const float* x = p.wave + p.wave_off[b];
     const int L = p.wave_len[b];
-    float2* z = zall + warp * ZS;
+    float2* zwarp = zall + warp * FPW * ZS;
     float* mel = melall + warp * p.n_mels;
     const int half_win = p.win >> 1;
 
-    for (int frame = t_begin + warp; frame < t_end; frame += WPC) {
+    for (int frame0 = t_begin + warp * FPW; frame0 < t_end; frame0 += WPC * FPW) {
+      // ---- steps 0-2 for each frame of the trip (frame validity is warp-uniform)
+#pragma unroll
+      for (int f = 0; f < FPW; ++f) {
+        const int frame = frame0 + f;
+        if (frame >= t_end) break;
+        float2* z = zwarp + f * ZS;
         // ---- step 0: the frame's samples (pre-emphasis, reflect padding, window) into the frame buffer.  All the loads
         // of the loop are independent, so eight of them are in flight per lane; fetched inside step 1 the compiler
         // serialised them behind the FFT's registers (one L2 / HBM round trip per pair of points: 32 % of the MFCC
@@ -173,22 +183,33 @@ __global__ void __launch_bounds__(WPC * 32, (640 / (WPC * 32)) > 0 ? 640 / (WPC 
                 z[k1 * 33 + lane] = y;
             }
         }
+      }
         __syncwarp();
-        // ---- step 3: 32 points per lane (lanes k1 < A), natural-order store
+        // ---- step 3: 32 points per lane, natural-order store.  A = 32: lane k1 of the single frame; A = 16: lanes 0-15 take
+        // the rows of the trip's first frame, lanes 16-31 those of the second
         {
             float2 c[32];
-            if (lane < A) {
+            const int f3 = FPW == 2 ? (lane >> 4) : 0, k1 = FPW == 2 ? (lane & 15) : lane;
+            const bool act = k1 < A && frame0 + f3 < t_end;
+            float2* z3 = zwarp + f3 * ZS;
+            if (act) {
 #pragma unroll
-                for (int n2 = 0; n2 < 32; ++n2) c[n2] = z[lane * 33 + n2];
+                for (int n2 = 0; n2 < 32; ++n2) c[n2] = z3[k1 * 33 + n2];
             }
             __syncwarp();                                        // every row is in registers before Z overwrites S
-            if (lane < A) {
+            if (act) {
                 fft_dif<32>(c);
 #pragma unroll
-                for (int r = 0; r < 32; ++r) z[lane + A * brev<32>(r)] = c[r];     // Z[k1 + A k2]
+                for (int r = 0; r < 32; ++r) z3[k1 + A * brev<32>(r)] = c[r];     // Z[k1 + A k2]
             }
         }
         __syncwarp();
+      // ---- power spectrum, mel, log (and DCT) per frame of the trip
+#pragma unroll
+      for (int f = 0; f < FPW; ++f) {
+        const int frame = frame0 + f;
+        if (frame >= t_end) break;
+        float2* z = zwarp + f * ZS;
         // unpack the real spectrum, take |X|^2 for k = 0..NC and store it in natural order into a power buffer that
         // aliases z (all reads first).  Bins k and NC - k share everything but two signs:
         //   X[k]      = ((s.x + wd.y) - i (wd.x - s.y)) / 2,   X[NC - k] = conj-symmetric with wd -> conj(wd),
@@ -290,6 +311,7 @@ __global__ void __launch_bounds__(WPC * 32, (640 / (WPC * 32)) > 0 ? 640 / (WPC 
             }
         }
         __syncwarp();     // the next frame's fill overwrites z / pwr / mel
+      }
     }
 }
 
@@ -443,7 +465,8 @@ int frontend_launch(const FrontendConsts& fc, const float* wave, const long long
     }
     auto smem_bytes = [&](int NC, int WPC, int* dct_off) {
         const size_t zs = std::max<size_t>((size_t)(NC / 32) * 33, (size_t)NC + 2);      // complex slots per frame buffer (kernel: ZS)
-        size_t floats = 2 * (size_t)NC + 2 * ((size_t)NC + 2) + 2 * (size_t)WPC * zs + (size_t)WPC * fc.n_mels + fc.win + fc.n_w +
+        const size_t fpw = NC / 32 == 16 ? 2 : 1;                                        // frame buffers per warp (kernel: FPW)
+        size_t floats = 2 * (size_t)NC + 2 * ((size_t)NC + 2) + 2 * (size_t)WPC * fpw * zs + (size_t)WPC * fc.n_mels + fc.win + fc.n_w +
                         3 * (size_t)fc.n_mels;
         floats = (floats + 3) / 4 * 4;
         *dct_off = (int)floats;

@@ -359,8 +359,9 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if (word & (1u << j)) {
-                                const float qq = p.q ? __ldg(p.q + col0 + j) * p.rq_scale : 0.f;
-                                *o++ = fmaf(v[j], mul, rr) + qq;
+                                // the same roundings as the matrix path (product, then sum: no contraction into an FMA)
+                                const float qq = p.q ? __fmul_rn(__ldg(p.q + col0 + j), p.rq_scale) : 0.f;
+                                *o++ = __fadd_rn(fmaf(v[j], mul, rr), qq);
                             }
                         }
                     }

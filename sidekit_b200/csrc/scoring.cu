@@ -382,8 +382,10 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                                               fmaf(v[4 * k + 3], mul, rr));
                     __syncwarp();
                     const int rs = lane >> 3;
+                    // explicit roundings (product, then sum) so that every output mode performs the same arithmetic
                     float4 qv = qpre[cbi];
-                    qv.x *= p.rq_scale; qv.y *= p.rq_scale; qv.z *= p.rq_scale; qv.w *= p.rq_scale;
+                    qv.x = __fmul_rn(qv.x, p.rq_scale); qv.y = __fmul_rn(qv.y, p.rq_scale);
+                    qv.z = __fmul_rn(qv.z, p.rq_scale); qv.w = __fmul_rn(qv.w, p.rq_scale);
                     if (p.out_mode == 2) {
                         __half* o = reinterpret_cast<__half*>(p.out) + (size_t)(row0 + rs) * p.ld_out + col0 + c4;
                         const size_t step = (size_t)4 * p.ld_out;
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                         for (int it = 0; it < 8; ++it, o += step) {
                             if (it * 4 + rs >= n_rows) break;
                             const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
-                            const __half2 h0 = __floats2half2_rn(x.x + qv.x, x.y + qv.y), h1 = __floats2half2_rn(x.z + qv.z, x.w + qv.w);
+                            const __half2 h0 = __floats2half2_rn(__fadd_rn(x.x, qv.x), __fadd_rn(x.y, qv.y)), h1 = __floats2half2_rn(__fadd_rn(x.z, qv.z), __fadd_rn(x.w, qv.w));
                             __stcs(reinterpret_cast<uint2*>(o), make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1)));
                         }
                     } else if (p.out_f64) {
@@ -401,8 +403,8 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                         for (int it = 0; it < 8; ++it, o += step) {
                             if (it * 4 + rs >= n_rows) break;
                             const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
-                            __stcs(reinterpret_cast<double2*>(o), make_double2((double)(x.x + qv.x), (double)(x.y + qv.y)));
-                            __stcs(reinterpret_cast<double2*>(o) + 1, make_double2((double)(x.z + qv.z), (double)(x.w + qv.w)));
+                            __stcs(reinterpret_cast<double2*>(o), make_double2((double)__fadd_rn(x.x, qv.x), (double)__fadd_rn(x.y, qv.y)));
+                            __stcs(reinterpret_cast<double2*>(o) + 1, make_double2((double)__fadd_rn(x.z, qv.z), (double)__fadd_rn(x.w, qv.w)));
                         }
                     } else {
                         float* o = reinterpret_cast<float*>(p.out) + (size_t)(row0 + rs) * p.ld_out + col0 + c4;
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                             const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + rs) * 36 + c4);
                             // streaming store: the score matrix is written once and never re-read by this kernel, so it
                             // should not evict the T operand tiles from L2
-                            __stcs(reinterpret_cast<float4*>(o), make_float4(x.x + qv.x, x.y + qv.y, x.z + qv.z, x.w + qv.w));
+                            __stcs(reinterpret_cast<float4*>(o), make_float4(__fadd_rn(x.x, qv.x), __fadd_rn(x.y, qv.y), __fadd_rn(x.z, qv.z), __fadd_rn(x.w, qv.w)));
                         }
                     }
                     continue;
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                 __syncwarp();
                 const int col = col0 + lane;
                 const bool col_ok = col < p.Nt;
-                const float qq = ((p.q && col_ok) ? __ldg(p.q + col) : 0.f) * p.rq_scale;
+                const float qq = __fmul_rn((p.q && col_ok) ? __ldg(p.q + col) : 0.f, p.rq_scale);
                 const float ca = (p.ca && col_ok) ? __ldg(p.ca + col) * mscale : 0.f;
                 float* o = reinterpret_cast<float*>(p.out) + (size_t)row0 * p.ld_out + col;
                 double* od = reinterpret_cast<double*>(p.out) + (size_t)row0 * p.ld_out + col;
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                         const float ra_r = __shfl_sync(0xffffffffu, ra, r), rr_r = __shfl_sync(0xffffffffu, rr, r);
                         sv = fmaf(sv, ra_r + ca + a0, rr_r);
                     }
-                    sv += qq;
+                    sv = __fadd_rn(sv, qq);
                     if (r < n_rows && col_ok) {
                         if (p.out_mode == 2) oh[(size_t)r * p.ld_out] = __float2half_rn(sv);
                         else if (p.out_f64) od[(size_t)r * p.ld_out] = (double)sv;

@@ -137,8 +137,6 @@ struct ScoreParams {
 
 struct TrialTables { const uint32_t* words; const uint32_t* offsets; int ld, Ne, Nt; };
 
-constexpr int kScEpiWarps = 8;
-constexpr int kScThreads = (2 + kScEpiWarps) * 32;   // warps: 0 producer, 1 MMA, 2..9 epilogue (2 per TMEM quadrant)
 constexpr int kScKChunk = 64;
 
 // smem: [ctrl 256 B][A hi (+lo)][B ring][8 warps x [32][36] fp32 transpose buffers]
@@ -149,14 +147,20 @@ struct ScoreSmem {
     static constexpr int kStageBytes = 128 * kChunk * 2;              // one part (hi or lo) of one operand of one stage
     // resident-panel mode: a stage holds a T chunk; streaming mode (large K): an E chunk and a T chunk
     static constexpr int kRingStageBytes = (STREAM_A ? 2 : 1) * kParts * kStageBytes;
-    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? 7 : 3);
+    // Epilogue warps: the epilogue (TMEM load, row / column terms, 32 x 32 transpose, stores) is a latency chain of ~3000
+    // cycles per 128 x 128 tile against 1024 cycles of MMAs -- with 8 warps (two 32-column blocks each) the tensor pipe was
+    // 9 % busy and DRAM 55 % (profiles/r02h_ncu_score_gemm_f32.txt).  16 warps take one block each; the resident-panel
+    // split-precision variant keeps 8 (its hi + lo panel leaves no room for 16 transpose buffers).
+    static constexpr int kEpiWarps = (PASSES == 1 || STREAM_A) ? 16 : 8;
+    static constexpr int kThreads = (2 + kEpiWarps) * 32;  // warps: 0 producer, 1 MMA, 2.. epilogue (kEpiWarps / 4 per TMEM quadrant)
+    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? 5 : 3);
     static constexpr int kStageRowBytes = 36 * 4;        // [32][36] fp32 transpose buffer per epilogue warp (16-byte rows)
     __host__ __device__ static size_t a_bytes(int Dp) { return STREAM_A ? 0 : (size_t)kParts * 128 * Dp * 2; }
-    static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kRingStageBytes + kScEpiWarps * 32 * kStageRowBytes; }
+    static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kRingStageBytes + kEpiWarps * 32 * kStageRowBytes; }
 };
 
 template <int PASSES, bool STREAM_A>
-__global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScoreParams p) {
+__global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) score_gemm_kernel(const ScoreParams p) {
     using SM = ScoreSmem<PASSES, STREAM_A>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int i = 0; i < SM::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kScEpiWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], SM::kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -284,9 +288,10 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
             __syncwarp();
         }
     } else if (warp >= 2) {
-        // ---------------------------------------------------------------- epilogue: 8 warps, 2 per TMEM lane quadrant
+        // ---------------------------------------------------------------- epilogue: kEpiWarps / 4 warps per TMEM lane quadrant
+        constexpr int NB = 32 / SM::kEpiWarps;             // 32-column blocks per warp and tile: 2 (8 warps) or 1 (16 warps)
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;                  // which two of the four 32-column blocks
+        const int part = (warp - 2) >> 2;                  // which NB of the four 32-column blocks
         float* stg = reinterpret_cast<float*>(stage_smem) + (warp - 2) * 32 * 36;   // warp-private [32][36] transpose buffer
         const int esz = p.out_mode == 1 ? 8 : (p.out_mode == 2 ? 2 : 4);
         const bool out_ok = p.out_mode == 3 ? true
@@ -303,6 +308,19 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
         int cur_panel = -1;
         float ra = 0.f, rr = 0.f;
         const int c4 = (lane & 7) * 4;
+        uint32_t mwn[NB], mon[NB];                         // trial-list mode: mask words / offsets of the NEXT tile
+#pragma unroll
+        for (int cbi = 0; cbi < NB; ++cbi) { mwn[cbi] = 0u; mon[cbi] = 0u; }
+        if (p.out_mode == 3 && t_begin < t_end && panel0 * 128 + q * 32 + lane < p.Ne) {
+#pragma unroll
+            for (int cbi = 0; cbi < NB; ++cbi) {
+                const int wcol = nt0 * 4 + part * NB + cbi;
+                if (wcol < p.mask_ld) {
+                    mwn[cbi] = __ldg(p.mask_words + (size_t)(panel0 * 128 + q * 32 + lane) * p.mask_ld + wcol);
+                    mon[cbi] = __ldg(p.word_off + (size_t)(panel0 * 128 + q * 32 + lane) * p.mask_ld + wcol);
+                }
+            }
+        }
         for (int t = t_begin; t < t_end; ++t, ++nt_done) {
             const int buf = (int)(nt_done & 1);
             const int row0 = panel * 128 + q * 32;
@@ -313,36 +331,43 @@ __global__ void __launch_bounds__(kScThreads, 1) score_gemm_kernel(const ScorePa
                 rr = fmaf((p.r && my_row < p.Ne) ? p.r[my_row] : 0.f, p.rq_scale, p.c0);
             }
             const int n_rows = min(32, p.Ne - row0);
-            float4 qpre[2];
+            float4 qpre[NB];
 #pragma unroll
-            for (int cbi = 0; cbi < 2; ++cbi) {
-                const int col = nt * 128 + (half * 2 + cbi) * 32 + c4;
+            for (int cbi = 0; cbi < NB; ++cbi) {
+                const int col = nt * 128 + (part * NB + cbi) * 32 + c4;
                 qpre[cbi] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.q && vec_ok && col + 4 <= p.Nt) qpre[cbi] = __ldg(reinterpret_cast<const float4*>(p.q + col));
             }
-            // trial-list mode: lane = row (the accumulator's native layout, no transpose): this row's mask word of both
-            // 32-column blocks and, for the non-empty ones, their output offsets -- fetched before the accumulator wait
-            // like the column terms
-            uint32_t mw[2] = {0u, 0u}, mo[2] = {0u, 0u};
-            if (p.out_mode == 3 && my_row < p.Ne) {
+            // trial-list mode: lane = row (the accumulator's native layout, no transpose): this row's mask words and output
+            // offsets, fetched ONE TILE AHEAD (a mask word comes from L2 / HBM, ~1 us away: loaded at the top of its own tile it
+            // was 36 % of the kernel's stall samples and the tensor pipe sat at 4 %)
+            uint32_t mw[NB], mo[NB];
 #pragma unroll
-                for (int cbi = 0; cbi < 2; ++cbi) {
-                    const int wcol = nt * 4 + half * 2 + cbi;
-                    if (wcol < p.mask_ld) mw[cbi] = __ldg(p.mask_words + (size_t)my_row * p.mask_ld + wcol);
+            for (int cbi = 0; cbi < NB; ++cbi) { mw[cbi] = mwn[cbi]; mo[cbi] = mon[cbi]; mwn[cbi] = 0u; mon[cbi] = 0u; }
+            if (p.out_mode == 3 && t + 1 < t_end) {
+                int ntn = nt + 1, pn = panel;
+                if (ntn == p.n_ntiles) { ntn = 0; ++pn; }
+                const int rown = pn * 128 + q * 32 + lane;
+                if (rown < p.Ne) {
+#pragma unroll
+                    for (int cbi = 0; cbi < NB; ++cbi) {
+                        const int wcol = ntn * 4 + part * NB + cbi;
+                        if (wcol < p.mask_ld) {
+                            mwn[cbi] = __ldg(p.mask_words + (size_t)rown * p.mask_ld + wcol);
+                            mon[cbi] = __ldg(p.word_off + (size_t)rown * p.mask_ld + wcol);
+                        }
+                    }
                 }
-#pragma unroll
-                for (int cbi = 0; cbi < 2; ++cbi)
-                    if (mw[cbi] != 0u) mo[cbi] = __ldg(p.word_off + (size_t)my_row * p.mask_ld + nt * 4 + half * 2 + cbi);
             }
             mbar_wait(&acc_full[buf], (nt_done >> 1) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int cbi = 0; cbi < 2; ++cbi) {
-                const int cb = half * 2 + cbi;
+            for (int cbi = 0; cbi < NB; ++cbi) {
+                const int cb = part * NB + cbi;
                 const int col0 = nt * 128 + cb * 32;
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + cb * 32, v);
-                if (cbi == 1) {   // this warp's share of the accumulator is read: release the TMEM buffer
+                if (cbi == NB - 1) {   // this warp's share of the accumulator is read: release the TMEM buffer
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -576,7 +601,7 @@ static int launch_score(const ScoreParams& p, int grid, cudaStream_t st) {
     if (configured.first()) {
         SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<PASSES, STREAM_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
-    SKB_CUDA_CHECK(launch_pdl(score_gemm_kernel<PASSES, STREAM_A>, dim3(grid), dim3(kScThreads), smem, st, p));
+    SKB_CUDA_CHECK(launch_pdl(score_gemm_kernel<PASSES, STREAM_A>, dim3(grid), dim3(ScoreSmem<PASSES, STREAM_A>::kThreads), smem, st, p));
     g_launches++;
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;

@@ -147,13 +147,13 @@ struct ScoreSmem {
     static constexpr int kStageBytes = 128 * kChunk * 2;              // one part (hi or lo) of one operand of one stage
     // resident-panel mode: a stage holds a T chunk; streaming mode (large K): an E chunk and a T chunk
     static constexpr int kRingStageBytes = (STREAM_A ? 2 : 1) * kParts * kStageBytes;
-    // Epilogue warps: the epilogue (TMEM load, row / column terms, 32 x 32 transpose, stores) is a latency chain of ~3000
-    // cycles per 128 x 128 tile against 1024 cycles of MMAs -- with 8 warps (two 32-column blocks each) the tensor pipe was
-    // 9 % busy and DRAM 55 % (profiles/r02h_ncu_score_gemm_f32.txt).  16 warps take one block each; the resident-panel
-    // split-precision variant keeps 8 (its hi + lo panel leaves no room for 16 transpose buffers).
-    static constexpr int kEpiWarps = (PASSES == 1 || STREAM_A) ? 16 : 8;
+    // Epilogue warps: 8 (two 32-column blocks each).  16 warps with one block each -- to hide the epilogue's latency chain,
+    // which leaves the tensor pipe 9 % busy and DRAM at 55 % (profiles/r02h_ncu_score_gemm_f32.txt) -- measured SLOWER
+    // (343 -> 571 us at 20k x 20k: 576 threads cap the kernel at 96 registers and the ring at 5 stages) and is not adopted
+    // (profiles/r02_score_epilogue_experiments.txt).
+    static constexpr int kEpiWarps = 8;
     static constexpr int kThreads = (2 + kEpiWarps) * 32;  // warps: 0 producer, 1 MMA, 2.. epilogue (kEpiWarps / 4 per TMEM quadrant)
-    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? 5 : 3);
+    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? 7 : 3);
     static constexpr int kStageRowBytes = 36 * 4;        // [32][36] fp32 transpose buffer per epilogue warp (16-byte rows)
     __host__ __device__ static size_t a_bytes(int Dp) { return STREAM_A ? 0 : (size_t)kParts * 128 * Dp * 2; }
     static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kRingStageBytes + kEpiWarps * 32 * kStageRowBytes; }

@@ -147,19 +147,21 @@ struct ScoreSmem {
     static constexpr int kStageBytes = 128 * kChunk * 2;              // one part (hi or lo) of one operand of one stage
     // resident-panel mode: a stage holds a T chunk; streaming mode (large K): an E chunk and a T chunk
     static constexpr int kRingStageBytes = (STREAM_A ? 2 : 1) * kParts * kStageBytes;
-    // Epilogue warps: 8 (two 32-column blocks each).  16 warps with one block each -- to hide the epilogue's latency chain,
-    // which leaves the tensor pipe 9 % busy and DRAM at 55 % (profiles/r02h_ncu_score_gemm_f32.txt) -- measured SLOWER
-    // (343 -> 571 us at 20k x 20k: 576 threads cap the kernel at 96 registers and the ring at 5 stages) and is not adopted
-    // (profiles/r02_score_epilogue_experiments.txt).
+    // Epilogue warps (SKB_SCORE_EPI16 compile-time switch: 16 warps with one 32-column block each for the single-pass /
+    // streaming variants instead of 8 with two; see profiles/r02_score_epilogue_experiments.txt)
+#ifdef SKB_SCORE_EPI16
+    static constexpr int kEpiWarps = (PASSES == 1 || STREAM_A) ? 16 : 8;
+#else
     static constexpr int kEpiWarps = 8;
+#endif
     static constexpr int kThreads = (2 + kEpiWarps) * 32;  // warps: 0 producer, 1 MMA, 2.. epilogue (kEpiWarps / 4 per TMEM quadrant)
-    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? 7 : 3);
+    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? (kEpiWarps == 16 ? 5 : 7) : 3);
     static constexpr int kStageRowBytes = 36 * 4;        // [32][36] fp32 transpose buffer per epilogue warp (16-byte rows)
     __host__ __device__ static size_t a_bytes(int Dp) { return STREAM_A ? 0 : (size_t)kParts * 128 * Dp * 2; }
     static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kRingStageBytes + kEpiWarps * 32 * kStageRowBytes; }
 };
 
-template <int PASSES, bool STREAM_A>
+template <int PASSES, bool STREAM_A, bool TRIALS>
 __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) score_gemm_kernel(const ScoreParams p) {
     using SM = ScoreSmem<PASSES, STREAM_A>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
         }
     } else if (warp >= 2) {
         // ---------------------------------------------------------------- epilogue: kEpiWarps / 4 warps per TMEM lane quadrant
-        constexpr int NB = 32 / SM::kEpiWarps;             // 32-column blocks per warp and tile: 2 (8 warps) or 1 (16 warps)
+        constexpr int NB = 16 / SM::kEpiWarps;             // 32-column blocks per warp and tile: 2 (8 warps) or 1 (16 warps)
         const int q = warp & 3;
         const int part = (warp - 2) >> 2;                  // which NB of the four 32-column blocks
         float* stg = reinterpret_cast<float*>(stage_smem) + (warp - 2) * 32 * 36;   // warp-private [32][36] transpose buffer
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
         uint32_t mwn[NB], mon[NB];                         // trial-list mode: mask words / offsets of the NEXT tile
 #pragma unroll
         for (int cbi = 0; cbi < NB; ++cbi) { mwn[cbi] = 0u; mon[cbi] = 0u; }
-        if (p.out_mode == 3 && t_begin < t_end && panel0 * 128 + q * 32 + lane < p.Ne) {
+        if (TRIALS && t_begin < t_end && panel0 * 128 + q * 32 + lane < p.Ne) {
 #pragma unroll
             for (int cbi = 0; cbi < NB; ++cbi) {
                 const int wcol = nt0 * 4 + part * NB + cbi;
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
             uint32_t mw[NB], mo[NB];
 #pragma unroll
             for (int cbi = 0; cbi < NB; ++cbi) { mw[cbi] = mwn[cbi]; mo[cbi] = mon[cbi]; mwn[cbi] = 0u; mon[cbi] = 0u; }
-            if (p.out_mode == 3 && t + 1 < t_end) {
+            if (TRIALS && t + 1 < t_end) {
                 int ntn = nt + 1, pn = panel;
                 if (ntn == p.n_ntiles) { ntn = 0; ++pn; }
                 const int rown = pn * 128 + q * 32 + lane;
@@ -373,21 +375,27 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
                 if (col0 >= p.Nt || n_rows <= 0) continue;
-                if (p.out_mode == 3) {
+                if (TRIALS) {
                     // Only the trials of the mask are written, compacted in row-major order: each lane walks the set bits
-                    // of ITS row's word.  No transpose, no shared memory, (almost) no stores for a sparse mask: the kernel
-                    // is then bound by the tensor pipe / the operand stream instead of the HBM write.
+                    // of ITS row's word (lane = row, the accumulator's native layout: no transpose).  A block without any
+                    // trial costs a TMEM load and a vote; otherwise the rows are parked in the warp's staging buffer so that
+                    // the set bits can index them.  (Almost) no stores for a sparse mask: the kernel is then bound by the
+                    // operand stream / the tensor pipe instead of the HBM write.
                     uint32_t word = mw[cbi];
-                    if (word != 0u) {
+                    if (__any_sync(0xffffffffu, word != 0u)) {
+                        __syncwarp();
+                        float4* srow = reinterpret_cast<float4*>(stg + lane * 36);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) srow[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                        __syncwarp();
                         const float mul = ra + a0;
                         float* o = reinterpret_cast<float*>(p.out) + mo[cbi];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (word & (1u << j)) {
-                                // the same roundings as the matrix path (product, then sum: no contraction into an FMA)
-                                const float qq = p.q ? __fmul_rn(__ldg(p.q + col0 + j), p.rq_scale) : 0.f;
-                                *o++ = __fadd_rn(fmaf(v[j], mul, rr), qq);
-                            }
+                        while (word != 0u) {
+                            const int j = __ffs(word) - 1;
+                            word &= word - 1u;
+                            // the same roundings as the matrix path (product, then sum: no contraction into an FMA)
+                            const float qq = p.q ? __fmul_rn(__ldg(p.q + col0 + j), p.rq_scale) : 0.f;
+                            *o++ = __fadd_rn(fmaf(stg[lane * 36 + j], mul, rr), qq);
                         }
                     }
                     continue;
@@ -590,7 +598,7 @@ static void ws_operand(PackedOp* op, int rows, int D, int slot, size_t offset_ha
     op->exp = reinterpret_cast<int*>(op->stats + 2);
 }
 
-template <int PASSES, bool STREAM_A>
+template <int PASSES, bool STREAM_A, bool TRIALS = false>
 static int launch_score(const ScoreParams& p, int grid, cudaStream_t st) {
     static PerDeviceOnce configured;
     const size_t smem = ScoreSmem<PASSES, STREAM_A>::total(p.Dp);
@@ -599,9 +607,9 @@ static int launch_score(const ScoreParams& p, int grid, cudaStream_t st) {
         return SKB_ERR_ARG;
     }
     if (configured.first()) {
-        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<PASSES, STREAM_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<PASSES, STREAM_A, TRIALS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
-    SKB_CUDA_CHECK(launch_pdl(score_gemm_kernel<PASSES, STREAM_A>, dim3(grid), dim3(ScoreSmem<PASSES, STREAM_A>::kThreads), smem, st, p));
+    SKB_CUDA_CHECK(launch_pdl(score_gemm_kernel<PASSES, STREAM_A, TRIALS>, dim3(grid), dim3(ScoreSmem<PASSES, STREAM_A>::kThreads), smem, st, p));
     g_launches++;
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
@@ -636,6 +644,16 @@ int gemm_packed(const PackedOp& E, const PackedOp& T, const float* ra, const flo
     // Both pass variants are launched when the count is decided on the device; exactly one does the work.
     static const bool force_stream = getenv("SKB_FORCE_STREAM_A") != nullptr;   // experiment knob
     const bool stream_a = E.Dp > 256 || force_stream;
+    if (out_mode == 3) {
+        if (stream_a) {
+            set_last_error(__FILE__, __LINE__, "trial-list mode supports embeddings of up to 256 dimensions");
+            return SKB_ERR_ARG;
+        }
+        if (passes != 3) rc = launch_score<1, false, true>(p, grid, st);
+        if (rc) return rc;
+        if (passes != 1) rc = launch_score<3, false, true>(p, grid, st);
+        return rc;
+    }
     if (passes != 3) rc = stream_a ? launch_score<1, true>(p, grid, st) : launch_score<1, false>(p, grid, st);
     if (rc) return rc;
     if (passes != 1) rc = stream_a ? launch_score<3, true>(p, grid, st) : launch_score<3, false>(p, grid, st);

@@ -140,7 +140,10 @@ struct TrialTables { const uint32_t* words; const uint32_t* offsets; int ld, Ne,
 constexpr int kScKChunk = 64;
 
 // smem: [ctrl 256 B][A hi (+lo)][B ring][8 warps x [32][36] fp32 transpose buffers]
-template <int PASSES, bool STREAM_A>
+// MT = row panels per work item (resident-panel single-pass variant only): with MT = 2 a streamed T tile feeds TWO 128-row
+// panels, which halves the L2 -> shared-memory operand traffic per trial (64 KB per 128 x 128 tile at MT = 1: at 20k x 20k
+// that is 1.6 GB per call, as much as the fp32 matrix itself, and what bounds the modes that do not write the matrix).
+template <int PASSES, bool STREAM_A, int MT = 1>
 struct ScoreSmem {
     static constexpr int kParts = PASSES == 1 ? 1 : 2;
     static constexpr int kChunk = PASSES == 1 ? 64 : 32;              // K elements per stage
@@ -155,15 +158,17 @@ struct ScoreSmem {
     static constexpr int kEpiWarps = 8;
 #endif
     static constexpr int kThreads = (2 + kEpiWarps) * 32;  // warps: 0 producer, 1 MMA, 2.. epilogue (kEpiWarps / 4 per TMEM quadrant)
-    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? (kEpiWarps == 16 ? 5 : 7) : 3);
+    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? (MT == 2 ? 3 : (kEpiWarps == 16 ? 5 : 7)) : 3);
+    static constexpr int kTmemCols = 2 * MT * 128;       // double-buffered accumulators
     static constexpr int kStageRowBytes = 36 * 4;        // [32][36] fp32 transpose buffer per epilogue warp (16-byte rows)
-    __host__ __device__ static size_t a_bytes(int Dp) { return STREAM_A ? 0 : (size_t)kParts * 128 * Dp * 2; }
+    __host__ __device__ static size_t a_bytes(int Dp) { return STREAM_A ? 0 : (size_t)MT * kParts * 128 * Dp * 2; }
     static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kRingStageBytes + kEpiWarps * 32 * kStageRowBytes; }
 };
 
-template <int PASSES, bool STREAM_A, bool TRIALS>
-__global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) score_gemm_kernel(const ScoreParams p) {
-    using SM = ScoreSmem<PASSES, STREAM_A>;
+template <int PASSES, bool STREAM_A, bool TRIALS, int MT>
+__global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A, MT>::kThreads, 1) score_gemm_kernel(const ScoreParams p) {
+    using SM = ScoreSmem<PASSES, STREAM_A, MT>;
+    static_assert(MT == 1 || (PASSES == 1 && !STREAM_A), "two row panels per item: single-pass resident-panel variant only");
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* a_empty = a_full + 1;
@@ -182,9 +187,12 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
     if (decide_passes(p.statsE, p.statsT, p.D, p.abs_alpha, p.passes_req) != PASSES) return;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // contiguous run of tiles for this CTA (panel-major), walked with incremental (panel, nt) counters
-    const int t_begin = (int)((long long)p.tiles_total * blockIdx.x / gridDim.x);
-    const int t_end = (int)((long long)p.tiles_total * (blockIdx.x + 1) / gridDim.x);
+    // contiguous run of work items for this CTA (panel-group-major), walked with incremental (group, nt) counters; an item =
+    // MT row panels x one 128-column tile ("panel" below counts panel GROUPS)
+    const int n_panels = p.Ne_pad >> 7;
+    const int tiles_total = ((n_panels + MT - 1) / MT) * p.n_ntiles;
+    const int t_begin = (int)((long long)tiles_total * blockIdx.x / gridDim.x);
+    const int t_end = (int)((long long)tiles_total * (blockIdx.x + 1) / gridDim.x);
     const int panel0 = t_begin / p.n_ntiles, nt0 = t_begin % p.n_ntiles;
     const int n_kc = p.Dp / SM::kChunk;
 
@@ -195,7 +203,7 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], SM::kEpiWarps); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<256>(tmem_slot);
+    if (warp == 1) tmem_alloc<SM::kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -211,12 +219,14 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
                 if (!STREAM_A && new_panel) {
                     mbar_wait(a_empty, a_ph);
                     a_ph ^= 1;
-                    mbar_arrive_expect_tx(a_full, SM::kParts * a_part);
-                    for (int part = 0; part < SM::kParts; ++part) {
-                        const uint16_t* src = (part == 0 ? p.Ehi : p.Elo) + (size_t)panel * p.Dp * 128;
-                        for (uint32_t off = 0; off < a_part; off += 32768)      // whole panel image is contiguous
-                            bulk_g2s(a_smem + part * a_part + off, src + off / 2, min(32768u, a_part - off), a_full);
-                    }
+                    const int n_pan = min(MT, n_panels - panel * MT);
+                    mbar_arrive_expect_tx(a_full, n_pan * SM::kParts * a_part);
+                    for (int m = 0; m < n_pan; ++m)
+                        for (int part = 0; part < SM::kParts; ++part) {
+                            const uint16_t* src = (part == 0 ? p.Ehi : p.Elo) + (size_t)(panel * MT + m) * p.Dp * 128;
+                            for (uint32_t off = 0; off < a_part; off += 32768)      // whole panel image is contiguous
+                                bulk_g2s(a_smem + (m * SM::kParts + part) * a_part + off, src + off / 2, min(32768u, a_part - off), a_full);
+                        }
                 }
                 for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(&b_empty[s], b_ph);
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
                     uint8_t* dst = b_smem + (size_t)s * SM::kRingStageBytes;
                     if (STREAM_A) {
                         for (int part = 0; part < SM::kParts; ++part, dst += SM::kStageBytes) {
-                            const uint16_t* src = (part == 0 ? p.Ehi : p.Elo) + ((size_t)panel * p.Dp + (size_t)kc * SM::kChunk) * 128;
+                            const uint16_t* src = (part == 0 ? p.Ehi : p.Elo) + ((size_t)panel * p.Dp + (size_t)kc * SM::kChunk) * 128;   // (MT == 1)
                             bulk_g2s(dst, src, SM::kStageBytes, &b_full[s]);
                         }
                     }
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
         const uint32_t idesc = umma_idesc_f16(128, 128, false);
         const uint64_t desc_hi = (static_cast<uint64_t>(2048 >> 4) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
                                  (static_cast<uint64_t>(1) << 46);
-        int nt = nt0, s = 0;
+        int nt = nt0, s = 0, group = panel0;
         uint32_t b_ph = 0, a_ph = 0, nt_done = 0;
         bool new_panel = true;
         for (int t = t_begin; t < t_end; ++t, ++nt_done) {
@@ -251,10 +261,11 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
                 mbar_wait(a_full, a_ph);
                 a_ph ^= 1;
             }
+            const int n_pan = min(MT, n_panels - group * MT);
             const int buf = (int)(nt_done & 1);
             mbar_wait(&acc_empty[buf], ((nt_done >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * 128;
+            const uint32_t d_tmem = tmem_base + buf * (MT * 128);
             for (int kc = 0; kc < n_kc; ++kc) {
                 mbar_wait(&b_full[s], b_ph);
                 tc_fence_after();
@@ -270,9 +281,13 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
                         const uint32_t b_b = b_hi + (combo == 1 ? SM::kStageBytes : 0);
 #pragma unroll
                         for (int ks = 0; ks < SM::kChunk / 16; ++ks) {
-                            const uint64_t ad = desc_hi | (((a_b + ks * 2 * 2048) >> 4) & 0x3FFF);
                             const uint64_t bd = desc_hi | (((b_b + ks * 2 * 2048) >> 4) & 0x3FFF);
-                            umma_f16(d_tmem, ad, bd, idesc, (kc > 0 || combo > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                            for (int m = 0; m < MT; ++m) {
+                                if (m >= n_pan) break;
+                                const uint64_t ad = desc_hi | (((a_b + m * SM::kParts * a_part + ks * 2 * 2048) >> 4) & 0x3FFF);
+                                umma_f16(d_tmem + m * 128, ad, bd, idesc, (kc > 0 || combo > 0 || ks > 0) ? 1u : 0u);
+                            }
                         }
                     }
                     umma_commit(&b_empty[s]);
@@ -281,7 +296,7 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
                 if (++s == SM::kBStages) { s = 0; b_ph ^= 1; }
             }
             new_panel = false;
-            if (++nt == p.n_ntiles) { nt = 0; new_panel = true; }
+            if (++nt == p.n_ntiles) { nt = 0; new_panel = true; ++group; }
             const bool last_of_panel = new_panel || (t + 1 == t_end);
             if (elect_one()) {
                 umma_commit(&acc_full[buf]);
@@ -308,31 +323,43 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
         // Row terms change only with the panel; column terms are fetched BEFORE waiting for the accumulator, so their
         // L2 latency hides behind the MMAs instead of stalling every 32x32 block (was 52 % of all stall samples).
         int cur_panel = -1;
-        float ra = 0.f, rr = 0.f;
+        float ra_m[MT], rr_m[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { ra_m[m] = 0.f; rr_m[m] = 0.f; }
         const int c4 = (lane & 7) * 4;
-        uint32_t mwn[NB], mon[NB];                         // trial-list mode: mask words / offsets of the NEXT tile
+        uint32_t mwn[MT][NB], mon[MT][NB];                 // trial-list mode: mask words / offsets of the NEXT item
+        auto fetch_mask = [&](int grp, int ntile) {
 #pragma unroll
-        for (int cbi = 0; cbi < NB; ++cbi) { mwn[cbi] = 0u; mon[cbi] = 0u; }
-        if (TRIALS && t_begin < t_end && panel0 * 128 + q * 32 + lane < p.Ne) {
+            for (int m = 0; m < MT; ++m) {
+                const int rown = (grp * MT + m) * 128 + q * 32 + lane;
 #pragma unroll
-            for (int cbi = 0; cbi < NB; ++cbi) {
-                const int wcol = nt0 * 4 + part * NB + cbi;
-                if (wcol < p.mask_ld) {
-                    mwn[cbi] = __ldg(p.mask_words + (size_t)(panel0 * 128 + q * 32 + lane) * p.mask_ld + wcol);
-                    mon[cbi] = __ldg(p.word_off + (size_t)(panel0 * 128 + q * 32 + lane) * p.mask_ld + wcol);
+                for (int cbi = 0; cbi < NB; ++cbi) {
+                    const int wcol = ntile * 4 + part * NB + cbi;
+                    mwn[m][cbi] = 0u; mon[m][cbi] = 0u;
+                    if (rown < p.Ne && wcol < p.mask_ld) {
+                        mwn[m][cbi] = __ldg(p.mask_words + (size_t)rown * p.mask_ld + wcol);
+                        mon[m][cbi] = __ldg(p.word_off + (size_t)rown * p.mask_ld + wcol);
+                    }
                 }
             }
-        }
+        };
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int cbi = 0; cbi < NB; ++cbi) { mwn[m][cbi] = 0u; mon[m][cbi] = 0u; }
+        if (TRIALS && t_begin < t_end) fetch_mask(panel0, nt0);
         for (int t = t_begin; t < t_end; ++t, ++nt_done) {
             const int buf = (int)(nt_done & 1);
-            const int row0 = panel * 128 + q * 32;
-            const int my_row = row0 + lane;
+            const int n_pan = min(MT, n_panels - panel * MT);
             if (panel != cur_panel) {
                 cur_panel = panel;
-                ra = (p.ra && my_row < p.Ne) ? p.ra[my_row] * mscale : 0.f;
-                rr = fmaf((p.r && my_row < p.Ne) ? p.r[my_row] : 0.f, p.rq_scale, p.c0);
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const int r = (panel * MT + m) * 128 + q * 32 + lane;
+                    ra_m[m] = (p.ra && r < p.Ne) ? p.ra[r] * mscale : 0.f;
+                    rr_m[m] = fmaf((p.r && r < p.Ne) ? p.r[r] : 0.f, p.rq_scale, p.c0);
+                }
             }
-            const int n_rows = min(32, p.Ne - row0);
             float4 qpre[NB];
 #pragma unroll
             for (int cbi = 0; cbi < NB; ++cbi) {
@@ -341,35 +368,33 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
                 if (p.q && vec_ok && col + 4 <= p.Nt) qpre[cbi] = __ldg(reinterpret_cast<const float4*>(p.q + col));
             }
             // trial-list mode: lane = row (the accumulator's native layout, no transpose): this row's mask words and output
-            // offsets, fetched ONE TILE AHEAD (a mask word comes from L2 / HBM, ~1 us away: loaded at the top of its own tile it
+            // offsets, fetched ONE ITEM AHEAD (a mask word comes from L2 / HBM, ~1 us away: loaded at the top of its own tile it
             // was 36 % of the kernel's stall samples and the tensor pipe sat at 4 %)
-            uint32_t mw[NB], mo[NB];
+            uint32_t mw_m[MT][NB], mo_m[MT][NB];
 #pragma unroll
-            for (int cbi = 0; cbi < NB; ++cbi) { mw[cbi] = mwn[cbi]; mo[cbi] = mon[cbi]; mwn[cbi] = 0u; mon[cbi] = 0u; }
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int cbi = 0; cbi < NB; ++cbi) { mw_m[m][cbi] = mwn[m][cbi]; mo_m[m][cbi] = mon[m][cbi]; }
             if (TRIALS && t + 1 < t_end) {
                 int ntn = nt + 1, pn = panel;
                 if (ntn == p.n_ntiles) { ntn = 0; ++pn; }
-                const int rown = pn * 128 + q * 32 + lane;
-                if (rown < p.Ne) {
-#pragma unroll
-                    for (int cbi = 0; cbi < NB; ++cbi) {
-                        const int wcol = ntn * 4 + part * NB + cbi;
-                        if (wcol < p.mask_ld) {
-                            mwn[cbi] = __ldg(p.mask_words + (size_t)rown * p.mask_ld + wcol);
-                            mon[cbi] = __ldg(p.word_off + (size_t)rown * p.mask_ld + wcol);
-                        }
-                    }
-                }
+                fetch_mask(pn, ntn);
             }
             mbar_wait(&acc_full[buf], (nt_done >> 1) & 1);
             tc_fence_after();
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+            if (m >= n_pan) break;
+            const int row0 = (panel * MT + m) * 128 + q * 32;
+            const int n_rows = min(32, p.Ne - row0);
+            const float ra = ra_m[m], rr = rr_m[m];
 #pragma unroll
             for (int cbi = 0; cbi < NB; ++cbi) {
                 const int cb = part * NB + cbi;
                 const int col0 = nt * 128 + cb * 32;
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + cb * 32, v);
-                if (cbi == NB - 1) {   // this warp's share of the accumulator is read: release the TMEM buffer
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (MT * 128) + m * 128 + cb * 32, v);
+                if (cbi == NB - 1 && m == n_pan - 1) {   // this warp's share of the accumulators is read: release the TMEM buffer
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -381,7 +406,7 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
                     // trial costs a TMEM load and a vote; otherwise the rows are parked in the warp's staging buffer so that
                     // the set bits can index them.  (Almost) no stores for a sparse mask: the kernel is then bound by the
                     // operand stream / the tensor pipe instead of the HBM write.
-                    uint32_t word = mw[cbi];
+                    uint32_t word = mw_m[m][cbi];
                     if (__any_sync(0xffffffffu, word != 0u)) {
                         __syncwarp();
                         float4* srow = reinterpret_cast<float4*>(stg + lane * 36);
@@ -389,7 +414,7 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
                         for (int k = 0; k < 8; ++k) srow[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                         __syncwarp();
                         const float mul = ra + a0;
-                        float* o = reinterpret_cast<float*>(p.out) + mo[cbi];
+                        float* o = reinterpret_cast<float*>(p.out) + mo_m[m][cbi];
                         while (word != 0u) {
                             const int j = __ffs(word) - 1;
                             word &= word - 1u;
@@ -486,13 +511,14 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A>::kThreads, 1) scor
                     }
                 }
             }
+            }   // panels of the item
             if (++nt == p.n_ntiles) { nt = 0; ++panel; }
         }
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<256>(tmem_base);
+        tmem_dealloc<SM::kTmemCols>(tmem_base);
     }
 }
 
@@ -598,18 +624,20 @@ static void ws_operand(PackedOp* op, int rows, int D, int slot, size_t offset_ha
     op->exp = reinterpret_cast<int*>(op->stats + 2);
 }
 
-template <int PASSES, bool STREAM_A, bool TRIALS = false>
-static int launch_score(const ScoreParams& p, int grid, cudaStream_t st) {
+template <int PASSES, bool STREAM_A, bool TRIALS = false, int MT = 1>
+static int launch_score(const ScoreParams& p, int /*grid_unused*/, cudaStream_t st) {
     static PerDeviceOnce configured;
-    const size_t smem = ScoreSmem<PASSES, STREAM_A>::total(p.Dp);
+    const size_t smem = ScoreSmem<PASSES, STREAM_A, MT>::total(p.Dp);
+    const int n_panels = p.Ne_pad / 128;
+    const int grid = std::min(((n_panels + MT - 1) / MT) * p.n_ntiles, kNumSMs);
     if (smem > 227 * 1024) {
         set_last_error(__FILE__, __LINE__, "score_gemm: operand panel does not fit in shared memory");
         return SKB_ERR_ARG;
     }
     if (configured.first()) {
-        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<PASSES, STREAM_A, TRIALS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<PASSES, STREAM_A, TRIALS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
-    SKB_CUDA_CHECK(launch_pdl(score_gemm_kernel<PASSES, STREAM_A, TRIALS>, dim3(grid), dim3(ScoreSmem<PASSES, STREAM_A>::kThreads), smem, st, p));
+    SKB_CUDA_CHECK(launch_pdl(score_gemm_kernel<PASSES, STREAM_A, TRIALS, MT>, dim3(grid), dim3(ScoreSmem<PASSES, STREAM_A, MT>::kThreads), smem, st, p));
     g_launches++;
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
@@ -643,18 +671,22 @@ int gemm_packed(const PackedOp& E, const PackedOp& T, const float* ra, const flo
     // Large K (dense layers of the pooling / head) streams both operands; K <= 256 keeps the E panel resident.
     // Both pass variants are launched when the count is decided on the device; exactly one does the work.
     static const bool force_stream = getenv("SKB_FORCE_STREAM_A") != nullptr;   // experiment knob
+    static const bool one_panel = getenv("SKB_SCORE_ONE_PANEL") != nullptr;     // A/B knob: one row panel per work item
     const bool stream_a = E.Dp > 256 || force_stream;
     if (out_mode == 3) {
         if (stream_a) {
             set_last_error(__FILE__, __LINE__, "trial-list mode supports embeddings of up to 256 dimensions");
             return SKB_ERR_ARG;
         }
-        if (passes != 3) rc = launch_score<1, false, true>(p, grid, st);
+        // two row panels per item when the two resident single-pass panels fit (D <= 256): half the operand stream
+        const bool two = p.Dp <= 256 && E.rows_pad >= 256 && !one_panel;
+        if (passes != 3) rc = two ? launch_score<1, false, true, 2>(p, grid, st) : launch_score<1, false, true>(p, grid, st);
         if (rc) return rc;
         if (passes != 1) rc = launch_score<3, false, true>(p, grid, st);
         return rc;
     }
-    if (passes != 3) rc = stream_a ? launch_score<1, true>(p, grid, st) : launch_score<1, false>(p, grid, st);
+    const bool two = !stream_a && p.Dp <= 256 && E.rows_pad >= 256 && !one_panel;
+    if (passes != 3) rc = stream_a ? launch_score<1, true>(p, grid, st) : (two ? launch_score<1, false, false, 2>(p, grid, st) : launch_score<1, false>(p, grid, st));
     if (rc) return rc;
     if (passes != 1) rc = stream_a ? launch_score<3, true>(p, grid, st) : launch_score<3, false>(p, grid, st);
     return rc;

@@ -671,7 +671,11 @@ int gemm_packed(const PackedOp& E, const PackedOp& T, const float* ra, const flo
     // Large K (dense layers of the pooling / head) streams both operands; K <= 256 keeps the E panel resident.
     // Both pass variants are launched when the count is decided on the device; exactly one does the work.
     static const bool force_stream = getenv("SKB_FORCE_STREAM_A") != nullptr;   // experiment knob
-    static const bool one_panel = getenv("SKB_SCORE_ONE_PANEL") != nullptr;     // A/B knob: one row panel per work item
+    // Two row panels per work item (MT = 2: a streamed T tile feeds two resident E panels, half the L2 -> SM operand stream)
+    // are built but OFF: measured at 20k x 20k they change the matrix modes by < 2 % and slow the trial-list mode down
+    // (271 -> 318 us) -- the two panels leave a 3-stage T ring, and the stream is bound by ring depth x L2 latency, not by
+    // L2 bandwidth (profiles/r02_score_epilogue_experiments.txt).  SKB_SCORE_TWO_PANELS=1 enables them.
+    static const bool one_panel = getenv("SKB_SCORE_TWO_PANELS") == nullptr;
     const bool stream_a = E.Dp > 256 || force_stream;
     if (out_mode == 3) {
         if (stream_a) {

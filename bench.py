@@ -832,7 +832,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--utts", type=int, default=96, help="mean utterances per GPU per step")
+    ap.add_argument("--utts", type=int, default=108, help="mean utterances per GPU per step (108 x 11 s = the 1200 audio-s batch budget "
+                                                            "that bulk.make_batches uses by default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not run nvidia-smi beside the timed region")
     args = ap.parse_args()

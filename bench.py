@@ -102,7 +102,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -401,7 +401,15 @@ def run_ours(args):
             model.extract_packed(device_audio(wls, 5 + k, device), wls)
         if dist_on:
             bulk.gather_embeddings(local_emb, shards, 256, device)
-        sampler.mark()                                         # nvidia-smi came up during the reserve / warm-up above
+        # nvidia-smi must be UP before the timed region (its start-up holds the driver lock for tens of milliseconds: 9.3 instead
+        # of 8.5 ms per step when it lands inside), and the GPU must not idle while we wait for it (the clocks would drop):
+        # keep running warm-up batches until the sampler has delivered its first rows
+        t_wait = time.perf_counter()
+        while sampler.proc is not None and len(sampler.rows) < 2 and time.perf_counter() - t_wait < 5.0:
+            wls = [int(wl[i]) for i in wb[0]]
+            model.extract_packed(device_audio(wls, 5, device), wls)
+            torch.cuda.synchronize()
+        sampler.mark()
         l0 = lib.skb_kernel_launches()
         ms = timed(job_dev, 1, dist_on)
         launches = lib.skb_kernel_launches() - l0

@@ -383,9 +383,14 @@ def run_ours(args):
     wb = bulk.make_batches_equal_cost(numpy.argsort(wl, kind="stable"), wl, W)
     order = list(reversed(range(K)))                        # longest utterances first, as extract_embeddings_sharded does
 
+    step_events = []
+
     def job_dev(_):
         for k in order:
             model.extract_packed(flats[k], blens[k], out=local_emb[offs[k]:offs[k + 1]])
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            step_events.append(ev)
         return bulk.gather_embeddings(local_emb, shards, 256, device)          # the one collective of the path
 
     sampler = ClockSampler(local)
@@ -399,8 +404,7 @@ def run_ours(args):
         for k in reversed(range(W)):
             wls = [int(wl[i]) for i in wb[k]]
             model.extract_packed(device_audio(wls, 5 + k, device), wls)
-        if dist_on:
-            bulk.gather_embeddings(local_emb, shards, 256, device)
+        bulk.gather_embeddings(local_emb, shards, 256, device)     # warm-up of the collective / the scatter kernels too
         # nvidia-smi must be UP before the timed region (its start-up holds the driver lock for tens of milliseconds: 9.3 instead
         # of 8.5 ms per step when it lands inside), and the GPU must not idle while we wait for it (the clocks would drop):
         # keep running warm-up batches until the sampler has delivered its first rows
@@ -414,6 +418,7 @@ def run_ours(args):
         ms = timed(job_dev, 1, dist_on)
         launches = lib.skb_kernel_launches() - l0
         clocks = sampler.stop()
+        step_ms = [step_events[i].elapsed_time(step_events[i + 1]) for i in range(len(step_events) - 1)]
         model.check_overflow()
         # end to end: the same job from pinned HOST batches -- every batch's waveforms cross PCIe inside the timed region
         # (overlapped with the previous batch's compute on a second stream), its embeddings come back to the host, the
@@ -483,6 +488,8 @@ def run_ours(args):
                                    "(MAC-balanced, length-sorted) and each shard cut into `steps` equal-MAC length buckets; one NCCL "
                                    "all-gather of the embeddings closes the timed region" % args.utts,
                            "utterances": int(n_total), "audio_s_per_step_per_gpu": all_audio / world / K,
+                           "utterances_per_step_rank0": [len(blens[k]) for k in order],
+                           "device_ms_between_steps_rank0": [round(v, 3) for v in step_ms],
                            "accumulate": "fp32", "parallelism": "utterance-sharded x%d, one NCCL all_gather of the embeddings per shard" % world,
                            "l2": "every batch is new data (%.0f MB of audio per step) and every step streams >1 GB of activations, so "
                                  "nothing survives in the 126 MB L2 between steps; every batch is also a never-seen length composition "

@@ -311,10 +311,18 @@ class Xtractor(torch.nn.Module):
             self._out_host = torch.empty((total, self.embedding_size), dtype=torch.float32, pin_memory=True)
         free_ev = [None, None]
         outs, row = [], 0
+        # both staging buffers are sized for the largest batch of the call up front: growing one in the middle of the
+        # pipeline costs a drain of both streams
+        n_max = max((flat.numel() for flat, _ in batches), default=0)
+        for k in range(2):
+            if self._stage[k] is None or self._stage[k].numel() < n_max:
+                compute.synchronize()                              # (re)allocation: nothing in flight may still use the old buffer
+                copy_s.synchronize()
+                self._stage[k] = torch.empty((n_max + n_max // 8,), dtype=torch.float32, device=device)
         for i, (flat, lengths) in enumerate(batches):
             k, n = i % 2, flat.numel()
             if self._stage[k] is None or self._stage[k].numel() < n:
-                compute.synchronize()                              # (re)allocation: nothing in flight may still use the old buffer
+                compute.synchronize()
                 copy_s.synchronize()
                 self._stage[k] = torch.empty((n + n // 8,), dtype=torch.float32, device=device)
             with torch.cuda.stream(copy_s):

@@ -924,16 +924,23 @@ __global__ void __launch_bounds__(256) plan_activate_kernel(const __grid_constan
     int k = 0;
     while (k + 1 < a.n_ps && blk >= a.ps[k + 1].first_block) ++k;
     const ActPs& z = a.ps[k];
-    const int rel = (blk - z.first_block) * blockDim.x + threadIdx.x;
-    if (rel >= z.n) return;
-    const int row = rel / z.Wp, w = rel - row * z.Wp;
+    // one thread per (line, chunk plane of the phase-split buffer): only the pad column, the pad lines and the odd-row phases
+    // of an utterance's last line need zeros (walking every pixel cost 0.1 ms per batch: profiles/r02s_launches_hr34_step_summary.txt)
+    const int idx = (blk - z.first_block) * blockDim.x + threadIdx.x;
+    const int n_planes = 4 * z.cpp;
+    const int n_lines = z.n / z.Wp;
+    if (idx >= n_lines * n_planes) return;
+    const int row = idx / n_planes, j = idx - row * n_planes;
     const int b = z.row_b[row], hh = z.row_h[row];
-    int first_phase;
-    if (b < 0 || hh < 0 || w >= z.W) first_phase = 0;                                    // pad pixel: all four phases
-    else if (2 * hh + 1 >= z.src_utt_count[b] / z.src_W) first_phase = 2;                // no odd source line below
-    else return;
-    for (int j = first_phase * z.cpp; j < 4 * z.cpp; ++j)
-        *reinterpret_cast<uint4*>(z.buf + ((size_t)j * z.plane + z.G + rel) * 8) = make_uint4(0u, 0u, 0u, 0u);
+    uint16_t* line = z.buf + ((size_t)j * z.plane + z.G + (size_t)row * z.Wp) * 8;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    if (b < 0 || hh < 0) {                                                           // pad line: every pixel, all four phases
+        for (int w = 0; w < z.Wp; ++w) *reinterpret_cast<uint4*>(line + (size_t)w * 8) = zero;
+        return;
+    }
+    for (int w = z.W; w < z.Wp; ++w) *reinterpret_cast<uint4*>(line + (size_t)w * 8) = zero;   // pad column(s)
+    if (j >= 2 * z.cpp && 2 * hh + 1 >= z.src_utt_count[b] / z.src_W)               // no odd source line below: phases 2, 3
+        for (int w = 0; w < z.W; ++w) *reinterpret_cast<uint4*>(line + (size_t)w * 8) = zero;
 }
 
 // Make `h->plan` current: size the shared work buffers for it and re-establish the few invariants that depend on the
@@ -993,7 +1000,7 @@ static int activate_plan(skb_xtractor* h, cudaStream_t st) {
             z.buf = (uint16_t*)h->act[l * 5 + 3].p; z.plane = Lo.plane; z.cpp = Ls.C / 8; z.G = Lo.G; z.n = Lo.p_end - Lo.G;
             z.Wp = Lo.Wp; z.W = Lo.W; z.src_W = Ls.W; z.first_block = blocks;
             z.row_b = h->d32 + Lo.o_row_b; z.row_h = h->d32 + Lo.o_row_h; z.src_utt_count = h->d32 + Ls.o_utt_count;
-            blocks += (z.n + 255) / 256;
+            blocks += ((z.n / z.Wp) * 4 * z.cpp + 255) / 256;
         }
         a.sums = (unsigned long long*)h->sums.p;
         a.n_sums = B * Cmax;

@@ -79,6 +79,10 @@ int skb_xtractor_reserve(skb_xtractor_t* h, int max_utts, int64_t max_total_samp
  * value it saw before its forward calls: any increase means the weights / inputs do not fit fp16 and the embeddings
  * of those calls are wrong -- rebuild the handle with compute_dtype 1 (bf16).  Always 0 for bf16 handles. */
 int skb_xtractor_overflow_count(skb_xtractor_t* h, void* stream, int64_t* count);
+/* Makes `stream` wait until the geometry tables of the last forward call on `h` have been uploaded.  For callers that
+ * stream waveforms on a second stream (Xtractor.extract_stream): the next batch's host-to-device copy must not get
+ * onto the copy engine ahead of the current batch's tables. */
+int skb_xtractor_wait_tables(skb_xtractor_t* h, void* stream);
 /* Same call with HOST buffers: H2D of the waveforms, forward, D2H of the results, synchronous. */
 int skb_xtractor_forward_host(skb_xtractor_t* h, const float* wave_host, const int64_t* lengths, int n_utt,
                               int norm_embedding, float* emb_host, float* logits_host, void* stream);

@@ -49,6 +49,7 @@ def _declare(lib):
         "skb_xtractor_pre_embedding": (i32, [vp, i32, vp, vp]),
         "skb_xtractor_reserve": (i32, [vp, i32, i64, vp]),
         "skb_xtractor_overflow_count": (i32, [vp, vp, c_i64_p]),
+        "skb_xtractor_wait_tables": (i32, [vp, vp]),
         "skb_conv2d_bn_act": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp, f32, f32, vp, vp, i32, vp, vp]),
         "skb_ops_overflow_count": (i32, [vp, c_i64_p]),
         "skb_channel_mean": (i32, [vp, i32, i32, i64, vp, vp]),

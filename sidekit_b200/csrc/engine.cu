@@ -1631,6 +1631,18 @@ int skb_xtractor_overflow_count(skb_xtractor_t* h, void* stream, int64_t* count)
     return SKB_OK;
 }
 
+int skb_xtractor_wait_tables(skb_xtractor_t* h, void* stream) {
+    if (!h) {
+        set_last_error(__FILE__, __LINE__, "bad arguments");
+        return SKB_ERR_ARG;
+    }
+    // the geometry tables of the last forward call go over the same host-to-device copy engine as a caller's waveform
+    // copies: a 67 MB waveform copy that becomes eligible at the same instant as the tables delays the forward by its
+    // whole duration (profiles/r02u_e2e_timeline.txt), so the copy stream lets the tables go first
+    if (h->slot.uploaded) SKB_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, h->slot.uploaded, 0));
+    return SKB_OK;
+}
+
 int skb_xtractor_pre_embedding(skb_xtractor_t* h, int n_utt, float* out_dev, void* stream) {
     if (!h || !out_dev || !h->plan_valid || n_utt != h->plan.B) {
         set_last_error(__FILE__, __LINE__, "pre_embedding: no matching forward call");

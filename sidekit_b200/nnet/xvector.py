@@ -336,6 +336,10 @@ class Xtractor(torch.nn.Module):
                                emb_out=None if device_out is None else device_out[row:row + len(lengths)])
             free_ev[k] = torch.cuda.Event()
             free_ev[k].record(compute)
+            # the next waveform copy and this forward's geometry tables share the host-to-device copy engine and become
+            # eligible at the same instant (when the previous forward ends): the tables must go first, or the forward
+            # stalls for the whole 1.2 ms of the waveform copy (profiles/r02u_e2e_timeline.txt)
+            _lib.check(_lib.lib().skb_xtractor_wait_tables(self._handle(device), ctypes.c_void_p(copy_s.cuda_stream)))
             dst = self._out_host[row:row + emb.shape[0]]
             dst.copy_(emb, non_blocking=True)
             outs.append(dst)

@@ -32,19 +32,38 @@ extern std::atomic<long long> g_launches;
 // ----------------------------------------------------------------------------- operand preparation
 // stats[0] = max |x| (as float bits), stats[1] = max row sum of squares (float bits).  blockIdx.y selects the operand, so
 // both matrices of a scoring call are scanned by one launch.
-struct AbsmaxArgs { const float* X[2]; int rows[2]; unsigned* stats[2]; };
-__global__ void absmax_kernel(const AbsmaxArgs a, int D) {
-    // one warp per row, block-level max, a single pair of atomics per CTA
-    __shared__ float smx[8], sss[8];
-    pdl_wait();                                        // launched with launch_pdl (common.cuh): stats were zeroed in stream order
+// No zeroing and no atomics on the results: every CTA leaves its pair of maxima in a scratch list, the CTA that arrives last
+// (a self-resetting ticket) reduces the list and stores stats[] (round 1: memset + 2 atomicMax per CTA; the memset alone was
+// 2 us of a 60 us row-panel step).
+struct AbsmaxArgs { const float* X[2]; int rows[2]; unsigned* stats[2]; float2* partial[2]; unsigned* ticket[2]; };
+constexpr int kAbsmaxWarps = 16;
+constexpr int kAbsmaxMaxCtas = 8 * kNumSMs;
+__global__ void __launch_bounds__(kAbsmaxWarps * 32) absmax_kernel(const AbsmaxArgs a, int D) {
+    // one warp per row (every lane sums its columns lane, lane + 32, ... in order, then a shuffle tree: the row sums do not
+    // depend on the launch shape), eight loads in flight per lane
+    __shared__ float smx[kAbsmaxWarps], sss[kAbsmaxWarps];
+    __shared__ bool s_last;
+    pdl_wait();                                        // launched with launch_pdl (common.cuh): the scratch list may still be read
     const float* __restrict__ X = a.X[blockIdx.y];
     const int rows = a.rows[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float mx = 0.f, ssm = 0.f;
-    for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    for (int row = blockIdx.x * kAbsmaxWarps + warp; row < rows; row += gridDim.x * kAbsmaxWarps) {
+        const float* __restrict__ xr = X + (size_t)row * D;
         float ss = 0.f;
-        for (int k = lane; k < D; k += 32) {
-            const float v = X[(size_t)row * D + k];
+        int k = lane;
+        for (; k + 7 * 32 < D; k += 8 * 32) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(xr + k + 32 * i);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                mx = fmaxf(mx, fabsf(v[i]));
+                ss = fmaf(v[i], v[i], ss);
+            }
+        }
+        for (; k < D; k += 32) {
+            const float v = __ldg(xr + k);
             mx = fmaxf(mx, fabsf(v));
             ss = fmaf(v, v, ss);
         }
@@ -54,9 +73,30 @@ __global__ void absmax_kernel(const AbsmaxArgs a, int D) {
     if (lane == 0) { smx[warp] = mx; sss[warp] = ssm; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; ++i) { mx = fmaxf(mx, smx[i]); ssm = fmaxf(ssm, sss[i]); }
-        atomicMax(a.stats[blockIdx.y], __float_as_uint(mx));          // non-negative floats order like their bit patterns
-        atomicMax(a.stats[blockIdx.y] + 1, __float_as_uint(ssm));
+        for (int i = 1; i < kAbsmaxWarps; ++i) { mx = fmaxf(mx, smx[i]); ssm = fmaxf(ssm, sss[i]); }
+        a.partial[blockIdx.y][blockIdx.x] = make_float2(mx, ssm);
+        __threadfence();
+        s_last = atomicAdd(a.ticket[blockIdx.y], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    mx = 0.f; ssm = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+        const float2 v = __ldcg(a.partial[blockIdx.y] + i);
+        mx = fmaxf(mx, v.x);
+        ssm = fmaxf(ssm, v.y);
+    }
+    mx = warp_max(mx);
+    ssm = warp_max(ssm);
+    __syncthreads();                                   // smx / sss were read by thread 0 above
+    if (lane == 0) { smx[warp] = mx; sss[warp] = ssm; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < kAbsmaxWarps; ++i) { mx = fmaxf(mx, smx[i]); ssm = fmaxf(ssm, sss[i]); }
+        a.stats[blockIdx.y][0] = __float_as_uint(mx);
+        a.stats[blockIdx.y][1] = __float_as_uint(ssm);
+        *a.ticket[blockIdx.y] = 0u;                    // ready for the next launch
     }
 }
 
@@ -81,33 +121,69 @@ __device__ __forceinline__ int decide_passes(const unsigned* statsE, const unsig
 // blockIdx.y selects the operand.  The scale exponent is derived from the operand's statistics by every thread (and
 // stored once for the GEMM epilogue).
 struct PackArgs { const float* X[2]; int rows[2], rows_pad[2]; const unsigned* stats[2]; int* exp_out[2]; uint16_t* hi[2]; uint16_t* lo[2]; };
-__global__ void pack_split_kernel(const PackArgs a, int D, int Dp) {
+// One CTA per (128-row tile, 64-column group): the rows are READ along K (8 lanes x 32 bytes per row segment: whole sectors),
+// split, transposed through shared memory ([chunk][row] with a row stride of 129 16-byte units: conflict-free both ways) and
+// WRITTEN as the tile's eight 2 KB chunk planes.  (Round 1 read with one lane per row -- 1 KB apart -- which cost 26 us for a
+// 20 000 x 256 operand, profiles/r02l_score_modes_launches.csv.)
+constexpr int kPackRowStride = 129;
+__global__ void __launch_bounds__(256) pack_split_kernel(const PackArgs a, int D, int Dp) {
+    __shared__ uint4 s_hi[8 * kPackRowStride], s_lo[8 * kPackRowStride];
     pdl_wait();
-    const int op = blockIdx.y;
-    const float* __restrict__ X = a.X[op];
+    const int op = blockIdx.z;
     const int rows = a.rows[op], rows_pad = a.rows_pad[op];
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int chunks = Dp >> 3;
+    const int tile = blockIdx.x, jg0 = blockIdx.y * 8;
+    const float* __restrict__ X = a.X[op];
     const int e_scale = scale_exponent(a.stats[op]);
-    if (idx == 0) a.exp_out[op][0] = e_scale;
-    if (idx >= (long long)rows_pad * chunks) return;
-    const int row = (int)(idx % rows_pad), j = (int)(idx / rows_pad);
+    if (tile == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.exp_out[op][0] = e_scale;
+    if (tile * 128 >= rows_pad) return;                  // the grid is sized for the larger of the two operands
     const float sc = ldexpf(1.f, e_scale);
-    float h[8], l[8];
+    const int jl = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+    const int k0 = (jg0 + jl) * 8;
+    const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && k0 + 8 <= D;
+    float v[4][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int k = j * 8 + e;
-        const float v = (row < rows && k < D) ? X[(size_t)row * D + k] * sc : 0.f;
-        const float hv = __half2float(__float2half_rn(v));
-        h[e] = hv;
-        l[e] = v - hv;
+    for (int ps = 0; ps < 4; ++ps) {
+        const int row = tile * 128 + ps * 32 + r0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[ps][e] = 0.f;
+        if (row < rows) {
+            const float* src = X + (size_t)row * D + k0;
+            if (vec) {
+                const float4 x0 = __ldg(reinterpret_cast<const float4*>(src)), x1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                v[ps][0] = x0.x; v[ps][1] = x0.y; v[ps][2] = x0.z; v[ps][3] = x0.w;
+                v[ps][4] = x1.x; v[ps][5] = x1.y; v[ps][6] = x1.z; v[ps][7] = x1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (k0 + e < D) v[ps][e] = __ldg(src + e);
+            }
+        }
     }
-    uint4 oh, ol;
-    oh.x = pack2<false>(h[0], h[1]); oh.y = pack2<false>(h[2], h[3]); oh.z = pack2<false>(h[4], h[5]); oh.w = pack2<false>(h[6], h[7]);
-    ol.x = pack2<false>(l[0], l[1]); ol.y = pack2<false>(l[2], l[3]); ol.z = pack2<false>(l[4], l[5]); ol.w = pack2<false>(l[6], l[7]);
-    const size_t o = (((size_t)(row >> 7) * chunks + j) * 128 + (row & 127)) * 8;
-    *reinterpret_cast<uint4*>(a.hi[op] + o) = oh;
-    *reinterpret_cast<uint4*>(a.lo[op] + o) = ol;
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+        float h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float x = v[ps][e] * sc;
+            const float hv = __half2float(__float2half_rn(x));
+            h[e] = hv;
+            l[e] = x - hv;
+        }
+        uint4 oh, ol;
+        oh.x = pack2<false>(h[0], h[1]); oh.y = pack2<false>(h[2], h[3]); oh.z = pack2<false>(h[4], h[5]); oh.w = pack2<false>(h[6], h[7]);
+        ol.x = pack2<false>(l[0], l[1]); ol.y = pack2<false>(l[2], l[3]); ol.z = pack2<false>(l[4], l[5]); ol.w = pack2<false>(l[6], l[7]);
+        s_hi[jl * kPackRowStride + ps * 32 + r0] = oh;
+        s_lo[jl * kPackRowStride + ps * 32 + r0] = ol;
+    }
+    __syncthreads();
+    const int chunks = Dp >> 3;
+#pragma unroll
+    for (int u = threadIdx.x; u < 8 * 128; u += 256) {
+        const int j = u >> 7, row = u & 127;
+        const size_t o = (((size_t)tile * chunks + jg0 + j) * 128 + row) * 8;
+        *reinterpret_cast<uint4*>(a.hi[op] + o) = s_hi[j * kPackRowStride + row];
+        *reinterpret_cast<uint4*>(a.lo[op] + o) = s_lo[j * kPackRowStride + row];
+    }
 }
 
 // ----------------------------------------------------------------------------- the GEMM
@@ -166,7 +242,7 @@ struct ScoreSmem {
 };
 
 template <int PASSES, bool STREAM_A, bool TRIALS, int MT>
-__global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A, MT>::kThreads, 1) score_gemm_kernel(const ScoreParams p) {
+__device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
     using SM = ScoreSmem<PASSES, STREAM_A, MT>;
     static_assert(MT == 1 || (PASSES == 1 && !STREAM_A), "two row panels per item: single-pass resident-panel variant only");
     extern __shared__ __align__(128) uint8_t smem[];
@@ -522,7 +598,60 @@ __global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A, MT>::kThreads, 1) 
     }
 }
 
+template <int PASSES, bool STREAM_A, bool TRIALS, int MT>
+__global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A, MT>::kThreads, 1) score_gemm_kernel(const ScoreParams p) {
+    score_gemm_body<PASSES, STREAM_A, TRIALS, MT>(p);
+}
+
+// passes decided on the device (passes_req == 0), resident-panel variants: ONE launch that runs the body the statistics
+// select (round 1 launched both instantiations and let one of them return at once: a 3 us no-op per call, 5 % of a
+// 2500-row panel at 8 GPUs).  Shared memory is sized for the larger of the two layouts by launch_score_auto.
+static_assert(ScoreSmem<1, false>::kThreads == ScoreSmem<3, false>::kThreads, "the auto kernel needs one block size");
+template <bool TRIALS>
+__global__ void __launch_bounds__(ScoreSmem<1, false>::kThreads, 1) score_gemm_auto_kernel(const ScoreParams p) {
+    pdl_wait();
+    if (decide_passes(p.statsE, p.statsT, p.D, p.abs_alpha, 0) == 1) score_gemm_body<1, false, TRIALS, 1>(p);
+    else score_gemm_body<3, false, TRIALS, 1>(p);
+}
+
 // ----------------------------------------------------------------------------- packed operands, workspace, launch
+struct ScoreWorkspace {
+    uint16_t* planes = nullptr;
+    size_t planes_cap = 0;
+    unsigned* stats = nullptr;   // 2 x (2 stats + 1 exponent) + passes
+    float2* partial = nullptr;   // absmax_kernel: per-CTA maxima of the two operands of a call
+    unsigned* ticket = nullptr;  // absmax_kernel: arrival counters (zero between launches)
+    float* tmp = nullptr;        // scratch score matrix (as-norm cohort scores)
+    size_t tmp_cap = 0;
+};
+// one workspace per (host thread, device): the buffers are cudaMalloc'd on the device that is current at first use
+static thread_local ScoreWorkspace g_ws_dev[kMaxDevices];
+#define g_ws (g_ws_dev[current_device()])
+
+static int ws_ensure(size_t plane_bytes, size_t tmp_bytes) {
+    if (!g_ws.stats) SKB_CUDA_CHECK(cudaMalloc(&g_ws.stats, 8 * sizeof(unsigned)));
+    if (!g_ws.partial) SKB_CUDA_CHECK(cudaMalloc(&g_ws.partial, 2 * (size_t)kAbsmaxMaxCtas * sizeof(float2)));
+    if (!g_ws.ticket) {
+        SKB_CUDA_CHECK(cudaMalloc(&g_ws.ticket, 2 * sizeof(unsigned)));
+        SKB_CUDA_CHECK(cudaMemset(g_ws.ticket, 0, 2 * sizeof(unsigned)));
+    }
+    if (plane_bytes > g_ws.planes_cap) {
+        if (getenv("SKB_TRACE_ALLOC")) fprintf(stderr, "skb: scoring plane workspace grows %zu -> %zu bytes\n", g_ws.planes_cap, plane_bytes);
+        if (g_ws.planes) cudaFree(g_ws.planes);
+        g_ws.planes = nullptr; g_ws.planes_cap = 0;
+        SKB_CUDA_CHECK(cudaMalloc(&g_ws.planes, plane_bytes));
+        g_ws.planes_cap = plane_bytes;
+    }
+    if (tmp_bytes > g_ws.tmp_cap) {
+        if (getenv("SKB_TRACE_ALLOC")) fprintf(stderr, "skb: scoring scratch grows %zu -> %zu bytes\n", g_ws.tmp_cap, tmp_bytes);
+        if (g_ws.tmp) cudaFree(g_ws.tmp);
+        g_ws.tmp = nullptr; g_ws.tmp_cap = 0;
+        SKB_CUDA_CHECK(cudaMalloc(&g_ws.tmp, tmp_bytes));
+        g_ws.tmp_cap = tmp_bytes;
+    }
+    return SKB_OK;
+}
+
 static int packed_alloc(PackedOp* op, int rows, int D) {
     op->rows = rows; op->D = D;
     op->Dp = (D + kScKChunk - 1) / kScKChunk * kScKChunk;
@@ -545,27 +674,30 @@ void packed_free(PackedOp* op) {
 // one or two operands (same D) per pair of launches
 static int packed_fill(const float* X0, PackedOp* op0, const float* X1, PackedOp* op1, cudaStream_t st) {
     const int n_ops = op1 ? 2 : 1;
+    int rc = ws_ensure(0, 0);
+    if (rc) return rc;
     AbsmaxArgs aa;
     PackArgs pa;
     PackedOp* ops[2] = {op0, op1};
     const float* Xs[2] = {X0, X1};
-    int max_rows = 0;
-    long long max_n = 0;
+    int max_rows = 0, max_tiles = 0;
     for (int i = 0; i < 2; ++i) {
         PackedOp* o = ops[i < n_ops ? i : 0];
         aa.X[i] = pa.X[i] = Xs[i < n_ops ? i : 0];
         aa.rows[i] = pa.rows[i] = o->rows;
         aa.stats[i] = o->stats;
+        aa.partial[i] = g_ws.partial + (size_t)i * kAbsmaxMaxCtas;
+        aa.ticket[i] = g_ws.ticket + i;
         pa.stats[i] = o->stats;
         pa.rows_pad[i] = o->rows_pad; pa.exp_out[i] = o->exp; pa.hi[i] = o->hi; pa.lo[i] = o->lo;
         if (i < n_ops) {
-            SKB_CUDA_CHECK(cudaMemsetAsync(o->stats, 0, 2 * sizeof(unsigned), st));
             max_rows = std::max(max_rows, o->rows);
-            max_n = std::max(max_n, (long long)o->rows_pad * (o->Dp / 8));
+            max_tiles = std::max(max_tiles, o->rows_pad / 128);
         }
     }
-    SKB_CUDA_CHECK(launch_pdl(absmax_kernel, dim3(std::min((max_rows + 7) / 8, 4 * kNumSMs), n_ops), dim3(256), 0, st, aa, op0->D));
-    SKB_CUDA_CHECK(launch_pdl(pack_split_kernel, dim3((unsigned)((max_n + 255) / 256), n_ops), dim3(256), 0, st, pa, op0->D, op0->Dp));
+    SKB_CUDA_CHECK(launch_pdl(absmax_kernel, dim3(std::max(1, std::min((max_rows + kAbsmaxWarps - 1) / kAbsmaxWarps, kAbsmaxMaxCtas)), n_ops),
+                              dim3(kAbsmaxWarps * 32), 0, st, aa, op0->D));
+    SKB_CUDA_CHECK(launch_pdl(pack_split_kernel, dim3((unsigned)std::max(1, max_tiles), op0->Dp / 64, n_ops), dim3(256), 0, st, pa, op0->D, op0->Dp));
     g_launches += 2;
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
@@ -575,36 +707,6 @@ int packed_create(const float* X_dev, int rows, int D, PackedOp* op, cudaStream_
     int rc = packed_alloc(op, rows, D);
     if (rc) return rc;
     return packed_fill(X_dev, op, nullptr, nullptr, st);
-}
-
-struct ScoreWorkspace {
-    uint16_t* planes = nullptr;
-    size_t planes_cap = 0;
-    unsigned* stats = nullptr;   // 2 x (2 stats + 1 exponent) + passes
-    float* tmp = nullptr;        // scratch score matrix (as-norm cohort scores)
-    size_t tmp_cap = 0;
-};
-// one workspace per (host thread, device): the buffers are cudaMalloc'd on the device that is current at first use
-static thread_local ScoreWorkspace g_ws_dev[kMaxDevices];
-#define g_ws (g_ws_dev[current_device()])
-
-static int ws_ensure(size_t plane_bytes, size_t tmp_bytes) {
-    if (!g_ws.stats) SKB_CUDA_CHECK(cudaMalloc(&g_ws.stats, 8 * sizeof(unsigned)));
-    if (plane_bytes > g_ws.planes_cap) {
-        if (getenv("SKB_TRACE_ALLOC")) fprintf(stderr, "skb: scoring plane workspace grows %zu -> %zu bytes\n", g_ws.planes_cap, plane_bytes);
-        if (g_ws.planes) cudaFree(g_ws.planes);
-        g_ws.planes = nullptr; g_ws.planes_cap = 0;
-        SKB_CUDA_CHECK(cudaMalloc(&g_ws.planes, plane_bytes));
-        g_ws.planes_cap = plane_bytes;
-    }
-    if (tmp_bytes > g_ws.tmp_cap) {
-        if (getenv("SKB_TRACE_ALLOC")) fprintf(stderr, "skb: scoring scratch grows %zu -> %zu bytes\n", g_ws.tmp_cap, tmp_bytes);
-        if (g_ws.tmp) cudaFree(g_ws.tmp);
-        g_ws.tmp = nullptr; g_ws.tmp_cap = 0;
-        SKB_CUDA_CHECK(cudaMalloc(&g_ws.tmp, tmp_bytes));
-        g_ws.tmp_cap = tmp_bytes;
-    }
-    return SKB_OK;
 }
 
 // pre-size the workspace of gemm_nt_split for A operands of up to M rows x K columns (skb_xtractor_reserve)
@@ -638,6 +740,24 @@ static int launch_score(const ScoreParams& p, int /*grid_unused*/, cudaStream_t 
         SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<PASSES, STREAM_A, TRIALS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     SKB_CUDA_CHECK(launch_pdl(score_gemm_kernel<PASSES, STREAM_A, TRIALS, MT>, dim3(grid), dim3(ScoreSmem<PASSES, STREAM_A, MT>::kThreads), smem, st, p));
+    g_launches++;
+    SKB_CUDA_CHECK(cudaGetLastError());
+    return SKB_OK;
+}
+
+template <bool TRIALS>
+static int launch_score_auto(const ScoreParams& p, cudaStream_t st) {
+    static PerDeviceOnce configured;
+    const size_t smem = std::max(ScoreSmem<1, false>::total(p.Dp), ScoreSmem<3, false>::total(p.Dp));
+    const int grid = std::min((p.Ne_pad / 128) * p.n_ntiles, kNumSMs);
+    if (smem > 227 * 1024) {
+        set_last_error(__FILE__, __LINE__, "score_gemm: operand panel does not fit in shared memory");
+        return SKB_ERR_ARG;
+    }
+    if (configured.first()) {
+        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_auto_kernel<TRIALS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    SKB_CUDA_CHECK(launch_pdl(score_gemm_auto_kernel<TRIALS>, dim3(grid), dim3(ScoreSmem<1, false>::kThreads), smem, st, p));
     g_launches++;
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
@@ -684,12 +804,14 @@ int gemm_packed(const PackedOp& E, const PackedOp& T, const float* ra, const flo
         }
         // two row panels per item when the two resident single-pass panels fit (D <= 256): half the operand stream
         const bool two = p.Dp <= 256 && E.rows_pad >= 256 && !one_panel;
+        if (passes == 0 && !two) return launch_score_auto<true>(p, st);
         if (passes != 3) rc = two ? launch_score<1, false, true, 2>(p, grid, st) : launch_score<1, false, true>(p, grid, st);
         if (rc) return rc;
         if (passes != 1) rc = launch_score<3, false, true>(p, grid, st);
         return rc;
     }
     const bool two = !stream_a && p.Dp <= 256 && E.rows_pad >= 256 && !one_panel;
+    if (passes == 0 && !stream_a && !two) return launch_score_auto<false>(p, st);
     if (passes != 3) rc = stream_a ? launch_score<1, true>(p, grid, st) : (two ? launch_score<1, false, false, 2>(p, grid, st) : launch_score<1, false>(p, grid, st));
     if (rc) return rc;
     if (passes != 1) rc = stream_a ? launch_score<3, true>(p, grid, st) : launch_score<3, false>(p, grid, st);

@@ -69,6 +69,10 @@ __device__ __forceinline__ void pdl_trigger() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
+// explicit trigger (whatever SKB_PDL_EARLY_TRIGGER says): the next kernel of the stream may be scheduled once every CTA of
+// this grid has got here -- used by se_border_kernel AFTER its own pdl_wait, so that the channel-total pass that follows
+// (which needs nothing from the border sums) runs beside it instead of behind it
+__device__ __forceinline__ void pdl_trigger_now() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

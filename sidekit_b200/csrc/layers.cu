@@ -252,11 +252,9 @@ __device__ __forceinline__ long long warp_sum8_i64(const long long (&t)[8], int 
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(256, 4) plane_sum_kernel(const uint16_t* __restrict__ act, long long plane, int G, int p_end,
-                                                        const int* __restrict__ pix_b, const int* __restrict__ span_b, int C,
-                                                        int planes_per_block, unsigned long long* __restrict__ sums) {
-    pdl_trigger();
-    pdl_wait();
+__device__ __forceinline__ void plane_sum_body(const uint16_t* __restrict__ act, long long plane, int G, int p_end,
+                                               const int* __restrict__ pix_b, const int* __restrict__ span_b, int C,
+                                               int planes_per_block, unsigned long long* __restrict__ sums) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int span = blockIdx.x * 8 + warp;
     const int base = G + span * kSpanPix;
@@ -311,6 +309,19 @@ __global__ void __launch_bounds__(256, 4) plane_sum_kernel(const uint16_t* __res
     }
 }
 
+// beside_previous = 1: the previous kernel of the stream is se_border_kernel, which waited for conv1 BEFORE it let this grid
+// start and whose results this kernel does not use -- so the sums start at once, beside the border CTAs, and the wait
+// moves to the end (this grid must not complete before the border grid: the kernel after it waits for this one only).
+template <bool BF16>
+__global__ void __launch_bounds__(256, 4) plane_sum_kernel(const uint16_t* __restrict__ act, long long plane, int G, int p_end,
+                                                        const int* __restrict__ pix_b, const int* __restrict__ span_b, int C,
+                                                        int planes_per_block, unsigned long long* __restrict__ sums, int beside_previous) {
+    pdl_trigger();
+    if (!beside_previous) pdl_wait();
+    plane_sum_body<BF16>(act, plane, G, p_end, pix_b, span_b, C, planes_per_block, sums);
+    if (beside_previous) pdl_wait();
+}
+
 // span_b table for plane_sum_kernel (built once per batch composition)
 __global__ void span_table_kernel(const int* __restrict__ pix_b, int n, int n_spans, int* __restrict__ span_b) {
     const int span = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -336,16 +347,16 @@ int launch_span_table(const int* pix_b, int n_pix, int* span_b, cudaStream_t st)
 }
 
 int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, const int* span_b, int C,
-                     unsigned long long* sums, cudaStream_t st) {
+                     unsigned long long* sums, cudaStream_t st, bool beside_previous) {
     const int n = p_end - G;
     const int n_spans = span_table_size(n);
     const int chunks = C / 8;
     const int ppb = chunks >= 16 ? 4 : (chunks >= 8 ? 2 : 1);      // keep >= ~4 waves of CTAs on the small levels
     dim3 grid((n_spans + 7) / 8, chunks / ppb);
     if (bf16)
-        SKB_CUDA_CHECK(launch_pdl(plane_sum_kernel<true>, grid, dim3(256), 0, st, act, plane, G, p_end, pix_b, span_b, C, ppb, sums));
+        SKB_CUDA_CHECK(launch_pdl(plane_sum_kernel<true>, grid, dim3(256), 0, st, act, plane, G, p_end, pix_b, span_b, C, ppb, sums, beside_previous ? 1 : 0));
     else
-        SKB_CUDA_CHECK(launch_pdl(plane_sum_kernel<false>, grid, dim3(256), 0, st, act, plane, G, p_end, pix_b, span_b, C, ppb, sums));
+        SKB_CUDA_CHECK(launch_pdl(plane_sum_kernel<false>, grid, dim3(256), 0, st, act, plane, G, p_end, pix_b, span_b, C, ppb, sums, beside_previous ? 1 : 0));
     SKB_LAUNCH_CHECK(st);
     return SKB_OK;
 }
@@ -359,8 +370,8 @@ __global__ void __launch_bounds__(256) se_border_kernel(const uint16_t* __restri
                                                         float* __restrict__ brd) {
     __shared__ float part[256][33];
     __shared__ float part2[8][32];
-    pdl_trigger();
     pdl_wait();
+    pdl_trigger_now();                              // conv1 is complete: the channel-total pass may start beside this grid
     const int b = blockIdx.x, j = blockIdx.y;
     const int H = utt_count[b] / W;
     const uint16_t* base = y1 + ((size_t)j * plane + G + (size_t)utt_row0[b] * Wp) * 8;     // pixel (0, 0) of chunk j
@@ -534,7 +545,7 @@ __global__ void __launch_bounds__(256) se_fc_kernel(unsigned long long* __restri
 
 int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, long long plane, int G, int Wp, int W,
                     const int* utt_row0, const int* utt_count, int B, int Cin, int Cout, const float* w2t, const float* b2,
-                    const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st) {
+                    const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st, const PlaneSumArgs* totals) {
     // brd_ws: [B][8][Cin] border sums, followed by [n_slices][B][Cout] partial means
     if (Cout > 256 || 256 % Cout != 0) {
         set_last_error(__FILE__, __LINE__, "squeeze-excitation: channel count must divide 256");
@@ -546,6 +557,11 @@ int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, lon
     else
         SKB_CUDA_CHECK(launch_pdl(se_border_kernel<false>, grid, dim3(256), 0, st, y1, plane, G, Wp, W, utt_row0, utt_count, Cin, brd_ws));
     SKB_LAUNCH_CHECK(st);
+    // the channel totals (when conv1's epilogue did not produce them) run BESIDE the border sums: see plane_sum_kernel
+    if (totals) {
+        int rc = launch_plane_sum(bf16, y1, plane, G, totals->p_end, totals->pix_b, totals->span_b, Cin, sums, st, true);
+        if (rc) return rc;
+    }
     const int n_slices = Cin / kSeCh;
     float* partial = brd_ws + (size_t)B * 8 * Cin;
     dim3 g2(n_slices, (B + kSeUtt - 1) / kSeUtt);

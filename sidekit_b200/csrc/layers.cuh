@@ -27,12 +27,14 @@ int launch_stem7(bool bf16, const float* feats, const long long* feat_off, const
                  const int* row_b, const int* row_h, unsigned* overflow, cudaStream_t st);
 int launch_broadcast_rows(const float* bias, int B, int A, float* out, cudaStream_t st);
 int launch_plane_sum(bool bf16, const uint16_t* act, long long plane, int G, int p_end, const int* pix_b, const int* span_b, int C,
-                     unsigned long long* sums, cudaStream_t st);
+                     unsigned long long* sums, cudaStream_t st, bool beside_previous = false);
+struct PlaneSumArgs { int p_end; const int* pix_b; const int* span_b; };   // launch_se_scale: channel totals beside the border sums
 int span_table_size(int n_pix);
 int launch_span_table(const int* pix_b, int n_pix, int* span_b, cudaStream_t st);
 int launch_se_scale(bool bf16, unsigned long long* sums, const uint16_t* y1, long long plane, int G, int Wp, int W,
                     const int* utt_row0, const int* utt_count, int B, int Cin, int Cout, const float* w2t, const float* b2,
-                    const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st);
+                    const float* fc1, const float* fc2, float* brd_ws, float* scale, cudaStream_t st,
+                    const PlaneSumArgs* totals = nullptr);
 int launch_gather_frames(bool bf16, const uint16_t* act, long long plane, int C, int W, int Wp, int G,
                          const int* frame_row, int n_frames, uint16_t* X, cudaStream_t st);
 int launch_gather_pack(const uint16_t* act, long long plane, int C, int W, int Wp, int G, const int* frame_row, int n_frames,

@@ -15,10 +15,10 @@ with torch.no_grad():
     if which == "hr34":
         model = bench.build_model("halfresnet34", 256, dev)
         K = 20
-        lengths = bench.config4_lengths(K * 108)
+        lengths = bench.config4_lengths(K * 96)
         shard = bulk.plan_shards(lengths, 1)[0]
         batches = bulk.make_batches_equal_cost(shard, lengths, K)
-        pick = [10, 9, 11, 8, 12][:n + 2]                     # mid-length buckets (B ~ 80)
+        pick = [10, 9, 11, 8, 12][:n + 2]                     # mid-length buckets (B ~ 75, 1043 audio-s: the bench step)
         data = [([int(lengths[i]) for i in batches[k]]) for k in pick]
         flats = [bench.device_audio(bl, 100 + j, dev) for j, bl in enumerate(data)]
         model.reserve(int(1.1 * max(len(b) for b in data)), 1.1 * max(sum(b) for b in data) / 16000.0, dev)

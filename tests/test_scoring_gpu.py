@@ -75,6 +75,25 @@ def test_mahalanobis_scoring_kat_and_random():
     _check(sc, S.mahalanobis_scoring(ids_e, E, ids_t, T, ids_e, ids_t, mask, M), 1e-3, numpy.float64)
 
 
+def test_mahalanobis_near_identical_vectors_do_not_cancel():
+    """The expanded form -0.5 e'me - 0.5 t'mt + e'mt cancels when e is close to t: with the split-precision
+    cross term and fp32 row / column terms the scores of near-identical pairs (true value ~ -1e-4) stay inside the 1e-3 gate."""
+    rng = numpy.random.default_rng(77)
+    D, N = 256, 300
+    E = synth.synth_embeddings(N, D, seed=43, unit_norm=False)
+    T = E + 1e-3 * rng.standard_normal((N, D))
+    A = rng.standard_normal((D, D)) * 0.05
+    M = A @ A.T + numpy.eye(D)
+    ids_e = numpy.array(["m%04d" % i for i in range(N)])
+    ids_t = numpy.array(["s%04d" % i for i in range(N)])
+    mask = numpy.ones((N, N), dtype=bool)
+    sc = sk.mahalanobis_scoring(_ss(ids_e, E), _ss(ids_t, T), _ndx(ids_e, ids_t, mask), M)
+    ref = S.mahalanobis_scoring(ids_e, E, ids_t, T, ids_e, ids_t, mask, M)[3]
+    assert numpy.abs(numpy.diag(ref)).max() < 1e-3                   # the near-identical pairs: tiny true scores
+    assert numpy.abs(numpy.diag(sc.scoremat) - numpy.diag(ref)).max() < 1e-3
+    assert numpy.abs(sc.scoremat - ref).max() < 1e-3 * max(1.0, numpy.abs(ref).max() / 100.0)
+
+
 def test_two_covariance_mutates_callers_objects_like_the_reference():
     k = kat.kat_inputs()
     en, te = _ss(k["en_ids"], k["en"]), _ss(k["te_ids"], k["te"])

@@ -192,21 +192,7 @@ def fast_PLDA_scoring(enroll, test, ndx, mu, F, Sigma, test_uncertainty=None, Vt
         logging.warning("Enrollment models are not unique, average i-vectors")
         enroll_ctr = enroll_ctr.mean_stat_per_model()
 
-    # D x D algebra on the host in float64, exactly as the reference (:429-448)
-    invSigma = scipy.linalg.inv(Sigma)
-    I_spk = numpy.eye(F.shape[1], dtype='float')
-    K = F.T.dot(invSigma * scaling_factor).dot(F)
-    K1 = scipy.linalg.inv(K + I_spk)
-    K2 = scipy.linalg.inv(2 * K + I_spk)
-    alpha1 = numpy.linalg.slogdet(K1)[1]
-    alpha2 = numpy.linalg.slogdet(K2)[1]
-    plda_cst = alpha2 / 2.0 - alpha1
-    Sigma_ac = numpy.dot(F, F.T)
-    Sigma_tot = Sigma_ac + Sigma
-    Sigma_tot_inv = scipy.linalg.inv(Sigma_tot)
-    Tmp = numpy.linalg.inv(Sigma_tot - Sigma_ac.dot(Sigma_tot_inv).dot(Sigma_ac))
-    Phi = Sigma_tot_inv - Tmp
-    Psi = Sigma_tot_inv.dot(Sigma_ac).dot(Tmp)
+    Phi, Psi, plda_cst = _simplified_plda_terms(F, Sigma, scaling_factor)
 
     dev = _device()
     E, T = _dev32(enroll_ctr.stat1, dev), _dev32(test_ctr.stat1, dev)
@@ -218,11 +204,61 @@ def fast_PLDA_scoring(enroll, test, ndx, mu, F, Sigma, test_uncertainty=None, Vt
     return _finish(clean_ndx, S, numpy.float64)
 
 
+def _logdet_spd(a):
+    """log det of a symmetric positive-definite matrix from its Cholesky factor."""
+    return 2.0 * float(numpy.log(numpy.diag(scipy.linalg.cholesky(a, lower=True))).sum())
+
+
+def _simplified_plda_terms(F, Sigma, scaling_factor):
+    """The three model-dependent quantities of the two-covariance log-likelihood ratio (what the reference derives at
+    iv_scoring.py:429-448), D x D float64 algebra on the host.  With the between-class covariance ``B = F F'``, the total
+    covariance ``T = B + Sigma`` and the Schur complement ``M = T - B T^-1 B`` of the stacked (enrol, test) covariance:
+
+        llr(e, t) = e' Psi t + (e' Phi e + t' Phi t) / 2 + cst,   Psi = T^-1 B M^-1,   Phi = T^-1 - M^-1,
+        cst = log det(I + K) - log det(I + 2 K) / 2,              K = s F' Sigma^-1 F.
+
+    Linear solves against ``T`` and ``Sigma`` instead of the explicit inverses wherever a product follows."""
+    F = numpy.asarray(F, dtype=numpy.float64)
+    Sigma = numpy.asarray(Sigma, dtype=numpy.float64)
+    rank = F.shape[1]
+    K = scaling_factor * (F.T @ scipy.linalg.solve(Sigma, F, assume_a="sym")) if rank else numpy.zeros((0, 0))
+    K = 0.5 * (K + K.T)
+    eye = numpy.eye(rank)
+    cst = (_logdet_spd(eye + K) - 0.5 * _logdet_spd(eye + 2.0 * K)) if rank else 0.0
+    between = F @ F.T
+    total = between + Sigma
+    total_inv = scipy.linalg.inv(total)
+    ti_b = total_inv @ between
+    schur_inv = scipy.linalg.inv(total - between @ ti_b)
+    return total_inv - schur_inv, ti_b @ schur_inv, cst
+
+
 def _open_set(S, p_known):
     """Open-set correction (iv_scoring.py:356-366, :467-475), vectorised: sum_{k != i} exp(S_kj) = colsum_j - exp(S_ij)."""
     N = S.shape[0]
     tmp = torch.exp(S)
     return S - torch.log(p_known * (tmp.sum(dim=0, keepdim=True) - tmp) / (N - 1) + (1 - p_known))
+
+
+def _full_plda_terms(F, G, Sigma, scaling_factor):
+    """``(Psi, Phi, cst)`` of the PLDA model with a channel subspace (the quantities of iv_scoring.py:296-313), D x D float64
+    algebra on the host.  ``P = s Sigma^-1`` is the residual precision; marginalising the channel factor turns it into
+    ``Pc = P - P G (I + G' P G)^-1 G' P`` (Woodbury), the speaker factor then sees ``B = F' Pc`` and ``K = B F``, and
+
+        llr(e, t) = e' Psi t + (e' Phi e + t' Phi t) / 2 + cst,   Psi = B' (I + 2K)^-1 B,   Phi = Psi - B' (I + K)^-1 B,
+        cst = log det(I + K) - log det(I + 2 K) / 2."""
+    F = numpy.asarray(F, dtype=numpy.float64)
+    G = numpy.asarray(G, dtype=numpy.float64)
+    P = scaling_factor * scipy.linalg.inv(numpy.asarray(Sigma, dtype=numpy.float64))
+    PG = P @ G
+    Pc = P - PG @ scipy.linalg.solve(numpy.eye(G.shape[1]) + G.T @ PG, PG.T) if G.shape[1] else P
+    B = F.T @ Pc
+    K = B @ F
+    eye = numpy.eye(F.shape[1])
+    inv1, inv2 = scipy.linalg.inv(eye + K), scipy.linalg.inv(eye + 2.0 * K)
+    cst = 0.5 * numpy.linalg.slogdet(inv2)[1] - numpy.linalg.slogdet(inv1)[1]
+    Psi = B.T @ inv2 @ B
+    return Psi, Psi - B.T @ inv1 @ B, cst
 
 
 def full_PLDA_scoring(enroll, test, ndx, mu, F, G, Sigma, p_known=0.0, scaling_factor=1., check_missing=True):
@@ -237,18 +273,7 @@ def full_PLDA_scoring(enroll, test, ndx, mu, F, G, Sigma, p_known=0.0, scaling_f
     enroll_copy = copy.copy(enroll)            # shallow: every StatServer method used below REBINDS its arrays, none writes in place,
     test_copy = copy.copy(test)                # so the caller's objects are untouched without two (N, D) float64 copies
     clean_ndx = _check_missing_model(enroll_copy, test_copy, ndx) if check_missing else ndx
-    invSigma = scipy.linalg.inv(Sigma)
-    I_iv = numpy.eye(mu.shape[0], dtype='float')
-    I_ch = numpy.eye(G.shape[1], dtype='float')
-    I_spk = numpy.eye(F.shape[1], dtype='float')
-    A = numpy.linalg.inv(G.T.dot(invSigma * scaling_factor).dot(G) + I_ch)
-    B = F.T.dot(invSigma * scaling_factor).dot(I_iv - G.dot(A).dot(G.T).dot(invSigma * scaling_factor))
-    K = B.dot(F)
-    K1 = scipy.linalg.inv(K + I_spk)
-    K2 = scipy.linalg.inv(2 * K + I_spk)
-    constant = numpy.linalg.slogdet(K2)[1] / 2.0 - numpy.linalg.slogdet(K1)[1]
-    Psi = B.T.dot(K2).dot(B)
-    Phi = B.T.dot(K2 - K1).dot(B)
+    Psi, Phi, constant = _full_plda_terms(F, G, Sigma, scaling_factor)
     Phi = 0.5 * (Phi + Phi.T)                      # symmetric up to rounding; the device routine assumes it
     dev = _device()
     E, T = _dev32(enroll_copy.stat1, dev), _dev32(test_copy.stat1, dev)

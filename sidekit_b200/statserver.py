@@ -68,16 +68,17 @@ class StatServer:
         self._take(_first_index(self.modelset, numpy.asarray(model_list)))
 
     def norm_stat1(self):
-        vect_norm = numpy.clip(numpy.linalg.norm(self.stat1, axis=1), 1e-08, numpy.inf)
-        self.stat1 = (self.stat1.transpose() / vect_norm).transpose()
+        """Length normalisation (statserver.py:797-802): rows scaled to unit Euclidean norm (norms floored at 1e-8)."""
+        self.stat1 = self.stat1 / numpy.maximum(numpy.linalg.norm(self.stat1, axis=1, keepdims=True), 1e-08)
 
     def rotate_stat1(self, R):
-        self.stat1 = numpy.dot(self.stat1, R)
+        """statserver.py:804-810."""
+        self.stat1 = self.stat1 @ R
 
     def center_stat1(self, mu):
-        dim = self.stat1.shape[1] / self.stat0.shape[1]
-        index_map = numpy.repeat(numpy.arange(self.stat0.shape[1]), dim)
-        self.stat1 = self.stat1 - (self.stat0[:, index_map] * mu.astype(STAT_TYPE))
+        """statserver.py:812-817: ``stat1 -= stat0 (per distribution, broadcast over its block of stat1) * mu``."""
+        block = self.stat1.shape[1] // self.stat0.shape[1]
+        self.stat1 = self.stat1 - numpy.repeat(self.stat0, block, axis=1) * mu.astype(STAT_TYPE)
 
     def mean_stat_per_model(self):
         out = StatServer()
@@ -183,35 +184,34 @@ class StatServer:
         out.stop = numpy.empty(out.segset.shape, "|O")
         return out, numpy.bincount(inv, minlength=n).astype(STAT_TYPE)
 
+    @staticmethod
+    def _inverse_sqrt_factor(sigma):
+        """``V diag(lambda^-1/2)`` of a symmetric matrix, eigenvalues in DESCENDING order (the column order fixes the
+        coordinates of the whitened vectors, so it is part of the contract)."""
+        lam, vec = scipy.linalg.eigh(sigma)
+        order = numpy.argsort(lam.real)[::-1]
+        return vec.real[:, order] / numpy.sqrt(lam.real[order])
+
     def whiten_stat1(self, mu, sigma, isSqrInvSigma=False):
-        """statserver.py:852-896: diagonal (1-D sigma) or full-covariance (2-D) whitening."""
-        if sigma.ndim == 1:
-            self.center_stat1(mu)
-            self.stat1 = self.stat1 / numpy.sqrt(sigma.astype(STAT_TYPE))
-        elif sigma.ndim == 2:
-            sqr_inv_sigma = sigma
-            if not isSqrInvSigma:
-                eigen_values, eigen_vectors = scipy.linalg.eigh(sigma)
-                ind = eigen_values.real.argsort()[::-1]
-                eigen_values = eigen_values.real[ind]
-                eigen_vectors = eigen_vectors.real[:, ind]
-                sqr_inv_sigma = numpy.dot(eigen_vectors, numpy.diag(1 / numpy.sqrt(eigen_values.real)))
-            self.center_stat1(mu)
-            self.rotate_stat1(sqr_inv_sigma)
-        else:
+        """statserver.py:852-896: centre, then whiten with a diagonal (1-D ``sigma``) or full (2-D) covariance; with
+        ``isSqrInvSigma`` the 2-D argument already is the whitening matrix."""
+        if sigma.ndim not in (1, 2):
             raise Exception('Wrong dimension of Sigma, must be 1 or 2')
+        self.center_stat1(mu)
+        if sigma.ndim == 1:
+            self.stat1 = self.stat1 / numpy.sqrt(sigma.astype(STAT_TYPE))
+        else:
+            self.rotate_stat1(sigma if isSqrInvSigma else self._inverse_sqrt_factor(sigma))
 
     def whiten_cholesky_stat1(self, mu, sigma):
-        """statserver.py:898-918."""
-        if sigma.ndim == 2:
-            chol_invcov = scipy.linalg.cholesky(scipy.linalg.inv(sigma)).T
-            self.center_stat1(mu)
-            self.stat1 = self.stat1.dot(chol_invcov)
-        elif sigma.ndim == 1:
-            self.center_stat1(mu)
+        """statserver.py:898-918: as ``whiten_stat1`` with the lower Cholesky factor of the precision as whitening matrix."""
+        if sigma.ndim not in (1, 2):
+            raise Exception('Wrong dimension of Sigma, must be 1 or 2')
+        self.center_stat1(mu)
+        if sigma.ndim == 1:
             self.stat1 = self.stat1 / numpy.sqrt(sigma)
         else:
-            raise Exception('Wrong dimension of Sigma, must be 1 or 2')
+            self.stat1 = self.stat1 @ scipy.linalg.cholesky(scipy.linalg.inv(sigma), lower=True)
 
     def get_total_covariance_stat1(self):
         """statserver.py:920-928."""
@@ -257,23 +257,22 @@ class StatServer:
         return scipy.linalg.cholesky(scipy.linalg.inv(WCCN)).T
 
     def estimate_spectral_norm_stat1(self, it=1, mode='efr'):
-        """statserver.py:1279-1314: the (mean, covariance) lists of ``it`` whiten + length-norm iterations."""
-        spectral_norm_mean, spectral_norm_cov = [], []
-        tmp_iv = copy.deepcopy(self)
-        for i in range(it):
-            spectral_norm_mean.append(tmp_iv.get_mean_stat1())
-            if mode == 'efr':
-                spectral_norm_cov.append(tmp_iv.get_total_covariance_stat1())
-            elif mode == 'sphNorm':
-                spectral_norm_cov.append(tmp_iv.get_within_covariance_stat1())
-            tmp_iv.whiten_stat1(spectral_norm_mean[i], spectral_norm_cov[i])
-            tmp_iv.norm_stat1()
-        return spectral_norm_mean, spectral_norm_cov
+        """statserver.py:1279-1314: the (mean, covariance) pairs of ``it`` rounds of "whiten, then length-normalise", each
+        estimated on the output of the round before.  ``mode``: 'efr' = total covariance, 'sphNorm' = within-class."""
+        covariance_of = {'efr': StatServer.get_total_covariance_stat1, 'sphNorm': StatServer.get_within_covariance_stat1}
+        work = copy.deepcopy(self)
+        means, covs = [], []
+        for _ in range(it):
+            means.append(work.get_mean_stat1())
+            if mode in covariance_of:                 # (any other mode: the reference appends no covariance and fails below)
+                covs.append(covariance_of[mode](work))
+            work.spectral_norm_stat1(means[-1:], covs[-1:])
+        return means, covs
 
     def spectral_norm_stat1(self, spectral_norm_mean, spectral_norm_cov, is_sqr_inv_sigma=False):
-        """statserver.py:1316-1333."""
+        """statserver.py:1316-1333: apply the rounds estimated above."""
         assert len(spectral_norm_mean) == len(spectral_norm_cov), \
             'Number of mean vectors and covariance matrices is different'
-        for mu, Cov in zip(spectral_norm_mean, spectral_norm_cov):
-            self.whiten_stat1(mu, Cov, is_sqr_inv_sigma)
+        for mean, cov in zip(spectral_norm_mean, spectral_norm_cov):
+            self.whiten_stat1(mean, cov, is_sqr_inv_sigma)
             self.norm_stat1()

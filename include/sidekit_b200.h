@@ -169,6 +169,10 @@ void skb_trial_index_destroy(skb_trial_index_t* t);
 int skb_score_gemm_trials(const float* E_dev, const float* T_dev, int Ne, int Nt, int D, const float* rowterm_dev,
                           const float* colterm_dev, double cst, double alpha, int passes, const skb_trial_index_t* trials,
                           float* out_trials_dev, void* stream);
+/* The same against a test side packed once with skb_packed_create (only the enrol side is packed per call). */
+int skb_score_gemm_trials_packed(const float* E_dev, int Ne, const skb_packed_t* T, const float* rowterm_dev, const float* colterm_dev,
+                                 double cst, double alpha, int passes, const skb_trial_index_t* trials, float* out_trials_dev,
+                                 void* stream);
 
 /* dst[i] = (double)src[i]: the float64 view of a float32 score matrix, produced chunk by chunk on its way to the host
  * (sidekit's PLDA / two-covariance scorers return float64, iv_scoring.py:205, :462). */

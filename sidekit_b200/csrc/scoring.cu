@@ -219,10 +219,16 @@ constexpr int kScKChunk = 64;
 // MT = row panels per work item (resident-panel single-pass variant only): with MT = 2 a streamed T tile feeds TWO 128-row
 // panels, which halves the L2 -> shared-memory operand traffic per trial (64 KB per 128 x 128 tile at MT = 1: at 20k x 20k
 // that is 1.6 GB per call, as much as the fp32 matrix itself, and what bounds the modes that do not write the matrix).
-template <int PASSES, bool STREAM_A, int MT = 1>
+// KC = K elements per ring stage of the single-pass resident-panel variant (64 or 128).  Every tcgen05.commit costs the
+// tensor pipe a drain of ~140 ns (the MMAs behind it do not start before the ones in front have completed): with 64-wide
+// stages a 128 x 128 x 256 tile is 4 x (4 MMAs + commit) and the pipe idles 60 % of the time; 128-wide stages (8 MMAs per
+// commit, 32 KB bulk copies) take the MMA-only time of a 20k x 20k call from 0.246 to 0.200 ms
+// (profiles/r02x_score_issue_bound.txt).
+template <int PASSES, bool STREAM_A, int MT = 1, int KC = 64>
 struct ScoreSmem {
     static constexpr int kParts = PASSES == 1 ? 1 : 2;
-    static constexpr int kChunk = PASSES == 1 ? 64 : 32;              // K elements per stage
+    static_assert(KC == 64 || (KC == 128 && PASSES == 1 && !STREAM_A && MT == 1), "128-wide stages: single-pass resident-panel variant only");
+    static constexpr int kChunk = PASSES == 1 ? KC : 32;              // K elements per stage
     static constexpr int kStageBytes = 128 * kChunk * 2;              // one part (hi or lo) of one operand of one stage
     // resident-panel mode: a stage holds a T chunk; streaming mode (large K): an E chunk and a T chunk
     static constexpr int kRingStageBytes = (STREAM_A ? 2 : 1) * kParts * kStageBytes;
@@ -234,16 +240,38 @@ struct ScoreSmem {
     static constexpr int kEpiWarps = 8;
 #endif
     static constexpr int kThreads = (2 + kEpiWarps) * 32;  // warps: 0 producer, 1 MMA, 2.. epilogue (kEpiWarps / 4 per TMEM quadrant)
-    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? (MT == 2 ? 3 : (kEpiWarps == 16 ? 5 : 7)) : 3);
-    static constexpr int kTmemCols = 2 * MT * 128;       // double-buffered accumulators
+    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? (KC == 128 ? 3 : (MT == 2 ? 3 : (kEpiWarps == 16 ? 5 : 7))) : 3);
+    // Resident-panel variants keep the E panel in TENSOR memory (copied there once per panel with tcgen05.cp): a tcgen05.mma
+    // then reads only the T tile through the shared-memory pipe.  With both operands in shared memory a 128 x 128 x 256 tile
+    // moved 128 KB of operand reads + 64 KB of incoming T + 64-128 KB of epilogue staging through a 128 B/clk pipe: 2000-2500
+    // cycles against 1024 of math -- every output mode was bound by shared-memory bandwidth (profiles/r02x_score_smem_bound.txt).
+#ifdef SKB_SCORE_A_SMEM
+    static constexpr bool kATmem = false;
+#else
+    static constexpr bool kATmem = !STREAM_A && MT == 1;
+#endif
+    static constexpr int kAccCols = 2 * MT * 128;        // double-buffered accumulators
+    static constexpr int kTmemCols = kATmem ? 512 : kAccCols;   // + kParts x 128 columns of A (Dp <= 256)
     static constexpr int kStageRowBytes = 36 * 4;        // [32][36] fp32 transpose buffer per epilogue warp (16-byte rows)
     __host__ __device__ static size_t a_bytes(int Dp) { return STREAM_A ? 0 : (size_t)MT * kParts * 128 * Dp * 2; }
     static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kRingStageBytes + kEpiWarps * 32 * kStageRowBytes; }
 };
 
-template <int PASSES, bool STREAM_A, bool TRIALS, int MT>
+#ifdef SKB_SCORE_TIMING
+// diagnostic build only (./build.sh -DSKB_SCORE_TIMING): where do the roles of score_gemm_kernel wait?  Cycles summed over CTAs.
+__device__ unsigned long long g_score_t[16];
+#define SKB_T0() const long long t0__ = clock64()
+#define SKB_TADD(i) atomicAdd(&g_score_t[i], (unsigned long long)(clock64() - t0__))
+#define SKB_TIMED_WAIT(i, stmt) do { const long long tw__ = clock64(); stmt; if ((threadIdx.x & 31) == 0) atomicAdd(&g_score_t[i], (unsigned long long)(clock64() - tw__)); } while (0)
+#else
+#define SKB_T0()
+#define SKB_TADD(i)
+#define SKB_TIMED_WAIT(i, stmt) stmt
+#endif
+
+template <int PASSES, bool STREAM_A, bool TRIALS, int MT, int KC = 64>
 __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
-    using SM = ScoreSmem<PASSES, STREAM_A, MT>;
+    using SM = ScoreSmem<PASSES, STREAM_A, MT, KC>;
     static_assert(MT == 1 || (PASSES == 1 && !STREAM_A), "two row panels per item: single-pass resident-panel variant only");
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
@@ -288,6 +316,7 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
     if (warp == 0) {
         // ---------------------------------------------------------------- producer: E panel (on change) + T chunks
         if (lane == 0) {
+            SKB_T0();
             int panel = panel0, nt = nt0, s = 0;
             uint32_t b_ph = 1, a_ph = 1;
             bool new_panel = true;
@@ -305,7 +334,7 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
                         }
                 }
                 for (int kc = 0; kc < n_kc; ++kc) {
-                    mbar_wait(&b_empty[s], b_ph);
+                    SKB_TIMED_WAIT(4, mbar_wait(&b_empty[s], b_ph));
                     mbar_arrive_expect_tx(&b_full[s], SM::kRingStageBytes);
                     uint8_t* dst = b_smem + (size_t)s * SM::kRingStageBytes;
                     if (STREAM_A) {
@@ -314,72 +343,102 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
                             bulk_g2s(dst, src, SM::kStageBytes, &b_full[s]);
                         }
                     }
+#ifdef SKB_X_NOCOPY
+                    // experiment: the T tiles are not copied at all (the MMAs run on whatever the ring holds): what does the MMA /
+                    // epilogue pipeline do without the incoming stream?
+                    for (int part = 0; part < SM::kParts; ++part, dst += SM::kStageBytes) {
+                        const uint16_t* src = (part == 0 ? p.Thi : p.Tlo) + ((size_t)(nt & 1) * p.Dp + (size_t)kc * SM::kChunk) * 128;
+                        if (t < t_begin + 2) bulk_g2s(dst, src, SM::kStageBytes, &b_full[s]);
+                        else if (part == 0) {
+                            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&b_full[s])), "r"((uint32_t)SM::kRingStageBytes) : "memory");
+                        }
+                    }
+#else
                     for (int part = 0; part < SM::kParts; ++part, dst += SM::kStageBytes) {
                         const uint16_t* src = (part == 0 ? p.Thi : p.Tlo) + ((size_t)nt * p.Dp + (size_t)kc * SM::kChunk) * 128;
                         bulk_g2s(dst, src, SM::kStageBytes, &b_full[s]);   // contiguous planes
                     }
+#endif
                     if (++s == SM::kBStages) { s = 0; b_ph ^= 1; }
                 }
                 new_panel = false;
                 if (++nt == p.n_ntiles) { nt = 0; ++panel; new_panel = true; }
             }
+            SKB_TADD(7);
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one elected lane)
+        // ---------------------------------------------------------------- MMA issuer: ONE lane runs the whole loop
+        // (The tensor pipe needs 256 cycles for the four MMAs of a stage; with a warp-uniform loop -- every lane polling the
+        // barriers, elect.sync + __syncwarp around each stage -- the issue path took ~800 cycles per stage and the pipe idled
+        // two thirds of the time: tools/score_timing_probe.py, profiles/r02x_score_issue_bound.txt.)
+        if (lane == 0) {
         const uint32_t idesc = umma_idesc_f16(128, 128, false);
         const uint64_t desc_hi = (static_cast<uint64_t>(2048 >> 4) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
                                  (static_cast<uint64_t>(1) << 46);
         int nt = nt0, s = 0, group = panel0;
         uint32_t b_ph = 0, a_ph = 0, nt_done = 0;
         bool new_panel = true;
+        SKB_T0();
         for (int t = t_begin; t < t_end; ++t, ++nt_done) {
             if (!STREAM_A && new_panel) {
-                mbar_wait(a_full, a_ph);
+                SKB_TIMED_WAIT(3, mbar_wait(a_full, a_ph));
                 a_ph ^= 1;
+                if (SM::kATmem) {
+                    // the panel moves on into tensor memory (behind the MMAs of the previous panel, which execute first: one
+                    // in-order pipe); its shared-memory image is free as soon as the copies are done
+                    tc_fence_after();
+                    for (int part = 0; part < SM::kParts; ++part)
+                        for (int ks = 0; ks < p.Dp / 16; ++ks)
+                            tmem_cp_128x256b(tmem_base + SM::kAccCols + part * 128 + ks * 8,
+                                             desc_hi | (((smem_u32(a_smem) + part * a_part + ks * 2 * 2048) >> 4) & 0x3FFF));
+                    umma_commit(a_empty);
+                }
             }
             const int n_pan = min(MT, n_panels - group * MT);
             const int buf = (int)(nt_done & 1);
-            mbar_wait(&acc_empty[buf], ((nt_done >> 1) & 1) ^ 1);
+            SKB_TIMED_WAIT(2, mbar_wait(&acc_empty[buf], ((nt_done >> 1) & 1) ^ 1));
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * (MT * 128);
             for (int kc = 0; kc < n_kc; ++kc) {
-                mbar_wait(&b_full[s], b_ph);
+                SKB_TIMED_WAIT(1, mbar_wait(&b_full[s], b_ph));
                 tc_fence_after();
                 const uint32_t st_base = smem_u32(b_smem + (size_t)s * SM::kRingStageBytes);
                 const uint32_t b_hi = st_base + (STREAM_A ? SM::kParts * SM::kStageBytes : 0);
                 const uint32_t a_hi = STREAM_A ? st_base : smem_u32(a_smem) + kc * (SM::kChunk / 8) * 2048;
                 const uint32_t a_lo_off = STREAM_A ? SM::kStageBytes : a_part;
-                if (elect_one()) {
 #pragma unroll
-                    for (int combo = 0; combo < (PASSES == 1 ? 1 : 3); ++combo) {
-                        // combo 0: hi*hi, 1: hi*lo, 2: lo*hi
-                        const uint32_t a_b = a_hi + (combo == 2 ? a_lo_off : 0);
-                        const uint32_t b_b = b_hi + (combo == 1 ? SM::kStageBytes : 0);
+                for (int combo = 0; combo < (PASSES == 1 ? 1 : 3); ++combo) {
+                    // combo 0: hi*hi, 1: hi*lo, 2: lo*hi
+                    const uint32_t a_b = a_hi + (combo == 2 ? a_lo_off : 0);
+                    const uint32_t b_b = b_hi + (combo == 1 ? SM::kStageBytes : 0);
 #pragma unroll
-                        for (int ks = 0; ks < SM::kChunk / 16; ++ks) {
-                            const uint64_t bd = desc_hi | (((b_b + ks * 2 * 2048) >> 4) & 0x3FFF);
+                    for (int ks = 0; ks < SM::kChunk / 16; ++ks) {
+                        const uint64_t bd = desc_hi | (((b_b + ks * 2 * 2048) >> 4) & 0x3FFF);
+                        const uint32_t acc = (kc > 0 || combo > 0 || ks > 0) ? 1u : 0u;
+                        if (SM::kATmem) {
+                            umma_f16_ts(d_tmem, tmem_base + SM::kAccCols + (combo == 2 ? 128 : 0) + (kc * (SM::kChunk / 16) + ks) * 8, bd, idesc, acc);
+                        } else {
 #pragma unroll
                             for (int m = 0; m < MT; ++m) {
                                 if (m >= n_pan) break;
                                 const uint64_t ad = desc_hi | (((a_b + m * SM::kParts * a_part + ks * 2 * 2048) >> 4) & 0x3FFF);
-                                umma_f16(d_tmem + m * 128, ad, bd, idesc, (kc > 0 || combo > 0 || ks > 0) ? 1u : 0u);
+                                umma_f16(d_tmem + m * 128, ad, bd, idesc, acc);
                             }
                         }
                     }
-                    umma_commit(&b_empty[s]);
                 }
-                __syncwarp();
+                umma_commit(&b_empty[s]);
                 if (++s == SM::kBStages) { s = 0; b_ph ^= 1; }
             }
             new_panel = false;
             if (++nt == p.n_ntiles) { nt = 0; new_panel = true; ++group; }
             const bool last_of_panel = new_panel || (t + 1 == t_end);
-            if (elect_one()) {
-                umma_commit(&acc_full[buf]);
-                if (!STREAM_A && last_of_panel) umma_commit(a_empty);
-            }
-            __syncwarp();
+            umma_commit(&acc_full[buf]);
+            if (!STREAM_A && !SM::kATmem && last_of_panel) umma_commit(a_empty);
         }
+        SKB_TADD(0);
+        }
+        __syncwarp();
     } else if (warp >= 2) {
         // ---------------------------------------------------------------- epilogue: kEpiWarps / 4 warps per TMEM lane quadrant
         constexpr int NB = 16 / SM::kEpiWarps;             // 32-column blocks per warp and tile: 2 (8 warps) or 1 (16 warps)
@@ -396,6 +455,7 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
         const float mscale = p.mul_scaled ? inv_scale : 1.f;
         int panel = panel0, nt = nt0;
         uint32_t nt_done = 0;
+        SKB_T0();
         // Row terms change only with the panel; column terms are fetched BEFORE waiting for the accumulator, so their
         // L2 latency hides behind the MMAs instead of stalling every 32x32 block (was 52 % of all stall samples).
         int cur_panel = -1;
@@ -424,6 +484,18 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
 #pragma unroll
             for (int cbi = 0; cbi < NB; ++cbi) { mwn[m][cbi] = 0u; mon[m][cbi] = 0u; }
         if (TRIALS && t_begin < t_end) fetch_mask(panel0, nt0);
+        float4 qnext[NB];
+        auto fetch_q = [&](int ntile) {
+#pragma unroll
+            for (int cbi = 0; cbi < NB; ++cbi) {
+                const int col = ntile * 128 + (part * NB + cbi) * 32 + c4;
+                qnext[cbi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.q && vec_ok && col + 4 <= p.Nt) qnext[cbi] = __ldg(reinterpret_cast<const float4*>(p.q + col));
+            }
+        };
+#pragma unroll
+        for (int cbi = 0; cbi < NB; ++cbi) qnext[cbi] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t_begin < t_end) fetch_q(nt0);
         for (int t = t_begin; t < t_end; ++t, ++nt_done) {
             const int buf = (int)(nt_done & 1);
             const int n_pan = min(MT, n_panels - panel * MT);
@@ -436,12 +508,15 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
                     rr_m[m] = fmaf((p.r && r < p.Ne) ? p.r[r] : 0.f, p.rq_scale, p.c0);
                 }
             }
+            // column terms: fetched ONE ITEM AHEAD as well (fetched at the top of their own tile they were the first thing the
+            // epilogue stalled on whenever the accumulator was already waiting: 15 % of the stall samples)
             float4 qpre[NB];
 #pragma unroll
-            for (int cbi = 0; cbi < NB; ++cbi) {
-                const int col = nt * 128 + (part * NB + cbi) * 32 + c4;
-                qpre[cbi] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.q && vec_ok && col + 4 <= p.Nt) qpre[cbi] = __ldg(reinterpret_cast<const float4*>(p.q + col));
+            for (int cbi = 0; cbi < NB; ++cbi) qpre[cbi] = qnext[cbi];
+            {
+                int ntn = nt + 1;
+                if (ntn == p.n_ntiles) ntn = 0;
+                if (t + 1 < t_end) fetch_q(ntn);
             }
             // trial-list mode: lane = row (the accumulator's native layout, no transpose): this row's mask words and output
             // offsets, fetched ONE ITEM AHEAD (a mask word comes from L2 / HBM, ~1 us away: loaded at the top of its own tile it
@@ -456,7 +531,8 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
                 if (ntn == p.n_ntiles) { ntn = 0; ++pn; }
                 fetch_mask(pn, ntn);
             }
-            mbar_wait(&acc_full[buf], (nt_done >> 1) & 1);
+            if (warp == 2) { SKB_TIMED_WAIT(5, mbar_wait(&acc_full[buf], (nt_done >> 1) & 1)); }
+            else mbar_wait(&acc_full[buf], (nt_done >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
@@ -476,6 +552,10 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
                 if (col0 >= p.Nt || n_rows <= 0) continue;
+#ifdef SKB_X_NOEPI
+                if (v[0] == 1.2345e-30f) reinterpret_cast<float*>(p.out)[0] = v[1];   // experiment: TMEM loads only
+                continue;
+#endif
                 if (TRIALS) {
                     // Only the trials of the mask are written, compacted in row-major order: each lane walks the set bits
                     // of ITS row's word (lane = row, the accumulator's native layout: no transpose).  A block without any
@@ -488,6 +568,15 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
                         float4* srow = reinterpret_cast<float4*>(stg + lane * 36);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) srow[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                        // the block's 32 (scaled) column terms ride in the 4 pad floats of the first 8 staging rows: they were
+                        // fetched before the accumulator wait (qpre); looked up with a dependent __ldg per trial they were 43 %
+                        // of the kernel's stall samples (profiles/r02x_ncu_score_triallist.txt)
+                        const bool q_staged = p.q != nullptr && vec_ok && col0 + 32 <= p.Nt;
+                        if (q_staged && lane < 8) {
+                            const float4 qv = qpre[cbi];
+                            *reinterpret_cast<float4*>(stg + lane * 36 + 32) =
+                                make_float4(__fmul_rn(qv.x, p.rq_scale), __fmul_rn(qv.y, p.rq_scale), __fmul_rn(qv.z, p.rq_scale), __fmul_rn(qv.w, p.rq_scale));
+                        }
                         __syncwarp();
                         const float mul = ra + a0;
                         float* o = reinterpret_cast<float*>(p.out) + mo_m[m][cbi];
@@ -495,7 +584,8 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
                             const int j = __ffs(word) - 1;
                             word &= word - 1u;
                             // the same roundings as the matrix path (product, then sum: no contraction into an FMA)
-                            const float qq = p.q ? __fmul_rn(__ldg(p.q + col0 + j), p.rq_scale) : 0.f;
+                            const float qq = q_staged ? stg[(j >> 2) * 36 + 32 + (j & 3)]
+                                                      : (p.q ? __fmul_rn(__ldg(p.q + col0 + j), p.rq_scale) : 0.f);
                             *o++ = __fadd_rn(fmaf(stg[lane * 36 + j], mul, rr), qq);
                         }
                     }
@@ -590,6 +680,7 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
             }   // panels of the item
             if (++nt == p.n_ntiles) { nt = 0; ++panel; }
         }
+        if (warp == 2 && lane == 0) { SKB_TADD(6); }
     }
     __syncthreads();
     if (warp == 1) {
@@ -598,19 +689,19 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
     }
 }
 
-template <int PASSES, bool STREAM_A, bool TRIALS, int MT>
-__global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A, MT>::kThreads, 1) score_gemm_kernel(const ScoreParams p) {
-    score_gemm_body<PASSES, STREAM_A, TRIALS, MT>(p);
+template <int PASSES, bool STREAM_A, bool TRIALS, int MT, int KC>
+__global__ void __launch_bounds__(ScoreSmem<PASSES, STREAM_A, MT, KC>::kThreads, 1) score_gemm_kernel(const ScoreParams p) {
+    score_gemm_body<PASSES, STREAM_A, TRIALS, MT, KC>(p);
 }
 
 // passes decided on the device (passes_req == 0), resident-panel variants: ONE launch that runs the body the statistics
 // select (round 1 launched both instantiations and let one of them return at once: a 3 us no-op per call, 5 % of a
 // 2500-row panel at 8 GPUs).  Shared memory is sized for the larger of the two layouts by launch_score_auto.
 static_assert(ScoreSmem<1, false>::kThreads == ScoreSmem<3, false>::kThreads, "the auto kernel needs one block size");
-template <bool TRIALS>
+template <bool TRIALS, int KC>
 __global__ void __launch_bounds__(ScoreSmem<1, false>::kThreads, 1) score_gemm_auto_kernel(const ScoreParams p) {
     pdl_wait();
-    if (decide_passes(p.statsE, p.statsT, p.D, p.abs_alpha, 0) == 1) score_gemm_body<1, false, TRIALS, 1>(p);
+    if (decide_passes(p.statsE, p.statsT, p.D, p.abs_alpha, 0) == 1) score_gemm_body<1, false, TRIALS, 1, KC>(p);
     else score_gemm_body<3, false, TRIALS, 1>(p);
 }
 
@@ -726,10 +817,10 @@ static void ws_operand(PackedOp* op, int rows, int D, int slot, size_t offset_ha
     op->exp = reinterpret_cast<int*>(op->stats + 2);
 }
 
-template <int PASSES, bool STREAM_A, bool TRIALS = false, int MT = 1>
+template <int PASSES, bool STREAM_A, bool TRIALS = false, int MT = 1, int KC = 64>
 static int launch_score(const ScoreParams& p, int /*grid_unused*/, cudaStream_t st) {
     static PerDeviceOnce configured;
-    const size_t smem = ScoreSmem<PASSES, STREAM_A, MT>::total(p.Dp);
+    const size_t smem = ScoreSmem<PASSES, STREAM_A, MT, KC>::total(p.Dp);
     const int n_panels = p.Ne_pad / 128;
     const int grid = std::min(((n_panels + MT - 1) / MT) * p.n_ntiles, kNumSMs);
     if (smem > 227 * 1024) {
@@ -737,30 +828,40 @@ static int launch_score(const ScoreParams& p, int /*grid_unused*/, cudaStream_t 
         return SKB_ERR_ARG;
     }
     if (configured.first()) {
-        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<PASSES, STREAM_A, TRIALS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_kernel<PASSES, STREAM_A, TRIALS, MT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
-    SKB_CUDA_CHECK(launch_pdl(score_gemm_kernel<PASSES, STREAM_A, TRIALS, MT>, dim3(grid), dim3(ScoreSmem<PASSES, STREAM_A, MT>::kThreads), smem, st, p));
+    SKB_CUDA_CHECK(launch_pdl(score_gemm_kernel<PASSES, STREAM_A, TRIALS, MT, KC>, dim3(grid), dim3(ScoreSmem<PASSES, STREAM_A, MT, KC>::kThreads), smem, st, p));
     g_launches++;
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
 }
 
-template <bool TRIALS>
-static int launch_score_auto(const ScoreParams& p, cudaStream_t st) {
+template <bool TRIALS, int KC>
+static int launch_score_auto_kc(const ScoreParams& p, cudaStream_t st) {
     static PerDeviceOnce configured;
-    const size_t smem = std::max(ScoreSmem<1, false>::total(p.Dp), ScoreSmem<3, false>::total(p.Dp));
+    const size_t smem = std::max(ScoreSmem<1, false, 1, KC>::total(p.Dp), ScoreSmem<3, false>::total(p.Dp));
     const int grid = std::min((p.Ne_pad / 128) * p.n_ntiles, kNumSMs);
     if (smem > 227 * 1024) {
         set_last_error(__FILE__, __LINE__, "score_gemm: operand panel does not fit in shared memory");
         return SKB_ERR_ARG;
     }
     if (configured.first()) {
-        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_auto_kernel<TRIALS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SKB_CUDA_CHECK(cudaFuncSetAttribute(score_gemm_auto_kernel<TRIALS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
-    SKB_CUDA_CHECK(launch_pdl(score_gemm_auto_kernel<TRIALS>, dim3(grid), dim3(ScoreSmem<1, false>::kThreads), smem, st, p));
+    SKB_CUDA_CHECK(launch_pdl(score_gemm_auto_kernel<TRIALS, KC>, dim3(grid), dim3(ScoreSmem<1, false>::kThreads), smem, st, p));
     g_launches++;
     SKB_CUDA_CHECK(cudaGetLastError());
     return SKB_OK;
+}
+
+// 128-wide ring stages whenever the padded K allows it (see ScoreSmem)
+template <bool TRIALS>
+static int launch_score_auto(const ScoreParams& p, cudaStream_t st) {
+    return p.Dp % 128 == 0 ? launch_score_auto_kc<TRIALS, 128>(p, st) : launch_score_auto_kc<TRIALS, 64>(p, st);
+}
+template <bool TRIALS>
+static int launch_score_single_pass(const ScoreParams& p, int grid, cudaStream_t st) {
+    return p.Dp % 128 == 0 ? launch_score<1, false, TRIALS, 1, 128>(p, grid, st) : launch_score<1, false, TRIALS, 1, 64>(p, grid, st);
 }
 
 // out = acc * (ra_i + ca_j + a0) + rq_scale * (r_i + q_j) + c0 on two packed operands
@@ -805,14 +906,14 @@ int gemm_packed(const PackedOp& E, const PackedOp& T, const float* ra, const flo
         // two row panels per item when the two resident single-pass panels fit (D <= 256): half the operand stream
         const bool two = p.Dp <= 256 && E.rows_pad >= 256 && !one_panel;
         if (passes == 0 && !two) return launch_score_auto<true>(p, st);
-        if (passes != 3) rc = two ? launch_score<1, false, true, 2>(p, grid, st) : launch_score<1, false, true>(p, grid, st);
+        if (passes != 3) rc = two ? launch_score<1, false, true, 2>(p, grid, st) : launch_score_single_pass<true>(p, grid, st);
         if (rc) return rc;
         if (passes != 1) rc = launch_score<3, false, true>(p, grid, st);
         return rc;
     }
     const bool two = !stream_a && p.Dp <= 256 && E.rows_pad >= 256 && !one_panel;
     if (passes == 0 && !stream_a && !two) return launch_score_auto<false>(p, st);
-    if (passes != 3) rc = stream_a ? launch_score<1, true>(p, grid, st) : (two ? launch_score<1, false, false, 2>(p, grid, st) : launch_score<1, false>(p, grid, st));
+    if (passes != 3) rc = stream_a ? launch_score<1, true>(p, grid, st) : (two ? launch_score<1, false, false, 2>(p, grid, st) : launch_score_single_pass<false>(p, grid, st));
     if (rc) return rc;
     if (passes != 1) rc = stream_a ? launch_score<3, true>(p, grid, st) : launch_score<3, false>(p, grid, st);
     return rc;
@@ -1206,6 +1307,40 @@ int skb_score_gemm_trials(const float* E_dev, const float* T_dev, int Ne, int Nt
     return score_gemm_general(E_dev, T_dev, Ne, Nt, D, nullptr, nullptr, (float)alpha, rowterm_dev, colterm_dev, (float)(alpha * cst),
                               (float)alpha, (float)fabs(alpha), passes, 3, out_trials_dev, 0, 0, (cudaStream_t)stream, &tt);
 }
+
+int skb_score_gemm_trials_packed(const float* E_dev, int Ne, const skb_packed_t* T, const float* rowterm_dev, const float* colterm_dev,
+                                 double cst, double alpha, int passes, const skb_trial_index_t* trials, float* out_trials_dev,
+                                 void* stream) {
+    if (!E_dev || !T || !trials || trials->Ne != Ne || trials->Nt != T->op.rows || !out_trials_dev || Ne <= 0) {
+        set_last_error(__FILE__, __LINE__, "score_gemm_trials_packed: the trial index does not match the operands");
+        return SKB_ERR_ARG;
+    }
+    if (trials->device != current_device() || T->device != current_device()) {
+        set_last_error(__FILE__, __LINE__, "score_gemm_trials_packed: the trial index / packed operand lives on another CUDA device");
+        return SKB_ERR_STATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = T->op.D, Dp = T->op.Dp;
+    const size_t eh = (size_t)Dp * ((Ne + 127) / 128 * 128);
+    int rc = ws_ensure(2 * eh * sizeof(uint16_t), 0);
+    if (rc) return rc;
+    PackedOp e;
+    ws_operand(&e, Ne, D, 0, 0);
+    if ((rc = packed_fill(E_dev, &e, nullptr, nullptr, st))) return rc;
+    TrialTables tt{trials->words, trials->offsets, trials->ld, Ne, T->op.rows};
+    return gemm_packed(e, T->op, nullptr, nullptr, (float)alpha, rowterm_dev, colterm_dev, (float)(alpha * cst), (float)alpha,
+                       (float)fabs(alpha), passes, 3, out_trials_dev, 0, st, &tt);
+}
+
+#ifdef SKB_SCORE_TIMING
+int skb_debug_score_timing(unsigned long long* out16) {
+    SKB_CUDA_CHECK(cudaDeviceSynchronize());
+    SKB_CUDA_CHECK(cudaMemcpyFromSymbol(out16, skb::g_score_t, 16 * sizeof(unsigned long long)));
+    unsigned long long z[16] = {0};
+    SKB_CUDA_CHECK(cudaMemcpyToSymbol(skb::g_score_t, z, sizeof(z)));
+    return SKB_OK;
+}
+#endif
 
 int skb_widen_f32_f64(const float* src_dev, double* dst_dev, int64_t n, void* stream) {
     if (!src_dev || !dst_dev || n < 0) {

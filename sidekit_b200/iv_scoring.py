@@ -115,11 +115,18 @@ class TrialIndex:
 def score_trials(E, T, trials, rowterm=None, colterm=None, cst=0.0, alpha=1.0, passes=0):
     """The scores of the trials of a mask only, as a 1-D float32 CUDA tensor in row-major mask order -- what the reference
     selects with ``scoremat[trialmask]`` (xvector.py:243-245) -- without the Ne x Nt matrix ever reaching HBM.
-    ``trials``: a ``TrialIndex`` or an (Ne, Nt) bool mask."""
+    ``trials``: a ``TrialIndex`` or an (Ne, Nt) bool mask; ``T`` may be a ``PackedEmbeddings``."""
     if not isinstance(trials, TrialIndex):
         trials = TrialIndex(trials, E.device)
     Ne, D = E.shape
     out = torch.empty((max(trials.n_trials, 1),), dtype=torch.float32, device=E.device)
+    if isinstance(T, PackedEmbeddings):
+        with torch.cuda.device(E.device):
+            _lib.check(_lib.lib().skb_score_gemm_trials_packed(
+                E.data_ptr(), Ne, T._ptr, None if rowterm is None else rowterm.data_ptr(),
+                None if colterm is None else colterm.data_ptr(), float(cst), float(alpha), int(passes), trials._ptr, out.data_ptr(),
+                _lib.stream_ptr()))
+        return out[:trials.n_trials]
     with torch.cuda.device(E.device):
         _lib.check(_lib.lib().skb_score_gemm_trials(
             E.data_ptr(), T.data_ptr(), Ne, T.shape[0], D, None if rowterm is None else rowterm.data_ptr(),

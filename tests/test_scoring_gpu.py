@@ -318,6 +318,13 @@ def test_trial_list_mode_and_fp16_output():
         got = score_trials(E, T, idx, r, q, cst=0.25, alpha=1.5, passes=0)
         assert got.shape == (int(mask.sum()),)
         assert torch.equal(got, full[torch.from_numpy(mask).cuda()])            # same arithmetic, same order
+        from sidekit_b200.iv_scoring import PackedEmbeddings
+        assert torch.equal(score_trials(E, PackedEmbeddings(T), idx, r, q, cst=0.25, alpha=1.5, passes=0), got)   # test side packed once
+        assert torch.equal(score_trials(E, T, idx, r, None, cst=0.25, alpha=1.5, passes=0),
+                           score_matrix(E, T, r, None, cst=0.25, alpha=1.5, passes=0)[torch.from_numpy(mask).cuda()])   # no column term
+        qu = torch.randn(Nt + 1, device="cuda")[1:]                                 # a column term that is not 16-byte aligned
+        assert torch.equal(score_trials(E, T, idx, r, qu, cst=0.25, alpha=1.5, passes=0),
+                           score_matrix(E, T, r, qu, cst=0.25, alpha=1.5, passes=0)[torch.from_numpy(mask).cuda()])
         half = score_matrix(E, T, r, q, cst=0.25, alpha=1.5, passes=0, out_dtype=torch.float16)
         assert half.dtype == torch.float16 and torch.equal(half, full.half())
 

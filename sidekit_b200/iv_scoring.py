@@ -228,7 +228,7 @@ def _simplified_plda_terms(F, Sigma, scaling_factor):
     F = numpy.asarray(F, dtype=numpy.float64)
     Sigma = numpy.asarray(Sigma, dtype=numpy.float64)
     rank = F.shape[1]
-    K = scaling_factor * (F.T @ scipy.linalg.solve(Sigma, F, assume_a="sym")) if rank else numpy.zeros((0, 0))
+    K = scaling_factor * (F.T @ numpy.linalg.solve(Sigma, F)) if rank else numpy.zeros((0, 0))
     K = 0.5 * (K + K.T)
     eye = numpy.eye(rank)
     cst = (_logdet_spd(eye + K) - 0.5 * _logdet_spd(eye + 2.0 * K)) if rank else 0.0

@@ -12,7 +12,6 @@ import ctypes
 import logging
 
 import numpy
-import scipy.linalg
 import torch
 
 from . import _lib
@@ -211,11 +210,6 @@ def fast_PLDA_scoring(enroll, test, ndx, mu, F, Sigma, test_uncertainty=None, Vt
     return _finish(clean_ndx, S, numpy.float64)
 
 
-def _logdet_spd(a):
-    """log det of a symmetric positive-definite matrix from its Cholesky factor."""
-    return 2.0 * float(numpy.log(numpy.diag(scipy.linalg.cholesky(a, lower=True))).sum())
-
-
 def _simplified_plda_terms(F, Sigma, scaling_factor):
     """The three model-dependent quantities of the two-covariance log-likelihood ratio (what the reference derives at
     iv_scoring.py:429-448), D x D float64 algebra on the host.  With the between-class covariance ``B = F F'``, the total
@@ -224,19 +218,21 @@ def _simplified_plda_terms(F, Sigma, scaling_factor):
         llr(e, t) = e' Psi t + (e' Phi e + t' Phi t) / 2 + cst,   Psi = T^-1 B M^-1,   Phi = T^-1 - M^-1,
         cst = log det(I + K) - log det(I + 2 K) / 2,              K = s F' Sigma^-1 F.
 
-    Linear solves against ``T`` and ``Sigma`` instead of the explicit inverses wherever a product follows."""
+    ``numpy.linalg`` throughout: the matrix products run on numpy's BLAS threads, and alternating between numpy's and
+    scipy's thread pools inside one function cost 0.25-0.4 s per call on a many-core host (tools/api_probe.py)."""
     F = numpy.asarray(F, dtype=numpy.float64)
     Sigma = numpy.asarray(Sigma, dtype=numpy.float64)
     rank = F.shape[1]
-    K = scaling_factor * (F.T @ numpy.linalg.solve(Sigma, F)) if rank else numpy.zeros((0, 0))
-    K = 0.5 * (K + K.T)
-    eye = numpy.eye(rank)
-    cst = (_logdet_spd(eye + K) - 0.5 * _logdet_spd(eye + 2.0 * K)) if rank else 0.0
+    cst = 0.0
+    if rank:
+        K = scaling_factor * (F.T @ numpy.linalg.solve(Sigma, F))
+        eye = numpy.eye(rank)
+        cst = numpy.linalg.slogdet(eye + K)[1] - 0.5 * numpy.linalg.slogdet(eye + 2.0 * K)[1]
     between = F @ F.T
     total = between + Sigma
-    total_inv = scipy.linalg.inv(total)
+    total_inv = numpy.linalg.inv(total)
     ti_b = total_inv @ between
-    schur_inv = scipy.linalg.inv(total - between @ ti_b)
+    schur_inv = numpy.linalg.inv(total - between @ ti_b)
     return total_inv - schur_inv, ti_b @ schur_inv, cst
 
 
@@ -256,14 +252,14 @@ def _full_plda_terms(F, G, Sigma, scaling_factor):
         cst = log det(I + K) - log det(I + 2 K) / 2."""
     F = numpy.asarray(F, dtype=numpy.float64)
     G = numpy.asarray(G, dtype=numpy.float64)
-    P = scaling_factor * scipy.linalg.inv(numpy.asarray(Sigma, dtype=numpy.float64))
+    P = scaling_factor * numpy.linalg.inv(numpy.asarray(Sigma, dtype=numpy.float64))
     PG = P @ G
-    Pc = P - PG @ scipy.linalg.solve(numpy.eye(G.shape[1]) + G.T @ PG, PG.T) if G.shape[1] else P
+    Pc = P - PG @ numpy.linalg.solve(numpy.eye(G.shape[1]) + G.T @ PG, PG.T) if G.shape[1] else P
     B = F.T @ Pc
     K = B @ F
     eye = numpy.eye(F.shape[1])
-    inv1, inv2 = scipy.linalg.inv(eye + K), scipy.linalg.inv(eye + 2.0 * K)
-    cst = 0.5 * numpy.linalg.slogdet(inv2)[1] - numpy.linalg.slogdet(inv1)[1]
+    inv1, inv2 = numpy.linalg.inv(eye + K), numpy.linalg.inv(eye + 2.0 * K)
+    cst = numpy.linalg.slogdet(eye + K)[1] - 0.5 * numpy.linalg.slogdet(eye + 2.0 * K)[1]
     Psi = B.T @ inv2 @ B
     return Psi, Psi - B.T @ inv1 @ B, cst
 
@@ -343,10 +339,11 @@ def two_covariance_scoring(enroll, test, ndx, W, B, check_missing=True):
         logging.warning("Enrollment models are not unique, average i-vectors")
         enroll = enroll.mean_stat_per_model()
     clean_ndx = _check_missing_model(enroll, test, ndx) if check_missing else ndx
-    iW = scipy.linalg.inv(W)
-    iB = scipy.linalg.inv(B)
-    G = iW @ scipy.linalg.inv(iB + 2 * iW) @ iW
-    H = iW @ scipy.linalg.inv(iB + iW) @ iW
+    # W^-1 (B^-1 + c W^-1)^-1 W^-1 = (W B^-1 W + c W)^-1: one solve and two inverses (numpy.linalg, see _simplified_plda_terms)
+    W = numpy.asarray(W, dtype=numpy.float64)
+    WBW = W @ numpy.linalg.solve(numpy.asarray(B, dtype=numpy.float64), W)
+    G = numpy.linalg.inv(WBW + 2.0 * W)
+    H = numpy.linalg.inv(WBW + W)
     # (e+t)' G (e+t) - t' H t - e' H e  =  e'(G-H)e + t'(G-H)t + 2 e' G t
     dev = _device()
     E, T = _dev32(enroll.stat1, dev), _dev32(test.stat1, dev)

@@ -224,10 +224,13 @@ constexpr int kScKChunk = 64;
 // stages a 128 x 128 x 256 tile is 4 x (4 MMAs + commit) and the pipe idles 60 % of the time; 128-wide stages (8 MMAs per
 // commit, 32 KB bulk copies) take the MMA-only time of a 20k x 20k call from 0.246 to 0.200 ms
 // (profiles/r02x_score_issue_bound.txt).
+#ifndef SKB_KC128_STAGES
+#define SKB_KC128_STAGES 3      // 32 KB stages of the 128-wide variant (4 fit since the E panel is staged through 32 KB, and are slower: profiles/r02x_score_issue_bound.txt)
+#endif
 template <int PASSES, bool STREAM_A, int MT = 1, int KC = 64>
 struct ScoreSmem {
     static constexpr int kParts = PASSES == 1 ? 1 : 2;
-    static_assert(KC == 64 || (KC == 128 && PASSES == 1 && !STREAM_A && MT == 1), "128-wide stages: single-pass resident-panel variant only");
+    static_assert(KC == 64 || ((KC == 128 || KC == 256) && PASSES == 1 && !STREAM_A && MT == 1), "wide stages: single-pass resident-panel variant only");
     static constexpr int kChunk = PASSES == 1 ? KC : 32;              // K elements per stage
     static constexpr int kStageBytes = 128 * kChunk * 2;              // one part (hi or lo) of one operand of one stage
     // resident-panel mode: a stage holds a T chunk; streaming mode (large K): an E chunk and a T chunk
@@ -240,7 +243,7 @@ struct ScoreSmem {
     static constexpr int kEpiWarps = 8;
 #endif
     static constexpr int kThreads = (2 + kEpiWarps) * 32;  // warps: 0 producer, 1 MMA, 2.. epilogue (kEpiWarps / 4 per TMEM quadrant)
-    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? (KC == 128 ? 3 : (MT == 2 ? 3 : (kEpiWarps == 16 ? 5 : 7))) : 3);
+    static constexpr int kBStages = STREAM_A ? 4 : (PASSES == 1 ? (KC == 256 ? 2 : (KC == 128 ? SKB_KC128_STAGES : (MT == 2 ? 3 : (kEpiWarps == 16 ? 5 : 7)))) : 3);
     // Resident-panel variants keep the E panel in TENSOR memory (copied there once per panel with tcgen05.cp): a tcgen05.mma
     // then reads only the T tile through the shared-memory pipe.  With both operands in shared memory a 128 x 128 x 256 tile
     // moved 128 KB of operand reads + 64 KB of incoming T + 64-128 KB of epilogue staging through a 128 B/clk pipe: 2000-2500
@@ -253,7 +256,15 @@ struct ScoreSmem {
     static constexpr int kAccCols = 2 * MT * 128;        // double-buffered accumulators
     static constexpr int kTmemCols = kATmem ? 512 : kAccCols;   // + kParts x 128 columns of A (Dp <= 256)
     static constexpr int kStageRowBytes = 36 * 4;        // [32][36] fp32 transpose buffer per epilogue warp (16-byte rows)
-    __host__ __device__ static size_t a_bytes(int Dp) { return STREAM_A ? 0 : (size_t)MT * kParts * 128 * Dp * 2; }
+    // E panel in shared memory: the whole panel (MT x kParts x 128 x Dp) when the MMAs read it there; with the panel in tensor
+    // memory only a staging piece (kAPieceK K-columns of one part), through which the panel is passed on piece by piece
+#ifndef SKB_A_PIECE_K
+#define SKB_A_PIECE_K 128    // measured: 128 K-columns (32 KB) beats 64 and 32 (profiles/r02x_score_issue_bound.txt)
+#endif
+    static constexpr int kAPieceK = SKB_A_PIECE_K;
+    __host__ __device__ static size_t a_bytes(int Dp) {
+        return STREAM_A ? 0 : (kATmem ? (size_t)128 * kAPieceK * 2 : (size_t)MT * kParts * 128 * Dp * 2);
+    }
     static size_t total(int Dp) { return 256 + a_bytes(Dp) + (size_t)kBStages * kRingStageBytes + kEpiWarps * 32 * kStageRowBytes; }
 };
 
@@ -321,7 +332,17 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
             uint32_t b_ph = 1, a_ph = 1;
             bool new_panel = true;
             for (int t = t_begin; t < t_end; ++t) {
-                if (!STREAM_A && new_panel) {
+                if (SM::kATmem && new_panel) {
+                    // piece by piece through the staging buffer (the MMA lane copies each piece on into tensor memory)
+                    for (int part = 0; part < SM::kParts; ++part)
+                        for (int k0 = 0; k0 < p.Dp; k0 += SM::kAPieceK) {
+                            mbar_wait(a_empty, a_ph);
+                            a_ph ^= 1;
+                            const uint32_t bytes = (uint32_t)min(SM::kAPieceK, p.Dp - k0) * 256u;       // 128 rows x 2 bytes per K column
+                            mbar_arrive_expect_tx(a_full, bytes);
+                            bulk_g2s(a_smem, (part == 0 ? p.Ehi : p.Elo) + (size_t)panel * p.Dp * 128 + (size_t)k0 * 128, bytes, a_full);
+                        }
+                } else if (!STREAM_A && new_panel) {
                     mbar_wait(a_empty, a_ph);
                     a_ph ^= 1;
                     const int n_pan = min(MT, n_panels - panel * MT);
@@ -380,19 +401,23 @@ __device__ __forceinline__ void score_gemm_body(const ScoreParams& p) {
         bool new_panel = true;
         SKB_T0();
         for (int t = t_begin; t < t_end; ++t, ++nt_done) {
-            if (!STREAM_A && new_panel) {
+            if (SM::kATmem && new_panel) {
+                // the panel moves on into tensor memory piece by piece (behind the MMAs of the previous panel, which execute
+                // first: one in-order pipe); the staging buffer is free again as soon as a piece's copies are done
+                for (int part = 0; part < SM::kParts; ++part)
+                    for (int k0 = 0; k0 < p.Dp; k0 += SM::kAPieceK) {
+                        SKB_TIMED_WAIT(3, mbar_wait(a_full, a_ph));
+                        a_ph ^= 1;
+                        tc_fence_after();
+                        const int n_ks = min(SM::kAPieceK, p.Dp - k0) / 16;
+                        for (int ks = 0; ks < n_ks; ++ks)
+                            tmem_cp_128x256b(tmem_base + SM::kAccCols + part * 128 + (k0 / 16 + ks) * 8,
+                                             desc_hi | (((smem_u32(a_smem) + ks * 2 * 2048) >> 4) & 0x3FFF));
+                        umma_commit(a_empty);
+                    }
+            } else if (!STREAM_A && new_panel) {
                 SKB_TIMED_WAIT(3, mbar_wait(a_full, a_ph));
                 a_ph ^= 1;
-                if (SM::kATmem) {
-                    // the panel moves on into tensor memory (behind the MMAs of the previous panel, which execute first: one
-                    // in-order pipe); its shared-memory image is free as soon as the copies are done
-                    tc_fence_after();
-                    for (int part = 0; part < SM::kParts; ++part)
-                        for (int ks = 0; ks < p.Dp / 16; ++ks)
-                            tmem_cp_128x256b(tmem_base + SM::kAccCols + part * 128 + ks * 8,
-                                             desc_hi | (((smem_u32(a_smem) + part * a_part + ks * 2 * 2048) >> 4) & 0x3FFF));
-                    umma_commit(a_empty);
-                }
             }
             const int n_pan = min(MT, n_panels - group * MT);
             const int buf = (int)(nt_done & 1);
@@ -854,14 +879,24 @@ static int launch_score_auto_kc(const ScoreParams& p, cudaStream_t st) {
     return SKB_OK;
 }
 
-// 128-wide ring stages whenever the padded K allows it (see ScoreSmem)
+// The widest ring stage the padded K allows (see ScoreSmem): the whole K = 256 of an x-vector in ONE stage (one commit per
+// tile), else 128- or 64-wide stages.  SKB_SCORE_KC=64|128|256 caps the width (A/B knob).
+static int stage_width(const ScoreParams& p) {
+    static const int cap = getenv("SKB_SCORE_KC") ? atoi(getenv("SKB_SCORE_KC")) : 128;
+    if (p.Dp == 256 && cap >= 256) return 256;
+    if (p.Dp % 128 == 0 && cap >= 128) return 128;
+    return 64;
+}
 template <bool TRIALS>
 static int launch_score_auto(const ScoreParams& p, cudaStream_t st) {
-    return p.Dp % 128 == 0 ? launch_score_auto_kc<TRIALS, 128>(p, st) : launch_score_auto_kc<TRIALS, 64>(p, st);
+    const int kc = stage_width(p);
+    return kc == 256 ? launch_score_auto_kc<TRIALS, 256>(p, st) : (kc == 128 ? launch_score_auto_kc<TRIALS, 128>(p, st) : launch_score_auto_kc<TRIALS, 64>(p, st));
 }
 template <bool TRIALS>
 static int launch_score_single_pass(const ScoreParams& p, int grid, cudaStream_t st) {
-    return p.Dp % 128 == 0 ? launch_score<1, false, TRIALS, 1, 128>(p, grid, st) : launch_score<1, false, TRIALS, 1, 64>(p, grid, st);
+    const int kc = stage_width(p);
+    return kc == 256 ? launch_score<1, false, TRIALS, 1, 256>(p, grid, st)
+                     : (kc == 128 ? launch_score<1, false, TRIALS, 1, 128>(p, grid, st) : launch_score<1, false, TRIALS, 1, 64>(p, grid, st));
 }
 
 // out = acc * (ra_i + ca_j + a0) + rq_scale * (r_i + q_j) + c0 on two packed operands

@@ -23,7 +23,8 @@ with torch.no_grad():
         model.extract_packed(flats[k], blens[k])
     torch.cuda.synchronize()
     print("bucket  utts  audio-s  GMAC   ms/step   front-end  stem   conv    SE   pool+head")
-    for k in range(K):
+    only = [int(v) for v in os.environ.get('SKB_PROBE_BUCKETS', '').split(',') if v] or list(range(K))
+    for k in only:
         f = lambda i: model.extract_packed(flats[k], blens[k])
         for i in range(2):
             f(i)

@@ -393,8 +393,10 @@ def run_ours(args):
             step_events.append(ev)
         return bulk.gather_embeddings(local_emb, shards, 256, device)          # the one collective of the path
 
+    # ONE sampler per job (rank 0's GPU): every nvidia-smi poll takes the driver lock, and eight of them at 10 Hz beside eight
+    # ranks are a perturbation of their own
     sampler = ClockSampler(local)
-    if not args.no_clock_sampler:
+    if not args.no_clock_sampler and rank == 0:
         sampler.start()
     with torch.no_grad():
         # the bulk run's batch budget is known up front (what bulk.make_batches is given): every work buffer and plan-cache
@@ -408,8 +410,16 @@ def run_ours(args):
         # nvidia-smi must be UP before the timed region (its start-up holds the driver lock for tens of milliseconds: 9.3 instead
         # of 8.5 ms per step when it lands inside), and the GPU must not idle while we wait for it (the clocks would drop):
         # keep running warm-up batches until the sampler has delivered its first rows
+        # (all ranks keep their GPUs busy until rank 0's sampler is up)
         t_wait = time.perf_counter()
-        while sampler.proc is not None and len(sampler.rows) < 2 and time.perf_counter() - t_wait < 5.0:
+        while True:
+            ready = 0 if (sampler.proc is not None and len(sampler.rows) < 2 and time.perf_counter() - t_wait < 5.0) else 1
+            if dist_on:
+                flag = torch.tensor([ready], device=device, dtype=torch.int32)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                ready = int(flag.item())
+            if ready:
+                break
             wls = [int(wl[i]) for i in wb[0]]
             model.extract_packed(device_audio(wls, 5, device), wls)
             torch.cuda.synchronize()
